@@ -1,0 +1,224 @@
+/*
+ * swinvox_b200.h -- C-ABI of libswinvox_b200.so (sm_100a).
+ *
+ * The reference (SwinVox) has no FFI of its own: its boundary for the hot path is the
+ * Python nn.Module API of models/{encoder,swin_transformer,cross_view_attention,decoder,
+ * merger,refiner}.py plus the metric loop core/test.py:141-164.  The Python shells in
+ * swinvox_b200/models/*.py keep that API and drive this library through ctypes.  Each
+ * entry point below cites the reference operation it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ *     (PyTorch).  The library allocates nothing persistent besides the plan object itself.
+ *   - all activations are fp32, channels-last ([N,H,W,C] / [N,D,H,W,C]); contractions run on
+ *     tcgen05 kind::tf32 with fp32 accumulation in TMEM.
+ *   - every function returns 0 on success, non-zero on failure; svx_last_error() returns a
+ *     thread-local message.  No exceptions cross the ABI.
+ *   - launches are stream ordered on the cudaStream_t passed as `void* stream`.
+ */
+#ifndef SWINVOX_B200_H
+#define SWINVOX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVX_ABI_VERSION 1
+
+/* activation codes for svx_gemm_desc.act */
+enum { SVX_ACT_NONE = 0, SVX_ACT_RELU = 1, SVX_ACT_LEAKY = 2, SVX_ACT_GELU = 3 };
+/* A operand modes */
+enum { SVX_A_PLAIN = 0, SVX_A_GATHER = 1 };
+/* special epilogues */
+enum { SVX_EPI_STD = 0, SVX_EPI_DEC_TAIL = 1 /* decoder layer4+layer5+cat, decoder.py:80-89 */ };
+/* pooling modes */
+enum { SVX_POOL_MAX = 0, SVX_POOL_AVG = 1 };
+
+/*
+ * One tensor-core contraction  out[r, j] = act( sum_k A[r,k] * W[j,k] + bias[j] ) (+ residual[r,j])
+ * Replaces every nn.Linear / nn.Conv2d / nn.Conv3d / nn.ConvTranspose3d of the reference
+ * (encoder.py:22-111, timm Swin linears, cross_view_attention.py:38-53, decoder.py:24-46,
+ * merger.py:20-54, refiner.py:21-70) with BatchNorm (eval) folded into W/bias by the host.
+ *
+ * A operand:
+ *   SVX_A_PLAIN : row-major [M, K] with row stride lda (elements), streamed by TMA.
+ *   SVX_A_GATHER: implicit im2col.  Row r decodes to (n, od, oh, ow) over out_{D,H,W};
+ *                 k = tap*Cin + c; the element read is
+ *                   in[n, od*stride_d + taps[tap].d, oh*stride_h + taps[tap].h,
+ *                         ow*stride_w + taps[tap].w, in_c0 + c]
+ *                 of a channels-last tensor with pixel stride in_Cs, zero outside the tensor.
+ *                 Cin, in_c0, in_Cs must be multiples of 4 (16-byte cp.async chunks).
+ * W: [Npad, Kpad] fp32, K contiguous, zero padded, values pre-rounded to TF32 (rna) by the host.
+ * result = out_scale * (res_after_act ? act(acc+bias) + res : act(acc+bias+res)).
+ * Output row r is stored at out + o_base + n*o_sn + od*o_sd + oh*o_sh + ow*o_sw (elements),
+ * columns contiguous.  `residual` uses the same mapping.
+ */
+typedef struct svx_gemm_desc {
+  int32_t M, N, K;          /* logical sizes; N columns are written */
+  int32_t Kpad, Npad;       /* padded weight extents (Kpad % 32 == 0, Npad % block_n == 0) */
+  int32_t block_n;          /* N tile: 16, 32, 64, 96, 128, 192 or 256 */
+  int32_t a_mode;
+  const float* A;
+  int64_t lda;
+  /* gather description */
+  int32_t in_D, in_H, in_W, in_Cs, in_c0, Cin;
+  int32_t out_D, out_H, out_W;
+  int32_t stride_d, stride_h, stride_w;
+  int32_t ntaps;
+  const int32_t* taps;      /* device int32[ntaps][4] = {dd, dh, dw, 0} */
+  /* weights / epilogue */
+  const float* W;
+  const float* bias;        /* [Npad] or NULL */
+  const float* residual;    /* or NULL */
+  float* out;
+  int64_t o_base, o_sn, o_sd, o_sh, o_sw;
+  int32_t act;
+  float act_param;          /* LeakyReLU slope */
+  int32_t res_after_act;    /* 0: act(acc+bias+res) (ResNet); 1: act(acc+bias)+res (Swin, refiner skips) */
+  float out_scale;          /* applied last (refiner.py:103 uses 0.5); 1.0 otherwise */
+  int32_t round_tf32;       /* round the stored result to TF32 (it feeds another contraction) */
+  int32_t epi_mode;
+  const float* epi_aux;     /* SVX_EPI_DEC_TAIL: layer5 weights w5[8] */
+  float* epi_out2;          /* SVX_EPI_DEC_TAIL: planar coarse volume [n, OD*OH*OW] */
+  int64_t o2_base, o2_sn, o2_sd, o2_sh, o2_sw;
+} svx_gemm_desc;
+
+/* Explicit im2col for tiny channel counts (ResNet stem 7x7 s2 on 3 channels, Swin patch-embed
+ * 4x4 s4, refiner layer1 4x4x4 on 1 channel).  Input addressed with arbitrary element strides
+ * so NCHW user tensors are read in place.  Row r=(n,od,oh,ow); k=((kd*KH+kh)*KW+kw)*C+c. */
+typedef struct svx_im2col_desc {
+  const float* in; float* out;
+  int32_t N, C, D, H, W;
+  int64_t s_n, s_c, s_d, s_h, s_w;
+  int32_t KD, KH, KW, stride, pad_d, pad_h, pad_w;
+  int32_t OD, OH, OW, Kpad;
+  int32_t round_tf32;
+} svx_im2col_desc;
+
+/* Channels-last pooling (resnet maxpool, encoder.py:123 avg_pool2d, decoder.py:59-67 adaptive
+ * pool + depth replicate, refiner.py MaxPool3d).  Output (od,oh,ow) reduces the window starting
+ * at (od*sd - pd, ...) of extent (kd,kh,kw); out-of-range taps are skipped (max) / not counted. */
+typedef struct svx_pool_desc {
+  const float* in; float* out;
+  int32_t N, C, D, H, W, in_Cs, out_Cs;
+  int32_t KD, KH, KW, SD, SH, SW, PD, PH, PW, OD, OH, OW;
+  int32_t mode, round_tf32;
+} svx_pool_desc;
+
+/* Row LayerNorm over C channels (timm norm1/norm2/patch_embed.norm/downsample.norm), eps 1e-5.
+ * merge=1 gathers the PatchMerging 2x2 neighbourhood: in is [N,H,W,C/4], row (n,y,x) over
+ * (H/2,W/2) concatenates (2y,2x),(2y+1,2x),(2y,2x+1),(2y+1,2x+1). */
+typedef struct svx_lnrows_desc {
+  const float* in; float* out; const float* gamma; const float* beta;
+  int32_t rows, C; int32_t merge, H, W; float eps; int32_t round_tf32;
+} svx_lnrows_desc;
+
+/* nn.LayerNorm([C,H,W]) of the Swin wrapper (swin_transformer.py:64-67,84-86): statistics over
+ * all L=C*H*W values of one sample, affine laid out like the data ([H,W,C]). */
+typedef struct svx_lnsample_desc {
+  const float* in; float* out; const float* gamma; const float* beta;
+  int32_t N, L; float eps; int32_t round_tf32;
+} svx_lnsample_desc;
+
+/* W-MSA / SW-MSA (timm WindowAttention + roll/partition/reverse).  qkv is [N*H*W, 3C] in token
+ * order, columns (which, head, d); out is [N*H*W, C].  bias is the expanded relative-position
+ * bias [heads, 49, 49].  The cyclic shift and the -100 region mask are applied by indexing. */
+typedef struct svx_winattn_desc {
+  const float* qkv; float* out; const float* bias;
+  int32_t N, H, W, C, heads, shift; float scale; int32_t round_tf32;
+} svx_winattn_desc;
+
+/* depthwise k=s conv without padding (cross_view_attention.py:26-34), channels-last */
+typedef struct svx_dwconv_desc {
+  const float* in; float* out; const float* w /* [k*k, C] */; const float* bias;
+  int32_t N, H, W, C, k, OH, OW; int32_t round_tf32;
+} svx_dwconv_desc;
+
+/* attention over the view axis (cross_view_attention.py:81-103). qkv: [B*V, P, 3*R] channels-last
+ * (P = h*w positions, R = reduced channels); out: [B*V, P, R]. */
+typedef struct svx_viewattn_desc {
+  const float* qkv; float* out;
+  int32_t B, V, P, R, heads; float scale; int32_t round_tf32;
+} svx_viewattn_desc;
+
+/* out = bilinear_resize(in, align_corners=False) + skip  (cross_view_attention.py:110-120) */
+typedef struct svx_bilinear_desc {
+  const float* in; const float* skip; float* out;
+  int32_t N, IH, IW, OH, OW, C; int32_t round_tf32;
+} svx_bilinear_desc;
+
+/* per-voxel softmax over views + weighted sum (merger.py:98-104).
+ * weights, coarse: [B, V, P]; out: [B, P]. */
+typedef struct svx_mergefuse_desc {
+  const float* weights; const float* coarse; float* out;
+  int32_t B, V, P;
+} svx_mergefuse_desc;
+
+/* sigmoid -> threshold -> I/U/TP/FP/FN per object (core/test.py:141-164).
+ * logits, gt: [B, P] (gt holds {0,1}); prob_thresholds: device float[T] (cfg.TEST.VOXEL_THRESH);
+ * counts: int32[B, T, 5] = {I,U,TP,FP,FN}, zeroed by the launch itself (cudaMemsetAsync). */
+typedef struct svx_metrics_desc {
+  const float* logits; const float* gt; const float* prob_thresholds; int32_t* counts;
+  int32_t B, P, T;
+} svx_metrics_desc;
+
+/* layout change [N, C, P] (planar) <-> [N, P, Cs] (channels-last, first C of Cs channels) */
+typedef struct svx_transpose_desc {
+  const float* in; float* out;
+  int32_t N, C, P, Cs; int32_t to_channels_last; int32_t round_tf32;
+} svx_transpose_desc;
+
+/* ---- library ------------------------------------------------------------------------ */
+int svx_abi_version(void);
+const char* svx_last_error(void);
+/* sizeof() of every descriptor, so the Python mirror can verify its struct layout */
+int svx_desc_sizes(int32_t* sizes, int n);
+int svx_device_info(int device, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---- immediate launches (one op on `stream`) ----------------------------------------- */
+int svx_gemm(const svx_gemm_desc*, void* stream);
+int svx_im2col(const svx_im2col_desc*, void* stream);
+int svx_pool(const svx_pool_desc*, void* stream);
+int svx_layernorm_rows(const svx_lnrows_desc*, void* stream);
+int svx_layernorm_sample(const svx_lnsample_desc*, void* stream);
+int svx_window_attention(const svx_winattn_desc*, void* stream);
+int svx_dwconv(const svx_dwconv_desc*, void* stream);
+int svx_view_attention(const svx_viewattn_desc*, void* stream);
+int svx_bilinear_add(const svx_bilinear_desc*, void* stream);
+int svx_merger_fuse(const svx_mergefuse_desc*, void* stream);
+int svx_voxel_metrics(const svx_metrics_desc*, void* stream);
+int svx_transpose(const svx_transpose_desc*, void* stream);
+
+/* ---- plans: a recorded op list replayed per forward (one per module instance/shape) --- */
+typedef struct svx_plan svx_plan;
+svx_plan* svx_plan_create(void);
+void svx_plan_destroy(svx_plan*);
+int svx_plan_num_ops(const svx_plan*);
+int svx_plan_add_gemm(svx_plan*, const svx_gemm_desc*);
+int svx_plan_add_im2col(svx_plan*, const svx_im2col_desc*);
+int svx_plan_add_pool(svx_plan*, const svx_pool_desc*);
+int svx_plan_add_layernorm_rows(svx_plan*, const svx_lnrows_desc*);
+int svx_plan_add_layernorm_sample(svx_plan*, const svx_lnsample_desc*);
+int svx_plan_add_window_attention(svx_plan*, const svx_winattn_desc*);
+int svx_plan_add_dwconv(svx_plan*, const svx_dwconv_desc*);
+int svx_plan_add_view_attention(svx_plan*, const svx_viewattn_desc*);
+int svx_plan_add_bilinear_add(svx_plan*, const svx_bilinear_desc*);
+int svx_plan_add_merger_fuse(svx_plan*, const svx_mergefuse_desc*);
+int svx_plan_add_voxel_metrics(svx_plan*, const svx_metrics_desc*);
+int svx_plan_add_transpose(svx_plan*, const svx_transpose_desc*);
+/* run every op in order on `stream`; use_graph != 0 replays a CUDA graph captured on first use */
+int svx_plan_run(svx_plan*, void* stream, int use_graph);
+/* run ops [first, last) only (profiling / bisecting) */
+int svx_plan_run_range(svx_plan*, int first, int last, void* stream);
+/* device time of each op (CUDA events on `stream`, mean of `iters` launches); ms has num_ops entries */
+int svx_plan_time_ops(svx_plan*, void* stream, int iters, float* ms);
+/* number of kernel launches one svx_plan_run issues */
+int svx_plan_num_launches(const svx_plan*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWINVOX_B200_H */

@@ -1,0 +1,485 @@
+// svx_gemm.cu -- the contraction engine of the SwinVox forward path on sm_100a.
+//
+// One warp-specialised kernel serves every Linear / Conv2d / Conv3d / ConvTranspose3d of the
+// reference (encoder.py:22-111, timm Swin linears, cross_view_attention.py:38-53,
+// decoder.py:24-46, merger.py:20-54, refiner.py:21-70):
+//
+//   warp 0-3  epilogue   TMEM -> registers (tcgen05.ld) -> bias / residual / activation -> global
+//   warp 4    TMA        weights (and the A operand when it is a plain matrix) -> 128B-swizzled smem
+//   warp 5    MMA        one elected thread issues tcgen05.mma kind::tf32, accumulating in TMEM
+//   warp 6-9  gather     implicit im2col: cp.async 16-byte chunks of channels-last pixels, written
+//                        with the same 128B swizzle TMA would produce, zero-filled at the borders
+//
+// Tile: 128 (rows = output pixels) x BN (output channels) x 32 (fp32 k-chunk = one swizzle row).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "svx_internal.h"
+#include "svx_ptx.cuh"
+
+namespace svx {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;
+constexpr int UMMA_K = 8;
+constexpr int A_STAGE_BYTES = BM * BK * 4;
+constexpr int kThreads = 320;
+constexpr int kGatherLag = 2;
+
+struct GemmParams {
+  int M, N, K, nk, tiles_n, a_mode;
+  const float* A;
+  int in_D, in_H, in_W, in_Cs, in_c0, Cin;
+  int out_D, out_H, out_W;
+  int sd, sh, sw;
+  const int4* taps;
+  const float* bias;
+  const float* residual;
+  float* out;
+  long long o_base, o_sn, o_sd, o_sh, o_sw;
+  int act;
+  float act_param;
+  int res_after_act;
+  float out_scale;
+  int round_tf32, epi_mode;
+  const float* epi_aux;
+  float* out2;
+  long long o2_base, o2_sn, o2_sd, o2_sh, o2_sw;
+  int vec_ok;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = (BN > 64 && BN <= 128) ? 3 : 4;
+  static constexpr int kBBytes = BN * BK * 4;
+  static constexpr int kStageBytes = A_STAGE_BYTES + kBBytes;
+  static constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int kMinBlocks = (BN <= 128) ? 2 : 1;
+  // stages + 1024 alignment slack + barriers/tmem slot (256) + bias
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + BN * 4;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act, float slope) {
+  switch (act) {
+    case SVX_ACT_RELU: return fmaxf(x, 0.f);
+    case SVX_ACT_LEAKY: return x > 0.f ? x : x * slope;
+    case SVX_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    default: return x;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, Cfg<BN>::kMinBlocks)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const GemmParams p) {
+  using C = Cfg<BN>;
+  constexpr int S = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + S * C::kStageBytes;
+  // barrier layout: full[S], empty[S], tmem_full, then tmem slot, then bias
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * S);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 1);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + S * C::kStageBytes + 8 * (2 * S + 1));
+  float* sbias = reinterpret_cast<float*>(smem_gen + S * C::kStageBytes + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x % p.tiles_n;
+  const int tile_m = blockIdx.x / p.tiles_n;
+  const int m0 = tile_m * BM;
+  const int n0 = tile_n * BN;
+  const int nk = p.nk;
+  const bool gather = p.a_mode == SVX_A_GATHER;
+
+  // ---- one-time setup ---------------------------------------------------------------------
+  if (warp == 4 && lane == 0) {
+    if (!gather) tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 5) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(full_bar(s), gather ? 5u : 1u);
+        mbar_init(empty_bar(s), 1u);
+      }
+      mbar_init(tmem_full_bar, 1u);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<C::kTmemCols>(tmem_slot);
+  }
+  if (warp < 4) {
+    for (int j = threadIdx.x; j < BN; j += 128) sbias[j] = p.bias ? p.bias[n0 + j] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 4) {
+    // ---- TMA producer ---------------------------------------------------------------------
+    if (lane == 0) {
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % S;
+        const uint32_t ph = (kc / S) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t a_dst = smem_base + s * C::kStageBytes;
+        const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+        if (!gather) {
+          mbar_arrive_expect_tx(full_bar(s), A_STAGE_BYTES + C::kBBytes);
+          tma_load_2d(a_dst, &map_a, full_bar(s), kc * BK, m0);
+        } else {
+          mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
+        }
+        tma_load_2d(b_dst, &map_b, full_bar(s), kc * BK, n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ---- MMA issuer -----------------------------------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % S;
+        const uint32_t ph = (kc / S) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + s * C::kStageBytes;
+        const uint64_t da = umma_desc_sw128(a_addr);
+        const uint64_t db = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advance 8 fp32 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+          umma_tf32(tmem_base, da + 2u * k, db + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  } else if (warp >= 6) {
+    // ---- A gather producers (implicit im2col) ---------------------------------------------
+    if (gather) {
+      const int gw = warp - 6;
+      const int j = lane & 7;      // 16-byte chunk inside the 128-byte k-row
+      const int rsub = lane >> 3;  // row inside a group of 4
+      long long base[8];
+      int crd[8];  // zd | zh<<10 | zw<<20 | valid<<30
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = m0 + gw * 32 + i * 4 + rsub;
+        if (r < p.M) {
+          const int ow = r % p.out_W;
+          int t = r / p.out_W;
+          const int oh = t % p.out_H;
+          t /= p.out_H;
+          const int od = t % p.out_D;
+          const int n = t / p.out_D;
+          const int zd = od * p.sd, zh = oh * p.sh, zw = ow * p.sw;
+          base[i] = ((((long long)n * p.in_D + zd) * p.in_H + zh) * p.in_W + zw) * p.in_Cs;
+          crd[i] = zd | (zh << 10) | (zw << 20) | (1 << 30);
+        } else {
+          base[i] = 0;
+          crd[i] = 0;
+        }
+      }
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % S;
+        const uint32_t ph = (kc / S) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const int k4 = kc * BK + j * 4;
+        const bool kv = k4 < p.K;
+        int dd = 0, dh = 0, dw = 0, delta = 0;
+        if (kv) {
+          const int tap = k4 / p.Cin;
+          const int c = k4 - tap * p.Cin;
+          const int4 t = __ldg(p.taps + tap);
+          dd = t.x; dh = t.y; dw = t.z;
+          delta = ((dd * p.in_H + dh) * p.in_W + dw) * p.in_Cs + p.in_c0 + c;
+        }
+        const uint32_t a_dst = smem_base + s * C::kStageBytes;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = gw * 32 + i * 4 + rsub;
+          const int id = (crd[i] & 1023) + dd;
+          const int ih = ((crd[i] >> 10) & 1023) + dh;
+          const int iw = ((crd[i] >> 20) & 1023) + dw;
+          const bool ok = kv && (crd[i] >> 30) && (unsigned)id < (unsigned)p.in_D &&
+                          (unsigned)ih < (unsigned)p.in_H && (unsigned)iw < (unsigned)p.in_W;
+          const float* src = ok ? (p.A + base[i] + delta) : p.A;
+          const uint32_t dst = a_dst + row * 128 + ((j ^ (row & 7)) << 4);
+          cp_async16_zfill(dst, src, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        if (kc >= kGatherLag) {
+          cp_async_wait<kGatherLag>();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar((kc - kGatherLag) % S));
+        }
+      }
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        for (int kc = (nk > kGatherLag ? nk - kGatherLag : 0); kc < nk; ++kc) mbar_arrive(full_bar(kc % S));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue (warps 0-3; warp w owns TMEM lanes 32w..32w+31) ----------------------------
+    mbar_wait(tmem_full_bar, 0u);
+    tc_fence_after();
+    const int r = m0 + warp * 32 + lane;
+    const bool valid = r < p.M;
+    long long off = 0, off2 = 0;
+    if (valid) {
+      const int ow = r % p.out_W;
+      int t = r / p.out_W;
+      const int oh = t % p.out_H;
+      t /= p.out_H;
+      const int od = t % p.out_D;
+      const int n = t / p.out_D;
+      off = p.o_base + n * p.o_sn + od * p.o_sd + oh * p.o_sh + ow * p.o_sw;
+      off2 = p.o2_base + n * p.o2_sn + od * p.o2_sd + oh * p.o2_sh + ow * p.o2_sw;
+    }
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      const int jb = n0 + c0;
+      if (jb >= p.N) break;  // warp-uniform
+      uint32_t v[16];
+      __syncwarp();
+      tmem_ld16(lane_addr + c0, v);
+      tmem_ld_wait();
+      if (valid) {
+      float x[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) x[q] = __uint_as_float(v[q]) + sbias[c0 + q];
+      if (p.epi_mode == SVX_EPI_DEC_TAIL) {
+        // decoder.py:80-89: raw = cat(relu(bn(layer4)), layer5(.)) ; coarse = layer5(.)
+        float g = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          x[q] = fmaxf(x[q], 0.f);
+          g = fmaf(__ldg(p.epi_aux + q), x[q], g);
+        }
+        x[8] = g;
+#pragma unroll
+        for (int q = 9; q < 16; ++q) x[q] = 0.f;
+        p.out2[off2] = g;
+      } else {
+        const float* res = p.residual ? p.residual + off + jb : nullptr;
+        float rv[16];
+        if (res) {
+          if (p.vec_ok) {
+#pragma unroll
+            for (int q = 0; q < 16; q += 4) {
+              if (jb + q < p.N) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(res + q));
+                rv[q] = t4.x; rv[q + 1] = t4.y; rv[q + 2] = t4.z; rv[q + 3] = t4.w;
+              } else {
+                rv[q] = rv[q + 1] = rv[q + 2] = rv[q + 3] = 0.f;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) rv[q] = (jb + q < p.N) ? __ldg(res + q) : 0.f;
+          }
+          if (!p.res_after_act) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) x[q] += rv[q];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) x[q] = apply_act(x[q], p.act, p.act_param);
+        if (res && p.res_after_act) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) x[q] += rv[q];
+        }
+        if (p.out_scale != 1.f) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) x[q] *= p.out_scale;
+        }
+      }
+      if (p.round_tf32) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) x[q] = round_tf32(x[q]);
+      }
+      float* dst = p.out + off + jb;
+      if (p.vec_ok) {
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+          if (jb + q < p.N)
+            *reinterpret_cast<float4*>(dst + q) = make_float4(x[q], x[q + 1], x[q + 2], x[q + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          if (jb + q < p.N) dst[q] = x[q];
+        }
+      }
+      }  // valid
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row pitch `pitch_elems`; box = box_rows x 32 columns, 128B swizzle
+int encode_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+               uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_elems * 4};
+  cuuint32_t box[2] = {BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+template <int BN>
+int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    SVX_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg<BN>::kSmemBytes));
+    configured = true;
+  }
+  gemm_tf32_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ma, mb, p);
+  SVX_LAUNCH_OK("gemm_tf32_kernel");
+  return 0;
+}
+
+}  // namespace
+
+struct GemmPrepared {
+  CUtensorMap map_a, map_b;
+  GemmParams p;
+  int bn, grid;
+};
+
+int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
+  *out = nullptr;
+  SVX_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "gemm: empty problem M=%d N=%d K=%d", d.M, d.N, d.K);
+  SVX_REQUIRE(d.block_n == 16 || d.block_n == 32 || d.block_n == 64 || d.block_n == 96 || d.block_n == 128 ||
+                  d.block_n == 192 || d.block_n == 256,
+              "gemm: block_n=%d unsupported", d.block_n);
+  SVX_REQUIRE(d.Kpad % BK == 0 && d.Kpad >= d.K, "gemm: Kpad=%d must be a multiple of 32 and >= K=%d", d.Kpad, d.K);
+  SVX_REQUIRE(d.Npad % d.block_n == 0 && d.Npad >= d.N, "gemm: Npad=%d vs N=%d block_n=%d", d.Npad, d.N, d.block_n);
+  SVX_REQUIRE(d.A && d.W && d.out, "gemm: null operand");
+  SVX_REQUIRE((reinterpret_cast<uintptr_t>(d.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.W) & 15) == 0,
+              "gemm: A and W must be 16-byte aligned");
+  SVX_REQUIRE(d.out_D > 0 && d.out_H > 0 && d.out_W > 0, "gemm: row decode extents must be positive");
+  GemmPrepared* g = new GemmPrepared();
+  GemmParams& p = g->p;
+  memset(&p, 0, sizeof(p));
+  if (d.a_mode == SVX_A_PLAIN) {
+    if (d.lda % 4 != 0 || d.lda < d.K) {
+      delete g;
+      return fail("gemm: plain A needs lda %% 4 == 0 and lda >= K (lda=%lld K=%d)", (long long)d.lda, d.K);
+    }
+    if (encode_map(&g->map_a, d.A, (uint64_t)d.M, (uint64_t)d.K, (uint64_t)d.lda, BM)) { delete g; return 1; }
+  } else if (d.a_mode == SVX_A_GATHER) {
+    bool ok = d.Cin > 0 && d.Cin % 4 == 0 && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.ntaps > 0 && d.taps &&
+              d.K == d.ntaps * d.Cin && d.in_D > 0 && d.in_H > 0 && d.in_W > 0 && d.in_D < 1024 &&
+              d.in_H < 1024 && d.in_W < 1024;
+    if (!ok) {
+      delete g;
+      return fail("gemm: bad gather description (Cin=%d c0=%d Cs=%d ntaps=%d K=%d)", d.Cin, d.in_c0, d.in_Cs,
+                  d.ntaps, d.K);
+    }
+    memset(&g->map_a, 0, sizeof(g->map_a));
+  } else {
+    delete g;
+    return fail("gemm: unknown a_mode %d", d.a_mode);
+  }
+  if (encode_map(&g->map_b, d.W, (uint64_t)d.Npad, (uint64_t)d.Kpad, (uint64_t)d.Kpad, (uint32_t)d.block_n)) {
+    delete g;
+    return 1;
+  }
+  if (d.epi_mode == SVX_EPI_DEC_TAIL &&
+      !(d.block_n == 16 && d.N == 16 && d.epi_aux && d.epi_out2)) {
+    delete g;
+    return fail("gemm: decoder tail epilogue needs block_n=16, N=16, aux weights and a coarse output");
+  }
+  p.M = d.M; p.N = d.N; p.K = d.K; p.nk = d.Kpad / BK; p.tiles_n = d.Npad / d.block_n; p.a_mode = d.a_mode;
+  p.A = d.A;
+  p.in_D = d.in_D; p.in_H = d.in_H; p.in_W = d.in_W; p.in_Cs = d.in_Cs; p.in_c0 = d.in_c0; p.Cin = d.Cin;
+  p.out_D = d.out_D; p.out_H = d.out_H; p.out_W = d.out_W;
+  p.sd = d.stride_d; p.sh = d.stride_h; p.sw = d.stride_w;
+  p.taps = reinterpret_cast<const int4*>(d.taps);
+  p.bias = d.bias; p.residual = d.residual; p.out = d.out;
+  p.o_base = d.o_base; p.o_sn = d.o_sn; p.o_sd = d.o_sd; p.o_sh = d.o_sh; p.o_sw = d.o_sw;
+  p.act = d.act; p.act_param = d.act_param; p.res_after_act = d.res_after_act;
+  p.out_scale = d.out_scale; p.round_tf32 = d.round_tf32; p.epi_mode = d.epi_mode;
+  p.epi_aux = d.epi_aux; p.out2 = d.epi_out2;
+  p.o2_base = d.o2_base; p.o2_sn = d.o2_sn; p.o2_sd = d.o2_sd; p.o2_sh = d.o2_sh; p.o2_sw = d.o2_sw;
+  auto al4 = [](long long v) { return (v & 3) == 0; };
+  p.vec_ok = (d.N % 4 == 0) && al4(d.o_base) && al4(d.o_sn) && al4(d.o_sd) && al4(d.o_sh) && al4(d.o_sw) &&
+             (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
+             (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0);
+  const long long tiles_m = (d.M + BM - 1) / BM;
+  const long long grid = tiles_m * p.tiles_n;
+  if (grid > 0x7fffffffLL) { delete g; return fail("gemm: grid too large"); }
+  g->bn = d.block_n;
+  g->grid = (int)grid;
+  *out = g;
+  return 0;
+}
+
+void gemm_prepared_free(GemmPrepared* p) { delete p; }
+
+int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void* stream) {
+  GemmPrepared* g = prepared;
+  if (!g) {
+    if (int rc = gemm_prepare(d, &g)) return rc;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = 0;
+  switch (g->bn) {
+    case 16: rc = launch_bn<16>(g->map_a, g->map_b, g->p, g->grid, st); break;
+    case 32: rc = launch_bn<32>(g->map_a, g->map_b, g->p, g->grid, st); break;
+    case 64: rc = launch_bn<64>(g->map_a, g->map_b, g->p, g->grid, st); break;
+    case 96: rc = launch_bn<96>(g->map_a, g->map_b, g->p, g->grid, st); break;
+    case 192: rc = launch_bn<192>(g->map_a, g->map_b, g->p, g->grid, st); break;
+    case 128: rc = launch_bn<128>(g->map_a, g->map_b, g->p, g->grid, st); break;
+    default: rc = launch_bn<256>(g->map_a, g->map_b, g->p, g->grid, st); break;
+  }
+  if (!prepared) delete g;
+  return rc;
+}
+
+int gemm_num_launches(const svx_gemm_desc&) { return 1; }
+
+}  // namespace svx

@@ -1,0 +1,616 @@
+// svx_ops.cu -- the bandwidth-bound and small CUDA-core stages of the SwinVox forward path:
+// im2col for tiny channel counts, pooling, LayerNorm (row-wise and whole-sample), shifted-window
+// attention, cross-view attention pieces, merger softmax-fuse, threshold/IoU counters, layout changes.
+#include <cuda_runtime.h>
+
+#include "svx_internal.h"
+#include "svx_ptx.cuh"
+
+namespace svx {
+namespace {
+
+constexpr int kSmCount = 148;
+
+__device__ __forceinline__ float maybe_round(float x, int r) { return r ? round_tf32(x) : x; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum for blockDim.x <= 1024; `red` is 32 floats of shared memory
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < nw) ? red[l] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+inline int grid_for(long long work, int block, int max_blocks = kSmCount * 32) {
+  long long g = (work + block - 1) / block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---- im2col (tiny C) -------------------------------------------------------------------------
+__global__ void im2col_kernel(const svx_im2col_desc d, long long total, int K) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % d.Kpad);
+    long long r = idx / d.Kpad;
+    float v = 0.f;
+    if (k < K) {
+      const int c = k % d.C;
+      int t = k / d.C;
+      const int kw = t % d.KW; t /= d.KW;
+      const int kh = t % d.KH;
+      const int kd = t / d.KH;
+      const int ow = (int)(r % d.OW); r /= d.OW;
+      const int oh = (int)(r % d.OH); r /= d.OH;
+      const int od = (int)(r % d.OD);
+      const long long n = r / d.OD;
+      const int id = od * d.stride - d.pad_d + kd;
+      const int ih = oh * d.stride - d.pad_h + kh;
+      const int iw = ow * d.stride - d.pad_w + kw;
+      if ((unsigned)id < (unsigned)d.D && (unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W)
+        v = __ldg(d.in + n * d.s_n + c * d.s_c + id * d.s_d + ih * d.s_h + iw * d.s_w);
+    }
+    d.out[idx] = maybe_round(v, d.round_tf32);
+  }
+}
+
+// ---- pooling ------------------------------------------------------------------------------------
+__global__ void pool_kernel(const svx_pool_desc d, long long total) {
+  const int c4n = d.C >> 2;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % c4n);
+    long long r = idx / c4n;
+    const int ow = (int)(r % d.OW); r /= d.OW;
+    const int oh = (int)(r % d.OH); r /= d.OH;
+    const int od = (int)(r % d.OD);
+    const long long n = r / d.OD;
+    float4 acc = d.mode == SVX_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = 0;
+    for (int kd = 0; kd < d.KD; ++kd) {
+      const int id = od * d.SD - d.PD + kd;
+      if ((unsigned)id >= (unsigned)d.D) continue;
+      for (int kh = 0; kh < d.KH; ++kh) {
+        const int ih = oh * d.SH - d.PH + kh;
+        if ((unsigned)ih >= (unsigned)d.H) continue;
+        for (int kw = 0; kw < d.KW; ++kw) {
+          const int iw = ow * d.SW - d.PW + kw;
+          if ((unsigned)iw >= (unsigned)d.W) continue;
+          const float4 v = __ldg(reinterpret_cast<const float4*>(
+              d.in + (((n * d.D + id) * d.H + ih) * d.W + iw) * (long long)d.in_Cs + c4 * 4));
+          if (d.mode == SVX_POOL_MAX) {
+            acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y);
+            acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
+          } else {
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+          ++cnt;
+        }
+      }
+    }
+    if (d.mode == SVX_POOL_AVG) {
+      const float inv = 1.f / (float)(cnt > 0 ? cnt : 1);
+      acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    }
+    acc.x = maybe_round(acc.x, d.round_tf32); acc.y = maybe_round(acc.y, d.round_tf32);
+    acc.z = maybe_round(acc.z, d.round_tf32); acc.w = maybe_round(acc.w, d.round_tf32);
+    *reinterpret_cast<float4*>(d.out + (((n * d.OD + od) * d.OH + oh) * d.OW + ow) * (long long)d.out_Cs + c4 * 4) = acc;
+  }
+}
+
+// ---- row LayerNorm: one warp per row ---------------------------------------------------------------
+__global__ void lnrows_kernel(const svx_lnrows_desc d) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int C = d.C;
+  const int Cq = C >> 2;  // merge: channels of one source pixel
+  const float invC = 1.f / (float)C;
+  for (long long row = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); row < d.rows;
+       row += (long long)gridDim.x * wpb) {
+    const float* src[4];
+    if (d.merge) {
+      const int W2 = d.W >> 1, H2 = d.H >> 1;
+      const int x = (int)(row % W2);
+      long long t = row / W2;
+      const int y = (int)(t % H2);
+      const long long n = t / H2;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int dy = s & 1, dx = s >> 1;  // timm order: (h0,w0) (h1,w0) (h0,w1) (h1,w1)
+        src[s] = d.in + ((n * d.H + 2 * y + dy) * d.W + 2 * x + dx) * (long long)Cq;
+      }
+    } else {
+      src[0] = d.in + row * (long long)C;
+      src[1] = src[2] = src[3] = src[0];
+    }
+    auto load4 = [&](int c) -> float4 {
+      if (d.merge) {
+        const int s = c / Cq;
+        return __ldg(reinterpret_cast<const float4*>(src[s] + (c - s * Cq)));
+      }
+      return __ldg(reinterpret_cast<const float4*>(src[0] + c));
+    };
+    float sum = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = load4(c);
+      sum += (v.x + v.y) + (v.z + v.w);
+    }
+    const float mean = warp_sum(sum) * invC;
+    float sq = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = load4(c);
+      const float a = v.x - mean, b = v.y - mean, e = v.z - mean, f = v.w - mean;
+      sq += (a * a + b * b) + (e * e + f * f);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * invC + d.eps);
+    float* dst = d.out + row * (long long)C;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = load4(c);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(d.gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(d.beta + c));
+      float4 o;
+      o.x = maybe_round((v.x - mean) * rstd * g.x + b.x, d.round_tf32);
+      o.y = maybe_round((v.y - mean) * rstd * g.y + b.y, d.round_tf32);
+      o.z = maybe_round((v.z - mean) * rstd * g.z + b.z, d.round_tf32);
+      o.w = maybe_round((v.w - mean) * rstd * g.w + b.w, d.round_tf32);
+      *reinterpret_cast<float4*>(dst + c) = o;
+    }
+  }
+}
+
+// ---- whole-sample LayerNorm: one CTA per sample ----------------------------------------------------
+__global__ void __launch_bounds__(1024) lnsample_kernel(const svx_lnsample_desc d) {
+  __shared__ float red[32];
+  const long long L = d.L;
+  const int L4 = d.L >> 2;
+  for (int n = blockIdx.x; n < d.N; n += gridDim.x) {
+    const float4* x = reinterpret_cast<const float4*>(d.in + n * L);
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < L4; i += blockDim.x) {
+      const float4 v = x[i];
+      sum += (v.x + v.y) + (v.z + v.w);
+    }
+    const float mean = block_sum(sum, red) / (float)L;
+    float sq = 0.f;
+    for (int i = threadIdx.x; i < L4; i += blockDim.x) {
+      const float4 v = x[i];
+      const float a = v.x - mean, b = v.y - mean, e = v.z - mean, f = v.w - mean;
+      sq += (a * a + b * b) + (e * e + f * f);
+    }
+    const float rstd = rsqrtf(block_sum(sq, red) / (float)L + d.eps);
+    float4* y = reinterpret_cast<float4*>(d.out + n * L);
+    const float4* g4 = reinterpret_cast<const float4*>(d.gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(d.beta);
+    for (int i = threadIdx.x; i < L4; i += blockDim.x) {
+      const float4 v = x[i];
+      const float4 g = __ldg(g4 + i);
+      const float4 b = __ldg(b4 + i);
+      float4 o;
+      o.x = maybe_round((v.x - mean) * rstd * g.x + b.x, d.round_tf32);
+      o.y = maybe_round((v.y - mean) * rstd * g.y + b.y, d.round_tf32);
+      o.z = maybe_round((v.z - mean) * rstd * g.z + b.z, d.round_tf32);
+      o.w = maybe_round((v.w - mean) * rstd * g.w + b.w, d.round_tf32);
+      y[i] = o;
+    }
+  }
+}
+
+// ---- shifted-window attention: one CTA per (window, head), one thread per query token ------------------
+constexpr int WS = 7, WT = 49, HD = 32;
+
+__global__ void __launch_bounds__(64) winattn_kernel(const svx_winattn_desc d) {
+  __shared__ __align__(16) float sk[WT * HD];
+  __shared__ __align__(16) float sv[WT * HD];
+  __shared__ int stok[WT];
+  __shared__ int sreg[WT];
+  const int head = blockIdx.x % d.heads;
+  long long w = blockIdx.x / d.heads;
+  const int nwx = d.W / WS, nwy = d.H / WS;
+  const int wx = (int)(w % nwx); w /= nwx;
+  const int wy = (int)(w % nwy);
+  const long long n = w / nwy;
+  const int C3 = 3 * d.C;
+  const int t = threadIdx.x;
+  if (t < WT) {
+    const int py = wy * WS + t / WS, px = wx * WS + t % WS;  // position in the rolled map
+    const int oy = (py + d.shift) % d.H, ox = (px + d.shift) % d.W;
+    stok[t] = (int)((n * d.H + oy) * d.W + ox);
+    int reg = 0;
+    if (d.shift > 0) {
+      const int ry = py < d.H - WS ? 0 : (py < d.H - d.shift ? 1 : 2);
+      const int rx = px < d.W - WS ? 0 : (px < d.W - d.shift ? 1 : 2);
+      reg = ry * 3 + rx;
+    }
+    sreg[t] = reg;
+  }
+  __syncthreads();
+  for (int i = t; i < WT * (HD / 4); i += 64) {
+    const int tok = i / (HD / 4), q4 = i % (HD / 4);
+    const float* row = d.qkv + (long long)stok[tok] * C3 + head * HD + q4 * 4;
+    *reinterpret_cast<float4*>(sk + tok * HD + q4 * 4) = __ldg(reinterpret_cast<const float4*>(row + d.C));
+    *reinterpret_cast<float4*>(sv + tok * HD + q4 * 4) = __ldg(reinterpret_cast<const float4*>(row + 2 * d.C));
+  }
+  __syncthreads();
+  if (t >= WT) return;
+  float q[HD];
+  {
+    const float* row = d.qkv + (long long)stok[t] * C3 + head * HD;
+#pragma unroll
+    for (int i = 0; i < HD; i += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(row + i));
+      q[i] = v.x * d.scale; q[i + 1] = v.y * d.scale; q[i + 2] = v.z * d.scale; q[i + 3] = v.w * d.scale;
+    }
+  }
+  const float* brow = d.bias + ((long long)head * WT + t) * WT;
+  const int myreg = sreg[t];
+  float s[WT];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < WT; ++j) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < HD; i += 4) {
+      const float4 kv = *reinterpret_cast<const float4*>(sk + j * HD + i);
+      acc = fmaf(q[i], kv.x, acc); acc = fmaf(q[i + 1], kv.y, acc);
+      acc = fmaf(q[i + 2], kv.z, acc); acc = fmaf(q[i + 3], kv.w, acc);
+    }
+    acc += __ldg(brow + j);
+    if (sreg[j] != myreg) acc += -100.f;
+    s[j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int j = 0; j < WT; ++j) {
+    s[j] = __expf(s[j] - mx);
+    den += s[j];
+  }
+  const float inv = 1.f / den;
+  float o[HD];
+#pragma unroll
+  for (int i = 0; i < HD; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < WT; ++j) {
+    const float pj = s[j] * inv;
+#pragma unroll
+    for (int i = 0; i < HD; i += 4) {
+      const float4 vv = *reinterpret_cast<const float4*>(sv + j * HD + i);
+      o[i] = fmaf(pj, vv.x, o[i]); o[i + 1] = fmaf(pj, vv.y, o[i + 1]);
+      o[i + 2] = fmaf(pj, vv.z, o[i + 2]); o[i + 3] = fmaf(pj, vv.w, o[i + 3]);
+    }
+  }
+  float* dst = d.out + (long long)stok[t] * d.C + head * HD;
+#pragma unroll
+  for (int i = 0; i < HD; i += 4)
+    *reinterpret_cast<float4*>(dst + i) =
+        make_float4(maybe_round(o[i], d.round_tf32), maybe_round(o[i + 1], d.round_tf32),
+                    maybe_round(o[i + 2], d.round_tf32), maybe_round(o[i + 3], d.round_tf32));
+}
+
+// ---- depthwise k=s conv, channels-last ---------------------------------------------------------------
+__global__ void dwconv_kernel(const svx_dwconv_desc d, long long total) {
+  const int c4n = d.C >> 2;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % c4n);
+    long long r = idx / c4n;
+    const int ox = (int)(r % d.OW); r /= d.OW;
+    const int oy = (int)(r % d.OH);
+    const long long n = r / d.OH;
+    float4 acc = d.bias ? __ldg(reinterpret_cast<const float4*>(d.bias + c4 * 4)) : make_float4(0, 0, 0, 0);
+    for (int ky = 0; ky < d.k; ++ky)
+      for (int kx = 0; kx < d.k; ++kx) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(
+            d.in + ((n * d.H + oy * d.k + ky) * d.W + ox * d.k + kx) * (long long)d.C + c4 * 4));
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(d.w + (ky * d.k + kx) * d.C + c4 * 4));
+        acc.x = fmaf(v.x, wv.x, acc.x); acc.y = fmaf(v.y, wv.y, acc.y);
+        acc.z = fmaf(v.z, wv.z, acc.z); acc.w = fmaf(v.w, wv.w, acc.w);
+      }
+    acc.x = maybe_round(acc.x, d.round_tf32); acc.y = maybe_round(acc.y, d.round_tf32);
+    acc.z = maybe_round(acc.z, d.round_tf32); acc.w = maybe_round(acc.w, d.round_tf32);
+    *reinterpret_cast<float4*>(d.out + ((n * d.OH + oy) * d.OW + ox) * (long long)d.C + c4 * 4) = acc;
+  }
+}
+
+// ---- attention over the view axis: one CTA per (object, head) ----------------------------------------
+constexpr int kMaxViews = 32;
+__global__ void __launch_bounds__(256) viewattn_kernel(const svx_viewattn_desc d) {
+  __shared__ float sc[kMaxViews * kMaxViews];
+  const int head = blockIdx.x % d.heads;
+  const long long b = blockIdx.x / d.heads;
+  const int V = d.V, P = d.P, R = d.R, hd = R / d.heads;
+  const int R3 = 3 * R;
+  const int L = P * hd;  // dot-product length
+  const float* base = d.qkv + b * V * (long long)P * R3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int pair = warp; pair < V * V; pair += nw) {
+    const int v1 = pair / V, v2 = pair % V;
+    float acc = 0.f;
+    for (int e = lane; e < L; e += 32) {
+      const int pos = e / hd, dd = e % hd;
+      const float qv = base[((long long)v1 * P + pos) * R3 + head * hd + dd];
+      const float kv = base[((long long)v2 * P + pos) * R3 + R + head * hd + dd];
+      acc = fmaf(qv, kv, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sc[v1 * kMaxViews + v2] = acc * d.scale;
+  }
+  __syncthreads();
+  for (int v1 = warp; v1 < V; v1 += nw) {
+    float x = lane < V ? sc[v1 * kMaxViews + lane] : -INFINITY;
+    const float mx = warp_max(x);
+    const float e = lane < V ? __expf(x - mx) : 0.f;
+    const float den = warp_sum(e);
+    if (lane < V) sc[v1 * kMaxViews + lane] = e / den;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < V * L; idx += blockDim.x) {
+    const int v1 = idx / L, e = idx % L;
+    const int pos = e / hd, dd = e % hd;
+    float acc = 0.f;
+    for (int v2 = 0; v2 < V; ++v2)
+      acc = fmaf(sc[v1 * kMaxViews + v2], base[((long long)v2 * P + pos) * R3 + 2 * R + head * hd + dd], acc);
+    d.out[((b * V + v1) * P + pos) * (long long)R + head * hd + dd] = maybe_round(acc, d.round_tf32);
+  }
+}
+
+// ---- bilinear resize (align_corners=False) + skip ------------------------------------------------------
+__global__ void bilinear_kernel(const svx_bilinear_desc d, long long total) {
+  const int c4n = d.C >> 2;
+  const float sy = (float)d.IH / (float)d.OH, sx = (float)d.IW / (float)d.OW;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % c4n);
+    long long r = idx / c4n;
+    const int ox = (int)(r % d.OW); r /= d.OW;
+    const int oy = (int)(r % d.OH);
+    const long long n = r / d.OH;
+    float fy = fmaxf((oy + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * sx - 0.5f, 0.f);
+    const int y0 = min((int)fy, d.IH - 1), x0 = min((int)fx, d.IW - 1);
+    const int y1 = min(y0 + 1, d.IH - 1), x1 = min(x0 + 1, d.IW - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    auto at = [&](int y, int x) {
+      return __ldg(reinterpret_cast<const float4*>(d.in + ((n * d.IH + y) * d.IW + x) * (long long)d.C + c4 * 4));
+    };
+    const float4 a = at(y0, x0), b = at(y0, x1), c = at(y1, x0), e = at(y1, x1);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const long long o = ((n * d.OH + oy) * d.OW + ox) * (long long)d.C + c4 * 4;
+    const float4 s = d.skip ? __ldg(reinterpret_cast<const float4*>(d.skip + o)) : make_float4(0, 0, 0, 0);
+    float4 v;
+    v.x = maybe_round(w00 * a.x + w01 * b.x + w10 * c.x + w11 * e.x + s.x, d.round_tf32);
+    v.y = maybe_round(w00 * a.y + w01 * b.y + w10 * c.y + w11 * e.y + s.y, d.round_tf32);
+    v.z = maybe_round(w00 * a.z + w01 * b.z + w10 * c.z + w11 * e.z + s.z, d.round_tf32);
+    v.w = maybe_round(w00 * a.w + w01 * b.w + w10 * c.w + w11 * e.w + s.w, d.round_tf32);
+    *reinterpret_cast<float4*>(d.out + o) = v;
+  }
+}
+
+// ---- merger: per-voxel softmax over views and weighted fusion (merger.py:98-104) -------------------------
+__global__ void mergefuse_kernel(const svx_mergefuse_desc d, long long total4) {
+  const int P4 = d.P >> 2;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long b = idx / P4;
+    const int p4 = (int)(idx % P4);
+    const float4* w = reinterpret_cast<const float4*>(d.weights + b * d.V * (long long)d.P) + p4;
+    const float4* c = reinterpret_cast<const float4*>(d.coarse + b * d.V * (long long)d.P) + p4;
+    float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int v = 0; v < d.V; ++v) {
+      const float4 x = __ldg(w + (long long)v * P4);
+      mx.x = fmaxf(mx.x, x.x); mx.y = fmaxf(mx.y, x.y); mx.z = fmaxf(mx.z, x.z); mx.w = fmaxf(mx.w, x.w);
+    }
+    float4 den = make_float4(0, 0, 0, 0), num = make_float4(0, 0, 0, 0);
+    for (int v = 0; v < d.V; ++v) {
+      const float4 x = __ldg(w + (long long)v * P4);
+      const float4 g = __ldg(c + (long long)v * P4);
+      const float ex = __expf(x.x - mx.x), ey = __expf(x.y - mx.y), ez = __expf(x.z - mx.z), ew = __expf(x.w - mx.w);
+      den.x += ex; den.y += ey; den.z += ez; den.w += ew;
+      num.x = fmaf(ex, g.x, num.x); num.y = fmaf(ey, g.y, num.y);
+      num.z = fmaf(ez, g.z, num.z); num.w = fmaf(ew, g.w, num.w);
+    }
+    reinterpret_cast<float4*>(d.out + b * (long long)d.P)[p4] =
+        make_float4(num.x / den.x, num.y / den.y, num.z / den.z, num.w / den.w);
+  }
+}
+
+// ---- sigmoid / threshold / I,U,TP,FP,FN counters (core/test.py:141-164) -----------------------------------
+constexpr int kMaxThresh = 8;
+__global__ void __launch_bounds__(256) metrics_kernel(const svx_metrics_desc d, int chunks) {
+  __shared__ int sacc[kMaxThresh * 5];
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  for (int i = threadIdx.x; i < kMaxThresh * 5; i += blockDim.x) sacc[i] = 0;
+  __syncthreads();
+  float th[kMaxThresh];
+#pragma unroll
+  for (int t = 0; t < kMaxThresh; ++t) th[t] = t < d.T ? __ldg(d.prob_thresholds + t) : 2.f;
+  int cI[kMaxThresh], cU[kMaxThresh], cFP[kMaxThresh], cFN[kMaxThresh];
+#pragma unroll
+  for (int t = 0; t < kMaxThresh; ++t) cI[t] = cU[t] = cFP[t] = cFN[t] = 0;
+  const int per = (d.P + chunks - 1) / chunks;
+  const int beg = chunk * per, end = min(d.P, beg + per);
+  const float* lg = d.logits + (long long)b * d.P;
+  const float* gt = d.gt + (long long)b * d.P;
+  for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    const float prob = 1.f / (1.f + expf(-lg[i]));
+    const int g = gt[i] != 0.f;
+#pragma unroll
+    for (int t = 0; t < kMaxThresh; ++t) {
+      const int v = prob >= th[t];
+      cI[t] += v & g; cU[t] += v | g; cFP[t] += v & (g ^ 1); cFN[t] += (v ^ 1) & g;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < kMaxThresh; ++t) {
+    if (t >= d.T) break;
+    int a = cI[t], u = cU[t], fp = cFP[t], fn = cFN[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o); u += __shfl_xor_sync(0xffffffffu, u, o);
+      fp += __shfl_xor_sync(0xffffffffu, fp, o); fn += __shfl_xor_sync(0xffffffffu, fn, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&sacc[t * 5 + 0], a); atomicAdd(&sacc[t * 5 + 1], u); atomicAdd(&sacc[t * 5 + 2], a);
+      atomicAdd(&sacc[t * 5 + 3], fp); atomicAdd(&sacc[t * 5 + 4], fn);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d.T * 5; i += blockDim.x) atomicAdd(d.counts + (long long)b * d.T * 5 + i, sacc[i]);
+}
+
+// ---- [N,C,P] <-> [N,P,Cs] ------------------------------------------------------------------------------
+__global__ void transpose_kernel(const svx_transpose_desc d) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  if (d.to_channels_last) {
+    const float* src = d.in + (long long)n * d.C * d.P;
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, p = p0 + tx;
+      tile[i][tx] = (c < d.C && p < d.P) ? src[(long long)c * d.P + p] : 0.f;
+    }
+    __syncthreads();
+    float* dst = d.out + (long long)n * d.P * d.Cs;
+    for (int i = ty; i < 32; i += 8) {
+      const int p = p0 + i, c = c0 + tx;
+      if (p < d.P && c < d.Cs) dst[(long long)p * d.Cs + c] = c < d.C ? maybe_round(tile[tx][i], d.round_tf32) : 0.f;
+    }
+  } else {
+    const float* src = d.in + (long long)n * d.P * d.Cs;
+    for (int i = ty; i < 32; i += 8) {
+      const int p = p0 + i, c = c0 + tx;
+      tile[i][tx] = (p < d.P && c < d.C) ? src[(long long)p * d.Cs + c] : 0.f;
+    }
+    __syncthreads();
+    float* dst = d.out + (long long)n * d.C * d.P;
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, p = p0 + tx;
+      if (c < d.C && p < d.P) dst[(long long)c * d.P + p] = maybe_round(tile[tx][i], d.round_tf32);
+    }
+  }
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+int im2col_launch(const svx_im2col_desc& d, void* stream) {
+  const int K = d.KD * d.KH * d.KW * d.C;
+  SVX_REQUIRE(d.in && d.out && d.N > 0 && K > 0 && d.Kpad >= K, "im2col: bad description");
+  const long long total = (long long)d.N * d.OD * d.OH * d.OW * d.Kpad;
+  im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total, K);
+  SVX_LAUNCH_OK("im2col_kernel");
+  return 0;
+}
+
+int pool_launch(const svx_pool_desc& d, void* stream) {
+  SVX_REQUIRE(d.in && d.out && d.C % 4 == 0 && d.in_Cs % 4 == 0 && d.out_Cs % 4 == 0 && al16(d.in) && al16(d.out),
+              "pool: channels must be multiples of 4 and pointers 16-byte aligned");
+  const long long total = (long long)d.N * d.OD * d.OH * d.OW * (d.C / 4);
+  pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
+  SVX_LAUNCH_OK("pool_kernel");
+  return 0;
+}
+
+int lnrows_launch(const svx_lnrows_desc& d, void* stream) {
+  SVX_REQUIRE(d.in && d.out && d.gamma && d.beta && d.rows > 0, "layernorm_rows: null operand");
+  SVX_REQUIRE(d.C % 4 == 0 && (!d.merge || (d.C % 16 == 0 && d.H % 2 == 0 && d.W % 2 == 0)),
+              "layernorm_rows: C=%d unsupported", d.C);
+  SVX_REQUIRE(al16(d.in) && al16(d.out) && al16(d.gamma) && al16(d.beta), "layernorm_rows: unaligned pointer");
+  const int wpb = 8;
+  lnrows_kernel<<<grid_for(d.rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(d);
+  SVX_LAUNCH_OK("lnrows_kernel");
+  return 0;
+}
+
+int lnsample_launch(const svx_lnsample_desc& d, void* stream) {
+  SVX_REQUIRE(d.in && d.out && d.gamma && d.beta && d.N > 0 && d.L > 0 && d.L % 4 == 0, "layernorm_sample: bad description");
+  lnsample_kernel<<<d.N, 1024, 0, (cudaStream_t)stream>>>(d);
+  SVX_LAUNCH_OK("lnsample_kernel");
+  return 0;
+}
+
+int winattn_launch(const svx_winattn_desc& d, void* stream) {
+  SVX_REQUIRE(d.qkv && d.out && d.bias, "window_attention: null operand");
+  SVX_REQUIRE(d.H % WS == 0 && d.W % WS == 0 && d.C == d.heads * HD && d.shift >= 0 && d.shift < WS,
+              "window_attention: needs 7x7 windows, head_dim 32 (H=%d W=%d C=%d heads=%d)", d.H, d.W, d.C, d.heads);
+  const long long blocks = (long long)d.N * (d.H / WS) * (d.W / WS) * d.heads;
+  SVX_REQUIRE(blocks < 0x7fffffffLL, "window_attention: grid too large");
+  winattn_kernel<<<(int)blocks, 64, 0, (cudaStream_t)stream>>>(d);
+  SVX_LAUNCH_OK("winattn_kernel");
+  return 0;
+}
+
+int dwconv_launch(const svx_dwconv_desc& d, void* stream) {
+  SVX_REQUIRE(d.in && d.out && d.w && d.C % 4 == 0 && d.k >= 1, "dwconv: bad description");
+  const long long total = (long long)d.N * d.OH * d.OW * (d.C / 4);
+  dwconv_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
+  SVX_LAUNCH_OK("dwconv_kernel");
+  return 0;
+}
+
+int viewattn_launch(const svx_viewattn_desc& d, void* stream) {
+  SVX_REQUIRE(d.qkv && d.out && d.V >= 1 && d.V <= kMaxViews && d.R % d.heads == 0,
+              "view_attention: supports 1..%d views (V=%d)", kMaxViews, d.V);
+  viewattn_kernel<<<d.B * d.heads, 256, 0, (cudaStream_t)stream>>>(d);
+  SVX_LAUNCH_OK("viewattn_kernel");
+  return 0;
+}
+
+int bilinear_launch(const svx_bilinear_desc& d, void* stream) {
+  SVX_REQUIRE(d.in && d.out && d.C % 4 == 0, "bilinear_add: bad description");
+  const long long total = (long long)d.N * d.OH * d.OW * (d.C / 4);
+  bilinear_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
+  SVX_LAUNCH_OK("bilinear_kernel");
+  return 0;
+}
+
+int mergefuse_launch(const svx_mergefuse_desc& d, void* stream) {
+  SVX_REQUIRE(d.weights && d.coarse && d.out && d.B > 0 && d.V > 0 && d.P % 4 == 0, "merger_fuse: bad description");
+  SVX_REQUIRE(al16(d.weights) && al16(d.coarse) && al16(d.out), "merger_fuse: unaligned pointer");
+  const long long total4 = (long long)d.B * (d.P / 4);
+  mergefuse_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(d, total4);
+  SVX_LAUNCH_OK("mergefuse_kernel");
+  return 0;
+}
+
+int metrics_launch(const svx_metrics_desc& d, void* stream) {
+  SVX_REQUIRE(d.logits && d.gt && d.prob_thresholds && d.counts && d.T >= 1 && d.T <= kMaxThresh && d.B > 0 && d.P > 0,
+              "voxel_metrics: supports 1..%d thresholds", kMaxThresh);
+  SVX_CUDA_OK(cudaMemsetAsync(d.counts, 0, sizeof(int32_t) * (size_t)d.B * d.T * 5, (cudaStream_t)stream));
+  int chunks = (2 * kSmCount + d.B - 1) / d.B;
+  if (chunks < 1) chunks = 1;
+  const int max_chunks = (d.P + 2047) / 2048;
+  if (chunks > max_chunks) chunks = max_chunks;
+  metrics_kernel<<<d.B * chunks, 256, 0, (cudaStream_t)stream>>>(d, chunks);
+  SVX_LAUNCH_OK("metrics_kernel");
+  return 0;
+}
+
+int transpose_launch(const svx_transpose_desc& d, void* stream) {
+  SVX_REQUIRE(d.in && d.out && d.N > 0 && d.C > 0 && d.P > 0 && d.Cs >= d.C, "transpose: bad description");
+  SVX_REQUIRE(d.N <= 65535, "transpose: N too large");
+  const int cext = d.to_channels_last ? d.Cs : d.C;
+  dim3 grid((d.P + 31) / 32, (cext + 31) / 32, d.N);
+  transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(d);
+  SVX_LAUNCH_OK("transpose_kernel");
+  return 0;
+}
+
+}  // namespace svx

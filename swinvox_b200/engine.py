@@ -1,0 +1,411 @@
+"""Host-side plan builder for libswinvox_b200: activation bookkeeping, weight re-layout, BatchNorm
+folding and tap tables.  Everything here runs once per (module, input shape); the per-forward work
+is a single ``svx_plan_run`` call.
+
+Layout conventions: activations are fp32 channels-last buffers ``[N, D, H, W, Cs]`` (2-D maps use
+D=1); contraction weights are ``[Npad, Kpad]`` with k = tap*Cin + c, pre-rounded to TF32.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, A_GATHER, A_PLAIN, EPI_DEC_TAIL, EPI_STD, POOL_AVG,
+                   POOL_MAX)
+
+BLOCK_NS = (16, 32, 64, 96, 128, 192, 256)
+
+
+def tf32_round(t):
+    """round-to-nearest (ties away) to TF32, the host twin of cvt.rna.tf32.f32"""
+    t = t.contiguous().float()
+    bits = t.view(torch.int32)
+    bits = (bits + 0x1000) & ~0x1FFF
+    return bits.view(torch.float32)
+
+
+def choose_block_n(n):
+    if n <= 16:
+        return 16
+    if n <= 32:
+        return 32
+    if n <= 64:
+        return 64
+    for bn in (128, 192, 96):
+        if n % bn == 0:
+            return bn
+    return 128 if n > 96 else 96
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class Act:
+    """channels [c0, c0+C) of a channels-last buffer [N, D, H, W, Cs]"""
+    buf: torch.Tensor
+    N: int
+    D: int
+    H: int
+    W: int
+    C: int
+    c0: int = 0
+
+    @property
+    def Cs(self):
+        return self.buf.shape[-1]
+
+    @property
+    def pixels(self):
+        return self.N * self.D * self.H * self.W
+
+    def view(self):
+        """logical [N, D, H, W, C] torch view (for tests / module boundaries)"""
+        return self.buf.view(self.N, self.D, self.H, self.W, self.Cs)[..., self.c0:self.c0 + self.C]
+
+    def channels(self, c0, c):
+        return Act(self.buf, self.N, self.D, self.H, self.W, c, self.c0 + c0)
+
+
+@dataclass
+class WeightPack:
+    W: torch.Tensor      # [Npad, Kpad] tf32-rounded
+    bias: torch.Tensor   # [Npad]
+    N: int
+    K: int
+    block_n: int
+
+    @property
+    def Kpad(self):
+        return self.W.shape[1]
+
+    @property
+    def Npad(self):
+        return self.W.shape[0]
+
+
+def pack_matrix(w2d, bias, device, block_n=None, n_logical=None):
+    """w2d: [N, K] fp32 (already folded / permuted)."""
+    n, k = w2d.shape
+    n_log = n_logical or n
+    bn = block_n or choose_block_n(n_log)
+    npad, kpad = round_up(max(n, n_log), bn), round_up(k, 32)
+    W = torch.zeros(npad, kpad, dtype=torch.float32, device=device)
+    W[:n, :k] = tf32_round(w2d.detach().to(device=device, dtype=torch.float32))
+    b = torch.zeros(npad, dtype=torch.float32, device=device)
+    if bias is not None:
+        b[:n] = bias.detach().to(device=device, dtype=torch.float32)
+    return WeightPack(W, b, n_log, k, bn)
+
+
+def fold_bn(weight, bias, bn):
+    """Fold eval-mode BatchNorm (running stats) into the preceding conv: returns (w, b).
+    `weight` has output channels on dim 0."""
+    w = weight.detach().float()
+    cout = w.shape[0]
+    b = bias.detach().float() if bias is not None else torch.zeros(cout, device=w.device)
+    if bn is None:
+        return w, b
+    s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    w = w * s.view(-1, *([1] * (w.dim() - 1)))
+    b = (b - bn.running_mean.detach().float()) * s + bn.bias.detach().float()
+    return w, b
+
+
+def conv_taps(kd, kh, kw, pd, ph, pw):
+    return [(a - pd, b - ph, c - pw) for a in range(kd) for b in range(kh) for c in range(kw)]
+
+
+def pack_conv(weight, bias, bn, device, cin_pad=None, block_n=None, n_logical=None):
+    """nn.Conv2d / nn.Conv3d weight [Cout, Cin, (KD,) KH, KW] -> WeightPack with k = tap*Cin_pad + c."""
+    w, b = fold_bn(weight, bias, bn)
+    if w.dim() == 4:
+        w = w.unsqueeze(2)
+    cout, cin = w.shape[:2]
+    cp = cin_pad or round_up(cin, 4)
+    w = w.permute(0, 2, 3, 4, 1)  # [Cout, KD, KH, KW, Cin]
+    if cp != cin:
+        w = torch.nn.functional.pad(w, (0, cp - cin))
+    return pack_matrix(w.reshape(cout, -1), b, device, block_n, n_logical)
+
+
+def convT_class_taps(ks, pad, par):
+    """taps (kernel index k, input offset delta) feeding output parity `par` of a stride-2 ConvTranspose."""
+    return [(k, (par + pad - k) // 2) for k in range(ks) if (k - par - pad) % 2 == 0]
+
+
+def pack_convT_class(weight, bn, device, pads, parity, cin_pad=None, block_n=None, n_logical=None, bias=None):
+    """One stride-2 parity class of nn.ConvTranspose3d (weight [Cin, Cout, KD, KH, KW]).
+    Returns (WeightPack, taps[(dd,dh,dw)])."""
+    w = weight.detach().float().transpose(0, 1)  # [Cout, Cin, KD, KH, KW]
+    w, b = fold_bn(w, bias, bn)
+    cout, cin = w.shape[:2]
+    cp = cin_pad or round_up(cin, 4)
+    td = convT_class_taps(w.shape[2], pads[0], parity[0])
+    th = convT_class_taps(w.shape[3], pads[1], parity[1])
+    tw = convT_class_taps(w.shape[4], pads[2], parity[2])
+    cols, taps = [], []
+    for kd, dd in td:
+        for kh, dh in th:
+            for kw, dw in tw:
+                col = w[:, :, kd, kh, kw]
+                if cp != cin:
+                    col = torch.nn.functional.pad(col, (0, cp - cin))
+                cols.append(col)
+                taps.append((dd, dh, dw))
+    return pack_matrix(torch.cat(cols, dim=1), b, device, block_n, n_logical), taps
+
+
+class Plan:
+    """A recorded op list bound to fixed device buffers."""
+
+    def __init__(self, device, lib=None):
+        self.lib = lib or _lib.get()
+        self.device = torch.device(device)
+        self.handle = C.c_void_p(self.lib.svx_plan_create())
+        if not self.handle:
+            raise _lib.SvxError("svx_plan_create failed")
+        self.keep = {}
+        self.op_names = []
+        self.flops = []
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.svx_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---- memory ------------------------------------------------------------------------------
+    def empty(self, *shape, dtype=torch.float32):
+        return self.hold(torch.empty(*shape, dtype=dtype, device=self.device))
+
+    def zeros(self, *shape, dtype=torch.float32):
+        return self.hold(torch.zeros(*shape, dtype=dtype, device=self.device))
+
+    def new_act(self, N, D, H, W, C, Cs=None, zero=False):
+        Cs = Cs or C
+        buf = (self.zeros if zero else self.empty)(N * D * H * W, Cs)
+        return Act(buf, N, D, H, W, C, 0)
+
+    def hold(self, t):
+        """keep every tensor whose address is baked into an op alive as long as the plan"""
+        if isinstance(t, Act):
+            self.keep[id(t.buf)] = t.buf
+        elif t is not None:
+            self.keep[id(t)] = t
+        return t
+
+    # ---- execution ---------------------------------------------------------------------------
+    def _stream(self):
+        if self.device.type == "cuda":
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(0)
+
+    def run(self, graph=False):
+        _lib.check(self.lib.svx_plan_run(self.handle, self._stream(), 1 if graph else 0), self.lib)
+
+    def run_range(self, first, last):
+        _lib.check(self.lib.svx_plan_run_range(self.handle, first, last, self._stream()), self.lib)
+
+    def time_ops(self, iters=5):
+        n = self.num_ops
+        ms = (C.c_float * n)()
+        _lib.check(self.lib.svx_plan_time_ops(self.handle, self._stream(), iters, ms), self.lib)
+        return list(ms)
+
+    @property
+    def num_ops(self):
+        return self.lib.svx_plan_num_ops(self.handle)
+
+    @property
+    def num_launches(self):
+        return self.lib.svx_plan_num_launches(self.handle)
+
+    def _add(self, op, desc, name, flops=0.0):
+        add = getattr(self.lib, _lib.OPS[op][1])
+        _lib.check(add(self.handle, C.byref(desc)), self.lib)
+        self.op_names.append(name or op)
+        self.flops.append(flops)
+
+    # ---- contractions ------------------------------------------------------------------------
+    def _taps_tensor(self, taps):
+        t = torch.tensor([[a, b, c, 0] for a, b, c in taps], dtype=torch.int32, device=self.device)
+        return self.hold(t)
+
+    def _fill_epilogue(self, d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out):
+        d.W = pack.W.data_ptr()
+        d.bias = pack.bias.data_ptr()
+        d.N, d.K, d.Kpad, d.Npad, d.block_n = pack.N, pack.K, pack.Kpad, pack.Npad, pack.block_n
+        d.out = self.hold(out).buf.data_ptr()
+        if out_map is None:
+            Cs = out.Cs
+            out_map = (out.c0, out.D * out.H * out.W * Cs, out.H * out.W * Cs, out.W * Cs, Cs)
+        d.o_base, d.o_sn, d.o_sd, d.o_sh, d.o_sw = out_map
+        d.act, d.act_param = act, act_param
+        d.out_scale = out_scale
+        d.round_tf32 = 1 if round_out else 0
+        d.epi_mode = EPI_STD
+        if residual is not None:
+            assert residual.Cs == out.Cs and residual.c0 == out.c0 and residual.pixels == out.pixels, \
+                "residual must share the output layout"
+            d.residual = self.hold(residual).buf.data_ptr()
+            d.res_after_act = 1 if res_after_act else 0
+        self.hold(pack.W)
+        self.hold(pack.bias)
+
+    def linear(self, x, pack, out, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True,
+               out_scale=1.0, round_out=False, name=None):
+        """x: Act read as a [pixels, C] matrix (plain TMA operand); out: Act with C == pack.N."""
+        assert x.C == pack.K and out.C >= pack.N and x.pixels == out.pixels, (x.C, pack.K, out.C, pack.N)
+        assert x.c0 % 4 == 0 and x.Cs % 4 == 0
+        d = _lib.GemmDesc()
+        d.M = x.pixels
+        d.a_mode = A_PLAIN
+        d.A = self.hold(x).buf.data_ptr() + 4 * x.c0
+        d.lda = x.Cs
+        d.out_D, d.out_H, d.out_W = 1, 1, 1
+        self._fill_epilogue(d, pack, out, (out.c0, out.Cs, 0, 0, 0), act, act_param, residual, res_after_act,
+                            out_scale, round_out)
+        self._add("gemm", d, name or "linear", 2.0 * d.M * pack.N * pack.K)
+        return out
+
+    def conv(self, x, pack, taps, out, stride=(1, 1, 1), out_map=None, rows_dhw=None, act=ACT_NONE, act_param=0.0,
+             residual=None, res_after_act=True, out_scale=1.0, round_out=False, name=None, epi_tail=None):
+        """Implicit-GEMM convolution.  rows_dhw: extents the GEMM rows run over (default: out D,H,W)."""
+        cin_pad = pack.K // len(taps)
+        assert cin_pad * len(taps) == pack.K and cin_pad % 4 == 0 and cin_pad >= x.C
+        assert x.c0 % 4 == 0 and x.Cs % 4 == 0 and x.c0 + cin_pad <= x.Cs, (x.c0, cin_pad, x.Cs)
+        rd, rh, rw = rows_dhw or (out.D, out.H, out.W)
+        d = _lib.GemmDesc()
+        d.M = x.N * rd * rh * rw
+        d.a_mode = A_GATHER
+        d.A = self.hold(x).buf.data_ptr()
+        d.in_D, d.in_H, d.in_W, d.in_Cs, d.in_c0, d.Cin = x.D, x.H, x.W, x.Cs, x.c0, cin_pad
+        d.out_D, d.out_H, d.out_W = rd, rh, rw
+        d.stride_d, d.stride_h, d.stride_w = stride
+        d.ntaps = len(taps)
+        d.taps = self._taps_tensor(taps).data_ptr()
+        self._fill_epilogue(d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out)
+        if epi_tail is not None:
+            aux, out2, map2 = epi_tail
+            d.epi_mode = EPI_DEC_TAIL
+            d.epi_aux = self.hold(aux).data_ptr()
+            d.epi_out2 = self.hold(out2).data_ptr()
+            d.o2_base, d.o2_sn, d.o2_sd, d.o2_sh, d.o2_sw = map2
+        self._add("gemm", d, name or "conv", 2.0 * d.M * pack.N * pack.K)
+        return out
+
+    # ---- everything else ------------------------------------------------------------------------
+    def im2col(self, src, strides, N, Cin, dhw, kernel, stride, pads, out_dhw, kpad, round_out=True, name=None):
+        """src: tensor read in place with element strides (s_n, s_c, s_d, s_h, s_w)."""
+        OD, OH, OW = out_dhw
+        out = self.new_act(N, OD, OH, OW, kpad)
+        d = _lib.Im2colDesc()
+        d.inp, d.out = self.hold(src).data_ptr(), out.buf.data_ptr()
+        d.N, d.C, (d.D, d.H, d.W) = N, Cin, dhw
+        d.s_n, d.s_c, d.s_d, d.s_h, d.s_w = strides
+        d.KD, d.KH, d.KW = kernel
+        d.stride = stride
+        d.pad_d, d.pad_h, d.pad_w = pads
+        d.OD, d.OH, d.OW, d.Kpad = OD, OH, OW, kpad
+        d.round_tf32 = 1 if round_out else 0
+        self._add("im2col", d, name)
+        return out
+
+    def pool(self, x, out, kernel, stride, pads, mode, round_out=False, name=None):
+        d = _lib.PoolDesc()
+        assert x.c0 == 0 and out.c0 == 0, "pool works on whole buffers"
+        d.inp, d.out = self.hold(x).buf.data_ptr(), self.hold(out).buf.data_ptr()
+        d.N, d.C, d.D, d.H, d.W, d.in_Cs, d.out_Cs = x.N, x.C, x.D, x.H, x.W, x.Cs, out.Cs
+        d.KD, d.KH, d.KW = kernel
+        d.SD, d.SH, d.SW = stride
+        d.PD, d.PH, d.PW = pads
+        d.OD, d.OH, d.OW = out.D, out.H, out.W
+        d.mode = mode
+        d.round_tf32 = 1 if round_out else 0
+        self._add("pool", d, name)
+        return out
+
+    def layernorm_rows(self, x, gamma, beta, out, merge_hw=None, eps=1e-5, round_out=True, name=None):
+        d = _lib.LnRowsDesc()
+        d.inp, d.out = self.hold(x).buf.data_ptr(), self.hold(out).buf.data_ptr()
+        d.gamma, d.beta = self.hold(gamma).data_ptr(), self.hold(beta).data_ptr()
+        d.rows, d.C = out.pixels, out.C
+        if merge_hw:
+            d.merge, d.H, d.W = 1, merge_hw[0], merge_hw[1]
+        d.eps = eps
+        d.round_tf32 = 1 if round_out else 0
+        self._add("layernorm_rows", d, name)
+        return out
+
+    def layernorm_sample(self, x, gamma, beta, out, eps=1e-5, round_out=True, name=None):
+        d = _lib.LnSampleDesc()
+        d.inp, d.out = self.hold(x).buf.data_ptr(), self.hold(out).buf.data_ptr()
+        d.gamma, d.beta = self.hold(gamma).data_ptr(), self.hold(beta).data_ptr()
+        d.N, d.L = x.N, x.D * x.H * x.W * x.Cs
+        d.eps = eps
+        d.round_tf32 = 1 if round_out else 0
+        self._add("layernorm_sample", d, name)
+        return out
+
+    def window_attention(self, qkv, out, bias, H, W, heads, shift, scale, round_out=True, name=None):
+        d = _lib.WinAttnDesc()
+        d.qkv, d.out, d.bias = self.hold(qkv).buf.data_ptr(), self.hold(out).buf.data_ptr(), self.hold(bias).data_ptr()
+        d.N, d.H, d.W, d.C, d.heads, d.shift, d.scale = qkv.N, H, W, out.C, heads, shift, scale
+        d.round_tf32 = 1 if round_out else 0
+        self._add("window_attention", d, name, 4.0 * qkv.N * H * W * 49 * out.C)
+        return out
+
+    def dwconv(self, x, w, bias, out, k, round_out=True, name=None):
+        d = _lib.DwConvDesc()
+        d.inp, d.out, d.w = self.hold(x).buf.data_ptr(), self.hold(out).buf.data_ptr(), self.hold(w).data_ptr()
+        d.bias = self.hold(bias).data_ptr() if bias is not None else None
+        d.N, d.H, d.W, d.C, d.k, d.OH, d.OW = x.N, x.H, x.W, x.C, k, out.H, out.W
+        d.round_tf32 = 1 if round_out else 0
+        self._add("dwconv", d, name)
+        return out
+
+    def view_attention(self, qkv, out, B, V, heads, scale, round_out=True, name=None):
+        d = _lib.ViewAttnDesc()
+        d.qkv, d.out = self.hold(qkv).buf.data_ptr(), self.hold(out).buf.data_ptr()
+        d.B, d.V, d.P, d.R, d.heads, d.scale = B, V, qkv.H * qkv.W, out.C, heads, scale
+        d.round_tf32 = 1 if round_out else 0
+        self._add("view_attention", d, name)
+        return out
+
+    def bilinear_add(self, x, skip, out, round_out=True, name=None):
+        d = _lib.BilinearDesc()
+        d.inp, d.out = self.hold(x).buf.data_ptr(), self.hold(out).buf.data_ptr()
+        d.skip = self.hold(skip).buf.data_ptr() if skip is not None else None
+        d.N, d.IH, d.IW, d.OH, d.OW, d.C = x.N, x.H, x.W, out.H, out.W, x.C
+        d.round_tf32 = 1 if round_out else 0
+        self._add("bilinear_add", d, name)
+        return out
+
+    def merger_fuse(self, weights, coarse, out, B, V, P, name=None):
+        d = _lib.MergeFuseDesc()
+        d.weights, d.coarse, d.out = self.hold(weights).data_ptr(), self.hold(coarse).data_ptr(), self.hold(out).data_ptr()
+        d.B, d.V, d.P = B, V, P
+        self._add("merger_fuse", d, name)
+        return out
+
+    def voxel_metrics(self, logits, gt, thresholds, counts, B, P, name=None):
+        d = _lib.MetricsDesc()
+        d.logits, d.gt, d.prob_thresholds, d.counts = (self.hold(logits).data_ptr(), self.hold(gt).data_ptr(),
+                                                       self.hold(thresholds).data_ptr(), self.hold(counts).data_ptr())
+        d.B, d.P, d.T = B, P, thresholds.numel()
+        self._add("voxel_metrics", d, name)
+        return counts
+
+    def transpose(self, src, dst, N, Cc, P, Cs, to_channels_last, round_out=False, name=None):
+        d = _lib.TransposeDesc()
+        d.inp, d.out = self.hold(src).data_ptr(), self.hold(dst).data_ptr()
+        d.N, d.C, d.P, d.Cs = N, Cc, P, Cs
+        d.to_channels_last = 1 if to_channels_last else 0
+        d.round_tf32 = 1 if round_out else 0
+        self._add("transpose", d, name)
+        return dst

@@ -1,0 +1,391 @@
+// svx_hostsim.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// A CPU twin of the device kernels in swinvox_b200/csrc, compiled with g++ into
+// tests/hostsim/libsvx_hostsim.so.  It implements the same descriptor semantics
+// (include/swinvox_b200.h) with plain loops so that the host logic of the product -- weight
+// re-layout, BatchNorm folding, tap tables, transposed-convolution parity classes, window/shift
+// indexing, plan construction -- can be checked against the oracle in the CPU-only test tier.
+// The swinvox_b200 package never loads this library; tests inject it explicitly.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../swinvox_b200/csrc/svx_internal.h"
+
+namespace svx {
+
+static inline float tf32_trunc(float x) {  // what tcgen05 kind::tf32 sees of an fp32 operand
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u &= 0xFFFFE000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+static inline float tf32_rna(float x) {  // cvt.rna.tf32.f32
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+static inline float rnd(float x, int r) { return r ? tf32_rna(x) : x; }
+
+static inline float act_fn(float x, int act, float slope) {
+  switch (act) {
+    case SVX_ACT_RELU: return x > 0.f ? x : 0.f;
+    case SVX_ACT_LEAKY: return x > 0.f ? x : x * slope;
+    case SVX_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    default: return x;
+  }
+}
+
+struct GemmPrepared { int unused; };
+int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
+  *out = nullptr;
+  SVX_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "gemm: empty problem");
+  SVX_REQUIRE(d.Kpad % 32 == 0 && d.Kpad >= d.K, "gemm: bad Kpad");
+  SVX_REQUIRE(d.Npad % d.block_n == 0 && d.Npad >= d.N, "gemm: bad Npad");
+  if (d.a_mode == SVX_A_GATHER)
+    SVX_REQUIRE(d.Cin % 4 == 0 && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.K == d.ntaps * d.Cin, "gemm: bad gather");
+  else
+    SVX_REQUIRE(d.lda % 4 == 0 && d.lda >= d.K, "gemm: bad lda");
+  if (d.epi_mode == SVX_EPI_DEC_TAIL)
+    SVX_REQUIRE(d.block_n == 16 && d.N == 16 && d.epi_aux && d.epi_out2, "gemm: bad decoder tail");
+  *out = new GemmPrepared();
+  return 0;
+}
+void gemm_prepared_free(GemmPrepared* p) { delete p; }
+int gemm_num_launches(const svx_gemm_desc&) { return 1; }
+
+int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
+  if (!prepared) {
+    GemmPrepared* g = nullptr;
+    if (int rc = gemm_prepare(d, &g)) return rc;
+    delete g;
+  }
+  const long long rows_per_n = (long long)d.out_D * d.out_H * d.out_W;
+#pragma omp parallel
+  {
+    std::vector<float> arow(d.K);
+#pragma omp for schedule(static)
+    for (int r = 0; r < d.M; ++r) {
+      const int ow = r % d.out_W;
+      int t = r / d.out_W;
+      const int oh = t % d.out_H;
+      t /= d.out_H;
+      const int od = t % d.out_D;
+      const long long n = t / d.out_D;
+      (void)rows_per_n;
+      if (d.a_mode == SVX_A_PLAIN) {
+        for (int k = 0; k < d.K; ++k) arow[k] = tf32_trunc(d.A[(long long)r * d.lda + k]);
+      } else {
+        for (int tap = 0; tap < d.ntaps; ++tap) {
+          const int id = od * d.stride_d + d.taps[tap * 4 + 0];
+          const int ih = oh * d.stride_h + d.taps[tap * 4 + 1];
+          const int iw = ow * d.stride_w + d.taps[tap * 4 + 2];
+          const bool ok = id >= 0 && id < d.in_D && ih >= 0 && ih < d.in_H && iw >= 0 && iw < d.in_W;
+          const float* px = d.A + (((n * d.in_D + id) * d.in_H + ih) * (long long)d.in_W + iw) * d.in_Cs + d.in_c0;
+          for (int c = 0; c < d.Cin; ++c) arow[tap * d.Cin + c] = ok ? tf32_trunc(px[c]) : 0.f;
+        }
+      }
+      const long long off = d.o_base + n * d.o_sn + od * d.o_sd + oh * d.o_sh + ow * d.o_sw;
+      float x[16];
+      if (d.epi_mode == SVX_EPI_DEC_TAIL) {
+        float g = 0.f;
+        for (int j = 0; j < 8; ++j) {
+          float acc = 0.f;
+          const float* w = d.W + (long long)j * d.Kpad;
+          for (int k = 0; k < d.K; ++k) acc += arow[k] * tf32_trunc(w[k]);
+          acc += d.bias ? d.bias[j] : 0.f;
+          x[j] = acc > 0.f ? acc : 0.f;
+          g = fmaf(d.epi_aux[j], x[j], g);
+        }
+        x[8] = g;
+        for (int j = 9; j < 16; ++j) x[j] = 0.f;
+        d.epi_out2[d.o2_base + n * d.o2_sn + od * d.o2_sd + oh * d.o2_sh + ow * d.o2_sw] = g;
+        for (int j = 0; j < 16; ++j) d.out[off + j] = rnd(x[j], d.round_tf32);
+        continue;
+      }
+      for (int j = 0; j < d.N; ++j) {
+        float acc = 0.f;
+        const float* w = d.W + (long long)j * d.Kpad;
+        for (int k = 0; k < d.K; ++k) acc += arow[k] * tf32_trunc(w[k]);
+        float v = acc + (d.bias ? d.bias[j] : 0.f);
+        const float res = d.residual ? d.residual[off + j] : 0.f;
+        if (d.residual && !d.res_after_act) v += res;
+        v = act_fn(v, d.act, d.act_param);
+        if (d.residual && d.res_after_act) v += res;
+        v *= d.out_scale;
+        d.out[off + j] = rnd(v, d.round_tf32);
+      }
+    }
+  }
+  return 0;
+}
+
+int im2col_launch(const svx_im2col_desc& d, void*) {
+  const int K = d.KD * d.KH * d.KW * d.C;
+  const long long rows = (long long)d.N * d.OD * d.OH * d.OW;
+#pragma omp parallel for
+  for (long long r = 0; r < rows; ++r) {
+    long long t = r;
+    const int ow = t % d.OW; t /= d.OW;
+    const int oh = t % d.OH; t /= d.OH;
+    const int od = t % d.OD;
+    const long long n = t / d.OD;
+    float* dst = d.out + r * d.Kpad;
+    int k = 0;
+    for (int kd = 0; kd < d.KD; ++kd)
+      for (int kh = 0; kh < d.KH; ++kh)
+        for (int kw = 0; kw < d.KW; ++kw)
+          for (int c = 0; c < d.C; ++c, ++k) {
+            const int id = od * d.stride - d.pad_d + kd, ih = oh * d.stride - d.pad_h + kh,
+                      iw = ow * d.stride - d.pad_w + kw;
+            float v = 0.f;
+            if (id >= 0 && id < d.D && ih >= 0 && ih < d.H && iw >= 0 && iw < d.W)
+              v = d.in[n * d.s_n + c * d.s_c + id * d.s_d + ih * d.s_h + iw * d.s_w];
+            dst[k] = rnd(v, d.round_tf32);
+          }
+    for (; k < d.Kpad; ++k) dst[k] = 0.f;
+  }
+  return 0;
+}
+
+int pool_launch(const svx_pool_desc& d, void*) {
+  const long long rows = (long long)d.N * d.OD * d.OH * d.OW;
+#pragma omp parallel for
+  for (long long r = 0; r < rows; ++r) {
+    long long t = r;
+    const int ow = t % d.OW; t /= d.OW;
+    const int oh = t % d.OH; t /= d.OH;
+    const int od = t % d.OD;
+    const long long n = t / d.OD;
+    for (int c = 0; c < d.C; ++c) {
+      float acc = d.mode == SVX_POOL_MAX ? -INFINITY : 0.f;
+      int cnt = 0;
+      for (int kd = 0; kd < d.KD; ++kd)
+        for (int kh = 0; kh < d.KH; ++kh)
+          for (int kw = 0; kw < d.KW; ++kw) {
+            const int id = od * d.SD - d.PD + kd, ih = oh * d.SH - d.PH + kh, iw = ow * d.SW - d.PW + kw;
+            if (id < 0 || id >= d.D || ih < 0 || ih >= d.H || iw < 0 || iw >= d.W) continue;
+            const float v = d.in[(((n * d.D + id) * d.H + ih) * d.W + iw) * (long long)d.in_Cs + c];
+            acc = d.mode == SVX_POOL_MAX ? std::max(acc, v) : acc + v;
+            ++cnt;
+          }
+      if (d.mode == SVX_POOL_AVG) acc /= (float)std::max(cnt, 1);
+      d.out[r * d.out_Cs + c] = rnd(acc, d.round_tf32);
+    }
+  }
+  return 0;
+}
+
+int lnrows_launch(const svx_lnrows_desc& d, void*) {
+#pragma omp parallel
+  {
+    std::vector<float> row(d.C);
+#pragma omp for
+    for (int r = 0; r < d.rows; ++r) {
+      if (d.merge) {
+        const int Cq = d.C / 4, W2 = d.W / 2, H2 = d.H / 2;
+        const int x = r % W2, y = (r / W2) % H2;
+        const long long n = r / (W2 * H2);
+        for (int s = 0; s < 4; ++s) {
+          const int dy = s & 1, dx = s >> 1;
+          const float* src = d.in + ((n * d.H + 2 * y + dy) * d.W + 2 * x + dx) * (long long)Cq;
+          for (int c = 0; c < Cq; ++c) row[s * Cq + c] = src[c];
+        }
+      } else {
+        memcpy(row.data(), d.in + (long long)r * d.C, sizeof(float) * d.C);
+      }
+      double mean = 0, var = 0;
+      for (int c = 0; c < d.C; ++c) mean += row[c];
+      mean /= d.C;
+      for (int c = 0; c < d.C; ++c) var += (row[c] - mean) * (row[c] - mean);
+      var /= d.C;
+      const float rstd = 1.f / sqrtf((float)var + d.eps);
+      for (int c = 0; c < d.C; ++c)
+        d.out[(long long)r * d.C + c] = rnd((row[c] - (float)mean) * rstd * d.gamma[c] + d.beta[c], d.round_tf32);
+    }
+  }
+  return 0;
+}
+
+int lnsample_launch(const svx_lnsample_desc& d, void*) {
+#pragma omp parallel for
+  for (int n = 0; n < d.N; ++n) {
+    const float* x = d.in + (long long)n * d.L;
+    double mean = 0, var = 0;
+    for (int i = 0; i < d.L; ++i) mean += x[i];
+    mean /= d.L;
+    for (int i = 0; i < d.L; ++i) var += (x[i] - mean) * (x[i] - mean);
+    var /= d.L;
+    const float rstd = 1.f / sqrtf((float)var + d.eps);
+    for (int i = 0; i < d.L; ++i)
+      d.out[(long long)n * d.L + i] = rnd((x[i] - (float)mean) * rstd * d.gamma[i] + d.beta[i], d.round_tf32);
+  }
+  return 0;
+}
+
+int winattn_launch(const svx_winattn_desc& d, void*) {
+  SVX_REQUIRE(d.H % 7 == 0 && d.W % 7 == 0 && d.C == d.heads * 32, "window_attention: bad shape");
+  const int nwy = d.H / 7, nwx = d.W / 7;
+  const long long nwin = (long long)d.N * nwy * nwx;
+#pragma omp parallel for
+  for (long long w = 0; w < nwin; ++w) {
+    const int wx = w % nwx, wy = (w / nwx) % nwy;
+    const long long n = w / (nwx * nwy);
+    long long tok[49];
+    int reg[49];
+    for (int t = 0; t < 49; ++t) {
+      const int py = wy * 7 + t / 7, px = wx * 7 + t % 7;
+      tok[t] = (n * d.H + (py + d.shift) % d.H) * d.W + (px + d.shift) % d.W;
+      reg[t] = 0;
+      if (d.shift > 0) {
+        const int ry = py < d.H - 7 ? 0 : (py < d.H - d.shift ? 1 : 2);
+        const int rx = px < d.W - 7 ? 0 : (px < d.W - d.shift ? 1 : 2);
+        reg[t] = ry * 3 + rx;
+      }
+    }
+    for (int h = 0; h < d.heads; ++h)
+      for (int i = 0; i < 49; ++i) {
+        const float* q = d.qkv + tok[i] * 3 * d.C + h * 32;
+        float s[49], mx = -INFINITY;
+        for (int j = 0; j < 49; ++j) {
+          const float* k = d.qkv + tok[j] * 3 * d.C + d.C + h * 32;
+          float acc = 0.f;
+          for (int e = 0; e < 32; ++e) acc += q[e] * d.scale * k[e];
+          acc += d.bias[((long long)h * 49 + i) * 49 + j];
+          if (reg[i] != reg[j]) acc += -100.f;
+          s[j] = acc;
+          mx = std::max(mx, acc);
+        }
+        float den = 0.f;
+        for (int j = 0; j < 49; ++j) { s[j] = expf(s[j] - mx); den += s[j]; }
+        for (int e = 0; e < 32; ++e) {
+          float acc = 0.f;
+          for (int j = 0; j < 49; ++j) acc += s[j] / den * d.qkv[tok[j] * 3 * d.C + 2 * d.C + h * 32 + e];
+          d.out[tok[i] * d.C + h * 32 + e] = rnd(acc, d.round_tf32);
+        }
+      }
+  }
+  return 0;
+}
+
+int dwconv_launch(const svx_dwconv_desc& d, void*) {
+  for (long long n = 0; n < d.N; ++n)
+    for (int oy = 0; oy < d.OH; ++oy)
+      for (int ox = 0; ox < d.OW; ++ox)
+        for (int c = 0; c < d.C; ++c) {
+          float acc = d.bias ? d.bias[c] : 0.f;
+          for (int ky = 0; ky < d.k; ++ky)
+            for (int kx = 0; kx < d.k; ++kx)
+              acc += d.in[((n * d.H + oy * d.k + ky) * d.W + ox * d.k + kx) * (long long)d.C + c] *
+                     d.w[(ky * d.k + kx) * d.C + c];
+          d.out[((n * d.OH + oy) * d.OW + ox) * (long long)d.C + c] = rnd(acc, d.round_tf32);
+        }
+  return 0;
+}
+
+int viewattn_launch(const svx_viewattn_desc& d, void*) {
+  const int hd = d.R / d.heads, R3 = 3 * d.R;
+  for (long long b = 0; b < d.B; ++b)
+    for (int h = 0; h < d.heads; ++h) {
+      const float* base = d.qkv + b * d.V * (long long)d.P * R3;
+      std::vector<float> sc(d.V * d.V);
+      for (int v1 = 0; v1 < d.V; ++v1) {
+        float mx = -INFINITY;
+        for (int v2 = 0; v2 < d.V; ++v2) {
+          float acc = 0.f;
+          for (int pos = 0; pos < d.P; ++pos)
+            for (int e = 0; e < hd; ++e)
+              acc += base[((long long)v1 * d.P + pos) * R3 + h * hd + e] *
+                     base[((long long)v2 * d.P + pos) * R3 + d.R + h * hd + e];
+          sc[v1 * d.V + v2] = acc * d.scale;
+          mx = std::max(mx, acc * d.scale);
+        }
+        float den = 0.f;
+        for (int v2 = 0; v2 < d.V; ++v2) { sc[v1 * d.V + v2] = expf(sc[v1 * d.V + v2] - mx); den += sc[v1 * d.V + v2]; }
+        for (int v2 = 0; v2 < d.V; ++v2) sc[v1 * d.V + v2] /= den;
+      }
+      for (int v1 = 0; v1 < d.V; ++v1)
+        for (int pos = 0; pos < d.P; ++pos)
+          for (int e = 0; e < hd; ++e) {
+            float acc = 0.f;
+            for (int v2 = 0; v2 < d.V; ++v2)
+              acc += sc[v1 * d.V + v2] * base[((long long)v2 * d.P + pos) * R3 + 2 * d.R + h * hd + e];
+            d.out[((b * d.V + v1) * d.P + pos) * (long long)d.R + h * hd + e] = rnd(acc, d.round_tf32);
+          }
+    }
+  return 0;
+}
+
+int bilinear_launch(const svx_bilinear_desc& d, void*) {
+  const float sy = (float)d.IH / d.OH, sx = (float)d.IW / d.OW;
+  for (long long n = 0; n < d.N; ++n)
+    for (int oy = 0; oy < d.OH; ++oy)
+      for (int ox = 0; ox < d.OW; ++ox) {
+        const float fy = std::max((oy + 0.5f) * sy - 0.5f, 0.f), fx = std::max((ox + 0.5f) * sx - 0.5f, 0.f);
+        const int y0 = std::min((int)fy, d.IH - 1), x0 = std::min((int)fx, d.IW - 1);
+        const int y1 = std::min(y0 + 1, d.IH - 1), x1 = std::min(x0 + 1, d.IW - 1);
+        const float ly = fy - y0, lx = fx - x0;
+        for (int c = 0; c < d.C; ++c) {
+          auto at = [&](int y, int x) { return d.in[((n * d.IH + y) * d.IW + x) * (long long)d.C + c]; };
+          const long long o = ((n * d.OH + oy) * d.OW + ox) * (long long)d.C + c;
+          float v = (1 - ly) * (1 - lx) * at(y0, x0) + (1 - ly) * lx * at(y0, x1) + ly * (1 - lx) * at(y1, x0) +
+                    ly * lx * at(y1, x1);
+          if (d.skip) v += d.skip[o];
+          d.out[o] = rnd(v, d.round_tf32);
+        }
+      }
+  return 0;
+}
+
+int mergefuse_launch(const svx_mergefuse_desc& d, void*) {
+  for (long long b = 0; b < d.B; ++b)
+    for (int p = 0; p < d.P; ++p) {
+      float mx = -INFINITY;
+      for (int v = 0; v < d.V; ++v) mx = std::max(mx, d.weights[(b * d.V + v) * (long long)d.P + p]);
+      float den = 0.f, num = 0.f;
+      for (int v = 0; v < d.V; ++v) {
+        const float e = expf(d.weights[(b * d.V + v) * (long long)d.P + p] - mx);
+        den += e;
+        num += e * d.coarse[(b * d.V + v) * (long long)d.P + p];
+      }
+      d.out[b * d.P + p] = num / den;
+    }
+  return 0;
+}
+
+int metrics_launch(const svx_metrics_desc& d, void*) {
+  SVX_REQUIRE(d.T >= 1 && d.T <= 8, "voxel_metrics: supports 1..8 thresholds");
+  for (long long b = 0; b < d.B; ++b)
+    for (int t = 0; t < d.T; ++t) {
+      int I = 0, U = 0, FP = 0, FN = 0;
+      for (int p = 0; p < d.P; ++p) {
+        const float prob = 1.f / (1.f + expf(-d.logits[b * d.P + p]));
+        const int v = prob >= d.prob_thresholds[t], g = d.gt[b * d.P + p] != 0.f;
+        I += v & g; U += v | g; FP += v & !g; FN += !v & g;
+      }
+      int32_t* c = d.counts + (b * d.T + t) * 5;
+      c[0] = I; c[1] = U; c[2] = I; c[3] = FP; c[4] = FN;
+    }
+  return 0;
+}
+
+int transpose_launch(const svx_transpose_desc& d, void*) {
+  for (long long n = 0; n < d.N; ++n)
+    for (int p = 0; p < d.P; ++p) {
+      if (d.to_channels_last) {
+        for (int c = 0; c < d.Cs; ++c)
+          d.out[(n * d.P + p) * (long long)d.Cs + c] = c < d.C ? rnd(d.in[(n * d.C + c) * (long long)d.P + p], d.round_tf32) : 0.f;
+      } else {
+        for (int c = 0; c < d.C; ++c)
+          d.out[(n * d.C + c) * (long long)d.P + p] = rnd(d.in[(n * d.P + p) * (long long)d.Cs + c], d.round_tf32);
+      }
+    }
+  return 0;
+}
+
+}  // namespace svx
