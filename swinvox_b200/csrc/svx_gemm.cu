@@ -14,6 +14,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "svx_internal.h"
 #include "svx_ptx.cuh"
 
@@ -47,6 +49,7 @@ struct GemmParams {
   float* out2;
   long long o2_base, o2_sn, o2_sd, o2_sh, o2_sw;
   int vec_ok;
+  int consumer_fence;  // 1: the MMA thread issues the generic->async proxy fence (experiment)
 };
 
 template <int BN>
@@ -148,6 +151,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int s = kc % S;
         const uint32_t ph = (kc / S) & 1;
         mbar_wait(full_bar(s), ph);
+        if (gather && p.consumer_fence) fence_proxy_async_smem();
         tc_fence_after();
         const uint32_t a_addr = smem_base + s * C::kStageBytes;
         const uint64_t da = umma_desc_sw128(a_addr);
@@ -218,13 +222,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         cp_async_commit();
         if (kc >= kGatherLag) {
           cp_async_wait<kGatherLag>();
-          fence_proxy_async_smem();
+          if (!p.consumer_fence) fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(full_bar((kc - kGatherLag) % S));
         }
       }
       cp_async_wait<0>();
-      fence_proxy_async_smem();
+      if (!p.consumer_fence) fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
         for (int kc = (nk > kGatherLag ? nk - kGatherLag : 0); kc < nk; ++kc) mbar_arrive(full_bar(kc % S));
@@ -449,6 +453,10 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   p.vec_ok = (d.N % 4 == 0) && al4(d.o_base) && al4(d.o_sn) && al4(d.o_sd) && al4(d.o_sh) && al4(d.o_sw) &&
              (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
              (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0);
+  {
+    const char* e = getenv("SVX_CONSUMER_FENCE");
+    p.consumer_fence = (e && e[0] == '1') ? 1 : 0;
+  }
   const long long tiles_m = (d.M + BM - 1) / BM;
   const long long grid = tiles_m * p.tiles_n;
   if (grid > 0x7fffffffLL) { delete g; return fail("gemm: grid too large"); }

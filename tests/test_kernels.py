@@ -31,7 +31,7 @@ def dev(request, hostsim):
 
 def sync(dev):
     if dev == "cuda":
-        sync(DEV)
+        torch.cuda.synchronize()
 
 
 
