@@ -81,7 +81,7 @@ typedef struct svx_gemm_desc {
   float out_scale;          /* applied last (refiner.py:103 uses 0.5); 1.0 otherwise */
   int32_t round_tf32;       /* round the stored result to TF32 (it feeds another contraction) */
   int32_t epi_mode;
-  const float* epi_aux;     /* SVX_EPI_DEC_TAIL: layer5 weights w5[8] */
+  const float* epi_aux;     /* SVX_EPI_DEC_TAIL: layer5 weights w5[0..7], bias w5[8] */
   float* epi_out2;          /* SVX_EPI_DEC_TAIL: planar coarse volume [n, OD*OH*OW] */
   int64_t o2_base, o2_sn, o2_sd, o2_sh, o2_sw;
 } svx_gemm_desc;

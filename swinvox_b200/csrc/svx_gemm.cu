@@ -267,7 +267,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int q = 0; q < 16; ++q) x[q] = __uint_as_float(v[q]) + sbias[c0 + q];
       if (p.epi_mode == SVX_EPI_DEC_TAIL) {
         // decoder.py:80-89: raw = cat(relu(bn(layer4)), layer5(.)) ; coarse = layer5(.)
-        float g = 0.f;
+        float g = __ldg(p.epi_aux + 8);  // layer5 bias (0 when TCONV_USE_BIAS is off)
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           x[q] = fmaxf(x[q], 0.f);
@@ -285,7 +285,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int q = 0; q < 16; q += 4) {
               if (jb + q < p.N) {
-                const float4 t4 = __ldg(reinterpret_cast<const float4*>(res + q));
+                const float4 t4 = *reinterpret_cast<const float4*>(res + q);  // plain load: out may alias residual
                 rv[q] = t4.x; rv[q + 1] = t4.y; rv[q + 2] = t4.z; rv[q + 3] = t4.w;
               } else {
                 rv[q] = rv[q + 1] = rv[q + 2] = rv[q + 3] = 0.f;
@@ -293,7 +293,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           } else {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) rv[q] = (jb + q < p.N) ? __ldg(res + q) : 0.f;
+            for (int q = 0; q < 16; ++q) rv[q] = (jb + q < p.N) ? res[q] : 0.f;
           }
           if (!p.res_after_act) {
 #pragma unroll

@@ -170,6 +170,7 @@ class Plan:
         self.keep = {}
         self.op_names = []
         self.flops = []
+        self.taps = {}   # name -> Act of selected intermediates (parity tests / debugging)
 
     def __del__(self):
         try:
@@ -409,3 +410,13 @@ class Plan:
         d.round_tf32 = 1 if round_out else 0
         self._add("transpose", d, name)
         return dst
+
+
+def transpose_now(plan, src, dst, N, Cc, P, Cs, to_channels_last, round_out=False):
+    """immediate (non-recorded) layout change on the plan's stream: module-boundary conversions"""
+    d = _lib.TransposeDesc()
+    d.inp, d.out = src.data_ptr(), dst.data_ptr()
+    d.N, d.C, d.P, d.Cs = N, Cc, P, Cs
+    d.to_channels_last = 1 if to_channels_last else 0
+    d.round_tf32 = 1 if round_out else 0
+    _lib.check(plan.lib.svx_transpose(C.byref(d), plan._stream()), plan.lib)

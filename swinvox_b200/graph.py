@@ -1,0 +1,369 @@
+"""Lowering of the SwinVox modules onto libswinvox_b200 ops.
+
+Each ``lower_*`` function reads the parameters of a (reference-layout) nn.Module container, prepares the
+weights (BatchNorm folding, TF32 rounding, k = tap*Cin + c re-layout, transposed-convolution parity
+classes) and records the ops into an engine.Plan.  Reference semantics are cited per function.
+
+Rounding policy: a tensor is stored rounded to TF32 (`round_out`) exactly when its next consumer is a
+tensor-core contraction, so kind::tf32's operand truncation never adds a bias; everything else stays
+full fp32 (residual streams, attention inputs, module outputs).
+"""
+import torch
+
+from . import engine as E
+from .engine import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, POOL_AVG, POOL_MAX, Act
+
+WINDOW = 7
+
+
+def _dev(plan):
+    return plan.device
+
+
+# --------------------------------------------------------------------------------------------------
+# ResNet-50 trunk: torchvision resnet50 children[:7]  (models/encoder.py:22-23,119)
+# --------------------------------------------------------------------------------------------------
+def lower_resnet_trunk(plan, resnet, img, N):
+    """img: [N,3,224,224] fp32 NCHW tensor (read in place).  Returns Act [N,14,14,1024]."""
+    dev = _dev(plan)
+    conv1, bn1 = resnet[0], resnet[1]
+    cols = plan.im2col(img, (3 * 224 * 224, 224 * 224, 0, 224, 1), N, 3, (1, 224, 224), (1, 7, 7), 2, (0, 3, 3),
+                       (1, 112, 112), 160, name="resnet.stem.im2col")
+    w, b = E.fold_bn(conv1.weight, conv1.bias, bn1)
+    pk = E.pack_matrix(w.permute(0, 2, 3, 1).reshape(64, 147), b, dev)
+    stem = plan.new_act(N, 1, 112, 112, 64)
+    plan.linear(cols, E.WeightPack(pk.W, pk.bias, 64, 160, pk.block_n), stem, act=ACT_RELU, name="resnet.stem")
+    x = plan.new_act(N, 1, 56, 56, 64)
+    plan.pool(stem, x, (1, 3, 3), (1, 2, 2), (0, 1, 1), POOL_MAX, round_out=True, name="resnet.maxpool")
+    for li in (4, 5, 6):
+        for bi, blk in enumerate(resnet[li]):
+            x = _bottleneck(plan, blk, x, f"resnet.{li}.{bi}")
+    return x
+
+
+def _bottleneck(plan, blk, x, name):
+    dev = _dev(plan)
+    s = blk.conv2.stride[0]
+    width, cout = blk.conv1.out_channels, blk.conv3.out_channels
+    H2 = (x.H + 2 - 3) // s + 1
+    t1 = plan.new_act(x.N, 1, x.H, x.W, width)
+    plan.linear(x, E.pack_conv(blk.conv1.weight, None, blk.bn1, dev), t1, act=ACT_RELU, round_out=True, name=name + ".conv1")
+    t2 = plan.new_act(x.N, 1, H2, H2, width)
+    plan.conv(t1, E.pack_conv(blk.conv2.weight, None, blk.bn2, dev), E.conv_taps(1, 3, 3, 0, 1, 1), t2, stride=(1, s, s),
+              act=ACT_RELU, round_out=True, name=name + ".conv2")
+    if blk.downsample is not None:
+        idn = plan.new_act(x.N, 1, H2, H2, cout)
+        pk = E.pack_conv(blk.downsample[0].weight, None, blk.downsample[1], dev)
+        if s == 1:
+            plan.linear(x, pk, idn, name=name + ".downsample")
+        else:
+            plan.conv(x, pk, [(0, 0, 0)], idn, stride=(1, s, s), name=name + ".downsample")
+    else:
+        idn = x
+    out = plan.new_act(x.N, 1, H2, H2, cout)
+    plan.linear(t2, E.pack_conv(blk.conv3.weight, None, blk.bn3, dev), out, act=ACT_RELU, residual=idn,
+                res_after_act=False, round_out=True, name=name + ".conv3")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Swin-T (timm swin_tiny_patch4_window7_224, features_only) + the wrapper's per-stage LayerNorm([C,H,W])
+# (models/swin_transformer.py:71-94; timm semantics restated in SURVEY 8c)
+# --------------------------------------------------------------------------------------------------
+def relative_position_bias(table, heads):
+    """[169, heads] table -> expanded [heads, 49, 49] (index (dh+6)*13 + (dw+6))"""
+    ws = WINDOW
+    coords = torch.stack(torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij")).flatten(1)
+    rel = coords[:, :, None] - coords[:, None, :]
+    idx = ((rel[0] + ws - 1) * (2 * ws - 1) + (rel[1] + ws - 1)).to(table.device)
+    return table.detach().float()[idx.view(-1)].view(ws * ws, ws * ws, heads).permute(2, 0, 1).contiguous()
+
+
+def lower_swin(plan, swin, img, N):
+    """swin: the SwinTransformer wrapper (has .model, .layer_norm, .cfg).  Returns the list of per-stage
+    Acts [N,H,W,C] AFTER the wrapper LayerNorm, in SWIN_T_STAGES order, stored TF32-rounded NHWC."""
+    dev = _dev(plan)
+    model = swin.model
+    stages = [i % 4 for i in swin.cfg.NETWORK.SWIN_T_STAGES]
+    pe = model.patch_embed
+    cols = plan.im2col(img, (3 * 224 * 224, 224 * 224, 0, 224, 1), N, 3, (1, 224, 224), (1, 4, 4), 4, (0, 0, 0),
+                       (1, 56, 56), 64, name="swin.patch_embed.im2col")
+    pk = E.pack_matrix(pe.proj.weight.detach().permute(0, 2, 3, 1).reshape(96, 48), pe.proj.bias, dev)
+    emb = plan.new_act(N, 1, 56, 56, 96)
+    plan.linear(cols, E.WeightPack(pk.W, pk.bias, 96, 64, pk.block_n), emb, name="swin.patch_embed.proj")
+    x = plan.new_act(N, 1, 56, 56, 96)
+    plan.layernorm_rows(emb, pe.norm.weight.detach().float().to(dev), pe.norm.bias.detach().float().to(dev), x,
+                        eps=pe.norm.eps, round_out=False, name="swin.patch_embed.norm")
+    feats = {}
+    for s in range(max(stages) + 1):
+        layer = getattr(model, f"layers_{s}")
+        Cc, H = 96 * 2 ** s, 56 // 2 ** s
+        heads = Cc // 32
+        if s > 0:
+            ds = layer.downsample
+            merged = plan.new_act(N, 1, H, H, 2 * Cc)  # 4 * (C/2) concatenated channels
+            plan.layernorm_rows(x, ds.norm.weight.detach().float().to(dev), ds.norm.bias.detach().float().to(dev),
+                                merged, merge_hw=(2 * H, 2 * H), eps=ds.norm.eps, name=f"swin.{s}.merge.norm")
+            x = plan.new_act(N, 1, H, H, Cc)
+            plan.linear(merged, E.pack_matrix(ds.reduction.weight, None, dev), x, name=f"swin.{s}.merge.reduction")
+        for j, blk in enumerate(layer.blocks):
+            nm = f"swin.{s}.{j}"
+            shift = WINDOW // 2 if (j % 2 == 1 and H > WINDOW) else 0
+            y = plan.new_act(N, 1, H, H, Cc)
+            plan.layernorm_rows(x, blk.norm1.weight.detach().float().to(dev), blk.norm1.bias.detach().float().to(dev), y,
+                                eps=blk.norm1.eps, name=nm + ".norm1")
+            qkv = plan.new_act(N, 1, H, H, 3 * Cc)
+            plan.linear(y, E.pack_matrix(blk.attn.qkv.weight, blk.attn.qkv.bias, dev), qkv, name=nm + ".qkv")
+            att = plan.new_act(N, 1, H, H, Cc)
+            bias = relative_position_bias(blk.attn.relative_position_bias_table, heads).to(dev)
+            plan.window_attention(qkv, att, bias, H, H, heads, shift, 32 ** -0.5, name=nm + ".attn")
+            x1 = plan.new_act(N, 1, H, H, Cc)
+            plan.linear(att, E.pack_matrix(blk.attn.proj.weight, blk.attn.proj.bias, dev), x1, residual=x,
+                        name=nm + ".proj")
+            y2 = plan.new_act(N, 1, H, H, Cc)
+            plan.layernorm_rows(x1, blk.norm2.weight.detach().float().to(dev), blk.norm2.bias.detach().float().to(dev), y2,
+                                eps=blk.norm2.eps, name=nm + ".norm2")
+            hid = plan.new_act(N, 1, H, H, 4 * Cc)
+            plan.linear(y2, E.pack_matrix(blk.mlp.fc1.weight, blk.mlp.fc1.bias, dev), hid, act=ACT_GELU, round_out=True,
+                        name=nm + ".fc1")
+            x = plan.new_act(N, 1, H, H, Cc)
+            plan.linear(hid, E.pack_matrix(blk.mlp.fc2.weight, blk.mlp.fc2.bias, dev), x, residual=x1, name=nm + ".fc2")
+        feats[s] = x
+    outs = []
+    for i, s in enumerate(stages):
+        ln = swin.layer_norm[i]
+        Cc, H = 96 * 2 ** s, 56 // 2 ** s
+        f = plan.new_act(N, 1, H, H, Cc)
+        # affine is stored [C,H,W] (it normalises an NCHW tensor); our data is [H,W,C]
+        g = ln.weight.detach().float().permute(1, 2, 0).contiguous().to(dev)
+        b = ln.bias.detach().float().permute(1, 2, 0).contiguous().to(dev)
+        plan.layernorm_sample(feats[s], g, b, f, eps=ln.eps, name=f"swin.layer_norm.{i}")
+        outs.append(f)
+    return outs
+
+
+# --------------------------------------------------------------------------------------------------
+# Cross-view attention (models/cross_view_attention.py:59-134)
+# --------------------------------------------------------------------------------------------------
+def lower_cva(plan, cva, x, B, V):
+    """x: Act [B*V,7,7,C] (C=512).  Returns Act of the same shape (TF32-rounded: it feeds fusion_layer)."""
+    dev = _dev(plan)
+    N, Cc, R, heads = x.N, x.C, cva.reduced_channels, cva.num_heads
+    ratio = cva.attention_spatial_downsample_ratio
+    if ratio > 1:
+        h = (x.H - ratio) // ratio + 1
+        small = plan.new_act(N, 1, h, h, Cc)
+        dw = cva.downsample_qkv
+        plan.dwconv(x, dw.weight.detach().float().reshape(Cc, ratio * ratio).t().contiguous().to(dev),
+                    dw.bias.detach().float().to(dev) if dw.bias is not None else None, small, ratio, name="cva.downsample_qkv")
+    else:
+        h, small = x.H, x
+    qkv = plan.new_act(N, 1, h, h, 3 * R)
+    plan.linear(small, E.pack_conv(cva.qkv_conv.weight, cva.qkv_conv.bias, None, dev), qkv, name="cva.qkv_conv")
+    att = plan.new_act(N, 1, h, h, R)
+    plan.view_attention(qkv, att, B, V, heads, 1.0 / float(cva.head_dim * V) ** 0.5, name="cva.attention")
+    y = plan.new_act(N, 1, x.H, x.W, Cc)
+    pk = E.pack_conv(cva.proj_conv.weight, cva.proj_conv.bias, None, dev)
+    if ratio > 1:
+        proj = plan.new_act(N, 1, h, h, Cc)
+        plan.linear(att, pk, proj, name="cva.proj_conv")
+        plan.bilinear_add(proj, x, y, name="cva.upsample_residual")
+    else:
+        plan.linear(att, pk, y, residual=x, round_out=True, name="cva.proj_conv")
+    hid = plan.new_act(N, 1, x.H, x.W, Cc)
+    plan.linear(y, E.pack_conv(cva.ffn[0].weight, cva.ffn[0].bias, None, dev), hid, act=ACT_GELU, round_out=True,
+                name="cva.ffn.0")
+    out = plan.new_act(N, 1, x.H, x.W, Cc)
+    plan.linear(hid, E.pack_conv(cva.ffn[2].weight, cva.ffn[2].bias, cva.batch_norm, dev), out, round_out=True,
+                name="cva.ffn.2+bn")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Encoder (models/encoder.py:113-164)
+# --------------------------------------------------------------------------------------------------
+def lower_encoder(plan, enc, img, B, V):
+    """img: [B*V,3,224,224] NCHW staging tensor.  Returns Act [B*V,7,7,256] (full fp32)."""
+    dev = _dev(plan)
+    N = B * V
+    net = enc.cfg.NETWORK
+    cat = plan.new_act(N, 1, 7, 7, 512)
+    # ResNet branch.  avg_pool2d(conv1x1(x)) == conv1x1(avg_pool2d(x)): pool first, 4x fewer MACs.
+    r = lower_resnet_trunk(plan, enc.resnet, img, N)
+    rp = plan.new_act(N, 1, 7, 7, 1024)
+    plan.pool(r, rp, (1, 2, 2), (1, 2, 2), (0, 0, 0), POOL_AVG, round_out=True, name="encoder.avg_pool")
+    plan.linear(rp, E.pack_conv(enc.resnet_reduce.weight, enc.resnet_reduce.bias, None, dev), cat.channels(0, 256),
+                round_out=True, name="encoder.resnet_reduce")
+    # Swin branch
+    feats = lower_swin(plan, enc.swin_transformer, img, N)
+    sw = cat.channels(256, 256)
+    if net.USE_SWIN_T_MULTI_STAGE:
+        n_st = len(feats)
+        for i, f in enumerate(feats):
+            chain = enc.swin_downsamples[i]
+            convs = [] if isinstance(chain, torch.nn.Identity) else [(chain[k], chain[k + 1]) for k in range(0, len(chain), 3)]
+            first, last_stage = i == 0, i == n_st - 1
+            red = enc.swin_stage_reduces[i]
+            pk = E.pack_conv(red.weight, red.bias, None, dev)
+            if not convs:   # the reduce itself accumulates into the running sum
+                plan.linear(f, pk, sw, residual=None if first else sw, round_out=last_stage, name=f"encoder.swin_reduce.{i}")
+                continue
+            t = plan.new_act(N, 1, f.H, f.W, 256)
+            plan.linear(f, pk, t, round_out=True, name=f"encoder.swin_reduce.{i}")
+            for ci, (conv, bn) in enumerate(convs):
+                Ho = (t.H + 2 - 3) // 2 + 1
+                final = ci == len(convs) - 1
+                o = sw if final else plan.new_act(N, 1, Ho, Ho, 256)
+                plan.conv(t, E.pack_conv(conv.weight, conv.bias, bn, dev), E.conv_taps(1, 3, 3, 0, 1, 1), o,
+                          stride=(1, 2, 2), act=ACT_RELU, residual=(sw if (final and not first) else None),
+                          res_after_act=True, round_out=(not final) or last_stage, name=f"encoder.swin_down.{i}.{ci}")
+                t = Act(o.buf, N, 1, Ho, Ho, 256, o.c0)
+    else:
+        plan.linear(feats[-1], E.pack_conv(enc.swin_reduce.weight, enc.swin_reduce.bias, None, dev), sw, round_out=True,
+                    name="encoder.swin_reduce")
+    x = cat
+    plan.taps.update(resnet=cat.channels(0, 256), swin_sum=sw, swin=feats, pre_cva=cat)
+    if net.USE_CROSS_VIEW_ATTENTION:
+        x = lower_cva(plan, enc.cross_view_attention, cat, B, V)
+    plan.taps["post_cva"] = x
+    seq = [("fusion_layer", enc.fusion_layer), ("layer1", enc.layer1), ("layer2", enc.layer2), ("layer3", enc.layer3)]
+    for li, (nm, layer) in enumerate(seq):
+        o = plan.new_act(N, 1, 7, 7, 256)
+        plan.conv(x, E.pack_conv(layer[0].weight, layer[0].bias, layer[1], dev), E.conv_taps(1, 3, 3, 0, 1, 1), o,
+                  act=ACT_RELU, round_out=li < len(seq) - 1, name="encoder." + nm)
+        x = o
+    return x
+
+
+# --------------------------------------------------------------------------------------------------
+# Decoder (models/decoder.py:48-99)
+# --------------------------------------------------------------------------------------------------
+def _convT_layer(plan, x, conv, bn, pads, out, name, act=ACT_RELU, residual=None, round_out=True, n_logical=None,
+                 block_n=None, epi_tail=None, out_elem_map=None, out_scale=1.0):
+    """stride-2 ConvTranspose3d as 8 parity-class implicit GEMMs; out dims are 2x the input dims."""
+    dev = _dev(plan)
+    od, oh, ow = 2 * x.D, 2 * x.H, 2 * x.W
+    Cs = out.Cs if isinstance(out, Act) else 1
+    for pd in (0, 1):
+        for ph in (0, 1):
+            for pw in (0, 1):
+                pk, taps = E.pack_convT_class(conv.weight, bn, dev, pads, (pd, ph, pw), n_logical=n_logical,
+                                              block_n=block_n, bias=conv.bias)
+                vox = (pd * oh + ph) * ow + pw
+                omap = (out.c0 + vox * Cs, od * oh * ow * Cs, 2 * oh * ow * Cs, 2 * ow * Cs, 2 * Cs)
+                tail = None
+                if epi_tail is not None:
+                    aux, out2 = epi_tail
+                    tail = (aux, out2, (vox, od * oh * ow, 2 * oh * ow, 2 * ow, 2))
+                plan.conv(x, pk, taps, out, out_map=omap, rows_dhw=(x.D, x.H, x.W), act=act, residual=residual,
+                          res_after_act=True, round_out=round_out, out_scale=out_scale, epi_tail=tail,
+                          name=f"{name}.p{pd}{ph}{pw}")
+    return out
+
+
+def lower_decoder(plan, dec, feat, N):
+    """feat: Act [N,7,7,256].  Returns (raw16 Act [N,32,32,32,16] with 9 live channels, coarse [N, 32768])."""
+    dev = _dev(plan)
+    g = plan.new_act(N, 2, 2, 2, 256)
+    # AdaptiveAvgPool2d 7->2 = windows [0,4) and [3,7); the new depth axis replicates (stride_d = 0)
+    src = Act(feat.buf, N, 1, 7, 7, 256, feat.c0)
+    plan.pool(src, g, (1, 4, 4), (0, 3, 3), (0, 0, 0), POOL_AVG, round_out=True, name="decoder.spatial_reduce")
+    x = g
+    for li, (layer, pads, cout) in enumerate(((dec.layer1, (2, 1, 1), 128), (dec.layer2, (1, 1, 1), 64),
+                                              (dec.layer3, (1, 1, 1), 32))):
+        o = plan.new_act(N, 2 * x.D, 2 * x.H, 2 * x.W, cout)
+        _convT_layer(plan, x, layer[0], layer[1], pads, o, f"decoder.layer{li + 1}")
+        x = o
+    raw = plan.new_act(N, 32, 32, 32, 16)
+    coarse = plan.empty(N, 32768)
+    l5 = dec.layer5[0]
+    w5 = torch.zeros(9)
+    w5[:8] = l5.weight.detach().float().reshape(8).cpu()
+    if l5.bias is not None:
+        w5[8] = l5.bias.detach().float().cpu()[0]
+    _convT_layer(plan, x, dec.layer4[0], dec.layer4[1], (1, 1, 1), raw, "decoder.layer4+5", n_logical=16, block_n=16,
+                 epi_tail=(w5.to(dev), coarse))
+    return raw, coarse
+
+
+# --------------------------------------------------------------------------------------------------
+# Merger (models/merger.py:56-107)
+# --------------------------------------------------------------------------------------------------
+def lower_merger(plan, mer, raw, coarse, B, V):
+    """raw: Act [N,32,32,32,16] (9 live channels, TF32-rounded, pad channels zero); coarse: [N,32768] tensor.
+    Returns merged [B, 32768] tensor."""
+    dev = _dev(plan)
+    N = B * V
+    slope = float(mer.cfg.NETWORK.LEAKY_VALUE)
+    taps = E.conv_taps(3, 3, 3, 1, 1, 1)
+    cat = plan.new_act(N, 32, 32, 32, 64)
+    x = raw
+    for i, layer in enumerate((mer.layer1, mer.layer2, mer.layer3, mer.layer4)):
+        o = cat.channels(16 * i, 16)
+        plan.conv(x, E.pack_conv(layer[0].weight, layer[0].bias, layer[1], dev, cin_pad=16, n_logical=16, block_n=16), taps, o,
+                  act=ACT_LEAKY, act_param=slope, round_out=True, name=f"merger.layer{i + 1}")
+        x = o
+    # layer5 sees cat(w1..w4): reference channel 9*g + c lives at 16*g + c here
+    w5 = mer.layer5[0].weight.detach().float()
+    w5p = torch.zeros(9, 64, 3, 3, 3, device=w5.device)
+    for gi in range(4):
+        w5p[:, 16 * gi:16 * gi + 9] = w5[:, 9 * gi:9 * gi + 9]
+    t = plan.new_act(N, 32, 32, 32, 16)
+    plan.conv(cat, E.pack_conv(w5p, mer.layer5[0].bias, mer.layer5[1], dev, cin_pad=64, n_logical=16, block_n=16), taps, t,
+              act=ACT_LEAKY, act_param=slope, round_out=True, name="merger.layer5")
+    wts = plan.empty(N, 32768)
+    wact = Act(wts.view(-1, 1), N, 32, 32, 32, 1, 0)
+    pk6 = E.pack_conv(mer.layer6[0].weight, mer.layer6[0].bias, mer.layer6[1], dev, cin_pad=16, block_n=16)
+    plan.conv(t, pk6, taps, wact, act=ACT_LEAKY, act_param=slope, name="merger.layer6")
+    merged = plan.empty(B, 32768)
+    plan.merger_fuse(wts, coarse, merged, B, V, 32768, name="merger.softmax_fuse")
+    return merged, wts
+
+
+# --------------------------------------------------------------------------------------------------
+# Refiner (models/refiner.py:72-106)
+# --------------------------------------------------------------------------------------------------
+def lower_refiner(plan, ref, vol, B):
+    """vol: [B, 32768] fp32 tensor (planar 32^3).  Returns refined [B, 32768]."""
+    dev = _dev(plan)
+    slope = float(ref.cfg.NETWORK.LEAKY_VALUE)
+    # layer1: Conv3d(1,32,k4,p2) -> 33^3, MaxPool3d(2) floors to 16^3: only conv outputs 0..31 are ever used
+    cols = plan.im2col(vol, (32768, 0, 1024, 32, 1), B, 1, (32, 32, 32), (4, 4, 4), 1, (2, 2, 2), (32, 32, 32), 64,
+                       name="refiner.layer1.im2col")
+    c1 = ref.layer1[0]
+    w, b = E.fold_bn(c1.weight, c1.bias, ref.layer1[1])
+    f32 = plan.new_act(B, 32, 32, 32, 32)
+    plan.linear(cols, E.pack_matrix(w.reshape(32, 64), b, dev), f32, act=ACT_LEAKY, act_param=slope, name="refiner.layer1")
+    l16 = plan.new_act(B, 16, 16, 16, 32)
+    plan.pool(f32, l16, (2, 2, 2), (2, 2, 2), (0, 0, 0), POOL_MAX, round_out=True, name="refiner.layer1.pool")
+    x, skips = l16, [l16]
+    for li, (layer, cout) in enumerate(((ref.layer2, 64), (ref.layer3, 128))):
+        full = plan.new_act(B, x.D, x.H, x.W, cout)   # conv outputs 0..D-1 of the (D+1)^3 the reference computes
+        plan.conv(x, E.pack_conv(layer[0].weight, layer[0].bias, layer[1], dev), E.conv_taps(4, 4, 4, 2, 2, 2), full,
+                  act=ACT_LEAKY, act_param=slope, name=f"refiner.layer{li + 2}")
+        p = plan.new_act(B, x.D // 2, x.H // 2, x.W // 2, cout)
+        plan.pool(full, p, (2, 2, 2), (2, 2, 2), (0, 0, 0), POOL_MAX, round_out=True, name=f"refiner.layer{li + 2}.pool")
+        skips.append(p)
+        x = p
+    l4 = x  # [B,4,4,4,128] == [B, 8192] in (d,h,w,c) order; the reference flattens (c,d,h,w)
+    fc4, fc5 = ref.layer4[0], ref.layer5[0]
+    w4 = fc4.weight.detach().float().view(2048, 128, 64).permute(0, 2, 1).reshape(2048, 8192)
+    h = plan.new_act(B, 1, 1, 1, 2048)
+    flat = Act(l4.buf.view(B, 8192), B, 1, 1, 1, 8192, 0)
+    plan.linear(flat, E.pack_matrix(w4, fc4.bias, dev, block_n=32), h, act=ACT_RELU, round_out=True, name="refiner.layer4")
+    w5 = fc5.weight.detach().float().view(128, 64, 2048).permute(1, 0, 2).reshape(8192, 2048)
+    b5 = fc5.bias.detach().float().view(128, 64).t().reshape(8192)
+    r4buf = plan.empty(B * 64, 128)
+    r4 = Act(r4buf, B, 4, 4, 4, 128, 0)
+    plan.linear(h, E.pack_matrix(w5, b5, dev, block_n=32), Act(r4buf.view(B, 8192), B, 1, 1, 1, 8192, 0), act=ACT_RELU,
+                residual=flat, res_after_act=True, round_out=True, name="refiner.layer5+skip")
+    r8 = plan.new_act(B, 8, 8, 8, 64)
+    _convT_layer(plan, r4, ref.layer6[0], ref.layer6[1], (1, 1, 1), r8, "refiner.layer6", residual=skips[1])
+    r16 = plan.new_act(B, 16, 16, 16, 32)
+    _convT_layer(plan, r8, ref.layer7[0], ref.layer7[1], (1, 1, 1), r16, "refiner.layer7", residual=skips[0])
+    out = plan.empty(B, 32768)
+    oact = Act(out.view(-1, 1), B, 32, 32, 32, 1, 0)
+    vact = Act(vol.view(-1, 1), B, 32, 32, 32, 1, 0)
+    _convT_layer(plan, r16, ref.layer8[0], None, (1, 1, 1), oact, "refiner.layer8", act=ACT_NONE, residual=vact,
+                 round_out=False, block_n=16, out_scale=0.5)
+    return out

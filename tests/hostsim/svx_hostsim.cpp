@@ -93,7 +93,7 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
       const long long off = d.o_base + n * d.o_sn + od * d.o_sd + oh * d.o_sh + ow * d.o_sw;
       float x[16];
       if (d.epi_mode == SVX_EPI_DEC_TAIL) {
-        float g = 0.f;
+        float g = d.epi_aux[8];
         for (int j = 0; j < 8; ++j) {
           float acc = 0.f;
           const float* w = d.W + (long long)j * d.Kpad;

@@ -13,26 +13,7 @@ from swinvox_b200 import engine as E
 
 
 
-@pytest.fixture(params=[pytest.param("hostsim"), pytest.param("cuda", marks=pytest.mark.gpu)])
-def dev(request, hostsim):
-    from swinvox_b200 import _lib
-    saved = _lib._lib
-    if request.param == "hostsim":
-        _lib._lib = hostsim
-        yield "cpu"
-    else:
-        if not torch.cuda.is_available():
-            pytest.skip("no CUDA device")
-        _lib._lib = None
-        _lib.get()
-        yield "cuda"
-    _lib._lib = saved
-
-
-def sync(dev):
-    if dev == "cuda":
-        torch.cuda.synchronize()
-
+from util import dev, sync  # noqa: F401  (dual-backend fixture)
 
 
 def rel_err(got, ref):
@@ -195,7 +176,7 @@ def test_decoder_tail_epilogue(dev):
     x = E.tf32_round(torch.randn(2, 32, 4, 4, 4))
     ct = torch.nn.ConvTranspose3d(32, 8, 4, 2, 1, bias=False)
     bn = rand_bn(torch.nn.BatchNorm3d(8))
-    w5 = torch.randn(8)
+    w5 = torch.randn(9)
     p = E.Plan(DEV)
     raw = p.new_act(2, 8, 8, 8, 16)
     coarse = p.empty(2, 512)
@@ -212,7 +193,7 @@ def test_decoder_tail_epilogue(dev):
     sync(DEV)
     wf, bf = E.fold_bn(ct.weight.transpose(0, 1), None, bn)
     feat = F.relu(F.conv_transpose3d(x.double(), E.tf32_round(wf).transpose(0, 1).double(), bf.double(), 2, 1))
-    gen = (feat * w5.double().view(1, 8, 1, 1, 1)).sum(1)
+    gen = (feat * w5[:8].double().view(1, 8, 1, 1, 1)).sum(1) + w5[8].double()
     got = to_nchw(raw)
     assert rel_err(coarse.view(2, 8, 8, 8), gen) < 1e-4
     assert rel_err(got[:, :8], feat) < 6e-4

@@ -1,0 +1,182 @@
+"""Parity of the drop-in modules (swinvox_b200/models/*.py) with the oracle and with the golden vectors of the real
+reference, per stage, through the reference's own calling convention (core/test.py:120-130).  Each test runs on
+`hostsim` (CPU tier: checks lowering, weight re-layout, plan construction) and on `cuda` (gpu tier: the sm_100a
+kernels through the C-ABI)."""
+import pytest
+import torch
+
+from oracle import fixtures as FX
+from oracle import modules as M
+from swinvox_b200.models import CrossViewAttention, Decoder, Encoder, Merger, Refiner, SwinTransformer
+from util import RTOL_DEEP, RTOL_INTERNAL, dev, golden, stage_check, sync, voxel_check  # noqa: F401
+
+PRODUCT = dict(encoder=Encoder, decoder=Decoder, merger=Merger, refiner=Refiner)
+CFGS = {
+    "default": (dict(), 1, 2),
+    "single_stage_nocva": (dict(USE_SWIN_T_MULTI_STAGE=False, SWIN_T_STAGES=[3], USE_CROSS_VIEW_ATTENTION=False), 1, 1),
+}
+
+
+def nchw(act):
+    return act.view().squeeze(1).permute(0, 3, 1, 2)
+
+
+def oracle_forward(mods, images):
+    taps = {}
+    with torch.no_grad():
+        f = mods["encoder"](images, taps)
+        raw, gen = mods["decoder"](f)
+        m = mods["merger"](raw, gen, taps)
+        v = mods["refiner"](m, taps)
+    taps.update(encoder=f, raw=raw, gen=gen, merged=m, final=v)
+    return taps
+
+
+@pytest.mark.parametrize("tag", list(CFGS))
+def test_pipeline_parity_with_oracle_and_reference_golden(dev, tag):
+    over, B, V = CFGS[tag]
+    cfg = M.default_cfg(**over)
+    ref = oracle_forward(FX.build(cfg, "calibrated", 0), FX.structured_inputs(B, V, seed=1234))
+    prod = FX.build(cfg, "calibrated", 0, PRODUCT)
+    for m in prod.values():
+        m.to(dev)
+    images = FX.structured_inputs(B, V, seed=1234).to(dev)
+    with torch.no_grad():  # the reference's calling sequence, core/test.py:120-130
+        f = prod["encoder"](images)
+        raw, gen = prod["decoder"](f)
+        merged = prod["merger"](raw, gen)
+        final = prod["refiner"](merged)
+    sync(dev)
+    plan = next(iter(prod["encoder"]._plans.values()))[0]
+    reports = [stage_check("resnet branch", nchw(plan.taps["resnet"]), ref["resnet"], RTOL_DEEP)]
+    sw_ref = ref["swin"] if isinstance(ref["swin"], list) else [ref["swin"]]
+    for i, (a, b) in enumerate(zip(plan.taps["swin"], sw_ref)):
+        reports.append(stage_check(f"swin stage {i}", nchw(a), b, RTOL_DEEP))
+    reports.append(stage_check("post_cva", nchw(plan.taps["post_cva"]).reshape(ref["post_cva"].shape), ref["post_cva"], RTOL_DEEP))
+    reports.append(stage_check("encoder", f, ref["encoder"], RTOL_DEEP))
+    reports.append(stage_check("decoder.raw", raw, ref["raw"]))
+    reports.append(stage_check("decoder.gen", gen, ref["gen"]))
+    reports.append(stage_check("merger.weights", prod["merger"].last_volume_weights, ref["merger_weights"], RTOL_INTERNAL))
+    reports.append(stage_check("merger", merged, ref["merged"]))
+    reports.append(stage_check("refiner", final, ref["final"]))
+    # ... and against what the unmodified reference produced in the build container
+    g = golden(tag)
+    reports.append(stage_check("encoder vs reference golden", f, torch.from_numpy(g["encoder"]), RTOL_DEEP))
+    reports.append(stage_check("merged vs reference golden", merged, torch.from_numpy(g["merged"])))
+    reports.append(stage_check("final vs reference golden", final, torch.from_numpy(g["final"])))
+    vox = voxel_check(final, torch.from_numpy(g["final"]), FX.seeded_gt(B))
+    print("\n".join(reports))
+    print("voxels (th, mismatch, out-of-band mismatch, dIoU):", vox)
+
+
+def test_modules_accept_foreign_tensors(dev):
+    """each module alone, fed plain contiguous NCHW tensors as a reference caller would"""
+    cfg = M.default_cfg()
+    ora = FX.build(cfg, "calibrated", 0)
+    ref = oracle_forward(ora, FX.structured_inputs(1, 2, seed=1234))
+    prod = FX.build(cfg, "calibrated", 0, PRODUCT)
+    with torch.no_grad():
+        dec, mer, rf = prod["decoder"].to(dev), prod["merger"].to(dev), prod["refiner"].to(dev)
+        raw, gen = dec(ref["encoder"].to(dev))
+        stage_check("decoder.raw", raw, ref["raw"])
+        stage_check("decoder.gen", gen, ref["gen"])
+        merged = mer(ref["raw"].to(dev), ref["gen"].to(dev))
+        stage_check("merger", merged, ref["merged"])
+        stage_check("refiner", rf(ref["merged"].to(dev)), ref["final"])
+        # foreign input after a chained call must not disturb the upstream module's output buffer
+        keep = raw.clone()
+        dec(torch.zeros_like(ref["encoder"]).to(dev))
+        mer(raw, gen)
+        dec2 = dec(ref["encoder"].to(dev))[0]
+        assert torch.equal(dec2, keep)
+        cva_ref = ora["encoder"].cross_view_attention
+        cva = CrossViewAttention(cfg, 512)
+        cva.load_state_dict(cva_ref.state_dict())
+        cva.eval().to(dev)
+        stage_check("cross_view_attention", cva(ref["pre_cva"].to(dev)), ref["post_cva"], RTOL_DEEP)
+    sync(dev)
+
+
+def test_swin_wrapper_outputs(dev):
+    cfg = M.default_cfg()
+    ora = FX.build(cfg, "calibrated", 0)["encoder"].swin_transformer
+    sw = SwinTransformer(cfg, 3, 224, pretrained=False)
+    sw.load_state_dict(ora.state_dict())
+    sw.eval().to(dev)
+    x = FX.structured_inputs(1, 1, seed=5)[0]
+    with torch.no_grad():
+        ref, got = ora(x), sw(x.to(dev))
+    assert isinstance(got, list) and len(got) == 4
+    for i, (a, b) in enumerate(zip(got, ref)):
+        assert tuple(a.shape) == tuple(b.shape)
+        stage_check(f"swin wrapper stage {i}", a, b, RTOL_DEEP)
+    single = M.default_cfg(USE_SWIN_T_MULTI_STAGE=False, SWIN_T_STAGES=[3])
+    sw1 = SwinTransformer(single, 3, 224, pretrained=False).eval()
+    assert sw1.out_channels == [768] and sw1.out_spatial == [7]
+
+
+@pytest.mark.gpu
+def test_batched_multi_view_parity_gpu():
+    """B=2 objects x V=3 views (the metric's view count); views of one object interact only through CVA / merger"""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = M.default_cfg()
+    images = FX.structured_inputs(2, 3, seed=77)
+    ref = oracle_forward(FX.build(cfg, "calibrated", 0), images)
+    prod = FX.build(cfg, "calibrated", 0, PRODUCT)
+    with torch.no_grad():
+        for m in prod.values():
+            m.cuda()
+        f = prod["encoder"](images.cuda())
+        raw, gen = prod["decoder"](f)
+        final = prod["refiner"](prod["merger"](raw, gen))
+        # replaying the cached plans (second call, CUDA graph) must give the same bits
+        for m in prod.values():
+            m.use_graph = True
+        for _ in range(2):
+            f2 = prod["encoder"](images.cuda())
+            raw2, gen2 = prod["decoder"](f2)
+            final2 = prod["refiner"](prod["merger"](raw2, gen2))
+    torch.cuda.synchronize()
+    stage_check("encoder", f, ref["encoder"], RTOL_DEEP)
+    stage_check("refiner", final, ref["final"])
+    voxel_check(final, ref["final"], FX.seeded_gt(2))
+    assert torch.equal(final2, final)
+
+
+def test_eval_only_guards(dev):
+    cfg = M.default_cfg()
+    ref = Refiner(cfg).to(dev)
+    x = torch.zeros(1, 32, 32, 32, device=dev)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        ref.train()(x)
+    with pytest.raises(RuntimeError, match="no_grad"):
+        ref.eval()(x)
+    with torch.no_grad(), pytest.raises(ValueError):
+        ref(torch.zeros(1, 16, 16, 16, device=dev))
+
+
+def test_cpu_tensor_is_rejected_loudly():
+    """no CPU fallback: the real package refuses CPU tensors"""
+    from swinvox_b200 import _lib
+    with torch.no_grad(), pytest.raises(_lib.SvxError, match="no CPU fallback"):
+        Refiner(M.default_cfg()).eval()(torch.zeros(1, 32, 32, 32))
+
+
+@pytest.mark.parametrize("over", [dict(), dict(USE_SWIN_T_MULTI_STAGE=False, SWIN_T_STAGES=[3]),
+                                  dict(SWIN_T_STAGES=[2, 3], USE_CROSS_VIEW_ATTENTION=False),
+                                  dict(TCONV_USE_BIAS=True, ATT_SPATIAL_DOWNSAMPLE_RATIO=1)])
+def test_state_dict_layout_matches_reference(over):
+    """keys, order and shapes equal the oracle's, which make_golden.py pinned to the real reference modules;
+    strict load works both ways and with DataParallel's `module.` prefix stripped"""
+    cfg = M.default_cfg(**over)
+    torch.manual_seed(0)
+    pairs = [(Encoder(cfg), M.RefEncoder(cfg)), (Decoder(cfg), M.RefDecoder(cfg)), (Merger(cfg), M.RefMerger(cfg)),
+             (Refiner(cfg), M.RefRefiner(cfg))]
+    for mine, ref in pairs:
+        a, b = mine.state_dict(), ref.state_dict()
+        assert list(a) == list(b), type(mine).__name__
+        assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+        mine.load_state_dict(b, strict=True)
+        ref.load_state_dict(mine.state_dict(), strict=True)
+        assert sum(p.numel() for p in mine.parameters()) == sum(p.numel() for p in ref.parameters())
