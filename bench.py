@@ -1,0 +1,281 @@
+"""bench.py -- objects/sec of the SwinVox multi-view reconstruction forward (3 views 224x224 -> 32^3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--views V]
+
+One "step" = one pass of the hot path over one batch of synthetic input: encoder -> decoder -> merger -> refiner ->
+threshold/IoU counters (core/test.py:120-164) on B objects x V views per GPU (BASELINE.json configs[1]: batch 64 x
+3 views, merger + refiner, fp32/TF32).  N>1 is launched by torchrun, one rank per GPU; objects are sharded (weak
+scaling: B per GPU fixed) and the only exchange is the NCCL all_gather of logits + counters inside the timed region.
+`--impl reference` times the reference's CPU forward (the oracle port, bit-exact to /root/reference/models/*.py)
+on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "objects/sec, 3 views 224^2 -> 32^3"
+# algorithmic FLOPs (2*MAC) of the reference forward per object: 19.382*V + 2.485 GFLOP with CVA on
+GF_PER_VIEW, GF_PER_OBJECT = 19.382, 2.485
+GF_ATTENTION_PER_VIEW = 0.280 + 0.0561   # window-attention bmm + CVA: run outside the contraction kernel
+
+
+def rank_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons of one GPU during the timed region (NVML)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {pynvml.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.02)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def synthetic_batch(B, V, seed):
+    g = torch.Generator().manual_seed(seed)
+    images = torch.rand(B, V, 3, 224, 224, generator=g) * 2 - 1
+    gt = (torch.rand(B, 32, 32, 32, generator=g) < 0.1).float()
+    return images, gt
+
+
+def cpu_reference_rate(V, seconds_budget, sample_objects=2):
+    """reference CPU forward (oracle port) on all host cores; returns (objects/sec, cores, description)"""
+    from oracle import modules as M
+    torch.set_num_threads(os.cpu_count())
+    cfg = M.default_cfg()
+    torch.manual_seed(0)
+    enc, dec, mer, ref = M.RefEncoder(cfg).eval(), M.RefDecoder(cfg).eval(), M.RefMerger(cfg).eval(), M.RefRefiner(cfg).eval()
+    images, gt = synthetic_batch(sample_objects, V, 1)
+    with torch.no_grad():
+        def step():
+            vol = M.forward_pipeline(enc, dec, mer, ref, images, cfg)
+            return M.voxel_metrics(vol, gt)
+        step()  # warm-up
+        t0, n = time.perf_counter(), 0
+        while True:
+            step()
+            n += 1
+            if time.perf_counter() - t0 > seconds_budget or n >= 50:
+                break
+        dt = (time.perf_counter() - t0) / n
+    return sample_objects / dt, os.cpu_count(), f"{n} timed passes of {sample_objects} objects x {V} views (after 1 warm-up)"
+
+
+def run_reference(args):
+    rank, _, world = rank_env()
+    if rank != 0:
+        return
+    from oracle import modules as M
+    torch.set_num_threads(os.cpu_count())
+    cfg = M.default_cfg()
+    torch.manual_seed(0)
+    enc, dec, mer, ref = M.RefEncoder(cfg).eval(), M.RefDecoder(cfg).eval(), M.RefMerger(cfg).eval(), M.RefRefiner(cfg).eval()
+    sample = args.ref_sample
+    images, gt = synthetic_batch(sample, args.views, 1)
+    with torch.no_grad():
+        def step():
+            vol = M.forward_pipeline(enc, dec, mer, ref, images, cfg)
+            return M.voxel_metrics(vol, gt)
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = (time.perf_counter() - t0) / args.steps
+    value = sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"batch {args.batch} x {args.views} views, merger + refiner, CVA on (BASELINE configs[1])",
+                   "step": f"bounded sample: {sample} objects x {args.views} views per step on the host CPU"},
+        "cpu_baseline": {"value": value, "unit": "objects/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{args.steps} steps of {sample} objects x {args.views} views, {os.cpu_count()} threads"},
+        "e2e": {"value": value, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from swinvox_b200 import config as svx_config
+    from swinvox_b200.metrics import VoxelMetrics
+    from swinvox_b200.pipeline import DataParallelReconstructor, Reconstructor
+    rank, local_rank, world = rank_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (swinvox_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, V = args.batch, args.views
+    cfg = svx_config.make_cfg()
+    torch.manual_seed(0)
+    rec = Reconstructor(cfg, device=dev)   # random-init weights of the reference architecture
+    rec.set_graph(not args.no_graph)
+    dp = DataParallelReconstructor(rec)
+    images_h, gt_h = synthetic_batch(B, V, 100 + rank)
+    images_h, gt_h = images_h.pin_memory(), gt_h.pin_memory()
+    inbuf = rec.input_buffer(B, V)
+    inbuf.copy_(images_h)
+    gt_d = gt_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return dp.evaluate_local(inbuf, gt_d)
+
+    # ---- device-resident throughput ------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = ms.item() / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+
+    # ---- end to end: pinned host images in, logits + counters out, every step ------------------------------
+    logits_h = torch.empty(B, 32, 32, 32).pin_memory()
+    counts_h = torch.empty(B, len(cfg.TEST.VOXEL_THRESH), 5, dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        inbuf.copy_(images_h, non_blocking=True)
+        logits, counts = rec.evaluate(inbuf, gt_d)
+        logits_h.copy_(logits, non_blocking=True)
+        counts_h.copy_(counts, non_blocking=True)
+        torch.cuda.synchronize()
+        return VoxelMetrics.scores(counts_h)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = B * world / (e2e_s.item() / args.steps)
+
+    # ---- roofline of the dominant kernel (the tcgen05 contraction kernel), measured live with CUDA events -------
+    gemm_ms, total_ms, breakdown = 0.0, 0.0, []
+    for mod in rec.modules():
+        for entry in mod._plans.values():
+            plan = entry[0]
+            times = plan.time_ops(iters=3)
+            for nm, t, fl in zip(plan.op_names, times, plan.flops):
+                total_ms += t
+                is_gemm = fl > 0 and not nm.endswith(".attn")
+                if is_gemm:
+                    gemm_ms += t
+                breakdown.append((nm, t, fl))
+    algo_gf = B * ((GF_PER_VIEW - GF_ATTENTION_PER_VIEW) * V + GF_PER_OBJECT)
+    achieved = algo_gf / gemm_ms if gemm_ms > 0 else 0.0   # GFLOP / ms = TFLOP/s
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak = bf16_peak / 2.0   # kind::tf32 runs at half the bf16 rate; MEASURED_PEAKS.json has no tf32 entry
+    n_gemm = sum(1 for nm, t, fl in breakdown if fl > 0 and not nm.endswith(".attn"))
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "gemm_tf32_kernel", "launches_per_step": n_gemm,
+                "kernel_ms_per_step": gemm_ms, "all_kernels_ms_per_step": total_ms,
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32), of measured" if peaks
+                                else "fallback 1.4 PFLOP/s sustained bf16 / 2 (tf32), of fallback")}
+
+    if rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "op_breakdown.json"), "w") as fh:
+            json.dump(sorted(breakdown, key=lambda r: -r[1]), fh, indent=0)
+        cpu_value, cores, sample = cpu_reference_rate(V, args.cpu_seconds) if world == 1 else (None, None, None)
+        line = {
+            "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": f"batch {B} x {V} views per GPU, merger + refiner, CVA on, 224x224 -> 32^3 "
+                                   "(BASELINE configs[1])",
+                       "l2": "per-step working set (activations) is several GB, far larger than the 126 MB L2",
+                       "cuda_graph": not args.no_graph, "weights": "random init (reference architecture)"},
+            "e2e": {"value": e2e_value, "unit": "objects/s", "h2d_bytes_per_step": images_h.numel() * 4,
+                    "d2h_bytes_per_step": logits_h.numel() * 4 + counts_h.numel() * 4},
+            "gpu_launches": rec.num_launches() * args.steps,
+            "clocks": sampler.summary(),
+            "roofline": roofline,
+        }
+        if cpu_value is not None:
+            line["cpu_baseline"] = {"value": cpu_value, "unit": "objects/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="objects per GPU")
+    ap.add_argument("--views", type=int, default=3)
+    ap.add_argument("--ref-sample", type=int, default=4, help="objects per reference-arm step (bounded CPU sample)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget inside the default run")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,44 @@
+"""Threshold + IoU / F-score of the evaluation loop (reference core/test.py:141-164), batched on the device:
+one kernel produces the integer counters {I, U, TP, FP, FN} per object and threshold; the float formulas (with the
+reference's epsilons and its union == 0 convention) are applied to those counters on the host."""
+import torch
+
+from . import engine as E
+from .models._base import require_device
+
+
+class VoxelMetrics:
+    def __init__(self, thresholds=(0.2, 0.3, 0.4, 0.5)):
+        self.thresholds = [float(t) for t in thresholds]
+        self._plans = {}
+
+    def counts(self, logits, gt):
+        """logits, gt: [B,32,32,32] (or [B,P]) fp32 on the GPU -> int32 [B, T, 5] = I, U, TP, FP, FN (device)"""
+        require_device(logits)
+        B = logits.shape[0]
+        P = logits[0].numel()
+        key = (B, P, str(logits.device), logits.data_ptr(), gt.data_ptr())
+        if key not in self._plans:
+            plan = E.Plan(logits.device)
+            th = torch.tensor(self.thresholds, dtype=torch.float32, device=logits.device)
+            counts = plan.zeros(B, len(self.thresholds), 5, dtype=torch.int32)
+            lg, g = logits.reshape(B, P), gt.reshape(B, P)
+            if not (lg.is_contiguous() and g.is_contiguous()):
+                raise ValueError("VoxelMetrics needs contiguous logits / ground truth")
+            plan.voxel_metrics(lg, g, th, counts, B, P)
+            if len(self._plans) > 8:
+                self._plans.clear()
+            self._plans[key] = (plan, counts)
+        plan, counts = self._plans[key]
+        plan.run()
+        return counts
+
+    @staticmethod
+    def scores(counts):
+        """counts [B,T,5] -> (iou [B,T], f1 [B,T]) with the reference's conventions (core/test.py:150-164)"""
+        c = counts.to(torch.float32)
+        inter, union, tp, fp, fn = c.unbind(-1)
+        iou = torch.where(union > 0, inter / union.clamp_min(1), torch.where(inter == 0, torch.ones_like(inter),
+                                                                             torch.zeros_like(inter)))
+        prec, rec = tp / (tp + fp + 1e-8), tp / (tp + fn + 1e-8)
+        return iou, 2 * prec * rec / (prec + rec + 1e-8)
