@@ -31,7 +31,7 @@ extern "C" {
 /* activation codes for svx_gemm_desc.act */
 enum { SVX_ACT_NONE = 0, SVX_ACT_RELU = 1, SVX_ACT_LEAKY = 2, SVX_ACT_GELU = 3 };
 /* A operand modes */
-enum { SVX_A_PLAIN = 0, SVX_A_GATHER = 1 };
+enum { SVX_A_PLAIN = 0, SVX_A_GATHER = 1, SVX_A_FLAT = 2 };
 /* special epilogues */
 enum { SVX_EPI_STD = 0, SVX_EPI_DEC_TAIL = 1 /* decoder layer4+layer5+cat, decoder.py:80-89 */ };
 /* pooling modes */
@@ -51,6 +51,11 @@ enum { SVX_POOL_MAX = 0, SVX_POOL_AVG = 1 };
  *                         ow*stride_w + taps[tap].w, in_c0 + c]
  *                 of a channels-last tensor with pixel stride in_Cs, zero outside the tensor.
  *                 Cin, in_c0, in_Cs must be multiples of 4 (16-byte cp.async chunks).
+ *   SVX_A_FLAT  : stride-1 convolution over a zero-PADDED channels-last tensor viewed as the matrix
+ *                 [N*in_D*in_H*in_W, in_Cs] (in_* are the padded extents).  Row r is the flat padded position
+ *                 of the window corner; tap t reads row r + (dd*in_H + dh)*in_W + dw (taps >= 0), streamed by
+ *                 TMA one 32-channel chunk at a time.  Cin must be a multiple of 32.  Rows decode over
+ *                 out_{D,H,W} = in_{D,H,W}; only rows with od < valid_D, oh < valid_H, ow < valid_W are stored.
  * W: [Npad, Kpad] fp32, K contiguous, zero padded, values pre-rounded to TF32 (rna) by the host.
  * result = out_scale * (res_after_act ? act(acc+bias) + res : act(acc+bias+res)).
  * Output row r is stored at out + o_base + n*o_sn + od*o_sd + oh*o_sh + ow*o_sw (elements),
@@ -62,13 +67,15 @@ typedef struct svx_gemm_desc {
   int32_t block_n;          /* N tile: 16, 32, 64, 96, 128, 192 or 256 */
   int32_t a_mode;
   const float* A;
-  int64_t lda;
+  int64_t lda;              /* plain: row stride (elements); flat: number of rows of the padded matrix */
   /* gather description */
   int32_t in_D, in_H, in_W, in_Cs, in_c0, Cin;
   int32_t out_D, out_H, out_W;
   int32_t stride_d, stride_h, stride_w;
   int32_t ntaps;
-  const int32_t* taps;      /* device int32[ntaps][4] = {dd, dh, dw, 0} */
+  const int32_t* taps;      /* device int32[ntaps][4] = {dd, dh, dw, 0} (gather mode) */
+  const int32_t* taps_host; /* the same table in host memory (flat mode; read at plan-build time only) */
+  int32_t valid_D, valid_H, valid_W; /* flat mode: extents of the rows that are real outputs (0 = all) */
   /* weights / epilogue */
   const float* W;
   const float* bias;        /* [Npad] or NULL */

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libswinvox_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU = 0, 1, 2, 3
-A_PLAIN, A_GATHER = 0, 1
+A_PLAIN, A_GATHER, A_FLAT = 0, 1, 2
 EPI_STD, EPI_DEC_TAIL = 0, 1
 POOL_MAX, POOL_AVG = 0, 1
 
@@ -24,7 +24,7 @@ class GemmDesc(C.Structure):
         ("in_D", i32), ("in_H", i32), ("in_W", i32), ("in_Cs", i32), ("in_c0", i32), ("Cin", i32),
         ("out_D", i32), ("out_H", i32), ("out_W", i32),
         ("stride_d", i32), ("stride_h", i32), ("stride_w", i32),
-        ("ntaps", i32), ("taps", ptr),
+        ("ntaps", i32), ("taps", ptr), ("taps_host", ptr), ("valid_D", i32), ("valid_H", i32), ("valid_W", i32),
         ("W", ptr), ("bias", ptr), ("residual", ptr), ("out", ptr),
         ("o_base", i64), ("o_sn", i64), ("o_sd", i64), ("o_sh", i64), ("o_sw", i64),
         ("act", i32), ("act_param", f32), ("res_after_act", i32), ("out_scale", f32),

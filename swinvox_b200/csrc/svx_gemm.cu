@@ -1,16 +1,20 @@
 // svx_gemm.cu -- the contraction engine of the SwinVox forward path on sm_100a.
 //
-// One warp-specialised kernel serves every Linear / Conv2d / Conv3d / ConvTranspose3d of the
-// reference (encoder.py:22-111, timm Swin linears, cross_view_attention.py:38-53,
-// decoder.py:24-46, merger.py:20-54, refiner.py:21-70):
+// One persistent, warp-specialised kernel serves every Linear / Conv2d / Conv3d / ConvTranspose3d of the
+// reference (encoder.py:22-111, timm Swin linears, cross_view_attention.py:38-53, decoder.py:24-46,
+// merger.py:20-54, refiner.py:21-70):
 //
-//   warp 0-3  epilogue   TMEM -> registers (tcgen05.ld) -> bias / residual / activation -> global
-//   warp 4    TMA        weights (and the A operand when it is a plain matrix) -> 128B-swizzled smem
+//   warp 0-3  epilogue   TMEM -> registers (tcgen05.ld) -> smem transpose -> bias / residual / activation ->
+//                        coalesced 128-byte row segments to global; overlaps the next tile's main loop through
+//                        a double-buffered TMEM accumulator
+//   warp 4    TMA        weights, and the A operand when it is a plain matrix or a pre-padded stride-1
+//                        convolution ("flat" mode: one shifted 2-D box per filter tap) -> 128B-swizzled smem
 //   warp 5    MMA        one elected thread issues tcgen05.mma kind::tf32, accumulating in TMEM
-//   warp 6-9  gather     implicit im2col: cp.async 16-byte chunks of channels-last pixels, written
-//                        with the same 128B swizzle TMA would produce, zero-filled at the borders
+//   warp 6-9  gather     strided / unpadded convolutions: cp.async 16-byte chunks of channels-last pixels written
+//                        with the 128B swizzle TMA would produce, zero-filled at the borders
 //
-// Tile: 128 (rows = output pixels) x BN (output channels) x 32 (fp32 k-chunk = one swizzle row).
+// Tile: 128 (rows = output pixels) x BN (output channels) x 32 (fp32 k-chunk = one swizzle row).  Grid = one CTA
+// per SM; tiles are dealt round-robin (n fastest, so CTAs that share an A tile run together and hit L2).
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -28,13 +32,20 @@ constexpr int UMMA_K = 8;
 constexpr int A_STAGE_BYTES = BM * BK * 4;
 constexpr int kThreads = 320;
 constexpr int kGatherLag = 2;
+constexpr int kMaxTaps = 64;
+constexpr int kSlab = 16;                        // accumulator columns per epilogue pass
+constexpr int kEpiWarps = 8;                     // warps 0-3, plus warps 6-9 when they are not gathering
+constexpr int kStagingBytes = kEpiWarps * 32 * kSlab * 4;  // per epilogue warp: 32 rows x 16 columns fp32
+constexpr int kOffBytes = kEpiWarps * 32 * 8;
 
 struct GemmParams {
-  int M, N, K, nk, tiles_n, a_mode;
+  int M, N, K, Npad, nk, tiles_n, tiles_m, a_mode;
   const float* A;
   int in_D, in_H, in_W, in_Cs, in_c0, Cin;
   int out_D, out_H, out_W;
+  int valid_D, valid_H, valid_W;
   int sd, sh, sw;
+  int chunks_per_tap;
   const int4* taps;
   const float* bias;
   const float* residual;
@@ -49,75 +60,169 @@ struct GemmParams {
   float* out2;
   long long o2_base, o2_sn, o2_sd, o2_sh, o2_sw;
   int vec_ok;
-  int consumer_fence;  // 1: the MMA thread issues the generic->async proxy fence (experiment)
+  int flat_off[kMaxTaps];  // flat mode: row offset of each tap
 };
 
 template <int BN>
 struct Cfg {
-  static constexpr int kStages = (BN > 64 && BN <= 128) ? 3 : 4;
   static constexpr int kBBytes = BN * BK * 4;
   static constexpr int kStageBytes = A_STAGE_BYTES + kBBytes;
-  static constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  static constexpr int kMinBlocks = (BN <= 128) ? 2 : 1;
-  // stages + 1024 alignment slack + barriers/tmem slot (256) + bias
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + BN * 4;
+  static constexpr int kCtasPerSm = BN <= 96 ? 2 : 1;   // two resident CTAs double the epilogue / gather warps
+  static constexpr int kStagesRaw = ((kCtasPerSm == 2 ? 92 : 196) * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+  static constexpr uint32_t kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  static_assert(kStages >= kGatherLag + 1, "the gather pipeline needs more stages than its lag");
+  // stages + 1024 alignment slack + barriers (256) + staging + row offsets
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kStagingBytes + kOffBytes;
 };
+
+// exact-erf GELU (nn.GELU()) with a branch-free erf: Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7, ~14 instructions
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float erf_abs = fmaf(-poly * t, e, 1.f);
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float x, float slope) {
+  if constexpr (ACT == SVX_ACT_RELU) return fmaxf(x, 0.f);
+  if constexpr (ACT == SVX_ACT_LEAKY) return x > 0.f ? x : x * slope;
+  if constexpr (ACT == SVX_ACT_GELU) return gelu_erf(x);
+  return x;
+}
 
 __device__ __forceinline__ float apply_act(float x, int act, float slope) {
   switch (act) {
-    case SVX_ACT_RELU: return fmaxf(x, 0.f);
-    case SVX_ACT_LEAKY: return x > 0.f ? x : x * slope;
-    case SVX_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    case SVX_ACT_RELU: return act_t<SVX_ACT_RELU>(x, slope);
+    case SVX_ACT_LEAKY: return act_t<SVX_ACT_LEAKY>(x, slope);
+    case SVX_ACT_GELU: return act_t<SVX_ACT_GELU>(x, slope);
     default: return x;
   }
 }
 
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// row index -> (valid, output offset); rows decode as (n, od, oh, ow) over the row-space extents
+__device__ __forceinline__ bool decode_row(const GemmParams& p, int r, long long& off, long long& off2) {
+  if (r >= p.M) return false;
+  const int ow = r % p.out_W;
+  int t = r / p.out_W;
+  const int oh = t % p.out_H;
+  t /= p.out_H;
+  const int od = t % p.out_D;
+  const int n = t / p.out_D;
+  if (p.valid_W > 0 && (ow >= p.valid_W || oh >= p.valid_H || od >= p.valid_D)) return false;
+  off = p.o_base + n * p.o_sn + od * p.o_sd + oh * p.o_sh + ow * p.o_sw;
+  off2 = p.o2_base + n * p.o2_sn + od * p.o2_sd + oh * p.o2_sh + ow * p.o2_sw;
+  return true;
+}
+
+
+// One epilogue pass of a warp over a staged 32 x SLAB accumulator block: every warp-wide access covers whole
+// 16*CP-byte row segments (coalesced), rows are processed G at a time so their loads overlap.
+template <int SLAB, int ACT>
+__device__ __forceinline__ void store_slab(const GemmParams& p, const float* staging, const long long* soff,
+                                           int lane, int jb) {
+  constexpr int CP = SLAB / 4;
+  constexpr int RP = 32 / CP;
+  constexpr int G = CP < 4 ? CP : 4;
+  const int ch = lane % CP;
+  const int col = jb + ch * 4;
+  const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool has_res = p.residual != nullptr;
+  const bool pre = has_res && !p.res_after_act;
+  const float slope = p.act_param, scale = p.out_scale;
+  const bool rnd = p.round_tf32 != 0;
+#pragma unroll
+  for (int i0 = 0; i0 < CP; i0 += G) {
+    long long ro[G];
+    bool ok[G];
+    float4 a4[G], r4[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int row = (i0 + i) * RP + lane / CP;
+      ro[i] = soff[row];
+      ok[i] = ro[i] >= 0 && col < p.N;
+      a4[i] = *reinterpret_cast<const float4*>(staging + row * SLAB + ((ch ^ (row & (CP - 1))) << 2));
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i)   // plain loads: out may alias the residual
+      r4[i] = (has_res && ok[i]) ? *reinterpret_cast<const float4*>(p.residual + ro[i] + col)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      float x[4] = {a4[i].x + b4.x, a4[i].y + b4.y, a4[i].z + b4.z, a4[i].w + b4.w};
+      const float rv[4] = {r4[i].x, r4[i].y, r4[i].z, r4[i].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float t = pre ? x[q] + rv[q] : x[q];
+        t = act_t<ACT>(t, slope);
+        if (!pre) t += rv[q];
+        t *= scale;
+        x[q] = rnd ? round_tf32(t) : t;
+      }
+      if (ok[i]) *reinterpret_cast<float4*>(p.out + ro[i] + col) = make_float4(x[0], x[1], x[2], x[3]);
+    }
+  }
+}
+
 template <int BN>
-__global__ void __launch_bounds__(kThreads, Cfg<BN>::kMinBlocks)
+__global__ void __launch_bounds__(kThreads, Cfg<BN>::kCtasPerSm)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const GemmParams p) {
+                 const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
   constexpr int S = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + S * C::kStageBytes;
-  // barrier layout: full[S], empty[S], tmem_full, then tmem slot, then bias
+  // barrier layout: full[S], empty[S], tmem_full[2], tmem_empty[2], tmem slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * S);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 1);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + S * C::kStageBytes + 8 * (2 * S + 1));
-  float* sbias = reinterpret_cast<float*>(smem_gen + S * C::kStageBytes + 256);
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
+  uint8_t* aux_gen = smem_gen + S * C::kStageBytes;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(aux_gen + 8 * (2 * S + 4));
+  float* staging_all = reinterpret_cast<float*>(aux_gen + 256);
+  long long* soff_all = reinterpret_cast<long long*>(aux_gen + 256 + kStagingBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tile_n = blockIdx.x % p.tiles_n;
-  const int tile_m = blockIdx.x / p.tiles_n;
-  const int m0 = tile_m * BM;
-  const int n0 = tile_n * BN;
   const int nk = p.nk;
-  const bool gather = p.a_mode == SVX_A_GATHER;
+  const int a_mode = p.a_mode;
+  const int num_tiles = p.tiles_m * p.tiles_n;
 
   // ---- one-time setup ---------------------------------------------------------------------
   if (warp == 4 && lane == 0) {
-    if (!gather) tma_prefetch_desc(&map_a);
+    if (a_mode != SVX_A_GATHER) tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
   }
   if (warp == 5) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(full_bar(s), gather ? 5u : 1u);
+        mbar_init(full_bar(s), a_mode == SVX_A_GATHER ? 5u : 1u);
         mbar_init(empty_bar(s), 1u);
       }
-      mbar_init(tmem_full_bar, 1u);
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tmem_full_bar(a), 1u);
+        mbar_init(tmem_empty_bar(a), a_mode == SVX_A_GATHER ? 4u : 8u);
+      }
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc<C::kTmemCols>(tmem_slot);
-  }
-  if (warp < 4) {
-    for (int j = threadIdx.x; j < BN; j += 128) sbias[j] = p.bias ? p.bias[n0 + j] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -127,19 +232,28 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 4) {
     // ---- TMA producer ---------------------------------------------------------------------
     if (lane == 0) {
-      for (int kc = 0; kc < nk; ++kc) {
-        const int s = kc % S;
-        const uint32_t ph = (kc / S) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t a_dst = smem_base + s * C::kStageBytes;
-        const uint32_t b_dst = a_dst + A_STAGE_BYTES;
-        if (!gather) {
-          mbar_arrive_expect_tx(full_bar(s), A_STAGE_BYTES + C::kBBytes);
-          tma_load_2d(a_dst, &map_a, full_bar(s), kc * BK, m0);
-        } else {
-          mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+        for (int kc = 0; kc < nk; ++kc, ++g) {
+          const int s = g % S;
+          const uint32_t ph = (g / S) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t a_dst = smem_base + s * C::kStageBytes;
+          const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+          if (a_mode == SVX_A_PLAIN) {
+            mbar_arrive_expect_tx(full_bar(s), A_STAGE_BYTES + C::kBBytes);
+            tma_load_2d(a_dst, &map_a, full_bar(s), kc * BK, m0);
+          } else if (a_mode == SVX_A_FLAT) {
+            mbar_arrive_expect_tx(full_bar(s), A_STAGE_BYTES + C::kBBytes);
+            const int tap = kc / p.chunks_per_tap;
+            const int cc = kc - tap * p.chunks_per_tap;
+            tma_load_2d(a_dst, &map_a, full_bar(s), p.in_c0 + cc * BK, m0 + p.flat_off[tap]);
+          } else {
+            mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
+          }
+          tma_load_2d(b_dst, &map_b, full_bar(s), kc * BK, n0);
         }
-        tma_load_2d(b_dst, &map_b, full_bar(s), kc * BK, n0);
       }
     }
     __syncwarp();
@@ -147,190 +261,201 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ---- MMA issuer -----------------------------------------------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
-      for (int kc = 0; kc < nk; ++kc) {
-        const int s = kc % S;
-        const uint32_t ph = (kc / S) & 1;
-        mbar_wait(full_bar(s), ph);
-        if (gather && p.consumer_fence) fence_proxy_async_smem();
+      uint32_t g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it & 1u;
+        mbar_wait(tmem_empty_bar(as), ((it >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_base + s * C::kStageBytes;
-        const uint64_t da = umma_desc_sw128(a_addr);
-        const uint64_t db = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+        const uint32_t acc = tmem_base + as * BN;
+        for (int kc = 0; kc < nk; ++kc, ++g) {
+          const int s = g % S;
+          const uint32_t ph = (g / S) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + s * C::kStageBytes;
+          const uint64_t da = umma_desc_sw128(a_addr);
+          const uint64_t db = umma_desc_sw128(a_addr + A_STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 8 fp32 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-          umma_tf32(tmem_base, da + 2u * k, db + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 8 fp32 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+            umma_tf32(acc, da + 2u * k, db + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
         }
-        umma_commit(empty_bar(s));
+        umma_commit(tmem_full_bar(as));
       }
-      umma_commit(tmem_full_bar);
     }
     __syncwarp();
-  } else if (warp >= 6) {
-    // ---- A gather producers (implicit im2col) ---------------------------------------------
-    if (gather) {
+  } else if (warp >= 6 && a_mode == SVX_A_GATHER) {
+    // ---- A gather producers (implicit im2col for strided / unpadded convolutions) ----------------------
+    {
       const int gw = warp - 6;
       const int j = lane & 7;      // 16-byte chunk inside the 128-byte k-row
       const int rsub = lane >> 3;  // row inside a group of 4
-      long long base[8];
-      int crd[8];  // zd | zh<<10 | zw<<20 | valid<<30
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = m0 + gw * 32 + i * 4 + rsub;
-        if (r < p.M) {
-          const int ow = r % p.out_W;
-          int t = r / p.out_W;
-          const int oh = t % p.out_H;
-          t /= p.out_H;
-          const int od = t % p.out_D;
-          const int n = t / p.out_D;
-          const int zd = od * p.sd, zh = oh * p.sh, zw = ow * p.sw;
-          base[i] = ((((long long)n * p.in_D + zd) * p.in_H + zh) * p.in_W + zw) * p.in_Cs;
-          crd[i] = zd | (zh << 10) | (zw << 20) | (1 << 30);
-        } else {
-          base[i] = 0;
-          crd[i] = 0;
-        }
-      }
-      for (int kc = 0; kc < nk; ++kc) {
-        const int s = kc % S;
-        const uint32_t ph = (kc / S) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const int k4 = kc * BK + j * 4;
-        const bool kv = k4 < p.K;
-        int dd = 0, dh = 0, dw = 0, delta = 0;
-        if (kv) {
-          const int tap = k4 / p.Cin;
-          const int c = k4 - tap * p.Cin;
-          const int4 t = __ldg(p.taps + tap);
-          dd = t.x; dh = t.y; dw = t.z;
-          delta = ((dd * p.in_H + dh) * p.in_W + dw) * p.in_Cs + p.in_c0 + c;
-        }
-        const uint32_t a_dst = smem_base + s * C::kStageBytes;
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.tiles_n) * BM;
+        long long base[8];
+        int crd[8];  // zd | zh<<10 | zw<<20 | valid<<30
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int row = gw * 32 + i * 4 + rsub;
-          const int id = (crd[i] & 1023) + dd;
-          const int ih = ((crd[i] >> 10) & 1023) + dh;
-          const int iw = ((crd[i] >> 20) & 1023) + dw;
-          const bool ok = kv && (crd[i] >> 30) && (unsigned)id < (unsigned)p.in_D &&
-                          (unsigned)ih < (unsigned)p.in_H && (unsigned)iw < (unsigned)p.in_W;
-          const float* src = ok ? (p.A + base[i] + delta) : p.A;
-          const uint32_t dst = a_dst + row * 128 + ((j ^ (row & 7)) << 4);
-          cp_async16_zfill(dst, src, ok ? 16u : 0u);
+          const int r = m0 + gw * 32 + i * 4 + rsub;
+          if (r < p.M) {
+            const int ow = r % p.out_W;
+            int t = r / p.out_W;
+            const int oh = t % p.out_H;
+            t /= p.out_H;
+            const int od = t % p.out_D;
+            const int n = t / p.out_D;
+            const int zd = od * p.sd, zh = oh * p.sh, zw = ow * p.sw;
+            base[i] = ((((long long)n * p.in_D + zd) * p.in_H + zh) * p.in_W + zw) * p.in_Cs;
+            crd[i] = zd | (zh << 10) | (zw << 20) | (1 << 30);
+          } else {
+            base[i] = 0;
+            crd[i] = 0;
+          }
         }
-        cp_async_commit();
-        if (kc >= kGatherLag) {
-          cp_async_wait<kGatherLag>();
-          if (!p.consumer_fence) fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full_bar((kc - kGatherLag) % S));
+        for (int kc = 0; kc < nk; ++kc, ++g) {
+          const int s = g % S;
+          const uint32_t ph = (g / S) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const int k4 = kc * BK + j * 4;
+          const bool kv = k4 < p.K;
+          int dd = 0, dh = 0, dw = 0, delta = 0;
+          if (kv) {
+            const int tap = k4 / p.Cin;
+            const int c = k4 - tap * p.Cin;
+            const int4 t = __ldg(p.taps + tap);
+            dd = t.x; dh = t.y; dw = t.z;
+            delta = ((dd * p.in_H + dh) * p.in_W + dw) * p.in_Cs + p.in_c0 + c;
+          }
+          const uint32_t a_dst = smem_base + s * C::kStageBytes;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = gw * 32 + i * 4 + rsub;
+            const int id = (crd[i] & 1023) + dd;
+            const int ih = ((crd[i] >> 10) & 1023) + dh;
+            const int iw = ((crd[i] >> 20) & 1023) + dw;
+            const bool ok = kv && (crd[i] >> 30) && (unsigned)id < (unsigned)p.in_D &&
+                            (unsigned)ih < (unsigned)p.in_H && (unsigned)iw < (unsigned)p.in_W;
+            const float* src = ok ? (p.A + base[i] + delta) : p.A;
+            const uint32_t dst = a_dst + row * 128 + ((j ^ (row & 7)) << 4);
+            cp_async16_zfill(dst, src, ok ? 16u : 0u);
+          }
+          cp_async_commit();
+          if (g >= kGatherLag) {   // the pipeline runs across tile boundaries
+            cp_async_wait<kGatherLag>();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar((g - kGatherLag) % S));
+          }
         }
       }
       cp_async_wait<0>();
-      if (!p.consumer_fence) fence_proxy_async_smem();
+      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        for (int kc = (nk > kGatherLag ? nk - kGatherLag : 0); kc < nk; ++kc) mbar_arrive(full_bar(kc % S));
+        for (uint32_t q = (g > kGatherLag ? g - kGatherLag : 0); q < g; ++q) mbar_arrive(full_bar(q % S));
       }
       __syncwarp();
     }
   } else {
-    // ---- epilogue (warps 0-3; warp w owns TMEM lanes 32w..32w+31) ----------------------------
-    mbar_wait(tmem_full_bar, 0u);
-    tc_fence_after();
-    const int r = m0 + warp * 32 + lane;
-    const bool valid = r < p.M;
-    long long off = 0, off2 = 0;
-    if (valid) {
-      const int ow = r % p.out_W;
-      int t = r / p.out_W;
-      const int oh = t % p.out_H;
-      t /= p.out_H;
-      const int od = t % p.out_D;
-      const int n = t / p.out_D;
-      off = p.o_base + n * p.o_sn + od * p.o_sd + oh * p.o_sh + ow * p.o_sw;
-      off2 = p.o2_base + n * p.o2_sn + od * p.o2_sd + oh * p.o2_sh + ow * p.o2_sw;
-    }
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      const int jb = n0 + c0;
-      if (jb >= p.N) break;  // warp-uniform
-      uint32_t v[16];
+    // ---- epilogue: warps 0-3, helped by warps 6-9 whenever those are not gathering.  A warp may only touch the
+    // TMEM lane quarter (warp % 4); the two warps of a quarter take alternate 16-column slabs. ----------------
+    const int quarter = warp & 3;
+    const int part = warp >= 6 ? 1 : 0;
+    const int nparts = a_mode == SVX_A_GATHER ? 1 : 2;
+    const int ew = part * 4 + quarter;
+    float* staging = staging_all + ew * (32 * kSlab);
+    long long* soff = soff_all + ew * 32;
+    constexpr int SLAB = kSlab;
+    constexpr int CP = SLAB / 4;     // float4 chunks per staged row
+    const bool rowwise = (p.epi_mode == SVX_EPI_DEC_TAIL) || !p.vec_ok;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+      const uint32_t as = it & 1u;
+      long long off = 0, off2 = 0;
+      const bool valid = decode_row(p, m0 + quarter * 32 + lane, off, off2);
       __syncwarp();
-      tmem_ld16(lane_addr + c0, v);
-      tmem_ld_wait();
-      if (valid) {
-      float x[16];
+      soff[lane] = valid ? off : -1;
+      __syncwarp();
+      mbar_wait(tmem_full_bar(as), (it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c0 = part * SLAB; c0 < BN; c0 += nparts * SLAB) {
+        const int jb = n0 + c0;
+        if (jb >= p.N) break;  // warp-uniform
+        uint32_t v[SLAB];
+        __syncwarp();
+        tmem_ld16(lane_addr + c0, v);
+        tmem_ld_wait();
+        if (!rowwise) {
+          // transpose through smem so that every warp-wide store writes whole 64-byte row segments
 #pragma unroll
-      for (int q = 0; q < 16; ++q) x[q] = __uint_as_float(v[q]) + sbias[c0 + q];
-      if (p.epi_mode == SVX_EPI_DEC_TAIL) {
-        // decoder.py:80-89: raw = cat(relu(bn(layer4)), layer5(.)) ; coarse = layer5(.)
-        float g = __ldg(p.epi_aux + 8);  // layer5 bias (0 when TCONV_USE_BIAS is off)
+          for (int c = 0; c < CP; ++c)
+            *reinterpret_cast<uint4*>(staging + lane * SLAB + ((c ^ (lane & (CP - 1))) << 2)) =
+                make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          __syncwarp();
+          switch (p.act) {
+            case SVX_ACT_RELU: store_slab<SLAB, SVX_ACT_RELU>(p, staging, soff, lane, jb); break;
+            case SVX_ACT_LEAKY: store_slab<SLAB, SVX_ACT_LEAKY>(p, staging, soff, lane, jb); break;
+            case SVX_ACT_GELU: store_slab<SLAB, SVX_ACT_GELU>(p, staging, soff, lane, jb); break;
+            default: store_slab<SLAB, SVX_ACT_NONE>(p, staging, soff, lane, jb); break;
+          }
+        } else if (valid) {
+          // one thread = one output row (decoder tail needs the whole row; N % 4 != 0 outputs are scalar)
+          float x[SLAB];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          x[q] = fmaxf(x[q], 0.f);
-          g = fmaf(__ldg(p.epi_aux + q), x[q], g);
-        }
-        x[8] = g;
+          for (int q = 0; q < SLAB; ++q) x[q] = __uint_as_float(v[q]) + ((p.bias && jb + q < p.Npad) ? __ldg(p.bias + jb + q) : 0.f);
+          if (p.epi_mode == SVX_EPI_DEC_TAIL) {
+            // decoder.py:80-89: raw = cat(relu(bn(layer4)), layer5(.)) ; coarse = layer5(.)
+            float gsum = __ldg(p.epi_aux + 8);  // layer5 bias (0 when TCONV_USE_BIAS is off)
 #pragma unroll
-        for (int q = 9; q < 16; ++q) x[q] = 0.f;
-        p.out2[off2] = g;
-      } else {
-        const float* res = p.residual ? p.residual + off + jb : nullptr;
-        float rv[16];
-        if (res) {
+            for (int q = 0; q < 8; ++q) {
+              x[q] = fmaxf(x[q], 0.f);
+              gsum = fmaf(__ldg(p.epi_aux + q), x[q], gsum);
+            }
+            x[8] = gsum;
+#pragma unroll
+            for (int q = 9; q < SLAB; ++q) x[q] = 0.f;
+            p.out2[off2] = gsum;
+          } else {
+            const float* res = p.residual ? p.residual + off + jb : nullptr;
+#pragma unroll 4
+            for (int q = 0; q < SLAB; ++q) {
+              const float rvq = (res && jb + q < p.N) ? res[q] : 0.f;
+              float t = x[q];
+              if (!p.res_after_act) t += rvq;
+              t = apply_act(t, p.act, p.act_param);
+              if (p.res_after_act) t += rvq;
+              x[q] = t * p.out_scale;
+            }
+          }
+          if (p.round_tf32) {
+#pragma unroll
+            for (int q = 0; q < SLAB; ++q) x[q] = round_tf32(x[q]);
+          }
+          float* dst = p.out + off + jb;
           if (p.vec_ok) {
 #pragma unroll
-            for (int q = 0; q < 16; q += 4) {
-              if (jb + q < p.N) {
-                const float4 t4 = *reinterpret_cast<const float4*>(res + q);  // plain load: out may alias residual
-                rv[q] = t4.x; rv[q + 1] = t4.y; rv[q + 2] = t4.z; rv[q + 3] = t4.w;
-              } else {
-                rv[q] = rv[q + 1] = rv[q + 2] = rv[q + 3] = 0.f;
-              }
+            for (int q = 0; q < SLAB; q += 4) {
+              if (jb + q < p.N) *reinterpret_cast<float4*>(dst + q) = make_float4(x[q], x[q + 1], x[q + 2], x[q + 3]);
             }
           } else {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) rv[q] = (jb + q < p.N) ? res[q] : 0.f;
-          }
-          if (!p.res_after_act) {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) x[q] += rv[q];
+            for (int q = 0; q < SLAB; ++q) {
+              if (jb + q < p.N) dst[q] = x[q];
+            }
           }
         }
-#pragma unroll
-        for (int q = 0; q < 16; ++q) x[q] = apply_act(x[q], p.act, p.act_param);
-        if (res && p.res_after_act) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) x[q] += rv[q];
-        }
-        if (p.out_scale != 1.f) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) x[q] *= p.out_scale;
-        }
       }
-      if (p.round_tf32) {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) x[q] = round_tf32(x[q]);
-      }
-      float* dst = p.out + off + jb;
-      if (p.vec_ok) {
-#pragma unroll
-        for (int q = 0; q < 16; q += 4) {
-          if (jb + q < p.N)
-            *reinterpret_cast<float4*>(dst + q) = make_float4(x[q], x[q + 1], x[q + 2], x[q + 3]);
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          if (jb + q < p.N) dst[q] = x[q];
-        }
-      }
-      }  // valid
+      // hand the accumulator back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(as));
     }
-    __syncwarp();
   }
 
   tc_fence_before();
@@ -372,6 +497,17 @@ int encode_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t cols,
   return 0;
 }
 
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN>
 int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int grid, cudaStream_t st) {
   static bool configured = false;
@@ -408,6 +544,8 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   GemmPrepared* g = new GemmPrepared();
   GemmParams& p = g->p;
   memset(&p, 0, sizeof(p));
+  memset(&g->map_a, 0, sizeof(g->map_a));
+  p.chunks_per_tap = 1;
   if (d.a_mode == SVX_A_PLAIN) {
     if (d.lda % 4 != 0 || d.lda < d.K) {
       delete g;
@@ -423,7 +561,23 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
       return fail("gemm: bad gather description (Cin=%d c0=%d Cs=%d ntaps=%d K=%d)", d.Cin, d.in_c0, d.in_Cs,
                   d.ntaps, d.K);
     }
-    memset(&g->map_a, 0, sizeof(g->map_a));
+  } else if (d.a_mode == SVX_A_FLAT) {
+    bool ok = d.Cin > 0 && d.Cin % BK == 0 && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.ntaps > 0 &&
+              d.ntaps <= kMaxTaps && d.taps_host && d.K == d.ntaps * d.Cin && d.Kpad == d.K &&
+              d.out_D == d.in_D && d.out_H == d.in_H && d.out_W == d.in_W;
+    if (!ok) {
+      delete g;
+      return fail("gemm: bad flat-conv description (Cin=%d ntaps=%d K=%d Kpad=%d)", d.Cin, d.ntaps, d.K, d.Kpad);
+    }
+    const long long rows_total = (long long)d.lda;  // flat mode: lda carries the row count of the padded matrix
+    if (rows_total < d.M) { delete g; return fail("gemm: flat-conv matrix has %lld rows < M=%d", rows_total, d.M); }
+    for (int t = 0; t < d.ntaps; ++t) {
+      const int dd = d.taps_host[4 * t], dh = d.taps_host[4 * t + 1], dw = d.taps_host[4 * t + 2];
+      if (dd < 0 || dh < 0 || dw < 0) { delete g; return fail("gemm: flat-conv taps must be non-negative"); }
+      p.flat_off[t] = (dd * d.in_H + dh) * d.in_W + dw;
+    }
+    p.chunks_per_tap = d.Cin / BK;
+    if (encode_map(&g->map_a, d.A, (uint64_t)rows_total, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs, BM)) { delete g; return 1; }
   } else {
     delete g;
     return fail("gemm: unknown a_mode %d", d.a_mode);
@@ -437,10 +591,12 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     delete g;
     return fail("gemm: decoder tail epilogue needs block_n=16, N=16, aux weights and a coarse output");
   }
-  p.M = d.M; p.N = d.N; p.K = d.K; p.nk = d.Kpad / BK; p.tiles_n = d.Npad / d.block_n; p.a_mode = d.a_mode;
+  p.M = d.M; p.N = d.N; p.K = d.K; p.Npad = d.Npad; p.nk = d.Kpad / BK; p.tiles_n = d.Npad / d.block_n; p.a_mode = d.a_mode;
   p.A = d.A;
   p.in_D = d.in_D; p.in_H = d.in_H; p.in_W = d.in_W; p.in_Cs = d.in_Cs; p.in_c0 = d.in_c0; p.Cin = d.Cin;
   p.out_D = d.out_D; p.out_H = d.out_H; p.out_W = d.out_W;
+  p.valid_D = d.valid_D; p.valid_H = d.valid_H; p.valid_W = d.valid_W;
+  if (p.valid_W > 0 && (p.valid_D <= 0 || p.valid_H <= 0)) { delete g; return fail("gemm: valid extents must all be set"); }
   p.sd = d.stride_d; p.sh = d.stride_h; p.sw = d.stride_w;
   p.taps = reinterpret_cast<const int4*>(d.taps);
   p.bias = d.bias; p.residual = d.residual; p.out = d.out;
@@ -453,15 +609,13 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   p.vec_ok = (d.N % 4 == 0) && al4(d.o_base) && al4(d.o_sn) && al4(d.o_sd) && al4(d.o_sh) && al4(d.o_sw) &&
              (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
              (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0);
-  {
-    const char* e = getenv("SVX_CONSUMER_FENCE");
-    p.consumer_fence = (e && e[0] == '1') ? 1 : 0;
-  }
   const long long tiles_m = (d.M + BM - 1) / BM;
-  const long long grid = tiles_m * p.tiles_n;
-  if (grid > 0x7fffffffLL) { delete g; return fail("gemm: grid too large"); }
+  const long long tiles = tiles_m * p.tiles_n;
+  if (tiles > 0x7fffffffLL) { delete g; return fail("gemm: too many tiles"); }
+  p.tiles_m = (int)tiles_m;
   g->bn = d.block_n;
-  g->grid = (int)grid;
+  const int slots = sm_count() * (d.block_n <= 96 ? 2 : 1);
+  g->grid = (int)(tiles < slots ? tiles : slots);
   *out = g;
   return 0;
 }
@@ -480,8 +634,8 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void* stream) {
     case 32: rc = launch_bn<32>(g->map_a, g->map_b, g->p, g->grid, st); break;
     case 64: rc = launch_bn<64>(g->map_a, g->map_b, g->p, g->grid, st); break;
     case 96: rc = launch_bn<96>(g->map_a, g->map_b, g->p, g->grid, st); break;
-    case 192: rc = launch_bn<192>(g->map_a, g->map_b, g->p, g->grid, st); break;
     case 128: rc = launch_bn<128>(g->map_a, g->map_b, g->p, g->grid, st); break;
+    case 192: rc = launch_bn<192>(g->map_a, g->map_b, g->p, g->grid, st); break;
     default: rc = launch_bn<256>(g->map_a, g->map_b, g->p, g->grid, st); break;
   }
   if (!prepared) delete g;

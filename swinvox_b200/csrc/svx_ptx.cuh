@@ -34,16 +34,21 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  long long t0 = 0;
   for (uint32_t it = 0;; ++it) {
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t}\n"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)   // suspend-time hint (ns): sleep in hardware instead of spinning
         : "memory");
     if (done) break;
-    if (it > (1u << 24)) __trap();
+    if ((it & 255u) == 255u) {   // ~2 s of SM clocks without progress: a protocol bug, not a long main loop
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
   }
 }
 

@@ -11,8 +11,8 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, A_GATHER, A_PLAIN, EPI_DEC_TAIL, EPI_STD, POOL_AVG,
-                   POOL_MAX)
+from ._lib import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, A_FLAT, A_GATHER, A_PLAIN, EPI_DEC_TAIL, EPI_STD,
+                   POOL_AVG, POOL_MAX)
 
 BLOCK_NS = (16, 32, 64, 96, 128, 192, 256)
 
@@ -52,6 +52,18 @@ class Act:
     W: int
     C: int
     c0: int = 0
+    pad: tuple = (0, 0, 0)   # zero border (d, h, w) on each side; D/H/W above INCLUDE it
+
+    @property
+    def inner(self):
+        """extents of the real data inside the zero border"""
+        return (self.D - 2 * self.pad[0], self.H - 2 * self.pad[1], self.W - 2 * self.pad[2])
+
+    def interior_map(self):
+        """(base, s_n, s_d, s_h, s_w) element offsets of data voxel (n, d, h, w) inside the padded buffer"""
+        Cs = self.Cs
+        base = self.c0 + ((self.pad[0] * self.H + self.pad[1]) * self.W + self.pad[2]) * Cs
+        return (base, self.D * self.H * self.W * Cs, self.H * self.W * Cs, self.W * Cs, Cs)
 
     @property
     def Cs(self):
@@ -62,11 +74,13 @@ class Act:
         return self.N * self.D * self.H * self.W
 
     def view(self):
-        """logical [N, D, H, W, C] torch view (for tests / module boundaries)"""
-        return self.buf.view(self.N, self.D, self.H, self.W, self.Cs)[..., self.c0:self.c0 + self.C]
+        """logical [N, D, H, W, C] torch view of the real data (for tests / module boundaries)"""
+        v = self.buf.view(self.N, self.D, self.H, self.W, self.Cs)[..., self.c0:self.c0 + self.C]
+        pd, ph, pw = self.pad
+        return v[:, pd:self.D - pd, ph:self.H - ph, pw:self.W - pw]
 
     def channels(self, c0, c):
-        return Act(self.buf, self.N, self.D, self.H, self.W, c, self.c0 + c0)
+        return Act(self.buf, self.N, self.D, self.H, self.W, c, self.c0 + c0, self.pad)
 
 
 @dataclass
@@ -187,10 +201,12 @@ class Plan:
     def zeros(self, *shape, dtype=torch.float32):
         return self.hold(torch.zeros(*shape, dtype=dtype, device=self.device))
 
-    def new_act(self, N, D, H, W, C, Cs=None, zero=False):
+    def new_act(self, N, D, H, W, C, Cs=None, zero=False, pad=(0, 0, 0)):
+        """D, H, W are the data extents; `pad` adds a zero border that producers never write (flat-conv inputs)"""
         Cs = Cs or C
-        buf = (self.zeros if zero else self.empty)(N * D * H * W, Cs)
-        return Act(buf, N, D, H, W, C, 0)
+        Dp, Hp, Wp = D + 2 * pad[0], H + 2 * pad[1], W + 2 * pad[2]
+        buf = (self.zeros if (zero or any(pad)) else self.empty)(N * Dp * Hp * Wp, Cs)
+        return Act(buf, N, Dp, Hp, Wp, C, 0, tuple(pad))
 
     def hold(self, t):
         """keep every tensor whose address is baked into an op alive as long as the plan"""
@@ -243,16 +259,15 @@ class Plan:
         d.N, d.K, d.Kpad, d.Npad, d.block_n = pack.N, pack.K, pack.Kpad, pack.Npad, pack.block_n
         d.out = self.hold(out).buf.data_ptr()
         if out_map is None:
-            Cs = out.Cs
-            out_map = (out.c0, out.D * out.H * out.W * Cs, out.H * out.W * Cs, out.W * Cs, Cs)
+            out_map = out.interior_map()
         d.o_base, d.o_sn, d.o_sd, d.o_sh, d.o_sw = out_map
         d.act, d.act_param = act, act_param
         d.out_scale = out_scale
         d.round_tf32 = 1 if round_out else 0
         d.epi_mode = EPI_STD
         if residual is not None:
-            assert residual.Cs == out.Cs and residual.c0 == out.c0 and residual.pixels == out.pixels, \
-                "residual must share the output layout"
+            assert (residual.Cs == out.Cs and residual.c0 == out.c0 and residual.pixels == out.pixels
+                    and residual.pad == out.pad), "residual must share the output layout"
             d.residual = self.hold(residual).buf.data_ptr()
             d.res_after_act = 1 if res_after_act else 0
         self.hold(pack.W)
@@ -261,16 +276,16 @@ class Plan:
     def linear(self, x, pack, out, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True,
                out_scale=1.0, round_out=False, name=None):
         """x: Act read as a [pixels, C] matrix (plain TMA operand); out: Act with C == pack.N."""
-        assert x.C == pack.K and out.C >= pack.N and x.pixels == out.pixels, (x.C, pack.K, out.C, pack.N)
-        assert x.c0 % 4 == 0 and x.Cs % 4 == 0
+        oD, oH, oW = out.inner
+        assert x.C == pack.K and out.C >= pack.N and x.pixels == out.N * oD * oH * oW, (x.C, pack.K, out.C, pack.N)
+        assert x.c0 % 4 == 0 and x.Cs % 4 == 0 and not any(x.pad), "plain operands are dense matrices"
         d = _lib.GemmDesc()
         d.M = x.pixels
         d.a_mode = A_PLAIN
         d.A = self.hold(x).buf.data_ptr() + 4 * x.c0
         d.lda = x.Cs
-        d.out_D, d.out_H, d.out_W = 1, 1, 1
-        self._fill_epilogue(d, pack, out, (out.c0, out.Cs, 0, 0, 0), act, act_param, residual, res_after_act,
-                            out_scale, round_out)
+        d.out_D, d.out_H, d.out_W = oD, oH, oW
+        self._fill_epilogue(d, pack, out, None, act, act_param, residual, res_after_act, out_scale, round_out)
         self._add("gemm", d, name or "linear", 2.0 * d.M * pack.N * pack.K)
         return out
 
@@ -280,7 +295,8 @@ class Plan:
         cin_pad = pack.K // len(taps)
         assert cin_pad * len(taps) == pack.K and cin_pad % 4 == 0 and cin_pad >= x.C
         assert x.c0 % 4 == 0 and x.Cs % 4 == 0 and x.c0 + cin_pad <= x.Cs, (x.c0, cin_pad, x.Cs)
-        rd, rh, rw = rows_dhw or (out.D, out.H, out.W)
+        assert not any(x.pad), "gather mode reads unpadded tensors (use conv_flat for padded ones)"
+        rd, rh, rw = rows_dhw or out.inner
         d = _lib.GemmDesc()
         d.M = x.N * rd * rh * rw
         d.a_mode = A_GATHER
@@ -298,6 +314,34 @@ class Plan:
             d.epi_out2 = self.hold(out2).data_ptr()
             d.o2_base, d.o2_sn, d.o2_sd, d.o2_sh, d.o2_sw = map2
         self._add("gemm", d, name or "conv", 2.0 * d.M * pack.N * pack.K)
+        return out
+
+    def conv_flat(self, x, pack, taps, out, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True,
+                  out_scale=1.0, round_out=False, name=None, out_map=None, valid=None):
+        """Stride-1 convolution over a zero-padded input, A operand streamed by TMA (one shifted box per tap).
+        `taps` are non-negative (dd, dh, dw) offsets from the window corner in padded coordinates; `valid` =
+        number of window corners per axis that are real outputs (default: the extents of `out`)."""
+        cin = pack.K // len(taps)
+        assert cin * len(taps) == pack.K and cin % 32 == 0 and cin == x.C and pack.Kpad == pack.K, (cin, x.C, pack.K)
+        assert all(min(t) >= 0 for t in taps)
+        vD, vH, vW = valid or out.inner
+        d = _lib.GemmDesc()
+        rows_total = x.buf.shape[0]
+        per = x.D * x.H * x.W
+        d.M = (x.N - 1) * per + ((vD - 1) * x.H + (vH - 1)) * x.W + vW
+        d.a_mode = A_FLAT
+        d.A = self.hold(x).buf.data_ptr()
+        d.lda = rows_total
+        d.in_D, d.in_H, d.in_W, d.in_Cs, d.in_c0, d.Cin = x.D, x.H, x.W, x.Cs, x.c0, cin
+        d.out_D, d.out_H, d.out_W = x.D, x.H, x.W
+        d.valid_D, d.valid_H, d.valid_W = vD, vH, vW
+        d.stride_d = d.stride_h = d.stride_w = 1
+        d.ntaps = len(taps)
+        host = (C.c_int32 * (4 * len(taps)))(*[v for t in taps for v in (t[0], t[1], t[2], 0)])
+        self.keep[id(host)] = host
+        d.taps_host = C.cast(host, C.c_void_p)
+        self._fill_epilogue(d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out)
+        self._add("gemm", d, name or "conv_flat", 2.0 * x.N * vD * vH * vW * pack.N * pack.K)
         return out
 
     # ---- everything else ------------------------------------------------------------------------

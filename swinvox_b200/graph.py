@@ -46,11 +46,16 @@ def _bottleneck(plan, blk, x, name):
     s = blk.conv2.stride[0]
     width, cout = blk.conv1.out_channels, blk.conv3.out_channels
     H2 = (x.H + 2 - 3) // s + 1
-    t1 = plan.new_act(x.N, 1, x.H, x.W, width)
+    flat = s == 1 and width % 32 == 0   # stride-1 3x3: TMA-fed "flat" conv over a zero-padded conv1 output
+    t1 = plan.new_act(x.N, 1, x.H, x.W, width, pad=(0, 1, 1) if flat else (0, 0, 0))
     plan.linear(x, E.pack_conv(blk.conv1.weight, None, blk.bn1, dev), t1, act=ACT_RELU, round_out=True, name=name + ".conv1")
     t2 = plan.new_act(x.N, 1, H2, H2, width)
-    plan.conv(t1, E.pack_conv(blk.conv2.weight, None, blk.bn2, dev), E.conv_taps(1, 3, 3, 0, 1, 1), t2, stride=(1, s, s),
-              act=ACT_RELU, round_out=True, name=name + ".conv2")
+    pk2 = E.pack_conv(blk.conv2.weight, None, blk.bn2, dev)
+    if flat:
+        plan.conv_flat(t1, pk2, E.conv_taps(1, 3, 3, 0, 0, 0), t2, act=ACT_RELU, round_out=True, name=name + ".conv2")
+    else:
+        plan.conv(t1, pk2, E.conv_taps(1, 3, 3, 0, 1, 1), t2, stride=(1, s, s), act=ACT_RELU, round_out=True,
+                  name=name + ".conv2")
     if blk.downsample is not None:
         idn = plan.new_act(x.N, 1, H2, H2, cout)
         pk = E.pack_conv(blk.downsample[0].weight, None, blk.downsample[1], dev)
@@ -145,8 +150,9 @@ def lower_swin(plan, swin, img, N):
 # --------------------------------------------------------------------------------------------------
 # Cross-view attention (models/cross_view_attention.py:59-134)
 # --------------------------------------------------------------------------------------------------
-def lower_cva(plan, cva, x, B, V):
-    """x: Act [B*V,7,7,C] (C=512).  Returns Act of the same shape (TF32-rounded: it feeds fusion_layer)."""
+def lower_cva(plan, cva, x, B, V, out_pad=(0, 0, 0)):
+    """x: Act [B*V,7,7,C] (C=512).  Returns Act of the same shape (TF32-rounded: it feeds fusion_layer),
+    optionally inside a zero border so the next 3x3 convolution can stream it by TMA."""
     dev = _dev(plan)
     N, Cc, R, heads = x.N, x.C, cva.reduced_channels, cva.num_heads
     ratio = cva.attention_spatial_downsample_ratio
@@ -173,7 +179,7 @@ def lower_cva(plan, cva, x, B, V):
     hid = plan.new_act(N, 1, x.H, x.W, Cc)
     plan.linear(y, E.pack_conv(cva.ffn[0].weight, cva.ffn[0].bias, None, dev), hid, act=ACT_GELU, round_out=True,
                 name="cva.ffn.0")
-    out = plan.new_act(N, 1, x.H, x.W, Cc)
+    out = plan.new_act(N, 1, x.H, x.W, Cc, pad=out_pad)
     plan.linear(hid, E.pack_conv(cva.ffn[2].weight, cva.ffn[2].bias, cva.batch_norm, dev), out, round_out=True,
                 name="cva.ffn.2+bn")
     return out
@@ -224,13 +230,17 @@ def lower_encoder(plan, enc, img, B, V):
     x = cat
     plan.taps.update(resnet=cat.channels(0, 256), swin_sum=sw, swin=feats, pre_cva=cat)
     if net.USE_CROSS_VIEW_ATTENTION:
-        x = lower_cva(plan, enc.cross_view_attention, cat, B, V)
+        x = lower_cva(plan, enc.cross_view_attention, cat, B, V, out_pad=(0, 1, 1))
     plan.taps["post_cva"] = x
     seq = [("fusion_layer", enc.fusion_layer), ("layer1", enc.layer1), ("layer2", enc.layer2), ("layer3", enc.layer3)]
     for li, (nm, layer) in enumerate(seq):
-        o = plan.new_act(N, 1, 7, 7, 256)
-        plan.conv(x, E.pack_conv(layer[0].weight, layer[0].bias, layer[1], dev), E.conv_taps(1, 3, 3, 0, 1, 1), o,
-                  act=ACT_RELU, round_out=li < len(seq) - 1, name="encoder." + nm)
+        last = li == len(seq) - 1
+        o = plan.new_act(N, 1, 7, 7, 256, pad=(0, 0, 0) if last else (0, 1, 1))
+        pk = E.pack_conv(layer[0].weight, layer[0].bias, layer[1], dev)
+        if any(x.pad):   # zero-bordered input: one TMA box per filter tap
+            plan.conv_flat(x, pk, E.conv_taps(1, 3, 3, 0, 0, 0), o, act=ACT_RELU, round_out=not last, name="encoder." + nm)
+        else:
+            plan.conv(x, pk, E.conv_taps(1, 3, 3, 0, 1, 1), o, act=ACT_RELU, round_out=not last, name="encoder." + nm)
         x = o
     return x
 

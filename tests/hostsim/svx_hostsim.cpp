@@ -49,6 +49,10 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   SVX_REQUIRE(d.Npad % d.block_n == 0 && d.Npad >= d.N, "gemm: bad Npad");
   if (d.a_mode == SVX_A_GATHER)
     SVX_REQUIRE(d.Cin % 4 == 0 && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.K == d.ntaps * d.Cin, "gemm: bad gather");
+  else if (d.a_mode == SVX_A_FLAT)
+    SVX_REQUIRE(d.Cin % 32 == 0 && d.K == d.ntaps * d.Cin && d.Kpad == d.K && d.taps_host && d.ntaps <= 64 &&
+                    d.out_D == d.in_D && d.out_H == d.in_H && d.out_W == d.in_W && d.lda >= d.M,
+                "gemm: bad flat conv");
   else
     SVX_REQUIRE(d.lda % 4 == 0 && d.lda >= d.K, "gemm: bad lda");
   if (d.epi_mode == SVX_EPI_DEC_TAIL)
@@ -78,8 +82,17 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
       const int od = t % d.out_D;
       const long long n = t / d.out_D;
       (void)rows_per_n;
+      if (d.valid_W > 0 && (ow >= d.valid_W || oh >= d.valid_H || od >= d.valid_D)) continue;
       if (d.a_mode == SVX_A_PLAIN) {
         for (int k = 0; k < d.K; ++k) arow[k] = tf32_trunc(d.A[(long long)r * d.lda + k]);
+      } else if (d.a_mode == SVX_A_FLAT) {
+        for (int tap = 0; tap < d.ntaps; ++tap) {
+          const long long row = r + ((long long)d.taps_host[tap * 4] * d.in_H + d.taps_host[tap * 4 + 1]) * d.in_W +
+                                d.taps_host[tap * 4 + 2];
+          const bool ok = row < d.lda;  // TMA zero-fills rows past the end of the matrix
+          const float* px = d.A + row * d.in_Cs + d.in_c0;
+          for (int c = 0; c < d.Cin; ++c) arow[tap * d.Cin + c] = ok ? tf32_trunc(px[c]) : 0.f;
+        }
       } else {
         for (int tap = 0; tap < d.ntaps; ++tap) {
           const int id = od * d.stride_d + d.taps[tap * 4 + 0];

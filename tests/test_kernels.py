@@ -119,6 +119,30 @@ def test_conv2d_gather(dev, cin, cout, hw, k, s, p_):
     assert rel_err(to_nchw(out).squeeze(2), ref) < 1e-4
 
 
+@pytest.mark.parametrize("cin,cout,hw", [(64, 64, 14), (128, 96, 9), (512, 256, 7)])
+def test_conv2d_flat_tma(dev, cin, cout, hw):
+    """stride-1 3x3 conv over a zero-bordered input, A operand streamed by TMA (one shifted box per tap), writing
+    into the interior of another zero-bordered buffer"""
+    DEV = dev
+    torch.manual_seed(cin)
+    x = E.tf32_round(torch.randn(3, cin, hw, hw))
+    conv = torch.nn.Conv2d(cin, cout, 3, 1, 1)
+    bn = rand_bn(torch.nn.BatchNorm2d(cout))
+    p = E.Plan(DEV)
+    xin = p.new_act(3, 1, hw, hw, cin, pad=(0, 1, 1))
+    xin.view().copy_(x.permute(0, 2, 3, 1).unsqueeze(1))
+    out = p.new_act(3, 1, hw, hw, cout, pad=(0, 1, 1))
+    p.conv_flat(xin, E.pack_conv(conv.weight, conv.bias, bn, DEV), E.conv_taps(1, 3, 3, 0, 0, 0), out, act=E.ACT_RELU)
+    p.run()
+    sync(DEV)
+    wf, bf = E.fold_bn(conv.weight, conv.bias, bn)
+    ref = F.relu(F.conv2d(x.double(), E.tf32_round(wf).double(), bf.double(), 1, 1))
+    assert rel_err(out.view().squeeze(1).permute(0, 3, 1, 2), ref) < 1e-4
+    full = out.buf.view(3, hw + 2, hw + 2, cout).cpu()
+    assert full[:, 0].abs().max() == 0 and full[:, -1].abs().max() == 0 and full[:, :, 0].abs().max() == 0 \
+        and full[:, :, -1].abs().max() == 0, "the zero border must stay untouched"
+
+
 def test_conv3d_padded_channels(dev):
     """merger-style Conv3d 9->9 k3 on a 16-channel padded buffer read at a channel offset"""
     DEV = dev
