@@ -91,6 +91,9 @@ typedef struct svx_gemm_desc {
   const float* epi_aux;     /* SVX_EPI_DEC_TAIL: layer5 weights w5[0..7], bias w5[8] */
   float* epi_out2;          /* SVX_EPI_DEC_TAIL: planar coarse volume [n, OD*OH*OW] */
   int64_t o2_base, o2_sn, o2_sd, o2_sh, o2_sw;
+  int32_t cin_live;         /* flat mode: only the first cin_live of the Cin channels of a tap carry non-zero weights
+                               (0 = all); the kernel may skip the contraction steps beyond them */
+  int32_t reserved0;
 } svx_gemm_desc;
 
 /* Explicit im2col for tiny channel counts (ResNet stem 7x7 s2 on 3 channels, Swin patch-embed

@@ -46,6 +46,8 @@ struct GemmParams {
   int valid_D, valid_H, valid_W;
   int sd, sh, sw;
   int chunks_per_tap;
+  int cin_live;             // flat mode: channels of a tap with non-zero weights (slab kernel skips the rest)
+  int slab_base_off;        // slab kernel: encode the swizzle phase of a shifted operand in the descriptor
   const int4* taps;
   const float* bias;
   const float* residual;
@@ -463,6 +465,187 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 5) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
+
+// =====================================================================================================
+// Slab kernel: 3x3x3 stride-1 Conv3d with <= 16 output channels over a zero-padded channels-last volume
+// (the merger's layers, merger.py:20-54).  The general kernel re-fetches the A tile for each of the 27 taps
+// (27x L2 traffic for a contraction whose N is 9); here each (tile, 32-channel chunk) loads three 200-row
+// slabs (one per depth tap) ONCE by TMA and all nine (kh, kw) taps of a slab are MMA operands addressed by
+// shifting the smem descriptor's start address by (kh*Wp + kw) rows (base_offset carries the swizzle phase).
+// Weights stay resident in smem; 16 tiles accumulate side by side in TMEM (2 x 16 x 16 columns).
+// =====================================================================================================
+constexpr int SL_TS = 16;                  // tiles per super-tile (TMEM: 2 sets x 16 tiles x 16 columns)
+constexpr int SL_ROWS = 200;               // slab rows: 128 + 2*Wp + 2 <= 200  (Wp <= 35)
+constexpr int SL_SLAB_BYTES = SL_ROWS * 128;
+constexpr int SL_STAGE_BYTES = 3 * SL_SLAB_BYTES;
+constexpr int SL_W_BYTES = 27 * 16 * 128;  // 27 taps x [16 x 32] fp32
+constexpr int SL_THREADS = 192;
+constexpr int SL_SMEM = 1024 + SL_W_BYTES + 2 * SL_STAGE_BYTES + 256;
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_shifted(uint32_t smem_addr, int with_base_offset) {
+  // operand that starts in the middle of a 1024-byte swizzle atom.  The 128B swizzle is a function of the absolute
+  // shared-memory address (bits 4-6 ^= bits 7-9), which is also how TMA wrote the slab, so a plain start-address
+  // shift addresses the right bytes; `with_base_offset` additionally sets base_offset = (start >> 7) & 7
+  // (kept switchable: SVX_SLAB_BASEOFF=1).
+  uint64_t d = umma_desc_sw128(smem_addr);
+  if (with_base_offset) d |= static_cast<uint64_t>((smem_addr >> 7) & 7u) << 49;
+  return d;
+}
+
+__global__ void __launch_bounds__(SL_THREADS, 1)
+conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                  const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t w_smem = smem_base;
+  const uint32_t slab_smem = smem_base + SL_W_BYTES;
+  const uint32_t bar_base = slab_smem + 2 * SL_STAGE_BYTES;
+  // barriers: slab_full[2], slab_empty[2], w_full, w_empty, acc_full[2], acc_empty[2], tmem slot
+  auto slab_full = [&](int s) { return bar_base + 8u * s; };
+  auto slab_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+  const uint32_t w_full = bar_base + 8u * 4, w_empty = bar_base + 8u * 5;
+  auto acc_full = [&](int a) { return bar_base + 8u * (6 + a); };
+  auto acc_empty = [&](int a) { return bar_base + 8u * (8 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * 10;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + SL_W_BYTES + 2 * SL_STAGE_BYTES + 8 * 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nch = (p.cin_live + BK - 1) / BK;   // channel chunks that carry non-zero weights
+  const int Wp = p.in_W, HWp = p.in_H * p.in_W;
+  const int num_tiles = p.tiles_m;
+  const int num_st = (num_tiles + SL_TS - 1) / SL_TS;
+
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); }
+  if (warp == 5) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) { mbar_init(slab_full(s), 1u); mbar_init(slab_empty(s), 1u); }
+      mbar_init(w_full, 1u); mbar_init(w_empty, 1u);
+      for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1u); mbar_init(acc_empty(a), 4u); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t g = 0, wload = 0;
+      for (int st = blockIdx.x; st < num_st; st += gridDim.x) {
+        const int t_end = min(SL_TS, num_tiles - st * SL_TS);
+        for (int ch = 0; ch < nch; ++ch) {
+          if (nch > 1 || wload == 0) {   // weights of this channel chunk (resident for single-chunk layers)
+            mbar_wait(w_empty, (wload & 1u) ^ 1u);
+            mbar_arrive_expect_tx(w_full, SL_W_BYTES);
+            for (int tap = 0; tap < 27; ++tap)
+              tma_load_2d(w_smem + tap * 2048, &map_w, w_full, tap * p.Cin + ch * BK, 0);
+            ++wload;
+          }
+          for (int t = 0; t < t_end; ++t, ++g) {
+            const int s = g & 1;
+            mbar_wait(slab_empty(s), ((g >> 1) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(slab_full(s), SL_STAGE_BYTES);
+            const int q0 = (st * SL_TS + t) * BM;
+            for (int kd = 0; kd < 3; ++kd)
+              tma_load_2d(slab_smem + s * SL_STAGE_BYTES + kd * SL_SLAB_BYTES, &map_x, slab_full(s),
+                          p.in_c0 + ch * BK, q0 + kd * HWp);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BM, 16);
+      uint32_t g = 0, wuse = 0, it = 0;
+      for (int st = blockIdx.x; st < num_st; st += gridDim.x, ++it) {
+        const int t_end = min(SL_TS, num_tiles - st * SL_TS);
+        const uint32_t set = it & 1u;
+        mbar_wait(acc_empty(set), ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        for (int ch = 0; ch < nch; ++ch) {
+          const int ksteps = min(BK / UMMA_K, (p.cin_live - ch * BK + UMMA_K - 1) / UMMA_K);
+          if (nch > 1 || wuse == 0) {
+            mbar_wait(w_full, wuse & 1u);
+            tc_fence_after();
+            ++wuse;
+          }
+          for (int t = 0; t < t_end; ++t, ++g) {
+            const int s = g & 1;
+            mbar_wait(slab_full(s), (g >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + set * (SL_TS * 16) + t * 16;
+            for (int kd = 0; kd < 3; ++kd) {
+              const uint32_t slab = slab_smem + s * SL_STAGE_BYTES + kd * SL_SLAB_BYTES;
+              for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                  const int tap = (kd * 3 + kh) * 3 + kw;
+                  const uint64_t da = umma_desc_sw128_shifted(slab + (kh * Wp + kw) * 128, p.slab_base_off);
+                  const uint64_t db = umma_desc_sw128(w_smem + tap * 2048);
+                  for (int k = 0; k < ksteps; ++k)
+                    umma_tf32(acc, da + 2u * k, db + 2u * k, idesc, (ch | tap | k) != 0 ? 1u : 0u);
+                }
+              }
+            }
+            umma_commit(slab_empty(s));
+          }
+          if (nch > 1) umma_commit(w_empty);
+        }
+        umma_commit(acc_full(set));
+      }
+    }
+    __syncwarp();
+  } else {
+    // epilogue: one thread = one output voxel (16 channels = 64 contiguous bytes)
+    uint32_t it = 0;
+    for (int st = blockIdx.x; st < num_st; st += gridDim.x, ++it) {
+      const int t_end = min(SL_TS, num_tiles - st * SL_TS);
+      const uint32_t set = it & 1u;
+      mbar_wait(acc_full(set), (it >> 1) & 1u);
+      tc_fence_after();
+      for (int t = 0; t < t_end; ++t) {
+        long long off = 0, off2 = 0;
+        const bool valid = decode_row(p, (st * SL_TS + t) * BM + warp * 32 + lane, off, off2);
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + set * (SL_TS * 16) + t * 16 + (static_cast<uint32_t>(warp * 32) << 16), v);
+        tmem_ld_wait();
+        if (valid) {
+          float x[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            float tv = __uint_as_float(v[q]) + (p.bias ? __ldg(p.bias + q) : 0.f);
+            tv = apply_act(tv, p.act, p.act_param) * p.out_scale;
+            x[q] = p.round_tf32 ? round_tf32(tv) : tv;
+          }
+          float* dst = p.out + off;
+          if (p.vec_ok) {
+#pragma unroll
+            for (int q = 0; q < 16; q += 4)
+              if (q < p.N) *reinterpret_cast<float4*>(dst + q) = make_float4(x[q], x[q + 1], x[q + 2], x[q + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              if (q < p.N) dst[q] = x[q];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(set));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<512>(tmem_base);
+}
+
 // ---- host side --------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -484,6 +667,7 @@ EncodeTiledFn get_encode_fn() {
 // 2-D fp32 tensor [rows, cols] with row pitch `pitch_elems`; box = box_rows x 32 columns, 128B swizzle
 int encode_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                uint32_t box_rows) {
+  if (box_rows > 256) return fail("TMA box of %u rows exceeds 256", box_rows);
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {cols, rows};
@@ -527,6 +711,7 @@ struct GemmPrepared {
   CUtensorMap map_a, map_b;
   GemmParams p;
   int bn, grid;
+  bool slab = false;   // 3x3x3, N <= 16 flat conv handled by conv3_slab_kernel
 };
 
 int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
@@ -577,7 +762,16 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
       p.flat_off[t] = (dd * d.in_H + dh) * d.in_W + dw;
     }
     p.chunks_per_tap = d.Cin / BK;
-    if (encode_map(&g->map_a, d.A, (uint64_t)rows_total, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs, BM)) { delete g; return 1; }
+    p.cin_live = (d.cin_live > 0 && d.cin_live <= d.Cin) ? d.cin_live : d.Cin;
+    p.slab_base_off = getenv("SVX_SLAB_BASEOFF") ? atoi(getenv("SVX_SLAB_BASEOFF")) : 0;
+    // the merger-style case: full 3x3x3 tap grid in (kd,kh,kw) order, <= 16 output channels, narrow rows
+    bool grid333 = d.ntaps == 27 && d.block_n == 16 && d.Npad == 16 && BM + 2 * d.in_W + 2 <= SL_ROWS &&
+                   d.epi_mode == SVX_EPI_STD && !d.residual && !getenv("SVX_NO_SLAB");
+    for (int t = 0; t < 27 && grid333; ++t)
+      grid333 = d.taps_host[4 * t] == t / 9 && d.taps_host[4 * t + 1] == (t / 3) % 3 && d.taps_host[4 * t + 2] == t % 3;
+    g->slab = grid333;
+    if (encode_map(&g->map_a, d.A, (uint64_t)rows_total, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs,
+                   g->slab ? SL_ROWS : BM)) { delete g; return 1; }
   } else {
     delete g;
     return fail("gemm: unknown a_mode %d", d.a_mode);
@@ -616,6 +810,10 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   g->bn = d.block_n;
   const int slots = sm_count() * (d.block_n <= 96 ? 2 : 1);
   g->grid = (int)(tiles < slots ? tiles : slots);
+  if (g->slab) {
+    const int num_st = (p.tiles_m + SL_TS - 1) / SL_TS;
+    g->grid = num_st < sm_count() ? num_st : sm_count();
+  }
   *out = g;
   return 0;
 }
@@ -629,6 +827,18 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void* stream) {
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = 0;
+  if (g->slab) {
+    static bool configured = false;
+    if (!configured) {
+      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM));
+      configured = true;
+    }
+    conv3_slab_kernel<<<g->grid, SL_THREADS, SL_SMEM, st>>>(g->map_a, g->map_b, g->p);
+    cudaError_t e = cudaGetLastError();
+    if (!prepared) delete g;
+    if (e != cudaSuccess) return fail("launch of conv3_slab_kernel failed: %s", cudaGetErrorString(e));
+    return 0;
+  }
   switch (g->bn) {
     case 16: rc = launch_bn<16>(g->map_a, g->map_b, g->p, g->grid, st); break;
     case 32: rc = launch_bn<32>(g->map_a, g->map_b, g->p, g->grid, st); break;

@@ -317,10 +317,11 @@ class Plan:
         return out
 
     def conv_flat(self, x, pack, taps, out, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True,
-                  out_scale=1.0, round_out=False, name=None, out_map=None, valid=None):
+                  out_scale=1.0, round_out=False, name=None, out_map=None, valid=None, cin_live=0):
         """Stride-1 convolution over a zero-padded input, A operand streamed by TMA (one shifted box per tap).
         `taps` are non-negative (dd, dh, dw) offsets from the window corner in padded coordinates; `valid` =
-        number of window corners per axis that are real outputs (default: the extents of `out`)."""
+        number of window corners per axis that are real outputs (default: the extents of `out`); `cin_live` = leading
+        channels of each tap whose weights are non-zero (lets the kernel skip the zero-padded tail of a chunk)."""
         cin = pack.K // len(taps)
         assert cin * len(taps) == pack.K and cin % 32 == 0 and cin == x.C and pack.Kpad == pack.K, (cin, x.C, pack.K)
         assert all(min(t) >= 0 for t in taps)
@@ -337,6 +338,7 @@ class Plan:
         d.valid_D, d.valid_H, d.valid_W = vD, vH, vW
         d.stride_d = d.stride_h = d.stride_w = 1
         d.ntaps = len(taps)
+        d.cin_live = cin_live
         host = (C.c_int32 * (4 * len(taps)))(*[v for t in taps for v in (t[0], t[1], t[2], 0)])
         self.keep[id(host)] = host
         d.taps_host = C.cast(host, C.c_void_p)

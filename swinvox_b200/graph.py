@@ -253,14 +253,15 @@ def _convT_layer(plan, x, conv, bn, pads, out, name, act=ACT_RELU, residual=None
     """stride-2 ConvTranspose3d as 8 parity-class implicit GEMMs; out dims are 2x the input dims."""
     dev = _dev(plan)
     od, oh, ow = 2 * x.D, 2 * x.H, 2 * x.W
-    Cs = out.Cs if isinstance(out, Act) else 1
+    assert tuple(out.inner) == (od, oh, ow)
+    ob, osn, osd, osh, osw = out.interior_map()
     for pd in (0, 1):
         for ph in (0, 1):
             for pw in (0, 1):
                 pk, taps = E.pack_convT_class(conv.weight, bn, dev, pads, (pd, ph, pw), n_logical=n_logical,
                                               block_n=block_n, bias=conv.bias)
                 vox = (pd * oh + ph) * ow + pw
-                omap = (out.c0 + vox * Cs, od * oh * ow * Cs, 2 * oh * ow * Cs, 2 * ow * Cs, 2 * Cs)
+                omap = (ob + pd * osd + ph * osh + pw * osw, osn, 2 * osd, 2 * osh, 2 * osw)
                 tail = None
                 if epi_tail is not None:
                     aux, out2 = epi_tail
@@ -272,7 +273,8 @@ def _convT_layer(plan, x, conv, bn, pads, out, name, act=ACT_RELU, residual=None
 
 
 def lower_decoder(plan, dec, feat, N):
-    """feat: Act [N,7,7,256].  Returns (raw16 Act [N,32,32,32,16] with 9 live channels, coarse [N, 32768])."""
+    """feat: Act [N,7,7,256].  Returns (raw Act: 32^3 voxels inside a zero border, 32-channel rows with 9 live
+    channels -- the layout the merger's slab convolution streams by TMA -- and coarse [N, 32768])."""
     dev = _dev(plan)
     g = plan.new_act(N, 2, 2, 2, 256)
     # AdaptiveAvgPool2d 7->2 = windows [0,4) and [3,7); the new depth axis replicates (stride_d = 0)
@@ -284,7 +286,7 @@ def lower_decoder(plan, dec, feat, N):
         o = plan.new_act(N, 2 * x.D, 2 * x.H, 2 * x.W, cout)
         _convT_layer(plan, x, layer[0], layer[1], pads, o, f"decoder.layer{li + 1}")
         x = o
-    raw = plan.new_act(N, 32, 32, 32, 16)
+    raw = plan.new_act(N, 32, 32, 32, 16, Cs=32, pad=(1, 1, 1))
     coarse = plan.empty(N, 32768)
     l5 = dec.layer5[0]
     w5 = torch.zeros(9)
@@ -300,31 +302,35 @@ def lower_decoder(plan, dec, feat, N):
 # Merger (models/merger.py:56-107)
 # --------------------------------------------------------------------------------------------------
 def lower_merger(plan, mer, raw, coarse, B, V):
-    """raw: Act [N,32,32,32,16] (9 live channels, TF32-rounded, pad channels zero); coarse: [N,32768] tensor.
-    Returns merged [B, 32768] tensor."""
+    """raw: Act of 32^3 voxels inside a (1,1,1) zero border, 32-channel rows (9 live, TF32-rounded, rest zero);
+    coarse: [N,32768] tensor.  Returns (merged [B, 32768], pre-softmax scores [N, 32768]).
+    All six Conv3d(k3,p1) layers run as TMA slab convolutions over zero-bordered 34^3 volumes."""
     dev = _dev(plan)
     N = B * V
     slope = float(mer.cfg.NETWORK.LEAKY_VALUE)
-    taps = E.conv_taps(3, 3, 3, 1, 1, 1)
-    cat = plan.new_act(N, 32, 32, 32, 64)
+    taps = E.conv_taps(3, 3, 3, 0, 0, 0)
+    cat = plan.new_act(N, 32, 32, 32, 64, pad=(1, 1, 1))   # four 16-channel groups: w1 | w2 | w3 | w4 (9 live each)
     x = raw
     for i, layer in enumerate((mer.layer1, mer.layer2, mer.layer3, mer.layer4)):
         o = cat.channels(16 * i, 16)
-        plan.conv(x, E.pack_conv(layer[0].weight, layer[0].bias, layer[1], dev, cin_pad=16, n_logical=16, block_n=16), taps, o,
-                  act=ACT_LEAKY, act_param=slope, round_out=True, name=f"merger.layer{i + 1}")
+        pk = E.pack_conv(layer[0].weight, layer[0].bias, layer[1], dev, cin_pad=32, n_logical=16, block_n=16)
+        # the 32-channel TMA box starts at the group's first channel; weights beyond the 9 live channels are zero
+        plan.conv_flat(Act(x.buf, N, 34, 34, 34, 32, x.c0, (1, 1, 1)), pk, taps, o, act=ACT_LEAKY, act_param=slope,
+                       round_out=True, cin_live=9, name=f"merger.layer{i + 1}")
         x = o
     # layer5 sees cat(w1..w4): reference channel 9*g + c lives at 16*g + c here
     w5 = mer.layer5[0].weight.detach().float()
     w5p = torch.zeros(9, 64, 3, 3, 3, device=w5.device)
     for gi in range(4):
         w5p[:, 16 * gi:16 * gi + 9] = w5[:, 9 * gi:9 * gi + 9]
-    t = plan.new_act(N, 32, 32, 32, 16)
-    plan.conv(cat, E.pack_conv(w5p, mer.layer5[0].bias, mer.layer5[1], dev, cin_pad=64, n_logical=16, block_n=16), taps, t,
-              act=ACT_LEAKY, act_param=slope, round_out=True, name="merger.layer5")
+    t = plan.new_act(N, 32, 32, 32, 16, Cs=32, pad=(1, 1, 1))
+    plan.conv_flat(cat, E.pack_conv(w5p, mer.layer5[0].bias, mer.layer5[1], dev, cin_pad=64, n_logical=16, block_n=16),
+                   taps, t, act=ACT_LEAKY, act_param=slope, round_out=True, cin_live=57, name="merger.layer5")
     wts = plan.empty(N, 32768)
     wact = Act(wts.view(-1, 1), N, 32, 32, 32, 1, 0)
-    pk6 = E.pack_conv(mer.layer6[0].weight, mer.layer6[0].bias, mer.layer6[1], dev, cin_pad=16, block_n=16)
-    plan.conv(t, pk6, taps, wact, act=ACT_LEAKY, act_param=slope, name="merger.layer6")
+    pk6 = E.pack_conv(mer.layer6[0].weight, mer.layer6[0].bias, mer.layer6[1], dev, cin_pad=32, block_n=16)
+    plan.conv_flat(Act(t.buf, N, 34, 34, 34, 32, 0, (1, 1, 1)), pk6, taps, wact, act=ACT_LEAKY, act_param=slope,
+                   cin_live=9, name="merger.layer6")
     merged = plan.empty(B, 32768)
     plan.merger_fuse(wts, coarse, merged, B, V, 32768, name="merger.softmax_fuse")
     return merged, wts

@@ -1,10 +1,11 @@
 """Drop-in for the reference's models/merger.py (:10-107): per-view 3-D conv stack producing voxel-wise scores,
 softmax over the views and weighted fusion of the coarse volumes.  forward() replays graph.lower_merger."""
+import torch
 import torch.nn as nn
 
 from .. import engine as E
 from .. import graph
-from ._base import src_key, ChannelsLastInput, PlanarInput, PlannedModule, mark_owned
+from ._base import PlanarInput, PlannedModule, mark_owned, owned_src, src_key
 
 
 class Merger(PlannedModule):
@@ -30,13 +31,18 @@ class Merger(PlannedModule):
 
         def build():
             plan = E.Plan(raw_features.device)
-            raw = ChannelsLastInput(plan, raw_features, N, 9, 32768, 16, round_in=True)
+            src = owned_src(raw_features)
+            bound = isinstance(src, torch.Tensor) and tuple(src.shape) == (N * 34 ** 3, 32)
+            # the decoder's own output buffer (zero-bordered 34^3 x 32-channel rows), or a private one
+            raw = E.Act(plan.hold(src) if bound else plan.zeros(N * 34 ** 3, 32), N, 34, 34, 34, 16, 0, (1, 1, 1))
             coarse = PlanarInput(plan, coarse_volumes, (N, 32768))
-            merged, weights = graph.lower_merger(plan, self, E.Act(raw.buf, N, 32, 32, 32, 16), coarse.buf, B, V)
-            return plan, raw, coarse, merged, weights
+            merged, weights = graph.lower_merger(plan, self, raw, coarse.buf, B, V)
+            return plan, (raw, bound), coarse, merged, weights
 
-        plan, raw, coarse, merged, weights = self._plan_for((B, V, str(raw_features.device), src_key(raw_features), src_key(coarse_volumes)), build)
-        raw.feed(raw_features)
+        plan, (raw, bound), coarse, merged, weights = self._plan_for(
+            (B, V, str(raw_features.device), src_key(raw_features), src_key(coarse_volumes)), build)
+        if not bound:   # foreign [B,V,9,32,32,32] tensor: re-layout into the interior (module-boundary path only)
+            raw.view()[..., :9].copy_(E.tf32_round(raw_features.reshape(N, 9, 32, 32, 32)).permute(0, 2, 3, 4, 1))
         coarse.feed(coarse_volumes)
         plan.run(self.use_graph)
         self.last_volume_weights = weights.view(B, V, 32, 32, 32)   # pre-softmax scores (parity/debug)

@@ -91,7 +91,9 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
                                 d.taps_host[tap * 4 + 2];
           const bool ok = row < d.lda;  // TMA zero-fills rows past the end of the matrix
           const float* px = d.A + row * d.in_Cs + d.in_c0;
-          for (int c = 0; c < d.Cin; ++c) arow[tap * d.Cin + c] = ok ? tf32_trunc(px[c]) : 0.f;
+          // TMA zero-fills columns past the end of a row as well (a 32-channel box may overhang the tensor)
+          for (int c = 0; c < d.Cin; ++c)
+            arow[tap * d.Cin + c] = (ok && d.in_c0 + c < d.in_Cs) ? tf32_trunc(px[c]) : 0.f;
         }
       } else {
         for (int tap = 0; tap < d.ntaps; ++tap) {

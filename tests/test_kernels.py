@@ -166,6 +166,63 @@ def test_conv3d_padded_channels(dev):
     assert got[:, 9:].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("dims,groups", [((6, 7, 9), 1), ((5, 32, 32), 1), ((4, 6, 8), 4), ((3, 32, 32), 4)])
+def test_conv3d_slab_merger_style(dev, dims, groups):
+    """merger-style Conv3d(k3, p1) with 9 output channels over a zero-bordered volume: the TMA slab kernel
+    (27 taps addressed inside three depth slabs).  groups=4 is layer5 (input = four 16-channel groups, 9 live each),
+    groups=1 the 9->9 layers reading a 32-channel box at a channel offset; outputs go to a channel group of another
+    zero-bordered buffer and, like layer6, to a planar single-channel volume."""
+    DEV = dev
+    torch.manual_seed(sum(dims) + groups)
+    D, H, W = dims
+    n = 2
+    cin = 9 * groups
+    x = E.tf32_round(torch.randn(n, cin, D, H, W))
+    conv = torch.nn.Conv3d(cin, 9, 3, padding=1)
+    bn = rand_bn(torch.nn.BatchNorm3d(9))
+    conv1 = torch.nn.Conv3d(cin, 1, 3, padding=1)
+    p = E.Plan(DEV)
+    src = p.new_act(n, D, H, W, 64, pad=(1, 1, 1))
+    xv = src.view()
+    for g in range(groups):
+        xv[..., 16 * g + (16 if groups == 1 else 0):][..., :9].copy_(x[:, 9 * g:9 * g + 9].permute(0, 2, 3, 4, 1))
+    if groups == 1:
+        xin = E.Act(src.buf, n, D + 2, H + 2, W + 2, 32, 16, (1, 1, 1))
+        pk = E.pack_conv(conv.weight, conv.bias, bn, DEV, cin_pad=32, n_logical=16, block_n=16)
+        pk1 = E.pack_conv(conv1.weight, conv1.bias, None, DEV, cin_pad=32, block_n=16)
+        live = 9
+    else:
+        xin = src
+        def spread(w):
+            wp = torch.zeros(w.shape[0], 64, 3, 3, 3)
+            for g in range(4):
+                wp[:, 16 * g:16 * g + 9] = w[:, 9 * g:9 * g + 9]
+            return wp
+        pk = E.pack_conv(spread(conv.weight.detach()), conv.bias, bn, DEV, cin_pad=64, n_logical=16, block_n=16)
+        pk1 = E.pack_conv(spread(conv1.weight.detach()), conv1.bias, None, DEV, cin_pad=64, block_n=16)
+        live = 57
+    taps = E.conv_taps(3, 3, 3, 0, 0, 0)
+    dst = p.new_act(n, D, H, W, 64, pad=(1, 1, 1))
+    out = dst.channels(32, 16)
+    p.conv_flat(xin, pk, taps, out, act=E.ACT_LEAKY, act_param=0.2, round_out=False, cin_live=live)
+    planar = p.empty(n, D * H * W)
+    p.conv_flat(xin, pk1, taps, E.Act(planar.view(-1, 1), n, D, H, W, 1, 0), cin_live=live)
+    p.run()
+    sync(DEV)
+    wf, bf = E.fold_bn(conv.weight, conv.bias, bn)
+    ref = F.leaky_relu(F.conv3d(x.double(), E.tf32_round(wf).double(), bf.double(), padding=1), 0.2)
+    got = out.view().permute(0, 4, 1, 2, 3).cpu()
+    assert rel_err(got[:, :9], ref) < 1e-4
+    assert got[:, 9:].abs().max().item() == 0.0
+    full = dst.buf.view(n, D + 2, H + 2, W + 2, 64).cpu()
+    assert full[:, 0].abs().max() == 0 and full[:, -1].abs().max() == 0 and full[:, :, 0].abs().max() == 0 and \
+        full[:, :, -1].abs().max() == 0 and full[:, :, :, 0].abs().max() == 0 and full[:, :, :, -1].abs().max() == 0, \
+        "the zero border must stay untouched"
+    assert full[..., :32].abs().max() == 0 and full[..., 48:].abs().max() == 0, "other channel groups must stay untouched"
+    ref1 = F.conv3d(x.double(), E.tf32_round(conv1.weight.detach()).double(), conv1.bias.detach().double(), padding=1)
+    assert rel_err(planar.view(n, 1, D, H, W).cpu(), ref1) < 1e-4
+
+
 @pytest.mark.parametrize("ks,pads,ind", [((4, 4, 4), (1, 1, 1), (3, 4, 5)), ((6, 4, 4), (2, 1, 1), (2, 2, 2))])
 def test_convtranspose3d_classes(dev, ks, pads, ind):
     DEV = dev
