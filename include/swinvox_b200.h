@@ -31,7 +31,7 @@ extern "C" {
 /* activation codes for svx_gemm_desc.act */
 enum { SVX_ACT_NONE = 0, SVX_ACT_RELU = 1, SVX_ACT_LEAKY = 2, SVX_ACT_GELU = 3 };
 /* A operand modes */
-enum { SVX_A_PLAIN = 0, SVX_A_GATHER = 1, SVX_A_FLAT = 2 };
+enum { SVX_A_PLAIN = 0, SVX_A_GATHER = 1, SVX_A_FLAT = 2, SVX_A_SLAB3 = 3 };
 /* special epilogues */
 enum { SVX_EPI_STD = 0, SVX_EPI_DEC_TAIL = 1 /* decoder layer4+layer5+cat, decoder.py:80-89 */ };
 /* pooling modes */
@@ -56,6 +56,13 @@ enum { SVX_POOL_MAX = 0, SVX_POOL_AVG = 1 };
  *                 of the window corner; tap t reads row r + (dd*in_H + dh)*in_W + dw (taps >= 0), streamed by
  *                 TMA one 32-channel chunk at a time.  Cin must be a multiple of 32.  Rows decode over
  *                 out_{D,H,W} = in_{D,H,W}; only rows with od < valid_D, oh < valid_H, ow < valid_W are stored.
+ *   SVX_A_SLAB3 : 3x3x3 stride-1 convolution with N <= 16 output channels over a zero-bordered channels-last
+ *                 volume [vol, in_D, in_H, in_W, in_Cs] (in_D = valid_D + 2; lda = total rows), reading the 32
+ *                 channels starting at in_c0 (a box that overhangs in_Cs reads zeros); output voxel (vol, d, h, w),
+ *                 d < valid_D, h < valid_H, w < valid_W, sums taps (d+kd, h+kh, w+kw).  M = vol*valid_D*valid_H*
+ *                 valid_W.  Weights are laid out for the kw-in-N formulation: W is [48, 288] with
+ *                 row = kw*16 + co, col = (kd*3 + kh)*32 + c; block_n = Npad = 48, K = Kpad = 288; cin_live =
+ *                 leading channels with non-zero weights (contraction steps beyond them are skipped).
  * W: [Npad, Kpad] fp32, K contiguous, zero padded, values pre-rounded to TF32 (rna) by the host.
  * result = out_scale * (res_after_act ? act(acc+bias) + res : act(acc+bias+res)).
  * Output row r is stored at out + o_base + n*o_sn + od*o_sd + oh*o_sh + ow*o_sw (elements),
@@ -64,7 +71,7 @@ enum { SVX_POOL_MAX = 0, SVX_POOL_AVG = 1 };
 typedef struct svx_gemm_desc {
   int32_t M, N, K;          /* logical sizes; N columns are written */
   int32_t Kpad, Npad;       /* padded weight extents (Kpad % 32 == 0, Npad % block_n == 0) */
-  int32_t block_n;          /* N tile: 16, 32, 64, 96, 128, 192 or 256 */
+  int32_t block_n;          /* N tile: 16, 32, 64, 96, 128, 192 or 256 (48 in slab mode) */
   int32_t a_mode;
   const float* A;
   int64_t lda;              /* plain: row stride (elements); flat: number of rows of the padded matrix */
@@ -91,8 +98,8 @@ typedef struct svx_gemm_desc {
   const float* epi_aux;     /* SVX_EPI_DEC_TAIL: layer5 weights w5[0..7], bias w5[8] */
   float* epi_out2;          /* SVX_EPI_DEC_TAIL: planar coarse volume [n, OD*OH*OW] */
   int64_t o2_base, o2_sn, o2_sd, o2_sh, o2_sw;
-  int32_t cin_live;         /* flat mode: only the first cin_live of the Cin channels of a tap carry non-zero weights
-                               (0 = all); the kernel may skip the contraction steps beyond them */
+  int32_t cin_live;         /* slab mode: only the first cin_live of the 32 box channels carry non-zero weights
+                               (0 = all); the kernel skips the contraction steps beyond them */
   int32_t reserved0;
 } svx_gemm_desc;
 

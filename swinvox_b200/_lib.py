@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libswinvox_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU = 0, 1, 2, 3
-A_PLAIN, A_GATHER, A_FLAT = 0, 1, 2
+A_PLAIN, A_GATHER, A_FLAT, A_SLAB3 = 0, 1, 2, 3
 EPI_STD, EPI_DEC_TAIL = 0, 1
 POOL_MAX, POOL_AVG = 0, 1
 

@@ -46,8 +46,7 @@ struct GemmParams {
   int valid_D, valid_H, valid_W;
   int sd, sh, sw;
   int chunks_per_tap;
-  int cin_live;             // flat mode: channels of a tap with non-zero weights (slab kernel skips the rest)
-  int slab_base_off;        // slab kernel: encode the swizzle phase of a shifted operand in the descriptor
+  int cin_live;             // slab mode: leading channels of the 32-channel box that carry non-zero weights
   const int4* taps;
   const float* bias;
   const float* residual;
@@ -232,8 +231,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t tmem_base = *tmem_slot_gen;
 
   if (warp == 4) {
-    // ---- TMA producer ---------------------------------------------------------------------
-    if (lane == 0) {
+    // ---- TMA producer (one elected thread: elect.sync lets ptxas issue the uniform-datapath TMA / MMA
+    // instructions directly instead of wrapping each in a divergence loop) ----------------------------
+    if (elect_one()) {
       uint32_t g = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
@@ -261,7 +261,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncwarp();
   } else if (warp == 5) {
     // ---- MMA issuer -----------------------------------------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
       uint32_t g = 0, it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -467,62 +467,66 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
 
 // =====================================================================================================
-// Slab kernel: 3x3x3 stride-1 Conv3d with <= 16 output channels over a zero-padded channels-last volume
-// (the merger's layers, merger.py:20-54).  The general kernel re-fetches the A tile for each of the 27 taps
-// (27x L2 traffic for a contraction whose N is 9); here each (tile, 32-channel chunk) loads three 200-row
-// slabs (one per depth tap) ONCE by TMA and all nine (kh, kw) taps of a slab are MMA operands addressed by
-// shifting the smem descriptor's start address by (kh*Wp + kw) rows (base_offset carries the swizzle phase).
-// Weights stay resident in smem; 16 tiles accumulate side by side in TMEM (2 x 16 x 16 columns).
+// Slab kernel: 3x3x3 stride-1 Conv3d with <= 16 output channels over a zero-bordered channels-last volume
+// (the merger's layers, merger.py:20-54).  With so few output channels a tcgen05.mma is bound by reading its
+// A operand from shared memory (~76 cycles per 128x8 fp32 block whatever N is, measured), so the kernel
+//   * marches along depth: one work unit = (volume, 126-row column of the (h,w) plane); each 200-row depth slab
+//     is loaded ONCE by TMA into a ring and serves the three output depths that touch it,
+//   * folds the kw taps into the MMA's N dimension: D[u, kw*16+co] = sum_{kd,kh,c} X[u + (kd*Hp+kh)*Wp, c] *
+//     W[kd,kh,kw,c,co], nine shifted-A MMAs per k-step instead of 27 (the (kd,kh) shift is a start-address shift
+//     of the smem descriptor inside the slab; the 128B swizzle is a function of the absolute smem address),
+//   * finishes out[u, co] = D[u, 0, co] + D[u+1, 1, co] + D[u+2, 2, co] in the epilogue with warp shuffles (rows
+//     are TMEM lanes); the two rows that cross a warp's lane quarter go through a small smem exchange, and tiles
+//     overlap by two rows.
+// Weights ([48, 9*32], row = kw*16+co, col = (kd*3+kh)*32 + c) stay resident in smem; eight accumulators ring
+// in TMEM so the epilogue of one depth overlaps the MMAs of the next.
 // =====================================================================================================
-constexpr int SL_TS = 16;                  // tiles per super-tile (TMEM: 2 sets x 16 tiles x 16 columns)
-constexpr int SL_ROWS = 200;               // slab rows: 128 + 2*Wp + 2 <= 200  (Wp <= 35)
-constexpr int SL_SLAB_BYTES = SL_ROWS * 128;
-constexpr int SL_STAGE_BYTES = 3 * SL_SLAB_BYTES;
-constexpr int SL_W_BYTES = 27 * 16 * 128;  // 27 taps x [16 x 32] fp32
-constexpr int SL_THREADS = 192;
-constexpr int SL_SMEM = 1024 + SL_W_BYTES + 2 * SL_STAGE_BYTES + 256;
+constexpr int S3_ROWS = 200;                       // slab rows: 128 + 2*Wp <= 200  (Wp <= 36)
+constexpr int S3_SLAB_BYTES = S3_ROWS * 128;       // 25 x 1024
+constexpr int S3_NSLAB = 5;
+constexpr int S3_N = 48;                           // MMA N: 3 kw groups x 16 output channels
+constexpr int S3_TAP_BYTES = S3_N * 128;           // one (kd,kh) weight block: 6 x 1024
+constexpr int S3_W_BYTES = 9 * S3_TAP_BYTES;
+constexpr int S3_NACC = 8, S3_ACC_STRIDE = 64;     // TMEM: 8 accumulators of 48 (stride 64) columns
+constexpr int S3_STEP = BM - 2;                    // valid rows per tile
+constexpr int S3_THREADS = 320;                   // warps 0-3 / 6-9: two epilogue sets, 4: TMA, 5: MMA
+constexpr int S3_XCHG_BYTES = 2 * BM * 128;        // per epilogue set: 128 rows x (D1[16] | D2[16]) staged for the row shift
+constexpr int S3_SMEM = 1024 + S3_W_BYTES + S3_NSLAB * S3_SLAB_BYTES + S3_XCHG_BYTES + 256;
 
-__device__ __forceinline__ uint64_t umma_desc_sw128_shifted(uint32_t smem_addr, int with_base_offset) {
-  // operand that starts in the middle of a 1024-byte swizzle atom.  The 128B swizzle is a function of the absolute
-  // shared-memory address (bits 4-6 ^= bits 7-9), which is also how TMA wrote the slab, so a plain start-address
-  // shift addresses the right bytes; `with_base_offset` additionally sets base_offset = (start >> 7) & 7
-  // (kept switchable: SVX_SLAB_BASEOFF=1).
-  uint64_t d = umma_desc_sw128(smem_addr);
-  if (with_base_offset) d |= static_cast<uint64_t>((smem_addr >> 7) & 7u) << 49;
-  return d;
-}
-
-__global__ void __launch_bounds__(SL_THREADS, 1)
+__global__ void __launch_bounds__(S3_THREADS, 1)
 conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t w_smem = smem_base;
-  const uint32_t slab_smem = smem_base + SL_W_BYTES;
-  const uint32_t bar_base = slab_smem + 2 * SL_STAGE_BYTES;
-  // barriers: slab_full[2], slab_empty[2], w_full, w_empty, acc_full[2], acc_empty[2], tmem slot
-  auto slab_full = [&](int s) { return bar_base + 8u * s; };
-  auto slab_empty = [&](int s) { return bar_base + 8u * (2 + s); };
-  const uint32_t w_full = bar_base + 8u * 4, w_empty = bar_base + 8u * 5;
-  auto acc_full = [&](int a) { return bar_base + 8u * (6 + a); };
-  auto acc_empty = [&](int a) { return bar_base + 8u * (8 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * 10;
+  const uint32_t slab_smem = smem_base + S3_W_BYTES;
+  constexpr int kXchgOff = S3_W_BYTES + S3_NSLAB * S3_SLAB_BYTES;
+  float* xchg = reinterpret_cast<float*>(smem_gen + kXchgOff);
+  const uint32_t bar_base = smem_base + kXchgOff + S3_XCHG_BYTES;
+  // barriers: slab_full[5], slab_empty[5], w_full, acc_full[8], acc_empty[8], tmem slot
+  auto slab_full = [&](uint32_t s) { return bar_base + 8u * s; };
+  auto slab_empty = [&](uint32_t s) { return bar_base + 8u * (S3_NSLAB + s); };
+  const uint32_t w_full = bar_base + 8u * (2 * S3_NSLAB);
+  auto acc_full = [&](uint32_t a) { return bar_base + 8u * (2 * S3_NSLAB + 1 + a); };
+  auto acc_empty = [&](uint32_t a) { return bar_base + 8u * (2 * S3_NSLAB + 1 + S3_NACC + a); };
+  constexpr int kSlotIdx = 2 * S3_NSLAB + 1 + 2 * S3_NACC;
+  const uint32_t tmem_slot = bar_base + 8u * kSlotIdx;
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + SL_W_BYTES + 2 * SL_STAGE_BYTES + 8 * 10);
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kXchgOff + S3_XCHG_BYTES + 8 * kSlotIdx);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nch = (p.cin_live + BK - 1) / BK;   // channel chunks that carry non-zero weights
   const int Wp = p.in_W, HWp = p.in_H * p.in_W;
-  const int num_tiles = p.tiles_m;
-  const int num_st = (num_tiles + SL_TS - 1) / SL_TS;
+  const int nd = p.valid_D;                 // output depths per unit; the unit streams nd + 2 slabs
+  const int ncol = p.tiles_n;               // 126-row columns per (h,w) plane
+  const int num_units = p.tiles_m;          // volumes x columns
 
   if (warp == 4 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); }
   if (warp == 5) {
     if (lane == 0) {
-      for (int s = 0; s < 2; ++s) { mbar_init(slab_full(s), 1u); mbar_init(slab_empty(s), 1u); }
-      mbar_init(w_full, 1u); mbar_init(w_empty, 1u);
-      for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1u); mbar_init(acc_empty(a), 4u); }
+      for (uint32_t s = 0; s < S3_NSLAB; ++s) { mbar_init(slab_full(s), 1u); mbar_init(slab_empty(s), 1u); }
+      mbar_init(w_full, 1u);
+      for (uint32_t a = 0; a < S3_NACC; ++a) { mbar_init(acc_full(a), 1u); mbar_init(acc_empty(a), 4u); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -534,111 +538,200 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   const uint32_t tmem_base = *tmem_slot_gen;
 
   if (warp == 4) {
-    if (lane == 0) {
-      uint32_t g = 0, wload = 0;
-      for (int st = blockIdx.x; st < num_st; st += gridDim.x) {
-        const int t_end = min(SL_TS, num_tiles - st * SL_TS);
-        for (int ch = 0; ch < nch; ++ch) {
-          if (nch > 1 || wload == 0) {   // weights of this channel chunk (resident for single-chunk layers)
-            mbar_wait(w_empty, (wload & 1u) ^ 1u);
-            mbar_arrive_expect_tx(w_full, SL_W_BYTES);
-            for (int tap = 0; tap < 27; ++tap)
-              tma_load_2d(w_smem + tap * 2048, &map_w, w_full, tap * p.Cin + ch * BK, 0);
-            ++wload;
-          }
-          for (int t = 0; t < t_end; ++t, ++g) {
-            const int s = g & 1;
-            mbar_wait(slab_empty(s), ((g >> 1) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(slab_full(s), SL_STAGE_BYTES);
-            const int q0 = (st * SL_TS + t) * BM;
-            for (int kd = 0; kd < 3; ++kd)
-              tma_load_2d(slab_smem + s * SL_STAGE_BYTES + kd * SL_SLAB_BYTES, &map_x, slab_full(s),
-                          p.in_c0 + ch * BK, q0 + kd * HWp);
-          }
+    // ---- TMA producer: weights once, then one slab per (unit, plane) ---------------------------------
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w_full, S3_W_BYTES);
+      for (int t = 0; t < 9; ++t) tma_load_2d(w_smem + t * S3_TAP_BYTES, &map_w, w_full, t * BK, 0);
+      uint32_t g = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int n = unit / ncol, col = unit - n * ncol;
+        const int row0 = n * p.in_D * HWp + col * S3_STEP;
+        for (int pl = 0; pl < nd + 2; ++pl, ++g) {
+          const uint32_t s = g % S3_NSLAB;
+          mbar_wait(slab_empty(s), ((g / S3_NSLAB) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(slab_full(s), S3_SLAB_BYTES);
+          tma_load_2d(slab_smem + s * S3_SLAB_BYTES, &map_x, slab_full(s), p.in_c0, row0 + pl * HWp);
         }
       }
     }
     __syncwarp();
   } else if (warp == 5) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(BM, 16);
-      uint32_t g = 0, wuse = 0, it = 0;
-      for (int st = blockIdx.x; st < num_st; st += gridDim.x, ++it) {
-        const int t_end = min(SL_TS, num_tiles - st * SL_TS);
-        const uint32_t set = it & 1u;
-        mbar_wait(acc_empty(set), ((it >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        for (int ch = 0; ch < nch; ++ch) {
-          const int ksteps = min(BK / UMMA_K, (p.cin_live - ch * BK + UMMA_K - 1) / UMMA_K);
-          if (nch > 1 || wuse == 0) {
-            mbar_wait(w_full, wuse & 1u);
-            tc_fence_after();
-            ++wuse;
+    // ---- MMA issuer -----------------------------------------------------------------------------------
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BM, S3_N);
+      const int ksteps = (p.cin_live + UMMA_K - 1) / UMMA_K;
+      mbar_wait(w_full, 0u);
+      tc_fence_after();
+      uint32_t sbase = 0, waited = 0, tg = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        for (int d = 0; d < nd; ++d, ++tg) {
+          while (waited < sbase + d + 3) {   // slabs d, d+1, d+2 of this unit
+            mbar_wait(slab_full(waited % S3_NSLAB), (waited / S3_NSLAB) & 1u);
+            ++waited;
           }
-          for (int t = 0; t < t_end; ++t, ++g) {
-            const int s = g & 1;
-            mbar_wait(slab_full(s), (g >> 1) & 1u);
-            tc_fence_after();
-            const uint32_t acc = tmem_base + set * (SL_TS * 16) + t * 16;
-            for (int kd = 0; kd < 3; ++kd) {
-              const uint32_t slab = slab_smem + s * SL_STAGE_BYTES + kd * SL_SLAB_BYTES;
-              for (int kh = 0; kh < 3; ++kh) {
+          const uint32_t a = tg % S3_NACC;
+          mbar_wait(acc_empty(a), ((tg / S3_NACC) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t acc = tmem_base + a * S3_ACC_STRIDE;
+          for (int kd = 0; kd < 3; ++kd) {
+            const uint32_t slab = slab_smem + ((sbase + d + kd) % S3_NSLAB) * S3_SLAB_BYTES;
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                  const int tap = (kd * 3 + kh) * 3 + kw;
-                  const uint64_t da = umma_desc_sw128_shifted(slab + (kh * Wp + kw) * 128, p.slab_base_off);
-                  const uint64_t db = umma_desc_sw128(w_smem + tap * 2048);
-                  for (int k = 0; k < ksteps; ++k)
-                    umma_tf32(acc, da + 2u * k, db + 2u * k, idesc, (ch | tap | k) != 0 ? 1u : 0u);
-                }
-              }
+            for (int kh = 0; kh < 3; ++kh) {
+              const uint64_t da = umma_desc_sw128(slab + kh * Wp * 128);
+              const uint64_t db = umma_desc_sw128(w_smem + (kd * 3 + kh) * S3_TAP_BYTES);
+              for (int k = 0; k < ksteps; ++k)
+                umma_tf32(acc, da + 2u * k, db + 2u * k, idesc, (kd | kh | k) != 0 ? 1u : 0u);
             }
-            umma_commit(slab_empty(s));
           }
-          if (nch > 1) umma_commit(w_empty);
+          umma_commit(slab_empty((sbase + d) % S3_NSLAB));   // plane d is not needed by later depths
+          if (d == nd - 1) {
+            umma_commit(slab_empty((sbase + d + 1) % S3_NSLAB));
+            umma_commit(slab_empty((sbase + d + 2) % S3_NSLAB));
+          }
+          umma_commit(acc_full(a));
         }
-        umma_commit(acc_full(set));
+        sbase += nd + 2;
       }
     }
     __syncwarp();
   } else {
-    // epilogue: one thread = one output voxel (16 channels = 64 contiguous bytes)
-    uint32_t it = 0;
-    for (int st = blockIdx.x; st < num_st; st += gridDim.x, ++it) {
-      const int t_end = min(SL_TS, num_tiles - st * SL_TS);
-      const uint32_t set = it & 1u;
-      mbar_wait(acc_full(set), (it >> 1) & 1u);
-      tc_fence_after();
-      for (int t = 0; t < t_end; ++t) {
-        long long off = 0, off2 = 0;
-        const bool valid = decode_row(p, (st * SL_TS + t) * BM + warp * 32 + lane, off, off2);
-        uint32_t v[16];
+    // ---- epilogue: one thread = one row u of the tile; out[u] = D0[u] + D1[u+1] + D2[u+2].  Two sets of four
+    // warps (0-3: even tiles, 6-9: odd tiles) so two tiles drain concurrently; the row shift goes through a
+    // swizzled smem staging buffer per set (rows u+1, u+2 may belong to another warp's TMEM lane quarter). ------
+    const int quarter = warp & 3;
+    const uint32_t set = warp >= 6 ? 1u : 0u;
+    const int r = quarter * 32 + lane;
+    const int r1 = min(r + 1, BM - 1), r2 = min(r + 2, BM - 1);
+    char* xb = reinterpret_cast<char*>(xchg) + set * (BM * 128);
+    char* my_row = xb + r * 128;
+    const char* row1 = xb + r1 * 128;
+    const char* row2 = xb + r2 * 128;
+    const int barid = 1 + static_cast<int>(set);
+    float bias[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) bias[q] = p.bias ? __ldg(p.bias + q) : 0.f;
+    const float slope = p.act_param, scale = p.out_scale;
+    const bool has_res = p.residual != nullptr;
+    const bool pre = has_res && !p.res_after_act, post = has_res && p.res_after_act;
+    const bool full16 = p.N == 16 && p.vec_ok;
+    uint32_t tg = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int n = unit / ncol, col = unit - n * ncol;
+      const int u = col * S3_STEP + r;
+      const int h = u / Wp, w = u - h * Wp;
+      const bool row_ok = r < S3_STEP && h < p.valid_H && w < p.valid_W;
+      const long long off0 = p.o_base + n * p.o_sn + h * p.o_sh + w * p.o_sw;
+      for (int d = 0; d < nd; ++d, ++tg) {
+        if ((tg & 1u) != set) continue;
+        const uint32_t a = tg % S3_NACC;
+        mbar_wait(acc_full(a), (tg / S3_NACC) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + a * S3_ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
+        uint32_t d0[16], d1[16], d2[16];
         __syncwarp();
-        tmem_ld16(tmem_base + set * (SL_TS * 16) + t * 16 + (static_cast<uint32_t>(warp * 32) << 16), v);
+        tmem_ld16(taddr, d0);
+        tmem_ld16(taddr + 16, d1);
+        tmem_ld16(taddr + 32, d2);
         tmem_ld_wait();
-        if (valid) {
-          float x[16];
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(a));   // the accumulator is in registers: hand it back
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            float tv = __uint_as_float(v[q]) + (p.bias ? __ldg(p.bias + q) : 0.f);
-            tv = apply_act(tv, p.act, p.act_param) * p.out_scale;
-            x[q] = p.round_tf32 ? round_tf32(tv) : tv;
-          }
+        for (int c = 0; c < 4; ++c) {
+          *reinterpret_cast<uint4*>(my_row + ((c ^ (r & 7)) << 4)) = make_uint4(d1[4 * c], d1[4 * c + 1], d1[4 * c + 2], d1[4 * c + 3]);
+          *reinterpret_cast<uint4*>(my_row + (((c + 4) ^ (r & 7)) << 4)) = make_uint4(d2[4 * c], d2[4 * c + 1], d2[4 * c + 2], d2[4 * c + 3]);
+        }
+        named_bar_sync(barid, 128);
+        float x[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 s1 = *reinterpret_cast<const float4*>(row1 + ((c ^ (r1 & 7)) << 4));
+          const float4 s2 = *reinterpret_cast<const float4*>(row2 + (((c + 4) ^ (r2 & 7)) << 4));
+          x[4 * c + 0] = (__uint_as_float(d0[4 * c + 0]) + s1.x) + (s2.x + bias[4 * c + 0]);
+          x[4 * c + 1] = (__uint_as_float(d0[4 * c + 1]) + s1.y) + (s2.y + bias[4 * c + 1]);
+          x[4 * c + 2] = (__uint_as_float(d0[4 * c + 2]) + s1.z) + (s2.z + bias[4 * c + 2]);
+          x[4 * c + 3] = (__uint_as_float(d0[4 * c + 3]) + s1.w) + (s2.w + bias[4 * c + 3]);
+        }
+        named_bar_sync(barid, 128);   // staging buffer may be overwritten by this set's next tile
+        if (row_ok) {
+          const long long off = off0 + d * p.o_sd;
           float* dst = p.out + off;
-          if (p.vec_ok) {
+          if (full16) {
+            if (has_res) {
+              float rv[16];
 #pragma unroll
-            for (int q = 0; q < 16; q += 4)
-              if (q < p.N) *reinterpret_cast<float4*>(dst + q) = make_float4(x[q], x[q + 1], x[q + 2], x[q + 3]);
+              for (int c = 0; c < 4; ++c) {
+                const float4 t4 = *reinterpret_cast<const float4*>(p.residual + off + 4 * c);
+                rv[4 * c] = t4.x; rv[4 * c + 1] = t4.y; rv[4 * c + 2] = t4.z; rv[4 * c + 3] = t4.w;
+              }
+              if (pre) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) x[q] += rv[q];
+              }
+              switch (p.act) {
+                case SVX_ACT_RELU:
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) x[q] = fmaxf(x[q], 0.f);
+                  break;
+                case SVX_ACT_LEAKY:
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) x[q] = act_t<SVX_ACT_LEAKY>(x[q], slope);
+                  break;
+                case SVX_ACT_GELU:
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) x[q] = gelu_erf(x[q]);
+                  break;
+                default: break;
+              }
+              if (post) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) x[q] += rv[q];
+              }
+            } else {
+              switch (p.act) {
+                case SVX_ACT_RELU:
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) x[q] = fmaxf(x[q], 0.f);
+                  break;
+                case SVX_ACT_LEAKY:
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) x[q] = act_t<SVX_ACT_LEAKY>(x[q], slope);
+                  break;
+                case SVX_ACT_GELU:
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) x[q] = gelu_erf(x[q]);
+                  break;
+                default: break;
+              }
+            }
+            if (scale != 1.f) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) x[q] *= scale;
+            }
+            if (p.round_tf32) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) x[q] = round_tf32(x[q]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
           } else {
+            // few output channels (layer6: one) or unaligned destinations: scalar path over the first N columns
 #pragma unroll
-            for (int q = 0; q < 16; ++q)
-              if (q < p.N) dst[q] = x[q];
+            for (int q = 0; q < 16; ++q) {
+              if (q < p.N) {
+                float tv = x[q];
+                const float rv = has_res ? p.residual[off + q] : 0.f;
+                if (pre) tv += rv;
+                tv = apply_act(tv, p.act, slope);
+                if (post) tv += rv;
+                tv *= scale;
+                dst[q] = p.round_tf32 ? round_tf32(tv) : tv;
+              }
+            }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(set));
     }
   }
   tc_fence_before();
@@ -711,14 +804,14 @@ struct GemmPrepared {
   CUtensorMap map_a, map_b;
   GemmParams p;
   int bn, grid;
-  bool slab = false;   // 3x3x3, N <= 16 flat conv handled by conv3_slab_kernel
+  bool slab = false;   // SVX_A_SLAB3: handled by conv3_slab_kernel
 };
 
 int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   *out = nullptr;
   SVX_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "gemm: empty problem M=%d N=%d K=%d", d.M, d.N, d.K);
   SVX_REQUIRE(d.block_n == 16 || d.block_n == 32 || d.block_n == 64 || d.block_n == 96 || d.block_n == 128 ||
-                  d.block_n == 192 || d.block_n == 256,
+                  d.block_n == 192 || d.block_n == 256 || (d.block_n == 48 && d.a_mode == SVX_A_SLAB3),
               "gemm: block_n=%d unsupported", d.block_n);
   SVX_REQUIRE(d.Kpad % BK == 0 && d.Kpad >= d.K, "gemm: Kpad=%d must be a multiple of 32 and >= K=%d", d.Kpad, d.K);
   SVX_REQUIRE(d.Npad % d.block_n == 0 && d.Npad >= d.N, "gemm: Npad=%d vs N=%d block_n=%d", d.Npad, d.N, d.block_n);
@@ -762,16 +855,21 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
       p.flat_off[t] = (dd * d.in_H + dh) * d.in_W + dw;
     }
     p.chunks_per_tap = d.Cin / BK;
-    p.cin_live = (d.cin_live > 0 && d.cin_live <= d.Cin) ? d.cin_live : d.Cin;
-    p.slab_base_off = getenv("SVX_SLAB_BASEOFF") ? atoi(getenv("SVX_SLAB_BASEOFF")) : 0;
-    // the merger-style case: full 3x3x3 tap grid in (kd,kh,kw) order, <= 16 output channels, narrow rows
-    bool grid333 = d.ntaps == 27 && d.block_n == 16 && d.Npad == 16 && BM + 2 * d.in_W + 2 <= SL_ROWS &&
-                   d.epi_mode == SVX_EPI_STD && !d.residual && !getenv("SVX_NO_SLAB");
-    for (int t = 0; t < 27 && grid333; ++t)
-      grid333 = d.taps_host[4 * t] == t / 9 && d.taps_host[4 * t + 1] == (t / 3) % 3 && d.taps_host[4 * t + 2] == t % 3;
-    g->slab = grid333;
-    if (encode_map(&g->map_a, d.A, (uint64_t)rows_total, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs,
-                   g->slab ? SL_ROWS : BM)) { delete g; return 1; }
+    if (encode_map(&g->map_a, d.A, (uint64_t)rows_total, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs, BM)) { delete g; return 1; }
+  } else if (d.a_mode == SVX_A_SLAB3) {
+    const int live = d.cin_live > 0 ? d.cin_live : BK;
+    bool ok = d.Cin == BK && live <= BK && d.in_Cs % 4 == 0 && d.in_c0 >= 0 && d.N <= 16 && d.block_n == S3_N &&
+              d.Npad == S3_N && d.K == 9 * BK && d.Kpad == 9 * BK && d.in_D == d.valid_D + 2 && d.valid_H > 0 &&
+              d.valid_W > 0 && d.valid_H <= d.in_H && d.valid_W <= d.in_W && BM + 2 * d.in_W <= S3_ROWS &&
+              d.epi_mode == SVX_EPI_STD && d.lda > 0;
+    if (!ok) {
+      delete g;
+      return fail("gemm: bad slab-conv description (Cin=%d live=%d N=%d block_n=%d Npad=%d K=%d Kpad=%d in=%dx%dx%d)",
+                  d.Cin, live, d.N, d.block_n, d.Npad, d.K, d.Kpad, d.in_D, d.in_H, d.in_W);
+    }
+    p.cin_live = live;
+    g->slab = true;
+    if (encode_map(&g->map_a, d.A, (uint64_t)d.lda, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs, S3_ROWS)) { delete g; return 1; }
   } else {
     delete g;
     return fail("gemm: unknown a_mode %d", d.a_mode);
@@ -810,9 +908,12 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   g->bn = d.block_n;
   const int slots = sm_count() * (d.block_n <= 96 ? 2 : 1);
   g->grid = (int)(tiles < slots ? tiles : slots);
-  if (g->slab) {
-    const int num_st = (p.tiles_m + SL_TS - 1) / SL_TS;
-    g->grid = num_st < sm_count() ? num_st : sm_count();
+  if (g->slab) {   // units = volumes x 126-row columns of the (h,w) plane
+    const int rows_plane = (d.valid_H - 1) * d.in_W + d.valid_W;
+    p.tiles_n = (rows_plane + S3_STEP - 1) / S3_STEP;
+    p.tiles_m = (d.M / (d.valid_D * d.valid_H * d.valid_W)) * p.tiles_n;
+    p.nk = 1;
+    g->grid = p.tiles_m < sm_count() ? p.tiles_m : sm_count();
   }
   *out = g;
   return 0;
@@ -830,10 +931,10 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void* stream) {
   if (g->slab) {
     static bool configured = false;
     if (!configured) {
-      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM));
+      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_SMEM));
       configured = true;
     }
-    conv3_slab_kernel<<<g->grid, SL_THREADS, SL_SMEM, st>>>(g->map_a, g->map_b, g->p);
+    conv3_slab_kernel<<<g->grid, S3_THREADS, S3_SMEM, st>>>(g->map_a, g->map_b, g->p);
     cudaError_t e = cudaGetLastError();
     if (!prepared) delete g;
     if (e != cudaSuccess) return fail("launch of conv3_slab_kernel failed: %s", cudaGetErrorString(e));

@@ -35,6 +35,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 inline int grid_for(long long work, int block, int max_blocks = kSmCount * 32) {
   long long g = (work + block - 1) / block;
   if (g > max_blocks) g = max_blocks;
@@ -42,30 +44,37 @@ inline int grid_for(long long work, int block, int max_blocks = kSmCount * 32) {
   return (int)g;
 }
 
-// ---- im2col (tiny C) -------------------------------------------------------------------------
-__global__ void im2col_kernel(const svx_im2col_desc d, long long total, int K) {
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+// ---- im2col (tiny C): one thread = four consecutive k of one row (one 16-byte store) ------------------------
+__global__ void im2col_kernel(const svx_im2col_desc d, long long total4, int K) {
+  const int K4 = d.Kpad >> 2;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(idx % d.Kpad);
-    long long r = idx / d.Kpad;
-    float v = 0.f;
-    if (k < K) {
-      const int c = k % d.C;
-      int t = k / d.C;
-      const int kw = t % d.KW; t /= d.KW;
-      const int kh = t % d.KH;
-      const int kd = t / d.KH;
-      const int ow = (int)(r % d.OW); r /= d.OW;
-      const int oh = (int)(r % d.OH); r /= d.OH;
-      const int od = (int)(r % d.OD);
-      const long long n = r / d.OD;
-      const int id = od * d.stride - d.pad_d + kd;
-      const int ih = oh * d.stride - d.pad_h + kh;
-      const int iw = ow * d.stride - d.pad_w + kw;
-      if ((unsigned)id < (unsigned)d.D && (unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W)
-        v = __ldg(d.in + n * d.s_n + c * d.s_c + id * d.s_d + ih * d.s_h + iw * d.s_w);
+    const int k0 = (int)(idx % K4) * 4;
+    long long r = idx / K4;
+    const int ow = (int)(r % d.OW); r /= d.OW;
+    const int oh = (int)(r % d.OH); r /= d.OH;
+    const int od = (int)(r % d.OD);
+    const long long n = r / d.OD;
+    const float* src = d.in + n * d.s_n;
+    const int id0 = od * d.stride - d.pad_d, ih0 = oh * d.stride - d.pad_h, iw0 = ow * d.stride - d.pad_w;
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = k0 + q;
+      float x = 0.f;
+      if (k < K) {
+        const int c = k % d.C;
+        int t = k / d.C;
+        const int kw = t % d.KW; t /= d.KW;
+        const int kh = t % d.KH;
+        const int kd = t / d.KH;
+        const int id = id0 + kd, ih = ih0 + kh, iw = iw0 + kw;
+        if ((unsigned)id < (unsigned)d.D && (unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W)
+          x = __ldg(src + c * d.s_c + id * d.s_d + ih * d.s_h + iw * d.s_w);
+      }
+      v[q] = maybe_round(x, d.round_tf32);
     }
-    d.out[idx] = maybe_round(v, d.round_tf32);
+    reinterpret_cast<float4*>(d.out)[idx] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -506,15 +515,29 @@ __global__ void transpose_kernel(const svx_transpose_desc d) {
   }
 }
 
-inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// planar [N, C<=4, P] -> [N, P, 4] (image staging: NCHW fp32 -> NHWC with a zero fourth channel); one thread = one pixel
+__global__ void interleave4_kernel(const svx_transpose_desc d, long long total) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long n = idx / d.P;
+    const int p = (int)(idx - n * d.P);
+    const float* src = d.in + n * (long long)d.C * d.P + p;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < d.C) v[c] = maybe_round(__ldg(src + (long long)c * d.P), d.round_tf32);
+    reinterpret_cast<float4*>(d.out)[idx] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
 
 }  // namespace
 
 int im2col_launch(const svx_im2col_desc& d, void* stream) {
   const int K = d.KD * d.KH * d.KW * d.C;
   SVX_REQUIRE(d.in && d.out && d.N > 0 && K > 0 && d.Kpad >= K, "im2col: bad description");
-  const long long total = (long long)d.N * d.OD * d.OH * d.OW * d.Kpad;
-  im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total, K);
+  SVX_REQUIRE(d.Kpad % 4 == 0 && al16(d.out), "im2col: Kpad must be a multiple of 4 and the output 16-byte aligned");
+  const long long total4 = (long long)d.N * d.OD * d.OH * d.OW * (d.Kpad / 4);
+  im2col_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(d, total4, K);
   SVX_LAUNCH_OK("im2col_kernel");
   return 0;
 }
@@ -605,6 +628,12 @@ int metrics_launch(const svx_metrics_desc& d, void* stream) {
 
 int transpose_launch(const svx_transpose_desc& d, void* stream) {
   SVX_REQUIRE(d.in && d.out && d.N > 0 && d.C > 0 && d.P > 0 && d.Cs >= d.C, "transpose: bad description");
+  if (d.to_channels_last && d.Cs == 4 && d.C <= 4 && al16(d.out)) {
+    const long long total = (long long)d.N * d.P;
+    interleave4_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
+    SVX_LAUNCH_OK("interleave4_kernel");
+    return 0;
+  }
   SVX_REQUIRE(d.N <= 65535, "transpose: N too large");
   const int cext = d.to_channels_last ? d.Cs : d.C;
   dim3 grid((d.P + 31) / 32, (cext + 31) / 32, d.N);

@@ -11,7 +11,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, A_FLAT, A_GATHER, A_PLAIN, EPI_DEC_TAIL, EPI_STD,
+from ._lib import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, A_FLAT, A_GATHER, A_PLAIN, A_SLAB3, EPI_DEC_TAIL, EPI_STD,
                    POOL_AVG, POOL_MAX)
 
 BLOCK_NS = (16, 32, 64, 96, 128, 192, 256)
@@ -143,6 +143,20 @@ def pack_conv(weight, bias, bn, device, cin_pad=None, block_n=None, n_logical=No
     if cp != cin:
         w = torch.nn.functional.pad(w, (0, cp - cin))
     return pack_matrix(w.reshape(cout, -1), b, device, block_n, n_logical)
+
+
+def pack_conv3_slab(weight, bias, bn, device, n_logical=None):
+    """nn.Conv3d(k=3) weight [Cout<=16, Cin<=32, 3, 3, 3] -> the slab kernel's kw-in-N layout: W[48, 288] with
+    row = kw*16 + co and col = (kd*3 + kh)*32 + c (BatchNorm folded, TF32-rounded)."""
+    w, b = fold_bn(weight, bias, bn)
+    cout, cin = w.shape[:2]
+    assert cout <= 16 and cin <= 32 and tuple(w.shape[2:]) == (3, 3, 3)
+    W = torch.zeros(3, 16, 9, 32, dtype=torch.float32, device=w.device)       # [kw, co, (kd,kh), c]
+    W[:, :cout, :, :cin] = w.permute(4, 0, 2, 3, 1).reshape(3, cout, 9, cin)
+    W = tf32_round(W.reshape(48, 288)).to(device)
+    bb = torch.zeros(48, dtype=torch.float32, device=device)
+    bb[:cout] = b.to(device)
+    return WeightPack(W, bb, n_logical or cout, 288, 48)
 
 
 def convT_class_taps(ks, pad, par):
@@ -317,11 +331,10 @@ class Plan:
         return out
 
     def conv_flat(self, x, pack, taps, out, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True,
-                  out_scale=1.0, round_out=False, name=None, out_map=None, valid=None, cin_live=0):
+                  out_scale=1.0, round_out=False, name=None, out_map=None, valid=None):
         """Stride-1 convolution over a zero-padded input, A operand streamed by TMA (one shifted box per tap).
         `taps` are non-negative (dd, dh, dw) offsets from the window corner in padded coordinates; `valid` =
-        number of window corners per axis that are real outputs (default: the extents of `out`); `cin_live` = leading
-        channels of each tap whose weights are non-zero (lets the kernel skip the zero-padded tail of a chunk)."""
+        number of window corners per axis that are real outputs (default: the extents of `out`)."""
         cin = pack.K // len(taps)
         assert cin * len(taps) == pack.K and cin % 32 == 0 and cin == x.C and pack.Kpad == pack.K, (cin, x.C, pack.K)
         assert all(min(t) >= 0 for t in taps)
@@ -338,12 +351,34 @@ class Plan:
         d.valid_D, d.valid_H, d.valid_W = vD, vH, vW
         d.stride_d = d.stride_h = d.stride_w = 1
         d.ntaps = len(taps)
-        d.cin_live = cin_live
         host = (C.c_int32 * (4 * len(taps)))(*[v for t in taps for v in (t[0], t[1], t[2], 0)])
         self.keep[id(host)] = host
         d.taps_host = C.cast(host, C.c_void_p)
         self._fill_epilogue(d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out)
         self._add("gemm", d, name or "conv_flat", 2.0 * x.N * vD * vH * vW * pack.N * pack.K)
+        return out
+
+    def conv3_slab(self, x, pack, out, cin_live, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True,
+                   out_scale=1.0, round_out=False, name=None):
+        """Conv3d(k3, s1, p1) with <= 16 output channels over a (1,1,1) zero-bordered volume `x` (an Act whose
+        channel window [c0, c0+32) is the TMA box; only the first `cin_live` channels carry weights).  `pack` comes
+        from pack_conv3_slab.  `out` may live in any buffer whose Act describes the same voxel grid."""
+        assert x.pad == (1, 1, 1) and pack.block_n == 48 and pack.Npad == 48 and pack.Kpad == 288
+        vD, vH, vW = x.inner
+        assert tuple(out.inner) == (vD, vH, vW) and out.N == x.N and out.C >= pack.N
+        d = _lib.GemmDesc()
+        d.M = x.N * vD * vH * vW
+        d.a_mode = A_SLAB3
+        d.A = self.hold(x).buf.data_ptr()
+        d.lda = x.buf.shape[0]
+        d.in_D, d.in_H, d.in_W, d.in_Cs, d.in_c0, d.Cin = x.D, x.H, x.W, x.Cs, x.c0, 32
+        d.out_D, d.out_H, d.out_W = vD, vH, vW
+        d.valid_D, d.valid_H, d.valid_W = vD, vH, vW
+        d.stride_d = d.stride_h = d.stride_w = 1
+        d.ntaps = 27
+        d.cin_live = cin_live
+        self._fill_epilogue(d, pack, out, None, act, act_param, residual, res_after_act, out_scale, round_out)
+        self._add("gemm", d, name or "conv3_slab", 2.0 * d.M * 27 * cin_live * pack.N)
         return out
 
     # ---- everything else ------------------------------------------------------------------------

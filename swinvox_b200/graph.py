@@ -23,16 +23,28 @@ def _dev(plan):
 # --------------------------------------------------------------------------------------------------
 # ResNet-50 trunk: torchvision resnet50 children[:7]  (models/encoder.py:22-23,119)
 # --------------------------------------------------------------------------------------------------
+def stage_image(plan, img, N):
+    """[N,3,224,224] NCHW fp32 tensor -> Act [N,224,224,4] (channels-last, zero fourth channel, TF32-rounded): the
+    layout both stems gather 16-byte pixels from.  Idempotent per plan."""
+    if isinstance(img, Act):
+        return img
+    key = ("nhwc4", img.data_ptr())
+    if key not in plan.taps:
+        a = plan.new_act(N, 1, 224, 224, 4)
+        plan.transpose(img, a.buf, N, 3, 224 * 224, 4, True, round_out=True, name="image.nhwc4")
+        plan.taps[key] = a
+    return plan.taps[key]
+
+
 def lower_resnet_trunk(plan, resnet, img, N):
-    """img: [N,3,224,224] fp32 NCHW tensor (read in place).  Returns Act [N,14,14,1024]."""
+    """img: [N,3,224,224] fp32 NCHW tensor (or the staged NHWC4 Act).  Returns Act [N,14,14,1024]."""
     dev = _dev(plan)
     conv1, bn1 = resnet[0], resnet[1]
-    cols = plan.im2col(img, (3 * 224 * 224, 224 * 224, 0, 224, 1), N, 3, (1, 224, 224), (1, 7, 7), 2, (0, 3, 3),
-                       (1, 112, 112), 160, name="resnet.stem.im2col")
-    w, b = E.fold_bn(conv1.weight, conv1.bias, bn1)
-    pk = E.pack_matrix(w.permute(0, 2, 3, 1).reshape(64, 147), b, dev)
+    x4 = stage_image(plan, img, N)
+    # 7x7 s2 p3 stem as an implicit GEMM over 49 one-pixel (4-channel) taps: K = 196
     stem = plan.new_act(N, 1, 112, 112, 64)
-    plan.linear(cols, E.WeightPack(pk.W, pk.bias, 64, 160, pk.block_n), stem, act=ACT_RELU, name="resnet.stem")
+    plan.conv(x4, E.pack_conv(conv1.weight, conv1.bias, bn1, dev, cin_pad=4), E.conv_taps(1, 7, 7, 0, 3, 3), stem,
+              stride=(1, 2, 2), act=ACT_RELU, name="resnet.stem")
     x = plan.new_act(N, 1, 56, 56, 64)
     plan.pool(stem, x, (1, 3, 3), (1, 2, 2), (0, 1, 1), POOL_MAX, round_out=True, name="resnet.maxpool")
     for li in (4, 5, 6):
@@ -91,11 +103,11 @@ def lower_swin(plan, swin, img, N):
     model = swin.model
     stages = [i % 4 for i in swin.cfg.NETWORK.SWIN_T_STAGES]
     pe = model.patch_embed
-    cols = plan.im2col(img, (3 * 224 * 224, 224 * 224, 0, 224, 1), N, 3, (1, 224, 224), (1, 4, 4), 4, (0, 0, 0),
-                       (1, 56, 56), 64, name="swin.patch_embed.im2col")
-    pk = E.pack_matrix(pe.proj.weight.detach().permute(0, 2, 3, 1).reshape(96, 48), pe.proj.bias, dev)
+    x4 = stage_image(plan, img, N)
     emb = plan.new_act(N, 1, 56, 56, 96)
-    plan.linear(cols, E.WeightPack(pk.W, pk.bias, 96, 64, pk.block_n), emb, name="swin.patch_embed.proj")
+    # patch embedding: 4x4 s4 conv = 16 one-pixel taps, K = 64
+    plan.conv(x4, E.pack_conv(pe.proj.weight, pe.proj.bias, None, dev, cin_pad=4), E.conv_taps(1, 4, 4, 0, 0, 0), emb,
+              stride=(1, 4, 4), name="swin.patch_embed.proj")
     x = plan.new_act(N, 1, 56, 56, 96)
     plan.layernorm_rows(emb, pe.norm.weight.detach().float().to(dev), pe.norm.bias.detach().float().to(dev), x,
                         eps=pe.norm.eps, round_out=False, name="swin.patch_embed.norm")
@@ -304,33 +316,37 @@ def lower_decoder(plan, dec, feat, N):
 def lower_merger(plan, mer, raw, coarse, B, V):
     """raw: Act of 32^3 voxels inside a (1,1,1) zero border, 32-channel rows (9 live, TF32-rounded, rest zero);
     coarse: [N,32768] tensor.  Returns (merged [B, 32768], pre-softmax scores [N, 32768]).
-    All six Conv3d(k3,p1) layers run as TMA slab convolutions over zero-bordered 34^3 volumes."""
+    All six Conv3d(k3,p1) layers run on the depth-marching TMA slab kernel over zero-bordered 34^3 volumes."""
     dev = _dev(plan)
     N = B * V
     slope = float(mer.cfg.NETWORK.LEAKY_VALUE)
-    taps = E.conv_taps(3, 3, 3, 0, 0, 0)
     cat = plan.new_act(N, 32, 32, 32, 64, pad=(1, 1, 1))   # four 16-channel groups: w1 | w2 | w3 | w4 (9 live each)
-    x = raw
+
+    def box(a, c0):   # the 32-channel TMA box starting at channel c0 of a zero-bordered buffer
+        return Act(a.buf, N, 34, 34, 34, 32, c0, (1, 1, 1))
+
+    x = box(raw, raw.c0)
     for i, layer in enumerate((mer.layer1, mer.layer2, mer.layer3, mer.layer4)):
         o = cat.channels(16 * i, 16)
-        pk = E.pack_conv(layer[0].weight, layer[0].bias, layer[1], dev, cin_pad=32, n_logical=16, block_n=16)
-        # the 32-channel TMA box starts at the group's first channel; weights beyond the 9 live channels are zero
-        plan.conv_flat(Act(x.buf, N, 34, 34, 34, 32, x.c0, (1, 1, 1)), pk, taps, o, act=ACT_LEAKY, act_param=slope,
-                       round_out=True, cin_live=9, name=f"merger.layer{i + 1}")
-        x = o
-    # layer5 sees cat(w1..w4): reference channel 9*g + c lives at 16*g + c here
-    w5 = mer.layer5[0].weight.detach().float()
-    w5p = torch.zeros(9, 64, 3, 3, 3, device=w5.device)
-    for gi in range(4):
-        w5p[:, 16 * gi:16 * gi + 9] = w5[:, 9 * gi:9 * gi + 9]
+        plan.conv3_slab(x, E.pack_conv3_slab(layer[0].weight, layer[0].bias, layer[1], dev, n_logical=16), o, 9,
+                        act=ACT_LEAKY, act_param=slope, round_out=True, name=f"merger.layer{i + 1}")
+        x = box(cat, 16 * i)
+    # layer5 sees cat(w1..w4): reference channel 9*g + c lives at 16*g + c here.  Two slab passes over the two
+    # 32-channel halves; the second adds the first's partial sums before bias / LeakyReLU.
+    w5, b5 = E.fold_bn(mer.layer5[0].weight, mer.layer5[0].bias, mer.layer5[1])
     t = plan.new_act(N, 32, 32, 32, 16, Cs=32, pad=(1, 1, 1))
-    plan.conv_flat(cat, E.pack_conv(w5p, mer.layer5[0].bias, mer.layer5[1], dev, cin_pad=64, n_logical=16, block_n=16),
-                   taps, t, act=ACT_LEAKY, act_param=slope, round_out=True, cin_live=57, name="merger.layer5")
+    for half in (0, 1):
+        wh = torch.zeros(9, 32, 3, 3, 3, device=w5.device)
+        for gi in (0, 1):
+            wh[:, 16 * gi:16 * gi + 9] = w5[:, 9 * (2 * half + gi):9 * (2 * half + gi) + 9]
+        pk = E.pack_conv3_slab(wh, b5 if half else None, None, dev, n_logical=16)
+        plan.conv3_slab(box(cat, 32 * half), pk, t, 25, act=ACT_LEAKY if half else ACT_NONE, act_param=slope,
+                        residual=t if half else None, res_after_act=False, round_out=bool(half),
+                        name=f"merger.layer5.{'ab'[half]}")
     wts = plan.empty(N, 32768)
     wact = Act(wts.view(-1, 1), N, 32, 32, 32, 1, 0)
-    pk6 = E.pack_conv(mer.layer6[0].weight, mer.layer6[0].bias, mer.layer6[1], dev, cin_pad=32, block_n=16)
-    plan.conv_flat(Act(t.buf, N, 34, 34, 34, 32, 0, (1, 1, 1)), pk6, taps, wact, act=ACT_LEAKY, act_param=slope,
-                   cin_live=9, name="merger.layer6")
+    plan.conv3_slab(box(t, 0), E.pack_conv3_slab(mer.layer6[0].weight, mer.layer6[0].bias, mer.layer6[1], dev), wact, 9,
+                    act=ACT_LEAKY, act_param=slope, name="merger.layer6")
     merged = plan.empty(B, 32768)
     plan.merger_fuse(wts, coarse, merged, B, V, 32768, name="merger.softmax_fuse")
     return merged, wts

@@ -53,6 +53,11 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     SVX_REQUIRE(d.Cin % 32 == 0 && d.K == d.ntaps * d.Cin && d.Kpad == d.K && d.taps_host && d.ntaps <= 64 &&
                     d.out_D == d.in_D && d.out_H == d.in_H && d.out_W == d.in_W && d.lda >= d.M,
                 "gemm: bad flat conv");
+  else if (d.a_mode == SVX_A_SLAB3)
+    SVX_REQUIRE(d.Cin == 32 && d.N <= 16 && d.block_n == 48 && d.Npad == 48 && d.K == 288 && d.Kpad == 288 &&
+                    d.in_D == d.valid_D + 2 && d.valid_H <= d.in_H && d.valid_W <= d.in_W && 128 + 2 * d.in_W <= 200 &&
+                    d.lda > 0 && d.epi_mode == SVX_EPI_STD,
+                "gemm: bad slab conv");
   else
     SVX_REQUIRE(d.lda % 4 == 0 && d.lda >= d.K, "gemm: bad lda");
   if (d.epi_mode == SVX_EPI_DEC_TAIL)
@@ -68,6 +73,42 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
     GemmPrepared* g = nullptr;
     if (int rc = gemm_prepare(d, &g)) return rc;
     delete g;
+  }
+  if (d.a_mode == SVX_A_SLAB3) {
+    // direct 3x3x3 convolution over the zero-bordered volume; weights in the kw-in-N layout
+    const int live = d.cin_live > 0 ? d.cin_live : 32;
+    const long long HWp = (long long)d.in_H * d.in_W;
+    const long long vox = (long long)d.valid_D * d.valid_H * d.valid_W;
+#pragma omp parallel for schedule(static)
+    for (long long r = 0; r < d.M; ++r) {
+      const long long n = r / vox;
+      long long t = r % vox;
+      const int w = (int)(t % d.valid_W); t /= d.valid_W;
+      const int h = (int)(t % d.valid_H);
+      const int dd = (int)(t / d.valid_H);
+      const long long off = d.o_base + n * d.o_sn + dd * d.o_sd + h * d.o_sh + w * d.o_sw;
+      for (int co = 0; co < d.N; ++co) {
+        float acc = 0.f;
+        for (int kd = 0; kd < 3; ++kd)
+          for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+              const long long row = (n * d.in_D + dd + kd) * HWp + (long long)(h + kh) * d.in_W + (w + kw);
+              if (row >= d.lda) continue;
+              const float* px = d.A + row * d.in_Cs + d.in_c0;
+              const float* wr = d.W + (long long)(kw * 16 + co) * d.Kpad + (kd * 3 + kh) * 32;
+              for (int c = 0; c < live; ++c)
+                if (d.in_c0 + c < d.in_Cs) acc += tf32_trunc(px[c]) * tf32_trunc(wr[c]);
+            }
+        float v = acc + (d.bias ? d.bias[co] : 0.f);
+        const float res = d.residual ? d.residual[off + co] : 0.f;
+        if (d.residual && !d.res_after_act) v += res;
+        v = act_fn(v, d.act, d.act_param);
+        if (d.residual && d.res_after_act) v += res;
+        v *= d.out_scale;
+        d.out[off + co] = rnd(v, d.round_tf32);
+      }
+    }
+    return 0;
   }
   const long long rows_per_n = (long long)d.out_D * d.out_H * d.out_W;
 #pragma omp parallel

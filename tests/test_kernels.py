@@ -166,54 +166,49 @@ def test_conv3d_padded_channels(dev):
     assert got[:, 9:].abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("dims,groups", [((6, 7, 9), 1), ((5, 32, 32), 1), ((4, 6, 8), 4), ((3, 32, 32), 4)])
-def test_conv3d_slab_merger_style(dev, dims, groups):
-    """merger-style Conv3d(k3, p1) with 9 output channels over a zero-bordered volume: the TMA slab kernel
-    (27 taps addressed inside three depth slabs).  groups=4 is layer5 (input = four 16-channel groups, 9 live each),
-    groups=1 the 9->9 layers reading a 32-channel box at a channel offset; outputs go to a channel group of another
-    zero-bordered buffer and, like layer6, to a planar single-channel volume."""
+@pytest.mark.parametrize("dims,c0,residual", [((6, 7, 9), 16, False), ((5, 32, 32), 0, False), ((4, 6, 8), 32, True),
+                                               ((3, 32, 32), 48, True), ((32, 32, 32), 16, False)])
+def test_conv3d_slab_merger_style(dev, dims, c0, residual):
+    """merger-style Conv3d(k3, p1) with 9 output channels over a zero-bordered volume on the depth-marching TMA slab
+    kernel (kw taps folded into the MMA's N, (kd,kh) taps addressed inside the depth slabs): reads a 32-channel box
+    at channel offset c0 (overhanging the 64-channel buffer at c0=48), writes a 16-channel group of another
+    zero-bordered buffer (optionally accumulating on it: layer5's second pass) and, like layer6, a planar
+    single-channel volume."""
     DEV = dev
-    torch.manual_seed(sum(dims) + groups)
+    torch.manual_seed(sum(dims) + c0)
     D, H, W = dims
     n = 2
-    cin = 9 * groups
+    cin = 9 if c0 == 48 else 25
     x = E.tf32_round(torch.randn(n, cin, D, H, W))
     conv = torch.nn.Conv3d(cin, 9, 3, padding=1)
     bn = rand_bn(torch.nn.BatchNorm3d(9))
     conv1 = torch.nn.Conv3d(cin, 1, 3, padding=1)
     p = E.Plan(DEV)
     src = p.new_act(n, D, H, W, 64, pad=(1, 1, 1))
-    xv = src.view()
-    for g in range(groups):
-        xv[..., 16 * g + (16 if groups == 1 else 0):][..., :9].copy_(x[:, 9 * g:9 * g + 9].permute(0, 2, 3, 4, 1))
-    if groups == 1:
-        xin = E.Act(src.buf, n, D + 2, H + 2, W + 2, 32, 16, (1, 1, 1))
-        pk = E.pack_conv(conv.weight, conv.bias, bn, DEV, cin_pad=32, n_logical=16, block_n=16)
-        pk1 = E.pack_conv(conv1.weight, conv1.bias, None, DEV, cin_pad=32, block_n=16)
-        live = 9
-    else:
-        xin = src
-        def spread(w):
-            wp = torch.zeros(w.shape[0], 64, 3, 3, 3)
-            for g in range(4):
-                wp[:, 16 * g:16 * g + 9] = w[:, 9 * g:9 * g + 9]
-            return wp
-        pk = E.pack_conv(spread(conv.weight.detach()), conv.bias, bn, DEV, cin_pad=64, n_logical=16, block_n=16)
-        pk1 = E.pack_conv(spread(conv1.weight.detach()), conv1.bias, None, DEV, cin_pad=64, block_n=16)
-        live = 57
-    taps = E.conv_taps(3, 3, 3, 0, 0, 0)
+    src.view()[..., c0:c0 + cin].copy_(x.permute(0, 2, 3, 4, 1))
+    xin = E.Act(src.buf, n, D + 2, H + 2, W + 2, 32, c0, (1, 1, 1))
     dst = p.new_act(n, D, H, W, 64, pad=(1, 1, 1))
     out = dst.channels(32, 16)
-    p.conv_flat(xin, pk, taps, out, act=E.ACT_LEAKY, act_param=0.2, round_out=False, cin_live=live)
+    r = torch.randn(n, 16, D, H, W) if residual else None
+    if residual:
+        out.view().copy_(r.permute(0, 2, 3, 4, 1))
+    p.conv3_slab(xin, E.pack_conv3_slab(conv.weight, conv.bias, bn, DEV, n_logical=16), out, cin, act=E.ACT_LEAKY,
+                 act_param=0.2, residual=out if residual else None, res_after_act=False)
     planar = p.empty(n, D * H * W)
-    p.conv_flat(xin, pk1, taps, E.Act(planar.view(-1, 1), n, D, H, W, 1, 0), cin_live=live)
+    p.conv3_slab(xin, E.pack_conv3_slab(conv1.weight, conv1.bias, None, DEV), E.Act(planar.view(-1, 1), n, D, H, W, 1, 0), cin)
     p.run()
     sync(DEV)
     wf, bf = E.fold_bn(conv.weight, conv.bias, bn)
-    ref = F.leaky_relu(F.conv3d(x.double(), E.tf32_round(wf).double(), bf.double(), padding=1), 0.2)
+    y = F.conv3d(x.double(), E.tf32_round(wf).double(), bf.double(), padding=1)
+    if residual:
+        y = y + r[:, :9].double()
+    ref = F.leaky_relu(y, 0.2)
     got = out.view().permute(0, 4, 1, 2, 3).cpu()
     assert rel_err(got[:, :9], ref) < 1e-4
-    assert got[:, 9:].abs().max().item() == 0.0
+    if residual:
+        assert rel_err(got[:, 9:], F.leaky_relu(r[:, 9:].double(), 0.2)) < 1e-6
+    else:
+        assert got[:, 9:].abs().max().item() == 0.0
     full = dst.buf.view(n, D + 2, H + 2, W + 2, 64).cpu()
     assert full[:, 0].abs().max() == 0 and full[:, -1].abs().max() == 0 and full[:, :, 0].abs().max() == 0 and \
         full[:, :, -1].abs().max() == 0 and full[:, :, :, 0].abs().max() == 0 and full[:, :, :, -1].abs().max() == 0, \
