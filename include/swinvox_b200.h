@@ -226,6 +226,13 @@ int svx_plan_add_bilinear_add(svx_plan*, const svx_bilinear_desc*);
 int svx_plan_add_merger_fuse(svx_plan*, const svx_mergefuse_desc*);
 int svx_plan_add_voxel_metrics(svx_plan*, const svx_metrics_desc*);
 int svx_plan_add_transpose(svx_plan*, const svx_transpose_desc*);
+/* Concurrency hints.  Ops are recorded into the current lane (default 0 = the caller's stream).  Ops of a side lane
+ * k in [1, 8] run in order on the plan's side stream k, forked from the caller's stream where the lane's first op
+ * since the last join sits in the op list; svx_plan_add_join makes the caller's stream wait for every side lane (the
+ * end of the plan joins implicitly).  The caller guarantees that ops of different lanes between two joins are
+ * independent.  Used for the eight output-parity classes of a stride-2 ConvTranspose3d. */
+int svx_plan_set_lane(svx_plan*, int lane);
+int svx_plan_add_join(svx_plan*);
 /* run every op in order on `stream`; use_graph != 0 replays a CUDA graph captured on first use */
 int svx_plan_run(svx_plan*, void* stream, int use_graph);
 /* run ops [first, last) only (profiling / bisecting) */

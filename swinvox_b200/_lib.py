@@ -137,7 +137,7 @@ OPS = {
 
 OTHER_SYMBOLS = ["svx_abi_version", "svx_last_error", "svx_desc_sizes", "svx_device_info", "svx_plan_create",
                  "svx_plan_destroy", "svx_plan_num_ops", "svx_plan_run", "svx_plan_run_range",
-                 "svx_plan_time_ops", "svx_plan_num_launches"]
+                 "svx_plan_time_ops", "svx_plan_num_launches", "svx_plan_set_lane", "svx_plan_add_join"]
 
 ALL_SYMBOLS = OTHER_SYMBOLS + [s for v in OPS.values() for s in v[:2]]
 
@@ -168,6 +168,8 @@ def bind(path):
     lib.svx_plan_run.argtypes = [ptr, ptr, C.c_int]
     lib.svx_plan_run_range.argtypes = [ptr, C.c_int, C.c_int, ptr]
     lib.svx_plan_time_ops.argtypes = [ptr, ptr, C.c_int, C.POINTER(C.c_float)]
+    lib.svx_plan_set_lane.argtypes = [ptr, C.c_int]
+    lib.svx_plan_add_join.argtypes = [ptr]
     lib.svx_desc_sizes.argtypes = [C.POINTER(i32), C.c_int]
     lib.svx_device_info.argtypes = [C.c_int, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     for imm, add, desc_t in OPS.values():

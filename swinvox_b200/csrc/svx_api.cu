@@ -25,7 +25,7 @@ int fail(const char* fmt, ...) {
 
 enum OpKind {
   OP_GEMM, OP_IM2COL, OP_POOL, OP_LNROWS, OP_LNSAMPLE, OP_WINATTN, OP_DWCONV, OP_VIEWATTN, OP_BILINEAR,
-  OP_MERGEFUSE, OP_METRICS, OP_TRANSPOSE
+  OP_MERGEFUSE, OP_METRICS, OP_TRANSPOSE, OP_JOIN
 };
 
 struct Op {
@@ -45,6 +45,7 @@ struct Op {
     svx_transpose_desc transpose;
   } u;
   GemmPrepared* prepared = nullptr;
+  int lane = 0;   // 0: the caller's stream; k > 0: side stream k (ops of different lanes may overlap until the next join)
 };
 
 int launch_op(Op& op, void* stream) {
@@ -61,17 +62,23 @@ int launch_op(Op& op, void* stream) {
     case OP_MERGEFUSE: return mergefuse_launch(op.u.mergefuse, stream);
     case OP_METRICS: return metrics_launch(op.u.metrics, stream);
     case OP_TRANSPOSE: return transpose_launch(op.u.transpose, stream);
+    case OP_JOIN: return 0;
   }
   return fail("unknown op kind");
 }
 
 }  // namespace svx
 
+constexpr int kMaxLanes = 8;
+
 struct svx_plan {
   std::vector<svx::Op> ops;
+  int cur_lane = 0;
 #ifndef SVX_HOSTSIM
   cudaGraphExec_t graph_exec = nullptr;
   size_t graph_ops = 0;
+  cudaStream_t side[kMaxLanes] = {};
+  cudaEvent_t fork_ev = nullptr, join_ev[kMaxLanes] = {};
 #endif
 };
 
@@ -143,6 +150,11 @@ void svx_plan_destroy(svx_plan* p) {
     if (op.prepared) gemm_prepared_free(op.prepared);
 #ifndef SVX_HOSTSIM
   if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+  for (int k = 0; k < kMaxLanes; ++k) {
+    if (p->side[k]) cudaStreamDestroy(p->side[k]);
+    if (p->join_ev[k]) cudaEventDestroy(p->join_ev[k]);
+  }
+  if (p->fork_ev) cudaEventDestroy(p->fork_ev);
 #endif
   delete p;
 }
@@ -155,6 +167,7 @@ int svx_plan_add_gemm(svx_plan* p, const svx_gemm_desc* d) {
   op.kind = OP_GEMM;
   op.u.gemm = *d;
   if (int rc = gemm_prepare(*d, &op.prepared)) return rc;
+  op.lane = p->cur_lane;
   p->ops.push_back(op);
   return 0;
 }
@@ -165,6 +178,7 @@ int svx_plan_add_gemm(svx_plan* p, const svx_gemm_desc* d) {
     Op op;                                                   \
     op.kind = kind_;                                         \
     op.u.member = *d;                                        \
+    op.lane = p->cur_lane;                                   \
     p->ops.push_back(op);                                    \
     return 0;                                                \
   }
@@ -180,12 +194,68 @@ SVX_PLAN_ADD(svx_plan_add_merger_fuse, svx_mergefuse_desc, OP_MERGEFUSE, mergefu
 SVX_PLAN_ADD(svx_plan_add_voxel_metrics, svx_metrics_desc, OP_METRICS, metrics)
 SVX_PLAN_ADD(svx_plan_add_transpose, svx_transpose_desc, OP_TRANSPOSE, transpose)
 
+int svx_plan_set_lane(svx_plan* p, int lane) {
+  if (!p || lane < 0 || lane > kMaxLanes) return fail("svx_plan_set_lane: lane must be in [0, %d]", kMaxLanes);
+  p->cur_lane = lane;
+  return 0;
+}
+
+int svx_plan_add_join(svx_plan* p) {
+  if (!p) return fail("svx_plan_add_join: null plan");
+  Op op;
+  op.kind = OP_JOIN;
+  memset(&op.u, 0, sizeof(op.u));
+  p->ops.push_back(op);
+  return 0;
+}
+
+// Ops of lane 0 run on the caller's stream.  The first op of a side lane since the last join forks that lane's
+// stream from the caller's stream at this point of the op list; a join op (and the end of the range) makes the
+// caller's stream wait for every side lane.  Works identically under stream capture (the lanes become graph branches).
 int svx_plan_run_range(svx_plan* p, int first, int last, void* stream) {
   if (!p) return fail("svx_plan_run_range: null plan");
   if (first < 0 || last > (int)p->ops.size() || first > last) return fail("svx_plan_run_range: bad range");
+#ifdef SVX_HOSTSIM
   for (int i = first; i < last; ++i)
     if (int rc = launch_op(p->ops[i], stream)) return rc;
   return 0;
+#else
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bool forked[kMaxLanes] = {};
+  auto join_all = [&]() -> int {
+    for (int k = 0; k < kMaxLanes; ++k) {
+      if (!forked[k]) continue;
+      SVX_CUDA_OK(cudaEventRecord(p->join_ev[k], p->side[k]));
+      SVX_CUDA_OK(cudaStreamWaitEvent(st, p->join_ev[k], 0));
+      forked[k] = false;
+    }
+    return 0;
+  };
+  for (int i = first; i < last; ++i) {
+    Op& op = p->ops[i];
+    if (op.kind == OP_JOIN) {
+      if (int rc = join_all()) return rc;
+      continue;
+    }
+    if (op.lane == 0) {
+      if (int rc = launch_op(op, stream)) return rc;
+      continue;
+    }
+    const int k = op.lane - 1;
+    if (!p->side[k]) {
+      SVX_CUDA_OK(cudaStreamCreateWithFlags(&p->side[k], cudaStreamNonBlocking));
+      SVX_CUDA_OK(cudaEventCreateWithFlags(&p->join_ev[k], cudaEventDisableTiming));
+    }
+    if (!p->fork_ev) SVX_CUDA_OK(cudaEventCreateWithFlags(&p->fork_ev, cudaEventDisableTiming));
+    if (!forked[k]) {
+      SVX_CUDA_OK(cudaEventRecord(p->fork_ev, st));
+      SVX_CUDA_OK(cudaStreamWaitEvent(p->side[k], p->fork_ev, 0));
+      forked[k] = true;
+    }
+    if (int rc = launch_op(op, p->side[k])) return rc;
+  }
+  return join_all();
+#endif
 }
 
 int svx_plan_run(svx_plan* p, void* stream, int use_graph) {
@@ -233,6 +303,7 @@ int svx_plan_time_ops(svx_plan* p, void* stream, int iters, float* ms) {
   SVX_CUDA_OK(cudaEventCreate(&b));
   int rc = 0;
   for (size_t i = 0; i < p->ops.size() && !rc; ++i) {
+    if (p->ops[i].kind == OP_JOIN) { ms[i] = 0.f; continue; }
     rc = launch_op(p->ops[i], stream);  // warm
     cudaEventRecord(a, st);
     for (int it = 0; it < iters && !rc; ++it) rc = launch_op(p->ops[i], stream);
@@ -252,7 +323,7 @@ int svx_plan_time_ops(svx_plan* p, void* stream, int iters, float* ms) {
 int svx_plan_num_launches(const svx_plan* p) {
   if (!p) return 0;
   int n = 0;
-  for (auto& op : p->ops) n += (op.kind == OP_GEMM) ? gemm_num_launches(op.u.gemm) : 1;
+  for (auto& op : p->ops) n += (op.kind == OP_GEMM) ? gemm_num_launches(op.u.gemm) : (op.kind == OP_JOIN ? 0 : 1);
   return n;
 }
 

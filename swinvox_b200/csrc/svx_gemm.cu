@@ -61,6 +61,8 @@ struct GemmParams {
   float* out2;
   long long o2_base, o2_sn, o2_sd, o2_sh, o2_sw;
   int vec_ok;
+  int epi_tma;              // plain row-major output: epilogue stores through TMA (map_c)
+  long long ldc;            // epi_tma: row pitch of out / residual (elements); out and residual already include o_base
   int flat_off[kMaxTaps];  // flat mode: row offset of each tap
 };
 
@@ -181,23 +183,25 @@ __device__ __forceinline__ void store_slab(const GemmParams& p, const float* sta
 template <int BN>
 __global__ void __launch_bounds__(kThreads, Cfg<BN>::kCtasPerSm)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ GemmParams p) {
+                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
   constexpr int S = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + S * C::kStageBytes;
+  // after the pipeline stages: epilogue staging (1024-byte aligned: TMA-store source blocks), row offsets, barriers
+  uint8_t* aux_gen = smem_gen + S * C::kStageBytes;
+  float* staging_all = reinterpret_cast<float*>(aux_gen);
+  long long* soff_all = reinterpret_cast<long long*>(aux_gen + kStagingBytes);
+  constexpr int kBarOff = kStagingBytes + kOffBytes;
+  const uint32_t bar_base = smem_base + S * C::kStageBytes + kBarOff;
   // barrier layout: full[S], empty[S], tmem_full[2], tmem_empty[2], tmem slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
-  uint8_t* aux_gen = smem_gen + S * C::kStageBytes;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(aux_gen + 8 * (2 * S + 4));
-  float* staging_all = reinterpret_cast<float*>(aux_gen + 256);
-  long long* soff_all = reinterpret_cast<long long*>(aux_gen + 256 + kStagingBytes);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(aux_gen + kBarOff + 8 * (2 * S + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -209,6 +213,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 4 && lane == 0) {
     if (a_mode != SVX_A_GATHER) tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (p.epi_tma) tma_prefetch_desc(&map_c);
   }
   if (warp == 5) {
     if (lane == 0) {
@@ -377,6 +382,98 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
       const uint32_t as = it & 1u;
+      if (p.epi_tma) {
+        // ---- plain row-major output: TMEM -> registers -> bias / residual / activation -> 64B-swizzled smem block
+        // (32 rows x 16 columns per warp) -> one TMA store per block.  No per-element address arithmetic, the
+        // store is coalesced by the TMA unit and clipped at the matrix edges. ----
+        mbar_wait(tmem_full_bar(as), (it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t lane_addr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+        const int row = m0 + quarter * 32 + lane;
+        const bool row_ok = row < p.M;
+        const float* res_row = p.residual + static_cast<long long>(row) * p.ldc;
+        const bool has_res = p.residual != nullptr;
+        const bool pre = has_res && !p.res_after_act, post = has_res && p.res_after_act;
+        char* stg = reinterpret_cast<char*>(staging);                       // 2 KB, 1024-byte aligned
+        const uint32_t stg_u32 = smem_u32(stg);
+        char* my_row = stg + lane * 64;
+        const int sw = (lane >> 1) & 3;                                        // 64B swizzle phase of this row
+#pragma unroll 1
+        for (int c0 = part * SLAB; c0 < BN; c0 += nparts * SLAB) {
+          const int jb = n0 + c0;
+          if (jb >= p.N) break;  // warp-uniform
+          uint32_t v[SLAB];
+          __syncwarp();
+          tmem_ld16(lane_addr + c0, v);
+          float4 rv[4];
+          if (has_res) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              rv[c] = (row_ok && jb + 4 * c < p.N) ? *reinterpret_cast<const float4*>(res_row + jb + 4 * c)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          float4 bv[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            bv[c] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + jb + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          tmem_ld_wait();
+          float x[SLAB];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            x[4 * c + 0] = __uint_as_float(v[4 * c + 0]) + bv[c].x;
+            x[4 * c + 1] = __uint_as_float(v[4 * c + 1]) + bv[c].y;
+            x[4 * c + 2] = __uint_as_float(v[4 * c + 2]) + bv[c].z;
+            x[4 * c + 3] = __uint_as_float(v[4 * c + 3]) + bv[c].w;
+          }
+          if (pre) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { x[4 * c] += rv[c].x; x[4 * c + 1] += rv[c].y; x[4 * c + 2] += rv[c].z; x[4 * c + 3] += rv[c].w; }
+          }
+          switch (p.act) {
+            case SVX_ACT_RELU:
+#pragma unroll
+              for (int q = 0; q < SLAB; ++q) x[q] = fmaxf(x[q], 0.f);
+              break;
+            case SVX_ACT_LEAKY:
+#pragma unroll
+              for (int q = 0; q < SLAB; ++q) x[q] = act_t<SVX_ACT_LEAKY>(x[q], p.act_param);
+              break;
+            case SVX_ACT_GELU:
+#pragma unroll
+              for (int q = 0; q < SLAB; ++q) x[q] = gelu_erf(x[q]);
+              break;
+            default: break;
+          }
+          if (post) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { x[4 * c] += rv[c].x; x[4 * c + 1] += rv[c].y; x[4 * c + 2] += rv[c].z; x[4 * c + 3] += rv[c].w; }
+          }
+          if (p.out_scale != 1.f) {
+#pragma unroll
+            for (int q = 0; q < SLAB; ++q) x[q] *= p.out_scale;
+          }
+          if (p.round_tf32) {
+#pragma unroll
+            for (int q = 0; q < SLAB; ++q) x[q] = round_tf32(x[q]);
+          }
+          // the previous block of this warp must have been read out of smem by the TMA unit
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<float4*>(my_row + ((c ^ sw) << 4)) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_c, stg_u32, jb, m0 + quarter * 32);
+            tma_store_commit();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar(as));
+        continue;
+      }
       long long off = 0, off2 = 0;
       const bool valid = decode_row(p, m0 + quarter * 32 + lane, off, off2);
       __syncwarp();
@@ -458,6 +555,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar(as));
     }
+    if (p.epi_tma && lane == 0) tma_store_wait_all<0>();   // smem must outlive the last bulk store
   }
 
   tc_fence_before();
@@ -757,18 +855,20 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D fp32 tensor [rows, cols] with row pitch `pitch_elems`; box = box_rows x 32 columns, 128B swizzle
+// 2-D fp32 tensor [rows, cols] with row pitch `pitch_elems`; box = box_rows x box_cols columns (32: 128B swizzle,
+// 16: 64B swizzle)
 int encode_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
-               uint32_t box_rows) {
+               uint32_t box_rows, uint32_t box_cols = BK) {
   if (box_rows > 256) return fail("TMA box of %u rows exceeds 256", box_rows);
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {pitch_elems * 4};
-  cuuint32_t box[2] = {BK, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
@@ -786,14 +886,15 @@ int sm_count() {
 }
 
 template <int BN>
-int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int grid, cudaStream_t st) {
+int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const GemmParams& p, int grid,
+              cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     SVX_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg<BN>::kSmemBytes));
     configured = true;
   }
-  gemm_tf32_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ma, mb, p);
+  gemm_tf32_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ma, mb, mc, p);
   SVX_LAUNCH_OK("gemm_tf32_kernel");
   return 0;
 }
@@ -801,7 +902,7 @@ int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p,
 }  // namespace
 
 struct GemmPrepared {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_c;
   GemmParams p;
   int bn, grid;
   bool slab = false;   // SVX_A_SLAB3: handled by conv3_slab_kernel
@@ -823,6 +924,7 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   GemmParams& p = g->p;
   memset(&p, 0, sizeof(p));
   memset(&g->map_a, 0, sizeof(g->map_a));
+  memset(&g->map_c, 0, sizeof(g->map_c));
   p.chunks_per_tap = 1;
   if (d.a_mode == SVX_A_PLAIN) {
     if (d.lda % 4 != 0 || d.lda < d.K) {
@@ -901,6 +1003,23 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   p.vec_ok = (d.N % 4 == 0) && al4(d.o_base) && al4(d.o_sn) && al4(d.o_sd) && al4(d.o_sh) && al4(d.o_sw) &&
              (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
              (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0);
+  // Plain row-major output (row r lands at out + o_base + r*ldc, every row a real output): the epilogue stores
+  // through TMA.  True for every linear layer and for convolutions writing an unpadded channels-last tensor.
+  {
+    const bool compact = d.o_sh == (long long)d.out_W * d.o_sw && d.o_sd == (long long)d.out_H * d.o_sh &&
+                         d.o_sn == (long long)d.out_D * d.o_sd;
+    const bool plain = compact && d.valid_W == 0 && d.epi_mode == SVX_EPI_STD && d.a_mode != SVX_A_SLAB3 &&
+                       d.block_n >= 32 && d.N % 4 == 0 && d.o_sw % 4 == 0 && d.o_sw >= d.N && (d.o_base & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
+                       (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0) && !getenv("SVX_NO_TMA_EPILOGUE");
+    if (plain) {
+      p.epi_tma = 1;
+      p.ldc = d.o_sw;
+      p.out = d.out + d.o_base;
+      if (d.residual) p.residual = d.residual + d.o_base;
+      if (encode_map(&g->map_c, p.out, (uint64_t)d.M, (uint64_t)d.N, (uint64_t)d.o_sw, 32, 16)) { delete g; return 1; }
+    }
+  }
   const long long tiles_m = (d.M + BM - 1) / BM;
   const long long tiles = tiles_m * p.tiles_n;
   if (tiles > 0x7fffffffLL) { delete g; return fail("gemm: too many tiles"); }
@@ -941,13 +1060,13 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void* stream) {
     return 0;
   }
   switch (g->bn) {
-    case 16: rc = launch_bn<16>(g->map_a, g->map_b, g->p, g->grid, st); break;
-    case 32: rc = launch_bn<32>(g->map_a, g->map_b, g->p, g->grid, st); break;
-    case 64: rc = launch_bn<64>(g->map_a, g->map_b, g->p, g->grid, st); break;
-    case 96: rc = launch_bn<96>(g->map_a, g->map_b, g->p, g->grid, st); break;
-    case 128: rc = launch_bn<128>(g->map_a, g->map_b, g->p, g->grid, st); break;
-    case 192: rc = launch_bn<192>(g->map_a, g->map_b, g->p, g->grid, st); break;
-    default: rc = launch_bn<256>(g->map_a, g->map_b, g->p, g->grid, st); break;
+    case 16: rc = launch_bn<16>(g->map_a, g->map_b, g->map_c, g->p, g->grid, st); break;
+    case 32: rc = launch_bn<32>(g->map_a, g->map_b, g->map_c, g->p, g->grid, st); break;
+    case 64: rc = launch_bn<64>(g->map_a, g->map_b, g->map_c, g->p, g->grid, st); break;
+    case 96: rc = launch_bn<96>(g->map_a, g->map_b, g->map_c, g->p, g->grid, st); break;
+    case 128: rc = launch_bn<128>(g->map_a, g->map_b, g->map_c, g->p, g->grid, st); break;
+    case 192: rc = launch_bn<192>(g->map_a, g->map_b, g->map_c, g->p, g->grid, st); break;
+    default: rc = launch_bn<256>(g->map_a, g->map_b, g->map_c, g->p, g->grid, st); break;
   }
   if (!prepared) delete g;
   return rc;

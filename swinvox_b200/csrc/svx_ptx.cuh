@@ -86,6 +86,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, uint3
       : "memory");
 }
 
+// smem tile -> global (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const void* map, uint32_t src, int32_t x, int32_t y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N bulk groups of this thread have finished READING their smem source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- TMEM / tcgen05 ------------------------------------------------------------------------
 template <uint32_t COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_slot) {

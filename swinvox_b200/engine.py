@@ -25,17 +25,28 @@ def tf32_round(t):
     return bits.view(torch.float32)
 
 
-def choose_block_n(n):
+def choose_block_n(n, rows=None, gather=False):
+    """N tile of one contraction.  Measured on B200 (profiles/r1_gemm_bench_v6.log): the widest tile that divides N
+    wins as long as the grid still fills the 148 SMs for a few waves; gather-mode convolutions re-fetch their A tile
+    once per N tile, so they take the widest tile regardless."""
     if n <= 16:
         return 16
     if n <= 32:
         return 32
     if n <= 64:
         return 64
-    for bn in (128, 192, 96):
-        if n % bn == 0:
-            return bn
-    return 128 if n > 96 else 96
+    cands = [bn for bn in (256, 192, 128, 96) if n % bn == 0] or [128 if n > 96 else 96]
+    if rows is None:
+        return cands[0] if gather else ([bn for bn in cands if bn <= 192] or cands)[0]
+    tiles_m = (rows + 127) // 128
+    overhead = 256 if gather else 48   # per-tile cost that does not shrink with the tile (epilogue latency / A gather)
+    best, best_cost = None, None
+    for bn in cands:
+        waves = -(-tiles_m * (-(-n // bn)) // 148)
+        cost = waves * (bn + overhead)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = bn, cost
+    return best
 
 
 def round_up(x, m):
@@ -83,17 +94,38 @@ class Act:
         return Act(self.buf, self.N, self.D, self.H, self.W, c, self.c0 + c0, self.pad)
 
 
-@dataclass
 class WeightPack:
-    W: torch.Tensor      # [Npad, Kpad] tf32-rounded
-    bias: torch.Tensor   # [Npad]
-    N: int
-    K: int
-    block_n: int
+    """Prepared weights of one contraction.  The N tile (and with it the zero padding of W to [Npad, Kpad]) is fixed
+    lazily by `finalize`, when the op that uses the pack knows its row count and operand mode."""
+
+    def __init__(self, W, bias, N, K, block_n=None):
+        self.raw_W, self.raw_bias = W, bias     # [n_rows, K] tf32-rounded / [n_rows]
+        self.N, self.K, self.block_n = N, K, block_n
+        self.W = self.bias = None
+        if block_n is not None:
+            self.finalize()
+
+    def finalize(self, rows=None, gather=False):
+        if self.W is not None:
+            return self
+        bn = self.block_n or choose_block_n(self.N, rows, gather)
+        n, k = self.raw_W.shape
+        npad, kpad = round_up(max(n, self.N), bn), round_up(k, 32)
+        if (npad, kpad) == (n, k):
+            self.W = self.raw_W.contiguous()
+        else:
+            self.W = torch.zeros(npad, kpad, dtype=torch.float32, device=self.raw_W.device)
+            self.W[:n, :k] = self.raw_W
+        self.bias = torch.zeros(npad, dtype=torch.float32, device=self.raw_W.device)
+        if self.raw_bias is not None:
+            self.bias[:self.raw_bias.numel()] = self.raw_bias
+        self.block_n = bn
+        self.raw_W = self.raw_bias = None
+        return self
 
     @property
     def Kpad(self):
-        return self.W.shape[1]
+        return round_up(self.K, 32)
 
     @property
     def Npad(self):
@@ -103,15 +135,9 @@ class WeightPack:
 def pack_matrix(w2d, bias, device, block_n=None, n_logical=None):
     """w2d: [N, K] fp32 (already folded / permuted)."""
     n, k = w2d.shape
-    n_log = n_logical or n
-    bn = block_n or choose_block_n(n_log)
-    npad, kpad = round_up(max(n, n_log), bn), round_up(k, 32)
-    W = torch.zeros(npad, kpad, dtype=torch.float32, device=device)
-    W[:n, :k] = tf32_round(w2d.detach().to(device=device, dtype=torch.float32))
-    b = torch.zeros(npad, dtype=torch.float32, device=device)
-    if bias is not None:
-        b[:n] = bias.detach().to(device=device, dtype=torch.float32)
-    return WeightPack(W, b, n_log, k, bn)
+    W = tf32_round(w2d.detach().to(device=device, dtype=torch.float32))
+    b = bias.detach().to(device=device, dtype=torch.float32) if bias is not None else None
+    return WeightPack(W, b, n_logical or n, k, block_n)
 
 
 def fold_bn(weight, bias, bn):
@@ -156,7 +182,7 @@ def pack_conv3_slab(weight, bias, bn, device, n_logical=None):
     W = tf32_round(W.reshape(48, 288)).to(device)
     bb = torch.zeros(48, dtype=torch.float32, device=device)
     bb[:cout] = b.to(device)
-    return WeightPack(W, bb, n_logical or cout, 288, 48)
+    return WeightPack(W, bb, n_logical or cout, 288, 48)   # [48, 288] is already the padded layout
 
 
 def convT_class_taps(ks, pad, par):
@@ -262,12 +288,25 @@ class Plan:
         self.op_names.append(name or op)
         self.flops.append(flops)
 
+    # ---- concurrency hints -----------------------------------------------------------------------
+    def lane(self, k):
+        """ops recorded from now on go to lane k (0 = the caller's stream, 1..8 = side streams / graph branches)"""
+        _lib.check(self.lib.svx_plan_set_lane(self.handle, k), self.lib)
+
+    def join(self):
+        """the caller's stream waits for every side lane; also resets the current lane to 0"""
+        self.lane(0)
+        _lib.check(self.lib.svx_plan_add_join(self.handle), self.lib)
+        self.op_names.append("join")
+        self.flops.append(0.0)
+
     # ---- contractions ------------------------------------------------------------------------
     def _taps_tensor(self, taps):
         t = torch.tensor([[a, b, c, 0] for a, b, c in taps], dtype=torch.int32, device=self.device)
         return self.hold(t)
 
     def _fill_epilogue(self, d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out):
+        pack.finalize(rows=d.M, gather=(d.a_mode == A_GATHER))
         d.W = pack.W.data_ptr()
         d.bias = pack.bias.data_ptr()
         d.N, d.K, d.Kpad, d.Npad, d.block_n = pack.N, pack.K, pack.Kpad, pack.Npad, pack.block_n

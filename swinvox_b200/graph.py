@@ -270,6 +270,7 @@ def _convT_layer(plan, x, conv, bn, pads, out, name, act=ACT_RELU, residual=None
     for pd in (0, 1):
         for ph in (0, 1):
             for pw in (0, 1):
+                plan.lane(1 + pd * 4 + ph * 2 + pw)   # the eight classes write disjoint voxels: run them concurrently
                 pk, taps = E.pack_convT_class(conv.weight, bn, dev, pads, (pd, ph, pw), n_logical=n_logical,
                                               block_n=block_n, bias=conv.bias)
                 vox = (pd * oh + ph) * ow + pw
@@ -281,6 +282,7 @@ def _convT_layer(plan, x, conv, bn, pads, out, name, act=ACT_RELU, residual=None
                 plan.conv(x, pk, taps, out, out_map=omap, rows_dhw=(x.D, x.H, x.W), act=act, residual=residual,
                           res_after_act=True, round_out=round_out, out_scale=out_scale, epi_tail=tail,
                           name=f"{name}.p{pd}{ph}{pw}")
+    plan.join()
     return out
 
 

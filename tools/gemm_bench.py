@@ -67,9 +67,9 @@ if __name__ == "__main__":
                       (150528, 576, 192), (150528, 768, 192), (150528, 192, 768),
                       (37632, 1152, 384), (37632, 1536, 384), (37632, 384, 1536), (37632, 256, 1024),
                       (9408, 2304, 768), (9408, 3072, 768), (9408, 768, 3072),
-                      (602112, 64, 256), (602112, 256, 64), (64, 2048, 8192), (64, 8192, 2048),
+                      (602112, 64, 256), (602112, 256, 64), (602112, 64, 64), (150528, 512, 128), (150528, 128, 512), (150528, 128, 256), (37632, 1024, 256), (37632, 256, 1024), (9408, 256, 768), (64, 2048, 8192), (64, 8192, 2048),
                       (8192, 8192, 8192)]:
-        for bn in ([64] if N == 64 else [96, 128, 192, 256]):
+        for bn in ([64] if N == 64 else [64, 96, 128, 192, 256]):
             if N % bn and not (N < bn):
                 continue
             if N < bn and bn != 96 and bn != 128:
