@@ -220,96 +220,178 @@ __global__ void __launch_bounds__(1024) lnsample_kernel(const svx_lnsample_desc 
   }
 }
 
-// ---- shifted-window attention: one CTA per (window, head), one thread per query token ------------------
+// ---- shifted-window attention (timm WindowAttention + roll / partition / reverse) on the tensor cores ------
+// One warp per (window, head); a CTA's four warps share one head so its relative-position bias sits in shared
+// memory.  Per item: K and V (49 x 32, padded to 56 rows) are staged in shared memory, S = Q K^T and O = P V run as
+// mma.sync m16n8k8 TF32 (fp32 accumulate) on 16-query-row strips, softmax (scale, bias, -100 shift mask) works on
+// the accumulator fragments in registers.  The cyclic shift, window partition and their inverses are index
+// arithmetic on the token rows.  P feeds the second contraction straight from the accumulator layout: inside every
+// block of 8 keys the contraction index is permuted (k <-> key 2t / 2t+1), identically for P's columns and V's rows.
 constexpr int WS = 7, WT = 49, HD = 32;
+constexpr int WA_WARPS = 4;
+constexpr int WA_STRIDE = 36;     // floats per staged K / V row: conflict-free fragment loads
+constexpr int WA_ROWS = 56;       // 49 keys padded to 7 blocks of 8
+constexpr int WA_BSTRIDE = 50;    // floats per bias row in shared memory
+constexpr int WA_BIAS_BYTES = (WT * WA_BSTRIDE * 4 + 15) / 16 * 16;
+constexpr int WA_WARP_BYTES = 2 * WA_ROWS * WA_STRIDE * 4 + 2 * 64 * 4;
+constexpr int WA_SMEM = WA_BIAS_BYTES + WA_WARPS * WA_WARP_BYTES;
 
-__global__ void __launch_bounds__(64) winattn_kernel(const svx_winattn_desc d) {
-  __shared__ __align__(16) float sk[WT * HD];
-  __shared__ __align__(16) float sv[WT * HD];
-  __shared__ int stok[WT];
-  __shared__ int sreg[WT];
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(WA_WARPS * 32) winattn_kernel(const svx_winattn_desc d, int ctas_per_head) {
+  extern __shared__ __align__(16) uint8_t wa_smem[];
+  float* sbias = reinterpret_cast<float*>(wa_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* mine = wa_smem + WA_BIAS_BYTES + warp * WA_WARP_BYTES;
+  float* Ks = reinterpret_cast<float*>(mine);
+  float* Vs = Ks + WA_ROWS * WA_STRIDE;
+  int* stok = reinterpret_cast<int*>(Vs + WA_ROWS * WA_STRIDE);
+  int* sreg = stok + 64;
   const int head = blockIdx.x % d.heads;
-  long long w = blockIdx.x / d.heads;
+  const int cta_in_head = blockIdx.x / d.heads;
+  for (int i = threadIdx.x; i < WT * WT; i += blockDim.x)
+    sbias[(i / WT) * WA_BSTRIDE + (i % WT)] = __ldg(d.bias + (long long)head * WT * WT + i);
+  __syncthreads();
   const int nwx = d.W / WS, nwy = d.H / WS;
-  const int wx = (int)(w % nwx); w /= nwx;
-  const int wy = (int)(w % nwy);
-  const long long n = w / nwy;
+  const long long num_windows = (long long)d.N * nwx * nwy;
   const int C3 = 3 * d.C;
-  const int t = threadIdx.x;
-  if (t < WT) {
-    const int py = wy * WS + t / WS, px = wx * WS + t % WS;  // position in the rolled map
-    const int oy = (py + d.shift) % d.H, ox = (px + d.shift) % d.W;
-    stok[t] = (int)((n * d.H + oy) * d.W + ox);
-    int reg = 0;
-    if (d.shift > 0) {
-      const int ry = py < d.H - WS ? 0 : (py < d.H - d.shift ? 1 : 2);
-      const int rx = px < d.W - WS ? 0 : (px < d.W - d.shift ? 1 : 2);
-      reg = ry * 3 + rx;
+  const int g = lane >> 2, t = lane & 3;
+  const float* qkv_h = d.qkv + head * HD;
+  for (long long win = (long long)cta_in_head * WA_WARPS + warp; win < num_windows;
+       win += (long long)ctas_per_head * WA_WARPS) {
+    const int wx = (int)(win % nwx);
+    const int wy = (int)((win / nwx) % nwy);
+    const long long n = win / ((long long)nwx * nwy);
+    __syncwarp();   // the previous item's fragment loads are done before its staging buffers are overwritten
+    for (int i = lane; i < 64; i += 32) {
+      const int tk = min(i, WT - 1);
+      const int py = wy * WS + tk / WS, px = wx * WS + tk % WS;   // position in the rolled map
+      const int oy = (py + d.shift) % d.H, ox = (px + d.shift) % d.W;
+      stok[i] = (int)((n * d.H + oy) * d.W + ox);
+      int reg = 0;
+      if (d.shift > 0) {
+        const int ry = py < d.H - WS ? 0 : (py < d.H - d.shift ? 1 : 2);
+        const int rx = px < d.W - WS ? 0 : (px < d.W - d.shift ? 1 : 2);
+        reg = ry * 3 + rx;
+      }
+      sreg[i] = reg;
     }
-    sreg[t] = reg;
-  }
-  __syncthreads();
-  for (int i = t; i < WT * (HD / 4); i += 64) {
-    const int tok = i / (HD / 4), q4 = i % (HD / 4);
-    const float* row = d.qkv + (long long)stok[tok] * C3 + head * HD + q4 * 4;
-    *reinterpret_cast<float4*>(sk + tok * HD + q4 * 4) = __ldg(reinterpret_cast<const float4*>(row + d.C));
-    *reinterpret_cast<float4*>(sv + tok * HD + q4 * 4) = __ldg(reinterpret_cast<const float4*>(row + 2 * d.C));
-  }
-  __syncthreads();
-  if (t >= WT) return;
-  float q[HD];
-  {
-    const float* row = d.qkv + (long long)stok[t] * C3 + head * HD;
+    __syncwarp();
+    for (int i = lane; i < WA_ROWS * 8; i += 32) {
+      const int row = i >> 3, ch = i & 7;
+      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+      if (row < WT) {
+        const float* base = qkv_h + (long long)stok[row] * C3 + ch * 4;
+        kk = __ldg(reinterpret_cast<const float4*>(base + d.C));
+        vv = __ldg(reinterpret_cast<const float4*>(base + 2 * d.C));
+      }
+      *reinterpret_cast<float4*>(Ks + row * WA_STRIDE + ch * 4) = kk;
+      *reinterpret_cast<float4*>(Vs + row * WA_STRIDE + ch * 4) = vv;
+    }
+    __syncwarp();
+    int kreg[7][2];
 #pragma unroll
-    for (int i = 0; i < HD; i += 4) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(row + i));
-      q[i] = v.x * d.scale; q[i + 1] = v.y * d.scale; q[i + 2] = v.z * d.scale; q[i + 3] = v.w * d.scale;
+    for (int nb = 0; nb < 7; ++nb) {
+      kreg[nb][0] = sreg[8 * nb + 2 * t];
+      kreg[nb][1] = sreg[8 * nb + 2 * t + 1];
+    }
+#pragma unroll 1
+    for (int m = 0; m < 4; ++m) {
+      const int r0 = 16 * m + g, r1 = r0 + 8;
+      const float* q0 = qkv_h + (long long)stok[r0] * C3;
+      const float* q1 = qkv_h + (long long)stok[r1] * C3;
+      uint32_t qa[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        qa[ks][0] = __float_as_uint(__ldg(q0 + 8 * ks + t));
+        qa[ks][1] = __float_as_uint(__ldg(q1 + 8 * ks + t));
+        qa[ks][2] = __float_as_uint(__ldg(q0 + 8 * ks + t + 4));
+        qa[ks][3] = __float_as_uint(__ldg(q1 + 8 * ks + t + 4));
+      }
+      float s[7][4];
+#pragma unroll
+      for (int nb = 0; nb < 7; ++nb) {
+        s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+        const float* kr = Ks + (8 * nb + g) * WA_STRIDE + t;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          mma_tf32_16x8x8(s[nb], qa[ks], __float_as_uint(kr[8 * ks]), __float_as_uint(kr[8 * ks + 4]));
+      }
+      const int myreg0 = sreg[r0], myreg1 = sreg[r1];
+      const float* b0p = sbias + min(r0, WT - 1) * WA_BSTRIDE + 2 * t;
+      const float* b1p = sbias + min(r1, WT - 1) * WA_BSTRIDE + 2 * t;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nb = 0; nb < 7; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * nb + 2 * t + e;
+          const bool ok = col < WT;
+          const int cc = ok ? 8 * nb + e : 0;   // in-bounds bias column (relative to 2t)
+          float v0 = fmaf(s[nb][e], d.scale, b0p[cc]) + (kreg[nb][e] != myreg0 ? -100.f : 0.f);
+          float v1 = fmaf(s[nb][2 + e], d.scale, b1p[cc]) + (kreg[nb][e] != myreg1 ? -100.f : 0.f);
+          v0 = ok ? v0 : -INFINITY;
+          v1 = ok ? v1 : -INFINITY;
+          s[nb][e] = v0;
+          s[nb][2 + e] = v1;
+          mx0 = fmaxf(mx0, v0);
+          mx1 = fmaxf(mx1, v1);
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int nb = 0; nb < 7; ++nb) {
+        s[nb][0] = __expf(s[nb][0] - mx0); s[nb][1] = __expf(s[nb][1] - mx0);
+        s[nb][2] = __expf(s[nb][2] - mx1); s[nb][3] = __expf(s[nb][3] - mx1);
+        sum0 += s[nb][0] + s[nb][1];
+        sum1 += s[nb][2] + s[nb][3];
+      }
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      float o[4][4];
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        // contraction slot t <-> key 8j+2t, slot t+4 <-> key 8j+2t+1: exactly the accumulator's column pair
+        uint32_t pa[4];
+        pa[0] = __float_as_uint(round_tf32(s[j][0]));
+        pa[1] = __float_as_uint(round_tf32(s[j][2]));
+        pa[2] = __float_as_uint(round_tf32(s[j][1]));
+        pa[3] = __float_as_uint(round_tf32(s[j][3]));
+        const float* vr = Vs + (8 * j + 2 * t) * WA_STRIDE + g;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn)
+          mma_tf32_16x8x8(o[dn], pa, __float_as_uint(vr[8 * dn]), __float_as_uint(vr[WA_STRIDE + 8 * dn]));
+      }
+      const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+      if (r0 < WT) {
+        float* dst = d.out + (long long)stok[r0] * d.C + head * HD + 2 * t;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn)
+          *reinterpret_cast<float2*>(dst + 8 * dn) =
+              make_float2(maybe_round(o[dn][0] * inv0, d.round_tf32), maybe_round(o[dn][1] * inv0, d.round_tf32));
+      }
+      if (r1 < WT) {
+        float* dst = d.out + (long long)stok[r1] * d.C + head * HD + 2 * t;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn)
+          *reinterpret_cast<float2*>(dst + 8 * dn) =
+              make_float2(maybe_round(o[dn][2] * inv1, d.round_tf32), maybe_round(o[dn][3] * inv1, d.round_tf32));
+      }
     }
   }
-  const float* brow = d.bias + ((long long)head * WT + t) * WT;
-  const int myreg = sreg[t];
-  float s[WT];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < WT; ++j) {
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < HD; i += 4) {
-      const float4 kv = *reinterpret_cast<const float4*>(sk + j * HD + i);
-      acc = fmaf(q[i], kv.x, acc); acc = fmaf(q[i + 1], kv.y, acc);
-      acc = fmaf(q[i + 2], kv.z, acc); acc = fmaf(q[i + 3], kv.w, acc);
-    }
-    acc += __ldg(brow + j);
-    if (sreg[j] != myreg) acc += -100.f;
-    s[j] = acc;
-    mx = fmaxf(mx, acc);
-  }
-  float den = 0.f;
-#pragma unroll
-  for (int j = 0; j < WT; ++j) {
-    s[j] = __expf(s[j] - mx);
-    den += s[j];
-  }
-  const float inv = 1.f / den;
-  float o[HD];
-#pragma unroll
-  for (int i = 0; i < HD; ++i) o[i] = 0.f;
-#pragma unroll
-  for (int j = 0; j < WT; ++j) {
-    const float pj = s[j] * inv;
-#pragma unroll
-    for (int i = 0; i < HD; i += 4) {
-      const float4 vv = *reinterpret_cast<const float4*>(sv + j * HD + i);
-      o[i] = fmaf(pj, vv.x, o[i]); o[i + 1] = fmaf(pj, vv.y, o[i + 1]);
-      o[i + 2] = fmaf(pj, vv.z, o[i + 2]); o[i + 3] = fmaf(pj, vv.w, o[i + 3]);
-    }
-  }
-  float* dst = d.out + (long long)stok[t] * d.C + head * HD;
-#pragma unroll
-  for (int i = 0; i < HD; i += 4)
-    *reinterpret_cast<float4*>(dst + i) =
-        make_float4(maybe_round(o[i], d.round_tf32), maybe_round(o[i + 1], d.round_tf32),
-                    maybe_round(o[i + 2], d.round_tf32), maybe_round(o[i + 3], d.round_tf32));
 }
 
 // ---- depthwise k=s conv, channels-last ---------------------------------------------------------------
@@ -573,9 +655,17 @@ int winattn_launch(const svx_winattn_desc& d, void* stream) {
   SVX_REQUIRE(d.qkv && d.out && d.bias, "window_attention: null operand");
   SVX_REQUIRE(d.H % WS == 0 && d.W % WS == 0 && d.C == d.heads * HD && d.shift >= 0 && d.shift < WS,
               "window_attention: needs 7x7 windows, head_dim 32 (H=%d W=%d C=%d heads=%d)", d.H, d.W, d.C, d.heads);
-  const long long blocks = (long long)d.N * (d.H / WS) * (d.W / WS) * d.heads;
-  SVX_REQUIRE(blocks < 0x7fffffffLL, "window_attention: grid too large");
-  winattn_kernel<<<(int)blocks, 64, 0, (cudaStream_t)stream>>>(d);
+  const long long windows = (long long)d.N * (d.H / WS) * (d.W / WS);
+  long long per_head = (windows + WA_WARPS - 1) / WA_WARPS;
+  const long long cap = (3LL * kSmCount + d.heads - 1) / d.heads;   // ~3 resident CTAs per SM over all heads
+  if (per_head > cap) per_head = cap;
+  if (per_head < 1) per_head = 1;
+  static bool configured = false;
+  if (!configured) {
+    SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
+    configured = true;
+  }
+  winattn_kernel<<<(int)(per_head * d.heads), WA_WARPS * 32, WA_SMEM, (cudaStream_t)stream>>>(d, (int)per_head);
   SVX_LAUNCH_OK("winattn_kernel");
   return 0;
 }

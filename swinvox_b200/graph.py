@@ -130,7 +130,7 @@ def lower_swin(plan, swin, img, N):
             plan.layernorm_rows(x, blk.norm1.weight.detach().float().to(dev), blk.norm1.bias.detach().float().to(dev), y,
                                 eps=blk.norm1.eps, name=nm + ".norm1")
             qkv = plan.new_act(N, 1, H, H, 3 * Cc)
-            plan.linear(y, E.pack_matrix(blk.attn.qkv.weight, blk.attn.qkv.bias, dev), qkv, name=nm + ".qkv")
+            plan.linear(y, E.pack_matrix(blk.attn.qkv.weight, blk.attn.qkv.bias, dev), qkv, round_out=True, name=nm + ".qkv")
             att = plan.new_act(N, 1, H, H, Cc)
             bias = relative_position_bias(blk.attn.relative_position_bias_table, heads).to(dev)
             plan.window_attention(qkv, att, bias, H, H, heads, shift, 32 ** -0.5, name=nm + ".attn")

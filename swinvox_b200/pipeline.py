@@ -91,3 +91,15 @@ class DataParallelReconstructor:
         dist.all_gather(all_logits, logits.contiguous(), group=self.group)
         dist.all_gather(all_counts, counts, group=self.group)
         return torch.cat(all_logits), torch.cat(all_counts)
+
+    @torch.no_grad()
+    def evaluate(self, images, gt):
+        """images [B,V,3,224,224], gt [B,32,32,32]: the GLOBAL batch, identical on every rank.  Each rank evaluates its
+        shard of objects (the last shards are padded by repeating the final object so every rank runs the same shape)
+        and the gathered results are trimmed back to B objects."""
+        B = images.shape[0]
+        per = (B + self.world - 1) // self.world
+        idx = torch.arange(self.rank * per, (self.rank + 1) * per).clamp_(max=B - 1)
+        dev = self.recon.device
+        logits, counts = self.evaluate_local(images[idx].to(dev), gt[idx].to(dev))
+        return logits[:B], counts[:B]

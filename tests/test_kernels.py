@@ -338,7 +338,7 @@ def test_window_attention(dev, H, heads, shift):
     DEV = dev
     torch.manual_seed(7)
     N, Cc = 2, heads * 32
-    qkv = torch.randn(N, H, H, 3 * Cc)
+    qkv = E.tf32_round(torch.randn(N, H, H, 3 * Cc))   # the qkv GEMM stores its output TF32-rounded
     bias = torch.randn(heads, 49, 49)
     scale = 32 ** -0.5
     p = E.Plan(DEV)
@@ -370,7 +370,8 @@ def test_window_attention(dev, H, heads, shift):
     o = o.transpose(1, 2).reshape(N, nw, nw, 7, 7, Cc).permute(0, 1, 3, 2, 4, 5).reshape(N, H, H, Cc)
     if shift:
         o = torch.roll(o, (shift, shift), (1, 2))
-    assert rel_err(out.view().reshape(N, H, H, Cc), o) < 2e-5
+    # the CUDA kernel contracts on the tensor cores (TF32 operands: P is rounded to 11 bits), the CPU twin in fp32
+    assert rel_err(out.view().reshape(N, H, H, Cc), o) < (1e-3 if DEV == "cuda" else 2e-5)
 
 
 def test_cva_pieces(dev):
