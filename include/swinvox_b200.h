@@ -33,7 +33,14 @@ enum { SVX_ACT_NONE = 0, SVX_ACT_RELU = 1, SVX_ACT_LEAKY = 2, SVX_ACT_GELU = 3 }
 /* A operand modes */
 enum { SVX_A_PLAIN = 0, SVX_A_GATHER = 1, SVX_A_FLAT = 2, SVX_A_SLAB3 = 3 };
 /* special epilogues */
-enum { SVX_EPI_STD = 0, SVX_EPI_DEC_TAIL = 1 /* decoder layer4+layer5+cat, decoder.py:80-89 */ };
+enum {
+  SVX_EPI_STD = 0,
+  SVX_EPI_DEC_TAIL = 1, /* decoder layer4+layer5+cat, decoder.py:80-89 */
+  SVX_EPI_POOL8 = 2     /* conv + BN + LeakyReLU + MaxPool3d(2) (refiner.py:21-26): the N columns are 8 groups (the 2x2x2
+                           conv positions of one pooled voxel) of N/8 channels; out[r, c] = act(max_g acc[r, g*N/8 + c] +
+                           bias[c]) -- valid because the activation is monotonic and the bias is shared by the group.
+                           Plain row-major output [M, N/8] only (o_sw = row pitch). */
+};
 /* pooling modes */
 enum { SVX_POOL_MAX = 0, SVX_POOL_AVG = 1 };
 

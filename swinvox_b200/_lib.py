@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libswinvox_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU = 0, 1, 2, 3
 A_PLAIN, A_GATHER, A_FLAT, A_SLAB3 = 0, 1, 2, 3
-EPI_STD, EPI_DEC_TAIL = 0, 1
+EPI_STD, EPI_DEC_TAIL, EPI_POOL8 = 0, 1, 2
 POOL_MAX, POOL_AVG = 0, 1
 
 i32, i64, f32, ptr = C.c_int32, C.c_int64, C.c_float, C.c_void_p

@@ -35,8 +35,7 @@ constexpr int kGatherLag = 2;
 constexpr int kMaxTaps = 64;
 constexpr int kSlab = 16;                        // accumulator columns per epilogue pass
 constexpr int kEpiWarps = 8;                     // warps 0-3, plus warps 6-9 when they are not gathering
-constexpr int kStagingBytes = kEpiWarps * 32 * kSlab * 4;  // per epilogue warp: 32 rows x 16 columns fp32
-constexpr int kOffBytes = kEpiWarps * 32 * 8;
+constexpr int kBlockBytes = 32 * kSlab * 4;      // one staged 32-row x 16-column fp32 block
 
 struct GemmParams {
   int M, N, K, Npad, nk, tiles_n, tiles_m, a_mode;
@@ -71,12 +70,18 @@ struct Cfg {
   static constexpr int kBBytes = BN * BK * 4;
   static constexpr int kStageBytes = A_STAGE_BYTES + kBBytes;
   static constexpr int kCtasPerSm = BN <= 96 ? 2 : 1;   // two resident CTAs double the epilogue / gather warps
-  static constexpr int kStagesRaw = ((kCtasPerSm == 2 ? 92 : 196) * 1024) / kStageBytes;
+  // per epilogue warp: kEpiBufs staged blocks for the TMA-store epilogue (the mapped-output epilogue uses the first
+  // block for its transpose and the 256 bytes after it for the row offsets); 512-byte multiples keep the 64B swizzle
+  static constexpr int kEpiBufs = BN == 96 ? 1 : 2;
+  static constexpr int kWarpStage = BN == 96 ? kBlockBytes + 512 : 2 * kBlockBytes;
+  static constexpr int kAuxBytes = kEpiWarps * kWarpStage + 256;          // + barriers
+  static constexpr int kBudget = (kCtasPerSm == 2 ? 115712 : 232448) - 1024 - kAuxBytes;
+  static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr uint32_t kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
   static_assert(kStages >= kGatherLag + 1, "the gather pipeline needs more stages than its lag");
   // stages + 1024 alignment slack + barriers (256) + staging + row offsets
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kStagingBytes + kOffBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kAuxBytes;
 };
 
 // exact-erf GELU (nn.GELU()) with a branch-free erf: Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7, ~14 instructions
@@ -191,9 +196,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   // after the pipeline stages: epilogue staging (1024-byte aligned: TMA-store source blocks), row offsets, barriers
   uint8_t* aux_gen = smem_gen + S * C::kStageBytes;
-  float* staging_all = reinterpret_cast<float*>(aux_gen);
-  long long* soff_all = reinterpret_cast<long long*>(aux_gen + kStagingBytes);
-  constexpr int kBarOff = kStagingBytes + kOffBytes;
+  constexpr int kBarOff = kEpiWarps * C::kWarpStage;
   const uint32_t bar_base = smem_base + S * C::kStageBytes + kBarOff;
   // barrier layout: full[S], empty[S], tmem_full[2], tmem_empty[2], tmem slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -373,12 +376,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int part = warp >= 6 ? 1 : 0;
     const int nparts = a_mode == SVX_A_GATHER ? 1 : 2;
     const int ew = part * 4 + quarter;
-    float* staging = staging_all + ew * (32 * kSlab);
-    long long* soff = soff_all + ew * 32;
+    float* staging = reinterpret_cast<float*>(aux_gen + ew * C::kWarpStage);
+    long long* soff = reinterpret_cast<long long*>(aux_gen + ew * C::kWarpStage + kBlockBytes);
     constexpr int SLAB = kSlab;
     constexpr int CP = SLAB / 4;     // float4 chunks per staged row
     const bool rowwise = (p.epi_mode == SVX_EPI_DEC_TAIL) || !p.vec_ok;
-    uint32_t it = 0;
+    uint32_t it = 0, buf = 0;   // buf: which of this warp's two staging blocks the next TMA store uses
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
       const uint32_t as = it & 1u;
@@ -386,31 +389,53 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // ---- plain row-major output: TMEM -> registers -> bias / residual / activation -> 64B-swizzled smem block
         // (32 rows x 16 columns per warp) -> one TMA store per block.  No per-element address arithmetic, the
         // store is coalesced by the TMA unit and clipped at the matrix edges. ----
-        mbar_wait(tmem_full_bar(as), (it >> 1) & 1u);
-        tc_fence_after();
         const uint32_t lane_addr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
         const int row = m0 + quarter * 32 + lane;
         const bool row_ok = row < p.M;
         const float* res_row = p.residual + static_cast<long long>(row) * p.ldc;
         const bool has_res = p.residual != nullptr;
         const bool pre = has_res && !p.res_after_act, post = has_res && p.res_after_act;
-        char* stg = reinterpret_cast<char*>(staging);                       // 2 KB, 1024-byte aligned
+        char* stg = reinterpret_cast<char*>(staging);                       // 2 x 2 KB, 1024-byte aligned
         const uint32_t stg_u32 = smem_u32(stg);
-        char* my_row = stg + lane * 64;
         const int sw = (lane >> 1) & 3;                                        // 64B swizzle phase of this row
+        const bool pool8 = p.epi_mode == SVX_EPI_POOL8;
+        const int ncols = pool8 ? (p.N >> 3) : BN;          // output columns this tile produces
+        // The residual does not depend on the accumulator: the first block's residual is requested before waiting
+        // for the MMAs of this tile, and each block requests the next block's while it works (HBM latency hidden).
+        float4 rv_next[4];
+        auto load_res = [&](int jbn) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            rv_next[c] = (row_ok && jbn + 4 * c < p.N) ? *reinterpret_cast<const float4*>(res_row + jbn + 4 * c)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        if (has_res && n0 + part * SLAB < p.N) load_res(n0 + part * SLAB);
+        mbar_wait(tmem_full_bar(as), (it >> 1) & 1u);
+        tc_fence_after();
 #pragma unroll 1
-        for (int c0 = part * SLAB; c0 < BN; c0 += nparts * SLAB) {
+        for (int c0 = part * SLAB; c0 < ncols; c0 += nparts * SLAB) {
           const int jb = n0 + c0;
           if (jb >= p.N) break;  // warp-uniform
           uint32_t v[SLAB];
           __syncwarp();
           tmem_ld16(lane_addr + c0, v);
+          if (pool8) {   // max over the eight conv positions of this pooled voxel (column groups of N/8)
+            tmem_ld_wait();
+#pragma unroll 1
+            for (int gq = 1; gq < 8; ++gq) {
+              uint32_t w[SLAB];
+              tmem_ld16(lane_addr + gq * ncols + c0, w);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < SLAB; ++q) v[q] = __float_as_uint(fmaxf(__uint_as_float(v[q]), __uint_as_float(w[q])));
+            }
+          }
           float4 rv[4];
           if (has_res) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              rv[c] = (row_ok && jb + 4 * c < p.N) ? *reinterpret_cast<const float4*>(res_row + jb + 4 * c)
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = 0; c < 4; ++c) rv[c] = rv_next[c];
+            const int c0n = c0 + nparts * SLAB;
+            if (c0n < ncols && n0 + c0n < p.N) load_res(n0 + c0n);
           }
           float4 bv[4];
 #pragma unroll
@@ -456,18 +481,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int q = 0; q < SLAB; ++q) x[q] = round_tf32(x[q]);
           }
-          // the previous block of this warp must have been read out of smem by the TMA unit
-          if (lane == 0) tma_store_wait_read<0>();
+          // this buffer's previous store (two blocks ago) must have been read out of smem by the TMA unit
+          if (lane == 0) tma_store_wait_read<C::kEpiBufs - 1>();
           __syncwarp();
+          char* my_row = stg + buf * 2048 + lane * 64;
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *reinterpret_cast<float4*>(my_row + ((c ^ sw) << 4)) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&map_c, stg_u32, jb, m0 + quarter * 32);
+            tma_store_2d(&map_c, stg_u32 + buf * 2048, jb, m0 + quarter * 32);
             tma_store_commit();
           }
+          buf = (buf + 1u) % C::kEpiBufs;
         }
         tc_fence_before();
         __syncwarp();
@@ -1008,8 +1035,10 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   {
     const bool compact = d.o_sh == (long long)d.out_W * d.o_sw && d.o_sd == (long long)d.out_H * d.o_sh &&
                          d.o_sn == (long long)d.out_D * d.o_sd;
-    const bool plain = compact && d.valid_W == 0 && d.epi_mode == SVX_EPI_STD && d.a_mode != SVX_A_SLAB3 &&
-                       d.block_n >= 32 && d.N % 4 == 0 && d.o_sw % 4 == 0 && d.o_sw >= d.N && (d.o_base & 3) == 0 &&
+    const bool pool8 = d.epi_mode == SVX_EPI_POOL8;
+    const int n_out = pool8 ? d.N / 8 : d.N;
+    const bool plain = compact && d.valid_W == 0 && (d.epi_mode == SVX_EPI_STD || pool8) && d.a_mode != SVX_A_SLAB3 &&
+                       d.block_n >= 32 && n_out % 4 == 0 && d.o_sw % 4 == 0 && d.o_sw >= n_out && (d.o_base & 3) == 0 &&
                        (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
                        (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0) && !getenv("SVX_NO_TMA_EPILOGUE");
     if (plain) {
@@ -1017,7 +1046,11 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
       p.ldc = d.o_sw;
       p.out = d.out + d.o_base;
       if (d.residual) p.residual = d.residual + d.o_base;
-      if (encode_map(&g->map_c, p.out, (uint64_t)d.M, (uint64_t)d.N, (uint64_t)d.o_sw, 32, 16)) { delete g; return 1; }
+      if (encode_map(&g->map_c, p.out, (uint64_t)d.M, (uint64_t)n_out, (uint64_t)d.o_sw, 32, 16)) { delete g; return 1; }
+    }
+    if (pool8 && !(plain && d.N == d.block_n && d.N % 128 == 0 && !d.residual)) {
+      delete g;
+      return fail("gemm: the pooled epilogue needs a plain [M, N/8] output, one N tile (block_n == N) and no residual");
     }
   }
   const long long tiles_m = (d.M + BM - 1) / BM;

@@ -23,6 +23,9 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // block-wide sum for blockDim.x <= 1024; `red` is 32 floats of shared memory
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
@@ -222,107 +225,129 @@ __global__ void __launch_bounds__(1024) lnsample_kernel(const svx_lnsample_desc 
 
 // ---- shifted-window attention (timm WindowAttention + roll / partition / reverse) on the tensor cores ------
 // One warp per (window, head); a CTA's four warps share one head so its relative-position bias sits in shared
-// memory.  Per item: K and V (49 x 32, padded to 56 rows) are staged in shared memory, S = Q K^T and O = P V run as
-// mma.sync m16n8k8 TF32 (fp32 accumulate) on 16-query-row strips, softmax (scale, bias, -100 shift mask) works on
+// memory.  Per item Q, K and V (49 x 32 each) are staged in shared memory by cp.async; S = Q K^T and O = P V run as
+// mma.sync m16n8k8 TF32 (fp32 accumulate) on 16-query-row strips; softmax (scale, bias, -100 shift mask) works on
 // the accumulator fragments in registers.  The cyclic shift, window partition and their inverses are index
-// arithmetic on the token rows.  P feeds the second contraction straight from the accumulator layout: inside every
-// block of 8 keys the contraction index is permuted (k <-> key 2t / 2t+1), identically for P's columns and V's rows.
+// arithmetic on the token rows.  Index maps are chosen so every fragment is a 16-byte shared-memory read:
+//   QK^T contraction slot (step ks, slot t / t+4)  <->  d = 8t + 2ks / 8t + 2ks + 1   (same map for Q and K)
+//   PV   contraction slot (block j, slot t / t+4)  <->  key 8j + 2t / 8j + 2t + 1     (= the accumulator's columns)
+//   PV   output column (tile dn, column c)         <->  d = 4c + dn                    (a lane ends up with 8 adjacent d)
 constexpr int WS = 7, WT = 49, HD = 32;
-constexpr int WA_WARPS = 4;
-constexpr int WA_STRIDE = 36;     // floats per staged K / V row: conflict-free fragment loads
-constexpr int WA_ROWS = 56;       // 49 keys padded to 7 blocks of 8
+constexpr int WA_ITEMS = 4;       // (window, head) items in flight per CTA, two warps each
+constexpr int WA_STRIDE = 36;     // floats per staged row: conflict-free 16-byte fragment loads
+constexpr int WA_ROWS = 56;       // 49 tokens padded to 7 blocks of 8 (rows 49..55 stay zero)
 constexpr int WA_BSTRIDE = 50;    // floats per bias row in shared memory
 constexpr int WA_BIAS_BYTES = (WT * WA_BSTRIDE * 4 + 15) / 16 * 16;
-constexpr int WA_WARP_BYTES = 2 * WA_ROWS * WA_STRIDE * 4 + 2 * 64 * 4;
-constexpr int WA_SMEM = WA_BIAS_BYTES + WA_WARPS * WA_WARP_BYTES;
+constexpr int WA_ITEM_BYTES = 3 * WA_ROWS * WA_STRIDE * 4 + 2 * 64 * 4;
+constexpr int WA_SMEM = WA_BIAS_BYTES + WA_ITEMS * WA_ITEM_BYTES;
+constexpr float kLog2e = 1.4426950408889634f;
 
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-__global__ void __launch_bounds__(WA_WARPS * 32) winattn_kernel(const svx_winattn_desc d, int ctas_per_head) {
+// Two warps per item (query strips {0,1} and {2,3}); they stage the item together and meet on a named barrier.
+// Scores are kept in the log2 domain: scale and bias carry a factor log2(e), so the softmax exponent is one ex2.
+template <bool SHIFTED>
+__global__ void __launch_bounds__(WA_ITEMS * 64, 2) winattn_kernel(const svx_winattn_desc d, int ctas_per_head) {
   extern __shared__ __align__(16) uint8_t wa_smem[];
   float* sbias = reinterpret_cast<float*>(wa_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* mine = wa_smem + WA_BIAS_BYTES + warp * WA_WARP_BYTES;
-  float* Ks = reinterpret_cast<float*>(mine);
+  const int pair = warp >> 1, half = warp & 1, ptid = threadIdx.x & 63;
+  uint8_t* mine = wa_smem + WA_BIAS_BYTES + pair * WA_ITEM_BYTES;
+  float* Qs = reinterpret_cast<float*>(mine);
+  float* Ks = Qs + WA_ROWS * WA_STRIDE;
   float* Vs = Ks + WA_ROWS * WA_STRIDE;
-  int* stok = reinterpret_cast<int*>(Vs + WA_ROWS * WA_STRIDE);
-  int* sreg = stok + 64;
+  uint32_t* stok = reinterpret_cast<uint32_t*>(Vs + WA_ROWS * WA_STRIDE);   // token row offset in 16-byte units
+  int* sreg = reinterpret_cast<int*>(stok + 64);
   const int head = blockIdx.x % d.heads;
   const int cta_in_head = blockIdx.x / d.heads;
   for (int i = threadIdx.x; i < WT * WT; i += blockDim.x)
-    sbias[(i / WT) * WA_BSTRIDE + (i % WT)] = __ldg(d.bias + (long long)head * WT * WT + i);
+    sbias[(i / WT) * WA_BSTRIDE + (i % WT)] = __ldg(d.bias + (long long)head * WT * WT + i) * kLog2e;
+  for (int i = ptid; i < 3 * WA_ROWS * WA_STRIDE; i += 64) Qs[i] = 0.f;   // incl. the padding rows, never rewritten
   __syncthreads();
   const int nwx = d.W / WS, nwy = d.H / WS;
   const long long num_windows = (long long)d.N * nwx * nwy;
-  const int C3 = 3 * d.C;
+  const uint32_t C3q = (3 * d.C) >> 2, Cq = d.C >> 2;
   const int g = lane >> 2, t = lane & 3;
-  const float* qkv_h = d.qkv + head * HD;
-  for (long long win = (long long)cta_in_head * WA_WARPS + warp; win < num_windows;
-       win += (long long)ctas_per_head * WA_WARPS) {
+  const float4* qkv4 = reinterpret_cast<const float4*>(d.qkv + head * HD);
+  const uint32_t qs_u32 = smem_u32(Qs);
+  const float scale2 = d.scale * kLog2e;
+  const float kMask = -100.f * kLog2e;
+  const int barid = 1 + pair;
+  for (long long win = (long long)cta_in_head * WA_ITEMS + pair; win < num_windows;
+       win += (long long)ctas_per_head * WA_ITEMS) {
     const int wx = (int)(win % nwx);
     const int wy = (int)((win / nwx) % nwy);
     const long long n = win / ((long long)nwx * nwy);
-    __syncwarp();   // the previous item's fragment loads are done before its staging buffers are overwritten
-    for (int i = lane; i < 64; i += 32) {
-      const int tk = min(i, WT - 1);
+    named_bar(barid, 64);   // both warps are done with the previous item's staging buffers
+    {
+      const int tk = min(ptid, WT - 1);
       const int py = wy * WS + tk / WS, px = wx * WS + tk % WS;   // position in the rolled map
       const int oy = (py + d.shift) % d.H, ox = (px + d.shift) % d.W;
-      stok[i] = (int)((n * d.H + oy) * d.W + ox);
+      stok[ptid] = (uint32_t)((n * d.H + oy) * d.W + ox) * C3q;
       int reg = 0;
-      if (d.shift > 0) {
+      if (SHIFTED) {
         const int ry = py < d.H - WS ? 0 : (py < d.H - d.shift ? 1 : 2);
         const int rx = px < d.W - WS ? 0 : (px < d.W - d.shift ? 1 : 2);
         reg = ry * 3 + rx;
       }
-      sreg[i] = reg;
+      sreg[ptid] = reg;
     }
-    __syncwarp();
-    for (int i = lane; i < WA_ROWS * 8; i += 32) {
+    named_bar(barid, 64);
+    // stage Q | K | V rows (49 x 128 B each) with 16-byte cp.async: 8 lanes per row
+    for (int i = ptid; i < WT * 8; i += 64) {
       const int row = i >> 3, ch = i & 7;
-      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
-      if (row < WT) {
-        const float* base = qkv_h + (long long)stok[row] * C3 + ch * 4;
-        kk = __ldg(reinterpret_cast<const float4*>(base + d.C));
-        vv = __ldg(reinterpret_cast<const float4*>(base + 2 * d.C));
-      }
-      *reinterpret_cast<float4*>(Ks + row * WA_STRIDE + ch * 4) = kk;
-      *reinterpret_cast<float4*>(Vs + row * WA_STRIDE + ch * 4) = vv;
+      const float4* base = qkv4 + stok[row] + ch;
+      const uint32_t dst = qs_u32 + (row * WA_STRIDE + ch * 4) * 4;
+      cp_async16_zfill(dst, base, 16u);
+      cp_async16_zfill(dst + WA_ROWS * WA_STRIDE * 4, base + Cq, 16u);
+      cp_async16_zfill(dst + 2 * WA_ROWS * WA_STRIDE * 4, base + 2 * Cq, 16u);
     }
-    __syncwarp();
+    cp_async_commit();
     int kreg[7][2];
+    if (SHIFTED) {
 #pragma unroll
-    for (int nb = 0; nb < 7; ++nb) {
-      kreg[nb][0] = sreg[8 * nb + 2 * t];
-      kreg[nb][1] = sreg[8 * nb + 2 * t + 1];
-    }
-#pragma unroll 1
-    for (int m = 0; m < 4; ++m) {
-      const int r0 = 16 * m + g, r1 = r0 + 8;
-      const float* q0 = qkv_h + (long long)stok[r0] * C3;
-      const float* q1 = qkv_h + (long long)stok[r1] * C3;
-      uint32_t qa[4][4];
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        qa[ks][0] = __float_as_uint(__ldg(q0 + 8 * ks + t));
-        qa[ks][1] = __float_as_uint(__ldg(q1 + 8 * ks + t));
-        qa[ks][2] = __float_as_uint(__ldg(q0 + 8 * ks + t + 4));
-        qa[ks][3] = __float_as_uint(__ldg(q1 + 8 * ks + t + 4));
+      for (int nb = 0; nb < 7; ++nb) {
+        kreg[nb][0] = sreg[8 * nb + 2 * t];
+        kreg[nb][1] = sreg[8 * nb + 2 * t + 1];
       }
+    }
+    cp_async_wait<0>();
+    named_bar(barid, 64);
+#pragma unroll 1
+    for (int mi = 0; mi < 2; ++mi) {
+      const int r0 = 16 * (2 * half + mi) + g, r1 = r0 + 8;
+      const int r1c = min(r1, WA_ROWS - 1);
+      // Q fragments: lane t holds d = 8t .. 8t+7 of rows r0, r1 (contraction slot map above)
+      const float4 qa0 = *reinterpret_cast<const float4*>(Qs + r0 * WA_STRIDE + 8 * t);
+      const float4 qb0 = *reinterpret_cast<const float4*>(Qs + r0 * WA_STRIDE + 8 * t + 4);
+      const float4 qa1 = *reinterpret_cast<const float4*>(Qs + r1c * WA_STRIDE + 8 * t);
+      const float4 qb1 = *reinterpret_cast<const float4*>(Qs + r1c * WA_STRIDE + 8 * t + 4);
+      const float q0[8] = {qa0.x, qa0.y, qa0.z, qa0.w, qb0.x, qb0.y, qb0.z, qb0.w};
+      const float q1[8] = {qa1.x, qa1.y, qa1.z, qa1.w, qb1.x, qb1.y, qb1.z, qb1.w};
       float s[7][4];
 #pragma unroll
       for (int nb = 0; nb < 7; ++nb) {
         s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
-        const float* kr = Ks + (8 * nb + g) * WA_STRIDE + t;
+        const float4 ka = *reinterpret_cast<const float4*>(Ks + (8 * nb + g) * WA_STRIDE + 8 * t);
+        const float4 kb = *reinterpret_cast<const float4*>(Ks + (8 * nb + g) * WA_STRIDE + 8 * t + 4);
+        const float kk[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          mma_tf32_16x8x8(s[nb], qa[ks], __float_as_uint(kr[8 * ks]), __float_as_uint(kr[8 * ks + 4]));
+          mma_tf32_16x8x8(s[nb], __float_as_uint(q0[2 * ks]), __float_as_uint(q1[2 * ks]), __float_as_uint(q0[2 * ks + 1]),
+                          __float_as_uint(q1[2 * ks + 1]), __float_as_uint(kk[2 * ks]), __float_as_uint(kk[2 * ks + 1]));
       }
-      const int myreg0 = sreg[r0], myreg1 = sreg[r1];
+      const int myreg0 = SHIFTED ? sreg[r0] : 0, myreg1 = SHIFTED ? sreg[r1] : 0;
       const float* b0p = sbias + min(r0, WT - 1) * WA_BSTRIDE + 2 * t;
       const float* b1p = sbias + min(r1, WT - 1) * WA_BSTRIDE + 2 * t;
       float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -330,13 +355,18 @@ __global__ void __launch_bounds__(WA_WARPS * 32) winattn_kernel(const svx_winatt
       for (int nb = 0; nb < 7; ++nb) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int col = 8 * nb + 2 * t + e;
-          const bool ok = col < WT;
-          const int cc = ok ? 8 * nb + e : 0;   // in-bounds bias column (relative to 2t)
-          float v0 = fmaf(s[nb][e], d.scale, b0p[cc]) + (kreg[nb][e] != myreg0 ? -100.f : 0.f);
-          float v1 = fmaf(s[nb][2 + e], d.scale, b1p[cc]) + (kreg[nb][e] != myreg1 ? -100.f : 0.f);
-          v0 = ok ? v0 : -INFINITY;
-          v1 = ok ? v1 : -INFINITY;
+          // columns 8nb + 2t + e; only block 6 has columns beyond the 49 keys (everything but t == 0, e == 0)
+          const bool ok = nb < 6 || (t == 0 && e == 0);
+          float v0 = fmaf(s[nb][e], scale2, ok ? b0p[8 * nb + e] : 0.f);
+          float v1 = fmaf(s[nb][2 + e], scale2, ok ? b1p[8 * nb + e] : 0.f);
+          if (SHIFTED) {
+            v0 += kreg[nb][e] != myreg0 ? kMask : 0.f;
+            v1 += kreg[nb][e] != myreg1 ? kMask : 0.f;
+          }
+          if (nb == 6) {
+            v0 = ok ? v0 : -INFINITY;
+            v1 = ok ? v1 : -INFINITY;
+          }
           s[nb][e] = v0;
           s[nb][2 + e] = v1;
           mx0 = fmaxf(mx0, v0);
@@ -350,8 +380,8 @@ __global__ void __launch_bounds__(WA_WARPS * 32) winattn_kernel(const svx_winatt
       float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
       for (int nb = 0; nb < 7; ++nb) {
-        s[nb][0] = __expf(s[nb][0] - mx0); s[nb][1] = __expf(s[nb][1] - mx0);
-        s[nb][2] = __expf(s[nb][2] - mx1); s[nb][3] = __expf(s[nb][3] - mx1);
+        s[nb][0] = ex2_approx(s[nb][0] - mx0); s[nb][1] = ex2_approx(s[nb][1] - mx0);
+        s[nb][2] = ex2_approx(s[nb][2] - mx1); s[nb][3] = ex2_approx(s[nb][3] - mx1);
         sum0 += s[nb][0] + s[nb][1];
         sum1 += s[nb][2] + s[nb][3];
       }
@@ -364,31 +394,32 @@ __global__ void __launch_bounds__(WA_WARPS * 32) winattn_kernel(const svx_winatt
       for (int dn = 0; dn < 4; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
 #pragma unroll
       for (int j = 0; j < 7; ++j) {
-        // contraction slot t <-> key 8j+2t, slot t+4 <-> key 8j+2t+1: exactly the accumulator's column pair
-        uint32_t pa[4];
-        pa[0] = __float_as_uint(round_tf32(s[j][0]));
-        pa[1] = __float_as_uint(round_tf32(s[j][2]));
-        pa[2] = __float_as_uint(round_tf32(s[j][1]));
-        pa[3] = __float_as_uint(round_tf32(s[j][3]));
-        const float* vr = Vs + (8 * j + 2 * t) * WA_STRIDE + g;
-#pragma unroll
-        for (int dn = 0; dn < 4; ++dn)
-          mma_tf32_16x8x8(o[dn], pa, __float_as_uint(vr[8 * dn]), __float_as_uint(vr[WA_STRIDE + 8 * dn]));
+        const uint32_t p0 = __float_as_uint(round_tf32(s[j][0])), p1 = __float_as_uint(round_tf32(s[j][2]));
+        const uint32_t p2 = __float_as_uint(round_tf32(s[j][1])), p3 = __float_as_uint(round_tf32(s[j][3]));
+        // keys 8j+2t and 8j+2t+1; output column c of tile dn is d = 4c + dn, so lane column g reads d = 4g .. 4g+3
+        const float4 va = *reinterpret_cast<const float4*>(Vs + (8 * j + 2 * t) * WA_STRIDE + 4 * g);
+        const float4 vb = *reinterpret_cast<const float4*>(Vs + (8 * j + 2 * t + 1) * WA_STRIDE + 4 * g);
+        mma_tf32_16x8x8(o[0], p0, p1, p2, p3, __float_as_uint(va.x), __float_as_uint(vb.x));
+        mma_tf32_16x8x8(o[1], p0, p1, p2, p3, __float_as_uint(va.y), __float_as_uint(vb.y));
+        mma_tf32_16x8x8(o[2], p0, p1, p2, p3, __float_as_uint(va.z), __float_as_uint(vb.z));
+        mma_tf32_16x8x8(o[3], p0, p1, p2, p3, __float_as_uint(va.w), __float_as_uint(vb.w));
       }
+      // accumulator column 2t / 2t+1 of tile dn is d = 8t + dn / 8t + 4 + dn: the lane owns d = 8t .. 8t+7 of its rows
       const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+      float4* out4 = reinterpret_cast<float4*>(d.out + head * HD) + 2 * t;
       if (r0 < WT) {
-        float* dst = d.out + (long long)stok[r0] * d.C + head * HD + 2 * t;
-#pragma unroll
-        for (int dn = 0; dn < 4; ++dn)
-          *reinterpret_cast<float2*>(dst + 8 * dn) =
-              make_float2(maybe_round(o[dn][0] * inv0, d.round_tf32), maybe_round(o[dn][1] * inv0, d.round_tf32));
+        float4* dst = out4 + (stok[r0] / C3q) * Cq;
+        dst[0] = make_float4(maybe_round(o[0][0] * inv0, d.round_tf32), maybe_round(o[1][0] * inv0, d.round_tf32),
+                             maybe_round(o[2][0] * inv0, d.round_tf32), maybe_round(o[3][0] * inv0, d.round_tf32));
+        dst[1] = make_float4(maybe_round(o[0][1] * inv0, d.round_tf32), maybe_round(o[1][1] * inv0, d.round_tf32),
+                             maybe_round(o[2][1] * inv0, d.round_tf32), maybe_round(o[3][1] * inv0, d.round_tf32));
       }
       if (r1 < WT) {
-        float* dst = d.out + (long long)stok[r1] * d.C + head * HD + 2 * t;
-#pragma unroll
-        for (int dn = 0; dn < 4; ++dn)
-          *reinterpret_cast<float2*>(dst + 8 * dn) =
-              make_float2(maybe_round(o[dn][2] * inv1, d.round_tf32), maybe_round(o[dn][3] * inv1, d.round_tf32));
+        float4* dst = out4 + (stok[r1] / C3q) * Cq;
+        dst[0] = make_float4(maybe_round(o[0][2] * inv1, d.round_tf32), maybe_round(o[1][2] * inv1, d.round_tf32),
+                             maybe_round(o[2][2] * inv1, d.round_tf32), maybe_round(o[3][2] * inv1, d.round_tf32));
+        dst[1] = make_float4(maybe_round(o[0][3] * inv1, d.round_tf32), maybe_round(o[1][3] * inv1, d.round_tf32),
+                             maybe_round(o[2][3] * inv1, d.round_tf32), maybe_round(o[3][3] * inv1, d.round_tf32));
       }
     }
   }
@@ -656,16 +687,23 @@ int winattn_launch(const svx_winattn_desc& d, void* stream) {
   SVX_REQUIRE(d.H % WS == 0 && d.W % WS == 0 && d.C == d.heads * HD && d.shift >= 0 && d.shift < WS,
               "window_attention: needs 7x7 windows, head_dim 32 (H=%d W=%d C=%d heads=%d)", d.H, d.W, d.C, d.heads);
   const long long windows = (long long)d.N * (d.H / WS) * (d.W / WS);
-  long long per_head = (windows + WA_WARPS - 1) / WA_WARPS;
-  const long long cap = (3LL * kSmCount + d.heads - 1) / d.heads;   // ~3 resident CTAs per SM over all heads
+  SVX_REQUIRE(windows * WT * (3LL * d.C / 4) < 0xffffffffLL && d.C % 4 == 0 && al16(d.qkv) && al16(d.out),
+              "window_attention: tensor too large for 32-bit row offsets, or unaligned");
+  long long per_head = (windows + WA_ITEMS - 1) / WA_ITEMS;
+  const long long cap = (2LL * kSmCount + d.heads - 1) / d.heads;   // two resident CTAs per SM over all heads
   if (per_head > cap) per_head = cap;
   if (per_head < 1) per_head = 1;
   static bool configured = false;
   if (!configured) {
-    SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
+    SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
+    SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
     configured = true;
   }
-  winattn_kernel<<<(int)(per_head * d.heads), WA_WARPS * 32, WA_SMEM, (cudaStream_t)stream>>>(d, (int)per_head);
+  const int grid = (int)(per_head * d.heads);
+  if (d.shift > 0)
+    winattn_kernel<true><<<grid, WA_ITEMS * 64, WA_SMEM, (cudaStream_t)stream>>>(d, (int)per_head);
+  else
+    winattn_kernel<false><<<grid, WA_ITEMS * 64, WA_SMEM, (cudaStream_t)stream>>>(d, (int)per_head);
   SVX_LAUNCH_OK("winattn_kernel");
   return 0;
 }

@@ -11,7 +11,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, A_FLAT, A_GATHER, A_PLAIN, A_SLAB3, EPI_DEC_TAIL, EPI_STD,
+from ._lib import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, A_FLAT, A_GATHER, A_PLAIN, A_SLAB3, EPI_DEC_TAIL, EPI_POOL8, EPI_STD,
                    POOL_AVG, POOL_MAX)
 
 BLOCK_NS = (16, 32, 64, 96, 128, 192, 256)
@@ -327,10 +327,13 @@ class Plan:
         self.hold(pack.bias)
 
     def linear(self, x, pack, out, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True,
-               out_scale=1.0, round_out=False, name=None):
-        """x: Act read as a [pixels, C] matrix (plain TMA operand); out: Act with C == pack.N."""
+               out_scale=1.0, round_out=False, name=None, pool8=False):
+        """x: Act read as a [pixels, C] matrix (plain TMA operand); out: Act with C == pack.N.
+        pool8: the pack's N columns are 8 groups of N/8 channels (the conv positions under one MaxPool3d(2) window);
+        the epilogue stores act(max over groups + bias) into out (C == pack.N / 8)."""
         oD, oH, oW = out.inner
-        assert x.C == pack.K and out.C >= pack.N and x.pixels == out.N * oD * oH * oW, (x.C, pack.K, out.C, pack.N)
+        assert x.C == pack.K and x.pixels == out.N * oD * oH * oW, (x.C, pack.K, out.C, pack.N)
+        assert (out.C * 8 == pack.N) if pool8 else (out.C >= pack.N), (out.C, pack.N)
         assert x.c0 % 4 == 0 and x.Cs % 4 == 0 and not any(x.pad), "plain operands are dense matrices"
         d = _lib.GemmDesc()
         d.M = x.pixels
@@ -339,6 +342,8 @@ class Plan:
         d.lda = x.Cs
         d.out_D, d.out_H, d.out_W = oD, oH, oW
         self._fill_epilogue(d, pack, out, None, act, act_param, residual, res_after_act, out_scale, round_out)
+        if pool8:
+            d.epi_mode = EPI_POOL8
         self._add("gemm", d, name or "linear", 2.0 * d.M * pack.N * pack.K)
         return out
 

@@ -361,15 +361,23 @@ def lower_refiner(plan, ref, vol, B):
     """vol: [B, 32768] fp32 tensor (planar 32^3).  Returns refined [B, 32768]."""
     dev = _dev(plan)
     slope = float(ref.cfg.NETWORK.LEAKY_VALUE)
-    # layer1: Conv3d(1,32,k4,p2) -> 33^3, MaxPool3d(2) floors to 16^3: only conv outputs 0..31 are ever used
-    cols = plan.im2col(vol, (32768, 0, 1024, 32, 1), B, 1, (32, 32, 32), (4, 4, 4), 1, (2, 2, 2), (32, 32, 32), 64,
+    # layer1: Conv3d(1,32,k4,p2) -> 33^3, BN, LeakyReLU, MaxPool3d(2) (floors to 16^3: conv outputs 0..31 are used).
+    # One GEMM row per POOLED voxel: its 2x2x2 conv positions share one 5^3 input window (im2col, K = 125), the
+    # weights are the 4^3 kernel placed at the eight offsets inside that window (N = 8 x 32), and the epilogue takes
+    # the max over the eight column groups before bias / LeakyReLU (both commute with max).
+    cols = plan.im2col(vol, (32768, 0, 1024, 32, 1), B, 1, (32, 32, 32), (5, 5, 5), 2, (2, 2, 2), (16, 16, 16), 128,
                        name="refiner.layer1.im2col")
     c1 = ref.layer1[0]
     w, b = E.fold_bn(c1.weight, c1.bias, ref.layer1[1])
-    f32 = plan.new_act(B, 32, 32, 32, 32)
-    plan.linear(cols, E.pack_matrix(w.reshape(32, 64), b, dev), f32, act=ACT_LEAKY, act_param=slope, name="refiner.layer1")
+    w8 = torch.zeros(8, 32, 5, 5, 5, device=w.device)
+    for a_ in (0, 1):
+        for b_ in (0, 1):
+            for c_ in (0, 1):
+                w8[a_ * 4 + b_ * 2 + c_, :, a_:a_ + 4, b_:b_ + 4, c_:c_ + 4] = w[:, 0]
     l16 = plan.new_act(B, 16, 16, 16, 32)
-    plan.pool(f32, l16, (2, 2, 2), (2, 2, 2), (0, 0, 0), POOL_MAX, round_out=True, name="refiner.layer1.pool")
+    w8p = torch.nn.functional.pad(w8.reshape(256, 125), (0, 3))   # K = 125 padded to the im2col row length
+    plan.linear(cols, E.pack_matrix(w8p, b, dev, block_n=256), l16, act=ACT_LEAKY, act_param=slope,
+                round_out=True, pool8=True, name="refiner.layer1+pool")
     x, skips = l16, [l16]
     for li, (layer, cout) in enumerate(((ref.layer2, 64), (ref.layer3, 128))):
         full = plan.new_act(B, x.D, x.H, x.W, cout)   # conv outputs 0..D-1 of the (D+1)^3 the reference computes

@@ -164,6 +164,21 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
         for (int j = 0; j < 16; ++j) d.out[off + j] = rnd(x[j], d.round_tf32);
         continue;
       }
+      if (d.epi_mode == SVX_EPI_POOL8) {
+        const int nc = d.N / 8;
+        for (int c = 0; c < nc; ++c) {
+          float best = -INFINITY;
+          for (int gq = 0; gq < 8; ++gq) {
+            float acc = 0.f;
+            const float* w = d.W + (long long)(gq * nc + c) * d.Kpad;
+            for (int k = 0; k < d.K; ++k) acc += arow[k] * tf32_trunc(w[k]);
+            best = std::max(best, acc);
+          }
+          float v = act_fn(best + (d.bias ? d.bias[c] : 0.f), d.act, d.act_param) * d.out_scale;
+          d.out[off + c] = rnd(v, d.round_tf32);
+        }
+        continue;
+      }
       for (int j = 0; j < d.N; ++j) {
         float acc = 0.f;
         const float* w = d.W + (long long)j * d.Kpad;

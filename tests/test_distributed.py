@@ -69,13 +69,13 @@ def test_gloo_world2_matches_single_process(hostsim, tmp_path):
     r1 = torch.load(os.path.join(tmp_path, "rank1.pt"))
     assert torch.equal(r0[0], r1[0]) and torch.equal(r0[1], r1[1]), "every rank must hold the same gathered result"
     # single-process evaluation of the same three objects
-    _use_hostsim()
     from oracle import fixtures as FX
     from oracle import modules as M
     from swinvox_b200 import _lib
     from swinvox_b200.models import _base
     import swinvox_b200.metrics as metrics
     saved = (_lib._lib, _base.require_device, metrics.require_device)
+    _use_hostsim()
     try:
         cfg = M.default_cfg(**CFG_OVER)
         rec = _build(cfg)
@@ -86,5 +86,4 @@ def test_gloo_world2_matches_single_process(hostsim, tmp_path):
         assert torch.allclose(r0[0], logits, rtol=0, atol=1e-6)
         assert torch.equal(r0[1], counts)
     finally:
-        _lib._lib = None
-        _base.require_device, metrics.require_device = saved[1], saved[2]
+        _lib._lib, _base.require_device, metrics.require_device = saved
