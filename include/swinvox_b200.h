@@ -107,7 +107,8 @@ typedef struct svx_gemm_desc {
   int64_t o2_base, o2_sn, o2_sd, o2_sh, o2_sw;
   int32_t cin_live;         /* slab mode: only the first cin_live of the 32 box channels carry non-zero weights
                                (0 = all); the kernel skips the contraction steps beyond them */
-  int32_t reserved0;
+  int32_t res_via_mma;      /* plain mode, pre-activation residual holding TF32-exact values: add it on the tensor cores.
+                               W then is [Npad, Kpad + block_n]: the extra columns of row n are one-hot at n % block_n */
 } svx_gemm_desc;
 
 /* Explicit im2col for tiny channel counts (ResNet stem 7x7 s2 on 3 channels, Swin patch-embed

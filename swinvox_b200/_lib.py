@@ -30,7 +30,7 @@ class GemmDesc(C.Structure):
         ("act", i32), ("act_param", f32), ("res_after_act", i32), ("out_scale", f32),
         ("round_tf32", i32), ("epi_mode", i32), ("epi_aux", ptr), ("epi_out2", ptr),
         ("o2_base", i64), ("o2_sn", i64), ("o2_sd", i64), ("o2_sh", i64), ("o2_sw", i64),
-        ("cin_live", i32), ("reserved0", i32),
+        ("cin_live", i32), ("res_via_mma", i32),
     ]
 
 

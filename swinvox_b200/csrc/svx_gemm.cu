@@ -61,6 +61,7 @@ struct GemmParams {
   long long o2_base, o2_sn, o2_sd, o2_sh, o2_sw;
   int vec_ok;
   int epi_tma;              // plain row-major output: epilogue stores through TMA (map_c)
+  int nk_a;                 // k-chunks read from map_a; the remaining nk - nk_a come from the residual (map_r)
   long long ldc;            // epi_tma: row pitch of out / residual (elements); out and residual already include o_base
   int flat_off[kMaxTaps];  // flat mode: row offset of each tap
 };
@@ -188,7 +189,8 @@ __device__ __forceinline__ void store_slab(const GemmParams& p, const float* sta
 template <int BN>
 __global__ void __launch_bounds__(kThreads, Cfg<BN>::kCtasPerSm)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ GemmParams p) {
+                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
+                 const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
   constexpr int S = C::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -217,6 +219,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (a_mode != SVX_A_GATHER) tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (p.epi_tma) tma_prefetch_desc(&map_c);
+    if (p.nk_a < p.nk) tma_prefetch_desc(&map_r);
   }
   if (warp == 5) {
     if (lane == 0) {
@@ -253,7 +256,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t b_dst = a_dst + A_STAGE_BYTES;
           if (a_mode == SVX_A_PLAIN) {
             mbar_arrive_expect_tx(full_bar(s), A_STAGE_BYTES + C::kBBytes);
-            tma_load_2d(a_dst, &map_a, full_bar(s), kc * BK, m0);
+            if (kc < p.nk_a) tma_load_2d(a_dst, &map_a, full_bar(s), kc * BK, m0);
+            else tma_load_2d(a_dst, &map_r, full_bar(s), n0 + (kc - p.nk_a) * BK, m0);   // residual x identity
           } else if (a_mode == SVX_A_FLAT) {
             mbar_arrive_expect_tx(full_bar(s), A_STAGE_BYTES + C::kBBytes);
             const int tap = kc / p.chunks_per_tap;
@@ -400,16 +404,24 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int sw = (lane >> 1) & 3;                                        // 64B swizzle phase of this row
         const bool pool8 = p.epi_mode == SVX_EPI_POOL8;
         const int ncols = pool8 ? (p.N >> 3) : BN;          // output columns this tile produces
-        // The residual does not depend on the accumulator: the first block's residual is requested before waiting
-        // for the MMAs of this tile, and each block requests the next block's while it works (HBM latency hidden).
-        float4 rv_next[4];
-        auto load_res = [&](int jbn) {
+        // The residual does not depend on the accumulator: the residual of the first kAhead blocks is requested before
+        // waiting for the MMAs of this tile, and each block requests the one kAhead blocks later while it works, so
+        // several HBM round trips per warp are in flight (a shift-register of float4 quads keeps the indices static).
+        constexpr int kAhead = 1;   // deeper prefetch measured slower: the row-per-lane loads congest the L1 pipeline
+        float4 rq[kAhead][4];
+        auto load_res = [&](int jbn, float4 (&dst)[4]) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            rv_next[c] = (row_ok && jbn + 4 * c < p.N) ? *reinterpret_cast<const float4*>(res_row + jbn + 4 * c)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            dst[c] = (row_ok && jbn + 4 * c < p.N) ? *reinterpret_cast<const float4*>(res_row + jbn + 4 * c)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        if (has_res && n0 + part * SLAB < p.N) load_res(n0 + part * SLAB);
+        if (has_res) {
+#pragma unroll
+          for (int a = 0; a < kAhead; ++a) {
+            const int c0a = (part + a * nparts) * SLAB;
+            if (c0a < ncols && n0 + c0a < p.N) load_res(n0 + c0a, rq[a]);
+          }
+        }
         mbar_wait(tmem_full_bar(as), (it >> 1) & 1u);
         tc_fence_after();
 #pragma unroll 1
@@ -433,9 +445,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           float4 rv[4];
           if (has_res) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) rv[c] = rv_next[c];
-            const int c0n = c0 + nparts * SLAB;
-            if (c0n < ncols && n0 + c0n < p.N) load_res(n0 + c0n);
+            for (int c = 0; c < 4; ++c) rv[c] = rq[0][c];
+#pragma unroll
+            for (int a = 0; a + 1 < kAhead; ++a)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) rq[a][c] = rq[a + 1][c];
+            const int c0n = c0 + kAhead * nparts * SLAB;
+            if (c0n < ncols && n0 + c0n < p.N) load_res(n0 + c0n, rq[kAhead - 1]);
           }
           float4 bv[4];
 #pragma unroll
@@ -913,15 +929,15 @@ int sm_count() {
 }
 
 template <int BN>
-int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const GemmParams& p, int grid,
-              cudaStream_t st) {
+int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr,
+              const GemmParams& p, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     SVX_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg<BN>::kSmemBytes));
     configured = true;
   }
-  gemm_tf32_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ma, mb, mc, p);
+  gemm_tf32_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ma, mb, mc, mr, p);
   SVX_LAUNCH_OK("gemm_tf32_kernel");
   return 0;
 }
@@ -929,7 +945,7 @@ int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& m
 }  // namespace
 
 struct GemmPrepared {
-  CUtensorMap map_a, map_b, map_c;
+  CUtensorMap map_a, map_b, map_c, map_r;
   GemmParams p;
   int bn, grid;
   bool slab = false;   // SVX_A_SLAB3: handled by conv3_slab_kernel
@@ -952,6 +968,7 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   memset(&p, 0, sizeof(p));
   memset(&g->map_a, 0, sizeof(g->map_a));
   memset(&g->map_c, 0, sizeof(g->map_c));
+  memset(&g->map_r, 0, sizeof(g->map_r));
   p.chunks_per_tap = 1;
   if (d.a_mode == SVX_A_PLAIN) {
     if (d.lda % 4 != 0 || d.lda < d.K) {
@@ -1003,7 +1020,8 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     delete g;
     return fail("gemm: unknown a_mode %d", d.a_mode);
   }
-  if (encode_map(&g->map_b, d.W, (uint64_t)d.Npad, (uint64_t)d.Kpad, (uint64_t)d.Kpad, (uint32_t)d.block_n)) {
+  const int w_cols = d.Kpad + (d.res_via_mma ? d.block_n : 0);   // identity columns appended by the host
+  if (encode_map(&g->map_b, d.W, (uint64_t)d.Npad, (uint64_t)w_cols, (uint64_t)w_cols, (uint32_t)d.block_n)) {
     delete g;
     return 1;
   }
@@ -1012,7 +1030,7 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     delete g;
     return fail("gemm: decoder tail epilogue needs block_n=16, N=16, aux weights and a coarse output");
   }
-  p.M = d.M; p.N = d.N; p.K = d.K; p.Npad = d.Npad; p.nk = d.Kpad / BK; p.tiles_n = d.Npad / d.block_n; p.a_mode = d.a_mode;
+  p.M = d.M; p.N = d.N; p.K = d.K; p.Npad = d.Npad; p.nk = d.Kpad / BK; p.nk_a = p.nk; p.tiles_n = d.Npad / d.block_n; p.a_mode = d.a_mode;
   p.A = d.A;
   p.in_D = d.in_D; p.in_H = d.in_H; p.in_W = d.in_W; p.in_Cs = d.in_Cs; p.in_c0 = d.in_c0; p.Cin = d.Cin;
   p.out_D = d.out_D; p.out_H = d.out_H; p.out_W = d.out_W;
@@ -1047,6 +1065,17 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
       p.out = d.out + d.o_base;
       if (d.residual) p.residual = d.residual + d.o_base;
       if (encode_map(&g->map_c, p.out, (uint64_t)d.M, (uint64_t)n_out, (uint64_t)d.o_sw, 32, 16)) { delete g; return 1; }
+    }
+    if (d.res_via_mma) {
+      // act(A W^T + b + R) with R added by the tensor cores: the k loop runs block_n / 32 extra chunks whose A
+      // operand is the residual tile (TMA, coalesced) and whose B operand is an identity block.  Exact when R holds
+      // TF32-representable values (the caller's contract).
+      const bool ok = plain && d.a_mode == SVX_A_PLAIN && d.residual && !d.res_after_act && d.N % d.block_n == 0 &&
+                      d.block_n % BK == 0;
+      if (!ok) { delete g; return fail("gemm: res_via_mma needs a plain operand, a plain output, a pre-activation residual and N %% block_n == 0"); }
+      if (encode_map(&g->map_r, p.residual, (uint64_t)d.M, (uint64_t)d.N, (uint64_t)d.o_sw, BM)) { delete g; return 1; }
+      p.nk = p.nk_a + d.block_n / BK;
+      p.residual = nullptr;   // nothing left for the epilogue to add
     }
     if (pool8 && !(plain && d.N == d.block_n && d.N % 128 == 0 && !d.residual)) {
       delete g;
@@ -1093,13 +1122,13 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void* stream) {
     return 0;
   }
   switch (g->bn) {
-    case 16: rc = launch_bn<16>(g->map_a, g->map_b, g->map_c, g->p, g->grid, st); break;
-    case 32: rc = launch_bn<32>(g->map_a, g->map_b, g->map_c, g->p, g->grid, st); break;
-    case 64: rc = launch_bn<64>(g->map_a, g->map_b, g->map_c, g->p, g->grid, st); break;
-    case 96: rc = launch_bn<96>(g->map_a, g->map_b, g->map_c, g->p, g->grid, st); break;
-    case 128: rc = launch_bn<128>(g->map_a, g->map_b, g->map_c, g->p, g->grid, st); break;
-    case 192: rc = launch_bn<192>(g->map_a, g->map_b, g->map_c, g->p, g->grid, st); break;
-    default: rc = launch_bn<256>(g->map_a, g->map_b, g->map_c, g->p, g->grid, st); break;
+    case 16: rc = launch_bn<16>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st); break;
+    case 32: rc = launch_bn<32>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st); break;
+    case 64: rc = launch_bn<64>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st); break;
+    case 96: rc = launch_bn<96>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st); break;
+    case 128: rc = launch_bn<128>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st); break;
+    case 192: rc = launch_bn<192>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st); break;
+    default: rc = launch_bn<256>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st); break;
   }
   if (!prepared) delete g;
   return rc;

@@ -305,9 +305,20 @@ class Plan:
         t = torch.tensor([[a, b, c, 0] for a, b, c in taps], dtype=torch.int32, device=self.device)
         return self.hold(t)
 
-    def _fill_epilogue(self, d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out):
+    def _fill_epilogue(self, d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out,
+                       res_via_mma=False):
         pack.finalize(rows=d.M, gather=(d.a_mode == A_GATHER))
         d.W = pack.W.data_ptr()
+        if res_via_mma:
+            # the residual is added by the tensor cores: block_n identity columns appended to every weight row
+            assert residual is not None and not res_after_act and pack.N % pack.block_n == 0
+            if getattr(pack, "W_ext", None) is None:
+                eye = torch.zeros(pack.Npad, pack.block_n, dtype=torch.float32, device=pack.W.device)
+                idx = torch.arange(pack.Npad, device=pack.W.device)
+                eye[idx, idx % pack.block_n] = 1.0
+                pack.W_ext = torch.cat([pack.W, eye], dim=1).contiguous()
+            d.W = self.hold(pack.W_ext).data_ptr()
+            d.res_via_mma = 1
         d.bias = pack.bias.data_ptr()
         d.N, d.K, d.Kpad, d.Npad, d.block_n = pack.N, pack.K, pack.Kpad, pack.Npad, pack.block_n
         d.out = self.hold(out).buf.data_ptr()
@@ -327,8 +338,9 @@ class Plan:
         self.hold(pack.bias)
 
     def linear(self, x, pack, out, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True,
-               out_scale=1.0, round_out=False, name=None, pool8=False):
+               out_scale=1.0, round_out=False, name=None, pool8=False, res_via_mma=False):
         """x: Act read as a [pixels, C] matrix (plain TMA operand); out: Act with C == pack.N.
+        res_via_mma: the (pre-activation) residual holds TF32-exact values and is added by the tensor cores.
         pool8: the pack's N columns are 8 groups of N/8 channels (the conv positions under one MaxPool3d(2) window);
         the epilogue stores act(max over groups + bias) into out (C == pack.N / 8)."""
         oD, oH, oW = out.inner
@@ -341,7 +353,8 @@ class Plan:
         d.A = self.hold(x).buf.data_ptr() + 4 * x.c0
         d.lda = x.Cs
         d.out_D, d.out_H, d.out_W = oD, oH, oW
-        self._fill_epilogue(d, pack, out, None, act, act_param, residual, res_after_act, out_scale, round_out)
+        self._fill_epilogue(d, pack, out, None, act, act_param, residual, res_after_act, out_scale, round_out,
+                            res_via_mma=res_via_mma)
         if pool8:
             d.epi_mode = EPI_POOL8
         self._add("gemm", d, name or "linear", 2.0 * d.M * pack.N * pack.K)

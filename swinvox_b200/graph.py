@@ -71,15 +71,17 @@ def _bottleneck(plan, blk, x, name):
     if blk.downsample is not None:
         idn = plan.new_act(x.N, 1, H2, H2, cout)
         pk = E.pack_conv(blk.downsample[0].weight, None, blk.downsample[1], dev)
+        # the identity branch is stored TF32-rounded so that conv3 can add it on the tensor cores exactly
         if s == 1:
-            plan.linear(x, pk, idn, name=name + ".downsample")
+            plan.linear(x, pk, idn, round_out=True, name=name + ".downsample")
         else:
-            plan.conv(x, pk, [(0, 0, 0)], idn, stride=(1, s, s), name=name + ".downsample")
+            plan.conv(x, pk, [(0, 0, 0)], idn, stride=(1, s, s), round_out=True, name=name + ".downsample")
     else:
         idn = x
     out = plan.new_act(x.N, 1, H2, H2, cout)
-    plan.linear(t2, E.pack_conv(blk.conv3.weight, None, blk.bn3, dev), out, act=ACT_RELU, residual=idn,
-                res_after_act=False, round_out=True, name=name + ".conv3")
+    pk3 = E.pack_conv(blk.conv3.weight, None, blk.bn3, dev)
+    plan.linear(t2, pk3, out, act=ACT_RELU, residual=idn, res_after_act=False, round_out=True,
+                res_via_mma=(cout % 256 == 0), name=name + ".conv3")
     return out
 
 

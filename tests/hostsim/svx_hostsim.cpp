@@ -111,6 +111,7 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
     return 0;
   }
   const long long rows_per_n = (long long)d.out_D * d.out_H * d.out_W;
+  const long long w_pitch = d.Kpad + (d.res_via_mma ? d.block_n : 0);   // identity columns appended for the device
 #pragma omp parallel
   {
     std::vector<float> arow(d.K);
@@ -152,7 +153,7 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
         float g = d.epi_aux[8];
         for (int j = 0; j < 8; ++j) {
           float acc = 0.f;
-          const float* w = d.W + (long long)j * d.Kpad;
+          const float* w = d.W + (long long)j * w_pitch;
           for (int k = 0; k < d.K; ++k) acc += arow[k] * tf32_trunc(w[k]);
           acc += d.bias ? d.bias[j] : 0.f;
           x[j] = acc > 0.f ? acc : 0.f;
@@ -170,7 +171,7 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
           float best = -INFINITY;
           for (int gq = 0; gq < 8; ++gq) {
             float acc = 0.f;
-            const float* w = d.W + (long long)(gq * nc + c) * d.Kpad;
+            const float* w = d.W + (long long)(gq * nc + c) * w_pitch;
             for (int k = 0; k < d.K; ++k) acc += arow[k] * tf32_trunc(w[k]);
             best = std::max(best, acc);
           }
@@ -181,7 +182,7 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
       }
       for (int j = 0; j < d.N; ++j) {
         float acc = 0.f;
-        const float* w = d.W + (long long)j * d.Kpad;
+        const float* w = d.W + (long long)j * w_pitch;
         for (int k = 0; k < d.K; ++k) acc += arow[k] * tf32_trunc(w[k]);
         float v = acc + (d.bias ? d.bias[j] : 0.f);
         const float res = d.residual ? d.residual[off + j] : 0.f;

@@ -97,6 +97,25 @@ def test_gemm_epilogue(dev, act, res_after):
     assert rel_err(out.view().reshape(M, N), ref) < 6e-4  # result is rounded to TF32 (2^-11)
 
 
+@pytest.mark.parametrize("M,K,N,bn", [(333, 160, 256, 256), (1000, 64, 512, 128), (4096, 256, 1024, None)])
+def test_gemm_residual_on_tensor_cores(dev, M, K, N, bn):
+    """ResNet conv3-style epilogue relu(x W^T + b + r) with the TF32-exact residual added by the MMA itself
+    (identity columns appended to the weights, residual tile streamed by TMA as extra k-chunks)"""
+    DEV = dev
+    torch.manual_seed(M)
+    x = E.tf32_round(torch.randn(M, K))
+    w, b, r = torch.randn(N, K) / K ** 0.5, torch.randn(N), E.tf32_round(torch.randn(M, N))
+    p = E.Plan(DEV)
+    out = p.new_act(M, 1, 1, 1, N)
+    res = E.Act(r.to(DEV), M, 1, 1, 1, N)
+    p.linear(E.Act(x.to(DEV), M, 1, 1, 1, K), E.pack_matrix(w, b, DEV, block_n=bn), out, act=E.ACT_RELU, residual=res,
+             res_after_act=False, res_via_mma=True)
+    p.run()
+    sync(DEV)
+    ref = F.relu(x.double() @ E.tf32_round(w).double().t() + b.double() + r.double())
+    assert rel_err(out.view().reshape(M, N), ref) < 1e-4
+
+
 @pytest.mark.parametrize("cin,cout,hw,k,s,p_", [(64, 64, 14, 3, 1, 1), (32, 96, 15, 3, 2, 1), (256, 128, 7, 1, 1, 0),
                                                  (128, 256, 14, 1, 2, 0), (8, 16, 9, 5, 2, 2), (512, 256, 7, 3, 1, 1)])
 def test_conv2d_gather(dev, cin, cout, hw, k, s, p_):
