@@ -623,20 +623,30 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // in TMEM so the epilogue of one depth overlaps the MMAs of the next.
 // =====================================================================================================
 constexpr int S3_ROWS = 200;                       // slab rows: 128 + 2*Wp <= 200  (Wp <= 36)
-constexpr int S3_SLAB_BYTES = S3_ROWS * 128;       // 25 x 1024
-constexpr int S3_NSLAB = 5;
 constexpr int S3_N = 48;                           // MMA N: 3 kw groups x 16 output channels
-constexpr int S3_TAP_BYTES = S3_N * 128;           // one (kd,kh) weight block: 6 x 1024
-constexpr int S3_W_BYTES = 9 * S3_TAP_BYTES;
 constexpr int S3_NACC = 8, S3_ACC_STRIDE = 64;     // TMEM: 8 accumulators of 48 (stride 64) columns
 constexpr int S3_STEP = BM - 2;                    // valid rows per tile
-constexpr int S3_THREADS = 320;                   // warps 0-3 / 6-9: two epilogue sets, 4: TMA, 5: MMA
+constexpr int S3_THREADS = 320;                    // warps 0-3 / 6-9: two epilogue sets, 4: TMA, 5: MMA
 constexpr int S3_XCHG_BYTES = 2 * BM * 128;        // per epilogue set: 128 rows x (D1[16] | D2[16]) staged for the row shift
-constexpr int S3_SMEM = 1024 + S3_W_BYTES + S3_NSLAB * S3_SLAB_BYTES + S3_XCHG_BYTES + 256;
 
+// ROWB = bytes per staged row: 128 (32-channel box, 128B swizzle) or 64 (layers with <= 16 live channels: 16-channel
+// box, 64B swizzle -- half the L2 traffic and shared memory, which buys a twice deeper slab ring)
+template <int ROWB>
+struct S3Cfg {
+  static constexpr int kSlabBytes = S3_ROWS * ROWB;
+  static constexpr int kNSlab = ROWB == 128 ? 5 : 10;
+  static constexpr int kTapBytes = S3_N * ROWB;        // one (kd,kh) weight block
+  static constexpr int kWBytes = 9 * kTapBytes;
+  static constexpr int kSmem = 1024 + kWBytes + kNSlab * kSlabBytes + S3_XCHG_BYTES + 512;
+};
+
+template <int ROWB>
 __global__ void __launch_bounds__(S3_THREADS, 1)
 conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ GemmParams p) {
+  constexpr int S3_SLAB_BYTES = S3Cfg<ROWB>::kSlabBytes, S3_NSLAB = S3Cfg<ROWB>::kNSlab;
+  constexpr int S3_TAP_BYTES = S3Cfg<ROWB>::kTapBytes, S3_W_BYTES = S3Cfg<ROWB>::kWBytes;
+  constexpr int kBoxCh = ROWB / 4;   // channels per staged row
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -682,7 +692,7 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     // ---- TMA producer: weights once, then one slab per (unit, plane) ---------------------------------
     if (elect_one()) {
       mbar_arrive_expect_tx(w_full, S3_W_BYTES);
-      for (int t = 0; t < 9; ++t) tma_load_2d(w_smem + t * S3_TAP_BYTES, &map_w, w_full, t * BK, 0);
+      for (int t = 0; t < 9; ++t) tma_load_2d(w_smem + t * S3_TAP_BYTES, &map_w, w_full, t * BK, 0);   // first kBoxCh of the 32
       uint32_t g = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int n = unit / ncol, col = unit - n * ncol;
@@ -718,8 +728,9 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             const uint32_t slab = slab_smem + ((sbase + d + kd) % S3_NSLAB) * S3_SLAB_BYTES;
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
-              const uint64_t da = umma_desc_sw128(slab + kh * Wp * 128);
-              const uint64_t db = umma_desc_sw128(w_smem + (kd * 3 + kh) * S3_TAP_BYTES);
+              const uint64_t da = ROWB == 128 ? umma_desc_sw128(slab + kh * Wp * ROWB) : umma_desc_sw64(slab + kh * Wp * ROWB);
+              const uint64_t db = ROWB == 128 ? umma_desc_sw128(w_smem + (kd * 3 + kh) * S3_TAP_BYTES)
+                                              : umma_desc_sw64(w_smem + (kd * 3 + kh) * S3_TAP_BYTES);
               for (int k = 0; k < ksteps; ++k)
                 umma_tf32(acc, da + 2u * k, db + 2u * k, idesc, (kd | kh | k) != 0 ? 1u : 0u);
             }
@@ -949,6 +960,7 @@ struct GemmPrepared {
   GemmParams p;
   int bn, grid;
   bool slab = false;   // SVX_A_SLAB3: handled by conv3_slab_kernel
+  bool slab_narrow = false;   // 16-channel (64-byte) rows
 };
 
 int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
@@ -1015,13 +1027,18 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     }
     p.cin_live = live;
     g->slab = true;
-    if (encode_map(&g->map_a, d.A, (uint64_t)d.lda, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs, S3_ROWS)) { delete g; return 1; }
+    g->slab_narrow = live <= 16 && !getenv("SVX_SLAB_WIDE");
+    if (encode_map(&g->map_a, d.A, (uint64_t)d.lda, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs, S3_ROWS, g->slab_narrow ? 16 : BK)) {
+      delete g;
+      return 1;
+    }
   } else {
     delete g;
     return fail("gemm: unknown a_mode %d", d.a_mode);
   }
   const int w_cols = d.Kpad + (d.res_via_mma ? d.block_n : 0);   // identity columns appended by the host
-  if (encode_map(&g->map_b, d.W, (uint64_t)d.Npad, (uint64_t)w_cols, (uint64_t)w_cols, (uint32_t)d.block_n)) {
+  if (encode_map(&g->map_b, d.W, (uint64_t)d.Npad, (uint64_t)w_cols, (uint64_t)w_cols, (uint32_t)d.block_n,
+                 g->slab_narrow ? 16 : BK)) {
     delete g;
     return 1;
   }
@@ -1112,10 +1129,14 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void* stream) {
   if (g->slab) {
     static bool configured = false;
     if (!configured) {
-      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_SMEM));
+      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<128>::kSmem));
+      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<64>::kSmem));
       configured = true;
     }
-    conv3_slab_kernel<<<g->grid, S3_THREADS, S3_SMEM, st>>>(g->map_a, g->map_b, g->p);
+    if (g->slab_narrow)
+      conv3_slab_kernel<64><<<g->grid, S3_THREADS, S3Cfg<64>::kSmem, st>>>(g->map_a, g->map_b, g->p);
+    else
+      conv3_slab_kernel<128><<<g->grid, S3_THREADS, S3Cfg<128>::kSmem, st>>>(g->map_a, g->map_b, g->p);
     cudaError_t e = cudaGetLastError();
     if (!prepared) delete g;
     if (e != cudaSuccess) return fail("launch of conv3_slab_kernel failed: %s", cudaGetErrorString(e));

@@ -32,19 +32,32 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
                : "memory");
 }
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+#ifndef SVX_MBAR_HINT_NS
+#define SVX_MBAR_HINT_NS 20000   // suspend-time hint (ns); 0 = plain try_wait spin (measured no faster)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   long long t0 = 0;
   for (uint32_t it = 0;; ++it) {
+#if SVX_MBAR_HINT_NS > 0
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t}\n"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(20000u)   // suspend-time hint (ns): sleep in hardware instead of spinning
+        : "r"(bar), "r"(parity), "r"((uint32_t)SVX_MBAR_HINT_NS)
         : "memory");
+#else
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+#endif
     if (done) break;
-    if ((it & 255u) == 255u) {   // ~2 s of SM clocks without progress: a protocol bug, not a long main loop
+    if ((it & 1023u) == 1023u) {   // ~2 s of SM clocks without progress: a protocol bug, not a long main loop
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000LL) __trap();
@@ -153,6 +166,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1024 >> 4) << 32;                // stride byte offset: next 8-row group
   d |= static_cast<uint64_t>(1) << 46;                        // descriptor version (sm_100)
   d |= static_cast<uint64_t>(2) << 61;                        // SWIZZLE_128B
+  return d;
+}
+// K-major, 64-byte-swizzled operand tile: rows of 64 B (16 fp32), 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);  // start address
+  d |= static_cast<uint64_t>(1) << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(512 >> 4) << 32;                 // stride byte offset: next 8-row group
+  d |= static_cast<uint64_t>(1) << 46;                        // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(4) << 61;                        // SWIZZLE_64B
   return d;
 }
 // kind::tf32 instruction descriptor: fp32 accumulate, TF32 A/B, both K-major, M=128, N=n
