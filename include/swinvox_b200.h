@@ -31,15 +31,24 @@ extern "C" {
 /* activation codes for svx_gemm_desc.act */
 enum { SVX_ACT_NONE = 0, SVX_ACT_RELU = 1, SVX_ACT_LEAKY = 2, SVX_ACT_GELU = 3 };
 /* A operand modes */
-enum { SVX_A_PLAIN = 0, SVX_A_GATHER = 1, SVX_A_FLAT = 2, SVX_A_SLAB3 = 3 };
+enum { SVX_A_PLAIN = 0, SVX_A_GATHER = 1, SVX_A_FLAT = 2, SVX_A_SLAB3 = 3, SVX_A_IM2COL = 4 };
 /* special epilogues */
 enum {
   SVX_EPI_STD = 0,
   SVX_EPI_DEC_TAIL = 1, /* decoder layer4+layer5+cat, decoder.py:80-89 */
-  SVX_EPI_POOL8 = 2     /* conv + BN + LeakyReLU + MaxPool3d(2) (refiner.py:21-26): the N columns are 8 groups (the 2x2x2
+  SVX_EPI_POOL8 = 2,    /* conv + BN + LeakyReLU + MaxPool3d(2) (refiner.py:21-26): the N columns are 8 groups (the 2x2x2
                            conv positions of one pooled voxel) of N/8 channels; out[r, c] = act(max_g acc[r, g*N/8 + c] +
                            bias[c]) -- valid because the activation is monotonic and the bias is shared by the group.
                            Plain row-major output [M, N/8] only (o_sw = row pitch). */
+  SVX_EPI_CONVT8 = 3    /* stride-2 ConvTranspose3d(k4, p1) (decoder.py:37-46, refiner.py:62-70) with all eight output-parity
+                           classes of one INPUT voxel in the N dimension: row r = input voxel (n,d,h,w), K = the 3x3x3
+                           input neighbourhood x Cin (structural zeros where a tap does not feed a class), column
+                           j = cls*cls_cout + c with cls = pd*4 + ph*2 + pw.  Column j is stored at
+                             out + o_base + n*o_sn + d*o_sd + h*o_sh + w*o_sw + pd*c_sd + ph*c_sh + pw*c_sw + c
+                           (o_s* = twice the output voxel strides, c_s* = the output voxel strides); `residual` uses the same
+                           mapping.  With epi_aux set (cls_cout == 8) every class also gets the decoder tail of
+                           SVX_EPI_DEC_TAIL: channels 0-7 = relu, channel 8 = layer5, which also goes to
+                           epi_out2 + o2_base + ... + pd*c2_sd + ph*c2_sh + pw*c2_sw. */
 };
 /* pooling modes */
 enum { SVX_POOL_MAX = 0, SVX_POOL_AVG = 1 };
@@ -58,6 +67,10 @@ enum { SVX_POOL_MAX = 0, SVX_POOL_AVG = 1 };
  *                         ow*stride_w + taps[tap].w, in_c0 + c]
  *                 of a channels-last tensor with pixel stride in_Cs, zero outside the tensor.
  *                 Cin, in_c0, in_Cs must be multiples of 4 (16-byte cp.async chunks).
+ *   SVX_A_IM2COL: the same implicit im2col as SVX_A_GATHER (same row / k / tap meaning, taps given in taps_host),
+ *                 but fetched by the TMA unit in im2col mode (cuTensorMapEncodeIm2col over the NDHWC tensor, one
+ *                 128-pixel x 32-channel box per (tap, channel chunk), borders zero-filled by the hardware).  Needs
+ *                 Cin % 32 == 0; tap offsets and the implied padding must fit the descriptor's [-16, 15] corner range.
  *   SVX_A_FLAT  : stride-1 convolution over a zero-PADDED channels-last tensor viewed as the matrix
  *                 [N*in_D*in_H*in_W, in_Cs] (in_* are the padded extents).  Row r is the flat padded position
  *                 of the window corner; tap t reads row r + (dd*in_H + dh)*in_W + dw (taps >= 0), streamed by
@@ -109,6 +122,10 @@ typedef struct svx_gemm_desc {
                                (0 = all); the kernel skips the contraction steps beyond them */
   int32_t res_via_mma;      /* plain mode, pre-activation residual holding TF32-exact values: add it on the tensor cores.
                                W then is [Npad, Kpad + block_n]: the extra columns of row n are one-hot at n % block_n */
+  int32_t cls_cout;         /* SVX_EPI_CONVT8: output channels per parity class (1, 2, 4, 8 or a multiple of 16) */
+  int32_t reserved0;
+  int64_t c_sd, c_sh, c_sw;     /* SVX_EPI_CONVT8: element offsets of the class bits in out / residual */
+  int64_t c2_sd, c2_sh, c2_sw;  /* ... and in epi_out2 */
 } svx_gemm_desc;
 
 /* Explicit im2col for tiny channel counts (ResNet stem 7x7 s2 on 3 channels, Swin patch-embed

@@ -10,8 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libswinvox_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU = 0, 1, 2, 3
-A_PLAIN, A_GATHER, A_FLAT, A_SLAB3 = 0, 1, 2, 3
-EPI_STD, EPI_DEC_TAIL, EPI_POOL8 = 0, 1, 2
+A_PLAIN, A_GATHER, A_FLAT, A_SLAB3, A_IM2COL = 0, 1, 2, 3, 4
+EPI_STD, EPI_DEC_TAIL, EPI_POOL8, EPI_CONVT8 = 0, 1, 2, 3
 POOL_MAX, POOL_AVG = 0, 1
 
 i32, i64, f32, ptr = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -31,6 +31,8 @@ class GemmDesc(C.Structure):
         ("round_tf32", i32), ("epi_mode", i32), ("epi_aux", ptr), ("epi_out2", ptr),
         ("o2_base", i64), ("o2_sn", i64), ("o2_sd", i64), ("o2_sh", i64), ("o2_sw", i64),
         ("cin_live", i32), ("res_via_mma", i32),
+        ("cls_cout", i32), ("reserved0", i32), ("c_sd", i64), ("c_sh", i64), ("c_sw", i64),
+        ("c2_sd", i64), ("c2_sh", i64), ("c2_sw", i64),
     ]
 
 

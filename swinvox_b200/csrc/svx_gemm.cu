@@ -63,7 +63,10 @@ struct GemmParams {
   int epi_tma;              // plain row-major output: epilogue stores through TMA (map_c)
   int nk_a;                 // k-chunks read from map_a; the remaining nk - nk_a come from the residual (map_r)
   long long ldc;            // epi_tma: row pitch of out / residual (elements); out and residual already include o_base
-  int flat_off[kMaxTaps];  // flat mode: row offset of each tap
+  int cls_cout;             // SVX_EPI_CONVT8: channels per output-parity class
+  long long c_sd, c_sh, c_sw, c2_sd, c2_sh, c2_sw;   // class-bit offsets in out / residual and in out2
+  int i2c_lo_d, i2c_lo_h, i2c_lo_w;   // im2col mode: base-pixel coordinate of output 0 on each axis (= smallest tap)
+  int flat_off[kMaxTaps];  // flat mode: row offset of each tap; im2col mode: tap offsets packed w | h << 8 | d << 16
 };
 
 template <int BN>
@@ -246,6 +249,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // instructions directly instead of wrapping each in a divergence loop) ----------------------------
     if (elect_one()) {
       uint32_t g = 0;
+      int i2c_w = 0, i2c_h = 0, i2c_d = 0, i2c_n = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
         for (int kc = 0; kc < nk; ++kc, ++g) {
@@ -263,6 +267,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int tap = kc / p.chunks_per_tap;
             const int cc = kc - tap * p.chunks_per_tap;
             tma_load_2d(a_dst, &map_a, full_bar(s), p.in_c0 + cc * BK, m0 + p.flat_off[tap]);
+          } else if (a_mode == SVX_A_IM2COL) {
+            mbar_arrive_expect_tx(full_bar(s), A_STAGE_BYTES + C::kBBytes);
+            if (kc == 0) {   // first output pixel of the tile -> base pixel of the hardware traversal
+              i2c_w = m0 % p.out_W;
+              int t = m0 / p.out_W;
+              i2c_h = t % p.out_H;
+              t /= p.out_H;
+              i2c_d = t % p.out_D;
+              i2c_n = t / p.out_D;
+              i2c_w = i2c_w * p.sw + p.i2c_lo_w; i2c_h = i2c_h * p.sh + p.i2c_lo_h; i2c_d = i2c_d * p.sd + p.i2c_lo_d;
+            }
+            const int tap = kc / p.chunks_per_tap;
+            const int cc = kc - tap * p.chunks_per_tap;
+            const int o = p.flat_off[tap];
+            tma_load_im2col_5d(a_dst, &map_a, full_bar(s), p.in_c0 + cc * BK, i2c_w, i2c_h, i2c_d, i2c_n,
+                               (uint16_t)(o & 255), (uint16_t)((o >> 8) & 255), (uint16_t)((o >> 16) & 255));
           } else {
             mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
           }
@@ -384,7 +404,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     long long* soff = reinterpret_cast<long long*>(aux_gen + ew * C::kWarpStage + kBlockBytes);
     constexpr int SLAB = kSlab;
     constexpr int CP = SLAB / 4;     // float4 chunks per staged row
-    const bool rowwise = (p.epi_mode == SVX_EPI_DEC_TAIL) || !p.vec_ok;
+    const bool convt = p.epi_mode == SVX_EPI_CONVT8;
+    const bool rowwise = (p.epi_mode == SVX_EPI_DEC_TAIL) || convt || !p.vec_ok;
     uint32_t it = 0, buf = 0;   // buf: which of this warp's two staging blocks the next TMA store uses
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
@@ -551,6 +572,54 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           float x[SLAB];
 #pragma unroll
           for (int q = 0; q < SLAB; ++q) x[q] = __uint_as_float(v[q]) + ((p.bias && jb + q < p.Npad) ? __ldg(p.bias + jb + q) : 0.f);
+          if (convt) {
+            // all eight output-parity classes of a stride-2 transposed convolution sit side by side in N
+            auto cls_off = [&](int cls) { return (cls >> 2) * p.c_sd + ((cls >> 1) & 1) * p.c_sh + (cls & 1) * p.c_sw; };
+            if (p.epi_aux) {
+              // decoder tail (decoder.py:80-89) per class: 8 channels per class, two classes (pw = 0, 1) per slab
+              const float b8 = __ldg(p.epi_aux + 8);
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                const int cls = (jb >> 3) + hf;
+                float gsum = b8;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  x[8 * hf + q] = fmaxf(x[8 * hf + q], 0.f);
+                  gsum = fmaf(__ldg(p.epi_aux + q), x[8 * hf + q], gsum);
+                }
+                float* dst = p.out + off + cls_off(cls);
+                const float* xs = x + 8 * hf;
+                if (p.round_tf32) {
+                  *reinterpret_cast<float4*>(dst) = make_float4(round_tf32(xs[0]), round_tf32(xs[1]), round_tf32(xs[2]), round_tf32(xs[3]));
+                  *reinterpret_cast<float4*>(dst + 4) = make_float4(round_tf32(xs[4]), round_tf32(xs[5]), round_tf32(xs[6]), round_tf32(xs[7]));
+                  *reinterpret_cast<float4*>(dst + 8) = make_float4(round_tf32(gsum), 0.f, 0.f, 0.f);
+                } else {
+                  *reinterpret_cast<float4*>(dst) = make_float4(xs[0], xs[1], xs[2], xs[3]);
+                  *reinterpret_cast<float4*>(dst + 4) = make_float4(xs[4], xs[5], xs[6], xs[7]);
+                  *reinterpret_cast<float4*>(dst + 8) = make_float4(gsum, 0.f, 0.f, 0.f);
+                }
+                p.out2[off2 + (cls >> 2) * p.c2_sd + ((cls >> 1) & 1) * p.c2_sh + (cls & 1) * p.c2_sw] = gsum;
+              }
+            } else {
+              const int cc = p.cls_cout;
+#pragma unroll
+              for (int q = 0; q < SLAB; ++q) {
+                const int j = jb + q;
+                if (j < p.N) {
+                  const int cls = j / cc;
+                  const long long o = off + cls_off(cls) + (j - cls * cc);
+                  const float rvq = p.residual ? p.residual[o] : 0.f;
+                  float t = x[q];
+                  if (!p.res_after_act) t += rvq;
+                  t = apply_act(t, p.act, p.act_param);
+                  if (p.res_after_act) t += rvq;
+                  t *= p.out_scale;
+                  p.out[o] = p.round_tf32 ? round_tf32(t) : t;
+                }
+              }
+            }
+            continue;
+          }
           if (p.epi_mode == SVX_EPI_DEC_TAIL) {
             // decoder.py:80-89: raw = cat(relu(bn(layer4)), layer5(.)) ; coarse = layer5(.)
             float gsum = __ldg(p.epi_aux + 8);  // layer5 bias (0 when TCONV_USE_BIAS is off)
@@ -928,6 +997,37 @@ int encode_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t cols,
   return 0;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+// im2col-mode map over the channels-last tensor [N, D, H, W, Cs]: boxes of 128 pixels x 32 channels, 128B swizzle.
+// lo / up: bounding-box corners of the base pixel per axis (d, h, w); str: convolution strides (d, h, w).
+int encode_im2col_map(CUtensorMap* map, const float* ptr, uint64_t N, uint64_t D, uint64_t H, uint64_t W, uint64_t Cs,
+                      const int lo[3], const int up[3], const int str[3]) {
+  static EncodeIm2colFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
+  }
+  if (!fn) return fail("cuTensorMapEncodeIm2col entry point not available");
+  cuuint64_t dims[5] = {Cs, W, H, D, N};
+  cuuint64_t strides[4] = {Cs * 4, W * Cs * 4, H * W * Cs * 4, D * H * W * Cs * 4};
+  int lower[3] = {lo[2], lo[1], lo[0]}, upper[3] = {up[2], up[1], up[0]};   // the driver takes (w, h, d)
+  cuuint32_t estr[5] = {1, (cuuint32_t)str[2], (cuuint32_t)str[1], (cuuint32_t)str[0], 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(ptr), dims, strides, lower, upper, BK, BM,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeIm2col failed with CUresult %d (lo %d,%d,%d up %d,%d,%d)", (int)r, lo[0], lo[1], lo[2],
+                up[0], up[1], up[2]);
+  return 0;
+}
+
 int sm_count() {
   static int n = 0;
   if (!n) {
@@ -1014,6 +1114,40 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     }
     p.chunks_per_tap = d.Cin / BK;
     if (encode_map(&g->map_a, d.A, (uint64_t)rows_total, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs, BM)) { delete g; return 1; }
+  } else if (d.a_mode == SVX_A_IM2COL) {
+    bool ok = d.Cin > 0 && d.Cin % BK == 0 && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.ntaps > 0 && d.ntaps <= kMaxTaps &&
+              d.taps_host && d.K == d.ntaps * d.Cin && d.Kpad == d.K && d.in_D > 0 && d.in_H > 0 && d.in_W > 0 &&
+              d.stride_d >= 1 && d.stride_h >= 1 && d.stride_w >= 1 && d.stride_d <= 8 && d.stride_h <= 8 && d.stride_w <= 8 &&
+              d.M % (d.out_D * d.out_H * d.out_W) == 0;
+    if (!ok) {
+      delete g;
+      return fail("gemm: bad im2col description (Cin=%d c0=%d Cs=%d ntaps=%d K=%d Kpad=%d)", d.Cin, d.in_c0, d.in_Cs,
+                  d.ntaps, d.K, d.Kpad);
+    }
+    int lo[3] = {1 << 20, 1 << 20, 1 << 20}, hi[3] = {-(1 << 20), -(1 << 20), -(1 << 20)}, up[3];
+    for (int t = 0; t < d.ntaps; ++t)
+      for (int a = 0; a < 3; ++a) {
+        lo[a] = d.taps_host[4 * t + a] < lo[a] ? d.taps_host[4 * t + a] : lo[a];
+        hi[a] = d.taps_host[4 * t + a] > hi[a] ? d.taps_host[4 * t + a] : hi[a];
+      }
+    const int in_ext[3] = {d.in_D, d.in_H, d.in_W}, out_ext[3] = {d.out_D, d.out_H, d.out_W};
+    const int str[3] = {d.stride_d, d.stride_h, d.stride_w};
+    for (int a = 0; a < 3; ++a) {
+      // the base pixel of output o sits at lo + o*stride; the box ends exactly at the last output's base pixel
+      up[a] = lo[a] + (out_ext[a] - 1) * str[a] - (in_ext[a] - 1);
+      if (lo[a] < -16 || lo[a] > 15 || up[a] < -16 || up[a] > 15 || hi[a] - lo[a] > 255) {
+        delete g;
+        return fail("gemm: im2col corners out of the descriptor range (axis %d: lo=%d up=%d span=%d)", a, lo[a], up[a],
+                    hi[a] - lo[a]);
+      }
+    }
+    for (int t = 0; t < d.ntaps; ++t)
+      p.flat_off[t] = (d.taps_host[4 * t + 2] - lo[2]) | ((d.taps_host[4 * t + 1] - lo[1]) << 8) |
+                      ((d.taps_host[4 * t] - lo[0]) << 16);
+    p.i2c_lo_d = lo[0]; p.i2c_lo_h = lo[1]; p.i2c_lo_w = lo[2];
+    p.chunks_per_tap = d.Cin / BK;
+    const uint64_t n_img = (uint64_t)(d.M / (d.out_D * d.out_H * d.out_W));
+    if (encode_im2col_map(&g->map_a, d.A, n_img, d.in_D, d.in_H, d.in_W, d.in_Cs, lo, up, str)) { delete g; return 1; }
   } else if (d.a_mode == SVX_A_SLAB3) {
     const int live = d.cin_live > 0 ? d.cin_live : BK;
     bool ok = d.Cin == BK && live <= BK && d.in_Cs % 4 == 0 && d.in_c0 >= 0 && d.N <= 16 && d.block_n == S3_N &&
@@ -1047,6 +1181,15 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     delete g;
     return fail("gemm: decoder tail epilogue needs block_n=16, N=16, aux weights and a coarse output");
   }
+  if (d.epi_mode == SVX_EPI_CONVT8) {
+    const bool tail = d.epi_aux != nullptr;
+    const bool ok = d.a_mode != SVX_A_SLAB3 && d.cls_cout > 0 && d.N == 8 * d.cls_cout &&
+                    (tail ? (d.cls_cout == 8 && d.epi_out2 && !d.residual && ((d.o_base | d.o_sn | d.o_sd | d.o_sh | d.o_sw |
+                                                                                 d.c_sd | d.c_sh | d.c_sw) & 3) == 0 &&
+                             (reinterpret_cast<uintptr_t>(d.out) & 15) == 0)
+                          : true);
+    if (!ok) { delete g; return fail("gemm: bad transposed-convolution class epilogue (cls_cout=%d N=%d)", d.cls_cout, d.N); }
+  }
   p.M = d.M; p.N = d.N; p.K = d.K; p.Npad = d.Npad; p.nk = d.Kpad / BK; p.nk_a = p.nk; p.tiles_n = d.Npad / d.block_n; p.a_mode = d.a_mode;
   p.A = d.A;
   p.in_D = d.in_D; p.in_H = d.in_H; p.in_W = d.in_W; p.in_Cs = d.in_Cs; p.in_c0 = d.in_c0; p.Cin = d.Cin;
@@ -1060,6 +1203,7 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   p.act = d.act; p.act_param = d.act_param; p.res_after_act = d.res_after_act;
   p.out_scale = d.out_scale; p.round_tf32 = d.round_tf32; p.epi_mode = d.epi_mode;
   p.epi_aux = d.epi_aux; p.out2 = d.epi_out2;
+  p.cls_cout = d.cls_cout; p.c_sd = d.c_sd; p.c_sh = d.c_sh; p.c_sw = d.c_sw; p.c2_sd = d.c2_sd; p.c2_sh = d.c2_sh; p.c2_sw = d.c2_sw;
   p.o2_base = d.o2_base; p.o2_sn = d.o2_sn; p.o2_sd = d.o2_sd; p.o2_sh = d.o2_sh; p.o2_sw = d.o2_sw;
   auto al4 = [](long long v) { return (v & 3) == 0; };
   p.vec_ok = (d.N % 4 == 0) && al4(d.o_base) && al4(d.o_sn) && al4(d.o_sd) && al4(d.o_sh) && al4(d.o_sw) &&

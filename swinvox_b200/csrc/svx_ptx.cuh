@@ -99,6 +99,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, uint3
       : "memory");
 }
 
+// im2col-mode TMA over an NDHWC tensor: `pixelsPerColumn` consecutive base pixels starting at (w, h, d, n) -- traversed
+// w-fastest inside the descriptor's bounding box with the convolution stride -- each read at filter offset (ow, oh, od),
+// channels [c, c + channelsPerPixel); out-of-tensor pixels are zero-filled.
+__device__ __forceinline__ void tma_load_im2col_5d(uint32_t dst, const void* map, uint32_t bar, int32_t c, int32_t w,
+                                                   int32_t h, int32_t d, int32_t n, uint16_t ow, uint16_t oh,
+                                                   uint16_t od) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %9, %10};"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "h"(ow), "h"(oh), "h"(od)
+      : "memory");
+}
+
 // smem tile -> global (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_2d(const void* map, uint32_t src, int32_t x, int32_t y) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

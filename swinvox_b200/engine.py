@@ -6,12 +6,13 @@ Layout conventions: activations are fp32 channels-last buffers ``[N, D, H, W, Cs
 D=1); contraction weights are ``[Npad, Kpad]`` with k = tap*Cin + c, pre-rounded to TF32.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, A_FLAT, A_GATHER, A_PLAIN, A_SLAB3, EPI_DEC_TAIL, EPI_POOL8, EPI_STD,
+from ._lib import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, A_FLAT, A_GATHER, A_IM2COL, A_PLAIN, A_SLAB3, EPI_CONVT8, EPI_DEC_TAIL, EPI_POOL8, EPI_STD,
                    POOL_AVG, POOL_MAX)
 
 BLOCK_NS = (16, 32, 64, 96, 128, 192, 256)
@@ -212,6 +213,31 @@ def pack_convT_class(weight, bn, device, pads, parity, cin_pad=None, block_n=Non
     return pack_matrix(torch.cat(cols, dim=1), b, device, block_n, n_logical), taps
 
 
+def pack_convT_fused(weight, bn, device, bias=None, block_n=None):
+    """nn.ConvTranspose3d(k=4, s=2, p=1) weight [Cin, Cout, 4, 4, 4] with all eight output-parity classes in N:
+    W[cls*Cout + co, tap*Cin + c], tap = (td*3 + th)*3 + tw over the 3x3x3 INPUT neighbourhood (offsets t-1).
+    Along one axis, output 2i+par reads input i+delta through kernel index k = par + 1 - 2*delta, so parity 0 uses
+    delta in {-1, 0} and parity 1 uses {0, +1}; the other taps of a class are structural zeros."""
+    w = weight.detach().float().transpose(0, 1)  # [Cout, Cin, 4, 4, 4]
+    assert tuple(w.shape[2:]) == (4, 4, 4)
+    w, b = fold_bn(w, bias, bn)
+    cout, cin = w.shape[:2]
+    assert cin % 4 == 0
+    W = torch.zeros(8, cout, 27, cin, dtype=torch.float32, device=w.device)
+    for cls in range(8):
+        par = (cls >> 2, (cls >> 1) & 1, cls & 1)
+        per_axis = [dict((delta + 1, k) for k, delta in convT_class_taps(4, 1, pa)) for pa in par]   # t -> k
+        for td, kd in per_axis[0].items():
+            for th, kh in per_axis[1].items():
+                for tw, kw in per_axis[2].items():
+                    W[cls, :, (td * 3 + th) * 3 + tw, :] = w[:, :, kd, kh, kw]
+    n = 8 * cout
+    return pack_matrix(W.reshape(n, 27 * cin), b.repeat(8), device, block_n or (16 if n <= 16 else None), n)
+
+
+CONVT_FUSED_TAPS = [(a - 1, b - 1, c - 1) for a in range(3) for b in range(3) for c in range(3)]
+
+
 class Plan:
     """A recorded op list bound to fixed device buffers."""
 
@@ -305,6 +331,31 @@ class Plan:
         t = torch.tensor([[a, b, c, 0] for a, b, c in taps], dtype=torch.int32, device=self.device)
         return self.hold(t)
 
+    def _gather_operand(self, d, x, cin, taps, rows_dhw, stride):
+        """A operand of an implicit-GEMM convolution over the unpadded channels-last tensor `x`: fetched by the TMA unit
+        in im2col mode when the channel count allows whole 32-channel boxes (SVX_A_IM2COL), by cp.async gather warps
+        otherwise (SVX_A_GATHER: the 4-channel image stems)."""
+        rd, rh, rw = rows_dhw
+        d.M = x.N * rd * rh * rw
+        d.A = self.hold(x).buf.data_ptr()
+        d.in_D, d.in_H, d.in_W, d.in_Cs, d.in_c0, d.Cin = x.D, x.H, x.W, x.Cs, x.c0, cin
+        d.out_D, d.out_H, d.out_W = rd, rh, rw
+        d.stride_d, d.stride_h, d.stride_w = stride
+        d.ntaps = len(taps)
+        lo = [min(t[a] for t in taps) for a in range(3)]
+        up = [lo[a] + (rows_dhw[a] - 1) * stride[a] - ((x.D, x.H, x.W)[a] - 1) for a in range(3)]
+        tma = (cin % 32 == 0 and len(taps) <= 64 and all(-16 <= v <= 15 for v in lo + up)
+               and not os.environ.get("SVX_NO_IM2COL"))
+        if tma:
+            d.a_mode = A_IM2COL
+            host = (C.c_int32 * (4 * len(taps)))(*[v for t in taps for v in (t[0], t[1], t[2], 0)])
+            self.keep[id(host)] = host
+            d.taps_host = C.cast(host, C.c_void_p)
+        else:
+            d.a_mode = A_GATHER
+            d.taps = self._taps_tensor(taps).data_ptr()
+        return tma
+
     def _fill_epilogue(self, d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out,
                        res_via_mma=False):
         pack.finalize(rows=d.M, gather=(d.a_mode == A_GATHER))
@@ -367,16 +418,8 @@ class Plan:
         assert cin_pad * len(taps) == pack.K and cin_pad % 4 == 0 and cin_pad >= x.C
         assert x.c0 % 4 == 0 and x.Cs % 4 == 0 and x.c0 + cin_pad <= x.Cs, (x.c0, cin_pad, x.Cs)
         assert not any(x.pad), "gather mode reads unpadded tensors (use conv_flat for padded ones)"
-        rd, rh, rw = rows_dhw or out.inner
         d = _lib.GemmDesc()
-        d.M = x.N * rd * rh * rw
-        d.a_mode = A_GATHER
-        d.A = self.hold(x).buf.data_ptr()
-        d.in_D, d.in_H, d.in_W, d.in_Cs, d.in_c0, d.Cin = x.D, x.H, x.W, x.Cs, x.c0, cin_pad
-        d.out_D, d.out_H, d.out_W = rd, rh, rw
-        d.stride_d, d.stride_h, d.stride_w = stride
-        d.ntaps = len(taps)
-        d.taps = self._taps_tensor(taps).data_ptr()
+        self._gather_operand(d, x, cin_pad, taps, rows_dhw or out.inner, stride)
         self._fill_epilogue(d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out)
         if epi_tail is not None:
             aux, out2, map2 = epi_tail
@@ -385,6 +428,35 @@ class Plan:
             d.epi_out2 = self.hold(out2).data_ptr()
             d.o2_base, d.o2_sn, d.o2_sd, d.o2_sh, d.o2_sw = map2
         self._add("gemm", d, name or "conv", 2.0 * d.M * pack.N * pack.K)
+        return out
+
+    def convT_fused(self, x, pack, out, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True, out_scale=1.0,
+                    round_out=False, tail=None, name=None):
+        """ConvTranspose3d(k4, s2, p1) with the eight parity classes in N (SVX_EPI_CONVT8): one implicit GEMM whose rows
+        are the INPUT voxels of `x` (gathered 3x3x3 neighbourhood) and whose epilogue scatters column (cls, c) to
+        output voxel (2d+pd, 2h+ph, 2w+pw).  `pack` from pack_convT_fused.  tail = (aux[9], coarse tensor [N, OD*OH*OW]):
+        the decoder's layer5 + cat (8 channels per class)."""
+        cout = pack.N // 8
+        assert pack.N == 8 * cout and pack.K == 27 * x.C and x.C % 4 == 0 and not any(x.pad)
+        od, oh, ow = out.inner
+        assert (od, oh, ow) == (2 * x.D, 2 * x.H, 2 * x.W) and out.N == x.N and out.C >= (9 if tail else cout)
+        d = _lib.GemmDesc()
+        self._gather_operand(d, x, x.C, CONVT_FUSED_TAPS, (x.D, x.H, x.W), (1, 1, 1))
+        ob, osn, osd, osh, osw = out.interior_map()
+        self._fill_epilogue(d, pack, out, (ob, osn, 2 * osd, 2 * osh, 2 * osw), act, act_param, residual, res_after_act,
+                            out_scale, round_out)
+        d.epi_mode = EPI_CONVT8
+        d.cls_cout = cout
+        d.c_sd, d.c_sh, d.c_sw = osd, osh, osw
+        if tail is not None:
+            aux, out2 = tail
+            assert cout == 8 and residual is None and act == ACT_RELU
+            d.epi_aux = self.hold(aux).data_ptr()
+            d.epi_out2 = self.hold(out2).data_ptr()
+            d.o2_base, d.o2_sn, d.o2_sd, d.o2_sh, d.o2_sw = 0, od * oh * ow, 2 * oh * ow, 2 * ow, 2
+            d.c2_sd, d.c2_sh, d.c2_sw = oh * ow, ow, 1
+        # useful work only: 8 of the 27 taps feed each class
+        self._add("gemm", d, name or "convT_fused", 2.0 * d.M * pack.N * 8 * x.C)
         return out
 
     def conv_flat(self, x, pack, taps, out, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True,

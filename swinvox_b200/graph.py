@@ -309,8 +309,9 @@ def lower_decoder(plan, dec, feat, N):
     w5[:8] = l5.weight.detach().float().reshape(8).cpu()
     if l5.bias is not None:
         w5[8] = l5.bias.detach().float().cpu()[0]
-    _convT_layer(plan, x, dec.layer4[0], dec.layer4[1], (1, 1, 1), raw, "decoder.layer4+5", n_logical=16, block_n=16,
-                 epi_tail=(w5.to(dev), coarse))
+    # layer4 (32 -> 8 channels) + layer5 + cat: all eight parity classes in one GEMM (N = 64), tail in the epilogue
+    plan.convT_fused(x, E.pack_convT_fused(dec.layer4[0].weight, dec.layer4[1], dev, bias=dec.layer4[0].bias, block_n=64),
+                     raw, act=ACT_RELU, round_out=True, tail=(w5.to(dev), coarse), name="decoder.layer4+5")
     return raw, coarse
 
 
@@ -408,6 +409,7 @@ def lower_refiner(plan, ref, vol, B):
     out = plan.empty(B, 32768)
     oact = Act(out.view(-1, 1), B, 32, 32, 32, 1, 0)
     vact = Act(vol.view(-1, 1), B, 32, 32, 32, 1, 0)
-    _convT_layer(plan, r16, ref.layer8[0], None, (1, 1, 1), oact, "refiner.layer8", act=ACT_NONE, residual=vact,
-                 round_out=False, block_n=16, out_scale=0.5)
+    # layer8 (32 -> 1 channel): the eight parity classes are the N = 8 columns of one GEMM
+    plan.convT_fused(r16, E.pack_convT_fused(ref.layer8[0].weight, None, dev, bias=ref.layer8[0].bias), oact, act=ACT_NONE,
+                     residual=vact, res_after_act=True, out_scale=0.5, name="refiner.layer8")
     return out

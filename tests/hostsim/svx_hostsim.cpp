@@ -49,6 +49,20 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   SVX_REQUIRE(d.Npad % d.block_n == 0 && d.Npad >= d.N, "gemm: bad Npad");
   if (d.a_mode == SVX_A_GATHER)
     SVX_REQUIRE(d.Cin % 4 == 0 && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.K == d.ntaps * d.Cin, "gemm: bad gather");
+  else if (d.a_mode == SVX_A_IM2COL) {
+    SVX_REQUIRE(d.Cin % 32 == 0 && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.K == d.ntaps * d.Cin && d.Kpad == d.K &&
+                    d.taps_host && d.ntaps <= 64 && d.M % (d.out_D * d.out_H * d.out_W) == 0,
+                "gemm: bad im2col");
+    const int in_ext[3] = {d.in_D, d.in_H, d.in_W}, out_ext[3] = {d.out_D, d.out_H, d.out_W};
+    const int str[3] = {d.stride_d, d.stride_h, d.stride_w};
+    for (int a = 0; a < 3; ++a) {   // the corner range of the hardware descriptor
+      int lo = 1 << 20, hi = -(1 << 20);
+      for (int t = 0; t < d.ntaps; ++t) { lo = std::min(lo, d.taps_host[4 * t + a]); hi = std::max(hi, d.taps_host[4 * t + a]); }
+      const int up = lo + (out_ext[a] - 1) * str[a] - (in_ext[a] - 1);
+      SVX_REQUIRE(lo >= -16 && lo <= 15 && up >= -16 && up <= 15 && hi - lo <= 255 && str[a] >= 1 && str[a] <= 8,
+                  "gemm: im2col corners out of range");
+    }
+  }
   else if (d.a_mode == SVX_A_FLAT)
     SVX_REQUIRE(d.Cin % 32 == 0 && d.K == d.ntaps * d.Cin && d.Kpad == d.K && d.taps_host && d.ntaps <= 64 &&
                     d.out_D == d.in_D && d.out_H == d.in_H && d.out_W == d.in_W && d.lda >= d.M,
@@ -60,6 +74,9 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
                 "gemm: bad slab conv");
   else
     SVX_REQUIRE(d.lda % 4 == 0 && d.lda >= d.K, "gemm: bad lda");
+  if (d.epi_mode == SVX_EPI_CONVT8)
+    SVX_REQUIRE(d.a_mode != SVX_A_SLAB3 && d.cls_cout > 0 && d.N == 8 * d.cls_cout && (!d.epi_aux || (d.cls_cout == 8 && d.epi_out2)),
+                "gemm: bad transposed-convolution class epilogue");
   if (d.epi_mode == SVX_EPI_DEC_TAIL)
     SVX_REQUIRE(d.block_n == 16 && d.N == 16 && d.epi_aux && d.epi_out2, "gemm: bad decoder tail");
   *out = new GemmPrepared();
@@ -138,10 +155,11 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
             arow[tap * d.Cin + c] = (ok && d.in_c0 + c < d.in_Cs) ? tf32_trunc(px[c]) : 0.f;
         }
       } else {
+        const int32_t* tp = d.a_mode == SVX_A_IM2COL ? d.taps_host : d.taps;
         for (int tap = 0; tap < d.ntaps; ++tap) {
-          const int id = od * d.stride_d + d.taps[tap * 4 + 0];
-          const int ih = oh * d.stride_h + d.taps[tap * 4 + 1];
-          const int iw = ow * d.stride_w + d.taps[tap * 4 + 2];
+          const int id = od * d.stride_d + tp[tap * 4 + 0];
+          const int ih = oh * d.stride_h + tp[tap * 4 + 1];
+          const int iw = ow * d.stride_w + tp[tap * 4 + 2];
           const bool ok = id >= 0 && id < d.in_D && ih >= 0 && ih < d.in_H && iw >= 0 && iw < d.in_W;
           const float* px = d.A + (((n * d.in_D + id) * d.in_H + ih) * (long long)d.in_W + iw) * d.in_Cs + d.in_c0;
           for (int c = 0; c < d.Cin; ++c) arow[tap * d.Cin + c] = ok ? tf32_trunc(px[c]) : 0.f;
@@ -163,6 +181,38 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
         for (int j = 9; j < 16; ++j) x[j] = 0.f;
         d.epi_out2[d.o2_base + n * d.o2_sn + od * d.o2_sd + oh * d.o2_sh + ow * d.o2_sw] = g;
         for (int j = 0; j < 16; ++j) d.out[off + j] = rnd(x[j], d.round_tf32);
+        continue;
+      }
+      if (d.epi_mode == SVX_EPI_CONVT8) {
+        const int cc = d.cls_cout;
+        for (int cls = 0; cls < 8; ++cls) {
+          const long long o = off + (cls >> 2) * d.c_sd + ((cls >> 1) & 1) * d.c_sh + (cls & 1) * d.c_sw;
+          float g = d.epi_aux ? d.epi_aux[8] : 0.f;
+          for (int c = 0; c < cc; ++c) {
+            const int j = cls * cc + c;
+            float acc = 0.f;
+            const float* w = d.W + (long long)j * w_pitch;
+            for (int k = 0; k < d.K; ++k) acc += arow[k] * tf32_trunc(w[k]);
+            float v = acc + (d.bias ? d.bias[j] : 0.f);
+            if (d.epi_aux) {
+              v = v > 0.f ? v : 0.f;
+              g = fmaf(d.epi_aux[c], v, g);
+            } else {
+              const float res = d.residual ? d.residual[o + c] : 0.f;
+              if (d.residual && !d.res_after_act) v += res;
+              v = act_fn(v, d.act, d.act_param);
+              if (d.residual && d.res_after_act) v += res;
+              v *= d.out_scale;
+            }
+            d.out[o + c] = rnd(v, d.round_tf32);
+          }
+          if (d.epi_aux) {
+            d.out[o + 8] = rnd(g, d.round_tf32);
+            d.out[o + 9] = d.out[o + 10] = d.out[o + 11] = 0.f;
+            d.epi_out2[d.o2_base + n * d.o2_sn + od * d.o2_sd + oh * d.o2_sh + ow * d.o2_sw + (cls >> 2) * d.c2_sd +
+                       ((cls >> 1) & 1) * d.c2_sh + (cls & 1) * d.c2_sw] = g;
+          }
+        }
         continue;
       }
       if (d.epi_mode == SVX_EPI_POOL8) {

@@ -296,6 +296,52 @@ def test_decoder_tail_epilogue(dev):
     assert got[:, 9:].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("cout,ind", [(1, (3, 4, 5)), (4, (2, 3, 6)), (1, (16, 16, 16))])
+def test_convtranspose3d_fused_classes(dev, cout, ind):
+    """all eight parity classes in N (SVX_EPI_CONVT8): the refiner's layer8 form, (x + convT(y)) * 0.5"""
+    DEV = dev
+    torch.manual_seed(21 + cout)
+    cin, n = 32, 2
+    x = E.tf32_round(torch.randn(n, cin, *ind))
+    ct = torch.nn.ConvTranspose3d(cin, cout, 4, 2, 1, bias=True)
+    od, oh, ow = [2 * i for i in ind]
+    skip = torch.randn(n, cout, od, oh, ow)
+    p = E.Plan(DEV)
+    out = p.new_act(n, od, oh, ow, cout)
+    p.convT_fused(act_from_nchw(x, DEV), E.pack_convT_fused(ct.weight, None, DEV, bias=ct.bias), out, act=E.ACT_NONE,
+                  residual=act_from_nchw(skip, DEV), res_after_act=True, out_scale=0.5)
+    p.run()
+    sync(DEV)
+    ref = F.conv_transpose3d(x.double(), E.tf32_round(ct.weight.detach()).double(), ct.bias.detach().double(), 2, 1)
+    assert rel_err(to_nchw(out), (ref + skip.double()) * 0.5) < 1e-4
+
+
+def test_decoder_tail_fused_classes(dev):
+    """decoder layer4 + layer5 + cat with the eight classes in one GEMM, writing the merger's zero-bordered layout"""
+    DEV = dev
+    torch.manual_seed(5)
+    x = E.tf32_round(torch.randn(3, 32, 4, 5, 6))
+    ct = torch.nn.ConvTranspose3d(32, 8, 4, 2, 1, bias=False)
+    bn = rand_bn(torch.nn.BatchNorm3d(8))
+    w5 = torch.randn(9)
+    p = E.Plan(DEV)
+    raw = p.new_act(3, 8, 10, 12, 16, Cs=32, pad=(1, 1, 1))
+    coarse = p.empty(3, 8 * 10 * 12)
+    p.convT_fused(act_from_nchw(x, DEV), E.pack_convT_fused(ct.weight, bn, DEV, block_n=64), raw, act=E.ACT_RELU,
+                  round_out=True, tail=(w5.to(DEV), coarse))
+    p.run()
+    sync(DEV)
+    wf, bf = E.fold_bn(ct.weight.transpose(0, 1), None, bn)
+    feat = F.relu(F.conv_transpose3d(x.double(), E.tf32_round(wf).transpose(0, 1).double(), bf.double(), 2, 1))
+    gen = (feat * w5[:8].double().view(1, 8, 1, 1, 1)).sum(1) + w5[8].double()
+    got = to_nchw(raw)
+    assert rel_err(coarse.view(3, 8, 10, 12), gen) < 1e-4
+    assert rel_err(got[:, :8], feat) < 6e-4
+    assert rel_err(got[:, 8], gen) < 6e-4
+    assert got[:, 9:].abs().max().item() == 0.0
+    assert raw.buf.view(3, 10, 12, 14, 32)[:, 0].abs().max().item() == 0.0   # the zero border stays untouched
+
+
 def test_im2col_and_pools(dev):
     DEV = dev
     torch.manual_seed(4)

@@ -20,10 +20,15 @@ cfg = svx_config.make_cfg()
 rec = Reconstructor(cfg, device="cuda")
 images = torch.rand(B, V, 3, 224, 224, device="cuda") * 2 - 1
 with torch.no_grad():
-    feat = rec.encoder(images)
-    raw, gen = rec.decoder(feat)
-    vol = rec.merger(raw, gen)
-    out = rec.refiner(vol)
+    if os.environ.get("SVX_ISOLATE"):   # random stand-ins for the upstream modules (ncu captures only `which`)
+        feat = torch.randn(B, V, 256, 7, 7, device="cuda")
+        raw, gen = torch.randn(B, V, 9, 32, 32, 32, device="cuda"), torch.rand(B, V, 32, 32, 32, device="cuda")
+        vol = torch.rand(B, 32, 32, 32, device="cuda")
+    else:
+        feat = rec.encoder(images)
+        raw, gen = rec.decoder(feat)
+        vol = rec.merger(raw, gen)
+        out = rec.refiner(vol)
     torch.cuda.synchronize()
     fns = {"encoder": lambda: rec.encoder(images), "decoder": lambda: rec.decoder(feat),
            "merger": lambda: rec.merger(raw, gen), "refiner": lambda: rec.refiner(vol),
