@@ -208,18 +208,19 @@ def run_ours(args):
     e2e_value = B * world / (e2e_s.item() / args.steps)
 
     # ---- roofline of the dominant kernel (the tcgen05 contraction kernel), measured live with CUDA events -------
-    gemm_ms, slab_ms, total_ms, breakdown = 0.0, 0.0, 0.0, []
+    gemm_ms, slab_ms, total_ms, gemm_bytes, breakdown = 0.0, 0.0, 0.0, 0.0, []
     for mod in rec.modules():
         for entry in mod._plans.values():
             plan = entry[0]
             times = plan.time_ops(iters=3)
-            for nm, t, fl in zip(plan.op_names, times, plan.flops):
+            for nm, t, fl, nb in zip(plan.op_names, times, plan.flops, plan.bytes):
                 total_ms += t
                 if fl > 0 and nm.startswith("merger.layer"):
                     slab_ms += t
                 elif fl > 0 and not nm.endswith(".attn"):
                     gemm_ms += t
-                breakdown.append((nm, t, fl))
+                    gemm_bytes += nb
+                breakdown.append((nm, t, fl, nb))
     # dominant kernel = gemm_tf32_kernel (every Linear / Conv2d / Conv3d k4 / ConvTranspose3d).  Algorithmic FLOPs per
     # step = SURVEY 8(d) figure of the reference forward minus what other kernels execute (attention, merger convs).
     algo_gf = B * ((GF_PER_VIEW - GF_ATTENTION_PER_VIEW - GF_MERGER_PER_VIEW) * V + GF_PER_OBJECT)
@@ -231,9 +232,19 @@ def run_ours(args):
         pass
     bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak = bf16_peak / 2.0   # kind::tf32 runs at half the bf16 rate; MEASURED_PEAKS.json has no tf32 entry
-    n_gemm = sum(1 for nm, t, fl in breakdown if fl > 0 and not nm.endswith(".attn") and not nm.startswith("merger.layer"))
+    n_gemm = sum(1 for nm, t, fl, nb in breakdown if fl > 0 and not nm.endswith(".attn") and not nm.startswith("merger.layer"))
+    hbm = peaks.get("hbm_gbs", 6550.7)
+    # per-op roofline floor: every op is bounded by max(algorithmic FLOP / tensor peak, algorithmic bytes / HBM peak)
+    floor_ms = sum(max(fl / (peak * 1e9), nb / (hbm * 1e6)) for nm, t, fl, nb in breakdown)
+    traffic = None   # DRAM bytes per launch of the dominant kernel from the committed ncu launch list of this command
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["gemm_tf32_kernel"]["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "gemm_tf32_kernel", "launches_per_step": n_gemm,
+                "traffic": traffic, "kernel": "gemm_tf32_kernel", "launches_per_step": n_gemm,
+                "algorithmic_bytes_per_launch": gemm_bytes / max(n_gemm, 1),
+                "step_floor_ms": floor_ms, "step_frac_of_floor": floor_ms / total_ms if total_ms > 0 else None,
                 "kernel_ms_per_step": gemm_ms, "all_kernels_ms_per_step": total_ms,
                 "algorithmic_gflop_per_step": algo_gf, "conv3_slab_ms_per_step": slab_ms,
                 "tf32_cublas_tflops_measured": TF32_CUBLAS_MEASURED,
@@ -243,7 +254,7 @@ def run_ours(args):
     if rank == 0:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "op_breakdown.json"), "w") as fh:
-            json.dump(sorted(breakdown, key=lambda r: -r[1]), fh, indent=0)
+            json.dump(sorted(breakdown, key=lambda r: -r[1]), fh)
         cpu_value, cores, sample = cpu_reference_rate(V, args.cpu_seconds) if world == 1 else (None, None, None)
         line = {
             "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": args.steps,

@@ -213,6 +213,26 @@ typedef struct svx_transpose_desc {
   int32_t N, C, P, Cs; int32_t to_channels_last; int32_t round_tf32;
 } svx_transpose_desc;
 
+/* binvox run-length decode (utils/binvox_rw.py:119-153 read_as_3d_array; utils/data_loaders.py:84-87): the payload
+ * after the text header is (value, count) byte pairs; np.repeat(values, counts).astype(bool).reshape(dims) gives the
+ * volume in file order x, z, y (y fastest); fix_coords transposes it to x, y, z.  B objects per launch: their
+ * payloads are concatenated in `payload` (each starting at an even offset), object b owns bytes
+ * [offsets[b], offsets[b+1]).  out: fp32 {0,1} [B, d0, d2, d1] (fix_coords) or [B, d0, d1, d2]; status[b] = number of
+ * voxels the stream expands to (the caller compares it with d0*d1*d2, the reference's reshape would raise). */
+typedef struct svx_binvox_decode_desc {
+  const uint8_t* payload; const int64_t* offsets; float* out; int32_t* status;
+  int32_t B, d0, d1, d2, fix_coords;
+} svx_binvox_decode_desc;
+
+/* binvox run-length encode (utils/binvox_rw.py:239-300 write): volume fp32 [B, d0, d1, d2], voxel set iff
+ * value >= threshold; axis_xyz != 0: the volume is in x, y, z order and is written transposed (file order x, z, y).
+ * Runs are cut at 255 exactly like the reference's state machine, including its zero-length pair after a run whose
+ * length is a multiple of 255.  payload: [B, 2*d0*d1*d2] bytes (worst case), nbytes[b] = bytes written for b. */
+typedef struct svx_binvox_encode_desc {
+  const float* volume; float threshold; uint8_t* payload; int32_t* nbytes;
+  int32_t B, d0, d1, d2, axis_xyz;
+} svx_binvox_encode_desc;
+
 /* ---- library ------------------------------------------------------------------------ */
 int svx_abi_version(void);
 const char* svx_last_error(void);
@@ -233,6 +253,8 @@ int svx_bilinear_add(const svx_bilinear_desc*, void* stream);
 int svx_merger_fuse(const svx_mergefuse_desc*, void* stream);
 int svx_voxel_metrics(const svx_metrics_desc*, void* stream);
 int svx_transpose(const svx_transpose_desc*, void* stream);
+int svx_binvox_decode(const svx_binvox_decode_desc*, void* stream);
+int svx_binvox_encode(const svx_binvox_encode_desc*, void* stream);
 
 /* ---- plans: a recorded op list replayed per forward (one per module instance/shape) --- */
 typedef struct svx_plan svx_plan;

@@ -1,0 +1,180 @@
+// svx_io.cu -- binvox run-length streams <-> dense device volumes (the ground-truth side of the IoU step:
+// utils/binvox_rw.py:119-153 read_as_3d_array, :239-300 write; utils/data_loaders.py:84-87).
+// Byte / index work, HBM- and latency-bound: one CTA per object, the volume staged in shared memory as bytes so that
+// the global reads (payload) and writes (fp32 volume, pairs) are coalesced and the x,z,y -> x,y,z transpose is free.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "svx_internal.h"
+
+namespace svx {
+namespace {
+
+constexpr int kIoThreads = 256;
+
+// exclusive prefix sum of one int per thread over the CTA; returns the exclusive value, *total = CTA sum
+__device__ __forceinline__ int block_excl_scan(int v, int* warp_tot, int* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();   // warp_tot may still be read by the previous call
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < kIoThreads / 32; ++i) {
+    const int t = warp_tot[i];
+    if (i < w) base += t;
+    tot += t;
+  }
+  *total = tot;
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kIoThreads) binvox_decode_kernel(const svx_binvox_decode_desc d) {
+  extern __shared__ uint8_t vol[];   // P bytes, file order (x, z, y)
+  __shared__ int warp_tot[kIoThreads / 32];
+  const int P = d.d0 * d.d1 * d.d2;
+  for (int b = blockIdx.x; b < d.B; b += gridDim.x) {
+    for (int i = threadIdx.x; i < P; i += kIoThreads) vol[i] = 0;
+    __syncthreads();
+    const uint8_t* pay = d.payload + d.offsets[b];
+    const long long npairs = (d.offsets[b + 1] - d.offsets[b]) / 2;
+    long long carry = 0;
+    for (long long base = 0; base < npairs; base += kIoThreads) {
+      const long long p = base + threadIdx.x;
+      int val = 0, cnt = 0;
+      if (p < npairs) {
+        const uchar2 vc = *reinterpret_cast<const uchar2*>(pay + 2 * p);   // payload offsets are even (host contract)
+        val = vc.x;
+        cnt = vc.y;
+      }
+      int tot;
+      const long long start = carry + block_excl_scan(cnt, warp_tot, &tot);
+      if (val != 0) {   // np.repeat(values, counts).astype(bool): any non-zero value is "set"
+        for (int i = 0; i < cnt; ++i)
+          if (start + i < P) vol[start + i] = 1;
+      }
+      carry += tot;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) d.status[b] = (int)(carry > 0x7fffffffLL ? 0x7fffffffLL : carry);
+    float* out = d.out + (long long)b * P;
+    if (d.fix_coords) {   // out[x][y][z] = file[x][z][y]
+      for (int o = threadIdx.x; o < P; o += kIoThreads) {
+        const int z = o % d.d1;
+        const int t = o / d.d1;
+        const int y = t % d.d2, x = t / d.d2;
+        out[o] = vol[(x * d.d1 + z) * d.d2 + y] ? 1.f : 0.f;
+      }
+    } else {
+      for (int o = threadIdx.x; o < P; o += kIoThreads) out[o] = vol[o] ? 1.f : 0.f;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kIoThreads) binvox_encode_kernel(const svx_binvox_encode_desc d) {
+  extern __shared__ uint8_t smem[];
+  __shared__ int warp_tot[kIoThreads / 32];
+  const int P = d.d0 * d.d1 * d.d2;
+  uint8_t* vol = smem;                                               // P bytes, file order
+  int* starts = reinterpret_cast<int*>(smem + ((P + 15) / 16) * 16); // P + 1 run starts
+  const int seg = (P + kIoThreads - 1) / kIoThreads;
+  for (int b = blockIdx.x; b < d.B; b += gridDim.x) {
+    const float* in = d.volume + (long long)b * P;
+    if (d.axis_xyz) {   // input [x][y][z]; the file stores [x][z][y]: read coalesced, scatter into shared memory
+      for (int i = threadIdx.x; i < P; i += kIoThreads) {
+        const int z = i % d.d2;
+        const int t = i / d.d2;
+        const int y = t % d.d1, x = t / d.d1;
+        vol[(x * d.d2 + z) * d.d1 + y] = in[i] >= d.threshold ? 1 : 0;
+      }
+    } else {
+      for (int i = threadIdx.x; i < P; i += kIoThreads) vol[i] = in[i] >= d.threshold ? 1 : 0;
+    }
+    __syncthreads();
+    // run starts: thread t owns voxels [t*seg, (t+1)*seg)
+    const int f0 = threadIdx.x * seg, f1 = min(P, f0 + seg);
+    int nstart = 0;
+    for (int f = f0; f < f1; ++f) nstart += (f == 0 || vol[f] != vol[f - 1]) ? 1 : 0;
+    int R;
+    int r = block_excl_scan(nstart, warp_tot, &R);
+    for (int f = f0; f < f1; ++f)
+      if (f == 0 || vol[f] != vol[f - 1]) starts[r++] = f;
+    if (threadIdx.x == 0) starts[R] = P;
+    __syncthreads();
+    // pairs per run (the writer's state machine, binvox_rw.py:279-300): L / 255 full pairs, then (value, L % 255) --
+    // written even when it is 0 if another run follows, dropped when it is 0 at the end of the stream
+    const int rseg = (R + kIoThreads - 1) / kIoThreads;
+    const int r0 = threadIdx.x * rseg, r1 = min(R, r0 + rseg);
+    int npair = 0;
+    for (int q = r0; q < r1; ++q) {
+      const int L = starts[q + 1] - starts[q];
+      npair += L / 255 + ((q < R - 1 || L % 255 > 0) ? 1 : 0);
+    }
+    int total;
+    int pos = block_excl_scan(npair, warp_tot, &total);
+    uint8_t* out = d.payload + (long long)b * 2 * P;
+    for (int q = r0; q < r1; ++q) {
+      const int L = starts[q + 1] - starts[q];
+      const uint8_t v = vol[starts[q]];
+      for (int k = 0; k < L / 255; ++k, ++pos) *reinterpret_cast<uchar2*>(out + 2 * pos) = make_uchar2(v, 255);
+      if (q < R - 1 || L % 255 > 0) {
+        *reinterpret_cast<uchar2*>(out + 2 * pos) = make_uchar2(v, (uint8_t)(L % 255));
+        ++pos;
+      }
+    }
+    if (threadIdx.x == 0) d.nbytes[b] = 2 * total;
+    __syncthreads();
+  }
+}
+
+}  // namespace
+}  // namespace svx
+
+using namespace svx;
+
+extern "C" {
+
+int svx_binvox_decode(const svx_binvox_decode_desc* d, void* stream) {
+  if (!d) return fail("svx_binvox_decode: null descriptor");
+  SVX_REQUIRE(d->payload && d->offsets && d->out && d->status, "binvox_decode: null operand");
+  SVX_REQUIRE(d->B > 0 && d->d0 > 0 && d->d1 > 0 && d->d2 > 0, "binvox_decode: empty problem");
+  const long long P = (long long)d->d0 * d->d1 * d->d2;
+  SVX_REQUIRE(P <= 200 * 1024, "binvox_decode: volumes above 204800 voxels are not supported (got %lld)", P);
+  static bool configured = false;
+  if (!configured) {
+    SVX_CUDA_OK(cudaFuncSetAttribute(binvox_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  const int grid = d->B < 148 * 4 ? d->B : 148 * 4;
+  binvox_decode_kernel<<<grid, kIoThreads, (size_t)P, (cudaStream_t)stream>>>(*d);
+  SVX_LAUNCH_OK("binvox_decode_kernel");
+  return 0;
+}
+
+int svx_binvox_encode(const svx_binvox_encode_desc* d, void* stream) {
+  if (!d) return fail("svx_binvox_encode: null descriptor");
+  SVX_REQUIRE(d->volume && d->payload && d->nbytes, "binvox_encode: null operand");
+  SVX_REQUIRE(d->B > 0 && d->d0 > 0 && d->d1 > 0 && d->d2 > 0, "binvox_encode: empty problem");
+  const long long P = (long long)d->d0 * d->d1 * d->d2;
+  SVX_REQUIRE(P <= 40000, "binvox_encode: volumes above 40000 voxels are not supported (got %lld)", P);
+  const size_t smem = (size_t)((P + 15) / 16 * 16 + 4 * (P + 1));
+  static bool configured = false;
+  if (!configured) {
+    SVX_CUDA_OK(cudaFuncSetAttribute(binvox_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = true;
+  }
+  const int grid = d->B < 148 ? d->B : 148;
+  binvox_encode_kernel<<<grid, kIoThreads, smem, (cudaStream_t)stream>>>(*d);
+  SVX_LAUNCH_OK("binvox_encode_kernel");
+  return 0;
+}
+
+}  // extern "C"

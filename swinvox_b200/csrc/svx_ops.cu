@@ -186,6 +186,97 @@ __global__ void lnrows_kernel(const svx_lnrows_desc d) {
   }
 }
 
+// ---- row LayerNorm, register-resident: one warp normalises R rows at a time, each row read from HBM exactly once
+// (NV float4 per lane) so R*NV independent 16-byte loads are in flight per lane; statistics are the exact two-pass
+// mean / variance computed from the registers.
+template <int NV, int R>
+__global__ void __launch_bounds__(256) lnrows_reg_kernel(const svx_lnrows_desc d) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int C = d.C;
+  const int Cq = C >> 2;  // merge: channels of one source pixel
+  const float invC = 1.f / (float)C;
+  float4 gm[NV <= 6 ? NV : 1], bt[NV <= 6 ? NV : 1];
+  if constexpr (NV <= 6) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane * 4 + i * 128;
+      gm[i] = c < C ? __ldg(reinterpret_cast<const float4*>(d.gamma + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      bt[i] = c < C ? __ldg(reinterpret_cast<const float4*>(d.beta + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const long long groups = (d.rows + R - 1) / R;
+  for (long long grp = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); grp < groups; grp += (long long)gridDim.x * wpb) {
+    float4 v[R][NV];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = grp * R + r;
+      const bool rok = row < d.rows;
+      long long base = row * (long long)C;
+      int x = 0, y = 0;
+      long long n = 0;
+      if (d.merge) {
+        const int W2 = d.W >> 1, H2 = d.H >> 1;
+        x = (int)(row % W2);
+        const long long t = row / W2;
+        y = (int)(t % H2);
+        n = t / H2;
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane * 4 + i * 128;
+        const float* src;
+        if (d.merge) {
+          const int sidx = c / Cq;
+          const int dy = sidx & 1, dx = sidx >> 1;  // timm order: (h0,w0) (h1,w0) (h0,w1) (h1,w1)
+          src = d.in + ((n * d.H + 2 * y + dy) * d.W + 2 * x + dx) * (long long)Cq + (c - sidx * Cq);
+        } else {
+          src = d.in + base + c;
+        }
+        v[r][i] = (rok && c < C) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = grp * R + r;
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) sum += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+      const float mean = warp_sum(sum) * invC;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (lane * 4 + i * 128 < C) {
+          const float a = v[r][i].x - mean, b = v[r][i].y - mean, e = v[r][i].z - mean, f = v[r][i].w - mean;
+          sq += (a * a + b * b) + (e * e + f * f);
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(sq) * invC + d.eps);
+      if (row < d.rows) {
+        float* dst = d.out + row * (long long)C;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = lane * 4 + i * 128;
+          if (c < C) {
+            float4 g, b;
+            if constexpr (NV <= 6) { g = gm[i]; b = bt[i]; }
+            else {
+              g = __ldg(reinterpret_cast<const float4*>(d.gamma + c));
+              b = __ldg(reinterpret_cast<const float4*>(d.beta + c));
+            }
+            float4 o;
+            o.x = maybe_round((v[r][i].x - mean) * rstd * g.x + b.x, d.round_tf32);
+            o.y = maybe_round((v[r][i].y - mean) * rstd * g.y + b.y, d.round_tf32);
+            o.z = maybe_round((v[r][i].z - mean) * rstd * g.z + b.z, d.round_tf32);
+            o.w = maybe_round((v[r][i].w - mean) * rstd * g.w + b.w, d.round_tf32);
+            *reinterpret_cast<float4*>(dst + c) = o;
+          }
+        }
+      }
+    }
+  }
+}
+
 // ---- whole-sample LayerNorm: one CTA per sample ----------------------------------------------------
 __global__ void __launch_bounds__(1024) lnsample_kernel(const svx_lnsample_desc d) {
   __shared__ float red[32];
@@ -670,7 +761,15 @@ int lnrows_launch(const svx_lnrows_desc& d, void* stream) {
               "layernorm_rows: C=%d unsupported", d.C);
   SVX_REQUIRE(al16(d.in) && al16(d.out) && al16(d.gamma) && al16(d.beta), "layernorm_rows: unaligned pointer");
   const int wpb = 8;
-  lnrows_kernel<<<grid_for(d.rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(d);
+  const int nv = (d.C + 127) / 128;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto grid = [&](int r) { return grid_for((d.rows + r - 1) / r, wpb, kSmCount * 8); };
+  if (nv == 1) lnrows_reg_kernel<1, 4><<<grid(4), wpb * 32, 0, st>>>(d);
+  else if (nv == 2) lnrows_reg_kernel<2, 4><<<grid(4), wpb * 32, 0, st>>>(d);
+  else if (nv == 3) lnrows_reg_kernel<3, 2><<<grid(2), wpb * 32, 0, st>>>(d);
+  else if (nv <= 6) lnrows_reg_kernel<6, 1><<<grid(1), wpb * 32, 0, st>>>(d);
+  else if (nv <= 12) lnrows_reg_kernel<12, 1><<<grid(1), wpb * 32, 0, st>>>(d);
+  else lnrows_kernel<<<grid_for(d.rows, wpb), wpb * 32, 0, st>>>(d);
   SVX_LAUNCH_OK("lnrows_kernel");
   return 0;
 }

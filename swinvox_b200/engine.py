@@ -250,6 +250,7 @@ class Plan:
         self.keep = {}
         self.op_names = []
         self.flops = []
+        self.bytes = []   # algorithmic HBM bytes per op: every operand read once, every result written once
         self.taps = {}   # name -> Act of selected intermediates (parity tests / debugging)
 
     def __del__(self):
@@ -308,11 +309,12 @@ class Plan:
     def num_launches(self):
         return self.lib.svx_plan_num_launches(self.handle)
 
-    def _add(self, op, desc, name, flops=0.0):
+    def _add(self, op, desc, name, flops=0.0, nbytes=0.0):
         add = getattr(self.lib, _lib.OPS[op][1])
         _lib.check(add(self.handle, C.byref(desc)), self.lib)
         self.op_names.append(name or op)
         self.flops.append(flops)
+        self.bytes.append(float(nbytes))
 
     # ---- concurrency hints -----------------------------------------------------------------------
     def lane(self, k):
@@ -325,6 +327,7 @@ class Plan:
         _lib.check(self.lib.svx_plan_add_join(self.handle), self.lib)
         self.op_names.append("join")
         self.flops.append(0.0)
+        self.bytes.append(0.0)
 
     # ---- contractions ------------------------------------------------------------------------
     def _taps_tensor(self, taps):
@@ -408,7 +411,9 @@ class Plan:
                             res_via_mma=res_via_mma)
         if pool8:
             d.epi_mode = EPI_POOL8
-        self._add("gemm", d, name or "linear", 2.0 * d.M * pack.N * pack.K)
+        n_out = pack.N // 8 if pool8 else pack.N
+        self._add("gemm", d, name or "linear", 2.0 * d.M * pack.N * pack.K,
+                  4.0 * (d.M * pack.K + d.M * n_out * (2 if residual is not None else 1) + pack.N * pack.K))
         return out
 
     def conv(self, x, pack, taps, out, stride=(1, 1, 1), out_map=None, rows_dhw=None, act=ACT_NONE, act_param=0.0,
@@ -427,7 +432,8 @@ class Plan:
             d.epi_aux = self.hold(aux).data_ptr()
             d.epi_out2 = self.hold(out2).data_ptr()
             d.o2_base, d.o2_sn, d.o2_sd, d.o2_sh, d.o2_sw = map2
-        self._add("gemm", d, name or "conv", 2.0 * d.M * pack.N * pack.K)
+        self._add("gemm", d, name or "conv", 2.0 * d.M * pack.N * pack.K,
+                  4.0 * (x.pixels * x.C + d.M * pack.N * (2 if residual is not None else 1) + pack.N * pack.K))
         return out
 
     def convT_fused(self, x, pack, out, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True, out_scale=1.0,
@@ -456,7 +462,9 @@ class Plan:
             d.o2_base, d.o2_sn, d.o2_sd, d.o2_sh, d.o2_sw = 0, od * oh * ow, 2 * oh * ow, 2 * ow, 2
             d.c2_sd, d.c2_sh, d.c2_sw = oh * ow, ow, 1
         # useful work only: 8 of the 27 taps feed each class
-        self._add("gemm", d, name or "convT_fused", 2.0 * d.M * pack.N * 8 * x.C)
+        self._add("gemm", d, name or "convT_fused", 2.0 * d.M * pack.N * 8 * x.C,
+                  4.0 * (x.pixels * x.C + d.M * (8 * 10 if tail else pack.N * (2 if residual is not None else 1))
+                         + pack.N * pack.K))
         return out
 
     def conv_flat(self, x, pack, taps, out, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True,
@@ -484,7 +492,8 @@ class Plan:
         self.keep[id(host)] = host
         d.taps_host = C.cast(host, C.c_void_p)
         self._fill_epilogue(d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out)
-        self._add("gemm", d, name or "conv_flat", 2.0 * x.N * vD * vH * vW * pack.N * pack.K)
+        self._add("gemm", d, name or "conv_flat", 2.0 * x.N * vD * vH * vW * pack.N * pack.K,
+                  4.0 * (x.N * vD * vH * vW * (cin + pack.N * (2 if residual is not None else 1)) + pack.N * pack.K))
         return out
 
     def conv3_slab(self, x, pack, out, cin_live, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True,
@@ -507,7 +516,8 @@ class Plan:
         d.ntaps = 27
         d.cin_live = cin_live
         self._fill_epilogue(d, pack, out, None, act, act_param, residual, res_after_act, out_scale, round_out)
-        self._add("gemm", d, name or "conv3_slab", 2.0 * d.M * 27 * cin_live * pack.N)
+        self._add("gemm", d, name or "conv3_slab", 2.0 * d.M * 27 * cin_live * pack.N,
+                  4.0 * d.M * (cin_live + pack.N * (2 if residual is not None else 1)))
         return out
 
     # ---- everything else ------------------------------------------------------------------------
@@ -524,7 +534,7 @@ class Plan:
         d.pad_d, d.pad_h, d.pad_w = pads
         d.OD, d.OH, d.OW, d.Kpad = OD, OH, OW, kpad
         d.round_tf32 = 1 if round_out else 0
-        self._add("im2col", d, name)
+        self._add("im2col", d, name, 0.0, 4.0 * (N * Cin * dhw[0] * dhw[1] * dhw[2] + out.pixels * kpad))
         return out
 
     def pool(self, x, out, kernel, stride, pads, mode, round_out=False, name=None):
@@ -538,7 +548,7 @@ class Plan:
         d.OD, d.OH, d.OW = out.D, out.H, out.W
         d.mode = mode
         d.round_tf32 = 1 if round_out else 0
-        self._add("pool", d, name)
+        self._add("pool", d, name, 0.0, 4.0 * x.C * (x.pixels + out.pixels))
         return out
 
     def layernorm_rows(self, x, gamma, beta, out, merge_hw=None, eps=1e-5, round_out=True, name=None):
@@ -550,7 +560,7 @@ class Plan:
             d.merge, d.H, d.W = 1, merge_hw[0], merge_hw[1]
         d.eps = eps
         d.round_tf32 = 1 if round_out else 0
-        self._add("layernorm_rows", d, name)
+        self._add("layernorm_rows", d, name, 0.0, 8.0 * out.pixels * out.C)
         return out
 
     def layernorm_sample(self, x, gamma, beta, out, eps=1e-5, round_out=True, name=None):
@@ -560,7 +570,7 @@ class Plan:
         d.N, d.L = x.N, x.D * x.H * x.W * x.Cs
         d.eps = eps
         d.round_tf32 = 1 if round_out else 0
-        self._add("layernorm_sample", d, name)
+        self._add("layernorm_sample", d, name, 0.0, 8.0 * d.N * d.L)
         return out
 
     def window_attention(self, qkv, out, bias, H, W, heads, shift, scale, round_out=True, name=None):
@@ -568,7 +578,7 @@ class Plan:
         d.qkv, d.out, d.bias = self.hold(qkv).buf.data_ptr(), self.hold(out).buf.data_ptr(), self.hold(bias).data_ptr()
         d.N, d.H, d.W, d.C, d.heads, d.shift, d.scale = qkv.N, H, W, out.C, heads, shift, scale
         d.round_tf32 = 1 if round_out else 0
-        self._add("window_attention", d, name, 4.0 * qkv.N * H * W * 49 * out.C)
+        self._add("window_attention", d, name, 4.0 * qkv.N * H * W * 49 * out.C, 16.0 * qkv.N * H * W * out.C)
         return out
 
     def dwconv(self, x, w, bias, out, k, round_out=True, name=None):
@@ -601,7 +611,7 @@ class Plan:
         d = _lib.MergeFuseDesc()
         d.weights, d.coarse, d.out = self.hold(weights).data_ptr(), self.hold(coarse).data_ptr(), self.hold(out).data_ptr()
         d.B, d.V, d.P = B, V, P
-        self._add("merger_fuse", d, name)
+        self._add("merger_fuse", d, name, 0.0, 4.0 * (2 * V + 1) * B * P)
         return out
 
     def voxel_metrics(self, logits, gt, thresholds, counts, B, P, name=None):
@@ -609,7 +619,7 @@ class Plan:
         d.logits, d.gt, d.prob_thresholds, d.counts = (self.hold(logits).data_ptr(), self.hold(gt).data_ptr(),
                                                        self.hold(thresholds).data_ptr(), self.hold(counts).data_ptr())
         d.B, d.P, d.T = B, P, thresholds.numel()
-        self._add("voxel_metrics", d, name)
+        self._add("voxel_metrics", d, name, 0.0, 8.0 * B * P)
         return counts
 
     def transpose(self, src, dst, N, Cc, P, Cs, to_channels_last, round_out=False, name=None):
@@ -618,7 +628,7 @@ class Plan:
         d.N, d.C, d.P, d.Cs = N, Cc, P, Cs
         d.to_channels_last = 1 if to_channels_last else 0
         d.round_tf32 = 1 if round_out else 0
-        self._add("transpose", d, name)
+        self._add("transpose", d, name, 0.0, 4.0 * N * P * (Cc + Cs))
         return dst
 
 

@@ -398,6 +398,31 @@ def test_layernorms(dev):
                    F.layer_norm(xs.double(), (7, 7, 768), gs.double(), bs.double())) < 1e-5
 
 
+@pytest.mark.parametrize("rows,C,merge", [(1, 96, False), (1001, 96, False), (333, 192, False), (77, 384, False),
+                                          (50, 768, False), (13, 2048, False), (None, 384, True), (None, 768, True),
+                                          (None, 1536, True), (7, 100, False)])
+def test_layernorm_rows_widths(dev, rows, C, merge):
+    """every register-resident variant of the row LayerNorm (C / 128 float4 per lane) + ragged row counts"""
+    DEV = dev
+    torch.manual_seed(C + (rows or 0))
+    p = E.Plan(DEV)
+    g, b = torch.rand(C) + 0.5, torch.randn(C)
+    if merge:
+        n, H = 3, 6
+        xm = torch.randn(n, H, H, C // 4) * 1.5 + 0.3
+        o = p.new_act(n, 1, H // 2, H // 2, C)
+        p.layernorm_rows(E.Act(xm.view(-1, C // 4).to(DEV), n, 1, H, H, C // 4), g.to(DEV), b.to(DEV), o, merge_hw=(H, H),
+                         round_out=False)
+        ref_in = torch.cat([xm[:, 0::2, 0::2], xm[:, 1::2, 0::2], xm[:, 0::2, 1::2], xm[:, 1::2, 1::2]], -1).reshape(-1, C)
+    else:
+        ref_in = torch.randn(rows, C) * 2 + 0.5
+        o = p.new_act(rows, 1, 1, 1, C)
+        p.layernorm_rows(E.Act(ref_in.to(DEV), rows, 1, 1, 1, C), g.to(DEV), b.to(DEV), o, round_out=False)
+    p.run()
+    sync(DEV)
+    assert rel_err(o.view().reshape(-1, C), F.layer_norm(ref_in.double(), (C,), g.double(), b.double())) < 1e-5
+
+
 @pytest.mark.parametrize("H,heads,shift", [(14, 3, 0), (14, 3, 3), (7, 6, 0), (28, 2, 3)])
 def test_window_attention(dev, H, heads, shift):
     DEV = dev

@@ -144,6 +144,64 @@ def test_batched_multi_view_parity_gpu():
     assert torch.equal(final2, final)
 
 
+def _forward(prod, images):
+    with torch.no_grad():
+        f = prod["encoder"](images)
+        raw, gen = prod["decoder"](f)
+        return prod["refiner"](prod["merger"](raw, gen))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("V", [1, 5, 20, 24])
+def test_view_sweep_parity_gpu(V):
+    """BASELINE configs[2..4]: 5 views with cross-view attention, 20 views, and the ends of the 1..24 view sweep --
+    one object each against the oracle (the views of an object meet in CVA's softmax over views and the merger)"""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = M.default_cfg()
+    images = FX.structured_inputs(1, V, seed=100 + V)
+    ref = oracle_forward(FX.build(cfg, "calibrated", 0), images)
+    prod = FX.build(cfg, "calibrated", 0, PRODUCT)
+    for m in prod.values():
+        m.cuda()
+    final = _forward(prod, images.cuda())
+    torch.cuda.synchronize()
+    stage_check(f"refiner V={V}", final, ref["final"])
+    voxel_check(final, ref["final"], FX.seeded_gt(1))
+
+
+@pytest.mark.gpu
+def test_full_size_properties_gpu():
+    """BASELINE configs[1] at full size (64 objects x 3 views), through properties that need no oracle run:
+    objects are independent (an object's logits do not depend on its batch mates), and the result is invariant
+    under a permutation of an object's views (CVA is permutation-equivariant, the merger's softmax-weighted sum is
+    permutation-invariant: cross_view_attention.py:81-99, merger.py:98-104)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = M.default_cfg()
+    prod = FX.build(cfg, "calibrated", 0, PRODUCT)
+    for m in prod.values():
+        m.cuda()
+    g = torch.Generator().manual_seed(9)
+    images = (torch.rand(64, 3, 3, 224, 224, generator=g) * 2 - 1).cuda()
+    full = _forward(prod, images).clone()
+    assert torch.isfinite(full).all()
+    pair = _forward(prod, images[5:7].contiguous()).clone()
+    scale = full.abs().max().item()
+    assert (full[5:7] - pair).abs().max().item() <= 1e-5 * scale
+    perm = _forward(prod, images[:, [2, 0, 1]].contiguous()).clone()
+    assert (perm - full).abs().max().item() <= 2e-4 * scale
+    # threshold counters of the full batch: bit-exact against the same logits counted by torch (core/test.py:141-164)
+    from swinvox_b200.metrics import VoxelMetrics
+    gt = (torch.rand(64, 32, 32, 32, generator=g) < 0.1).float().cuda()
+    counts = VoxelMetrics(cfg.TEST.VOXEL_THRESH).counts(full, gt).cpu()
+    for ti, th in enumerate(cfg.TEST.VOXEL_THRESH):
+        v = (torch.sigmoid(full) >= th).float()
+        inter = (v * gt).flatten(1).sum(1).cpu().long()
+        union = ((v + gt) >= 1).flatten(1).sum(1).cpu().long()
+        assert torch.equal(counts[:, ti, 0].long(), inter) and torch.equal(counts[:, ti, 1].long(), union)
+
+
 def test_eval_only_guards(dev):
     cfg = M.default_cfg()
     ref = Refiner(cfg).to(dev)
