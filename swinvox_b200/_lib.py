@@ -117,6 +117,16 @@ class TransposeDesc(C.Structure):
     ]
 
 
+class BinvoxDecodeDesc(C.Structure):
+    _fields_ = [("payload", ptr), ("offsets", ptr), ("out", ptr), ("status", ptr),
+                ("B", i32), ("d0", i32), ("d1", i32), ("d2", i32), ("fix_coords", i32)]
+
+
+class BinvoxEncodeDesc(C.Structure):
+    _fields_ = [("volume", ptr), ("threshold", f32), ("payload", ptr), ("nbytes", ptr),
+                ("B", i32), ("d0", i32), ("d1", i32), ("d2", i32), ("axis_xyz", i32)]
+
+
 # order must match svx_desc_sizes()
 DESC_TYPES = [GemmDesc, Im2colDesc, PoolDesc, LnRowsDesc, LnSampleDesc, WinAttnDesc, DwConvDesc,
               ViewAttnDesc, BilinearDesc, MergeFuseDesc, MetricsDesc, TransposeDesc]
@@ -142,6 +152,8 @@ OTHER_SYMBOLS = ["svx_abi_version", "svx_last_error", "svx_desc_sizes", "svx_dev
                  "svx_plan_time_ops", "svx_plan_num_launches", "svx_plan_set_lane", "svx_plan_add_join"]
 
 ALL_SYMBOLS = OTHER_SYMBOLS + [s for v in OPS.values() for s in v[:2]]
+# data-format entry points (svx_io.cu): present in the CUDA library only (the CPU twin of the tests has no copy)
+IO_SYMBOLS = {"svx_binvox_decode": BinvoxDecodeDesc, "svx_binvox_encode": BinvoxEncodeDesc}
 
 
 class SvxError(RuntimeError):
@@ -174,6 +186,11 @@ def bind(path):
     lib.svx_plan_add_join.argtypes = [ptr]
     lib.svx_desc_sizes.argtypes = [C.POINTER(i32), C.c_int]
     lib.svx_device_info.argtypes = [C.c_int, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    for name, desc_t in IO_SYMBOLS.items():
+        if hasattr(lib, name):
+            getattr(lib, name).argtypes = [C.POINTER(desc_t), ptr]
+        elif os.path.abspath(path) == os.path.abspath(LIB_PATH):
+            raise SvxError(f"{path} does not export {name}")
     for imm, add, desc_t in OPS.values():
         getattr(lib, imm).argtypes = [C.POINTER(desc_t), ptr]
         getattr(lib, add).argtypes = [ptr, C.POINTER(desc_t)]

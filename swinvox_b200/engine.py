@@ -26,7 +26,7 @@ def tf32_round(t):
     return bits.view(torch.float32)
 
 
-def choose_block_n(n, rows=None, gather=False):
+def choose_block_n(n, rows=None, gather=False, heavy_epilogue=False):
     """N tile of one contraction.  Measured on B200 (profiles/r1_gemm_bench_v6.log): the widest tile that divides N
     wins as long as the grid still fills the 148 SMs for a few waves; gather-mode convolutions re-fetch their A tile
     once per N tile, so they take the widest tile regardless."""
@@ -37,6 +37,10 @@ def choose_block_n(n, rows=None, gather=False):
     if n <= 64:
         return 64
     cands = [bn for bn in (256, 192, 128, 96) if n % bn == 0] or [128 if n > 96 else 96]
+    if heavy_epilogue and n % 96 == 0:
+        # erf-GELU epilogues are bound by instruction issue in the epilogue warps (profiles/r1_ncu_swin_block_v17.txt):
+        # the 96-wide tile runs two CTAs per SM, i.e. twice the epilogue warps per SM
+        return 96
     if rows is None:
         return cands[0] if gather else ([bn for bn in cands if bn <= 192] or cands)[0]
     tiles_m = (rows + 127) // 128
@@ -106,10 +110,10 @@ class WeightPack:
         if block_n is not None:
             self.finalize()
 
-    def finalize(self, rows=None, gather=False):
+    def finalize(self, rows=None, gather=False, heavy_epilogue=False):
         if self.W is not None:
             return self
-        bn = self.block_n or choose_block_n(self.N, rows, gather)
+        bn = self.block_n or choose_block_n(self.N, rows, gather, heavy_epilogue)
         n, k = self.raw_W.shape
         npad, kpad = round_up(max(n, self.N), bn), round_up(k, 32)
         if (npad, kpad) == (n, k):
@@ -361,7 +365,7 @@ class Plan:
 
     def _fill_epilogue(self, d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out,
                        res_via_mma=False):
-        pack.finalize(rows=d.M, gather=(d.a_mode == A_GATHER))
+        pack.finalize(rows=d.M, gather=(d.a_mode == A_GATHER), heavy_epilogue=(act == ACT_GELU))
         d.W = pack.W.data_ptr()
         if res_via_mma:
             # the residual is added by the tensor cores: block_n identity columns appended to every weight row
