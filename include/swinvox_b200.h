@@ -201,10 +201,15 @@ typedef struct svx_mergefuse_desc {
 
 /* sigmoid -> threshold -> I/U/TP/FP/FN per object (core/test.py:141-164).
  * logits, gt: [B, P] (gt holds {0,1}); prob_thresholds: device float[T] (cfg.TEST.VOXEL_THRESH);
- * counts: int32[B, T, 5] = {I,U,TP,FP,FN}, zeroed by the launch itself (cudaMemsetAsync). */
+ * counts: int32[B, T, 5] = {I,U,TP,FP,FN}, zeroed by the launch itself (cudaMemsetAsync).
+ * bce_q20 (optional): int64[B], per object the sum over voxels of BCEWithLogits(logit, gt) =
+ * max(x,0) - x*gt + log1p(exp(-|x|)) (the EDLoss / RLoss of core/test.py:133-139 before the mean and the *10), in
+ * fixed point with 20 fractional bits so that the atomic accumulation is order-independent; zeroed by the launch. */
 typedef struct svx_metrics_desc {
   const float* logits; const float* gt; const float* prob_thresholds; int32_t* counts;
   int32_t B, P, T;
+  int32_t reserved0;
+  int64_t* bce_q20;
 } svx_metrics_desc;
 
 /* layout change [N, C, P] (planar) <-> [N, P, Cs] (channels-last, first C of Cs channels) */

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libswinvox_b200.so")
+# SVX_LIB_PATH: an instrumented build of the same sources (tools/probes/slab_profile.sh); never a different backend
+LIB_PATH = os.environ.get("SVX_LIB_PATH") or os.path.join(_HERE, "libswinvox_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU = 0, 1, 2, 3
 A_PLAIN, A_GATHER, A_FLAT, A_SLAB3, A_IM2COL = 0, 1, 2, 3, 4
@@ -106,7 +107,7 @@ class MergeFuseDesc(C.Structure):
 class MetricsDesc(C.Structure):
     _fields_ = [
         ("logits", ptr), ("gt", ptr), ("prob_thresholds", ptr), ("counts", ptr),
-        ("B", i32), ("P", i32), ("T", i32),
+        ("B", i32), ("P", i32), ("T", i32), ("reserved0", i32), ("bce_q20", ptr),
     ]
 
 

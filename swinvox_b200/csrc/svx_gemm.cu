@@ -688,14 +688,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 //   * finishes out[u, co] = D[u, 0, co] + D[u+1, 1, co] + D[u+2, 2, co] in the epilogue with warp shuffles (rows
 //     are TMEM lanes); the two rows that cross a warp's lane quarter go through a small smem exchange, and tiles
 //     overlap by two rows.
-//   * folds kd into N as well: a slab feeds three consecutive output depths, whose accumulators are neighbours in a
-//     TMEM ring, so each (kh, k-step) is ONE MMA with N = 144 for all three (see the issuer loop).
-// Weights ([48, 9*32], row = kw*16+co, col = (kd*3+kh)*32 + c) stay resident in smem, regrouped so the three kd blocks
-// of one kh are consecutive rows; ten accumulators ring in TMEM so the epilogue of one depth overlaps later MMAs.
+// Weights ([48, 9*32], row = kw*16+co, col = (kd*3+kh)*32 + c) stay resident in smem; eight accumulators ring
+// in TMEM so the epilogue of one depth overlaps the MMAs of the next.
 // =====================================================================================================
 constexpr int S3_ROWS = 200;                       // slab rows: 128 + 2*Wp <= 200  (Wp <= 36)
 constexpr int S3_N = 48;                           // MMA N: 3 kw groups x 16 output channels
-constexpr int S3_NACC = 10, S3_ACC_STRIDE = 48;    // TMEM: ring of 10 accumulators of 48 columns, descending depth order
+constexpr int S3_NACC = 8, S3_ACC_STRIDE = 64;     // TMEM: 8 accumulators of 48 (stride 64) columns
 constexpr int S3_STEP = BM - 2;                    // valid rows per tile
 constexpr int S3_THREADS = 320;                    // warps 0-3 / 6-9: two epilogue sets, 4: TMA, 5: MMA
 constexpr int S3_XCHG_BYTES = 2 * BM * 128;        // per epilogue set: 128 rows x (D1[16] | D2[16]) staged for the row shift
@@ -763,9 +761,7 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     // ---- TMA producer: weights once, then one slab per (unit, plane) ---------------------------------
     if (elect_one()) {
       mbar_arrive_expect_tx(w_full, S3_W_BYTES);
-      // global column block t = kd*3 + kh lands in slot kh*3 + kd: the three kd blocks of one kh form one [144, K] matrix
-      for (int t = 0; t < 9; ++t)
-        tma_load_2d(w_smem + ((t % 3) * 3 + t / 3) * S3_TAP_BYTES, &map_w, w_full, t * BK, 0);   // first kBoxCh of the 32
+      for (int t = 0; t < 9; ++t) tma_load_2d(w_smem + t * S3_TAP_BYTES, &map_w, w_full, t * BK, 0);   // first kBoxCh of the 32
       uint32_t g = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int n = unit / ncol, col = unit - n * ncol;
@@ -780,61 +776,42 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
     __syncwarp();
   } else if (warp == 5) {
-    // ---- MMA issuer: marches over the SLABS of a unit.  Slab s feeds output depths s (kd = 0), s-1 (kd = 1) and
-    // s-2 (kd = 2); the accumulators of consecutive depths sit side by side in TMEM in DESCENDING depth order, so one
-    // MMA per (kh, k-step) with the kd blocks stacked in N (N = 144 = 3 kd x 3 kw x 16 co) updates all three.  A
-    // tcgen05.mma of this shape costs the same ~100 cycles whatever N is (the 128-row A operand is read from shared
-    // memory), so this issues 3*ksteps + 1 instructions per slab instead of 9*ksteps (profiles/r1_ncu_merger_v17.txt:
-    // the issuing thread was the bottleneck, every other warp waited on it).  The depth that a slab opens (kd = 0)
-    // must start from zero: its first MMA is issued on its own with accumulate = 0. -----------------------------
+    // ---- MMA issuer -----------------------------------------------------------------------------------
     if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BM, S3_N);
       const int ksteps = (p.cin_live + UMMA_K - 1) / UMMA_K;
       mbar_wait(w_full, 0u);
       tc_fence_after();
-      uint32_t g = 0, tg0 = 0;   // g: slab counter (ring position), tg0: tile counter of the unit's depth 0
-      auto acc_col = [&](uint32_t tg) { return (S3_NACC - 1u - tg % S3_NACC) * S3_ACC_STRIDE; };
+      uint32_t sbase = 0, waited = 0, tg = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-        for (int sl = 0; sl < nd + 2; ++sl, ++g) {
-          mbar_wait(slab_full(g % S3_NSLAB), (g / S3_NSLAB) & 1u);
-          const int kd_lo = sl - (nd - 1) > 0 ? sl - (nd - 1) : 0, kd_hi = sl < 2 ? sl : 2;
-          if (sl < nd) {   // this slab opens depth sl: its ring slot must have been drained
-            const uint32_t tg = tg0 + sl;
-            mbar_wait(acc_empty(tg % S3_NACC), ((tg / S3_NACC) & 1u) ^ 1u);
+        for (int d = 0; d < nd; ++d, ++tg) {
+          while (waited < sbase + d + 3) {   // slabs d, d+1, d+2 of this unit
+            mbar_wait(slab_full(waited % S3_NSLAB), (waited / S3_NSLAB) & 1u);
+            ++waited;
           }
+          const uint32_t a = tg % S3_NACC;
+          mbar_wait(acc_empty(a), ((tg / S3_NACC) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t slab = slab_smem + (g % S3_NSLAB) * S3_SLAB_BYTES;
-          // issue kd range [a, b] of one (kh, k) step; the ring wraps between depth tg0+sl-kd and its successor when
-          // (tg0 + sl - kd) % S3_NACC == 0, where the columns stop being contiguous
-          auto issue = [&](int a, int b, int kh, int k, uint32_t accum) {
-            const uint64_t da = (ROWB == 128 ? umma_desc_sw128(slab + kh * Wp * ROWB) : umma_desc_sw64(slab + kh * Wp * ROWB)) + 2u * k;
-            int lo = a;
-            while (lo <= b) {
-              int hi = lo;
-              while (hi < b && (tg0 + sl - hi) % S3_NACC != 0) ++hi;   // depth (sl-hi) -> (sl-hi-1) stays contiguous
-              const uint32_t wb = w_smem + (kh * 3 + lo) * S3_TAP_BYTES;
-              const uint64_t db = (ROWB == 128 ? umma_desc_sw128(wb) : umma_desc_sw64(wb)) + 2u * k;
-              const uint32_t acc = tmem_base + acc_col(tg0 + sl - lo);
-              const int nblk = hi - lo + 1;
-              const uint32_t idesc = nblk == 1 ? umma_idesc_tf32(BM, S3_N) : nblk == 2 ? umma_idesc_tf32(BM, 2 * S3_N)
-                                                                                         : umma_idesc_tf32(BM, 3 * S3_N);
-              umma_tf32(acc, da, db, idesc, accum);
-              lo = hi + 1;
-            }
-          };
-          for (int kh = 0; kh < 3; ++kh) {
-            for (int k = 0; k < ksteps; ++k) {
-              if (kh == 0 && k == 0 && kd_lo == 0) {
-                issue(0, 0, 0, 0, 0u);                       // opens depth sl
-                if (kd_hi >= 1) issue(1, kd_hi, 0, 0, 1u);
-              } else {
-                issue(kd_lo, kd_hi, kh, k, 1u);
-              }
+          const uint32_t acc = tmem_base + a * S3_ACC_STRIDE;
+          for (int kd = 0; kd < 3; ++kd) {
+            const uint32_t slab = slab_smem + ((sbase + d + kd) % S3_NSLAB) * S3_SLAB_BYTES;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              const uint64_t da = ROWB == 128 ? umma_desc_sw128(slab + kh * Wp * ROWB) : umma_desc_sw64(slab + kh * Wp * ROWB);
+              const uint64_t db = ROWB == 128 ? umma_desc_sw128(w_smem + (kd * 3 + kh) * S3_TAP_BYTES)
+                                              : umma_desc_sw64(w_smem + (kd * 3 + kh) * S3_TAP_BYTES);
+              for (int k = 0; k < ksteps; ++k)
+                umma_tf32(acc, da + 2u * k, db + 2u * k, idesc, (kd | kh | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit(slab_empty(g % S3_NSLAB));             // each slab is consumed by exactly one step
-          if (sl >= 2) umma_commit(acc_full((tg0 + sl - 2) % S3_NACC));   // depth sl-2 has all three planes
+          umma_commit(slab_empty((sbase + d) % S3_NSLAB));   // plane d is not needed by later depths
+          if (d == nd - 1) {
+            umma_commit(slab_empty((sbase + d + 1) % S3_NSLAB));
+            umma_commit(slab_empty((sbase + d + 2) % S3_NSLAB));
+          }
+          umma_commit(acc_full(a));
         }
-        tg0 += nd;
+        sbase += nd + 2;
       }
     }
     __syncwarp();
@@ -870,7 +847,7 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const uint32_t a = tg % S3_NACC;
         mbar_wait(acc_full(a), (tg / S3_NACC) & 1u);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (S3_NACC - 1u - a) * S3_ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
+        const uint32_t taddr = tmem_base + a * S3_ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
         uint32_t d0[16], d1[16], d2[16];
         __syncwarp();
         tmem_ld16(taddr, d0);

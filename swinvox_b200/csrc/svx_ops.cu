@@ -646,6 +646,9 @@ __global__ void mergefuse_kernel(const svx_mergefuse_desc d, long long total4) {
 constexpr int kMaxThresh = 8;
 __global__ void __launch_bounds__(256) metrics_kernel(const svx_metrics_desc d, int chunks) {
   __shared__ int sacc[kMaxThresh * 5];
+  __shared__ unsigned long long sbce;
+  if (threadIdx.x == 0) sbce = 0ull;
+  long long bce = 0;
   const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
   for (int i = threadIdx.x; i < kMaxThresh * 5; i += blockDim.x) sacc[i] = 0;
   __syncthreads();
@@ -660,13 +663,22 @@ __global__ void __launch_bounds__(256) metrics_kernel(const svx_metrics_desc d, 
   const float* lg = d.logits + (long long)b * d.P;
   const float* gt = d.gt + (long long)b * d.P;
   for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
-    const float prob = 1.f / (1.f + expf(-lg[i]));
+    const float x = lg[i];
+    const float prob = 1.f / (1.f + expf(-x));
     const int g = gt[i] != 0.f;
 #pragma unroll
     for (int t = 0; t < kMaxThresh; ++t) {
       const int v = prob >= th[t];
       cI[t] += v & g; cU[t] += v | g; cFP[t] += v & (g ^ 1); cFN[t] += (v ^ 1) & g;
     }
+    if (d.bce_q20) {   // torch's stable form of BCEWithLogits, quantised per voxel to 2^-20
+      const float l = fmaxf(x, 0.f) - x * gt[i] + log1pf(expf(-fabsf(x)));
+      bce += __float2ll_rn(l * 1048576.f);
+    }
+  }
+  if (d.bce_q20) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bce += __shfl_xor_sync(0xffffffffu, bce, o);
   }
 #pragma unroll
   for (int t = 0; t < kMaxThresh; ++t) {
@@ -682,8 +694,10 @@ __global__ void __launch_bounds__(256) metrics_kernel(const svx_metrics_desc d, 
       atomicAdd(&sacc[t * 5 + 3], fp); atomicAdd(&sacc[t * 5 + 4], fn);
     }
   }
+  if (d.bce_q20 && (threadIdx.x & 31) == 0) atomicAdd(&sbce, (unsigned long long)bce);
   __syncthreads();
   for (int i = threadIdx.x; i < d.T * 5; i += blockDim.x) atomicAdd(d.counts + (long long)b * d.T * 5 + i, sacc[i]);
+  if (d.bce_q20 && threadIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(d.bce_q20) + b, sbce);
 }
 
 // ---- [N,C,P] <-> [N,P,Cs] ------------------------------------------------------------------------------
@@ -844,6 +858,7 @@ int metrics_launch(const svx_metrics_desc& d, void* stream) {
   SVX_REQUIRE(d.logits && d.gt && d.prob_thresholds && d.counts && d.T >= 1 && d.T <= kMaxThresh && d.B > 0 && d.P > 0,
               "voxel_metrics: supports 1..%d thresholds", kMaxThresh);
   SVX_CUDA_OK(cudaMemsetAsync(d.counts, 0, sizeof(int32_t) * (size_t)d.B * d.T * 5, (cudaStream_t)stream));
+  if (d.bce_q20) SVX_CUDA_OK(cudaMemsetAsync(d.bce_q20, 0, sizeof(int64_t) * (size_t)d.B, (cudaStream_t)stream));
   int chunks = (2 * kSmCount + d.B - 1) / d.B;
   if (chunks < 1) chunks = 1;
   const int max_chunks = (d.P + 2047) / 2048;

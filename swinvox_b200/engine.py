@@ -618,8 +618,10 @@ class Plan:
         self._add("merger_fuse", d, name, 0.0, 4.0 * (2 * V + 1) * B * P)
         return out
 
-    def voxel_metrics(self, logits, gt, thresholds, counts, B, P, name=None):
+    def voxel_metrics(self, logits, gt, thresholds, counts, B, P, name=None, bce=None):
         d = _lib.MetricsDesc()
+        if bce is not None:
+            d.bce_q20 = self.hold(bce).data_ptr()
         d.logits, d.gt, d.prob_thresholds, d.counts = (self.hold(logits).data_ptr(), self.hold(gt).data_ptr(),
                                                        self.hold(thresholds).data_ptr(), self.hold(counts).data_ptr())
         d.B, d.P, d.T = B, P, thresholds.numel()

@@ -12,12 +12,20 @@ class VoxelMetrics:
         self.thresholds = [float(t) for t in thresholds]
         self._plans = {}
 
-    def counts(self, logits, gt):
+    def counts_and_bce(self, logits, gt):
+        """-> (counts int32 [B,T,5], bce fp64 [B]): bce[b] = mean over voxels of BCEWithLogits(logits[b], gt[b]), the
+        per-sample EDLoss / RLoss of core/test.py:133-139 before its factor 10 (batch size 1 there)"""
+        counts = self.counts(logits, gt, want_bce=True)
+        key = self._last_key
+        return counts, self._plans[key][2].to(torch.float64) / (1048576.0 * logits[0].numel())
+
+    def counts(self, logits, gt, want_bce=False):
         """logits, gt: [B,32,32,32] (or [B,P]) fp32 on the GPU -> int32 [B, T, 5] = I, U, TP, FP, FN (device)"""
         require_device(logits)
         B = logits.shape[0]
         P = logits[0].numel()
-        key = (B, P, str(logits.device), logits.data_ptr(), gt.data_ptr())
+        key = (B, P, str(logits.device), logits.data_ptr(), gt.data_ptr(), bool(want_bce))
+        self._last_key = key
         if key not in self._plans:
             plan = E.Plan(logits.device)
             th = torch.tensor(self.thresholds, dtype=torch.float32, device=logits.device)
@@ -25,11 +33,12 @@ class VoxelMetrics:
             lg, g = logits.reshape(B, P), gt.reshape(B, P)
             if not (lg.is_contiguous() and g.is_contiguous()):
                 raise ValueError("VoxelMetrics needs contiguous logits / ground truth")
-            plan.voxel_metrics(lg, g, th, counts, B, P)
+            bce = plan.zeros(B, dtype=torch.int64) if want_bce else None
+            plan.voxel_metrics(lg, g, th, counts, B, P, bce=bce)
             if len(self._plans) > 8:
                 self._plans.clear()
-            self._plans[key] = (plan, counts)
-        plan, counts = self._plans[key]
+            self._plans[key] = (plan, counts, bce)
+        plan, counts, _ = self._plans[key]
         plan.run()
         return counts
 

@@ -493,6 +493,16 @@ int metrics_launch(const svx_metrics_desc& d, void*) {
       int32_t* c = d.counts + (b * d.T + t) * 5;
       c[0] = I; c[1] = U; c[2] = I; c[3] = FP; c[4] = FN;
     }
+  if (d.bce_q20)
+    for (long long b = 0; b < d.B; ++b) {
+      long long acc = 0;
+      for (int p = 0; p < d.P; ++p) {
+        const float x = d.logits[b * d.P + p];
+        const float l = fmaxf(x, 0.f) - x * d.gt[b * d.P + p] + log1pf(expf(-fabsf(x)));
+        acc += llrintf(l * 1048576.f);
+      }
+      d.bce_q20[b] = acc;
+    }
   return 0;
 }
 
