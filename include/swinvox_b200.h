@@ -70,7 +70,8 @@ enum { SVX_POOL_MAX = 0, SVX_POOL_AVG = 1 };
  *   SVX_A_IM2COL: the same implicit im2col as SVX_A_GATHER (same row / k / tap meaning, taps given in taps_host),
  *                 but fetched by the TMA unit in im2col mode (cuTensorMapEncodeIm2col over the NDHWC tensor, one
  *                 128-pixel x 32-channel box per (tap, channel chunk), borders zero-filled by the hardware).  Needs
- *                 Cin % 32 == 0; tap offsets and the implied padding must fit the descriptor's [-16, 15] corner range.
+ *                 Cin % 32 == 0, or Cin == 4 (image stems: one 16-byte pixel per tap, eight taps per k-chunk, Kpad may
+ *                 exceed K); tap offsets and the implied padding must fit the descriptor's [-16, 15] corner range.
  *   SVX_A_FLAT  : stride-1 convolution over a zero-PADDED channels-last tensor viewed as the matrix
  *                 [N*in_D*in_H*in_W, in_Cs] (in_* are the padded extents).  Row r is the flat padded position
  *                 of the window corner; tap t reads row r + (dd*in_H + dh)*in_W + dw (taps >= 0), streamed by

@@ -66,6 +66,7 @@ struct GemmParams {
   int cls_cout;             // SVX_EPI_CONVT8: channels per output-parity class
   long long c_sd, c_sh, c_sw, c2_sd, c2_sh, c2_sw;   // class-bit offsets in out / residual and in out2
   int i2c_lo_d, i2c_lo_h, i2c_lo_w;   // im2col mode: base-pixel coordinate of output 0 on each axis (= smallest tap)
+  int i2c_narrow, ntaps;              // 4-channel pixels (image stems): eight 16-byte taps per k-chunk, unswizzled A tile
   int flat_off[kMaxTaps];  // flat mode: row offset of each tap; im2col mode: tap offsets packed w | h << 8 | d << 16
 };
 
@@ -101,6 +102,53 @@ __device__ __forceinline__ float gelu_erf(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
   const float erf_abs = fmaf(-poly * t, e, 1.f);
   return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
+
+// The same GELU on two values at once with the packed fp32x2 pipe of sm_100 (FFMA2 / FMUL2): the erf-GELU epilogues are
+// bound by instruction issue in the epilogue warps (profiles/r1_ncu_hot_lines_v17.txt), packing halves the FMA-pipe
+// instructions per element; the two MUFU ops (rcp, ex2) per element stay scalar.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const uint64_t x = pack2(x0, x1);
+  const uint64_t ax = x & 0x7fffffff7fffffffull;
+  const uint64_t z = mul2(ax, pack2(0.70710678118654752440f, 0.70710678118654752440f));
+  // sqrt(log2 e) * |x| / sqrt 2: its square is z^2 * log2(e), the exponent of exp(-z^2) in base 2
+  const uint64_t zs = mul2(ax, pack2(0.84932180028801904272f, 0.84932180028801904272f));
+  const uint64_t den = fma2(pack2(0.3275911f, 0.3275911f), z, pack2(1.f, 1.f));
+  float d0, d1, t0, t1;
+  unpack2(den, d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t = pack2(t0, t1);
+  // Horner with NEGATED coefficients: npoly = -(a1 + t(a2 + t(a3 + t(a4 + t a5))))
+  uint64_t np = fma2(pack2(-1.061405429f, -1.061405429f), t, pack2(1.453152027f, 1.453152027f));
+  np = fma2(np, t, pack2(-1.421413741f, -1.421413741f));
+  np = fma2(np, t, pack2(0.284496736f, 0.284496736f));
+  np = fma2(np, t, pack2(-0.254829592f, -0.254829592f));
+  const uint64_t zz = mul2(zs, zs);
+  float q0, q1, e0, e1;
+  unpack2(zz, q0, q1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-q1));
+  const uint64_t erf_abs = fma2(mul2(np, t), pack2(e0, e1), pack2(1.f, 1.f));     // 1 - poly*t*exp(-z^2)
+  const uint64_t s = erf_abs | (x & 0x8000000080000000ull);                       // copysign (erf_abs >= 0)
+  const uint64_t hx = mul2(x, pack2(0.5f, 0.5f));
+  unpack2(fma2(hx, s, hx), x0, x1);
 }
 
 template <int ACT>
@@ -278,11 +326,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               i2c_n = t / p.out_D;
               i2c_w = i2c_w * p.sw + p.i2c_lo_w; i2c_h = i2c_h * p.sh + p.i2c_lo_h; i2c_d = i2c_d * p.sd + p.i2c_lo_d;
             }
-            const int tap = kc / p.chunks_per_tap;
-            const int cc = kc - tap * p.chunks_per_tap;
-            const int o = p.flat_off[tap];
-            tma_load_im2col_5d(a_dst, &map_a, full_bar(s), p.in_c0 + cc * BK, i2c_w, i2c_h, i2c_d, i2c_n,
-                               (uint16_t)(o & 255), (uint16_t)((o >> 8) & 255), (uint16_t)((o >> 16) & 255));
+            if (p.i2c_narrow) {
+              // 4-channel pixels: a k-chunk is eight taps, each its own 128-pixel x 16-byte box = one column of core
+              // matrices of the unswizzled K-major tile (taps past the filter re-read tap 0 against zero weights)
+#pragma unroll 1
+              for (int j = 0; j < 8; ++j) {
+                const int tap = kc * 8 + j;
+                const int o = p.flat_off[tap < p.ntaps ? tap : 0];
+                tma_load_im2col_5d(a_dst + j * (BM * 16), &map_a, full_bar(s), p.in_c0, i2c_w, i2c_h, i2c_d, i2c_n,
+                                   (uint16_t)(o & 255), (uint16_t)((o >> 8) & 255), (uint16_t)((o >> 16) & 255));
+              }
+            } else {
+              const int tap = kc / p.chunks_per_tap;
+              const int cc = kc - tap * p.chunks_per_tap;
+              const int o = p.flat_off[tap];
+              tma_load_im2col_5d(a_dst, &map_a, full_bar(s), p.in_c0 + cc * BK, i2c_w, i2c_h, i2c_d, i2c_n,
+                                 (uint16_t)(o & 255), (uint16_t)((o >> 8) & 255), (uint16_t)((o >> 16) & 255));
+            }
           } else {
             mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
           }
@@ -307,12 +367,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t a_addr = smem_base + s * C::kStageBytes;
-          const uint64_t da = umma_desc_sw128(a_addr);
+          const bool narrow = p.i2c_narrow != 0;
+          const uint64_t da = narrow ? umma_desc_nosw(a_addr, BM * 16, 128) : umma_desc_sw128(a_addr);
           const uint64_t db = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+          const uint32_t a_step = narrow ? (2u * BM * 16) >> 4 : 2u;   // two 16-byte K chunks per MMA: 2 boxes / 32 bytes
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 8 fp32 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-            umma_tf32(acc, da + 2u * k, db + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+            umma_tf32(acc, da + a_step * k, db + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(s));
         }
@@ -502,7 +564,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               break;
             case SVX_ACT_GELU:
 #pragma unroll
-              for (int q = 0; q < SLAB; ++q) x[q] = gelu_erf(x[q]);
+              for (int q = 0; q < SLAB; q += 2) gelu_erf2(x[q], x[q + 1]);
               break;
             default: break;
           }
@@ -1007,7 +1069,7 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 // im2col-mode map over the channels-last tensor [N, D, H, W, Cs]: boxes of 128 pixels x 32 channels, 128B swizzle.
 // lo / up: bounding-box corners of the base pixel per axis (d, h, w); str: convolution strides (d, h, w).
 int encode_im2col_map(CUtensorMap* map, const float* ptr, uint64_t N, uint64_t D, uint64_t H, uint64_t W, uint64_t Cs,
-                      const int lo[3], const int up[3], const int str[3]) {
+                      const int lo[3], const int up[3], const int str[3], bool narrow = false) {
   static EncodeIm2colFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -1021,8 +1083,10 @@ int encode_im2col_map(CUtensorMap* map, const float* ptr, uint64_t N, uint64_t D
   cuuint64_t strides[4] = {Cs * 4, W * Cs * 4, H * W * Cs * 4, D * H * W * Cs * 4};
   int lower[3] = {lo[2], lo[1], lo[0]}, upper[3] = {up[2], up[1], up[0]};   // the driver takes (w, h, d)
   cuuint32_t estr[5] = {1, (cuuint32_t)str[2], (cuuint32_t)str[1], (cuuint32_t)str[0], 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(ptr), dims, strides, lower, upper, BK, BM,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  // narrow: one 4-channel (16-byte) pixel per row, stored densely (no swizzle) = a column of 8x16B core matrices
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(ptr), dims, strides, lower, upper,
+                  narrow ? 4 : BK, BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  narrow ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail("cuTensorMapEncodeIm2col failed with CUresult %d (lo %d,%d,%d up %d,%d,%d)", (int)r, lo[0], lo[1], lo[2],
@@ -1117,8 +1181,9 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     p.chunks_per_tap = d.Cin / BK;
     if (encode_map(&g->map_a, d.A, (uint64_t)rows_total, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs, BM)) { delete g; return 1; }
   } else if (d.a_mode == SVX_A_IM2COL) {
-    bool ok = d.Cin > 0 && d.Cin % BK == 0 && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.ntaps > 0 && d.ntaps <= kMaxTaps &&
-              d.taps_host && d.K == d.ntaps * d.Cin && d.Kpad == d.K && d.in_D > 0 && d.in_H > 0 && d.in_W > 0 &&
+    const bool narrow = d.Cin == 4;
+    bool ok = d.Cin > 0 && (narrow || (d.Cin % BK == 0 && d.Kpad == d.K)) && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 &&
+              d.ntaps > 0 && d.ntaps <= kMaxTaps && d.taps_host && d.K == d.ntaps * d.Cin && d.in_D > 0 && d.in_H > 0 && d.in_W > 0 &&
               d.stride_d >= 1 && d.stride_h >= 1 && d.stride_w >= 1 && d.stride_d <= 8 && d.stride_h <= 8 && d.stride_w <= 8 &&
               d.M % (d.out_D * d.out_H * d.out_W) == 0;
     if (!ok) {
@@ -1147,9 +1212,11 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
       p.flat_off[t] = (d.taps_host[4 * t + 2] - lo[2]) | ((d.taps_host[4 * t + 1] - lo[1]) << 8) |
                       ((d.taps_host[4 * t] - lo[0]) << 16);
     p.i2c_lo_d = lo[0]; p.i2c_lo_h = lo[1]; p.i2c_lo_w = lo[2];
-    p.chunks_per_tap = d.Cin / BK;
+    p.chunks_per_tap = narrow ? 1 : d.Cin / BK;
+    p.i2c_narrow = narrow ? 1 : 0;
+    p.ntaps = d.ntaps;
     const uint64_t n_img = (uint64_t)(d.M / (d.out_D * d.out_H * d.out_W));
-    if (encode_im2col_map(&g->map_a, d.A, n_img, d.in_D, d.in_H, d.in_W, d.in_Cs, lo, up, str)) { delete g; return 1; }
+    if (encode_im2col_map(&g->map_a, d.A, n_img, d.in_D, d.in_H, d.in_W, d.in_Cs, lo, up, str, narrow)) { delete g; return 1; }
   } else if (d.a_mode == SVX_A_SLAB3) {
     const int live = d.cin_live > 0 ? d.cin_live : BK;
     bool ok = d.Cin == BK && live <= BK && d.in_Cs % 4 == 0 && d.in_c0 >= 0 && d.N <= 16 && d.block_n == S3_N &&

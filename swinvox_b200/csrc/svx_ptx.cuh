@@ -191,6 +191,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(4) << 61;                        // SWIZZLE_64B
   return d;
 }
+// K-major operand tile WITHOUT swizzle: 8-row x 16-byte core matrices stored contiguously (128 B); `sbo` = bytes between
+// consecutive 8-row groups, `lbo` = bytes between consecutive 16-byte chunks along K.
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;                        // descriptor version (sm_100); layout type 0 = no swizzle
+  return d;
+}
 // kind::tf32 instruction descriptor: fp32 accumulate, TF32 A/B, both K-major, M=128, N=n
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t m, uint32_t n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);

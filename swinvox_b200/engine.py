@@ -26,7 +26,7 @@ def tf32_round(t):
     return bits.view(torch.float32)
 
 
-def choose_block_n(n, rows=None, gather=False, heavy_epilogue=False):
+def choose_block_n(n, rows=None, gather=False, heavy_epilogue=False, k=None):
     """N tile of one contraction.  Measured on B200 (profiles/r1_gemm_bench_v6.log): the widest tile that divides N
     wins as long as the grid still fills the 148 SMs for a few waves; gather-mode convolutions re-fetch their A tile
     once per N tile, so they take the widest tile regardless."""
@@ -37,9 +37,11 @@ def choose_block_n(n, rows=None, gather=False, heavy_epilogue=False):
     if n <= 64:
         return 64
     cands = [bn for bn in (256, 192, 128, 96) if n % bn == 0] or [128 if n > 96 else 96]
-    if heavy_epilogue and n % 96 == 0:
+    if heavy_epilogue and n % 96 == 0 and (k is None or k <= 192):
         # erf-GELU epilogues are bound by instruction issue in the epilogue warps (profiles/r1_ncu_swin_block_v17.txt):
-        # the 96-wide tile runs two CTAs per SM, i.e. twice the epilogue warps per SM
+        # the 96-wide tile runs two CTAs per SM, i.e. twice the epilogue warps per SM.  Only while the main loop is
+        # short: a tcgen05.mma costs max(~89, N/2) cycles (profiles/r1_umma_tf32_issue_cost.txt), so N = 96 caps the
+        # tensor pipe at 53 % and loses on the deeper-K stages.
         return 96
     if rows is None:
         return cands[0] if gather else ([bn for bn in cands if bn <= 192] or cands)[0]
@@ -113,7 +115,7 @@ class WeightPack:
     def finalize(self, rows=None, gather=False, heavy_epilogue=False):
         if self.W is not None:
             return self
-        bn = self.block_n or choose_block_n(self.N, rows, gather, heavy_epilogue)
+        bn = self.block_n or choose_block_n(self.N, rows, gather, heavy_epilogue, self.K)
         n, k = self.raw_W.shape
         npad, kpad = round_up(max(n, self.N), bn), round_up(k, 32)
         if (npad, kpad) == (n, k):
@@ -351,8 +353,9 @@ class Plan:
         d.ntaps = len(taps)
         lo = [min(t[a] for t in taps) for a in range(3)]
         up = [lo[a] + (rows_dhw[a] - 1) * stride[a] - ((x.D, x.H, x.W)[a] - 1) for a in range(3)]
-        tma = (cin % 32 == 0 and len(taps) <= 64 and all(-16 <= v <= 15 for v in lo + up)
-               and not os.environ.get("SVX_NO_IM2COL"))
+        # whole 32-channel boxes, or 4-channel pixels (the image stems: eight 16-byte taps per k-chunk)
+        tma = ((cin % 32 == 0 or (cin == 4 and not os.environ.get("SVX_NO_IM2COL_NARROW")))
+               and len(taps) <= 64 and all(-16 <= v <= 15 for v in lo + up) and not os.environ.get("SVX_NO_IM2COL"))
         if tma:
             d.a_mode = A_IM2COL
             host = (C.c_int32 * (4 * len(taps)))(*[v for t in taps for v in (t[0], t[1], t[2], 0)])

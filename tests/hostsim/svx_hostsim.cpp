@@ -50,7 +50,7 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   if (d.a_mode == SVX_A_GATHER)
     SVX_REQUIRE(d.Cin % 4 == 0 && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.K == d.ntaps * d.Cin, "gemm: bad gather");
   else if (d.a_mode == SVX_A_IM2COL) {
-    SVX_REQUIRE(d.Cin % 32 == 0 && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.K == d.ntaps * d.Cin && d.Kpad == d.K &&
+    SVX_REQUIRE((d.Cin == 4 || (d.Cin % 32 == 0 && d.Kpad == d.K)) && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.K == d.ntaps * d.Cin &&
                     d.taps_host && d.ntaps <= 64 && d.M % (d.out_D * d.out_H * d.out_W) == 0,
                 "gemm: bad im2col");
     const int in_ext[3] = {d.in_D, d.in_H, d.in_W}, out_ext[3] = {d.out_D, d.out_H, d.out_W};

@@ -117,7 +117,8 @@ def test_gemm_residual_on_tensor_cores(dev, M, K, N, bn):
 
 
 @pytest.mark.parametrize("cin,cout,hw,k,s,p_", [(64, 64, 14, 3, 1, 1), (32, 96, 15, 3, 2, 1), (256, 128, 7, 1, 1, 0),
-                                                 (128, 256, 14, 1, 2, 0), (8, 16, 9, 5, 2, 2), (512, 256, 7, 3, 1, 1)])
+                                                 (128, 256, 14, 1, 2, 0), (8, 16, 9, 5, 2, 2), (512, 256, 7, 3, 1, 1),
+                                                 (4, 64, 30, 7, 2, 3), (4, 96, 24, 4, 4, 0), (4, 32, 11, 3, 1, 1)])
 def test_conv2d_gather(dev, cin, cout, hw, k, s, p_):
     DEV = dev
     torch.manual_seed(cin + cout)
