@@ -754,6 +754,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // in TMEM so the epilogue of one depth overlaps the MMAs of the next.
 // =====================================================================================================
 constexpr int S3_ROWS = 200;                       // slab rows: 128 + 2*Wp <= 200  (Wp <= 36)
+#ifndef S3_PARTS
+#define S3_PARTS 1                                 // a slab arrives as S3_PARTS TMA boxes (1 or 5; measured: no difference)
+#endif
+constexpr int S3_PART_ROWS = S3_ROWS / S3_PARTS;   // multiple of 8 (whole swizzle atoms)
 constexpr int S3_N = 48;                           // MMA N: 3 kw groups x 16 output channels
 constexpr int S3_NACC = 8, S3_ACC_STRIDE = 64;     // TMEM: 8 accumulators of 48 (stride 64) columns
 constexpr int S3_STEP = BM - 2;                    // valid rows per tile
@@ -771,7 +775,7 @@ struct S3Cfg {
   static constexpr int kSmem = 1024 + kWBytes + kNSlab * kSlabBytes + S3_XCHG_BYTES + 512;
 };
 
-template <int ROWB>
+template <int ROWB, bool PAIR>
 __global__ void __launch_bounds__(S3_THREADS, 1)
 conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ GemmParams p) {
@@ -798,54 +802,79 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       reinterpret_cast<volatile uint32_t*>(smem_gen + kXchgOff + S3_XCHG_BYTES + 8 * kSlotIdx);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // PAIR: the two CTAs of a cluster work on two different units in lock step; the leader (rank 0) issues ONE
+  // tcgen05.mma.cta_group::2 (M = 256: 128 rows from each CTA's slab, N/2 weight rows from each CTA) per step for both,
+  // halving the per-SM cost of the issue-bound ~89-cycle instructions (profiles/r1_umma_tf32_issue_cost.txt)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0u;
+  const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // scheduling slot (pair index)
+  const int nslots = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int Wp = p.in_W, HWp = p.in_H * p.in_W;
   const int nd = p.valid_D;                 // output depths per unit; the unit streams nd + 2 slabs
   const int ncol = p.tiles_n;               // 126-row columns per (h,w) plane
   const int num_units = p.tiles_m;          // volumes x columns
+  const int num_steps = PAIR ? (num_units + 1) / 2 : num_units;   // PAIR: step q covers units 2q (leader) and 2q+1 (peer)
+  auto unit_of = [&](int q) { const int u = PAIR ? 2 * q + (int)rank : q; return u < num_units ? u : num_units - 1; };
+  auto unit_real = [&](int q) { return (PAIR ? 2 * q + (int)rank : q) < num_units; };
 
   if (warp == 4 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); }
   if (warp == 5) {
     if (lane == 0) {
       for (uint32_t s = 0; s < S3_NSLAB; ++s) { mbar_init(slab_full(s), 1u); mbar_init(slab_empty(s), 1u); }
       mbar_init(w_full, 1u);
-      for (uint32_t a = 0; a < S3_NACC; ++a) { mbar_init(acc_full(a), 1u); mbar_init(acc_empty(a), 4u); }
+      // PAIR: the leader's acc_empty collects the epilogue warps of both CTAs
+      for (uint32_t a = 0; a < S3_NACC; ++a) { mbar_init(acc_full(a), 1u); mbar_init(acc_empty(a), PAIR ? 8u : 4u); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<512>(tmem_slot);
+    if (PAIR) tmem_alloc_pair<512>(tmem_slot); else tmem_alloc<512>(tmem_slot);
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
   if (warp == 4) {
     // ---- TMA producer: weights once, then one slab per (unit, plane) ---------------------------------
     if (elect_one()) {
-      mbar_arrive_expect_tx(w_full, S3_W_BYTES);
-      for (int t = 0; t < 9; ++t) tma_load_2d(w_smem + t * S3_TAP_BYTES, &map_w, w_full, t * BK, 0);   // first kBoxCh of the 32
+      // PAIR: every load of either CTA signals the LEADER's barrier (it is the leader that issues the MMAs); the
+      // leader expects the bytes of both.  Each CTA holds half of the weight rows of every tap (map_w boxes 24 rows).
+      constexpr uint32_t kWTap = PAIR ? S3_TAP_BYTES / 2 : S3_TAP_BYTES;
+      if (leader) mbar_arrive_expect_tx(w_full, S3_W_BYTES);
+      for (int t = 0; t < 9; ++t) {   // first kBoxCh of the 32
+        if (PAIR) tma_load_2d_pair(w_smem + t * kWTap, &map_w, leader_addr(w_full), t * BK, (int)rank * (S3_N / 2));
+        else tma_load_2d(w_smem + t * S3_TAP_BYTES, &map_w, w_full, t * BK, 0);
+      }
       uint32_t g = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      for (int q = cta; q < num_steps; q += nslots) {
+        const int unit = unit_of(q);
         const int n = unit / ncol, col = unit - n * ncol;
         const int row0 = n * p.in_D * HWp + col * S3_STEP;
         for (int pl = 0; pl < nd + 2; ++pl, ++g) {
           const uint32_t s = g % S3_NSLAB;
           mbar_wait(slab_empty(s), ((g / S3_NSLAB) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(slab_full(s), S3_SLAB_BYTES);
-          tma_load_2d(slab_smem + s * S3_SLAB_BYTES, &map_x, slab_full(s), p.in_c0, row0 + pl * HWp);
+          if (leader) mbar_arrive_expect_tx(slab_full(s), (PAIR ? 2u : 1u) * S3_SLAB_BYTES);
+#pragma unroll
+          for (int part = 0; part < S3_PARTS; ++part) {   // several boxes in flight: the TMA unit walks a box row by row
+            const uint32_t dst = slab_smem + s * S3_SLAB_BYTES + part * S3_PART_ROWS * ROWB;
+            const int row = row0 + pl * HWp + part * S3_PART_ROWS;
+            if (PAIR) tma_load_2d_pair(dst, &map_x, leader_addr(slab_full(s)), p.in_c0, row);
+            else tma_load_2d(dst, &map_x, slab_full(s), p.in_c0, row);
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 5) {
     // ---- MMA issuer -----------------------------------------------------------------------------------
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_tf32(BM, S3_N);
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_tf32(PAIR ? 2 * BM : BM, S3_N);
+      constexpr uint32_t kWTap = PAIR ? S3_TAP_BYTES / 2 : S3_TAP_BYTES;
       const int ksteps = (p.cin_live + UMMA_K - 1) / UMMA_K;
       mbar_wait(w_full, 0u);
       tc_fence_after();
       uint32_t sbase = 0, waited = 0, tg = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      for (int q = cta; q < num_steps; q += nslots) {
         for (int d = 0; d < nd; ++d, ++tg) {
           while (waited < sbase + d + 3) {   // slabs d, d+1, d+2 of this unit
             mbar_wait(slab_full(waited % S3_NSLAB), (waited / S3_NSLAB) & 1u);
@@ -860,18 +889,21 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
               const uint64_t da = ROWB == 128 ? umma_desc_sw128(slab + kh * Wp * ROWB) : umma_desc_sw64(slab + kh * Wp * ROWB);
-              const uint64_t db = ROWB == 128 ? umma_desc_sw128(w_smem + (kd * 3 + kh) * S3_TAP_BYTES)
-                                              : umma_desc_sw64(w_smem + (kd * 3 + kh) * S3_TAP_BYTES);
-              for (int k = 0; k < ksteps; ++k)
-                umma_tf32(acc, da + 2u * k, db + 2u * k, idesc, (kd | kh | k) != 0 ? 1u : 0u);
+              const uint64_t db = ROWB == 128 ? umma_desc_sw128(w_smem + (kd * 3 + kh) * kWTap)
+                                              : umma_desc_sw64(w_smem + (kd * 3 + kh) * kWTap);
+              for (int k = 0; k < ksteps; ++k) {
+                if (PAIR) umma_tf32_pair(acc, da + 2u * k, db + 2u * k, idesc, (kd | kh | k) != 0 ? 1u : 0u);
+                else umma_tf32(acc, da + 2u * k, db + 2u * k, idesc, (kd | kh | k) != 0 ? 1u : 0u);
+              }
             }
           }
-          umma_commit(slab_empty((sbase + d) % S3_NSLAB));   // plane d is not needed by later depths
+          auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
+          commit(slab_empty((sbase + d) % S3_NSLAB));   // plane d is not needed by later depths
           if (d == nd - 1) {
-            umma_commit(slab_empty((sbase + d + 1) % S3_NSLAB));
-            umma_commit(slab_empty((sbase + d + 2) % S3_NSLAB));
+            commit(slab_empty((sbase + d + 1) % S3_NSLAB));
+            commit(slab_empty((sbase + d + 2) % S3_NSLAB));
           }
-          umma_commit(acc_full(a));
+          commit(acc_full(a));
         }
         sbase += nd + 2;
       }
@@ -898,11 +930,12 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const bool pre = has_res && !p.res_after_act, post = has_res && p.res_after_act;
     const bool full16 = p.N == 16 && p.vec_ok;
     uint32_t tg = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+    for (int q = cta; q < num_steps; q += nslots) {
+      const int unit = unit_of(q);
       const int n = unit / ncol, col = unit - n * ncol;
       const int u = col * S3_STEP + r;
       const int h = u / Wp, w = u - h * Wp;
-      const bool row_ok = r < S3_STEP && h < p.valid_H && w < p.valid_W;
+      const bool row_ok = r < S3_STEP && h < p.valid_H && w < p.valid_W && unit_real(q);
       const long long off0 = p.o_base + n * p.o_sn + h * p.o_sh + w * p.o_sw;
       for (int d = 0; d < nd; ++d, ++tg) {
         if ((tg & 1u) != set) continue;
@@ -918,7 +951,13 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty(a));   // the accumulator is in registers: hand it back
+        if (lane == 0) {   // the accumulator is in registers: hand it back (to the leader, who issues the MMAs)
+          if (PAIR && !leader) mbar_arrive_cluster(leader_addr(acc_empty(a)));
+          else mbar_arrive(acc_empty(a));
+        }
+#ifdef SVX_SLAB_NOEPI   // experiment: how fast is the TMA + MMA side alone? (results are wrong)
+        if (d0[0] != 0x7fc12345u) continue;
+#endif
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           *reinterpret_cast<uint4*>(my_row + ((c ^ (r & 7)) << 4)) = make_uint4(d1[4 * c], d1[4 * c + 1], d1[4 * c + 2], d1[4 * c + 3]);
@@ -1018,8 +1057,8 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 5) tmem_dealloc<512>(tmem_base);
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 5) { if (PAIR) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base); }
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -1127,6 +1166,7 @@ struct GemmPrepared {
   int bn, grid;
   bool slab = false;   // SVX_A_SLAB3: handled by conv3_slab_kernel
   bool slab_narrow = false;   // 16-channel (64-byte) rows
+  bool slab_pair = false;     // CTA pairs (cta_group::2): one M = 256 MMA per step for two units
 };
 
 int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
@@ -1231,7 +1271,7 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     p.cin_live = live;
     g->slab = true;
     g->slab_narrow = live <= 16 && !getenv("SVX_SLAB_WIDE");
-    if (encode_map(&g->map_a, d.A, (uint64_t)d.lda, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs, S3_ROWS, g->slab_narrow ? 16 : BK)) {
+    if (encode_map(&g->map_a, d.A, (uint64_t)d.lda, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs, S3_PART_ROWS, g->slab_narrow ? 16 : BK)) {
       delete g;
       return 1;
     }
@@ -1240,8 +1280,11 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     return fail("gemm: unknown a_mode %d", d.a_mode);
   }
   const int w_cols = d.Kpad + (d.res_via_mma ? d.block_n : 0);   // identity columns appended by the host
-  if (encode_map(&g->map_b, d.W, (uint64_t)d.Npad, (uint64_t)w_cols, (uint64_t)w_cols, (uint32_t)d.block_n,
-                 g->slab_narrow ? 16 : BK)) {
+  // CTA pairs (cluster of 2, tcgen05.mma.cta_group::2) are correct (tests pass with SVX_SLAB_PAIR=1) but measured no
+  // faster than single CTAs on this kernel (profiles/README.md, "merger slab kernel experiments"): opt-in only.
+  g->slab_pair = g->slab && getenv("SVX_SLAB_PAIR") != nullptr;
+  if (encode_map(&g->map_b, d.W, (uint64_t)d.Npad, (uint64_t)w_cols, (uint64_t)w_cols,
+                 g->slab_pair ? (uint32_t)(S3_N / 2) : (uint32_t)d.block_n, g->slab_narrow ? 16 : BK)) {
     delete g;
     return 1;
   }
@@ -1325,6 +1368,11 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     p.tiles_m = (d.M / (d.valid_D * d.valid_H * d.valid_W)) * p.tiles_n;
     p.nk = 1;
     g->grid = p.tiles_m < sm_count() ? p.tiles_m : sm_count();
+    if (g->slab_pair) {   // whole pairs only; a pair handles two units per step
+      const int steps = (p.tiles_m + 1) / 2;
+      const int pairs = steps < sm_count() / 2 ? steps : sm_count() / 2;
+      g->grid = 2 * pairs;
+    }
   }
   *out = g;
   return 0;
@@ -1342,14 +1390,33 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void* stream) {
   if (g->slab) {
     static bool configured = false;
     if (!configured) {
-      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<128>::kSmem));
-      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<64>::kSmem));
+      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<128>::kSmem));
+      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<64>::kSmem));
+      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<128>::kSmem));
+      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<64>::kSmem));
       configured = true;
     }
-    if (g->slab_narrow)
-      conv3_slab_kernel<64><<<g->grid, S3_THREADS, S3Cfg<64>::kSmem, st>>>(g->map_a, g->map_b, g->p);
-    else
-      conv3_slab_kernel<128><<<g->grid, S3_THREADS, S3Cfg<128>::kSmem, st>>>(g->map_a, g->map_b, g->p);
+    if (g->slab_pair) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(g->grid);
+      cfg.blockDim = dim3(S3_THREADS);
+      cfg.dynamicSmemBytes = g->slab_narrow ? S3Cfg<64>::kSmem : S3Cfg<128>::kSmem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t le = g->slab_narrow ? cudaLaunchKernelEx(&cfg, conv3_slab_kernel<64, true>, g->map_a, g->map_b, g->p)
+                                      : cudaLaunchKernelEx(&cfg, conv3_slab_kernel<128, true>, g->map_a, g->map_b, g->p);
+      if (le != cudaSuccess) { if (!prepared) delete g; return fail("cluster launch of conv3_slab_kernel failed: %s", cudaGetErrorString(le)); }
+    } else if (g->slab_narrow) {
+      conv3_slab_kernel<64, false><<<g->grid, S3_THREADS, S3Cfg<64>::kSmem, st>>>(g->map_a, g->map_b, g->p);
+    } else {
+      conv3_slab_kernel<128, false><<<g->grid, S3_THREADS, S3Cfg<128>::kSmem, st>>>(g->map_a, g->map_b, g->p);
+    }
     cudaError_t e = cudaGetLastError();
     if (!prepared) delete g;
     if (e != cudaSuccess) return fail("launch of conv3_slab_kernel failed: %s", cudaGetErrorString(e));

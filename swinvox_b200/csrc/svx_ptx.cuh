@@ -112,6 +112,52 @@ __device__ __forceinline__ void tma_load_im2col_5d(uint32_t dst, const void* map
       : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of a TPC execute one M = 256 MMA ------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem offset in the pair's leader (even) CTA: bit 24 selects the CTA of the pair
+__device__ __forceinline__ uint32_t leader_addr(uint32_t smem_addr) { return smem_addr & 0xFEFFFFFFu; }
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA load whose completion bytes may be signalled on the PEER CTA's mbarrier (`bar` is a shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* map, uint32_t bar, int32_t x, int32_t y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 from each CTA's smem] * B[N rows: N/2 from each CTA's smem]^T; leader only
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at this smem offset in BOTH CTAs of the pair once the issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+
 // smem tile -> global (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_2d(const void* map, uint32_t src, int32_t x, int32_t y) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

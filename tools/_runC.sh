@@ -1,10 +1,4 @@
-for mode in "" "SVX_SLAB_KDN=1"; do
-  echo "== spin $mode"
-  env SVX_LIB_PATH=$PWD/tools/probes/libswinvox_b200_spin.bin SVX_ISOLATE=1 $mode python tools/run_module.py merger 64 3 3 2>&1 | grep -E "merger"
-  echo "== spin+profile $mode"
-  env SVX_LIB_PATH=$PWD/tools/probes/libswinvox_b200_spinprof.bin SVX_ISOLATE=1 $mode python tools/run_module.py merger 64 3 1 2>&1 | grep -E "slab profile" | sed -n 2,3p
-done
-echo "== spin bench"
-SVX_LIB_PATH=$PWD/tools/probes/libswinvox_b200_spin.bin python bench.py 2>/dev/null | cut -c1-220
-echo "== default bench"
-python bench.py 2>/dev/null | cut -c1-220
+for parts in 1 5; do for mode in "" "SVX_SLAB_NO_PAIR=1"; do
+echo "== parts=$parts $mode"; env SVX_LIB_PATH=$PWD/tools/probes/libswinvox_b200_parts$parts.bin $mode SVX_ISOLATE=1 timeout 120 python tools/run_module.py merger 64 3 3 2>&1 | grep "merger.layer" | sed -n '1p;5p'
+done; done
+SVX_LIB_PATH=$PWD/tools/probes/libswinvox_b200_parts5.bin timeout 180 python -m pytest tests/test_kernels.py -m gpu -q -x -k "slab" 2>&1 | tail -2
