@@ -891,6 +891,9 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
               const uint64_t da = ROWB == 128 ? umma_desc_sw128(slab + kh * Wp * ROWB) : umma_desc_sw64(slab + kh * Wp * ROWB);
               const uint64_t db = ROWB == 128 ? umma_desc_sw128(w_smem + (kd * 3 + kh) * kWTap)
                                               : umma_desc_sw64(w_smem + (kd * 3 + kh) * kWTap);
+#ifdef SVX_SLAB_NOMMA   // experiment: the TMA pipeline alone (results are wrong)
+              if (ksteps > 0) continue;
+#endif
               for (int k = 0; k < ksteps; ++k) {
                 if (PAIR) umma_tf32_pair(acc, da + 2u * k, db + 2u * k, idesc, (kd | kh | k) != 0 ? 1u : 0u);
                 else umma_tf32(acc, da + 2u * k, db + 2u * k, idesc, (kd | kh | k) != 0 ? 1u : 0u);

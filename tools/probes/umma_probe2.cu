@@ -35,6 +35,19 @@ __global__ void __launch_bounds__(128, 1) probe(int n, int group, int commit, in
       uint32_t acc = tmem;
       if (pattern == 1 || pattern == 3) acc = tmem + (g % 10) * 48;
       if (pattern == 2) acc = tmem + (7 - g % 8) * 48;
+      if (pattern >= 4) {
+        // the kd-in-N issuer's sequence: N=48 (accumulate 0) at c, N=96 at c+48, then N=144 at c (overlapping windows
+        // of different shapes); pattern 5: the same shapes but all three at disjoint columns
+        acc = tmem + (7 - g % 8) * 48;
+        const uint64_t da0 = umma_desc_sw128(base + (it % 3) * 200 * 128);
+        const uint32_t far = pattern == 5 ? 256u : 0u;
+        umma_tf32(acc, da0, db, umma_idesc_tf32(128, 48), pattern == 4 ? 0u : 1u);
+        umma_tf32(acc + 48 + (pattern == 5 ? 16u : 0u), da0, db, umma_idesc_tf32(128, 96), 1u);
+        for (int j = 2; j < group; ++j) {
+          const uint64_t da = umma_desc_sw128(base + ((it + j) % 3) * 200 * 128) + 2u * (j & 3);
+          umma_tf32(acc + far, da, db + 2u * (j & 3), umma_idesc_tf32(128, pattern == 5 ? 96 : 144), 1u);
+        }
+      } else
       for (int j = 0; j < group; ++j) {
         const uint64_t da = umma_desc_sw128(base + ((it + j) % 3) * 200 * 128) + 2u * (j & 3);
         umma_tf32(acc, da, db + 2u * (j & 3), idesc, (pattern == 3 && j == 0) ? 0u : 1u);
@@ -58,11 +71,11 @@ int main() {
   cudaMallocManaged(&out, 16);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   printf("# N group commits/group pattern : cycles per MMA (until everything completed), cycles per group\n");
-  for (int pattern : {0, 1, 3, 2})
+  for (int pattern : {4, 5, 2})
     for (int n : {48, 144, 192})
       for (int group : {4, 7, 18})
         for (int commit : {0, 1, 2}) {
-          if (pattern == 2 && n != 144) continue;
+          if (pattern >= 2 && n != 144) continue;
           if ((pattern == 1 || pattern == 3) && n != 48) continue;
           const int iters = group * 600;
           probe<<<148, 128, 200 * 1024>>>(n, group, commit, pattern, iters, out);
