@@ -239,6 +239,20 @@ typedef struct svx_binvox_encode_desc {
   int32_t B, d0, d1, d2, axis_xyz;
 } svx_binvox_encode_desc;
 
+/* Evaluation-time image pipeline (core/test.py:50-55): CenterCrop (utils/data_transforms.py:76-167, no bounding box) ->
+ * RandomBackground with a fixed colour (:415-452) -> Normalize (:57-62) -> ToTensor (:42-49), over renderings read as
+ * uint8 (utils/data_loaders.py:70-76 divides by 255).  in: uint8 [N, H, W, C] (C = 4: BGRA, C = 3: no alpha);
+ * [y0, y1) x [x0, x1) is the crop window (the host applies the reference's rule: centred crop_size window when the
+ * image is larger than it, else the whole image); the window is resized to OH x OW with cv2's INTER_LINEAR convention
+ * on the value/255 floats (all channels incl. alpha); where the resized alpha is exactly 0 the pixel becomes the
+ * background; out: fp32 [N, 3, OH, OW] = (x - mean) / std; bg_norm is the already normalised background colour. */
+typedef struct svx_preprocess_desc {
+  const uint8_t* in; float* out;
+  int32_t N, H, W, C, OH, OW;
+  int32_t y0, y1, x0, x1;
+  float mean[3], std[3], bg_norm[3];
+} svx_preprocess_desc;
+
 /* ---- library ------------------------------------------------------------------------ */
 int svx_abi_version(void);
 const char* svx_last_error(void);
@@ -261,6 +275,7 @@ int svx_voxel_metrics(const svx_metrics_desc*, void* stream);
 int svx_transpose(const svx_transpose_desc*, void* stream);
 int svx_binvox_decode(const svx_binvox_decode_desc*, void* stream);
 int svx_binvox_encode(const svx_binvox_encode_desc*, void* stream);
+int svx_preprocess(const svx_preprocess_desc*, void* stream);
 
 /* ---- plans: a recorded op list replayed per forward (one per module instance/shape) --- */
 typedef struct svx_plan svx_plan;

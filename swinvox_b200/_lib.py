@@ -128,6 +128,11 @@ class BinvoxEncodeDesc(C.Structure):
                 ("B", i32), ("d0", i32), ("d1", i32), ("d2", i32), ("axis_xyz", i32)]
 
 
+class PreprocessDesc(C.Structure):
+    _fields_ = [("inp", ptr), ("out", ptr), ("N", i32), ("H", i32), ("W", i32), ("C", i32), ("OH", i32), ("OW", i32),
+                ("y0", i32), ("y1", i32), ("x0", i32), ("x1", i32), ("mean", f32 * 3), ("std", f32 * 3), ("bg_norm", f32 * 3)]
+
+
 # order must match svx_desc_sizes()
 DESC_TYPES = [GemmDesc, Im2colDesc, PoolDesc, LnRowsDesc, LnSampleDesc, WinAttnDesc, DwConvDesc,
               ViewAttnDesc, BilinearDesc, MergeFuseDesc, MetricsDesc, TransposeDesc]
@@ -154,7 +159,8 @@ OTHER_SYMBOLS = ["svx_abi_version", "svx_last_error", "svx_desc_sizes", "svx_dev
 
 ALL_SYMBOLS = OTHER_SYMBOLS + [s for v in OPS.values() for s in v[:2]]
 # data-format entry points (svx_io.cu): present in the CUDA library only (the CPU twin of the tests has no copy)
-IO_SYMBOLS = {"svx_binvox_decode": BinvoxDecodeDesc, "svx_binvox_encode": BinvoxEncodeDesc}
+IO_SYMBOLS = {"svx_binvox_decode": BinvoxDecodeDesc, "svx_binvox_encode": BinvoxEncodeDesc,
+              "svx_preprocess": PreprocessDesc}
 
 
 class SvxError(RuntimeError):

@@ -178,3 +178,74 @@ int svx_binvox_encode(const svx_binvox_encode_desc* d, void* stream) {
 }
 
 }  // extern "C"
+
+// ---- evaluation-time image pipeline (core/test.py:50-55, utils/data_transforms.py:76-167,415-452,42-62) -------------
+// uint8 H x W x C renderings (C = 4: BGRA, or 3) -> centre crop -> bilinear resize (cv2 INTER_LINEAR convention) of the
+// value/255 floats -> background colour where the RESIZED alpha is exactly 0 -> (x - mean) / std -> planar fp32
+// [N, 3, OH, OW], the encoder's input.  One thread per output pixel (all channels): reads are the 2 x 2 source
+// neighbourhood (L1/L2-resident, the source is 3-5x smaller than the output), writes are coalesced per plane.
+namespace svx {
+namespace {
+
+__global__ void __launch_bounds__(256) preprocess_kernel(const svx_preprocess_desc d) {
+  const long long total = (long long)d.N * d.OH * d.OW;
+  const int ch = d.y1 - d.y0, cw = d.x1 - d.x0;   // crop window
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % d.OW);
+    const long long t = idx / d.OW;
+    const int oy = (int)(t % d.OH);
+    const long long n = t / d.OH;
+    // source coordinate fx = (o + 0.5) * src / dst - 0.5 as the exact rational ((2o+1) src - dst) / (2 dst)
+    auto coord = [](int o, int src, int dst, int& i0, int& i1, float& w1) {
+      const int num = (2 * o + 1) * src - dst, den = 2 * dst;
+      int s = num >= 0 ? num / den : -((-num + den - 1) / den);
+      float f = (float)(num - s * den) / (float)den;
+      if (s < 0) { s = 0; f = 0.f; }
+      if (s >= src - 1) { s = src - 1; f = 0.f; }
+      i0 = s; i1 = s + 1 < src ? s + 1 : src - 1; w1 = f;
+    };
+    int xa, xb, ya, yb;
+    float wx, wy;
+    coord(ox, cw, d.OW, xa, xb, wx);
+    coord(oy, ch, d.OH, ya, yb, wy);
+    const uint8_t* img = d.in + n * (long long)d.H * d.W * d.C;
+    const uint8_t* p00 = img + ((long long)(d.y0 + ya) * d.W + d.x0 + xa) * d.C;
+    const uint8_t* p01 = img + ((long long)(d.y0 + ya) * d.W + d.x0 + xb) * d.C;
+    const uint8_t* p10 = img + ((long long)(d.y0 + yb) * d.W + d.x0 + xa) * d.C;
+    const uint8_t* p11 = img + ((long long)(d.y0 + yb) * d.W + d.x0 + xb) * d.C;
+    auto lerp2 = [&](int c) {
+      const float v00 = __fdiv_rn((float)p00[c], 255.f), v01 = __fdiv_rn((float)p01[c], 255.f);
+      const float v10 = __fdiv_rn((float)p10[c], 255.f), v11 = __fdiv_rn((float)p11[c], 255.f);
+      const float r0 = fmaf(wx, v01 - v00, v00), r1 = fmaf(wx, v11 - v10, v10);
+      return fmaf(wy, r1 - r0, r0);
+    };
+    bool background = false;
+    if (d.C == 4) background = lerp2(3) == 0.f;   // alpha * bg + (1 - alpha) * img with alpha = (resized alpha == 0)
+    float* out = d.out + n * 3LL * d.OH * d.OW + (long long)oy * d.OW + ox;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = background ? d.bg_norm[c] : (lerp2(c) - d.mean[c]) / d.std[c];
+      out[(long long)c * d.OH * d.OW] = v;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace svx
+
+extern "C" int svx_preprocess(const svx_preprocess_desc* d, void* stream) {
+  using namespace svx;
+  if (!d) return fail("svx_preprocess: null descriptor");
+  SVX_REQUIRE(d->in && d->out && d->N > 0 && d->H > 0 && d->W > 0 && (d->C == 3 || d->C == 4) && d->OH > 0 && d->OW > 0,
+              "preprocess: bad description");
+  SVX_REQUIRE(d->y0 >= 0 && d->x0 >= 0 && d->y1 > d->y0 && d->x1 > d->x0 && d->y1 <= d->H && d->x1 <= d->W,
+              "preprocess: crop window outside the image");
+  SVX_REQUIRE((long long)(2 * d->OW + 1) * (d->x1 - d->x0) < 0x7fffffffLL && (long long)(2 * d->OH + 1) * (d->y1 - d->y0) < 0x7fffffffLL,
+              "preprocess: image too large");
+  const long long total = (long long)d->N * d->OH * d->OW;
+  long long grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  preprocess_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(*d);
+  SVX_LAUNCH_OK("preprocess_kernel");
+  return 0;
+}
