@@ -399,6 +399,25 @@ def test_layernorms(dev):
                    F.layer_norm(xs.double(), (7, 7, 768), gs.double(), bs.double())) < 1e-5
 
 
+@pytest.mark.parametrize("H,C,N", [(56, 96, 3), (28, 192, 2), (14, 384, 5), (7, 768, 2), (3, 100, 2)])
+@pytest.mark.parametrize("cluster", [False, True])
+def test_layernorm_sample_shapes(dev, H, C, N, cluster, monkeypatch):
+    """the wrapper's LayerNorm([C,H,W]) at the four Swin stage shapes and one tiny sample; `cluster` = the opt-in
+    thread-block-cluster kernel (distributed-shared-memory reduction), every register variant"""
+    DEV = dev
+    if cluster:
+        monkeypatch.setenv("SVX_LN_CLUSTER", "1")
+    torch.manual_seed(H + C)
+    xs = torch.randn(N, H, H, C) * 1.7 + 0.4
+    gs, bs = torch.rand(H, H, C) + 0.5, torch.randn(H, H, C)
+    p = E.Plan(DEV)
+    o = p.new_act(N, 1, H, H, C)
+    p.layernorm_sample(E.Act(xs.view(-1, C).to(DEV), N, 1, H, H, C), gs.to(DEV), bs.to(DEV), o, round_out=False)
+    p.run()
+    sync(DEV)
+    assert rel_err(o.view().reshape(N, H, H, C), F.layer_norm(xs.double(), (H, H, C), gs.double(), bs.double())) < 1e-5
+
+
 @pytest.mark.parametrize("rows,C,merge", [(1, 96, False), (1001, 96, False), (333, 192, False), (77, 384, False),
                                           (50, 768, False), (13, 2048, False), (None, 384, True), (None, 768, True),
                                           (None, 1536, True), (7, 100, False)])
