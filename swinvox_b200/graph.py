@@ -8,6 +8,8 @@ Rounding policy: a tensor is stored rounded to TF32 (`round_out`) exactly when i
 tensor-core contraction, so kind::tf32's operand truncation never adds a bias; everything else stays
 full fp32 (residual streams, attention inputs, module outputs).
 """
+import os
+
 import torch
 
 from . import engine as E
@@ -98,9 +100,11 @@ def relative_position_bias(table, heads):
     return table.detach().float()[idx.view(-1)].view(ws * ws, ws * ws, heads).permute(2, 0, 1).contiguous()
 
 
-def lower_swin(plan, swin, img, N):
+def lower_swin(plan, swin, img, N, stage_tail=None):
     """swin: the SwinTransformer wrapper (has .model, .layer_norm, .cfg).  Returns the list of per-stage
-    Acts [N,H,W,C] AFTER the wrapper LayerNorm, in SWIN_T_STAGES order, stored TF32-rounded NHWC."""
+    Acts [N,H,W,C] AFTER the wrapper LayerNorm, in SWIN_T_STAGES order, stored TF32-rounded NHWC.
+    stage_tail(i, f): optional callback recorded right after output i is available (in a side lane chosen by the
+    caller), so per-stage consumers overlap the remaining Swin stages."""
     dev = _dev(plan)
     model = swin.model
     stages = [i % 4 for i in swin.cfg.NETWORK.SWIN_T_STAGES]
@@ -114,6 +118,7 @@ def lower_swin(plan, swin, img, N):
     plan.layernorm_rows(emb, pe.norm.weight.detach().float().to(dev), pe.norm.bias.detach().float().to(dev), x,
                         eps=pe.norm.eps, round_out=False, name="swin.patch_embed.norm")
     feats = {}
+    outs = [None] * len(stages)
     for s in range(max(stages) + 1):
         layer = getattr(model, f"layers_{s}")
         Cc, H = 96 * 2 ** s, 56 // 2 ** s
@@ -148,16 +153,21 @@ def lower_swin(plan, swin, img, N):
             x = plan.new_act(N, 1, H, H, Cc)
             plan.linear(hid, E.pack_matrix(blk.mlp.fc2.weight, blk.mlp.fc2.bias, dev), x, residual=x1, name=nm + ".fc2")
         feats[s] = x
-    outs = []
-    for i, s in enumerate(stages):
-        ln = swin.layer_norm[i]
-        Cc, H = 96 * 2 ** s, 56 // 2 ** s
-        f = plan.new_act(N, 1, H, H, Cc)
-        # affine is stored [C,H,W] (it normalises an NCHW tensor); our data is [H,W,C]
-        g = ln.weight.detach().float().permute(1, 2, 0).contiguous().to(dev)
-        b = ln.bias.detach().float().permute(1, 2, 0).contiguous().to(dev)
-        plan.layernorm_sample(feats[s], g, b, f, eps=ln.eps, name=f"swin.layer_norm.{i}")
-        outs.append(f)
+        for i, si in enumerate(stages):   # wrapper LayerNorm (+ the caller's per-stage tail) as soon as the stage is done
+            if si != s:
+                continue
+            if stage_tail is not None:
+                plan.lane(2 + i % 6)
+            ln = swin.layer_norm[i]
+            f = plan.new_act(N, 1, H, H, Cc)
+            # affine is stored [C,H,W] (it normalises an NCHW tensor); our data is [H,W,C]
+            g = ln.weight.detach().float().permute(1, 2, 0).contiguous().to(dev)
+            b = ln.bias.detach().float().permute(1, 2, 0).contiguous().to(dev)
+            plan.layernorm_sample(x, g, b, f, eps=ln.eps, name=f"swin.layer_norm.{i}")
+            outs[i] = f
+            if stage_tail is not None:
+                stage_tail(i, f)
+                plan.lane(0)
     return outs
 
 
@@ -208,39 +218,69 @@ def lower_encoder(plan, enc, img, B, V):
     N = B * V
     net = enc.cfg.NETWORK
     cat = plan.new_act(N, 1, 7, 7, 512)
+    img = stage_image(plan, img, N)   # shared by both branches: staged before they fork
+    # The ResNet and the Swin branch are independent until the concat (encoder.py:119-143): they are recorded as two
+    # concurrent graph branches (lane 1 / lane 0), so the tail of one branch's persistent kernels overlaps the other's.
+    two_lanes = not os.environ.get("SVX_ENCODER_ONE_LANE")
+    if two_lanes:
+        plan.lane(1)
     # ResNet branch.  avg_pool2d(conv1x1(x)) == conv1x1(avg_pool2d(x)): pool first, 4x fewer MACs.
     r = lower_resnet_trunk(plan, enc.resnet, img, N)
     rp = plan.new_act(N, 1, 7, 7, 1024)
     plan.pool(r, rp, (1, 2, 2), (1, 2, 2), (0, 0, 0), POOL_AVG, round_out=True, name="encoder.avg_pool")
     plan.linear(rp, E.pack_conv(enc.resnet_reduce.weight, enc.resnet_reduce.bias, None, dev), cat.channels(0, 256),
                 round_out=True, name="encoder.resnet_reduce")
-    # Swin branch
-    feats = lower_swin(plan, enc.swin_transformer, img, N)
+    if two_lanes:
+        plan.lane(0)
+    # Swin branch.  Per-stage tails (wrapper LayerNorm, 1x1 reduce, all but the last strided convolution of the
+    # downsample chain; encoder.py:134-138) are recorded in side lanes right after their stage, so they overlap the later
+    # Swin stages; the last op of every chain accumulates into the running sum `sw` and therefore runs after the join,
+    # in stage order (the reference's summation order).
     sw = cat.channels(256, 256)
-    if net.USE_SWIN_T_MULTI_STAGE:
-        n_st = len(feats)
+    finals = []
+    multi = net.USE_SWIN_T_MULTI_STAGE
+    n_st = len(enc.cfg.NETWORK.SWIN_T_STAGES) if multi else 1
+
+    def stage_tail(i, f):
+        if not multi:
+            return
+        chain = enc.swin_downsamples[i]
+        convs = [] if isinstance(chain, torch.nn.Identity) else [(chain[k], chain[k + 1]) for k in range(0, len(chain), 3)]
+        first, last_stage = i == 0, i == n_st - 1
+        red = enc.swin_stage_reduces[i]
+        pk = E.pack_conv(red.weight, red.bias, None, dev)
+        if not convs:   # the reduce itself accumulates into the running sum
+            finals.append((i, lambda f=f, pk=pk, first=first, last_stage=last_stage, i=i: plan.linear(
+                f, pk, sw, residual=None if first else sw, round_out=last_stage, name=f"encoder.swin_reduce.{i}")))
+            return
+        t = plan.new_act(N, 1, f.H, f.W, 256)
+        plan.linear(f, pk, t, round_out=True, name=f"encoder.swin_reduce.{i}")
+        for ci, (conv, bn) in enumerate(convs):
+            Ho = (t.H + 2 - 3) // 2 + 1
+            pkc = E.pack_conv(conv.weight, conv.bias, bn, dev)
+            if ci == len(convs) - 1:
+                finals.append((i, lambda t=t, pkc=pkc, first=first, last_stage=last_stage, i=i, ci=ci: plan.conv(
+                    t, pkc, E.conv_taps(1, 3, 3, 0, 1, 1), sw, stride=(1, 2, 2), act=ACT_RELU,
+                    residual=None if first else sw, res_after_act=True, round_out=last_stage,
+                    name=f"encoder.swin_down.{i}.{ci}")))
+            else:
+                o = plan.new_act(N, 1, Ho, Ho, 256)
+                plan.conv(t, pkc, E.conv_taps(1, 3, 3, 0, 1, 1), o, stride=(1, 2, 2), act=ACT_RELU, round_out=True,
+                          name=f"encoder.swin_down.{i}.{ci}")
+                t = o
+
+    overlap = two_lanes and multi   # single-stage mode: the reduce below reads the LayerNorm output on lane 0
+    feats = lower_swin(plan, enc.swin_transformer, img, N, stage_tail=stage_tail if overlap else None)
+    if not overlap:
         for i, f in enumerate(feats):
-            chain = enc.swin_downsamples[i]
-            convs = [] if isinstance(chain, torch.nn.Identity) else [(chain[k], chain[k + 1]) for k in range(0, len(chain), 3)]
-            first, last_stage = i == 0, i == n_st - 1
-            red = enc.swin_stage_reduces[i]
-            pk = E.pack_conv(red.weight, red.bias, None, dev)
-            if not convs:   # the reduce itself accumulates into the running sum
-                plan.linear(f, pk, sw, residual=None if first else sw, round_out=last_stage, name=f"encoder.swin_reduce.{i}")
-                continue
-            t = plan.new_act(N, 1, f.H, f.W, 256)
-            plan.linear(f, pk, t, round_out=True, name=f"encoder.swin_reduce.{i}")
-            for ci, (conv, bn) in enumerate(convs):
-                Ho = (t.H + 2 - 3) // 2 + 1
-                final = ci == len(convs) - 1
-                o = sw if final else plan.new_act(N, 1, Ho, Ho, 256)
-                plan.conv(t, E.pack_conv(conv.weight, conv.bias, bn, dev), E.conv_taps(1, 3, 3, 0, 1, 1), o,
-                          stride=(1, 2, 2), act=ACT_RELU, residual=(sw if (final and not first) else None),
-                          res_after_act=True, round_out=(not final) or last_stage, name=f"encoder.swin_down.{i}.{ci}")
-                t = Act(o.buf, N, 1, Ho, Ho, 256, o.c0)
-    else:
+            stage_tail(i, f)
+    if not multi:
         plan.linear(feats[-1], E.pack_conv(enc.swin_reduce.weight, enc.swin_reduce.bias, None, dev), sw, round_out=True,
                     name="encoder.swin_reduce")
+    if two_lanes:
+        plan.join()
+    for _, emit in sorted(finals, key=lambda t: t[0]):   # the accumulating ops, in stage order
+        emit()
     x = cat
     plan.taps.update(resnet=cat.channels(0, 256), swin_sum=sw, swin=feats, pre_cva=cat)
     if net.USE_CROSS_VIEW_ATTENTION:

@@ -1,3 +1,3 @@
-for lib in nomma nomma_epi; do
-echo "== $lib"; env SVX_LIB_PATH=$PWD/tools/probes/libswinvox_b200_$lib.bin SVX_ISOLATE=1 timeout 120 python tools/run_module.py merger 64 3 3 2>&1 | grep "merger.layer" | sed -n '1p;5p;7p'
-done
+python -m pytest tests/test_modules.py -m gpu -q -x 2>&1 | tail -3
+echo "== two lanes"; python bench.py 2>/dev/null | cut -c1-200
+echo "== one lane"; SVX_ENCODER_ONE_LANE=1 python bench.py 2>/dev/null | cut -c1-200
