@@ -71,7 +71,7 @@ enum { SVX_POOL_MAX = 0, SVX_POOL_AVG = 1 };
  *                 but fetched by the TMA unit in im2col mode (cuTensorMapEncodeIm2col over the NDHWC tensor, one
  *                 128-pixel x 32-channel box per (tap, channel chunk), borders zero-filled by the hardware).  Needs
  *                 Cin % 32 == 0, or Cin == 4 (image stems: one 16-byte pixel per tap, eight taps per k-chunk, Kpad may
- *                 exceed K); tap offsets and the implied padding must fit the descriptor's [-16, 15] corner range.
+ *                 exceed K), or Cin == 8 (pixel pairs: one 32-byte box per tap, four taps per k-chunk, K % 32 == 0); tap offsets and the implied padding must fit the descriptor's [-16, 15] corner range.
  *   SVX_A_FLAT  : stride-1 convolution over a zero-PADDED channels-last tensor viewed as the matrix
  *                 [N*in_D*in_H*in_W, in_Cs] (in_* are the padded extents).  Row r is the flat padded position
  *                 of the window corner; tap t reads row r + (dd*in_H + dh)*in_W + dw (taps >= 0), streamed by
@@ -213,10 +213,14 @@ typedef struct svx_metrics_desc {
   int64_t* bce_q20;
 } svx_metrics_desc;
 
-/* layout change [N, C, P] (planar) <-> [N, P, Cs] (channels-last, first C of Cs channels) */
+/* layout change [N, C, P] (planar) <-> [N, P, Cs] (channels-last, first C of Cs channels).
+ * to_channels_last with row_w > 0 (Cs == 4 only): the P pixels of a sample are rows of row_w pixels and pixel (y, x)
+ * is stored at pixel y*row_pitch + row_x0 + x of the sample's (P/row_w)*row_pitch-pixel block -- zero columns left
+ * and right of every image row (never written), the layout the ResNet stem reads as 8-channel pixel pairs. */
 typedef struct svx_transpose_desc {
   const float* in; float* out;
   int32_t N, C, P, Cs; int32_t to_channels_last; int32_t round_tf32;
+  int32_t row_w, row_pitch, row_x0, reserved0;
 } svx_transpose_desc;
 
 /* binvox run-length decode (utils/binvox_rw.py:119-153 read_as_3d_array; utils/data_loaders.py:84-87): the payload

@@ -115,6 +115,7 @@ class TransposeDesc(C.Structure):
     _fields_ = [
         ("inp", ptr), ("out", ptr),
         ("N", i32), ("C", i32), ("P", i32), ("Cs", i32), ("to_channels_last", i32), ("round_tf32", i32),
+        ("row_w", i32), ("row_pitch", i32), ("row_x0", i32), ("reserved0", i32),
     ]
 
 

@@ -326,7 +326,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               i2c_n = t / p.out_D;
               i2c_w = i2c_w * p.sw + p.i2c_lo_w; i2c_h = i2c_h * p.sh + p.i2c_lo_h; i2c_d = i2c_d * p.sd + p.i2c_lo_d;
             }
-            if (p.i2c_narrow) {
+            if (p.i2c_narrow == 2) {
+              // 8-channel pixel pairs: a k-chunk is four taps, each a 128-pixel x 32-byte box (32B swizzle) = the A
+              // operand of ONE MMA K step
+#pragma unroll 1
+              for (int j = 0; j < 4; ++j) {
+                const int o = p.flat_off[kc * 4 + j];
+                tma_load_im2col_5d(a_dst + j * (BM * 32), &map_a, full_bar(s), p.in_c0, i2c_w, i2c_h, i2c_d, i2c_n,
+                                   (uint16_t)(o & 255), (uint16_t)((o >> 8) & 255), (uint16_t)((o >> 16) & 255));
+              }
+            } else if (p.i2c_narrow) {
               // 4-channel pixels: a k-chunk is eight taps, each its own 128-pixel x 16-byte box = one column of core
               // matrices of the unswizzled K-major tile (taps past the filter re-read tap 0 against zero weights)
 #pragma unroll 1
@@ -367,10 +376,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t a_addr = smem_base + s * C::kStageBytes;
-          const bool narrow = p.i2c_narrow != 0;
-          const uint64_t da = narrow ? umma_desc_nosw(a_addr, BM * 16, 128) : umma_desc_sw128(a_addr);
+          const int narrow = p.i2c_narrow;
+          const uint64_t da = narrow == 2 ? umma_desc_sw32(a_addr) : narrow ? umma_desc_nosw(a_addr, BM * 16, 128) : umma_desc_sw128(a_addr);
           const uint64_t db = umma_desc_sw128(a_addr + A_STAGE_BYTES);
-          const uint32_t a_step = narrow ? (2u * BM * 16) >> 4 : 2u;   // two 16-byte K chunks per MMA: 2 boxes / 32 bytes
+          // per MMA K step (32 bytes): +32 B inside the 128B atom / two 16-byte boxes / one 32-byte box
+          const uint32_t a_step = narrow ? (BM * 32u) >> 4 : 2u;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 8 fp32 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
@@ -1111,7 +1121,7 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 // im2col-mode map over the channels-last tensor [N, D, H, W, Cs]: boxes of 128 pixels x 32 channels, 128B swizzle.
 // lo / up: bounding-box corners of the base pixel per axis (d, h, w); str: convolution strides (d, h, w).
 int encode_im2col_map(CUtensorMap* map, const float* ptr, uint64_t N, uint64_t D, uint64_t H, uint64_t W, uint64_t Cs,
-                      const int lo[3], const int up[3], const int str[3], bool narrow = false) {
+                      const int lo[3], const int up[3], const int str[3], int box_ch = BK) {
   static EncodeIm2colFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -1127,8 +1137,9 @@ int encode_im2col_map(CUtensorMap* map, const float* ptr, uint64_t N, uint64_t D
   cuuint32_t estr[5] = {1, (cuuint32_t)str[2], (cuuint32_t)str[1], (cuuint32_t)str[0], 1};
   // narrow: one 4-channel (16-byte) pixel per row, stored densely (no swizzle) = a column of 8x16B core matrices
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(ptr), dims, strides, lower, upper,
-                  narrow ? 4 : BK, BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  narrow ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  (cuuint32_t)box_ch, BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  box_ch == 4 ? CU_TENSOR_MAP_SWIZZLE_NONE : box_ch == 8 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail("cuTensorMapEncodeIm2col failed with CUresult %d (lo %d,%d,%d up %d,%d,%d)", (int)r, lo[0], lo[1], lo[2],
@@ -1224,8 +1235,8 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     p.chunks_per_tap = d.Cin / BK;
     if (encode_map(&g->map_a, d.A, (uint64_t)rows_total, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs, BM)) { delete g; return 1; }
   } else if (d.a_mode == SVX_A_IM2COL) {
-    const bool narrow = d.Cin == 4;
-    bool ok = d.Cin > 0 && (narrow || (d.Cin % BK == 0 && d.Kpad == d.K)) && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 &&
+    const bool narrow = d.Cin == 4, pairs = d.Cin == 8;
+    bool ok = d.Cin > 0 && (narrow || ((pairs || d.Cin % BK == 0) && d.Kpad == d.K)) && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 &&
               d.ntaps > 0 && d.ntaps <= kMaxTaps && d.taps_host && d.K == d.ntaps * d.Cin && d.in_D > 0 && d.in_H > 0 && d.in_W > 0 &&
               d.stride_d >= 1 && d.stride_h >= 1 && d.stride_w >= 1 && d.stride_d <= 8 && d.stride_h <= 8 && d.stride_w <= 8 &&
               d.M % (d.out_D * d.out_H * d.out_W) == 0;
@@ -1255,11 +1266,11 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
       p.flat_off[t] = (d.taps_host[4 * t + 2] - lo[2]) | ((d.taps_host[4 * t + 1] - lo[1]) << 8) |
                       ((d.taps_host[4 * t] - lo[0]) << 16);
     p.i2c_lo_d = lo[0]; p.i2c_lo_h = lo[1]; p.i2c_lo_w = lo[2];
-    p.chunks_per_tap = narrow ? 1 : d.Cin / BK;
-    p.i2c_narrow = narrow ? 1 : 0;
+    p.chunks_per_tap = (narrow || pairs) ? 1 : d.Cin / BK;
+    p.i2c_narrow = narrow ? 1 : pairs ? 2 : 0;
     p.ntaps = d.ntaps;
     const uint64_t n_img = (uint64_t)(d.M / (d.out_D * d.out_H * d.out_W));
-    if (encode_im2col_map(&g->map_a, d.A, n_img, d.in_D, d.in_H, d.in_W, d.in_Cs, lo, up, str, narrow)) { delete g; return 1; }
+    if (encode_im2col_map(&g->map_a, d.A, n_img, d.in_D, d.in_H, d.in_W, d.in_Cs, lo, up, str, narrow ? 4 : pairs ? 8 : BK)) { delete g; return 1; }
   } else if (d.a_mode == SVX_A_SLAB3) {
     const int live = d.cin_live > 0 ? d.cin_live : BK;
     bool ok = d.Cin == BK && live <= BK && d.in_Cs % 4 == 0 && d.in_c0 >= 0 && d.N <= 16 && d.block_n == S3_N &&

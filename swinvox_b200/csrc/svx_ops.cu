@@ -820,7 +820,12 @@ __global__ void interleave4_kernel(const svx_transpose_desc d, long long total) 
 #pragma unroll
     for (int c = 0; c < 4; ++c)
       if (c < d.C) v[c] = maybe_round(__ldg(src + (long long)c * d.P), d.round_tf32);
-    reinterpret_cast<float4*>(d.out)[idx] = make_float4(v[0], v[1], v[2], v[3]);
+    long long o = idx;
+    if (d.row_w > 0) {   // zero columns around every image row
+      const int y = p / d.row_w, x = p - y * d.row_w;
+      o = n * (long long)(d.P / d.row_w) * d.row_pitch + (long long)y * d.row_pitch + d.row_x0 + x;
+    }
+    reinterpret_cast<float4*>(d.out)[o] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -969,6 +974,9 @@ int metrics_launch(const svx_metrics_desc& d, void* stream) {
 
 int transpose_launch(const svx_transpose_desc& d, void* stream) {
   SVX_REQUIRE(d.in && d.out && d.N > 0 && d.C > 0 && d.P > 0 && d.Cs >= d.C, "transpose: bad description");
+  SVX_REQUIRE(d.row_w == 0 || (d.to_channels_last && d.Cs == 4 && d.C <= 4 && d.P % d.row_w == 0 && d.row_x0 >= 0 &&
+                               d.row_x0 + d.row_w <= d.row_pitch && al16(d.out)),
+              "transpose: padded rows need the 4-channel channels-last form");
   if (d.to_channels_last && d.Cs == 4 && d.C <= 4 && al16(d.out)) {
     const long long total = (long long)d.N * d.P;
     interleave4_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);

@@ -237,6 +237,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(4) << 61;                        // SWIZZLE_64B
   return d;
 }
+// K-major, 32-byte-swizzled operand tile: rows of 32 B (8 fp32 = one MMA K step), 8-row groups 256 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;                        // SWIZZLE_32B
+  return d;
+}
 // K-major operand tile WITHOUT swizzle: 8-row x 16-byte core matrices stored contiguously (128 B); `sbo` = bytes between
 // consecutive 8-row groups, `lbo` = bytes between consecutive 16-byte chunks along K.
 __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {

@@ -354,7 +354,8 @@ class Plan:
         lo = [min(t[a] for t in taps) for a in range(3)]
         up = [lo[a] + (rows_dhw[a] - 1) * stride[a] - ((x.D, x.H, x.W)[a] - 1) for a in range(3)]
         # whole 32-channel boxes, or 4-channel pixels (the image stems: eight 16-byte taps per k-chunk)
-        tma = ((cin % 32 == 0 or (cin == 4 and not os.environ.get("SVX_NO_IM2COL_NARROW")))
+        narrow_ok = (cin == 4 or (cin == 8 and len(taps) % 4 == 0)) and not os.environ.get("SVX_NO_IM2COL_NARROW")
+        tma = ((cin % 32 == 0 or narrow_ok)
                and len(taps) <= 64 and all(-16 <= v <= 15 for v in lo + up) and not os.environ.get("SVX_NO_IM2COL"))
         if tma:
             d.a_mode = A_IM2COL
@@ -631,8 +632,11 @@ class Plan:
         self._add("voxel_metrics", d, name, 0.0, 8.0 * B * P)
         return counts
 
-    def transpose(self, src, dst, N, Cc, P, Cs, to_channels_last, round_out=False, name=None):
+    def transpose(self, src, dst, N, Cc, P, Cs, to_channels_last, round_out=False, name=None, rows=None):
+        """rows = (row_w, row_pitch, row_x0): write the 4-channel channels-last image with zero columns around each row"""
         d = _lib.TransposeDesc()
+        if rows is not None:
+            d.row_w, d.row_pitch, d.row_x0 = rows
         d.inp, d.out = self.hold(src).data_ptr(), self.hold(dst).data_ptr()
         d.N, d.C, d.P, d.Cs = N, Cc, P, Cs
         d.to_channels_last = 1 if to_channels_last else 0

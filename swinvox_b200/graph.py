@@ -25,17 +25,32 @@ def _dev(plan):
 # --------------------------------------------------------------------------------------------------
 # ResNet-50 trunk: torchvision resnet50 children[:7]  (models/encoder.py:22-23,119)
 # --------------------------------------------------------------------------------------------------
+IMG_PITCH = 226   # staged image rows: one zero pixel, 224 pixels, one zero pixel
+
+
 def stage_image(plan, img, N):
-    """[N,3,224,224] NCHW fp32 tensor -> Act [N,224,224,4] (channels-last, zero fourth channel, TF32-rounded): the
-    layout both stems gather 16-byte pixels from.  Idempotent per plan."""
+    """[N,3,224,224] NCHW fp32 tensor -> Act [N,224,226,4] (channels-last, zero fourth channel, TF32-rounded, one zero
+    pixel left and right of every row): Swin's patch embedding reads it as 16-byte pixels, the ResNet stem as the
+    8-channel pixel pairs (2j-1, 2j) of its stride-2 window.  Idempotent per plan."""
     if isinstance(img, Act):
         return img
     key = ("nhwc4", img.data_ptr())
     if key not in plan.taps:
-        a = plan.new_act(N, 1, 224, 224, 4)
-        plan.transpose(img, a.buf, N, 3, 224 * 224, 4, True, round_out=True, name="image.nhwc4")
+        a = plan.new_act(N, 1, 224, IMG_PITCH, 4, zero=True)
+        plan.transpose(img, a.buf, N, 3, 224 * 224, 4, True, round_out=True, name="image.nhwc4", rows=(224, IMG_PITCH, 1))
         plan.taps[key] = a
     return plan.taps[key]
+
+
+def pack_stem_pairs(conv1, bn1, dev):
+    """ResNet conv1 (7x7, stride 2, pad 3) over pixel pairs: output ow reads padded pixels 2(ow-1) + kw, i.e. pairs
+    (ow-1) + kw//2, element kw%2 -> K = 7 kh x 4 pair taps x (2 pixels x 4 channels) = 224; kw = 7 and channel 3 are zero."""
+    w, b = E.fold_bn(conv1.weight, conv1.bias, bn1)            # [64, 3, 7, 7]
+    W = torch.zeros(64, 7, 4, 2, 4, dtype=torch.float32, device=w.device)
+    for kw in range(7):
+        W[:, :, kw // 2, kw % 2, :3] = w[:, :, :, kw].permute(0, 2, 1)
+    taps = [(0, kh - 3, pt - 1) for kh in range(7) for pt in range(4)]
+    return E.pack_matrix(W.reshape(64, 224), b, dev), taps
 
 
 def lower_resnet_trunk(plan, resnet, img, N):
@@ -43,10 +58,11 @@ def lower_resnet_trunk(plan, resnet, img, N):
     dev = _dev(plan)
     conv1, bn1 = resnet[0], resnet[1]
     x4 = stage_image(plan, img, N)
-    # 7x7 s2 p3 stem as an implicit GEMM over 49 one-pixel (4-channel) taps: K = 196
+    # 7x7 s2 p3 stem as an implicit GEMM over 28 pixel-pair taps of 8 channels (32-byte TMA im2col boxes): K = 224
+    pairs = Act(x4.buf.view(-1, 8), N, 1, 224, IMG_PITCH // 2, 8)
     stem = plan.new_act(N, 1, 112, 112, 64)
-    plan.conv(x4, E.pack_conv(conv1.weight, conv1.bias, bn1, dev, cin_pad=4), E.conv_taps(1, 7, 7, 0, 3, 3), stem,
-              stride=(1, 2, 2), act=ACT_RELU, name="resnet.stem")
+    pk, taps = pack_stem_pairs(conv1, bn1, dev)
+    plan.conv(pairs, pk, taps, stem, stride=(1, 2, 1), act=ACT_RELU, name="resnet.stem")
     x = plan.new_act(N, 1, 56, 56, 64)
     plan.pool(stem, x, (1, 3, 3), (1, 2, 2), (0, 1, 1), POOL_MAX, round_out=True, name="resnet.maxpool")
     for li in (4, 5, 6):
@@ -111,9 +127,10 @@ def lower_swin(plan, swin, img, N, stage_tail=None):
     pe = model.patch_embed
     x4 = stage_image(plan, img, N)
     emb = plan.new_act(N, 1, 56, 56, 96)
-    # patch embedding: 4x4 s4 conv = 16 one-pixel taps, K = 64
-    plan.conv(x4, E.pack_conv(pe.proj.weight, pe.proj.bias, None, dev, cin_pad=4), E.conv_taps(1, 4, 4, 0, 0, 0), emb,
-              stride=(1, 4, 4), name="swin.patch_embed.proj")
+    # patch embedding: 4x4 s4 conv = 16 one-pixel taps, K = 64 (image column x sits at staged column x + 1)
+    plan.conv(x4, E.pack_conv(pe.proj.weight, pe.proj.bias, None, dev, cin_pad=4),
+              [(0, kh, kw + 1) for kh in range(4) for kw in range(4)], emb, stride=(1, 4, 4), rows_dhw=(1, 56, 56),
+              name="swin.patch_embed.proj")
     x = plan.new_act(N, 1, 56, 56, 96)
     plan.layernorm_rows(emb, pe.norm.weight.detach().float().to(dev), pe.norm.bias.detach().float().to(dev), x,
                         eps=pe.norm.eps, round_out=False, name="swin.patch_embed.norm")

@@ -50,7 +50,7 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   if (d.a_mode == SVX_A_GATHER)
     SVX_REQUIRE(d.Cin % 4 == 0 && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.K == d.ntaps * d.Cin, "gemm: bad gather");
   else if (d.a_mode == SVX_A_IM2COL) {
-    SVX_REQUIRE((d.Cin == 4 || (d.Cin % 32 == 0 && d.Kpad == d.K)) && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.K == d.ntaps * d.Cin &&
+    SVX_REQUIRE((d.Cin == 4 || ((d.Cin == 8 || d.Cin % 32 == 0) && d.Kpad == d.K)) && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.K == d.ntaps * d.Cin &&
                     d.taps_host && d.ntaps <= 64 && d.M % (d.out_D * d.out_H * d.out_W) == 0,
                 "gemm: bad im2col");
     const int in_ext[3] = {d.in_D, d.in_H, d.in_W}, out_ext[3] = {d.out_D, d.out_H, d.out_W};
@@ -510,8 +510,10 @@ int transpose_launch(const svx_transpose_desc& d, void*) {
   for (long long n = 0; n < d.N; ++n)
     for (int p = 0; p < d.P; ++p) {
       if (d.to_channels_last) {
+        long long o = n * d.P + p;
+        if (d.row_w > 0) o = n * (long long)(d.P / d.row_w) * d.row_pitch + (long long)(p / d.row_w) * d.row_pitch + d.row_x0 + p % d.row_w;
         for (int c = 0; c < d.Cs; ++c)
-          d.out[(n * d.P + p) * (long long)d.Cs + c] = c < d.C ? rnd(d.in[(n * d.C + c) * (long long)d.P + p], d.round_tf32) : 0.f;
+          d.out[o * (long long)d.Cs + c] = c < d.C ? rnd(d.in[(n * d.C + c) * (long long)d.P + p], d.round_tf32) : 0.f;
       } else {
         for (int c = 0; c < d.C; ++c)
           d.out[(n * d.C + c) * (long long)d.P + p] = rnd(d.in[(n * d.P + p) * (long long)d.Cs + c], d.round_tf32);
