@@ -1,3 +1,1 @@
-python -m pytest tests/test_modules.py -m gpu -q -x 2>&1 | tail -3
-echo "== two lanes"; python bench.py 2>/dev/null | cut -c1-200
-echo "== one lane"; SVX_ENCODER_ONE_LANE=1 python bench.py 2>/dev/null | cut -c1-200
+for i in 1 2 3; do python bench.py --steps 20 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['e2e']['value'], d['clocks'])"; done
