@@ -160,6 +160,7 @@ class BatchedEvaluator:
         if self.on_batch is not None and self.cuda:
             for s in (self._slot, self._slot ^ 1):     # oldest first
                 self._deliver(s)
+        self._reduce_over_ranks()
         nt = len(self._tax_index)
         packed = torch.cat([self._iou[:nt].flatten(), self._fsc[:nt].flatten(), self._cnt[:nt], self._loss]).cpu().numpy()
         T = len(self.thresholds)
@@ -178,6 +179,39 @@ class BatchedEvaluator:
         if print_tables:
             print(self.tables(report), end="", file=file)
         return float(np.max(mean_iou)) if nt else 0.0, report
+
+    def _reduce_over_ranks(self):
+        """data-parallel evaluation (one process per GPU, each rank fed its own shard of the test set): the per-taxonomy
+        sums are added over the ranks -- the only exchange, one small all_reduce (NCCL on GPUs) -- so every rank
+        reports the global result.  Taxonomies are re-indexed in a rank-independent order first."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        keys = [None] * dist.get_world_size()
+        dist.all_gather_object(keys, list(self._tax_index))
+        order = []
+        for ks in keys:                      # rank 0's first-seen order, then what later ranks add
+            for k in ks:
+                if k not in order:
+                    order.append(k)
+        if len(order) > self._cap:
+            raise ValueError("more than %d taxonomies" % self._cap)
+        perm = torch.tensor([self._tax_index.get(k, -1) for k in order], device=self.dev)
+        have = (perm >= 0)
+        src = perm.clamp_min(0)
+
+        def remap(t):
+            out = torch.zeros_like(t)
+            sel = t[src] * (have.to(t.dtype).view(-1, *([1] * (t.dim() - 1))))
+            out[:len(order)] = sel
+            return out
+
+        self._iou, self._fsc, self._cnt = remap(self._iou), remap(self._fsc), remap(self._cnt)
+        self._tax_index = {k: i for i, k in enumerate(order)}
+        n = torch.tensor([float(self.n_samples)], dtype=torch.float64, device=self.dev)
+        for t in (self._iou, self._fsc, self._cnt, self._loss, n):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        self.n_samples = int(round(n.item()))
 
     def tables(self, report):
         """the text of core/test.py:222-262"""

@@ -87,3 +87,48 @@ def test_gloo_world2_matches_single_process(hostsim, tmp_path):
         assert torch.equal(r0[1], counts)
     finally:
         _lib._lib, _base.require_device, metrics.require_device = saved
+
+
+def _eval_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    _use_hostsim()
+    from oracle import modules as M
+    from swinvox_b200.evaluate import BatchedEvaluator
+    from test_evaluate import FakeRecon, make_data
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = M.default_cfg()
+    tax, images, gt = make_data(7, 2, 11)
+    mine = list(range(rank, 7, world))          # interleaved shards: the ranks meet the taxonomies in different orders
+    ev = BatchedEvaluator(FakeRecon(cfg, "cpu"), 2, 2)
+    for lo in range(0, len(mine), 2):
+        idx = mine[lo:lo + 2]
+        ev.submit([tax[i] for i in idx], images[idx], gt[idx])
+    max_iou, rep = ev.finish(print_tables=False)
+    torch.save((max_iou, rep), os.path.join(out_dir, f"eval{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_evaluator_reports_global_tables(hostsim, tmp_path):
+    """BatchedEvaluator on two ranks with disjoint shards: after finish() both ranks hold the single-process result"""
+    import numpy as np
+    from oracle import eval_loop as OE
+    from oracle import modules as M
+    from test_evaluate import FakeRecon, make_data
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_eval_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "eval0.pt"), weights_only=False)
+    r1 = torch.load(os.path.join(tmp_path, "eval1.pt"), weights_only=False)
+    cfg = M.default_cfg()
+    tax, images, gt = make_data(7, 2, 11)
+    rec = FakeRecon(cfg, "cpu")
+    refined = rec.refiner(rec.merger(None, images))
+    ti, tf, mi, mf = OE.accumulate(tax, list(refined), list(gt), cfg.TEST.VOXEL_THRESH)
+    for max_iou, rep in (r0, r1):
+        assert rep["n_samples"] == 7 and abs(max_iou - float(np.max(mi))) < 1e-6
+        np.testing.assert_allclose(rep["mean_iou"], mi, atol=1e-6)
+        np.testing.assert_allclose(rep["mean_fscore"], mf, atol=1e-6)
+        for tid in ti:
+            assert rep["test_iou"][tid]["n_samples"] == ti[tid]["n_samples"]
+            np.testing.assert_allclose(rep["test_iou"][tid]["iou"], ti[tid]["iou"], atol=1e-6)
