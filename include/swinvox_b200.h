@@ -193,6 +193,16 @@ typedef struct svx_bilinear_desc {
   int32_t N, IH, IW, OH, OW, C; int32_t round_tf32;
 } svx_bilinear_desc;
 
+/* Conv3d(Cin <= 12 -> 1, k3, s1, p1) + folded BatchNorm + LeakyReLU on the CUDA cores in fp32 (merger.py:50-54, layer6:
+ * 243 MACs per voxel -- a tensor-core tile would spend a full 128 x N x 8 instruction slot per 8 of them).
+ * in: zero-bordered channels-last volume [N, D+2, H+2, W+2, Cs], channels [c0, c0 + Cin); w: [27, 12] (tap-major
+ * kd, kh, kw; channel-minor, zero padded), bias[1]; out: planar [N, D*H*W].  H % 16 == 0, W == 32, Cs % 4 == 0. */
+typedef struct svx_conv3to1_desc {
+  const float* in; const float* w; const float* bias; float* out;
+  int32_t N, D, H, W, Cs, c0, Cin;
+  float slope;
+} svx_conv3to1_desc;
+
 /* per-voxel softmax over views + weighted sum (merger.py:98-104).
  * weights, coarse: [B, V, P]; out: [B, P]. */
 typedef struct svx_mergefuse_desc {
@@ -275,6 +285,7 @@ int svx_dwconv(const svx_dwconv_desc*, void* stream);
 int svx_view_attention(const svx_viewattn_desc*, void* stream);
 int svx_bilinear_add(const svx_bilinear_desc*, void* stream);
 int svx_merger_fuse(const svx_mergefuse_desc*, void* stream);
+int svx_conv3to1(const svx_conv3to1_desc*, void* stream);
 int svx_voxel_metrics(const svx_metrics_desc*, void* stream);
 int svx_transpose(const svx_transpose_desc*, void* stream);
 int svx_binvox_decode(const svx_binvox_decode_desc*, void* stream);
@@ -296,6 +307,7 @@ int svx_plan_add_dwconv(svx_plan*, const svx_dwconv_desc*);
 int svx_plan_add_view_attention(svx_plan*, const svx_viewattn_desc*);
 int svx_plan_add_bilinear_add(svx_plan*, const svx_bilinear_desc*);
 int svx_plan_add_merger_fuse(svx_plan*, const svx_mergefuse_desc*);
+int svx_plan_add_conv3to1(svx_plan*, const svx_conv3to1_desc*);
 int svx_plan_add_voxel_metrics(svx_plan*, const svx_metrics_desc*);
 int svx_plan_add_transpose(svx_plan*, const svx_transpose_desc*);
 /* Concurrency hints.  Ops are recorded into the current lane (default 0 = the caller's stream).  Ops of a side lane

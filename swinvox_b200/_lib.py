@@ -119,6 +119,11 @@ class TransposeDesc(C.Structure):
     ]
 
 
+class Conv3to1Desc(C.Structure):
+    _fields_ = [("inp", ptr), ("w", ptr), ("bias", ptr), ("out", ptr),
+                ("N", i32), ("D", i32), ("H", i32), ("W", i32), ("Cs", i32), ("c0", i32), ("Cin", i32), ("slope", f32)]
+
+
 class BinvoxDecodeDesc(C.Structure):
     _fields_ = [("payload", ptr), ("offsets", ptr), ("out", ptr), ("status", ptr),
                 ("B", i32), ("d0", i32), ("d1", i32), ("d2", i32), ("fix_coords", i32)]
@@ -136,7 +141,7 @@ class PreprocessDesc(C.Structure):
 
 # order must match svx_desc_sizes()
 DESC_TYPES = [GemmDesc, Im2colDesc, PoolDesc, LnRowsDesc, LnSampleDesc, WinAttnDesc, DwConvDesc,
-              ViewAttnDesc, BilinearDesc, MergeFuseDesc, MetricsDesc, TransposeDesc]
+              ViewAttnDesc, BilinearDesc, MergeFuseDesc, MetricsDesc, TransposeDesc, Conv3to1Desc]
 
 # op name -> (immediate symbol, plan_add symbol, descriptor type)
 OPS = {
@@ -152,6 +157,7 @@ OPS = {
     "merger_fuse": ("svx_merger_fuse", "svx_plan_add_merger_fuse", MergeFuseDesc),
     "voxel_metrics": ("svx_voxel_metrics", "svx_plan_add_voxel_metrics", MetricsDesc),
     "transpose": ("svx_transpose", "svx_plan_add_transpose", TransposeDesc),
+    "conv3to1": ("svx_conv3to1", "svx_plan_add_conv3to1", Conv3to1Desc),
 }
 
 OTHER_SYMBOLS = ["svx_abi_version", "svx_last_error", "svx_desc_sizes", "svx_device_info", "svx_plan_create",

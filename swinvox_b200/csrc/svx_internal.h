@@ -51,6 +51,7 @@ int dwconv_launch(const svx_dwconv_desc& d, void* stream);
 int viewattn_launch(const svx_viewattn_desc& d, void* stream);
 int bilinear_launch(const svx_bilinear_desc& d, void* stream);
 int mergefuse_launch(const svx_mergefuse_desc& d, void* stream);
+int conv3to1_launch(const svx_conv3to1_desc& d, void* stream);
 int metrics_launch(const svx_metrics_desc& d, void* stream);
 int transpose_launch(const svx_transpose_desc& d, void* stream);
 

@@ -718,6 +718,73 @@ __global__ void mergefuse_kernel(const svx_mergefuse_desc d, long long total4) {
   }
 }
 
+// ---- Conv3d(Cin <= 12 -> 1, k3, p1) + LeakyReLU in fp32 on the CUDA cores (merger layer6) -------------------------------
+// One CTA marches along depth over a 16-row x 32-column tile of the (h, w) plane: three input planes (18 x 34 voxels x 12
+// channels) ring in shared memory, each plane is loaded from HBM once per tile; a thread owns four consecutive ROWS of
+// one column, so every staged voxel it reads (3 float4) feeds up to three kh taps of up to four outputs from registers,
+// and the 32 lanes of a warp read 32 adjacent voxels (48 bytes apart: bank-conflict free).
+constexpr int C31_TH = 16, C31_TW = 32, C31_THREADS = (C31_TH / 4) * C31_TW;
+constexpr int C31_PLANE = (C31_TH + 2) * (C31_TW + 2);          // staged voxels per plane
+__global__ void __launch_bounds__(C31_THREADS) conv3to1_kernel(const svx_conv3to1_desc d) {
+  extern __shared__ float4 c31_smem[];                          // [4 planes][C31_PLANE][3 float4] + weights [27][3]
+  float4* wsm = c31_smem + 4 * C31_PLANE * 3;
+  const int tiles_h = d.H / C31_TH;
+  const int n = blockIdx.x / tiles_h, h0 = (blockIdx.x % tiles_h) * C31_TH;
+  const int Hp = d.H + 2, Wp = d.W + 2;
+  const int ty = (threadIdx.x / C31_TW) * 4, tx = threadIdx.x % C31_TW;   // rows ty..ty+3 of column tx
+  for (int i = threadIdx.x; i < 27 * 3; i += C31_THREADS) wsm[i] = __ldg(reinterpret_cast<const float4*>(d.w) + i);
+  const float bias = d.bias ? __ldg(d.bias) : 0.f;
+  auto load_plane = [&](int dp) {   // padded depth index dp -> ring slot dp % 4, asynchronously (one cp.async group)
+    if (dp < d.D + 2) {
+      const float* src = d.in + (((long long)n * (d.D + 2) + dp) * Hp + h0) * (long long)Wp * d.Cs + d.c0;
+      const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(c31_smem + (dp % 4) * C31_PLANE * 3));
+      for (int i = threadIdx.x; i < C31_PLANE * 3; i += C31_THREADS) {
+        const int v = i / 3, q = i - v * 3;                     // the tile's rows are contiguous in the padded volume
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + (long long)v * d.Cs + 4 * q) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_plane(0);
+  load_plane(1);
+  load_plane(2);
+  for (int dd = 0; dd < d.D; ++dd) {
+    load_plane(dd + 3);                                         // lands while depths dd .. dd+? compute
+    asm volatile("cp.async.wait_group 1;" ::: "memory");        // planes dd, dd+1, dd+2 have landed
+    __syncthreads();
+    float acc[4] = {bias, bias, bias, bias};
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const float4* pl = c31_smem + ((dd + kd) % 4) * C31_PLANE * 3;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float4* col = pl + (ty * (C31_TW + 2) + tx + kw) * 3;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {                            // six staged rows feed four outputs x three kh taps
+          const float4* vx = col + j * (C31_TW + 2) * 3;
+          const float4 a = vx[0], b = vx[1], c = vx[2];
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const int o = j - kh;
+            if (o < 0 || o > 3) continue;
+            const float4* wk = wsm + ((kd * 3 + kh) * 3 + kw) * 3;
+            const float4 wa = wk[0], wb = wk[1], wc = wk[2];
+            float s = acc[o];
+            s = fmaf(a.x, wa.x, s); s = fmaf(a.y, wa.y, s); s = fmaf(a.z, wa.z, s); s = fmaf(a.w, wa.w, s);
+            s = fmaf(b.x, wb.x, s); s = fmaf(b.y, wb.y, s); s = fmaf(b.z, wb.z, s); s = fmaf(b.w, wb.w, s);
+            s = fmaf(c.x, wc.x, s); s = fmaf(c.y, wc.y, s); s = fmaf(c.z, wc.z, s); s = fmaf(c.w, wc.w, s);
+            acc[o] = s;
+          }
+        }
+      }
+    }
+    float* orow = d.out + (((long long)n * d.D + dd) * d.H + h0 + ty) * d.W + tx;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) orow[r * d.W] = acc[r] > 0.f ? acc[r] : acc[r] * d.slope;
+    __syncthreads();   // the slot of plane dd is overwritten by the load issued two iterations from now
+  }
+}
+
 // ---- sigmoid / threshold / I,U,TP,FP,FN counters (core/test.py:141-164) -----------------------------------
 constexpr int kMaxThresh = 8;
 __global__ void __launch_bounds__(256) metrics_kernel(const svx_metrics_desc d, int chunks) {
@@ -955,6 +1022,23 @@ int mergefuse_launch(const svx_mergefuse_desc& d, void* stream) {
   const long long total4 = (long long)d.B * (d.P / 4);
   mergefuse_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(d, total4);
   SVX_LAUNCH_OK("mergefuse_kernel");
+  return 0;
+}
+
+int conv3to1_launch(const svx_conv3to1_desc& d, void* stream) {
+  SVX_REQUIRE(d.in && d.w && d.out && d.N > 0 && d.D > 0, "conv3to1: null operand");
+  SVX_REQUIRE(d.Cin >= 1 && d.Cin <= 12 && d.W == C31_TW && d.H % C31_TH == 0 && d.Cs % 4 == 0 && d.c0 % 4 == 0 &&
+                  d.c0 + 12 <= d.Cs && al16(d.in) && al16(d.w) && al16(d.out),
+              "conv3to1: needs W == 32, H %% 16 == 0, 16-byte aligned 12-channel reads (Cin=%d W=%d H=%d Cs=%d c0=%d)",
+              d.Cin, d.W, d.H, d.Cs, d.c0);
+  const int smem = (4 * C31_PLANE * 3 + 27 * 3) * (int)sizeof(float4);
+  static bool configured = false;
+  if (!configured) {
+    SVX_CUDA_OK(cudaFuncSetAttribute(conv3to1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  conv3to1_kernel<<<d.N * (d.H / C31_TH), C31_THREADS, smem, (cudaStream_t)stream>>>(d);
+  SVX_LAUNCH_OK("conv3to1_kernel");
   return 0;
 }
 

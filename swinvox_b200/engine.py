@@ -615,6 +615,24 @@ class Plan:
         self._add("bilinear_add", d, name)
         return out
 
+    def conv3_to1(self, x, weight, bias, bn, out, slope, name=None):
+        """Conv3d(Cin <= 12 -> 1, k3, p1) + BatchNorm (folded) + LeakyReLU in fp32 on the CUDA cores, over the (1,1,1)
+        zero-bordered volume `x` (channels [c0, c0 + Cin)); out: planar [N, D*H*W] tensor"""
+        assert x.pad == (1, 1, 1)
+        w, b = fold_bn(weight, bias, bn)                     # [1, Cin, 3, 3, 3]
+        cin = w.shape[1]
+        W = torch.zeros(27, 12, dtype=torch.float32, device=w.device)
+        W[:, :cin] = w[0].permute(1, 2, 3, 0).reshape(27, cin)
+        d = _lib.Conv3to1Desc()
+        d.inp = self.hold(x).buf.data_ptr()
+        d.w, d.bias = self.hold(W.contiguous().to(self.device)).data_ptr(), self.hold(b.float().to(self.device)).data_ptr()
+        d.out = self.hold(out).data_ptr()
+        vD, vH, vW = x.inner
+        d.N, d.D, d.H, d.W, d.Cs, d.c0, d.Cin, d.slope = x.N, vD, vH, vW, x.Cs, x.c0, cin, slope
+        M = x.N * vD * vH * vW
+        self._add("conv3to1", d, name, 2.0 * M * 27 * cin, 4.0 * M * (cin + 1))
+        return out
+
     def merger_fuse(self, weights, coarse, out, B, V, P, name=None):
         d = _lib.MergeFuseDesc()
         d.weights, d.coarse, d.out = self.hold(weights).data_ptr(), self.hold(coarse).data_ptr(), self.hold(out).data_ptr()

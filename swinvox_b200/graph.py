@@ -403,12 +403,11 @@ def lower_merger(plan, mer, raw, coarse, B, V):
             wh[:, 16 * gi:16 * gi + 9] = w5[:, 9 * (2 * half + gi):9 * (2 * half + gi) + 9]
         pk = E.pack_conv3_slab(wh, b5 if half else None, None, dev, n_logical=16)
         plan.conv3_slab(box(cat, 32 * half), pk, t, 25, act=ACT_LEAKY if half else ACT_NONE, act_param=slope,
-                        residual=t if half else None, res_after_act=False, round_out=bool(half),
+                        residual=t if half else None, res_after_act=False, round_out=False,   # layer6 reads it in fp32
                         name=f"merger.layer5.{'ab'[half]}")
+    # layer6 (9 -> 1 channel): 243 MACs per voxel, fp32 on the CUDA cores (a tensor-core tile is issue-bound here)
     wts = plan.empty(N, 32768)
-    wact = Act(wts.view(-1, 1), N, 32, 32, 32, 1, 0)
-    plan.conv3_slab(box(t, 0), E.pack_conv3_slab(mer.layer6[0].weight, mer.layer6[0].bias, mer.layer6[1], dev), wact, 9,
-                    act=ACT_LEAKY, act_param=slope, name="merger.layer6")
+    plan.conv3_to1(box(t, 0), mer.layer6[0].weight, mer.layer6[0].bias, mer.layer6[1], wts, slope, name="merger.layer6")
     merged = plan.empty(B, 32768)
     plan.merger_fuse(wts, coarse, merged, B, V, 32768, name="merger.softmax_fuse")
     return merged, wts

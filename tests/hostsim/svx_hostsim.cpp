@@ -464,6 +464,30 @@ int bilinear_launch(const svx_bilinear_desc& d, void*) {
   return 0;
 }
 
+int conv3to1_launch(const svx_conv3to1_desc& d, void*) {
+  SVX_REQUIRE(d.in && d.w && d.out && d.Cin >= 1 && d.Cin <= 12 && d.W == 32 && d.H % 16 == 0 && d.Cs % 4 == 0 && d.c0 % 4 == 0,
+              "conv3to1: bad description");
+  const long long Hp = d.H + 2, Wp = d.W + 2, Dp = d.D + 2;
+#pragma omp parallel for
+  for (long long r = 0; r < (long long)d.N * d.D * d.H * d.W; ++r) {
+    const int w = (int)(r % d.W);
+    long long t = r / d.W;
+    const int h = (int)(t % d.H); t /= d.H;
+    const int dd = (int)(t % d.D);
+    const long long n = t / d.D;
+    float acc = d.bias ? d.bias[0] : 0.f;
+    for (int kd = 0; kd < 3; ++kd)
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+          const float* px = d.in + (((n * Dp + dd + kd) * Hp + h + kh) * Wp + w + kw) * d.Cs + d.c0;
+          const float* wr = d.w + ((kd * 3 + kh) * 3 + kw) * 12;
+          for (int c = 0; c < d.Cin; ++c) acc = fmaf(px[c], wr[c], acc);
+        }
+    d.out[r] = acc > 0.f ? acc : acc * d.slope;
+  }
+  return 0;
+}
+
 int mergefuse_launch(const svx_mergefuse_desc& d, void*) {
   for (long long b = 0; b < d.B; ++b)
     for (int p = 0; p < d.P; ++p) {

@@ -297,6 +297,28 @@ def test_decoder_tail_epilogue(dev):
     assert got[:, 9:].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("cin,c0,dims", [(9, 0, (5, 16, 32)), (12, 4, (3, 32, 32)), (1, 8, (2, 16, 32))])
+def test_conv3d_single_output_fp32(dev, cin, c0, dims):
+    """merger layer6 form: Conv3d(cin -> 1, k3, p1) + BatchNorm + LeakyReLU in fp32 on the CUDA cores"""
+    DEV = dev
+    torch.manual_seed(cin + c0)
+    n, (D, H, W) = 2, dims
+    x = torch.randn(n, cin, D, H, W)
+    conv = torch.nn.Conv3d(cin, 1, 3, padding=1)
+    bn = rand_bn(torch.nn.BatchNorm3d(1))
+    p = E.Plan(DEV)
+    vol = p.new_act(n, D, H, W, 32, pad=(1, 1, 1))
+    vol.view()[..., c0:c0 + cin] = x.permute(0, 2, 3, 4, 1).to(DEV)
+    vol.view()[..., c0 + cin:] = 7.0                      # channels past Cin carry zero weights, whatever they hold
+    out = p.empty(n, D * H * W)
+    p.conv3_to1(E.Act(vol.buf, n, D + 2, H + 2, W + 2, 32, c0, (1, 1, 1)), conv.weight, conv.bias, bn, out, 0.2)
+    p.run()
+    sync(DEV)
+    wf, bf = E.fold_bn(conv.weight, conv.bias, bn)
+    ref = F.leaky_relu(F.conv3d(x.double(), wf.double(), bf.double(), padding=1), 0.2)
+    assert rel_err(out.view(n, 1, D, H, W), ref) < 1e-5
+
+
 @pytest.mark.parametrize("cout,ind", [(1, (3, 4, 5)), (4, (2, 3, 6)), (1, (16, 16, 16))])
 def test_convtranspose3d_fused_classes(dev, cout, ind):
     """all eight parity classes in N (SVX_EPI_CONVT8): the refiner's layer8 form, (x + convT(y)) * 0.5"""
