@@ -128,6 +128,41 @@ __global__ void pool_kernel(const svx_pool_desc d, long long total) {
   }
 }
 
+// ---- MaxPool2d(3, stride 2, pad 1), channels-last (the ResNet stem's pool): a thread marches down the output rows of one
+// (column, 4-channel group); per output row it reads two NEW input rows (3 float4 each, horizontal max first) and reuses
+// the horizontal max of the row shared with the previous output row: 6 loads per output instead of 9.
+__global__ void __launch_bounds__(256) maxpool3s2_kernel(const svx_pool_desc d, int cols_per_block) {
+  const int c4n = d.C >> 2;
+  const int c4 = threadIdx.x % c4n;
+  const int ow = blockIdx.x * cols_per_block + threadIdx.x / c4n;
+  const long long n = blockIdx.y;
+  if (ow >= d.OW) return;
+  const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  auto hmax = [&](int ih) -> float4 {
+    if ((unsigned)ih >= (unsigned)d.H) return ninf;
+    const float* row = d.in + ((n * d.H + ih) * (long long)d.W) * d.in_Cs + c4 * 4;
+    float4 m = ninf;
+#pragma unroll
+    for (int k = -1; k <= 1; ++k) {
+      const int iw = 2 * ow + k;
+      if ((unsigned)iw < (unsigned)d.W) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row + (long long)iw * d.in_Cs));
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    return m;
+  };
+  float4 prev = hmax(-1);
+  for (int oh = 0; oh < d.OH; ++oh) {
+    const float4 a = hmax(2 * oh), b = hmax(2 * oh + 1);
+    float4 o;
+    o.x = maybe_round(fmaxf(prev.x, fmaxf(a.x, b.x)), d.round_tf32); o.y = maybe_round(fmaxf(prev.y, fmaxf(a.y, b.y)), d.round_tf32);
+    o.z = maybe_round(fmaxf(prev.z, fmaxf(a.z, b.z)), d.round_tf32); o.w = maybe_round(fmaxf(prev.w, fmaxf(a.w, b.w)), d.round_tf32);
+    *reinterpret_cast<float4*>(d.out + ((n * d.OH + oh) * (long long)d.OW + ow) * d.out_Cs + c4 * 4) = o;
+    prev = b;
+  }
+}
+
 // ---- row LayerNorm: one warp per row ---------------------------------------------------------------
 __global__ void lnrows_kernel(const svx_lnrows_desc d) {
   const int lane = threadIdx.x & 31;
@@ -912,6 +947,15 @@ int pool_launch(const svx_pool_desc& d, void* stream) {
   SVX_REQUIRE(d.in && d.out && d.C % 4 == 0 && d.in_Cs % 4 == 0 && d.out_Cs % 4 == 0 && al16(d.in) && al16(d.out),
               "pool: channels must be multiples of 4 and pointers 16-byte aligned");
   const long long total = (long long)d.N * d.OD * d.OH * d.OW * (d.C / 4);
+  if (d.mode == SVX_POOL_MAX && d.D == 1 && d.OD == 1 && d.KD == 1 && d.KH == 3 && d.KW == 3 && d.SH == 2 && d.SW == 2 &&
+      d.PD == 0 && d.PH == 1 && d.PW == 1 && d.C / 4 <= 256 && 256 % (d.C / 4) == 0 && d.N <= 65535 &&
+      d.OH == (d.H - 1) / 2 + 1 && d.OW == (d.W - 1) / 2 + 1) {
+    const int cols = 256 / (d.C / 4);
+    dim3 grid((d.OW + cols - 1) / cols, d.N);
+    maxpool3s2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, cols);
+    SVX_LAUNCH_OK("maxpool3s2_kernel");
+    return 0;
+  }
   pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
   SVX_LAUNCH_OK("pool_kernel");
   return 0;

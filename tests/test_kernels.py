@@ -365,6 +365,21 @@ def test_decoder_tail_fused_classes(dev):
     assert raw.buf.view(3, 10, 12, 14, 32)[:, 0].abs().max().item() == 0.0   # the zero border stays untouched
 
 
+@pytest.mark.parametrize("C,H,W,N", [(64, 112, 112, 2), (32, 9, 13, 3), (256, 7, 7, 1), (8, 2, 2, 2)])
+def test_maxpool_3x3_stride2(dev, C, H, W, N):
+    """the ResNet stem's MaxPool2d(3, 2, 1): row-marching kernel, odd sizes, one-pixel outputs; exact (max is exact)"""
+    DEV = dev
+    torch.manual_seed(C + H)
+    y = torch.randn(N, C, H, W)
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    p = E.Plan(DEV)
+    mp = p.new_act(N, 1, OH, OW, C)
+    p.pool(act_from_nchw(y, DEV), mp, (1, 3, 3), (1, 2, 2), (0, 1, 1), E.POOL_MAX)
+    p.run()
+    sync(DEV)
+    assert torch.equal(to_nchw(mp).squeeze(2), F.max_pool2d(y, 3, 2, 1))
+
+
 def test_im2col_and_pools(dev):
     DEV = dev
     torch.manual_seed(4)
