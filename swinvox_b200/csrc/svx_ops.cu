@@ -83,6 +83,51 @@ __global__ void im2col_kernel(const svx_im2col_desc d, long long total4, int K) 
   }
 }
 
+// ---- im2col of a single-channel volume, one CTA per output row line (n, od, oh): the KD x KH x rowlen input region that
+// the OW windows of the line share is staged in shared memory once (zero-filled outside the volume), a look-up table
+// maps k -> offset inside the region, and the CTA writes the OW x Kpad block with coalesced 16-byte stores.
+constexpr int kI2cRegionMax = 4096, kI2cKMax = 512;
+__global__ void __launch_bounds__(256) im2col_line_kernel(const svx_im2col_desc d, int K) {
+  __shared__ float region[kI2cRegionMax];
+  __shared__ short lut[kI2cKMax];
+  const int rowlen = (d.OW - 1) * d.stride + d.KW;
+  long long line = blockIdx.x;
+  const int oh = (int)(line % d.OH); line /= d.OH;
+  const int od = (int)(line % d.OD);
+  const long long n = line / d.OD;
+  const float* src = d.in + n * d.s_n;
+  for (int i = threadIdx.x; i < d.KD * d.KH * rowlen; i += blockDim.x) {
+    const int x = i % rowlen, t = i / rowlen;
+    const int kh = t % d.KH, kd = t / d.KH;
+    const int id = od * d.stride - d.pad_d + kd, ih = oh * d.stride - d.pad_h + kh, iw = x - d.pad_w;
+    float v = 0.f;
+    if ((unsigned)id < (unsigned)d.D && (unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W)
+      v = __ldg(src + id * d.s_d + ih * d.s_h + iw * d.s_w);
+    region[i] = maybe_round(v, d.round_tf32);
+  }
+  for (int k = threadIdx.x; k < d.Kpad; k += blockDim.x) {
+    short o = -1;
+    if (k < K) {
+      const int kw = k % d.KW, t = k / d.KW;
+      o = (short)(((t / d.KH) * d.KH + t % d.KH) * rowlen + kw);
+    }
+    lut[k] = o;
+  }
+  __syncthreads();
+  const int K4 = d.Kpad >> 2;
+  float* dst = d.out + ((n * d.OD + od) * d.OH + oh) * (long long)d.OW * d.Kpad;
+  for (int i = threadIdx.x; i < d.OW * K4; i += blockDim.x) {
+    const int ow = i / K4, k0 = (i - ow * K4) * 4;
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int o = lut[k0 + q];
+      v[q] = o >= 0 ? region[o + ow * d.stride] : 0.f;
+    }
+    *reinterpret_cast<float4*>(dst + (long long)ow * d.Kpad + k0) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 // ---- pooling ------------------------------------------------------------------------------------
 __global__ void pool_kernel(const svx_pool_desc d, long long total) {
   const int c4n = d.C >> 2;
@@ -938,6 +983,12 @@ int im2col_launch(const svx_im2col_desc& d, void* stream) {
   SVX_REQUIRE(d.in && d.out && d.N > 0 && K > 0 && d.Kpad >= K, "im2col: bad description");
   SVX_REQUIRE(d.Kpad % 4 == 0 && al16(d.out), "im2col: Kpad must be a multiple of 4 and the output 16-byte aligned");
   const long long total4 = (long long)d.N * d.OD * d.OH * d.OW * (d.Kpad / 4);
+  const long long lines = (long long)d.N * d.OD * d.OH;
+  if (d.C == 1 && d.Kpad <= kI2cKMax && d.KD * d.KH * ((d.OW - 1) * d.stride + d.KW) <= kI2cRegionMax && lines < 0x7fffffffLL) {
+    im2col_line_kernel<<<(int)lines, 256, 0, (cudaStream_t)stream>>>(d, K);
+    SVX_LAUNCH_OK("im2col_line_kernel");
+    return 0;
+  }
   im2col_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(d, total4, K);
   SVX_LAUNCH_OK("im2col_kernel");
   return 0;

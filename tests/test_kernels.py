@@ -380,6 +380,26 @@ def test_maxpool_3x3_stride2(dev, C, H, W, N):
     assert torch.equal(to_nchw(mp).squeeze(2), F.max_pool2d(y, 3, 2, 1))
 
 
+@pytest.mark.parametrize("D,k,stride,pad,kpad", [(32, 5, 2, 2, 128), (8, 3, 1, 1, 28), (9, 4, 2, 0, 64)])
+def test_im2col_single_channel_volume(dev, D, k, stride, pad, kpad):
+    """refiner layer1's window gather (one channel, k^3 windows) -- the shared-memory line kernel; exact copy"""
+    DEV = dev
+    torch.manual_seed(D + k)
+    B = 2
+    vol = torch.randn(B, D, D, D)
+    O = (D + 2 * pad - k) // stride + 1
+    p = E.Plan(DEV)
+    cols = p.im2col(vol.to(DEV), (D ** 3, 0, D * D, D, 1), B, 1, (D, D, D), (k, k, k), stride, (pad, pad, pad), (O, O, O), kpad,
+                    round_out=False)
+    p.run()
+    sync(DEV)
+    padded = F.pad(vol, (pad,) * 6)
+    win = padded.unfold(1, k, stride).unfold(2, k, stride).unfold(3, k, stride)      # [B, O, O, O, k, k, k]
+    ref = win.reshape(B * O ** 3, k ** 3)
+    got = cols.view().reshape(B * O ** 3, kpad).cpu()
+    assert torch.equal(got[:, :k ** 3], ref) and (kpad == k ** 3 or got[:, k ** 3:].abs().max().item() == 0.0)
+
+
 def test_im2col_and_pools(dev):
     DEV = dev
     torch.manual_seed(4)
