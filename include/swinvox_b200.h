@@ -129,6 +129,25 @@ typedef struct svx_gemm_desc {
   int64_t c2_sd, c2_sh, c2_sw;  /* ... and in epi_out2 */
 } svx_gemm_desc;
 
+/*
+ * The MLP of one Swin block (timm Mlp: fc1 -> nn.GELU() -> fc2; swin_transformer.py:71-94 runs it through
+ * timm's SwinTransformerBlock) together with the block's second residual, as ONE kernel:
+ *   out[r, :] = residual[r, :] + W2 * round_tf32(gelu(W1 * x[r, :] + b1)) + b2
+ * The 4C-wide hidden activation never leaves the SM: per 128-row tile the fc1 accumulator (TMEM) goes through the
+ * GELU epilogue into shared memory in the 128B-swizzled operand layout and is contracted with W2 straight away.
+ * x: [M, C] with row pitch ldx (the TF32-rounded norm2 output); W1: [hidden, C], W2: [C, hidden], both K-contiguous
+ * and pre-rounded to TF32; b1[hidden], b2[C]; residual / out: [M, C] with row pitch ldo (may alias).
+ * C = 96 or 192, hidden = 4*C; pointers 16-byte aligned, pitches multiples of 4.
+ */
+typedef struct svx_mlp_desc {
+  const float* x; int64_t ldx;
+  const float* W1; const float* b1;
+  const float* W2; const float* b2;
+  const float* residual; float* out; int64_t ldo;
+  int32_t M, C, hidden;
+  int32_t round_tf32;       /* round the stored result to TF32 */
+} svx_mlp_desc;
+
 /* Explicit im2col for tiny channel counts (ResNet stem 7x7 s2 on 3 channels, Swin patch-embed
  * 4x4 s4, refiner layer1 4x4x4 on 1 channel).  Input addressed with arbitrary element strides
  * so NCHW user tensors are read in place.  Row r=(n,od,oh,ow); k=((kd*KH+kh)*KW+kw)*C+c. */
@@ -276,6 +295,7 @@ int svx_device_info(int device, int32_t* sm_count, int32_t* cc_major, int32_t* c
 
 /* ---- immediate launches (one op on `stream`) ----------------------------------------- */
 int svx_gemm(const svx_gemm_desc*, void* stream);
+int svx_mlp(const svx_mlp_desc*, void* stream);
 int svx_im2col(const svx_im2col_desc*, void* stream);
 int svx_pool(const svx_pool_desc*, void* stream);
 int svx_layernorm_rows(const svx_lnrows_desc*, void* stream);
@@ -298,6 +318,7 @@ svx_plan* svx_plan_create(void);
 void svx_plan_destroy(svx_plan*);
 int svx_plan_num_ops(const svx_plan*);
 int svx_plan_add_gemm(svx_plan*, const svx_gemm_desc*);
+int svx_plan_add_mlp(svx_plan*, const svx_mlp_desc*);
 int svx_plan_add_im2col(svx_plan*, const svx_im2col_desc*);
 int svx_plan_add_pool(svx_plan*, const svx_pool_desc*);
 int svx_plan_add_layernorm_rows(svx_plan*, const svx_lnrows_desc*);

@@ -124,6 +124,12 @@ class Conv3to1Desc(C.Structure):
                 ("N", i32), ("D", i32), ("H", i32), ("W", i32), ("Cs", i32), ("c0", i32), ("Cin", i32), ("slope", f32)]
 
 
+class MlpDesc(C.Structure):
+    _fields_ = [("x", ptr), ("ldx", i64), ("W1", ptr), ("b1", ptr), ("W2", ptr), ("b2", ptr),
+                ("residual", ptr), ("out", ptr), ("ldo", i64),
+                ("M", i32), ("C", i32), ("hidden", i32), ("round_tf32", i32)]
+
+
 class BinvoxDecodeDesc(C.Structure):
     _fields_ = [("payload", ptr), ("offsets", ptr), ("out", ptr), ("status", ptr),
                 ("B", i32), ("d0", i32), ("d1", i32), ("d2", i32), ("fix_coords", i32)]
@@ -141,7 +147,7 @@ class PreprocessDesc(C.Structure):
 
 # order must match svx_desc_sizes()
 DESC_TYPES = [GemmDesc, Im2colDesc, PoolDesc, LnRowsDesc, LnSampleDesc, WinAttnDesc, DwConvDesc,
-              ViewAttnDesc, BilinearDesc, MergeFuseDesc, MetricsDesc, TransposeDesc, Conv3to1Desc]
+              ViewAttnDesc, BilinearDesc, MergeFuseDesc, MetricsDesc, TransposeDesc, Conv3to1Desc, MlpDesc]
 
 # op name -> (immediate symbol, plan_add symbol, descriptor type)
 OPS = {
@@ -158,6 +164,7 @@ OPS = {
     "voxel_metrics": ("svx_voxel_metrics", "svx_plan_add_voxel_metrics", MetricsDesc),
     "transpose": ("svx_transpose", "svx_plan_add_transpose", TransposeDesc),
     "conv3to1": ("svx_conv3to1", "svx_plan_add_conv3to1", Conv3to1Desc),
+    "mlp": ("svx_mlp", "svx_plan_add_mlp", MlpDesc),
 }
 
 OTHER_SYMBOLS = ["svx_abi_version", "svx_last_error", "svx_desc_sizes", "svx_device_info", "svx_plan_create",

@@ -25,7 +25,7 @@ int fail(const char* fmt, ...) {
 
 enum OpKind {
   OP_GEMM, OP_IM2COL, OP_POOL, OP_LNROWS, OP_LNSAMPLE, OP_WINATTN, OP_DWCONV, OP_VIEWATTN, OP_BILINEAR,
-  OP_MERGEFUSE, OP_METRICS, OP_TRANSPOSE, OP_CONV3TO1, OP_JOIN
+  OP_MERGEFUSE, OP_METRICS, OP_TRANSPOSE, OP_CONV3TO1, OP_MLP, OP_JOIN
 };
 
 struct Op {
@@ -44,8 +44,10 @@ struct Op {
     svx_metrics_desc metrics;
     svx_conv3to1_desc conv3to1;
     svx_transpose_desc transpose;
+    svx_mlp_desc mlp;
   } u;
   GemmPrepared* prepared = nullptr;
+  MlpPrepared* mlp_prepared = nullptr;
   int lane = 0;   // 0: the caller's stream; k > 0: side stream k (ops of different lanes may overlap until the next join)
 };
 
@@ -64,6 +66,7 @@ int launch_op(Op& op, void* stream) {
     case OP_METRICS: return metrics_launch(op.u.metrics, stream);
     case OP_TRANSPOSE: return transpose_launch(op.u.transpose, stream);
     case OP_CONV3TO1: return conv3to1_launch(op.u.conv3to1, stream);
+    case OP_MLP: return mlp_launch(op.u.mlp, op.mlp_prepared, stream);
     case OP_JOIN: return 0;
   }
   return fail("unknown op kind");
@@ -98,7 +101,7 @@ int svx_desc_sizes(int32_t* sizes, int n) {
                        (int32_t)sizeof(svx_dwconv_desc),   (int32_t)sizeof(svx_viewattn_desc),
                        (int32_t)sizeof(svx_bilinear_desc), (int32_t)sizeof(svx_mergefuse_desc),
                        (int32_t)sizeof(svx_metrics_desc),  (int32_t)sizeof(svx_transpose_desc),
-                       (int32_t)sizeof(svx_conv3to1_desc)};
+                       (int32_t)sizeof(svx_conv3to1_desc), (int32_t)sizeof(svx_mlp_desc)};
   const int have = (int)(sizeof(s) / sizeof(s[0]));
   for (int i = 0; i < n && i < have; ++i) sizes[i] = s[i];
   return have;
@@ -133,6 +136,10 @@ int svx_gemm(const svx_gemm_desc* d, void* stream) {
   if (!d) return fail("svx_gemm: null descriptor");
   return gemm_launch(*d, nullptr, stream);
 }
+int svx_mlp(const svx_mlp_desc* d, void* stream) {
+  if (!d) return fail("svx_mlp: null descriptor");
+  return mlp_launch(*d, nullptr, stream);
+}
 SVX_IMMEDIATE(svx_im2col, svx_im2col_desc, im2col_launch)
 SVX_IMMEDIATE(svx_pool, svx_pool_desc, pool_launch)
 SVX_IMMEDIATE(svx_layernorm_rows, svx_lnrows_desc, lnrows_launch)
@@ -152,6 +159,8 @@ void svx_plan_destroy(svx_plan* p) {
   if (!p) return;
   for (auto& op : p->ops)
     if (op.prepared) gemm_prepared_free(op.prepared);
+  for (auto& op : p->ops)
+    if (op.mlp_prepared) mlp_prepared_free(op.mlp_prepared);
 #ifndef SVX_HOSTSIM
   if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
   for (int k = 0; k < kMaxLanes; ++k) {
@@ -171,6 +180,17 @@ int svx_plan_add_gemm(svx_plan* p, const svx_gemm_desc* d) {
   op.kind = OP_GEMM;
   op.u.gemm = *d;
   if (int rc = gemm_prepare(*d, &op.prepared)) return rc;
+  op.lane = p->cur_lane;
+  p->ops.push_back(op);
+  return 0;
+}
+
+int svx_plan_add_mlp(svx_plan* p, const svx_mlp_desc* d) {
+  if (!p || !d) return fail("svx_plan_add_mlp: null argument");
+  Op op;
+  op.kind = OP_MLP;
+  op.u.mlp = *d;
+  if (int rc = mlp_prepare(*d, &op.mlp_prepared)) return rc;
   op.lane = p->cur_lane;
   p->ops.push_back(op);
   return 0;

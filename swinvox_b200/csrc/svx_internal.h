@@ -41,6 +41,10 @@ struct GemmPrepared;
 int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out);
 void gemm_prepared_free(GemmPrepared* p);
 int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void* stream);
+struct MlpPrepared;
+int mlp_prepare(const svx_mlp_desc& d, MlpPrepared** out);
+void mlp_prepared_free(MlpPrepared* p);
+int mlp_launch(const svx_mlp_desc& d, MlpPrepared* prepared, void* stream);
 
 int im2col_launch(const svx_im2col_desc& d, void* stream);
 int pool_launch(const svx_pool_desc& d, void* stream);

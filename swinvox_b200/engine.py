@@ -56,6 +56,11 @@ def choose_block_n(n, rows=None, gather=False, heavy_epilogue=False, k=None):
     return best
 
 
+def mlp_fusable(c, hidden):
+    """shapes the fused MLP kernel (svx_mlp.cu) is instantiated for: Swin stages 0 and 1"""
+    return c in (96, 192) and hidden == 4 * c and not os.environ.get("SVX_NO_MLP_FUSION")
+
+
 def round_up(x, m):
     return (x + m - 1) // m * m
 
@@ -422,6 +427,28 @@ class Plan:
         n_out = pack.N // 8 if pool8 else pack.N
         self._add("gemm", d, name or "linear", 2.0 * d.M * pack.N * pack.K,
                   4.0 * (d.M * pack.K + d.M * n_out * (2 if residual is not None else 1) + pack.N * pack.K))
+        return out
+
+    def mlp(self, x, pack1, pack2, out, residual, round_out=False, name=None):
+        """timm Mlp (fc1 -> GELU -> fc2) + the block's second residual as one kernel (svx_mlp_desc): the hidden activation
+        stays on the SM.  x: TF32-rounded norm2 output [pixels, C]; pack1 / pack2: fc1 [4C, C] / fc2 [C, 4C] packs."""
+        Cc, hid = pack1.K, pack1.N
+        assert mlp_fusable(Cc, hid) and pack2.K == hid and pack2.N == Cc and x.C == Cc and out.C == Cc
+        assert x.pixels == out.pixels == residual.pixels and not any(x.pad) and not any(out.pad) and not any(residual.pad)
+        assert x.c0 == 0 and out.c0 == 0 and residual.c0 == 0 and residual.Cs == out.Cs
+        for pk in (pack1, pack2):   # unpadded [N, K] matrices: the kernel has its own tiling
+            if pk.W is None:
+                pk.block_n = 32
+                pk.finalize()
+            assert tuple(pk.W.shape) == (pk.N, pk.K), "mlp: packs must not be padded"
+        d = _lib.MlpDesc()
+        d.x, d.ldx = self.hold(x).buf.data_ptr(), x.Cs
+        d.W1, d.b1 = self.hold(pack1.W).data_ptr(), self.hold(pack1.bias).data_ptr()
+        d.W2, d.b2 = self.hold(pack2.W).data_ptr(), self.hold(pack2.bias).data_ptr()
+        d.residual, d.out, d.ldo = self.hold(residual).buf.data_ptr(), self.hold(out).buf.data_ptr(), out.Cs
+        d.M, d.C, d.hidden = x.pixels, Cc, hid
+        d.round_tf32 = 1 if round_out else 0
+        self._add("mlp", d, name or "mlp", 4.0 * d.M * Cc * hid, 4.0 * (3 * d.M * Cc + 2 * Cc * hid))
         return out
 
     def conv(self, x, pack, taps, out, stride=(1, 1, 1), out_map=None, rows_dhw=None, act=ACT_NONE, act_param=0.0,

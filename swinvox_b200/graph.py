@@ -164,10 +164,15 @@ def lower_swin(plan, swin, img, N, stage_tail=None):
             y2 = plan.new_act(N, 1, H, H, Cc)
             plan.layernorm_rows(x1, blk.norm2.weight.detach().float().to(dev), blk.norm2.bias.detach().float().to(dev), y2,
                                 eps=blk.norm2.eps, name=nm + ".norm2")
+            x = plan.new_act(N, 1, H, H, Cc)
+            if E.mlp_fusable(Cc, blk.mlp.fc1.out_features):
+                # stages 0 / 1: fc1 -> GELU -> fc2 -> + x1 in one kernel, the 4C-wide hidden activation stays on the SM
+                plan.mlp(y2, E.pack_matrix(blk.mlp.fc1.weight, blk.mlp.fc1.bias, dev),
+                         E.pack_matrix(blk.mlp.fc2.weight, blk.mlp.fc2.bias, dev), x, residual=x1, name=nm + ".mlp")
+                continue
             hid = plan.new_act(N, 1, H, H, 4 * Cc)
             plan.linear(y2, E.pack_matrix(blk.mlp.fc1.weight, blk.mlp.fc1.bias, dev), hid, act=ACT_GELU, round_out=True,
                         name=nm + ".fc1")
-            x = plan.new_act(N, 1, H, H, Cc)
             plan.linear(hid, E.pack_matrix(blk.mlp.fc2.weight, blk.mlp.fc2.bias, dev), x, residual=x1, name=nm + ".fc2")
         feats[s] = x
         for i, si in enumerate(stages):   # wrapper LayerNorm (+ the caller's per-stage tail) as soon as the stage is done

@@ -303,6 +303,48 @@ int pool_launch(const svx_pool_desc& d, void*) {
   return 0;
 }
 
+struct MlpPrepared { int unused; };
+int mlp_prepare(const svx_mlp_desc& d, MlpPrepared** out) {
+  *out = nullptr;
+  SVX_REQUIRE(d.M > 0 && (d.C == 96 || d.C == 192) && d.hidden == 4 * d.C, "mlp: unsupported shape");
+  SVX_REQUIRE(d.x && d.W1 && d.b1 && d.W2 && d.b2 && d.residual && d.out, "mlp: null operand");
+  SVX_REQUIRE(d.ldx % 4 == 0 && d.ldx >= d.C && d.ldo % 4 == 0 && d.ldo >= d.C, "mlp: bad row pitch");
+  *out = new MlpPrepared();
+  return 0;
+}
+void mlp_prepared_free(MlpPrepared* p) { delete p; }
+
+// out = residual + W2 . round_tf32(gelu(W1 . x + b1)) + b2, operands as kind::tf32 sees them
+int mlp_launch(const svx_mlp_desc& d, MlpPrepared* prepared, void*) {
+  if (!prepared) {
+    MlpPrepared* g = nullptr;
+    if (int rc = mlp_prepare(d, &g)) return rc;
+    delete g;
+  }
+#pragma omp parallel
+  {
+    std::vector<float> xr(d.C), h(d.hidden);
+#pragma omp for schedule(static)
+    for (int r = 0; r < d.M; ++r) {
+      for (int k = 0; k < d.C; ++k) xr[k] = tf32_trunc(d.x[(long long)r * d.ldx + k]);
+      for (int j = 0; j < d.hidden; ++j) {
+        float acc = 0.f;
+        const float* w = d.W1 + (long long)j * d.C;
+        for (int k = 0; k < d.C; ++k) acc += xr[k] * tf32_trunc(w[k]);
+        h[j] = tf32_rna(act_fn(acc + d.b1[j], SVX_ACT_GELU, 0.f));
+      }
+      for (int c = 0; c < d.C; ++c) {
+        float acc = 0.f;
+        const float* w = d.W2 + (long long)c * d.hidden;
+        for (int j = 0; j < d.hidden; ++j) acc += h[j] * tf32_trunc(w[j]);
+        const long long o = (long long)r * d.ldo + c;
+        d.out[o] = rnd(acc + d.b2[c] + d.residual[o], d.round_tf32);
+      }
+    }
+  }
+  return 0;
+}
+
 int lnrows_launch(const svx_lnrows_desc& d, void*) {
 #pragma omp parallel
   {

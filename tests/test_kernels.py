@@ -97,6 +97,31 @@ def test_gemm_epilogue(dev, act, res_after):
     assert rel_err(out.view().reshape(M, N), ref) < 6e-4  # result is rounded to TF32 (2^-11)
 
 
+@pytest.mark.parametrize("M,C", [(128, 96), (1000, 96), (19 * 128 + 5, 96), (148 * 128 * 2 + 77, 96), (640, 192),
+                                 (3001, 192), (148 * 128 + 130, 192)])
+def test_mlp_fused(dev, M, C):
+    """timm Mlp + residual as one kernel (svx_mlp.cu): fc1 -> erf-GELU -> TF32 rounding -> fc2 -> + residual.  Sizes cover
+    one tile, ragged last tiles, several tiles per CTA (the chunk pipeline crosses tile boundaries) and both widths."""
+    DEV = dev
+    torch.manual_seed(M + C)
+    hid = 4 * C
+    x = E.tf32_round(torch.randn(M, C))
+    w1, b1 = torch.randn(hid, C) / C ** 0.5, torch.randn(hid) * 0.5
+    w2, b2 = torch.randn(C, hid) / hid ** 0.5, torch.randn(C) * 0.5
+    res = torch.randn(M, C)
+    p = E.Plan(DEV)
+    out = p.new_act(M, 1, 1, 1, C)
+    p.mlp(E.Act(x.to(DEV), M, 1, 1, 1, C), E.pack_matrix(w1, b1, DEV), E.pack_matrix(w2, b2, DEV), out,
+          residual=E.Act(res.to(DEV), M, 1, 1, 1, C))
+    p.run()
+    p.run()   # a second launch must not depend on leftover barrier / TMEM state
+    sync(DEV)
+    h = F.gelu(x.double() @ E.tf32_round(w1).double().t() + b1.double())
+    h = E.tf32_round(h.float()).double()
+    ref = h @ E.tf32_round(w2).double().t() + b2.double() + res.double()
+    assert rel_err(out.view().reshape(M, C), ref) < 2e-4
+
+
 @pytest.mark.parametrize("M,K,N,bn", [(333, 160, 256, 256), (1000, 64, 512, 128), (4096, 256, 1024, None)])
 def test_gemm_residual_on_tensor_cores(dev, M, K, N, bn):
     """ResNet conv3-style epilogue relu(x W^T + b + r) with the TF32-exact residual added by the MMA itself
