@@ -50,7 +50,11 @@ struct MlpCfg {
   static constexpr int kSPP = HC / 64;                     // 16-column slabs per epilogue warp and chunk
   static constexpr int kHFullCount = 4 * (2 / kSPP);       // warps that write one H k-chunk
   static constexpr int kWRows = C > HC ? C : HC;
-  static constexpr int kWStage = kWRows * ML_BK * 4;       // holds a W1 k-chunk (HC rows) or a W2 k-chunk (C rows)
+  static constexpr int kWStage = kWRows * ML_BK * 4;       // holds W1 k-chunks (HC rows each) or one W2 k-chunk (C rows)
+  static constexpr int kW1PerStageRaw = kWStage / (HC * ML_BK * 4);
+  // W1 k-chunks per ring stage: as many as fit in the slot and divide the chunk count (C = 192, HC = 64: 3 x 8 KB)
+  static constexpr int kW1PerStage = (kW1PerStageRaw >= 3 && kXChunks % 3 == 0) ? 3 : (kW1PerStageRaw >= 2 && kXChunks % 2 == 0) ? 2 : 1;
+  static constexpr int kW1Stages = kXChunks / kW1PerStage; // ring stages one fc1 chunk consumes
   static constexpr int kFixed = 1024 + 512 + kXBufs * kXBytes + kRBytes + kNHS * ML_KCH;
   static constexpr int kWStagesRaw = (ML_SMEM_MAX - kFixed) / kWStage;
   static constexpr int kWStages = kWStagesRaw > 8 ? 8 : kWStagesRaw;
@@ -63,10 +67,14 @@ struct MlpCfg {
 };
 
 #ifdef SVX_MLP_PROFILE   // role timers of CTA 0 (tools/probes/mlp_time.py): cycles spent in each kind of wait
-__device__ unsigned long long g_mlp_prof[16];
+__device__ unsigned long long g_mlp_prof[20];
 #define ML_TIMED_WAIT(slot, ...) do { const long long t0__ = clock64(); __VA_ARGS__; prof[slot] += clock64() - t0__; } while (0)
+#define ML_MARK(var) const long long var = clock64()
+#define ML_SPAN(slot, a, b) prof[slot] += (b) - (a)
 #else
 #define ML_TIMED_WAIT(slot, ...) do { __VA_ARGS__; } while (0)
+#define ML_MARK(var)
+#define ML_SPAN(slot, a, b)
 #endif
 
 struct MlpParams {
@@ -160,9 +168,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       auto load_g1 = [&](int n) {
         const int c = n % NC;
 #pragma unroll 1
-        for (int kc = 0; kc < K::kXChunks; ++kc) {
-          const int s = slot(HC * ML_BK * 4);
-          if (s >= 0) tma_load_2d(w_smem + s * K::kWStage, &map_w1, w_full(s), kc * ML_BK, c * HC);
+        for (int ks = 0; ks < K::kW1Stages; ++ks) {
+          const int s = slot(K::kW1PerStage * HC * ML_BK * 4);
+          if (s >= 0) {
+#pragma unroll
+            for (int u = 0; u < K::kW1PerStage; ++u)
+              tma_load_2d(w_smem + s * K::kWStage + u * (HC * ML_BK * 4), &map_w1, w_full(s),
+                          (ks * K::kW1PerStage + u) * ML_BK, c * HC);
+          }
         }
       };
       auto load_g2 = [&](int n) {
@@ -235,14 +248,18 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         tc_fence_after();
         const uint32_t acc = tmem_base + b * HC;
 #pragma unroll 1
-        for (int kc = 0; kc < K::kXChunks; ++kc, ++g) {
+        for (int ks = 0; ks < K::kW1Stages; ++ks, ++g) {
           const int s = g % WS;
           ML_TIMED_WAIT(2, mbar_wait(w_full(s), (g / WS) & 1u));
           tc_fence_after();
-          const uint64_t da = umma_desc_sw128(x_smem + xb * K::kXBytes + kc * ML_KCH);
-          const uint64_t db = umma_desc_sw128(w_smem + s * K::kWStage);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_tf32(acc, da + 2u * k, db + 2u * k, idesc1, (kc | k) != 0 ? 1u : 0u);
+          for (int u = 0; u < K::kW1PerStage; ++u) {
+            const int kc = ks * K::kW1PerStage + u;
+            const uint64_t da = umma_desc_sw128(x_smem + xb * K::kXBytes + kc * ML_KCH);
+            const uint64_t db = umma_desc_sw128(w_smem + s * K::kWStage + u * (HC * ML_BK * 4));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(acc, da + 2u * k, db + 2u * k, idesc1, (kc | k) != 0 ? 1u : 0u);
+          }
           umma_commit(w_empty(s));
         }
         umma_commit(acc1_full(b));
@@ -301,11 +318,21 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #endif
     for (int i = 0; i < nt; ++i) {
       const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * ML_BM;
+      if constexpr (!K::kStaged) {
+        // pull the tile's residual rows into L2 now; the tail reads them two dozen microseconds later
+        constexpr int kLines = C / 32;   // 128-byte lines per row
+        for (int idx = threadIdx.x; idx < ML_BM * kLines; idx += ML_EPI_WARPS * 32) {
+          const int row = m0 + idx / kLines;
+          if (row < p.M)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + static_cast<long long>(row) * p.ldo + (idx % kLines) * 32));
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < NC; ++c) {
         const int n = i * NC + c, b = n & 1;
         ML_TIMED_WAIT(0, mbar_wait(acc1_full(b), ((uint32_t)n >> 1) & 1u));
         tc_fence_after();
+        ML_MARK(ta);
         uint32_t v[K::kSPP][16];
 #pragma unroll
         for (int si = 0; si < K::kSPP; ++si) tmem_ld16(lane_addr + b * HC + (sl0 + si) * 16, v[si]);
@@ -313,6 +340,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc1_empty(b));     // the MMA thread may overwrite this accumulator
+        ML_MARK(tb);
+        ML_SPAN(4, ta, tb);
         float x[K::kSPP][16];
 #pragma unroll
         for (int si = 0; si < K::kSPP; ++si) {
@@ -334,7 +363,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
           for (int e = 0; e < 16; ++e) x[si][e] = __uint_as_float(__float_as_uint(x[si][e]) + 0x1000u);
         }
+        ML_MARK(tc);
+        ML_SPAN(5, tb, tc);
         ML_TIMED_WAIT(1, mbar_wait(h_empty, ((uint32_t)n & 1u) ^ 1u));   // the fc2 MMAs of the previous chunk have read H
+        ML_MARK(td);
 #pragma unroll
         for (int si = 0; si < K::kSPP; ++si) {
           const int half = (sl0 + si) & 1;
@@ -346,7 +378,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(h_full(j));
+        ML_MARK(te);
+        ML_SPAN(6, td, te);
       }
+      ML_MARK(tf);
       // ---- tile tail: out = acc2 + b2 + residual ------------------------------------------------------------
       const int ab = i & 1;
       const uint32_t acc2_addr = lane_addr + K::kAcc2Col + ab * C;
@@ -391,51 +426,71 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           mbar_arrive(r_done);
         }
       } else {
-        const int row = m0 + r;
-        const bool row_ok = row < p.M;
-        const float* res_row = p.residual + static_cast<long long>(row) * p.ldo;
-        float* out_row = p.out + static_cast<long long>(row) * p.ldo;
+        // No spare tile buffer (C = 192): each warp transposes its 32 x 16 accumulator blocks through 2 KB of the H
+        // ring so that every warp-wide global access covers 8 rows x 64 contiguous bytes instead of 32 rows x 16
+        // (the row-per-lane version spent a third of the tile here).  The 2 KB lie inside the H region this warp and its
+        // partner (same lane quarter, other slab) write during the GELU phase: H is dead between the last fc2 MMA of
+        // the tile (acc2_full) and the pair's next H write, which the pair barrier below orders behind both tails.
+        static_assert(K::kSPP == 1, "the staging carve-out assumes one slab per warp and chunk");
+        float* stage = reinterpret_cast<float*>(h_gen + j * ML_KCH + (q * 32 + (sl0 & 1) * 16) * 128);
+        const int trow = lane >> 2, tch = lane & 3;    // read-back mapping: 8 rows x 4 float4 per pass
+        // the residual does not depend on the accumulator: every block's share is requested before the wait (the lines
+        // were pulled into L2 at the start of the tile)
         float4 rv[K::kMaxOutSlabs][4];
 #pragma unroll
         for (int t = 0; t < K::kMaxOutSlabs; ++t) {
           const int sl = part + 4 * t;
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc)
-            rv[t][cc] = (row_ok && sl < K::kOutSlabs) ? *reinterpret_cast<const float4*>(res_row + sl * 16 + 4 * cc)
-                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const int row = m0 + q * 32 + g4 * 8 + trow;
+            rv[t][g4] = (row < p.M && sl < K::kOutSlabs)
+                            ? *reinterpret_cast<const float4*>(p.residual + static_cast<long long>(row) * p.ldo + sl * 16 + tch * 4)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
-        mbar_wait(acc2_full(ab), ((uint32_t)i >> 1) & 1u);
+        ML_TIMED_WAIT(3, mbar_wait(acc2_full(ab), ((uint32_t)i >> 1) & 1u));
         tc_fence_after();
 #pragma unroll
         for (int t = 0; t < K::kMaxOutSlabs; ++t) {
           const int sl = part + 4 * t;
-          if (sl < K::kOutSlabs) {   // warp-uniform
-            uint32_t v[16];
-            tmem_ld16(acc2_addr + sl * 16, v);
-            tmem_ld_wait();
-            const float4* bp = reinterpret_cast<const float4*>(p.b2 + sl * 16);
+          if (sl >= K::kOutSlabs) break;   // warp-uniform
+          uint32_t v[16];
+          tmem_ld16(acc2_addr + sl * 16, v);
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.b2 + sl * 16) + tch);
+          tmem_ld_wait();
+          __syncwarp();                      // the previous block has been read back by every lane
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              const float4 bv = __ldg(bp + cc);
-              float4 o;
-              o.x = __uint_as_float(v[4 * cc + 0]) + bv.x + rv[t][cc].x;
-              o.y = __uint_as_float(v[4 * cc + 1]) + bv.y + rv[t][cc].y;
-              o.z = __uint_as_float(v[4 * cc + 2]) + bv.z + rv[t][cc].z;
-              o.w = __uint_as_float(v[4 * cc + 3]) + bv.w + rv[t][cc].w;
-              if (p.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-              if (row_ok) *reinterpret_cast<float4*>(out_row + sl * 16 + 4 * cc) = o;
-            }
+          for (int cc = 0; cc < 4; ++cc)
+            *reinterpret_cast<uint4*>(stage + lane * 16 + ((cc ^ (lane & 3)) << 2)) =
+                make_uint4(v[4 * cc], v[4 * cc + 1], v[4 * cc + 2], v[4 * cc + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const int lr = g4 * 8 + trow;
+            const int row = m0 + q * 32 + lr;
+            const float4 a = *reinterpret_cast<const float4*>(stage + lr * 16 + ((tch ^ (lr & 3)) << 2));
+            float4 o;
+            o.x = a.x + bv.x + rv[t][g4].x; o.y = a.y + bv.y + rv[t][g4].y; o.z = a.z + bv.z + rv[t][g4].z;
+            o.w = a.w + bv.w + rv[t][g4].w;
+            if (p.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+            if (row < p.M) *reinterpret_cast<float4*>(p.out + static_cast<long long>(row) * p.ldo + sl * 16 + tch * 4) = o;
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc2_empty(ab));
+        // this warp and its partner are done with their carve-outs before either writes H again
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q * 2 + j) : "memory");
       }
+      ML_MARK(tg);
+      ML_SPAN(7, tf, tg);
     }
 #ifdef SVX_MLP_PROFILE
     if (warp == 0 && lane == 0 && blockIdx.x == 0) {
       for (int k = 0; k < 4; ++k) g_mlp_prof[8 + k] = (unsigned long long)prof[k];
       g_mlp_prof[12] = (unsigned long long)(clock64() - t_start);
+      for (int k = 4; k < 7; ++k) g_mlp_prof[9 + k] = (unsigned long long)prof[k];
+      g_mlp_prof[16] = (unsigned long long)prof[7];
     }
 #endif
   }
@@ -548,6 +603,6 @@ int mlp_launch(const svx_mlp_desc& d, MlpPrepared* prepared, void* stream) {
 
 #ifdef SVX_MLP_PROFILE
 extern "C" int svx_mlp_prof_read(unsigned long long* out) {
-  return cudaMemcpyFromSymbol(out, svx::g_mlp_prof, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : 1;
+  return cudaMemcpyFromSymbol(out, svx::g_mlp_prof, sizeof(unsigned long long) * 20) == cudaSuccess ? 0 : 1;
 }
 #endif

@@ -25,9 +25,10 @@ for M, Cc in ((192 * 56 * 56, 96), (192 * 28 * 28, 192)):
     print(f"{label:40s} M={M} C={Cc}: {t:.4f} ms  ({4.0 * M * Cc * hid / t / 1e9:.0f} TF/s)", flush=True)
     if hasattr(p.lib, "svx_mlp_prof_read"):   # SVX_MLP_PROFILE build: role timers of CTA 0, cycles per tile
         import ctypes
-        buf = (ctypes.c_uint64 * 16)()
+        buf = (ctypes.c_uint64 * 20)()
         p.lib.svx_mlp_prof_read(buf)
         nt = max(int(buf[7]), 1)
         names = ["mma:x_full", "mma:acc1_empty", "mma:w_full(fc1)", "mma:acc2_empty", "mma:h_full", "mma:w_full(fc2)",
-                 "mma:total", "tiles", "epi:acc1_full", "epi:h_empty", "epi:r_full", "epi:acc2_full", "epi:total"]
+                 "mma:total", "tiles", "epi:acc1_full", "epi:h_empty", "epi:r_full", "epi:acc2_full", "epi:total",
+                 "epi:tmem_ld", "epi:bias+gelu", "epi:sts+fence", "epi:tail(incl. waits)"]
         print("   " + "  ".join(f"{nm}={int(buf[k]) / nt:.0f}" for k, nm in enumerate(names) if k != 7) + f"  (tiles={nt})")
