@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(WA_ITEMS * 64, 2) winattn_kernel(const svx_win
   for (int i = ptid; i < 3 * WA_ROWS * WA_STRIDE; i += 64) Qs[i] = 0.f;   // incl. the padding rows, never rewritten
   __syncthreads();
   const int nwx = d.W / WS, nwy = d.H / WS;
-  const long long num_windows = (long long)d.N * nwx * nwy;
+  const int num_windows = d.N * nwx * nwy;   // < 2^31 (checked by the launcher): 32-bit index arithmetic throughout
   const uint32_t C3q = (3 * d.C) >> 2, Cq = d.C >> 2;
   const int g = lane >> 2, t = lane & 3;
   const float4* qkv4 = reinterpret_cast<const float4*>(d.qkv + head * HD);
@@ -531,17 +531,19 @@ __global__ void __launch_bounds__(WA_ITEMS * 64, 2) winattn_kernel(const svx_win
   const float scale2 = d.scale * kLog2e;
   const float kMask = -100.f * kLog2e;
   const int barid = 1 + pair;
-  for (long long win = (long long)cta_in_head * WA_ITEMS + pair; win < num_windows;
-       win += (long long)ctas_per_head * WA_ITEMS) {
-    const int wx = (int)(win % nwx);
-    const int wy = (int)((win / nwx) % nwy);
-    const long long n = win / ((long long)nwx * nwy);
+  for (int win = cta_in_head * WA_ITEMS + pair; win < num_windows; win += ctas_per_head * WA_ITEMS) {
+    const int wq = win / nwx;
+    const int wx = win - wq * nwx;
+    const int n = wq / nwy;
+    const int wy = wq - n * nwy;
     named_bar(barid, 64);   // both warps are done with the previous item's staging buffers
     {
       const int tk = min(ptid, WT - 1);
       const int py = wy * WS + tk / WS, px = wx * WS + tk % WS;   // position in the rolled map
-      const int oy = (py + d.shift) % d.H, ox = (px + d.shift) % d.W;
-      stok[ptid] = (uint32_t)((n * d.H + oy) * d.W + ox) * C3q;
+      int oy = py + d.shift, ox = px + d.shift;   // shift < H, W: one conditional subtraction instead of a modulo
+      oy -= oy >= d.H ? d.H : 0;
+      ox -= ox >= d.W ? d.W : 0;
+      stok[ptid] = (uint32_t)((n * d.H + oy) * d.W + ox);   // token row
       int reg = 0;
       if (SHIFTED) {
         const int ry = py < d.H - WS ? 0 : (py < d.H - d.shift ? 1 : 2);
@@ -554,7 +556,7 @@ __global__ void __launch_bounds__(WA_ITEMS * 64, 2) winattn_kernel(const svx_win
     // stage Q | K | V rows (49 x 128 B each) with 16-byte cp.async: 8 lanes per row
     for (int i = ptid; i < WT * 8; i += 64) {
       const int row = i >> 3, ch = i & 7;
-      const float4* base = qkv4 + stok[row] + ch;
+      const float4* base = qkv4 + stok[row] * C3q + ch;
       const uint32_t dst = qs_u32 + (row * WA_STRIDE + ch * 4) * 4;
       cp_async16_zfill(dst, base, 16u);
       cp_async16_zfill(dst + WA_ROWS * WA_STRIDE * 4, base + Cq, 16u);
@@ -652,17 +654,17 @@ __global__ void __launch_bounds__(WA_ITEMS * 64, 2) winattn_kernel(const svx_win
         mma_tf32_16x8x8(o[3], p0, p1, p2, p3, __float_as_uint(va.w), __float_as_uint(vb.w));
       }
       // accumulator column 2t / 2t+1 of tile dn is d = 8t + dn / 8t + 4 + dn: the lane owns d = 8t .. 8t+7 of its rows
-      const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+      const float inv0 = __frcp_rn(sum0), inv1 = __frcp_rn(sum1);
       float4* out4 = reinterpret_cast<float4*>(d.out + head * HD) + 2 * t;
       if (r0 < WT) {
-        float4* dst = out4 + (stok[r0] / C3q) * Cq;
+        float4* dst = out4 + stok[r0] * Cq;
         dst[0] = make_float4(maybe_round(o[0][0] * inv0, d.round_tf32), maybe_round(o[1][0] * inv0, d.round_tf32),
                              maybe_round(o[2][0] * inv0, d.round_tf32), maybe_round(o[3][0] * inv0, d.round_tf32));
         dst[1] = make_float4(maybe_round(o[0][1] * inv0, d.round_tf32), maybe_round(o[1][1] * inv0, d.round_tf32),
                              maybe_round(o[2][1] * inv0, d.round_tf32), maybe_round(o[3][1] * inv0, d.round_tf32));
       }
       if (r1 < WT) {
-        float4* dst = out4 + (stok[r1] / C3q) * Cq;
+        float4* dst = out4 + stok[r1] * Cq;
         dst[0] = make_float4(maybe_round(o[0][2] * inv1, d.round_tf32), maybe_round(o[1][2] * inv1, d.round_tf32),
                              maybe_round(o[2][2] * inv1, d.round_tf32), maybe_round(o[3][2] * inv1, d.round_tf32));
         dst[1] = make_float4(maybe_round(o[0][3] * inv1, d.round_tf32), maybe_round(o[1][3] * inv1, d.round_tf32),
