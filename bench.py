@@ -215,7 +215,7 @@ def run_ours(args):
     d2h_bytes = B * 32768 * 4 + B * len(cfg.TEST.VOXEL_THRESH) * 5 * 4
 
     # ---- roofline of the dominant kernel (the tcgen05 contraction kernel), measured live with CUDA events -------
-    gemm_ms, slab_ms, total_ms, gemm_bytes, breakdown = 0.0, 0.0, 0.0, 0.0, []
+    gemm_ms, slab_ms, mlp_ms, mlp_gf, total_ms, gemm_bytes, breakdown = 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, []
     for mod in rec.modules():
         for entry in mod._plans.values():
             plan = entry[0]
@@ -224,13 +224,16 @@ def run_ours(args):
                 total_ms += t
                 if fl > 0 and nm.startswith("merger.layer"):
                     slab_ms += t
+                elif nm.endswith(".mlp"):      # mlp_fused_kernel (Swin stages 0 / 1): its own kernel, not the dominant one
+                    mlp_ms += t
+                    mlp_gf += fl / 1e9
                 elif fl > 0 and not nm.endswith(".attn"):
                     gemm_ms += t
                     gemm_bytes += nb
                 breakdown.append((nm, t, fl, nb))
     # dominant kernel = gemm_tf32_kernel (every Linear / Conv2d / Conv3d k4 / ConvTranspose3d).  Algorithmic FLOPs per
     # step = SURVEY 8(d) figure of the reference forward minus what other kernels execute (attention, merger convs).
-    algo_gf = B * ((GF_PER_VIEW - GF_ATTENTION_PER_VIEW - GF_MERGER_PER_VIEW) * V + GF_PER_OBJECT)
+    algo_gf = B * ((GF_PER_VIEW - GF_ATTENTION_PER_VIEW - GF_MERGER_PER_VIEW) * V + GF_PER_OBJECT) - mlp_gf
     achieved = algo_gf / gemm_ms if gemm_ms > 0 else 0.0   # GFLOP / ms = TFLOP/s
     peaks = {}
     try:
@@ -239,7 +242,8 @@ def run_ours(args):
         pass
     bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak = bf16_peak / 2.0   # kind::tf32 runs at half the bf16 rate; MEASURED_PEAKS.json has no tf32 entry
-    n_gemm = sum(1 for nm, t, fl, nb in breakdown if fl > 0 and not nm.endswith(".attn") and not nm.startswith("merger.layer"))
+    n_gemm = sum(1 for nm, t, fl, nb in breakdown
+                 if fl > 0 and not nm.endswith((".attn", ".mlp")) and not nm.startswith("merger.layer"))
     hbm = peaks.get("hbm_gbs", 6550.7)
     # per-op roofline floor: every op is bounded by max(algorithmic FLOP / tensor peak, algorithmic bytes / HBM peak)
     floor_ms = sum(max(fl / (peak * 1e9), nb / (hbm * 1e6)) for nm, t, fl, nb in breakdown)
@@ -254,6 +258,7 @@ def run_ours(args):
                 "step_floor_ms": floor_ms, "step_frac_of_floor": floor_ms / total_ms if total_ms > 0 else None,
                 "kernel_ms_per_step": gemm_ms, "all_kernels_ms_per_step": total_ms,
                 "algorithmic_gflop_per_step": algo_gf, "conv3_slab_ms_per_step": slab_ms,
+                "mlp_fused_ms_per_step": mlp_ms, "mlp_fused_tflops": (mlp_gf / mlp_ms if mlp_ms > 0 else None),
                 "tf32_cublas_tflops_measured": TF32_CUBLAS_MEASURED,
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32), of measured" if peaks
                                 else "fallback 1.4 PFLOP/s sustained bf16 / 2 (tf32), of fallback")}

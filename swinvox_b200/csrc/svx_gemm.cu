@@ -35,7 +35,7 @@ constexpr int kThreads = 320;
 constexpr int kGatherLag = 2;
 constexpr int kMaxTaps = 64;
 constexpr int kSlab = 16;                        // accumulator columns per epilogue pass
-constexpr int kEpiWarps = 8;                     // warps 0-3, plus warps 6-9 when they are not gathering
+
 constexpr int kBlockBytes = 32 * kSlab * 4;      // one staged 32-row x 16-column fp32 block
 
 struct GemmParams {
@@ -71,7 +71,7 @@ struct GemmParams {
   int flat_off[kMaxTaps];  // flat mode: row offset of each tap; im2col mode: tap offsets packed w | h << 8 | d << 16
 };
 
-template <int BN>
+template <int BN, int PARTS = 2>
 struct Cfg {
   static constexpr int kBBytes = BN * BK * 4;
   static constexpr int kStageBytes = A_STAGE_BYTES + kBBytes;
@@ -80,6 +80,14 @@ struct Cfg {
   // block for its transpose and the 256 bytes after it for the row offsets); 512-byte multiples keep the 64B swizzle
   static constexpr int kEpiBufs = BN == 96 ? 1 : 2;
   static constexpr int kWarpStage = BN == 96 ? kBlockBytes + 512 : 2 * kBlockBytes;
+  // epilogue warps: warps 0-3 (part 0) and warps 6.. (parts 1..kParts-1; warps 6-9 gather instead in SVX_A_GATHER mode).
+  // PARTS = 4 (18 warps, 96 registers each) is the variant for erf-GELU epilogues on the one-CTA-per-SM tiles, which are
+  // bound by the epilogue warps' FP32 / MUFU issue: stage-2 fc1 0.71 -> 0.63 ms.  Every other epilogue is faster with
+  // PARTS = 2 (138 registers, one more pipeline stage): measured per op in profiles/r1_gemm_epilogue_parts_v23.txt.
+  static constexpr int kParts = PARTS;
+  static_assert(PARTS == 2 || kCtasPerSm == 1, "two resident CTAs leave no registers for extra epilogue warps");
+  static constexpr int kEpiWarps = 4 * kParts;
+  static constexpr int kThreadsT = 32 * (6 + 4 * (kParts - 1));
   static constexpr int kAuxBytes = kEpiWarps * kWarpStage + 256;          // + barriers
   static constexpr int kBudget = (kCtasPerSm == 2 ? 115712 : 232448) - 1024 - kAuxBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
@@ -176,19 +184,19 @@ __device__ __forceinline__ void store_slab(const GemmParams& p, const float* sta
   }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, Cfg<BN>::kCtasPerSm)
+template <int BN, int PARTS>
+__global__ void __launch_bounds__(Cfg<BN, PARTS>::kThreadsT, Cfg<BN, PARTS>::kCtasPerSm)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
                  const __grid_constant__ GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PARTS>;
   constexpr int S = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   // after the pipeline stages: epilogue staging (1024-byte aligned: TMA-store source blocks), row offsets, barriers
   uint8_t* aux_gen = smem_gen + S * C::kStageBytes;
-  constexpr int kBarOff = kEpiWarps * C::kWarpStage;
+  constexpr int kBarOff = C::kEpiWarps * C::kWarpStage;
   const uint32_t bar_base = smem_base + S * C::kStageBytes + kBarOff;
   // barrier layout: full[S], empty[S], tmem_full[2], tmem_empty[2], tmem slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -219,7 +227,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tmem_full_bar(a), 1u);
-        mbar_init(tmem_empty_bar(a), a_mode == SVX_A_GATHER ? 4u : 8u);
+        mbar_init(tmem_empty_bar(a), a_mode == SVX_A_GATHER ? 4u : 4u * C::kParts);
       }
       fence_barrier_init();
     }
@@ -331,7 +339,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
     __syncwarp();
-  } else if (warp >= 6 && a_mode == SVX_A_GATHER) {
+  } else if (warp >= 6 && warp < 10 && a_mode == SVX_A_GATHER) {
     // ---- A gather producers (implicit im2col for strided / unpadded convolutions) ----------------------
     {
       const int gw = warp - 6;
@@ -404,12 +412,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       __syncwarp();
     }
-  } else {
-    // ---- epilogue: warps 0-3, helped by warps 6-9 whenever those are not gathering.  A warp may only touch the
-    // TMEM lane quarter (warp % 4); the two warps of a quarter take alternate 16-column slabs. ----------------
+  } else if (warp < 4 || a_mode != SVX_A_GATHER) {
+    // ---- epilogue: warps 0-3, helped by warps 6.. whenever the A operand is not gathered.  A warp may only touch the
+    // TMEM lane quarter (warp % 4); the warps of a quarter take the 16-column slabs round-robin. ----------------
     const int quarter = warp & 3;
-    const int part = warp >= 6 ? 1 : 0;
-    const int nparts = a_mode == SVX_A_GATHER ? 1 : 2;
+    const int part = warp < 4 ? 0 : 1 + ((warp - 6) >> 2);
+    const int nparts = a_mode == SVX_A_GATHER ? 1 : C::kParts;
     const int ew = part * 4 + quarter;
     float* staging = reinterpret_cast<float*>(aux_gen + ew * C::kWarpStage);
     long long* soff = reinterpret_cast<long long*>(aux_gen + ew * C::kWarpStage + kBlockBytes);
@@ -1097,18 +1105,29 @@ int sm_count() {
   return n;
 }
 
+template <int BN, int PARTS>
+int launch_bn_parts(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr,
+                    const GemmParams& p, int grid, cudaStream_t st) {
+  using C = Cfg<BN, PARTS>;
+  static bool configured = false;
+  if (!configured) {
+    SVX_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    configured = true;
+  }
+  gemm_tf32_kernel<BN, PARTS><<<grid, C::kThreadsT, C::kSmemBytes, st>>>(ma, mb, mc, mr, p);
+  SVX_LAUNCH_OK("gemm_tf32_kernel");
+  return 0;
+}
+
 template <int BN>
 int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr,
               const GemmParams& p, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    SVX_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg<BN>::kSmemBytes));
-    configured = true;
+  if constexpr (BN >= 128) {
+    // erf-GELU epilogues through the TMA-store path: twice the epilogue warps (see Cfg)
+    if (p.act == SVX_ACT_GELU && p.epi_tma && p.a_mode != SVX_A_GATHER && !getenv("SVX_GEMM_NO_WIDE_EPILOGUE"))
+      return launch_bn_parts<BN, 4>(ma, mb, mc, mr, p, grid, st);
   }
-  gemm_tf32_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ma, mb, mc, mr, p);
-  SVX_LAUNCH_OK("gemm_tf32_kernel");
-  return 0;
+  return launch_bn_parts<BN, 2>(ma, mb, mc, mr, p, grid, st);
 }
 
 }  // namespace
