@@ -1124,7 +1124,8 @@ int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& m
               const GemmParams& p, int grid, cudaStream_t st) {
   if constexpr (BN >= 128) {
     // erf-GELU epilogues through the TMA-store path: twice the epilogue warps (see Cfg)
-    if (p.act == SVX_ACT_GELU && p.epi_tma && p.a_mode != SVX_A_GATHER && !getenv("SVX_GEMM_NO_WIDE_EPILOGUE"))
+    // (only while the main loop is short: at K = 768 the tensor pipe is the bound again and the variant loses)
+    if (p.act == SVX_ACT_GELU && p.epi_tma && p.a_mode != SVX_A_GATHER && p.K <= 512 && !getenv("SVX_GEMM_NO_WIDE_EPILOGUE"))
       return launch_bn_parts<BN, 4>(ma, mb, mc, mr, p, grid, st);
   }
   return launch_bn_parts<BN, 2>(ma, mb, mc, mr, p, grid, st);
