@@ -68,6 +68,7 @@ struct GemmParams {
   long long c_sd, c_sh, c_sw, c2_sd, c2_sh, c2_sw;   // class-bit offsets in out / residual and in out2
   int i2c_lo_d, i2c_lo_h, i2c_lo_w;   // im2col mode: base-pixel coordinate of output 0 on each axis (= smallest tap)
   int i2c_narrow, ntaps;              // 4-channel pixels (image stems): eight 16-byte taps per k-chunk, unswizzled A tile
+  const float* Wg;          // slab mode, fp16 operands: the fp32 weight matrix in global memory (converted once per CTA)
   int flat_off[kMaxTaps];  // flat mode: row offset of each tap; im2col mode: tap offsets packed w | h << 8 | d << 16
 };
 
@@ -723,28 +724,49 @@ constexpr int S3_XCHG_BYTES = 2 * BM * 128;        // per epilogue set: 128 rows
 
 // ROWB = bytes per staged row: 128 (32-channel box, 128B swizzle) or 64 (layers with <= 16 live channels: 16-channel
 // box, 64B swizzle -- half the L2 traffic and shared memory, which buys a twice deeper slab ring)
-template <int ROWB>
+// F16: the MMA operands are fp16 (kind::f16, K = 16 per instruction: half the issue-bound instructions of kind::tf32 for
+// the same channels).  HBM tensors stay fp32: each fp32 slab lands in a small staging ring by TMA, four converter warps
+// (10-13) rewrite it as an fp16 operand slab (rows of ROWB/2 bytes, the narrower swizzle), and convert the weights once
+// per CTA.  The activations and weights of this path are stored TF32-rounded (10 mantissa bits = fp16's), so the
+// conversion is exact for |x| in [6.1e-5, 65504]; smaller magnitudes lose relative, not absolute, accuracy (< 3e-8).
+constexpr int S3_THREADS_F16 = 448;
+template <int ROWB, bool F16 = false>
 struct S3Cfg {
-  static constexpr int kSlabBytes = S3_ROWS * ROWB;
-  static constexpr int kNSlab = ROWB == 128 ? 5 : 10;
-  static constexpr int kTapBytes = S3_N * ROWB;        // one (kd,kh) weight block
-  static constexpr int kWBytes = 9 * kTapBytes;
-  static constexpr int kSmem = 1024 + kWBytes + kNSlab * kSlabBytes + S3_XCHG_BYTES + 512;
+  static constexpr int kOpRowB = F16 ? ROWB / 2 : ROWB;            // bytes per operand row
+  static constexpr int kSlabBytes = S3_ROWS * kOpRowB;
+  static constexpr int kNSlab = F16 ? (ROWB == 128 ? 5 : 10) : (ROWB == 128 ? 5 : 10);
+  // fp32 staging slabs (F16 only): the TMA round trip is hidden by THIS ring now (three slots left the kernel
+  // latency-bound: one slab per third of a round trip), the operand ring only decouples converters and MMAs
+  static constexpr int kNStg = F16 ? (ROWB == 128 ? 4 : 6) : 0;
+  static constexpr int kTapBytes = S3_N * kOpRowB;     // one (kd,kh) weight block
+  static constexpr int kWBytes = (9 * kTapBytes + 1023) / 1024 * 1024;
+  static constexpr int kStgBytes = F16 ? S3_ROWS * ROWB : 0;
+  static constexpr int kSmem = 1024 + kWBytes + kNSlab * kSlabBytes + kNStg * kStgBytes + S3_XCHG_BYTES + 512;
+  static_assert(kSmem <= 232448, "slab kernel shared memory");
 };
 
-template <int ROWB, bool PAIR>
-__global__ void __launch_bounds__(S3_THREADS, 1)
+template <int ROWB, bool PAIR, bool F16>
+__global__ void __launch_bounds__(F16 ? S3_THREADS_F16 : S3_THREADS, 1)
 conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ GemmParams p) {
-  constexpr int S3_SLAB_BYTES = S3Cfg<ROWB>::kSlabBytes, S3_NSLAB = S3Cfg<ROWB>::kNSlab;
-  constexpr int S3_TAP_BYTES = S3Cfg<ROWB>::kTapBytes, S3_W_BYTES = S3Cfg<ROWB>::kWBytes;
+  static_assert(!(PAIR && F16), "the CTA-pair mode exists for kind::tf32 only");
+  using SC = S3Cfg<ROWB, F16>;
+  constexpr int S3_SLAB_BYTES = SC::kSlabBytes, S3_NSLAB = SC::kNSlab;
+  constexpr int S3_TAP_BYTES = SC::kTapBytes, S3_W_BYTES = SC::kWBytes;
+  constexpr int OPB = SC::kOpRowB;   // bytes per operand row in shared memory
   constexpr int kBoxCh = ROWB / 4;   // channels per staged row
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t w_smem = smem_base;
-  const uint32_t slab_smem = smem_base + S3_W_BYTES;
-  constexpr int kXchgOff = S3_W_BYTES + S3_NSLAB * S3_SLAB_BYTES;
+  // weights | fp32 staging ring (F16 only; 1024-byte aligned: its TMA boxes use the 128B swizzle) | operand slab ring
+  constexpr int kStgOff = S3_W_BYTES;
+  const uint32_t stg_smem = smem_base + kStgOff;
+  constexpr int S3_NSTG = SC::kNStg > 0 ? SC::kNStg : 1;
+  constexpr int kSlabOff = kStgOff + SC::kNStg * SC::kStgBytes;
+  static_assert(kSlabOff % 1024 == 0, "operand slab ring alignment");
+  const uint32_t slab_smem = smem_base + kSlabOff;
+  constexpr int kXchgOff = kSlabOff + S3_NSLAB * S3_SLAB_BYTES;
   float* xchg = reinterpret_cast<float*>(smem_gen + kXchgOff);
   const uint32_t bar_base = smem_base + kXchgOff + S3_XCHG_BYTES;
   // barriers: slab_full[5], slab_empty[5], w_full, acc_full[8], acc_empty[8], tmem slot
@@ -753,7 +775,9 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   const uint32_t w_full = bar_base + 8u * (2 * S3_NSLAB);
   auto acc_full = [&](uint32_t a) { return bar_base + 8u * (2 * S3_NSLAB + 1 + a); };
   auto acc_empty = [&](uint32_t a) { return bar_base + 8u * (2 * S3_NSLAB + 1 + S3_NACC + a); };
-  constexpr int kSlotIdx = 2 * S3_NSLAB + 1 + 2 * S3_NACC;
+  auto stg_full = [&](uint32_t s) { return bar_base + 8u * (2 * S3_NSLAB + 1 + 2 * S3_NACC + s); };
+  auto stg_empty = [&](uint32_t s) { return bar_base + 8u * (2 * S3_NSLAB + 1 + 2 * S3_NACC + S3_NSTG + s); };
+  constexpr int kSlotIdx = 2 * S3_NSLAB + 1 + 2 * S3_NACC + 2 * S3_NSTG;
   const uint32_t tmem_slot = bar_base + 8u * kSlotIdx;
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + kXchgOff + S3_XCHG_BYTES + 8 * kSlotIdx);
@@ -777,8 +801,9 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   if (warp == 4 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); }
   if (warp == 5) {
     if (lane == 0) {
-      for (uint32_t s = 0; s < S3_NSLAB; ++s) { mbar_init(slab_full(s), 1u); mbar_init(slab_empty(s), 1u); }
-      mbar_init(w_full, 1u);
+      for (uint32_t s = 0; s < S3_NSLAB; ++s) { mbar_init(slab_full(s), F16 ? 4u : 1u); mbar_init(slab_empty(s), 1u); }
+      mbar_init(w_full, F16 ? 4u : 1u);
+      for (uint32_t s = 0; s < S3_NSTG; ++s) { mbar_init(stg_full(s), 1u); mbar_init(stg_empty(s), 4u); }
       // PAIR: the leader's acc_empty collects the epilogue warps of both CTAs
       for (uint32_t a = 0; a < S3_NACC; ++a) { mbar_init(acc_full(a), 1u); mbar_init(acc_empty(a), PAIR ? 8u : 4u); }
       fence_barrier_init();
@@ -797,10 +822,12 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       // PAIR: every load of either CTA signals the LEADER's barrier (it is the leader that issues the MMAs); the
       // leader expects the bytes of both.  Each CTA holds half of the weight rows of every tap (map_w boxes 24 rows).
       constexpr uint32_t kWTap = PAIR ? S3_TAP_BYTES / 2 : S3_TAP_BYTES;
-      if (leader) mbar_arrive_expect_tx(w_full, S3_W_BYTES);
-      for (int t = 0; t < 9; ++t) {   // first kBoxCh of the 32
-        if (PAIR) tma_load_2d_pair(w_smem + t * kWTap, &map_w, leader_addr(w_full), t * BK, (int)rank * (S3_N / 2));
-        else tma_load_2d(w_smem + t * S3_TAP_BYTES, &map_w, w_full, t * BK, 0);
+      if constexpr (!F16) {
+        if (leader) mbar_arrive_expect_tx(w_full, 9 * S3_TAP_BYTES);
+        for (int t = 0; t < 9; ++t) {   // first kBoxCh of the 32
+          if (PAIR) tma_load_2d_pair(w_smem + t * kWTap, &map_w, leader_addr(w_full), t * BK, (int)rank * (S3_N / 2));
+          else tma_load_2d(w_smem + t * S3_TAP_BYTES, &map_w, w_full, t * BK, 0);
+        }
       }
       uint32_t g = 0;
       for (int q = cta; q < num_steps; q += nslots) {
@@ -808,6 +835,13 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const int n = unit / ncol, col = unit - n * ncol;
         const int row0 = n * p.in_D * HWp + col * S3_STEP;
         for (int pl = 0; pl < nd + 2; ++pl, ++g) {
+          if constexpr (F16) {   // fp32 slab -> staging ring; the converter warps fill the operand ring
+            const uint32_t s = g % S3_NSTG;
+            mbar_wait(stg_empty(s), ((g / S3_NSTG) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(stg_full(s), SC::kStgBytes);
+            tma_load_2d(stg_smem + s * SC::kStgBytes, &map_x, stg_full(s), p.in_c0, row0 + pl * HWp);
+            continue;
+          }
           const uint32_t s = g % S3_NSLAB;
           mbar_wait(slab_empty(s), ((g / S3_NSLAB) & 1u) ^ 1u);
           if (leader) mbar_arrive_expect_tx(slab_full(s), (PAIR ? 2u : 1u) * S3_SLAB_BYTES);
@@ -825,9 +859,9 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   } else if (warp == 5) {
     // ---- MMA issuer -----------------------------------------------------------------------------------
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_tf32(PAIR ? 2 * BM : BM, S3_N);
+      constexpr uint32_t idesc = F16 ? umma_idesc_f16(BM, S3_N) : umma_idesc_tf32(PAIR ? 2 * BM : BM, S3_N);
       constexpr uint32_t kWTap = PAIR ? S3_TAP_BYTES / 2 : S3_TAP_BYTES;
-      const int ksteps = (p.cin_live + UMMA_K - 1) / UMMA_K;
+      const int ksteps = F16 ? (p.cin_live + 15) / 16 : (p.cin_live + UMMA_K - 1) / UMMA_K;   // 32 operand bytes per step
       mbar_wait(w_full, 0u);
       tc_fence_after();
       uint32_t sbase = 0, waited = 0, tg = 0;
@@ -845,14 +879,17 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             const uint32_t slab = slab_smem + ((sbase + d + kd) % S3_NSLAB) * S3_SLAB_BYTES;
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
-              const uint64_t da = ROWB == 128 ? umma_desc_sw128(slab + kh * Wp * ROWB) : umma_desc_sw64(slab + kh * Wp * ROWB);
-              const uint64_t db = ROWB == 128 ? umma_desc_sw128(w_smem + (kd * 3 + kh) * kWTap)
-                                              : umma_desc_sw64(w_smem + (kd * 3 + kh) * kWTap);
+              const uint64_t da = OPB == 128 ? umma_desc_sw128(slab + kh * Wp * OPB)
+                                  : OPB == 64 ? umma_desc_sw64(slab + kh * Wp * OPB) : umma_desc_sw32(slab + kh * Wp * OPB);
+              const uint64_t db = OPB == 128 ? umma_desc_sw128(w_smem + (kd * 3 + kh) * kWTap)
+                                  : OPB == 64 ? umma_desc_sw64(w_smem + (kd * 3 + kh) * kWTap)
+                                              : umma_desc_sw32(w_smem + (kd * 3 + kh) * kWTap);
 #ifdef SVX_SLAB_NOMMA   // experiment: the TMA pipeline alone (results are wrong)
               if (ksteps > 0) continue;
 #endif
               for (int k = 0; k < ksteps; ++k) {
                 if (PAIR) umma_tf32_pair(acc, da + 2u * k, db + 2u * k, idesc, (kd | kh | k) != 0 ? 1u : 0u);
+                else if (F16) umma_f16(acc, da + 2u * k, db + 2u * k, idesc, (kd | kh | k) != 0 ? 1u : 0u);
                 else umma_tf32(acc, da + 2u * k, db + 2u * k, idesc, (kd | kh | k) != 0 ? 1u : 0u);
               }
             }
@@ -869,6 +906,67 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       }
     }
     __syncwarp();
+  } else if (warp >= 10) {
+    // ---- converter warps (F16 only): fp32 staging slab -> fp16 operand slab; weights once --------------------
+    if constexpr (F16) {
+      constexpr int UIN = ROWB / 16;    // 16-byte units per fp32 row (4 floats each)
+      constexpr int UOUT = OPB / 16;    // 16-byte units per fp16 row (8 halves each)
+      const int ct = threadIdx.x - 320; // 0..127
+      uint8_t* w_gen = smem_gen;
+      // an fp16 operand row r of OPB bytes: unit u is stored at u ^ swz(r) (32B swizzle: bit 2 of r; 64B: bits 1-2)
+      auto swz_out = [](int r) { return OPB == 32 ? ((r >> 2) & 1) : ((r >> 1) & 3); };
+      auto swz_in = [](int r) { return ROWB == 64 ? ((r >> 1) & 3) : (r & 7); };
+      auto pack8 = [](const float4& a, const float4& b) {
+        uint4 o;
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(a.y), "f"(a.x));
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(a.w), "f"(a.z));
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(b.y), "f"(b.x));
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(b.w), "f"(b.z));
+        return o;
+      };
+      // weights: W[row = kw*16+co][col = tap*32 + c] fp32 -> per tap a [48 rows x kBoxCh halves] swizzled block
+      for (int i = ct; i < 9 * S3_N * UOUT; i += 128) {
+        const int u = i % UOUT, row = (i / UOUT) % S3_N, t = i / (UOUT * S3_N);
+        const float* src = p.Wg + (long long)row * (9 * BK) + t * BK + u * 8;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        *reinterpret_cast<uint4*>(w_gen + t * S3_TAP_BYTES + row * OPB + ((u ^ swz_out(row)) << 4)) = pack8(a, b);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(w_full);
+      uint32_t g = 0;
+      for (int q = cta; q < num_steps; q += nslots) {
+        for (int pl = 0; pl < nd + 2; ++pl, ++g) {
+          const uint32_t ss = g % S3_NSTG, so = g % S3_NSLAB;
+          mbar_wait(stg_full(ss), (g / S3_NSTG) & 1u);
+          mbar_wait(slab_empty(so), ((g / S3_NSLAB) & 1u) ^ 1u);
+          const uint8_t* src = smem_gen + kStgOff + ss * SC::kStgBytes;
+          uint8_t* dst = smem_gen + kSlabOff + so * S3_SLAB_BYTES;
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int r = ct + rr * 128;
+            if (r < S3_ROWS) {
+              const uint8_t* srow = src + r * ROWB;
+              uint8_t* drow = dst + r * OPB;
+              const int si = swz_in(r), sw_o = swz_out(r);
+#pragma unroll
+              for (int u = 0; u < UOUT; ++u) {
+                const float4 a = *reinterpret_cast<const float4*>(srow + (((2 * u) ^ si) << 4));
+                const float4 b = *reinterpret_cast<const float4*>(srow + (((2 * u + 1) ^ si) << 4));
+                *reinterpret_cast<uint4*>(drow + ((u ^ sw_o) << 4)) = pack8(a, b);
+              }
+            }
+          }
+          static_assert(UIN == 2 * UOUT, "two fp32 units make one fp16 unit");
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(slab_full(so));
+            mbar_arrive(stg_empty(ss));
+          }
+        }
+      }
+    }
   } else {
     // ---- epilogue: one thread = one row u of the tile; out[u] = D0[u] + D1[u+1] + D2[u+2].  Two sets of four
     // warps (0-3: even tiles, 6-9: odd tiles) so two tiles drain concurrently; the row shift goes through a
@@ -1140,6 +1238,7 @@ struct GemmPrepared {
   bool slab = false;   // SVX_A_SLAB3: handled by conv3_slab_kernel
   bool slab_narrow = false;   // 16-channel (64-byte) rows
   bool slab_pair = false;     // CTA pairs (cta_group::2): one M = 256 MMA per step for two units
+  bool slab_f16 = false;      // fp16 MMA operands converted inside the kernel (kind::f16: half the MMA instructions)
 };
 
 int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
@@ -1256,6 +1355,8 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   // CTA pairs (cluster of 2, tcgen05.mma.cta_group::2) are correct (tests pass with SVX_SLAB_PAIR=1) but measured no
   // faster than single CTAs on this kernel (profiles/README.md, "merger slab kernel experiments"): opt-in only.
   g->slab_pair = g->slab && getenv("SVX_SLAB_PAIR") != nullptr;
+  g->slab_f16 = g->slab && !g->slab_pair && getenv("SVX_SLAB_TF32") == nullptr;
+  p.Wg = d.W;
   if (encode_map(&g->map_b, d.W, (uint64_t)d.Npad, (uint64_t)w_cols, (uint64_t)w_cols,
                  g->slab_pair ? (uint32_t)(S3_N / 2) : (uint32_t)d.block_n, g->slab_narrow ? 16 : BK)) {
     delete g;
@@ -1363,10 +1464,12 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void* stream) {
   if (g->slab) {
     static bool configured = false;
     if (!configured) {
-      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<128>::kSmem));
-      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<64>::kSmem));
-      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<128>::kSmem));
-      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<64>::kSmem));
+      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<128>::kSmem));
+      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<64>::kSmem));
+      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<128, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<128>::kSmem));
+      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<64, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<64>::kSmem));
+      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<128, true>::kSmem));
+      SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<64, true>::kSmem));
       configured = true;
     }
     if (g->slab_pair) {
@@ -1382,13 +1485,18 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void* stream) {
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      cudaError_t le = g->slab_narrow ? cudaLaunchKernelEx(&cfg, conv3_slab_kernel<64, true>, g->map_a, g->map_b, g->p)
-                                      : cudaLaunchKernelEx(&cfg, conv3_slab_kernel<128, true>, g->map_a, g->map_b, g->p);
+      cudaError_t le = g->slab_narrow ? cudaLaunchKernelEx(&cfg, conv3_slab_kernel<64, true, false>, g->map_a, g->map_b, g->p)
+                                      : cudaLaunchKernelEx(&cfg, conv3_slab_kernel<128, true, false>, g->map_a, g->map_b, g->p);
       if (le != cudaSuccess) { if (!prepared) delete g; return fail("cluster launch of conv3_slab_kernel failed: %s", cudaGetErrorString(le)); }
+    } else if (g->slab_f16) {
+      if (g->slab_narrow)
+        conv3_slab_kernel<64, false, true><<<g->grid, S3_THREADS_F16, S3Cfg<64, true>::kSmem, st>>>(g->map_a, g->map_b, g->p);
+      else
+        conv3_slab_kernel<128, false, true><<<g->grid, S3_THREADS_F16, S3Cfg<128, true>::kSmem, st>>>(g->map_a, g->map_b, g->p);
     } else if (g->slab_narrow) {
-      conv3_slab_kernel<64, false><<<g->grid, S3_THREADS, S3Cfg<64>::kSmem, st>>>(g->map_a, g->map_b, g->p);
+      conv3_slab_kernel<64, false, false><<<g->grid, S3_THREADS, S3Cfg<64>::kSmem, st>>>(g->map_a, g->map_b, g->p);
     } else {
-      conv3_slab_kernel<128, false><<<g->grid, S3_THREADS, S3Cfg<128>::kSmem, st>>>(g->map_a, g->map_b, g->p);
+      conv3_slab_kernel<128, false, false><<<g->grid, S3_THREADS, S3Cfg<128>::kSmem, st>>>(g->map_a, g->map_b, g->p);
     }
     cudaError_t e = cudaGetLastError();
     if (!prepared) delete g;
