@@ -146,6 +146,10 @@ typedef struct svx_mlp_desc {
   const float* residual; float* out; int64_t ldo;
   int32_t M, C, hidden;
   int32_t round_tf32;       /* round the stored result to TF32 */
+  /* optional fused pre-LayerNorm (the block's norm2; C = 96 only): when ln_gamma is set, x holds the UN-normalised rows
+   * (normally x == residual) and fc1 reads round_tf32(LayerNorm(x) * ln_gamma + ln_beta), normalised inside the kernel */
+  const float* ln_gamma; const float* ln_beta;
+  float ln_eps; int32_t reserved0;
 } svx_mlp_desc;
 
 /* Explicit im2col for tiny channel counts (ResNet stem 7x7 s2 on 3 channels, Swin patch-embed

@@ -127,7 +127,8 @@ class Conv3to1Desc(C.Structure):
 class MlpDesc(C.Structure):
     _fields_ = [("x", ptr), ("ldx", i64), ("W1", ptr), ("b1", ptr), ("W2", ptr), ("b2", ptr),
                 ("residual", ptr), ("out", ptr), ("ldo", i64),
-                ("M", i32), ("C", i32), ("hidden", i32), ("round_tf32", i32)]
+                ("M", i32), ("C", i32), ("hidden", i32), ("round_tf32", i32),
+                ("ln_gamma", ptr), ("ln_beta", ptr), ("ln_eps", f32), ("reserved0", i32)]
 
 
 class BinvoxDecodeDesc(C.Structure):

@@ -85,6 +85,9 @@ struct MlpParams {
   float* out;
   long long ldo;
   int round_tf32;
+  const float* ln_gamma;   // fused pre-LayerNorm (staged variant only): x is the un-normalised input (= the residual)
+  const float* ln_beta;
+  float ln_eps;
 };
 
 template <int C, int HC>
@@ -114,9 +117,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   auto acc2_empty = [&](int b) { return bar_base + 8u * (2 * WS + 15 + b); };
   const uint32_t r_full = bar_base + 8u * (2 * WS + 17);
   const uint32_t r_done = bar_base + 8u * (2 * WS + 18);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * WS + 19);
+  auto xn_full = [&](int b) { return bar_base + 8u * (2 * WS + 19 + b); };   // X tile normalised in place (fused LayerNorm)
+  const uint32_t tmem_slot = bar_base + 8u * (2 * WS + 21);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
-      smem_gen + (bar_base - smem_base) + 8 * (2 * WS + 19));
+      smem_gen + (bar_base - smem_base) + 8 * (2 * WS + 21));
+  const bool fuse_ln = K::kStaged && p.ln_gamma != nullptr;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,6 +146,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       mbar_init(h_empty, 1u);
       mbar_init(r_full, 1u);
       mbar_init(r_done, ML_EPI_WARPS);
+      mbar_init(xn_full(0), ML_EPI_WARPS);
+      mbar_init(xn_full(1), ML_EPI_WARPS);
       fence_barrier_init();
     }
     __syncwarp();
@@ -243,7 +250,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #endif
       auto g1 = [&](int n) {
         const int i = n / NC, c = n - i * NC, xb = i % XB, b = n & 1;
-        if (c == 0) ML_TIMED_WAIT(0, mbar_wait(x_full(xb), ((uint32_t)(i / XB)) & 1u));
+        if (c == 0) ML_TIMED_WAIT(0, mbar_wait(fuse_ln ? xn_full(xb) : x_full(xb), ((uint32_t)(i / XB)) & 1u));
         ML_TIMED_WAIT(1, mbar_wait(acc1_empty(b), (((uint32_t)n >> 1) & 1u) ^ 1u));
         tc_fence_after();
         const uint32_t acc = tmem_base + b * HC;
@@ -316,6 +323,58 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_start = clock64();
 #endif
+    // Fused pre-LayerNorm (norm2 of the Swin block): the X tile of tile i2 is normalised in place once TMA has
+    // delivered it -- four threads per row (a row = C/32 k-chunks x 8 swizzled 16-byte units), two-pass statistics in
+    // registers, TF32-rounded result -- and handed to the MMA thread through xn_full.
+    auto layernorm_tile = [&](int i2) {
+      if constexpr (K::kStaged) {
+        const int xb = i2 % XB;
+        mbar_wait(x_full(xb), ((uint32_t)(i2 / XB)) & 1u);
+        const int row = threadIdx.x >> 2, sub = threadIdx.x & 3;
+        uint8_t* xrow = smem_gen + xb * K::kXBytes + row * 128;
+        float4 v[K::kXChunks][2];
+        float sum = 0.f;
+#pragma unroll
+        for (int kc = 0; kc < K::kXChunks; ++kc)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            v[kc][h] = *reinterpret_cast<const float4*>(xrow + kc * ML_KCH + (((sub + 4 * h) ^ (row & 7)) << 4));
+            sum += (v[kc][h].x + v[kc][h].y) + (v[kc][h].z + v[kc][h].w);
+          }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float mean = sum * (1.f / (float)C);
+        float sq = 0.f;
+#pragma unroll
+        for (int kc = 0; kc < K::kXChunks; ++kc)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float a = v[kc][h].x - mean, b = v[kc][h].y - mean, e = v[kc][h].z - mean, f = v[kc][h].w - mean;
+            sq += (a * a + b * b) + (e * e + f * f);
+          }
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+        const float rstd = rsqrtf(sq * (1.f / (float)C) + p.ln_eps);
+#pragma unroll
+        for (int kc = 0; kc < K::kXChunks; ++kc)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int ch = kc * ML_BK + (sub + 4 * h) * 4;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + ch));
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_beta + ch));
+            float4 o;
+            o.x = round_tf32((v[kc][h].x - mean) * rstd * g.x + bt.x);
+            o.y = round_tf32((v[kc][h].y - mean) * rstd * g.y + bt.y);
+            o.z = round_tf32((v[kc][h].z - mean) * rstd * g.z + bt.z);
+            o.w = round_tf32((v[kc][h].w - mean) * rstd * g.w + bt.w);
+            *reinterpret_cast<float4*>(xrow + kc * ML_KCH + (((sub + 4 * h) ^ (row & 7)) << 4)) = o;
+          }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xn_full(xb));
+      }
+    };
+    if (fuse_ln && nt > 0) layernorm_tile(0);
     for (int i = 0; i < nt; ++i) {
       const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * ML_BM;
       if constexpr (!K::kStaged) {
@@ -380,6 +439,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         if (lane == 0) mbar_arrive(h_full(j));
         ML_MARK(te);
         ML_SPAN(6, td, te);
+        // the next tile's X has had the whole of this chunk to arrive; its first fc1 MMA is issued after chunk 1's fc2
+        if (c == 0 && fuse_ln && i + 1 < nt) layernorm_tile(i + 1);
       }
       ML_MARK(tf);
       // ---- tile tail: out = acc2 + b2 + residual ------------------------------------------------------------
@@ -558,6 +619,8 @@ int mlp_prepare(const svx_mlp_desc& d, MlpPrepared** out) {
   SVX_REQUIRE(al16(d.x) && al16(d.W1) && al16(d.b1) && al16(d.W2) && al16(d.b2) && al16(d.residual) && al16(d.out),
               "mlp: pointers must be 16-byte aligned");
   SVX_REQUIRE(d.ldx % 4 == 0 && d.ldx >= d.C && d.ldo % 4 == 0 && d.ldo >= d.C, "mlp: bad row pitch");
+  SVX_REQUIRE(!d.ln_gamma || (d.C == 96 && d.ln_beta && al16(d.ln_gamma) && al16(d.ln_beta)),
+              "mlp: the fused LayerNorm exists for C = 96 only and needs gamma and beta");
   MlpPrepared* g = new MlpPrepared();
   const int hc = d.C == 96 ? 128 : 64;
   int rc = encode_rows_map(&g->map_x, d.x, (uint64_t)d.M, (uint64_t)d.C, (uint64_t)d.ldx, ML_BM);
@@ -575,6 +638,9 @@ int mlp_prepare(const svx_mlp_desc& d, MlpPrepared** out) {
   g->p.out = d.out;
   g->p.ldo = d.ldo;
   g->p.round_tf32 = d.round_tf32;
+  g->p.ln_gamma = d.ln_gamma;
+  g->p.ln_beta = d.ln_beta;
+  g->p.ln_eps = d.ln_eps;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -61,6 +61,11 @@ def mlp_fusable(c, hidden):
     return c in (96, 192) and hidden == 4 * c and not os.environ.get("SVX_NO_MLP_FUSION")
 
 
+def mlp_ln_fusable(c):
+    """widths for which the fused MLP kernel can also apply the preceding LayerNorm (two X buffers: stage 0)"""
+    return c == 96 and not os.environ.get("SVX_NO_MLP_LN_FUSION")
+
+
 def round_up(x, m):
     return (x + m - 1) // m * m
 
@@ -429,7 +434,7 @@ class Plan:
                   4.0 * (d.M * pack.K + d.M * n_out * (2 if residual is not None else 1) + pack.N * pack.K))
         return out
 
-    def mlp(self, x, pack1, pack2, out, residual, round_out=False, name=None):
+    def mlp(self, x, pack1, pack2, out, residual, round_out=False, name=None, ln=None):
         """timm Mlp (fc1 -> GELU -> fc2) + the block's second residual as one kernel (svx_mlp_desc): the hidden activation
         stays on the SM.  x: TF32-rounded norm2 output [pixels, C]; pack1 / pack2: fc1 [4C, C] / fc2 [C, 4C] packs."""
         Cc, hid = pack1.K, pack1.N
@@ -448,7 +453,11 @@ class Plan:
         d.residual, d.out, d.ldo = self.hold(residual).buf.data_ptr(), self.hold(out).buf.data_ptr(), out.Cs
         d.M, d.C, d.hidden = x.pixels, Cc, hid
         d.round_tf32 = 1 if round_out else 0
-        self._add("mlp", d, name or "mlp", 4.0 * d.M * Cc * hid, 4.0 * (3 * d.M * Cc + 2 * Cc * hid))
+        if ln is not None:   # (gamma, beta, eps): x holds the un-normalised rows, the kernel applies the block's norm2 itself
+            assert mlp_ln_fusable(Cc)
+            d.ln_gamma, d.ln_beta, d.ln_eps = self.hold(ln[0]).data_ptr(), self.hold(ln[1]).data_ptr(), float(ln[2])
+        self._add("mlp", d, name or "mlp", 4.0 * d.M * Cc * hid,
+                  4.0 * ((2 if ln is not None and x is residual else 3) * d.M * Cc + 2 * Cc * hid))
         return out
 
     def conv(self, x, pack, taps, out, stride=(1, 1, 1), out_map=None, rows_dhw=None, act=ACT_NONE, act_param=0.0,

@@ -161,12 +161,19 @@ def lower_swin(plan, swin, img, N, stage_tail=None):
             x1 = plan.new_act(N, 1, H, H, Cc)
             plan.linear(att, E.pack_matrix(blk.attn.proj.weight, blk.attn.proj.bias, dev), x1, residual=x,
                         name=nm + ".proj")
-            y2 = plan.new_act(N, 1, H, H, Cc)
-            plan.layernorm_rows(x1, blk.norm2.weight.detach().float().to(dev), blk.norm2.bias.detach().float().to(dev), y2,
-                                eps=blk.norm2.eps, name=nm + ".norm2")
+            g2, b2 = blk.norm2.weight.detach().float().to(dev), blk.norm2.bias.detach().float().to(dev)
+            fused = E.mlp_fusable(Cc, blk.mlp.fc1.out_features)
             x = plan.new_act(N, 1, H, H, Cc)
-            if E.mlp_fusable(Cc, blk.mlp.fc1.out_features):
-                # stages 0 / 1: fc1 -> GELU -> fc2 -> + x1 in one kernel, the 4C-wide hidden activation stays on the SM
+            if fused and E.mlp_ln_fusable(Cc):
+                # stage 0: norm2 -> fc1 -> GELU -> fc2 -> + x1 in one kernel (x1 is read once, normalised in shared memory)
+                plan.mlp(x1, E.pack_matrix(blk.mlp.fc1.weight, blk.mlp.fc1.bias, dev),
+                         E.pack_matrix(blk.mlp.fc2.weight, blk.mlp.fc2.bias, dev), x, residual=x1, name=nm + ".mlp",
+                         ln=(g2, b2, blk.norm2.eps))
+                continue
+            y2 = plan.new_act(N, 1, H, H, Cc)
+            plan.layernorm_rows(x1, g2, b2, y2, eps=blk.norm2.eps, name=nm + ".norm2")
+            if fused:
+                # stage 1: fc1 -> GELU -> fc2 -> + x1 in one kernel, the 4C-wide hidden activation stays on the SM
                 plan.mlp(y2, E.pack_matrix(blk.mlp.fc1.weight, blk.mlp.fc1.bias, dev),
                          E.pack_matrix(blk.mlp.fc2.weight, blk.mlp.fc2.bias, dev), x, residual=x1, name=nm + ".mlp")
                 continue

@@ -309,6 +309,7 @@ int mlp_prepare(const svx_mlp_desc& d, MlpPrepared** out) {
   SVX_REQUIRE(d.M > 0 && (d.C == 96 || d.C == 192) && d.hidden == 4 * d.C, "mlp: unsupported shape");
   SVX_REQUIRE(d.x && d.W1 && d.b1 && d.W2 && d.b2 && d.residual && d.out, "mlp: null operand");
   SVX_REQUIRE(d.ldx % 4 == 0 && d.ldx >= d.C && d.ldo % 4 == 0 && d.ldo >= d.C, "mlp: bad row pitch");
+  SVX_REQUIRE(!d.ln_gamma || (d.C == 96 && d.ln_beta), "mlp: the fused LayerNorm exists for C = 96 only");
   *out = new MlpPrepared();
   return 0;
 }
@@ -326,6 +327,16 @@ int mlp_launch(const svx_mlp_desc& d, MlpPrepared* prepared, void*) {
     std::vector<float> xr(d.C), h(d.hidden);
 #pragma omp for schedule(static)
     for (int r = 0; r < d.M; ++r) {
+      if (d.ln_gamma) {   // fused pre-LayerNorm: fc1 reads round_tf32(LN(x) * gamma + beta)
+        double mean = 0, var = 0;
+        for (int k = 0; k < d.C; ++k) mean += d.x[(long long)r * d.ldx + k];
+        mean /= d.C;
+        for (int k = 0; k < d.C; ++k) { const double t = d.x[(long long)r * d.ldx + k] - mean; var += t * t; }
+        var /= d.C;
+        const float rstd = 1.f / sqrtf((float)var + d.ln_eps);
+        for (int k = 0; k < d.C; ++k)
+          xr[k] = tf32_rna((d.x[(long long)r * d.ldx + k] - (float)mean) * rstd * d.ln_gamma[k] + d.ln_beta[k]);
+      } else
       for (int k = 0; k < d.C; ++k) xr[k] = tf32_trunc(d.x[(long long)r * d.ldx + k]);
       for (int j = 0; j < d.hidden; ++j) {
         float acc = 0.f;

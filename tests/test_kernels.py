@@ -97,6 +97,29 @@ def test_gemm_epilogue(dev, act, res_after):
     assert rel_err(out.view().reshape(M, N), ref) < 6e-4  # result is rounded to TF32 (2^-11)
 
 
+@pytest.mark.parametrize("M", [128, 1000, 148 * 128 * 3 + 77])
+def test_mlp_fused_with_layernorm(dev, M):
+    """the stage-0 variant that also applies the block's norm2: x1 -> LN -> fc1 -> GELU -> fc2 -> + x1"""
+    DEV = dev
+    torch.manual_seed(M)
+    C, hid = 96, 384
+    x1 = torch.randn(M, C) * 1.5 + 0.3
+    g, b = torch.rand(C) + 0.5, torch.randn(C) * 0.2
+    w1, b1 = torch.randn(hid, C) / C ** 0.5, torch.randn(hid) * 0.5
+    w2, b2 = torch.randn(C, hid) / hid ** 0.5, torch.randn(C) * 0.5
+    p = E.Plan(DEV)
+    out = p.new_act(M, 1, 1, 1, C)
+    xa = E.Act(x1.to(DEV), M, 1, 1, 1, C)
+    p.mlp(xa, E.pack_matrix(w1, b1, DEV), E.pack_matrix(w2, b2, DEV), out, residual=xa, ln=(g.to(DEV), b.to(DEV), 1e-5))
+    p.run()
+    p.run()
+    sync(DEV)
+    y = F.layer_norm(x1.double(), (C,), g.double(), b.double(), 1e-5)
+    h = F.gelu(E.tf32_round(y.float()).double() @ E.tf32_round(w1).double().t() + b1.double())
+    ref = E.tf32_round(h.float()).double() @ E.tf32_round(w2).double().t() + b2.double() + x1.double()
+    assert rel_err(out.view().reshape(M, C), ref) < 5e-4   # LN output rounded to TF32 at slightly different values
+
+
 @pytest.mark.parametrize("M,C", [(128, 96), (1000, 96), (19 * 128 + 5, 96), (148 * 128 * 2 + 77, 96), (640, 192),
                                  (3001, 192), (148 * 128 + 130, 192)])
 def test_mlp_fused(dev, M, C):
