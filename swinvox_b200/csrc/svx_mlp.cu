@@ -439,8 +439,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         if (lane == 0) mbar_arrive(h_full(j));
         ML_MARK(te);
         ML_SPAN(6, td, te);
-        // the next tile's X has had the whole of this chunk to arrive; its first fc1 MMA is issued after chunk 1's fc2
-        if (c == 0 && fuse_ln && i + 1 < nt) layernorm_tile(i + 1);
+        // after chunk 1: the next tile's X (requested when the previous output tile had left) has had two chunks to
+        // arrive -- normalising it after chunk 0 stalled ~1.5k cycles per tile on x_full -- and its first fc1 MMA, issued
+        // behind chunk 1's fc2, is not needed before this tile's tail is done
+        if (c == (NC > 1 ? 1 : 0) && fuse_ln && i + 1 < nt) layernorm_tile(i + 1);
       }
       ML_MARK(tf);
       // ---- tile tail: out = acc2 + b2 + residual ------------------------------------------------------------

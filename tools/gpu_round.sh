@@ -16,4 +16,6 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
     --log-file gpurun_out/launches_r1_$tag.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launch_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"gemm_tf32_kernel" --launch-skip 60 -c 6 \
     -o gpurun_out/prof_gemm_$tag python tools/run_module.py encoder 64 3 1 > gpurun_out/ncu_gemm_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"mlp_fused_kernel|conv3_slab_kernel|winattn_kernel" -c 8 \
+    -o gpurun_out/prof_other_$tag python tools/run_module.py all 64 3 1 > gpurun_out/ncu_other_$tag.log 2>&1
 tail -2 gpurun_out/gpu_tests_$tag.log; cut -c1-300 gpurun_out/bench_$tag.json
