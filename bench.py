@@ -206,7 +206,8 @@ def run_ours(args):
         ev.submit(tax, images_h, gt_h)
     max_iou, report = ev.finish(print_tables=False)
     barrier()
-    assert got["batches"] == args.steps and report["n_samples"] == B * args.steps
+    # finish() adds the per-taxonomy sums over the ranks (one all_reduce): the report counts the whole job's samples
+    assert got["batches"] == args.steps and report["n_samples"] == B * args.steps * world, (got, report["n_samples"])
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)

@@ -84,6 +84,8 @@ enum { SVX_POOL_MAX = 0, SVX_POOL_AVG = 1 };
  *                 valid_W.  Weights are laid out for the kw-in-N formulation: W is [48, 288] with
  *                 row = kw*16 + co, col = (kd*3 + kh)*32 + c; block_n = Npad = 48, K = Kpad = 288; cin_live =
  *                 leading channels with non-zero weights (contraction steps beyond them are skipped).
+ *                 The MMA operands of this mode are fp16 (kind::f16, fp32 accumulation): the kernel converts the fp32
+ *                 slabs and weights in shared memory (exact for TF32-rounded values with |x| in [6.1e-5, 65504]).
  * W: [Npad, Kpad] fp32, K contiguous, zero padded, values pre-rounded to TF32 (rna) by the host.
  * result = out_scale * (res_after_act ? act(acc+bias) + res : act(acc+bias+res)).
  * Output row r is stored at out + o_base + n*o_sn + od*o_sd + oh*o_sh + ow*o_sw (elements),
