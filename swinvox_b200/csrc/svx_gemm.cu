@@ -734,14 +734,17 @@ template <int ROWB, bool F16 = false>
 struct S3Cfg {
   static constexpr int kOpRowB = F16 ? ROWB / 2 : ROWB;            // bytes per operand row
   static constexpr int kSlabBytes = S3_ROWS * kOpRowB;
-  static constexpr int kNSlab = F16 ? (ROWB == 128 ? 5 : 10) : (ROWB == 128 ? 5 : 10);
+  static constexpr int kNSlab = F16 ? (ROWB == 128 ? 4 : 10) : (ROWB == 128 ? 5 : 10);
   // fp32 staging slabs (F16 only): the TMA round trip is hidden by THIS ring now (three slots left the kernel
   // latency-bound: one slab per third of a round trip), the operand ring only decouples converters and MMAs
-  static constexpr int kNStg = F16 ? (ROWB == 128 ? 4 : 6) : 0;
+  static constexpr int kNStg = F16 ? (ROWB == 128 ? 3 : 6) : 0;
+  // F16: two exchange buffers per epilogue set, so a tile needs ONE 128-thread barrier (write | read) instead of two
+  static constexpr int kXchgBufs = F16 ? 2 : 1;
+  static constexpr int kXchgBytes = kXchgBufs * S3_XCHG_BYTES;
   static constexpr int kTapBytes = S3_N * kOpRowB;     // one (kd,kh) weight block
   static constexpr int kWBytes = (9 * kTapBytes + 1023) / 1024 * 1024;
   static constexpr int kStgBytes = F16 ? S3_ROWS * ROWB : 0;
-  static constexpr int kSmem = 1024 + kWBytes + kNSlab * kSlabBytes + kNStg * kStgBytes + S3_XCHG_BYTES + 512;
+  static constexpr int kSmem = 1024 + kWBytes + kNSlab * kSlabBytes + kNStg * kStgBytes + kXchgBytes + 512;
   static_assert(kSmem <= 232448, "slab kernel shared memory");
 };
 
@@ -768,7 +771,7 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   const uint32_t slab_smem = smem_base + kSlabOff;
   constexpr int kXchgOff = kSlabOff + S3_NSLAB * S3_SLAB_BYTES;
   float* xchg = reinterpret_cast<float*>(smem_gen + kXchgOff);
-  const uint32_t bar_base = smem_base + kXchgOff + S3_XCHG_BYTES;
+  const uint32_t bar_base = smem_base + kXchgOff + SC::kXchgBytes;
   // barriers: slab_full[5], slab_empty[5], w_full, acc_full[8], acc_empty[8], tmem slot
   auto slab_full = [&](uint32_t s) { return bar_base + 8u * s; };
   auto slab_empty = [&](uint32_t s) { return bar_base + 8u * (S3_NSLAB + s); };
@@ -780,7 +783,7 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   constexpr int kSlotIdx = 2 * S3_NSLAB + 1 + 2 * S3_NACC + 2 * S3_NSTG;
   const uint32_t tmem_slot = bar_base + 8u * kSlotIdx;
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + kXchgOff + S3_XCHG_BYTES + 8 * kSlotIdx);
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kXchgOff + SC::kXchgBytes + 8 * kSlotIdx);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // PAIR: the two CTAs of a cluster work on two different units in lock step; the leader (rank 0) issues ONE
@@ -975,10 +978,8 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const uint32_t set = warp >= 6 ? 1u : 0u;
     const int r = quarter * 32 + lane;
     const int r1 = min(r + 1, BM - 1), r2 = min(r + 2, BM - 1);
-    char* xb = reinterpret_cast<char*>(xchg) + set * (BM * 128);
-    char* my_row = xb + r * 128;
-    const char* row1 = xb + r1 * 128;
-    const char* row2 = xb + r2 * 128;
+    char* xb0 = reinterpret_cast<char*>(xchg) + set * (SC::kXchgBufs * BM * 128);
+    uint32_t xk = 0;   // tiles this set has exchanged (selects the buffer)
     const int barid = 1 + static_cast<int>(set);
     float bias[16];
 #pragma unroll
@@ -1016,6 +1017,11 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #ifdef SVX_SLAB_NOEPI   // experiment: how fast is the TMA + MMA side alone? (results are wrong)
         if (d0[0] != 0x7fc12345u) continue;
 #endif
+        char* xb = xb0 + (SC::kXchgBufs == 2 ? (xk & 1u) * (BM * 128) : 0u);
+        ++xk;
+        char* my_row = xb + r * 128;
+        const char* row1 = xb + r1 * 128;
+        const char* row2 = xb + r2 * 128;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           *reinterpret_cast<uint4*>(my_row + ((c ^ (r & 7)) << 4)) = make_uint4(d1[4 * c], d1[4 * c + 1], d1[4 * c + 2], d1[4 * c + 3]);
@@ -1032,7 +1038,9 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           x[4 * c + 2] = (__uint_as_float(d0[4 * c + 2]) + s1.z) + (s2.z + bias[4 * c + 2]);
           x[4 * c + 3] = (__uint_as_float(d0[4 * c + 3]) + s1.w) + (s2.w + bias[4 * c + 3]);
         }
-        named_bar_sync(barid, 128);   // staging buffer may be overwritten by this set's next tile
+        // one buffer: it may be overwritten by this set's next tile.  Two buffers: the next tile writes the other one, and
+        // nobody writes this one again before passing the next tile's barrier, i.e. after every thread finished this read
+        if (SC::kXchgBufs == 1) named_bar_sync(barid, 128);
         if (row_ok) {
           const long long off = off0 + d * p.o_sd;
           float* dst = p.out + off;
