@@ -239,6 +239,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of the previous kernel in
+  // the stream; its results are only touched from here on.  The next kernel may start its own preamble right away.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 4) {
     // ---- TMA producer (one elected thread: elect.sync lets ptxas issue the uniform-datapath TMA / MMA
@@ -1220,7 +1224,19 @@ int launch_bn_parts(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensor
     SVX_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
-  gemm_tf32_kernel<BN, PARTS><<<grid, C::kThreadsT, C::kSmemBytes, st>>>(ma, mb, mc, mr, p);
+  static const bool pdl = getenv("SVX_PDL") != nullptr;   // opt-in until validated on the GPU tier
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(C::kThreadsT);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, PARTS>, ma, mb, mc, mr, p);
+  if (le != cudaSuccess) return fail("launch of gemm_tf32_kernel failed: %s", cudaGetErrorString(le));
   SVX_LAUNCH_OK("gemm_tf32_kernel");
   return 0;
 }

@@ -157,6 +157,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();               // (see svx_gemm.cu: the preamble above overlapped the previous kernel's tail)
+  pdl_launch_dependents();
 
   if (warp == ML_WARP_W) {
     // ---- weight producer: the ring carries W1 / W2 k-chunks in the MMA thread's order -----------------------
@@ -599,7 +601,19 @@ int launch_mlp(const CUtensorMap& mx, const CUtensorMap& m1, const CUtensorMap& 
                                      MlpCfg<C, HC>::kSmem));
     configured = true;
   }
-  mlp_fused_kernel<C, HC><<<grid, ML_THREADS, MlpCfg<C, HC>::kSmem, st>>>(mx, m1, m2, mr, mo, p);
+  static const bool pdl = getenv("SVX_PDL") != nullptr;   // opt-in until validated on the GPU tier
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(ML_THREADS);
+  cfg.dynamicSmemBytes = MlpCfg<C, HC>::kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, mlp_fused_kernel<C, HC>, mx, m1, m2, mr, mo, p);
+  if (le != cudaSuccess) return fail("launch of mlp_fused_kernel failed: %s", cudaGetErrorString(le));
   SVX_LAUNCH_OK("mlp_fused_kernel");
   return 0;
 }

@@ -17,6 +17,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---- programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running; it must not touch the predecessor's results before pdl_wait()
+// (which returns once the predecessor grid has completed and flushed).  pdl_launch_dependents() lets the successor's CTAs
+// be scheduled as soon as this grid's CTAs make room. -----------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- mbarrier ---------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
