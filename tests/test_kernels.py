@@ -97,6 +97,27 @@ def test_gemm_epilogue(dev, act, res_after):
     assert rel_err(out.view().reshape(M, N), ref) < 6e-4  # result is rounded to TF32 (2^-11)
 
 
+@pytest.mark.parametrize("C,M", [(96, 192 * 56 * 56), (192, 192 * 28 * 28)])
+def test_mlp_fused_full_size_identity(dev, C, M):
+    """BASELINE-size property (64 objects x 3 views, Swin stages 0 / 1): with W2 = 0 the fused kernel must return
+    residual + b2 bit-exactly for every row -- every tile of every CTA goes through the staged / transposed tile tail."""
+    DEV = dev
+    if DEV == "cpu":
+        M = 4 * 128 + 3   # the CPU twin has no tiles to get wrong; keep the CPU tier fast
+    torch.manual_seed(C)
+    hid = 4 * C
+    x = E.tf32_round(torch.randn(M, C))
+    res = torch.randn(M, C)
+    b2 = torch.randn(C)
+    p = E.Plan(DEV)
+    out = p.new_act(M, 1, 1, 1, C)
+    p.mlp(E.Act(x.to(DEV), M, 1, 1, 1, C), E.pack_matrix(torch.randn(hid, C) / C ** 0.5, torch.randn(hid), DEV),
+          E.pack_matrix(torch.zeros(C, hid), b2, DEV), out, residual=E.Act(res.to(DEV), M, 1, 1, 1, C))
+    p.run()
+    sync(DEV)
+    assert torch.equal(out.view().reshape(M, C).cpu(), res + b2)
+
+
 @pytest.mark.parametrize("M", [128, 1000, 148 * 128 * 3 + 77])
 def test_mlp_fused_with_layernorm(dev, M):
     """the stage-0 variant that also applies the block's norm2: x1 -> LN -> fc1 -> GELU -> fc2 -> + x1"""
