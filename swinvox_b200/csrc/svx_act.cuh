@@ -75,27 +75,27 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
 __device__ __forceinline__ void gelu_erf2_fast(float& x0, float& x1) {
   const uint64_t x = pack2(x0, x1);
   const uint64_t ax = x & 0x7fffffff7fffffffull;
-  constexpr float c1 = 0.0705230784f * 0.70710678118654752440f, c2 = 0.0422820123f * 0.5f,
-                  c3 = 0.0092705272f * 0.35355339059327376220f, c4 = 0.0001520143f * 0.25f,
-                  c5 = 0.0002765672f * 0.17677669529663688110f, c6 = 0.0000430638f * 0.125f;
+  // P scaled by s = 2^(1/16), so that P^16 comes out doubled and its reciprocal is already 0.5 / P^16:
+  //   gelu(x) = max(x, 0) - |x| * (0.5 / P(|x|)^16)          (6 FMA + 4 MUL + 1 FMA on the FP32 pipe per element)
+  constexpr float s = 1.04427378242741384032f;
+  constexpr float c0 = s, c1 = s * 0.0705230784f * 0.70710678118654752440f, c2 = s * 0.0422820123f * 0.5f,
+                  c3 = s * 0.0092705272f * 0.35355339059327376220f, c4 = s * 0.0001520143f * 0.25f,
+                  c5 = s * 0.0002765672f * 0.17677669529663688110f, c6 = s * 0.0000430638f * 0.125f;
   uint64_t q = fma2(pack2(c6, c6), ax, pack2(c5, c5));
   q = fma2(q, ax, pack2(c4, c4));
   q = fma2(q, ax, pack2(c3, c3));
   q = fma2(q, ax, pack2(c2, c2));
   q = fma2(q, ax, pack2(c1, c1));
-  q = fma2(q, ax, pack2(1.f, 1.f));
+  q = fma2(q, ax, pack2(c0, c0));
   q = mul2(q, q);
   q = mul2(q, q);
   q = mul2(q, q);
-  q = mul2(q, q);                                      // P^16 (overflows to +inf for |x| > ~14: 1/inf = 0, erf = 1)
+  q = mul2(q, q);                                      // 2 P^16 (overflows to +inf for |x| > ~14: 1/inf = 0, erf = 1)
   float q0, q1, r0, r1;
   unpack2(q, q0, q1);
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(q0));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(q1));
-  const uint64_t hx = mul2(x, pack2(0.5f, 0.5f));
-  const uint64_t nhax = hx | 0x8000000080000000ull;   // -0.5 |x|
-  const uint64_t relu = fma2(nhax, pack2(-1.f, -1.f), hx);   // 0.5 x + 0.5 |x|
-  unpack2(fma2(nhax, pack2(r0, r1), relu), x0, x1);
+  unpack2(fma2(ax, pack2(-r0, -r1), pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), x0, x1);
 }
 
 }  // namespace svx
