@@ -6,9 +6,12 @@
 //   G1(c): acc1[b] (TMEM, 128 x HC)  = X (smem, resident for the tile) . W1[c]^T       tcgen05.mma kind::tf32
 //   E(c):  H (smem ring, 128B-swizzled K-major operand tiles) = round_tf32(gelu(acc1[b] + b1[c]))   16 epilogue warps
 //   G2(c): acc2 (TMEM, 128 x C)     += H . W2[:, c]^T
-// and after the last chunk out = acc2 + b2 + residual.  The single MMA-issuing thread runs the software pipeline
-// G1(0) G1(1) | G2(n) G1(n+2) ... over the chunk stream of ALL its tiles, so the tensor pipe works on chunk n+1 / n+2
-// while the epilogue warps are in the GELU of chunk n, also across tile boundaries.
+// and after the last chunk out = acc2 + b2 + residual (the tile tail: staged through shared memory by TMA for C = 96,
+// transposed to 64-byte row segments for C = 192).  With ln_gamma set (C = 96) the epilogue warps first apply the block's
+// norm2 to the TMA-delivered X tile in place, so the kernel reads the un-normalised x1 once and no norm2 kernel runs.
+// The single MMA-issuing thread runs the software pipeline G1(0) G1(1) | G2(n) G1(n+2) ... over the chunk stream of ALL
+// its tiles, so the tensor pipe works on chunk n+1 / n+2 while the epilogue warps are in the GELU of chunk n, also across
+// tile boundaries.
 //
 //   warps 0-15  epilogue: TMEM lane quarter = warp % 4, column part = warp / 4
 //   warp 16     TMA producer of the W1 / W2 k-chunks (a ring in exactly the order the MMA thread consumes them)
@@ -45,7 +48,6 @@ struct MlpCfg {
   // phase.  The tile borrows the X buffer of its own tile: X(i) is dead after the last fc1 MMA of tile i, the tail
   // comes two chunks later, and X(i+2) is not needed before the end of tile i+1.
   static constexpr bool kStaged = kXBufs == 2;
-  static constexpr int kRBytes = 0;
   static constexpr int kNHS = HC / ML_BK;                  // H ring slots = k-chunks of one hidden chunk
   static constexpr int kSPP = HC / 64;                     // 16-column slabs per epilogue warp and chunk
   static constexpr int kHFullCount = 4 * (2 / kSPP);       // warps that write one H k-chunk
@@ -55,7 +57,7 @@ struct MlpCfg {
   // W1 k-chunks per ring stage: as many as fit in the slot and divide the chunk count (C = 192, HC = 64: 3 x 8 KB)
   static constexpr int kW1PerStage = (kW1PerStageRaw >= 3 && kXChunks % 3 == 0) ? 3 : (kW1PerStageRaw >= 2 && kXChunks % 2 == 0) ? 2 : 1;
   static constexpr int kW1Stages = kXChunks / kW1PerStage; // ring stages one fc1 chunk consumes
-  static constexpr int kFixed = 1024 + 512 + kXBufs * kXBytes + kRBytes + kNHS * ML_KCH;
+  static constexpr int kFixed = 1024 + 512 + kXBufs * kXBytes + kNHS * ML_KCH;
   static constexpr int kWStagesRaw = (ML_SMEM_MAX - kFixed) / kWStage;
   static constexpr int kWStages = kWStagesRaw > 8 ? 8 : kWStagesRaw;
   static_assert(kWStages >= 3, "weight ring too shallow");
