@@ -45,3 +45,32 @@ def test_null_descriptor_is_an_error_not_a_crash():
     assert lib.svx_gemm(None, None) != 0
     assert b"null descriptor" in lib.svx_last_error()
     assert lib.svx_binvox_decode(None, None) != 0
+
+
+def test_mlp_rejects_unsupported_shapes_before_touching_the_device():
+    """svx_mlp validates its descriptor first (widths, hidden = 4C, alignment, LayerNorm only for C = 96): a bad
+    description is a return code + message, never a launch."""
+    lib = _lib.bind(_lib.LIB_PATH)
+    assert lib.svx_mlp(None, None) != 0 and b"null descriptor" in lib.svx_last_error()
+    buf = (C.c_float * 64)()
+    base = C.addressof(buf)
+    base += (16 - base % 16) % 16
+
+    def desc(Cc, hidden, ln=False):
+        d = _lib.MlpDesc()
+        d.x = d.W1 = d.b1 = d.W2 = d.b2 = d.residual = d.out = base
+        d.ldx = d.ldo = Cc
+        d.M, d.C, d.hidden = 128, Cc, hidden
+        if ln:
+            d.ln_gamma = d.ln_beta = base
+            d.ln_eps = 1e-5
+        return d
+
+    for bad in (desc(128, 512), desc(96, 192), desc(384, 1536), desc(192, 768, ln=True)):
+        plan = lib.svx_plan_create()
+        try:
+            assert lib.svx_plan_add_mlp(plan, C.byref(bad)) != 0
+            assert b"mlp" in lib.svx_last_error()
+            assert lib.svx_plan_num_ops(plan) == 0
+        finally:
+            lib.svx_plan_destroy(plan)
