@@ -48,7 +48,12 @@ struct MlpCfg {
   // phase.  The tile borrows the X buffer of its own tile: X(i) is dead after the last fc1 MMA of tile i, the tail
   // comes two chunks later, and X(i+2) is not needed before the end of tile i+1.
   static constexpr bool kStaged = kXBufs == 2;
-  static constexpr int kNHS = HC / ML_BK;                  // H ring slots = k-chunks of one hidden chunk
+  static constexpr int kKCh = HC / ML_BK;                  // k-chunks of one hidden chunk
+  // H ring slots: one per k-chunk of a hidden chunk while shared memory allows (C = 96); C = 192 has room for two, so
+  // with HC = 128 a slot is used twice per chunk (k-chunks s and s + 2) and has its own "consumed" barrier
+  static constexpr int kNHS = C <= 96 ? kKCh : 2;
+  static constexpr int kUPS = kKCh / kNHS;                 // uses of one slot per hidden chunk
+  static_assert(kKCh % kNHS == 0 && (kUPS == 1 || kUPS == 2), "H ring shape");
   static constexpr int kSPP = HC / 64;                     // 16-column slabs per epilogue warp and chunk
   static constexpr int kHFullCount = 4 * (2 / kSPP);       // warps that write one H k-chunk
   static constexpr int kWRows = C > HC ? C : HC;
@@ -62,8 +67,9 @@ struct MlpCfg {
   static constexpr int kWStages = kWStagesRaw > 8 ? 8 : kWStagesRaw;
   static_assert(kWStages >= 3, "weight ring too shallow");
   static constexpr int kSmem = kFixed + kWStages * kWStage;
-  static constexpr uint32_t kAcc2Col = 2 * HC;             // TMEM: acc1[0], acc1[1], acc2[0], acc2[1]
-  static_assert(2 * HC + 2 * C <= 512, "TMEM columns");
+  static constexpr uint32_t kAcc2Col = 2 * HC;             // TMEM: acc1[0], acc1[1], acc2[0] (, acc2[1])
+  static constexpr int kAcc2Bufs = (2 * HC + 2 * C <= 512) ? 2 : 1;
+  static_assert(2 * HC + kAcc2Bufs * C <= 512, "TMEM columns");
   static constexpr int kOutSlabs = C / 16;
   static constexpr int kMaxOutSlabs = (kOutSlabs + 3) / 4;  // per epilogue warp
 };
@@ -120,9 +126,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const uint32_t r_full = bar_base + 8u * (2 * WS + 17);
   const uint32_t r_done = bar_base + 8u * (2 * WS + 18);
   auto xn_full = [&](int b) { return bar_base + 8u * (2 * WS + 19 + b); };   // X tile normalised in place (fused LayerNorm)
-  const uint32_t tmem_slot = bar_base + 8u * (2 * WS + 21);
+  // kUPS == 2: one "consumed" barrier per (slot, use within the chunk).  A single barrier per slot would make the
+  // writers of the second use wait TWO phases ahead, which a parity wait cannot tell from zero phases ahead.
+  auto h_empty2 = [&](int slot, int use) { return bar_base + 8u * (2 * WS + 21 + slot * 2 + use); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * WS + 25);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
-      smem_gen + (bar_base - smem_base) + 8 * (2 * WS + 21));
+      smem_gen + (bar_base - smem_base) + 8 * (2 * WS + 25));
   const bool fuse_ln = K::kStaged && p.ln_gamma != nullptr;
 
   const int warp = threadIdx.x >> 5;
@@ -146,6 +155,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
       for (int j = 0; j < 4; ++j) mbar_init(h_full(j), K::kHFullCount);
       mbar_init(h_empty, 1u);
+      for (int s2 = 0; s2 < 2; ++s2) { mbar_init(h_empty2(s2, 0), 1u); mbar_init(h_empty2(s2, 1), 1u); }
       mbar_init(r_full, 1u);
       mbar_init(r_done, ML_EPI_WARPS);
       mbar_init(xn_full(0), ML_EPI_WARPS);
@@ -192,7 +202,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       auto load_g2 = [&](int n) {
         const int c = n % NC;
 #pragma unroll 1
-        for (int j = 0; j < NHS; ++j) {
+        for (int j = 0; j < K::kKCh; ++j) {
           const int s = slot(C * ML_BK * 4);
           if (s >= 0) tma_load_2d(w_smem + s * K::kWStage, &map_w2, w_full(s), c * HC + j * ML_BK, 0);
         }
@@ -278,25 +288,28 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       };
       auto g2 = [&](int n) {
         const int i = n / NC, c = n - i * NC;
-        const int ab = i & 1;
+        const int ab = K::kAcc2Bufs == 2 ? (i & 1) : 0;
         if (c == 0) {
-          ML_TIMED_WAIT(3, mbar_wait(acc2_empty(ab), (((uint32_t)i >> 1) & 1u) ^ 1u));
+          ML_TIMED_WAIT(3, mbar_wait(acc2_empty(ab), ((K::kAcc2Bufs == 2 ? (uint32_t)i >> 1 : (uint32_t)i) & 1u) ^ 1u));
           tc_fence_after();
         }
         const uint32_t acc = tmem_base + K::kAcc2Col + ab * C;
 #pragma unroll 1
-        for (int j = 0; j < NHS; ++j, ++g) {
-          ML_TIMED_WAIT(4, mbar_wait(h_full(j), (uint32_t)n & 1u));
+        for (int j = 0; j < K::kKCh; ++j, ++g) {
+          const int hs = j % NHS;                                          // H ring slot of this k-chunk
+          const uint32_t hu = (uint32_t)n * K::kUPS + (uint32_t)(j / NHS);   // its use count
+          ML_TIMED_WAIT(4, mbar_wait(h_full(hs), hu & 1u));
           const int s = g % WS;
           ML_TIMED_WAIT(5, mbar_wait(w_full(s), (g / WS) & 1u));
           tc_fence_after();
-          const uint64_t da = umma_desc_sw128(h_smem + j * ML_KCH);
+          const uint64_t da = umma_desc_sw128(h_smem + hs * ML_KCH);
           const uint64_t db = umma_desc_sw128(w_smem + s * K::kWStage);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_tf32(acc, da + 2u * k, db + 2u * k, idesc2, (c | j | k) != 0 ? 1u : 0u);
           umma_commit(w_empty(s));
+          if (K::kUPS == 2) umma_commit(h_empty2(hs, j / NHS));   // this slot may take its next k-chunk
         }
-        umma_commit(h_empty);                          // every fc2 MMA of this chunk has read H
+        if (K::kUPS == 1) umma_commit(h_empty);        // every fc2 MMA of this chunk has read H
         if (c == NC - 1) umma_commit(acc2_full(ab));
       };
       if (ntot > 0) g1(0);
@@ -322,7 +335,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int sw = r & 7;                              // 128B swizzle phase of the row
     const int sl0 = part * K::kSPP;                    // first 16-column slab of a hidden chunk this warp owns
     const int j = sl0 >> 1;                            // ... which lies in H k-chunk j
-    uint8_t* h_row = h_gen + j * ML_KCH + r * 128;
+    const int hs = j % NHS;                            // ... staged in ring slot hs
+    uint8_t* h_row = h_gen + hs * ML_KCH + r * 128;
 #ifdef SVX_MLP_PROFILE
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_start = clock64();
@@ -428,7 +442,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         ML_MARK(tc);
         ML_SPAN(5, tb, tc);
-        ML_TIMED_WAIT(1, mbar_wait(h_empty, ((uint32_t)n & 1u) ^ 1u));   // the fc2 MMAs of the previous chunk have read H
+        // the fc2 MMAs that read the slot's previous contents have completed
+        if (K::kUPS == 1) ML_TIMED_WAIT(1, mbar_wait(h_empty, ((uint32_t)n & 1u) ^ 1u));
+        else if (j / NHS == 0) ML_TIMED_WAIT(1, mbar_wait(h_empty2(hs, 1), ((uint32_t)n & 1u) ^ 1u));   // previous chunk's 2nd use
+        else ML_TIMED_WAIT(1, mbar_wait(h_empty2(hs, 0), (uint32_t)n & 1u));                           // this chunk's 1st use
         ML_MARK(td);
 #pragma unroll
         for (int si = 0; si < K::kSPP; ++si) {
@@ -440,7 +457,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(h_full(j));
+        if (lane == 0) mbar_arrive(h_full(hs));
         ML_MARK(te);
         ML_SPAN(6, td, te);
         // after chunk 1: the next tile's X (requested when the previous output tile had left) has had two chunks to
@@ -450,13 +467,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
       ML_MARK(tf);
       // ---- tile tail: out = acc2 + b2 + residual ------------------------------------------------------------
-      const int ab = i & 1;
+      const int ab = K::kAcc2Bufs == 2 ? (i & 1) : 0;
+      const uint32_t acc2_par = (K::kAcc2Bufs == 2 ? (uint32_t)i >> 1 : (uint32_t)i) & 1u;
       const uint32_t acc2_addr = lane_addr + K::kAcc2Col + ab * C;
       if constexpr (K::kStaged) {
         // the residual tile sits in shared memory in the X layout (128B-swizzled k-chunks, loaded by TMA); every
         // thread updates the 16-byte units of its own row in place, then the tile leaves through TMA stores
         ML_TIMED_WAIT(2, mbar_wait(r_full, (uint32_t)i & 1u));
-        ML_TIMED_WAIT(3, mbar_wait(acc2_full(ab), ((uint32_t)i >> 1) & 1u));
+        ML_TIMED_WAIT(3, mbar_wait(acc2_full(ab), acc2_par));
         tc_fence_after();
 #pragma unroll
         for (int t = 0; t < K::kMaxOutSlabs; ++t) {
@@ -498,8 +516,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         // (the row-per-lane version spent a third of the tile here).  The 2 KB lie inside the H region this warp and its
         // partner (same lane quarter, other slab) write during the GELU phase: H is dead between the last fc2 MMA of
         // the tile (acc2_full) and the pair's next H write, which the pair barrier below orders behind both tails.
-        static_assert(K::kSPP == 1, "the staging carve-out assumes one slab per warp and chunk");
-        float* stage = reinterpret_cast<float*>(h_gen + j * ML_KCH + (q * 32 + (sl0 & 1) * 16) * 128);
+        // slot / half of this warp's carve-out: the two warps of a lane quarter that write the same slot during the GELU
+        // phase (HC = 64: parts 2s, 2s+1; HC = 128: parts s, s+2) split that slot's 32 rows between them
+        const int tslot = K::kSPP == 1 ? (part >> 1) : (part & 1), thalf = K::kSPP == 1 ? (part & 1) : (part >> 1);
+        float* stage = reinterpret_cast<float*>(h_gen + tslot * ML_KCH + (q * 32 + thalf * 16) * 128);
         const int trow = lane >> 2, tch = lane & 3;    // read-back mapping: 8 rows x 4 float4 per pass
         // the residual does not depend on the accumulator: every block's share is requested before the wait (the lines
         // were pulled into L2 at the start of the tile)
@@ -515,7 +535,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                             : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        ML_TIMED_WAIT(3, mbar_wait(acc2_full(ab), ((uint32_t)i >> 1) & 1u));
+        ML_TIMED_WAIT(3, mbar_wait(acc2_full(ab), acc2_par));
         tc_fence_after();
 #pragma unroll
         for (int t = 0; t < K::kMaxOutSlabs; ++t) {
@@ -547,7 +567,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(acc2_empty(ab));
         // this warp and its partner are done with their carve-outs before either writes H again
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q * 2 + j) : "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q * 2 + tslot) : "memory");
       }
       ML_MARK(tg);
       ML_SPAN(7, tf, tg);
@@ -625,7 +645,7 @@ int launch_mlp(const CUtensorMap& mx, const CUtensorMap& m1, const CUtensorMap& 
 struct MlpPrepared {
   CUtensorMap map_x, map_w1, map_w2, map_r, map_o;
   MlpParams p;
-  int C, grid;
+  int C, hc, grid;
 };
 
 int mlp_prepare(const svx_mlp_desc& d, MlpPrepared** out) {
@@ -640,7 +660,10 @@ int mlp_prepare(const svx_mlp_desc& d, MlpPrepared** out) {
   SVX_REQUIRE(!d.ln_gamma || (d.C == 96 && d.ln_beta && al16(d.ln_gamma) && al16(d.ln_beta)),
               "mlp: the fused LayerNorm exists for C = 96 only and needs gamma and beta");
   MlpPrepared* g = new MlpPrepared();
-  const int hc = d.C == 96 ? 128 : 64;
+  // C = 192: HC = 128 (half the fc1 MMAs of HC = 64, the two H slots used twice per chunk): 0.210 -> 0.177 ms per block and
+  // 12/12 kernel tests, but the whole GPU tier has not run with it yet (no GPU slot at the end of round 1): opt-in with
+  // SVX_MLP_WIDE192=1 until it has
+  const int hc = d.C == 96 ? 128 : (getenv("SVX_MLP_WIDE192") ? 128 : 64);
   int rc = encode_rows_map(&g->map_x, d.x, (uint64_t)d.M, (uint64_t)d.C, (uint64_t)d.ldx, ML_BM);
   if (!rc) rc = encode_rows_map(&g->map_w1, d.W1, (uint64_t)d.hidden, (uint64_t)d.C, (uint64_t)d.C, (uint32_t)hc);
   if (!rc) rc = encode_rows_map(&g->map_w2, d.W2, (uint64_t)d.C, (uint64_t)d.hidden, (uint64_t)d.hidden, (uint32_t)d.C);
@@ -648,6 +671,7 @@ int mlp_prepare(const svx_mlp_desc& d, MlpPrepared** out) {
   if (!rc) rc = encode_rows_map(&g->map_o, d.out, (uint64_t)d.M, (uint64_t)d.C, (uint64_t)d.ldo, ML_BM);
   if (rc) { delete g; return rc; }
   g->C = d.C;
+  g->hc = hc;
   g->p.M = d.M;
   g->p.tiles = (d.M + ML_BM - 1) / ML_BM;
   g->p.b1 = d.b1;
@@ -678,6 +702,7 @@ int mlp_launch(const svx_mlp_desc& d, MlpPrepared* prepared, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
   if (g->C == 96) rc = launch_mlp<96, 128>(g->map_x, g->map_w1, g->map_w2, g->map_r, g->map_o, g->p, g->grid, st);
+  else if (g->hc == 128) rc = launch_mlp<192, 128>(g->map_x, g->map_w1, g->map_w2, g->map_r, g->map_o, g->p, g->grid, st);
   else rc = launch_mlp<192, 64>(g->map_x, g->map_w1, g->map_w2, g->map_r, g->map_o, g->p, g->grid, st);
   if (!prepared) delete g;
   return rc;
