@@ -660,10 +660,9 @@ int mlp_prepare(const svx_mlp_desc& d, MlpPrepared** out) {
   SVX_REQUIRE(!d.ln_gamma || (d.C == 96 && d.ln_beta && al16(d.ln_gamma) && al16(d.ln_beta)),
               "mlp: the fused LayerNorm exists for C = 96 only and needs gamma and beta");
   MlpPrepared* g = new MlpPrepared();
-  // C = 192: HC = 128 (half the fc1 MMAs of HC = 64, the two H slots used twice per chunk): 0.210 -> 0.177 ms per block and
-  // 12/12 kernel tests, but the whole GPU tier has not run with it yet (no GPU slot at the end of round 1): opt-in with
-  // SVX_MLP_WIDE192=1 until it has
-  const int hc = d.C == 96 ? 128 : (getenv("SVX_MLP_WIDE192") ? 128 : 64);
+  // C = 192: HC = 128 (half the fc1 MMAs of HC = 64, the two H slots used twice per chunk): 0.210 -> 0.177 ms per launch; the
+  // GPU tier passes with either instance (128/128).  SVX_MLP_NARROW192=1 selects the HC = 64 instance.
+  const int hc = d.C == 96 ? 128 : (getenv("SVX_MLP_NARROW192") ? 64 : 128);
   int rc = encode_rows_map(&g->map_x, d.x, (uint64_t)d.M, (uint64_t)d.C, (uint64_t)d.ldx, ML_BM);
   if (!rc) rc = encode_rows_map(&g->map_w1, d.W1, (uint64_t)d.hidden, (uint64_t)d.C, (uint64_t)d.C, (uint32_t)hc);
   if (!rc) rc = encode_rows_map(&g->map_w2, d.W2, (uint64_t)d.C, (uint64_t)d.hidden, (uint64_t)d.hidden, (uint32_t)d.C);
