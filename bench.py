@@ -96,6 +96,67 @@ def cpu_reference_rate(V, seconds_budget, sample_objects=2):
     return sample_objects / dt, os.cpu_count(), f"{n} timed passes of {sample_objects} objects x {V} views (after 1 warm-up)"
 
 
+def gpu_eager_rate(B, V, dev, seconds_budget=8.0):
+    """The on-box bar: the reference's modules as eager PyTorch on the SAME B200 -- cuDNN / cuBLAS,
+    cudnn.benchmark on (core/test.py:35), inputs resident, no per-sample host syncs, batched B x V (kinder than the
+    reference's batch-1 loop).  Timed twice: PyTorch's default precision (TF32 convolutions, fp32 matmul = what the
+    reference runs) and with TF32 matmul allowed as well.  Baseline leg only: nothing of it is on the product path."""
+    from oracle import modules as M
+    cfg = M.default_cfg()
+    torch.manual_seed(0)
+    mods = [M.RefEncoder(cfg), M.RefDecoder(cfg), M.RefMerger(cfg), M.RefRefiner(cfg)]
+    enc, dec, mer, ref = [m.eval().to(dev) for m in mods]
+    images, gt = synthetic_batch(B, V, 1)
+    images, gt = images.to(dev), gt.to(dev)
+    saved = (torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32)
+    out = {}
+    try:
+        torch.backends.cudnn.benchmark = True
+        for key, mm_tf32 in (("value", False), ("value_tf32_matmul", True)):
+            torch.backends.cuda.matmul.allow_tf32 = mm_tf32
+            with torch.no_grad():
+                def step():
+                    vol = M.forward_pipeline(enc, dec, mer, ref, images, cfg)
+                    return M.voxel_metrics(vol, gt)
+                for _ in range(3):
+                    step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n, t0 = 0, time.perf_counter()
+                e0.record()
+                while n < 3 or (time.perf_counter() - t0 < seconds_budget / 2 and n < 30):
+                    step()
+                    n += 1
+                e1.record()
+                torch.cuda.synchronize()
+            out[key] = B / (e0.elapsed_time(e1) / n * 1e-3)
+            out[key + "_steps"] = n
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32 = saved
+    del enc, dec, mer, ref, mods
+    torch.cuda.empty_cache()
+    out.update(unit="objects/s", kind="port (oracle modules, bit-exact to the reference's, as eager PyTorch on cuda)",
+               sample=f"batch {B} x {V} views resident on the device, cudnn.benchmark on; value = PyTorch default "
+                      "precision (TF32 convolutions, fp32 matmul), value_tf32_matmul = TF32 matmul allowed too")
+    return out
+
+
+def run_reference_gpu(args):
+    """`--impl reference-gpu`: the eager-PyTorch-on-B200 bar alone, as its own JSON line (N=1 only)"""
+    rank, local_rank, world = rank_env()
+    if rank != 0:
+        return
+    dev = torch.device("cuda", local_rank)
+    r = gpu_eager_rate(args.batch, args.views, dev, seconds_budget=max(8.0, args.steps))
+    line = {"impl": "reference-gpu", "metric": METRIC, "value": r["value"], "unit": "objects/s", "n_gpus": 1,
+            "steps": r["value_steps"], "warmup": 3, "ms_per_step": args.batch / r["value"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 convolutions / fp32 matmul (PyTorch default)",
+            "data": "synthetic",
+            "config": {"workload": f"batch {args.batch} x {args.views} views, merger + refiner, CVA on (BASELINE configs[1])"},
+            "gpu_eager_baseline": r}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     rank, _, world = rank_env()
     if rank != 0:
@@ -146,7 +207,7 @@ def run_ours(args):
     B, V = args.batch, args.views
     cfg = svx_config.make_cfg()
     torch.manual_seed(0)
-    rec = Reconstructor(cfg, device=dev)   # random-init weights of the reference architecture
+    rec = Reconstructor(cfg, device=dev, zero_copy=True)   # random-init weights of the reference architecture
     rec.set_graph(not args.no_graph)
     dp = DataParallelReconstructor(rec)
     images_h, gt_h = synthetic_batch(B, V, 100 + rank)
@@ -161,11 +222,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_resident():
-        return dp.evaluate_local(inbuf, gt_d)
+        # N > 1: the gather of step i runs on NCCL's stream under the forward of step i+1 (drained by dp.flush() below)
+        return dp.evaluate_local(inbuf, gt_d, wait=False)
 
     # ---- device-resident throughput ------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    dp.flush()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -173,6 +236,7 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         step_resident()
+    dp.flush()   # every step's gathered logits + counters have arrived before the clock stops
     e1.record()
     barrier()
     sampler.stop_flag = True
@@ -269,6 +333,12 @@ def run_ours(args):
         with open(os.path.join(ROOT, "gpurun_out", "op_breakdown.json"), "w") as fh:
             json.dump(sorted(breakdown, key=lambda r: -r[1]), fh)
         cpu_value, cores, sample = cpu_reference_rate(V, args.cpu_seconds) if world == 1 else (None, None, None)
+        eager = None
+        if world == 1 and not args.no_eager:
+            try:
+                eager = gpu_eager_rate(B, V, dev)
+            except Exception as e:  # noqa: BLE001  (a baseline leg must never take the product's line down)
+                eager = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         line = {
             "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -285,6 +355,8 @@ def run_ours(args):
         }
         if cpu_value is not None:
             line["cpu_baseline"] = {"value": cpu_value, "unit": "objects/s", "cores": cores, "kind": "port", "sample": sample}
+        if eager is not None:
+            line["gpu_eager_baseline"] = eager
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -295,7 +367,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline leg")
     ap.add_argument("--batch", type=int, default=64, help="objects per GPU")
     ap.add_argument("--views", type=int, default=3)
     ap.add_argument("--ref-sample", type=int, default=4, help="objects per reference-arm step (bounded CPU sample)")
@@ -304,6 +377,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         run_ours(args)
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SVX_ABI_VERSION 1
+#define SVX_ABI_VERSION 2
 
 /* activation codes for svx_gemm_desc.act */
 enum { SVX_ACT_NONE = 0, SVX_ACT_RELU = 1, SVX_ACT_LEAKY = 2, SVX_ACT_GELU = 3 };
@@ -50,6 +50,14 @@ enum {
                            SVX_EPI_DEC_TAIL: channels 0-7 = relu, channel 8 = layer5, which also goes to
                            epi_out2 + o2_base + ... + pd*c2_sd + ph*c2_sh + pw*c2_sw. */
 };
+/* svx_gemm_desc.operand_kind: element type of the MMA operands */
+enum {
+  SVX_OPERAND_DEFAULT = 0, /* fp32 storage read as TF32 (kind::tf32); SVX_A_SLAB3: fp16 operands converted in shared memory */
+  SVX_OPERAND_TF32 = 1,    /* SVX_A_SLAB3 only: keep kind::tf32 operands (full fp32 exponent range, twice the MMA instructions) */
+  SVX_OPERAND_BF16 = 2     /* A, W (and a res_via_mma residual) are bf16 in memory: kind::f16 with bf16 operands, fp32 accumulation */
+};
+/* svx_gemm_desc.io_flags: storage type of the epilogue tensors (default fp32) */
+enum { SVX_IO_OUT_BF16 = 1, SVX_IO_RES_BF16 = 2 };
 /* pooling modes */
 enum { SVX_POOL_MAX = 0, SVX_POOL_AVG = 1 };
 
@@ -85,7 +93,12 @@ enum { SVX_POOL_MAX = 0, SVX_POOL_AVG = 1 };
  *                 row = kw*16 + co, col = (kd*3 + kh)*32 + c; block_n = Npad = 48, K = Kpad = 288; cin_live =
  *                 leading channels with non-zero weights (contraction steps beyond them are skipped).
  *                 The MMA operands of this mode are fp16 (kind::f16, fp32 accumulation): the kernel converts the fp32
- *                 slabs and weights in shared memory (exact for TF32-rounded values with |x| in [6.1e-5, 65504]).
+ *                 slabs and weights in shared memory.  For the TF32-rounded values this path stores (10 mantissa bits =
+ *                 fp16's) the conversion is exact for |x| in [6.1e-5, 65504]; below that the absolute error is < 3e-8
+ *                 (fp16 subnormals), above it the value SATURATES to +-65504 and the kernel sets *range_flag (if given)
+ *                 so the caller can re-run with operand_kind = SVX_OPERAND_TF32.  BN-folded weights of any magnitude
+ *                 are handled by the host: W is pre-multiplied by a power of two that brings max|W| to [2^13, 2^14)
+ *                 and acc_scale holds its inverse (applied to the accumulator before the bias).
  * W: [Npad, Kpad] fp32, K contiguous, zero padded, values pre-rounded to TF32 (rna) by the host.
  * result = out_scale * (res_after_act ? act(acc+bias) + res : act(acc+bias+res)).
  * Output row r is stored at out + o_base + n*o_sn + od*o_sd + oh*o_sh + ow*o_sw (elements),
@@ -126,9 +139,12 @@ typedef struct svx_gemm_desc {
   int32_t res_via_mma;      /* plain mode, pre-activation residual holding TF32-exact values: add it on the tensor cores.
                                W then is [Npad, Kpad + block_n]: the extra columns of row n are one-hot at n % block_n */
   int32_t cls_cout;         /* SVX_EPI_CONVT8: output channels per parity class (1, 2, 4, 8 or a multiple of 16) */
-  int32_t reserved0;
+  float acc_scale;          /* SVX_A_SLAB3: the accumulator is multiplied by this before the bias is added (0 = 1) */
   int64_t c_sd, c_sh, c_sw;     /* SVX_EPI_CONVT8: element offsets of the class bits in out / residual */
   int64_t c2_sd, c2_sh, c2_sw;  /* ... and in epi_out2 */
+  int32_t* range_flag;      /* SVX_A_SLAB3 with fp16 operands: device int32, OR-ed with 1 when an activation saturated; or NULL */
+  int32_t operand_kind;     /* SVX_OPERAND_* */
+  int32_t io_flags;         /* SVX_IO_* bits */
 } svx_gemm_desc;
 
 /*
@@ -229,7 +245,8 @@ typedef struct svx_conv3to1_desc {
 } svx_conv3to1_desc;
 
 /* per-voxel softmax over views + weighted sum (merger.py:98-104).
- * weights, coarse: [B, V, P]; out: [B, P]. */
+ * weights, coarse: [B, V, P]; out: [B, P].  weights == NULL: the plain mean over the views, the reference's
+ * torch.mean(generated_volume, dim=1) when the merger is off or not yet enabled (core/test.py:123-126). */
 typedef struct svx_mergefuse_desc {
   const float* weights; const float* coarse; float* out;
   int32_t B, V, P;

@@ -155,12 +155,14 @@ def calibrate(mods, cfg, images):
         M.forward_pipeline(mods["encoder"], mods["decoder"], mods["merger"], mods["refiner"], images, cfg)
     for h in hooks:
         h.remove()
-    return calib
+    return calib   # modules the configuration skips (USE_MERGER / USE_REFINER off) have no entries: they keep the analytic draw
 
 
 def apply_calibration(mods, calib):
     for mk, mod in mods.items():
         for name, m in _units(mod):
+            if f"{mk}.{name}" not in calib:   # a module the configuration never runs (see calibrate)
+                continue
             scale, mean, tmean = calib[f"{mk}.{name}"]
             _rescale(m, scale, mean, tmean)
     return mods
@@ -168,9 +170,17 @@ def apply_calibration(mods, calib):
 
 def cfg_tag(cfg):
     n = cfg.NETWORK
-    return "ms{}_st{}_cva{}_r{}d{}h{}".format(int(n.USE_SWIN_T_MULTI_STAGE), "".join(map(str, n.SWIN_T_STAGES)),
-                                             int(n.USE_CROSS_VIEW_ATTENTION), n.CROSS_ATT_REDUCTION_RATIO,
-                                             n.ATT_SPATIAL_DOWNSAMPLE_RATIO, n.CROSS_ATT_NUM_HEADS)
+    tag = "ms{}_st{}_cva{}_r{}d{}h{}".format(int(n.USE_SWIN_T_MULTI_STAGE), "".join(map(str, n.SWIN_T_STAGES)),
+                                            int(n.USE_CROSS_VIEW_ATTENTION), n.CROSS_ATT_REDUCTION_RATIO,
+                                            n.ATT_SPATIAL_DOWNSAMPLE_RATIO, n.CROSS_ATT_NUM_HEADS)
+    # non-default switches that change which units exist / run (suffixes only, so the first fixtures keep their names)
+    if n.TCONV_USE_BIAS:
+        tag += "_tb1"
+    if not n.USE_MERGER:
+        tag += "_mg0"
+    if not n.USE_REFINER:
+        tag += "_rf0"
+    return tag
 
 
 def calibration_path(cfg, seed):

@@ -28,7 +28,17 @@ CONFIGS = {
     # tag: (network overrides, B, V)
     "default": (dict(), 1, 2),
     "single_stage_nocva": (dict(USE_SWIN_T_MULTI_STAGE=False, SWIN_T_STAGES=[3], USE_CROSS_VIEW_ATTENTION=False), 1, 1),
+    # every other NETWORK switch the hot path reads (config.py:83-94; encoder.py:41-85, decoder.py:24-46,
+    # core/test.py:123-130), one at a time.  These store the module outputs only (SLIM).
+    "stages_3": (dict(SWIN_T_STAGES=[3]), 1, 2),
+    "stages_23": (dict(SWIN_T_STAGES=[2, 3]), 1, 2),
+    "stages_13": (dict(SWIN_T_STAGES=[1, 3]), 1, 2),
+    "tconv_bias_ratio1": (dict(TCONV_USE_BIAS=True, ATT_SPATIAL_DOWNSAMPLE_RATIO=1), 1, 2),
+    "nocva": (dict(USE_CROSS_VIEW_ATTENTION=False), 1, 2),
+    "nomerger": (dict(USE_MERGER=False), 1, 2),
+    "norefiner": (dict(USE_REFINER=False), 1, 2),
 }
+FULL = ("default", "single_stage_nocva")   # fixtures that also carry the internal taps
 
 
 def import_reference():
@@ -67,7 +77,10 @@ def main():
     os.makedirs(FX.GOLDEN_DIR, exist_ok=True)
     ref_factory = import_reference()
     check_swin_vs_torchvision()
+    only = sys.argv[1:]
     for tag, (over, B, V) in CONFIGS.items():
+        if only and tag not in only:
+            continue
         cfg = M.default_cfg(**over)
         # calibration scalars (oracle forward), stored next to the goldens
         mods = FX.build(cfg, "analytic", 0)
@@ -82,16 +95,18 @@ def main():
             assert all(torch.equal(a[n], b[n]) for n in a)
         images = FX.structured_inputs(B, V, seed=1234)
         gt = FX.seeded_gt(B)
-        with torch.no_grad():
+        net = cfg.NETWORK
+        with torch.no_grad():   # the reference's gating, core/test.py:120-130 (epoch gates passed)
             fr = ref["encoder"](images)
             rawr, genr = ref["decoder"](fr)
-            mr = ref["merger"](rawr, genr)
-            vr = ref["refiner"](mr)
+            mr = ref["merger"](rawr, genr) if net.USE_MERGER else torch.mean(genr, dim=1)
+            vr = ref["refiner"](mr) if net.USE_REFINER else mr
             taps = {}
             fo = ora["encoder"](images, taps)
             rawo, geno = ora["decoder"](fo)
-            mo = ora["merger"](rawo, geno, taps)
-            vo = ora["refiner"](mo, taps)
+            mo = ora["merger"](rawo, geno, taps) if net.USE_MERGER else torch.mean(geno, dim=1)
+            vo = ora["refiner"](mo, taps) if net.USE_REFINER else mo
+            assert torch.equal(vo, M.forward_pipeline(ora["encoder"], ora["decoder"], ora["merger"], ora["refiner"], images, cfg))
         for name, a, b in (("encoder", fr, fo), ("raw", rawr, rawo), ("gen", genr, geno), ("merged", mr, mo), ("final", vr, vo)):
             assert torch.equal(a, b), f"{tag}: oracle {name} differs from the reference"
         counts, iou, f1 = M.voxel_metrics(vr, gt)
@@ -103,6 +118,12 @@ def main():
             union = torch.sum(torch.ge(_v.add(gt), 1)).float()
             ref_iou = 1.0 if union.item() == 0 and inter.item() == 0 else (inter / union).item() if union.item() > 0 else 0.0
             assert abs(ref_iou - iou[0, ti].item()) < 1e-7
+        if tag not in FULL:
+            np.savez_compressed(os.path.join(FX.GOLDEN_DIR, f"golden_{tag}.npz"), encoder=fr.numpy(), merged=mr.numpy(),
+                                final=vr.numpy(), gen=genr.numpy()[:, :, ::2, ::2, ::2], counts=counts.numpy(),
+                                iou=iou.numpy(), f1=f1.numpy(), B=B, V=V)
+            print(f"{tag}: reference == oracle (bit-exact); golden written; IoU {iou.tolist()}")
+            continue
         sw = taps["swin"] if isinstance(taps["swin"], list) else [taps["swin"]]
         np.savez_compressed(
             os.path.join(FX.GOLDEN_DIR, f"golden_{tag}.npz"),

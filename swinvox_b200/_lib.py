@@ -12,6 +12,8 @@ LIB_PATH = os.environ.get("SVX_LIB_PATH") or os.path.join(_HERE, "libswinvox_b20
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU = 0, 1, 2, 3
 A_PLAIN, A_GATHER, A_FLAT, A_SLAB3, A_IM2COL = 0, 1, 2, 3, 4
+OPERAND_DEFAULT, OPERAND_TF32, OPERAND_BF16 = 0, 1, 2
+IO_OUT_BF16, IO_RES_BF16 = 1, 2
 EPI_STD, EPI_DEC_TAIL, EPI_POOL8, EPI_CONVT8 = 0, 1, 2, 3
 POOL_MAX, POOL_AVG = 0, 1
 
@@ -32,8 +34,9 @@ class GemmDesc(C.Structure):
         ("round_tf32", i32), ("epi_mode", i32), ("epi_aux", ptr), ("epi_out2", ptr),
         ("o2_base", i64), ("o2_sn", i64), ("o2_sd", i64), ("o2_sh", i64), ("o2_sw", i64),
         ("cin_live", i32), ("res_via_mma", i32),
-        ("cls_cout", i32), ("reserved0", i32), ("c_sd", i64), ("c_sh", i64), ("c_sw", i64),
+        ("cls_cout", i32), ("acc_scale", f32), ("c_sd", i64), ("c_sh", i64), ("c_sw", i64),
         ("c2_sd", i64), ("c2_sh", i64), ("c2_sw", i64),
+        ("range_flag", ptr), ("operand_kind", i32), ("io_flags", i32),
     ]
 
 
@@ -223,7 +226,7 @@ def bind(path):
     for t, s in zip(DESC_TYPES, sizes):
         if C.sizeof(t) != s:
             raise SvxError(f"struct layout mismatch for {t.__name__}: python {C.sizeof(t)} bytes, library {s}")
-    if lib.svx_abi_version() != 1:
+    if lib.svx_abi_version() != 2:
         raise SvxError("ABI version mismatch")
     return lib
 

@@ -69,6 +69,8 @@ struct GemmParams {
   int i2c_lo_d, i2c_lo_h, i2c_lo_w;   // im2col mode: base-pixel coordinate of output 0 on each axis (= smallest tap)
   int i2c_narrow, ntaps;              // 4-channel pixels (image stems): eight 16-byte taps per k-chunk, unswizzled A tile
   const float* Wg;          // slab mode, fp16 operands: the fp32 weight matrix in global memory (converted once per CTA)
+  int* range_flag;          // slab mode, fp16 operands: OR-ed with 1 when an activation saturated in the conversion
+  float acc_scale;          // slab mode: accumulator scale applied before the bias (inverse of the host's weight scale)
   int flat_off[kMaxTaps];  // flat mode: row offset of each tap; im2col mode: tap offsets packed w | h << 8 | d << 16
 };
 
@@ -925,11 +927,21 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       auto swz_in = [](int r) { return ROWB == 64 ? ((r >> 1) & 3) : (r & 7); };
       auto pack8 = [](const float4& a, const float4& b) {
         uint4 o;
-        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(a.y), "f"(a.x));
-        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(a.w), "f"(a.z));
-        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(b.y), "f"(b.x));
-        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(b.w), "f"(b.z));
+        // saturating: |x| > 65504 becomes +-65504 instead of inf (and is reported through range_flag below)
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(a.y), "f"(a.x));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(a.w), "f"(a.z));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(b.y), "f"(b.x));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(b.w), "f"(b.z));
         return o;
+      };
+      // running max |x| over everything this thread converts (integer max of the sign-stripped bit patterns; NaN > inf)
+      uint32_t amax = 0u;
+      auto track = [&](const float4& a, const float4& b) {
+        const uint32_t m0 = max(max(__float_as_uint(a.x) & 0x7fffffffu, __float_as_uint(a.y) & 0x7fffffffu),
+                                max(__float_as_uint(a.z) & 0x7fffffffu, __float_as_uint(a.w) & 0x7fffffffu));
+        const uint32_t m1 = max(max(__float_as_uint(b.x) & 0x7fffffffu, __float_as_uint(b.y) & 0x7fffffffu),
+                                max(__float_as_uint(b.z) & 0x7fffffffu, __float_as_uint(b.w) & 0x7fffffffu));
+        amax = max(amax, max(m0, m1));
       };
       // weights: W[row = kw*16+co][col = tap*32 + c] fp32 -> per tap a [48 rows x kBoxCh halves] swizzled block
       for (int i = ct; i < 9 * S3_N * UOUT; i += 128) {
@@ -960,6 +972,7 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
               for (int u = 0; u < UOUT; ++u) {
                 const float4 a = *reinterpret_cast<const float4*>(srow + (((2 * u) ^ si) << 4));
                 const float4 b = *reinterpret_cast<const float4*>(srow + (((2 * u + 1) ^ si) << 4));
+                track(a, b);
                 *reinterpret_cast<uint4*>(drow + ((u ^ sw_o) << 4)) = pack8(a, b);
               }
             }
@@ -973,6 +986,7 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           }
         }
       }
+      if (p.range_flag && amax > 0x477fe000u) atomicOr(p.range_flag, 1);   // an activation beyond 65504: saturated above
     }
   } else {
     // ---- epilogue: one thread = one row u of the tile; out[u] = D0[u] + D1[u+1] + D2[u+2].  Two sets of four
@@ -988,7 +1002,7 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     float bias[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) bias[q] = p.bias ? __ldg(p.bias + q) : 0.f;
-    const float slope = p.act_param, scale = p.out_scale;
+    const float slope = p.act_param, scale = p.out_scale, acc_scale = p.acc_scale;
     const bool has_res = p.residual != nullptr;
     const bool pre = has_res && !p.res_after_act, post = has_res && p.res_after_act;
     const bool full16 = p.N == 16 && p.vec_ok;
@@ -1037,10 +1051,10 @@ conv3_slab_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         for (int c = 0; c < 4; ++c) {
           const float4 s1 = *reinterpret_cast<const float4*>(row1 + ((c ^ (r1 & 7)) << 4));
           const float4 s2 = *reinterpret_cast<const float4*>(row2 + (((c + 4) ^ (r2 & 7)) << 4));
-          x[4 * c + 0] = (__uint_as_float(d0[4 * c + 0]) + s1.x) + (s2.x + bias[4 * c + 0]);
-          x[4 * c + 1] = (__uint_as_float(d0[4 * c + 1]) + s1.y) + (s2.y + bias[4 * c + 1]);
-          x[4 * c + 2] = (__uint_as_float(d0[4 * c + 2]) + s1.z) + (s2.z + bias[4 * c + 2]);
-          x[4 * c + 3] = (__uint_as_float(d0[4 * c + 3]) + s1.w) + (s2.w + bias[4 * c + 3]);
+          x[4 * c + 0] = fmaf((__uint_as_float(d0[4 * c + 0]) + s1.x) + s2.x, acc_scale, bias[4 * c + 0]);
+          x[4 * c + 1] = fmaf((__uint_as_float(d0[4 * c + 1]) + s1.y) + s2.y, acc_scale, bias[4 * c + 1]);
+          x[4 * c + 2] = fmaf((__uint_as_float(d0[4 * c + 2]) + s1.z) + s2.z, acc_scale, bias[4 * c + 2]);
+          x[4 * c + 3] = fmaf((__uint_as_float(d0[4 * c + 3]) + s1.w) + s2.w, acc_scale, bias[4 * c + 3]);
         }
         // one buffer: it may be overwritten by this set's next tile.  Two buffers: the next tile writes the other one, and
         // nobody writes this one again before passing the next tile's barrier, i.e. after every thread finished this read
@@ -1379,8 +1393,10 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   // CTA pairs (cluster of 2, tcgen05.mma.cta_group::2) are correct (tests pass with SVX_SLAB_PAIR=1) but measured no
   // faster than single CTAs on this kernel (profiles/README.md, "merger slab kernel experiments"): opt-in only.
   g->slab_pair = g->slab && getenv("SVX_SLAB_PAIR") != nullptr;
-  g->slab_f16 = g->slab && !g->slab_pair && getenv("SVX_SLAB_TF32") == nullptr;
+  g->slab_f16 = g->slab && !g->slab_pair && d.operand_kind != SVX_OPERAND_TF32;
   p.Wg = d.W;
+  p.range_flag = g->slab_f16 ? d.range_flag : nullptr;
+  p.acc_scale = d.acc_scale != 0.f ? d.acc_scale : 1.f;
   if (encode_map(&g->map_b, d.W, (uint64_t)d.Npad, (uint64_t)w_cols, (uint64_t)w_cols,
                  g->slab_pair ? (uint32_t)(S3_N / 2) : (uint32_t)d.block_n, g->slab_narrow ? 16 : BK)) {
     delete g;

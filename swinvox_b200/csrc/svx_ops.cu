@@ -779,8 +779,18 @@ __global__ void mergefuse_kernel(const svx_mergefuse_desc d, long long total4) {
        idx += (long long)gridDim.x * blockDim.x) {
     const long long b = idx / P4;
     const int p4 = (int)(idx % P4);
-    const float4* w = reinterpret_cast<const float4*>(d.weights + b * d.V * (long long)d.P) + p4;
     const float4* c = reinterpret_cast<const float4*>(d.coarse + b * d.V * (long long)d.P) + p4;
+    if (!d.weights) {   // no merger (core/test.py:125-126): torch.mean(generated_volume, dim=1)
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int v = 0; v < d.V; ++v) {
+        const float4 g = __ldg(c + (long long)v * P4);
+        s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+      }
+      const float inv = 1.f / (float)d.V;
+      reinterpret_cast<float4*>(d.out + b * (long long)d.P)[p4] = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+      continue;
+    }
+    const float4* w = reinterpret_cast<const float4*>(d.weights + b * d.V * (long long)d.P) + p4;
     float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     for (int v = 0; v < d.V; ++v) {
       const float4 x = __ldg(w + (long long)v * P4);
@@ -1114,8 +1124,8 @@ int bilinear_launch(const svx_bilinear_desc& d, void* stream) {
 }
 
 int mergefuse_launch(const svx_mergefuse_desc& d, void* stream) {
-  SVX_REQUIRE(d.weights && d.coarse && d.out && d.B > 0 && d.V > 0 && d.P % 4 == 0, "merger_fuse: bad description");
-  SVX_REQUIRE(al16(d.weights) && al16(d.coarse) && al16(d.out), "merger_fuse: unaligned pointer");
+  SVX_REQUIRE(d.coarse && d.out && d.B > 0 && d.V > 0 && d.P % 4 == 0, "merger_fuse: bad description");
+  SVX_REQUIRE((!d.weights || al16(d.weights)) && al16(d.coarse) && al16(d.out), "merger_fuse: unaligned pointer");
   const long long total4 = (long long)d.B * (d.P / 4);
   mergefuse_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(d, total4);
   SVX_LAUNCH_OK("mergefuse_kernel");

@@ -6,6 +6,7 @@ Layout conventions: activations are fp32 channels-last buffers ``[N, D, H, W, Cs
 D=1); contraction weights are ``[Npad, Kpad]`` with k = tap*Cin + c, pre-rounded to TF32.
 """
 import ctypes as C
+import math
 import os
 from dataclasses import dataclass
 
@@ -196,10 +197,16 @@ def pack_conv3_slab(weight, bias, bn, device, n_logical=None):
     assert cout <= 16 and cin <= 32 and tuple(w.shape[2:]) == (3, 3, 3)
     W = torch.zeros(3, 16, 9, 32, dtype=torch.float32, device=w.device)       # [kw, co, (kd,kh), c]
     W[:, :cout, :, :cin] = w.permute(4, 0, 2, 3, 1).reshape(3, cout, 9, cin)
-    W = tf32_round(W.reshape(48, 288)).to(device)
+    # The kernel's MMA operands are fp16: a power-of-two scale brings the (BatchNorm-folded) weights to max|W| in
+    # [2^13, 2^14) whatever their magnitude; the kernel multiplies the accumulator by its inverse (exact) before the bias.
+    wmax = float(W.abs().max())
+    ws = 2.0 ** (13 - math.frexp(wmax)[1] + 1) if wmax > 0 and math.isfinite(wmax) else 1.0
+    W = tf32_round((W * ws).reshape(48, 288)).to(device)
     bb = torch.zeros(48, dtype=torch.float32, device=device)
     bb[:cout] = b.to(device)
-    return WeightPack(W, bb, n_logical or cout, 288, 48)   # [48, 288] is already the padded layout
+    pack = WeightPack(W, bb, n_logical or cout, 288, 48)   # [48, 288] is already the padded layout
+    pack.acc_scale = 1.0 / ws
+    return pack
 
 
 def convT_class_taps(ks, pad, par):
@@ -541,7 +548,7 @@ class Plan:
         return out
 
     def conv3_slab(self, x, pack, out, cin_live, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True,
-                   out_scale=1.0, round_out=False, name=None):
+                   out_scale=1.0, round_out=False, name=None, operands="fp16", range_flag=None):
         """Conv3d(k3, s1, p1) with <= 16 output channels over a (1,1,1) zero-bordered volume `x` (an Act whose
         channel window [c0, c0+32) is the TMA box; only the first `cin_live` channels carry weights).  `pack` comes
         from pack_conv3_slab.  `out` may live in any buffer whose Act describes the same voxel grid."""
@@ -559,6 +566,13 @@ class Plan:
         d.stride_d = d.stride_h = d.stride_w = 1
         d.ntaps = 27
         d.cin_live = cin_live
+        d.acc_scale = getattr(pack, "acc_scale", 1.0)
+        # operands: "fp16" (default: half the MMA instructions; activations beyond 65504 saturate and set range_flag) or
+        # "tf32" (fp32's exponent range)
+        assert operands in ("fp16", "tf32")
+        d.operand_kind = _lib.OPERAND_TF32 if operands == "tf32" else _lib.OPERAND_DEFAULT
+        if range_flag is not None and operands == "fp16":
+            d.range_flag = self.hold(range_flag).data_ptr()
         self._fill_epilogue(d, pack, out, None, act, act_param, residual, res_after_act, out_scale, round_out)
         self._add("gemm", d, name or "conv3_slab", 2.0 * d.M * 27 * cin_live * pack.N,
                   4.0 * d.M * (cin_live + pack.N * (2 if residual is not None else 1)))
@@ -670,10 +684,12 @@ class Plan:
         return out
 
     def merger_fuse(self, weights, coarse, out, B, V, P, name=None):
+        """weights None: the mean over the views (core/test.py:125-126)"""
         d = _lib.MergeFuseDesc()
-        d.weights, d.coarse, d.out = self.hold(weights).data_ptr(), self.hold(coarse).data_ptr(), self.hold(out).data_ptr()
+        d.weights = self.hold(weights).data_ptr() if weights is not None else None
+        d.coarse, d.out = self.hold(coarse).data_ptr(), self.hold(out).data_ptr()
         d.B, d.V, d.P = B, V, P
-        self._add("merger_fuse", d, name, 0.0, 4.0 * (2 * V + 1) * B * P)
+        self._add("merger_fuse", d, name, 0.0, 4.0 * ((2 if weights is not None else 1) * V + 1) * B * P)
         return out
 
     def voxel_metrics(self, logits, gt, thresholds, counts, B, P, name=None, bce=None):

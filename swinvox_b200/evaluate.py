@@ -45,6 +45,9 @@ class BatchedEvaluator:
             self.copy_stream = torch.cuda.Stream(self.dev)
             self.stage = [torch.empty_like(self.inbuf) for _ in range(2)]
             self.stage_gt = [torch.empty_like(self.gt) for _ in range(2)]
+            self.stage_tix_host = [torch.zeros(self.B, dtype=torch.int64).pin_memory() for _ in range(2)]
+            self.stage_tix = [torch.zeros(self.B, dtype=torch.int64, device=self.dev) for _ in range(2)]
+            self.tix = torch.zeros(self.B, dtype=torch.int64, device=self.dev)
             self.ready = [torch.cuda.Event() for _ in range(2)]
             self.consumed = [torch.cuda.Event() for _ in range(2)]
             for e in self.consumed:
@@ -57,6 +60,7 @@ class BatchedEvaluator:
                 self.out_counts = [torch.empty(T5, dtype=torch.int32).pin_memory() for _ in range(2)]
                 self.out_done = [torch.cuda.Event() for _ in range(2)]
                 self.out_n = [0, 0]
+                self.out_last = None   # out_done event of the newest D2H copy: it reads plan-owned buffers
         else:
             self.on_batch = on_batch
         self._slot = 0
@@ -84,8 +88,11 @@ class BatchedEvaluator:
         s = self._slot
         self._slot ^= 1
         if self.cuda:
+            self.consumed[s].synchronize()   # (host) the slot's pinned index buffer was read by its previous batch
+            self.stage_tix_host[s].copy_(torch.tensor(tix, dtype=torch.int64))
             with torch.cuda.stream(self.copy_stream):
                 self.consumed[s].wait(self.copy_stream)     # the compute stream has read this slot's previous batch
+                self.stage_tix[s].copy_(self.stage_tix_host[s], non_blocking=True)
                 self.stage[s][:n].copy_(images, non_blocking=True)
                 self.stage_gt[s][:n].copy_(gt, non_blocking=True)
                 if n < self.B:
@@ -101,8 +108,12 @@ class BatchedEvaluator:
         if self.cuda:
             cur = torch.cuda.current_stream(self.dev)
             self.ready[s].wait(cur)
+            if self.on_batch is not None and self.out_last is not None:
+                # the previous batch's device-to-host copies read the plan-owned logits / counters this run overwrites
+                self.out_last.wait(cur)
             self.inbuf.copy_(self.stage[s], non_blocking=True)      # device-to-device: the plans read fixed addresses
             self.gt.copy_(self.stage_gt[s], non_blocking=True)
+            self.tix.copy_(self.stage_tix[s], non_blocking=True)
             self.consumed[s].record(cur)
         else:   # the CPU twin of the tests
             self.inbuf[:n].copy_(images)
@@ -111,10 +122,13 @@ class BatchedEvaluator:
                 self.inbuf[n:] = self.inbuf[n - 1]
                 self.gt[n:] = self.gt[n - 1]
         with torch.no_grad():
-            r = self.recon
+            r = self.recon   # core/test.py:120-130, incl. the epoch gates of a loaded checkpoint
             raw, gen = r.decoder(r.encoder(self.inbuf))
-            merged = r.merger(raw, gen) if r.merger is not None else gen.mean(dim=1)
-            refined = r.refiner(merged) if r.refiner is not None else merged
+            if r.merger is not None and r._gate("EPOCH_START_USE_MERGER"):
+                merged = r.merger(raw, gen)
+            else:
+                merged = r.view_mean(gen)
+            refined = r.refiner(merged) if (r.refiner is not None and r._gate("EPOCH_START_USE_REFINER")) else merged
         counts, bce_r = self.metrics_ref.counts_and_bce(refined, self.gt)
         if refined is merged:
             bce_m = bce_r
@@ -123,13 +137,13 @@ class BatchedEvaluator:
         iou, fsc = VoxelMetrics.scores(counts)
         valid = torch.zeros(self.B, dtype=torch.float64, device=self.dev)
         valid[:n] = 1.0
-        t = torch.tensor(tix, device=self.dev)
+        t = self.tix if self.cuda else torch.tensor(tix, device=self.dev)
         self._iou.index_add_(0, t, iou.to(torch.float64) * valid[:, None])
         self._fsc.index_add_(0, t, fsc.to(torch.float64) * valid[:, None])
         self._cnt.index_add_(0, t, valid)
         self._loss += torch.stack([(bce_m * valid).sum(), (bce_r * valid).sum()]) * 10.0
         self.n_samples += n
-        self.last_logits = refined
+        self.last_logits = refined   # plan-owned: valid until the next batch runs (clone to keep)
         if self.on_batch is not None:
             if self.cuda:
                 self._deliver(s)                                   # the slot's previous occupant, if still undelivered
@@ -140,6 +154,7 @@ class BatchedEvaluator:
                     self.out_logits[s].copy_(refined, non_blocking=True)
                     self.out_counts[s].copy_(counts, non_blocking=True)
                     self.out_done[s].record(self.out_stream)
+                self.out_last = self.out_done[s]
                 self.out_n[s] = n
             else:
                 self.on_batch(refined[:n].clone(), counts[:n].clone())
@@ -160,6 +175,11 @@ class BatchedEvaluator:
         if self.on_batch is not None and self.cuda:
             for s in (self._slot, self._slot ^ 1):     # oldest first
                 self._deliver(s)
+        mer = getattr(self.recon, "merger", None)
+        if mer is not None and hasattr(mer, "saturated") and mer.saturated():
+            import warnings
+            warnings.warn("swinvox_b200: merger activations exceeded fp16's range (65504) during this evaluation; the fp16 "
+                          "tensor-core operands saturated.  The merger now uses tf32 operands: re-run the evaluation.")
         self._reduce_over_ranks()
         nt = len(self._tax_index)
         packed = torch.cat([self._iou[:nt].flatten(), self._fsc[:nt].flatten(), self._cnt[:nt], self._loss]).cpu().numpy()

@@ -387,10 +387,12 @@ def lower_decoder(plan, dec, feat, N):
 # --------------------------------------------------------------------------------------------------
 # Merger (models/merger.py:56-107)
 # --------------------------------------------------------------------------------------------------
-def lower_merger(plan, mer, raw, coarse, B, V):
+def lower_merger(plan, mer, raw, coarse, B, V, operands="fp16", range_flag=None):
     """raw: Act of 32^3 voxels inside a (1,1,1) zero border, 32-channel rows (9 live, TF32-rounded, rest zero);
     coarse: [N,32768] tensor.  Returns (merged [B, 32768], pre-softmax scores [N, 32768]).
-    All six Conv3d(k3,p1) layers run on the depth-marching TMA slab kernel over zero-bordered 34^3 volumes."""
+    All six Conv3d(k3,p1) layers run on the depth-marching TMA slab kernel over zero-bordered 34^3 volumes.
+    operands: MMA operand type of the slab kernel ("fp16": exact for this path's TF32-rounded activations up to 65504,
+    beyond that they saturate and `range_flag` (device int32[1]) is set; "tf32": fp32's range, twice the MMA instructions)."""
     dev = _dev(plan)
     N = B * V
     slope = float(mer.cfg.NETWORK.LEAKY_VALUE)
@@ -403,7 +405,8 @@ def lower_merger(plan, mer, raw, coarse, B, V):
     for i, layer in enumerate((mer.layer1, mer.layer2, mer.layer3, mer.layer4)):
         o = cat.channels(16 * i, 16)
         plan.conv3_slab(x, E.pack_conv3_slab(layer[0].weight, layer[0].bias, layer[1], dev, n_logical=16), o, 9,
-                        act=ACT_LEAKY, act_param=slope, round_out=True, name=f"merger.layer{i + 1}")
+                        act=ACT_LEAKY, act_param=slope, round_out=True, name=f"merger.layer{i + 1}", operands=operands,
+                        range_flag=range_flag)
         x = box(cat, 16 * i)
     # layer5 sees cat(w1..w4): reference channel 9*g + c lives at 16*g + c here.  Two slab passes over the two
     # 32-channel halves; the second adds the first's partial sums before bias / LeakyReLU.
@@ -416,7 +419,7 @@ def lower_merger(plan, mer, raw, coarse, B, V):
         pk = E.pack_conv3_slab(wh, b5 if half else None, None, dev, n_logical=16)
         plan.conv3_slab(box(cat, 32 * half), pk, t, 25, act=ACT_LEAKY if half else ACT_NONE, act_param=slope,
                         residual=t if half else None, res_after_act=False, round_out=False,   # layer6 reads it in fp32
-                        name=f"merger.layer5.{'ab'[half]}")
+                        name=f"merger.layer5.{'ab'[half]}", operands=operands, range_flag=range_flag)
     # layer6 (9 -> 1 channel): 243 MACs per voxel, fp32 on the CUDA cores (a tensor-core tile is issue-bound here)
     wts = plan.empty(N, 32768)
     plan.conv3_to1(box(t, 0), mer.layer6[0].weight, mer.layer6[0].bias, mer.layer6[1], wts, slope, name="merger.layer6")

@@ -4,7 +4,7 @@ reference's epsilons and its union == 0 convention) are applied to those counter
 import torch
 
 from . import engine as E
-from .models._base import require_device
+from .models import _base
 
 
 class VoxelMetrics:
@@ -21,18 +21,20 @@ class VoxelMetrics:
 
     def counts(self, logits, gt, want_bce=False):
         """logits, gt: [B,32,32,32] (or [B,P]) fp32 on the GPU -> int32 [B, T, 5] = I, U, TP, FP, FN (device)"""
-        require_device(logits)
+        _base.require_device(logits)
         B = logits.shape[0]
         P = logits[0].numel()
+        if not (logits.is_contiguous() and gt.is_contiguous()):   # reshape would silently bind the plan to a copy
+            raise ValueError("VoxelMetrics needs contiguous logits / ground truth")
+        if logits.dtype != torch.float32 or gt.dtype != torch.float32:
+            raise TypeError("VoxelMetrics needs float32 logits / ground truth")
         key = (B, P, str(logits.device), logits.data_ptr(), gt.data_ptr(), bool(want_bce))
         self._last_key = key
         if key not in self._plans:
             plan = E.Plan(logits.device)
             th = torch.tensor(self.thresholds, dtype=torch.float32, device=logits.device)
             counts = plan.zeros(B, len(self.thresholds), 5, dtype=torch.int32)
-            lg, g = logits.reshape(B, P), gt.reshape(B, P)
-            if not (lg.is_contiguous() and g.is_contiguous()):
-                raise ValueError("VoxelMetrics needs contiguous logits / ground truth")
+            lg, g = logits.view(B, P), gt.view(B, P)
             bce = plan.zeros(B, dtype=torch.int64) if want_bce else None
             plan.voxel_metrics(lg, g, th, counts, B, P, bce=bce)
             if len(self._plans) > 8:

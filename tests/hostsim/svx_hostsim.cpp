@@ -96,7 +96,10 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
     const int live = d.cin_live > 0 ? d.cin_live : 32;
     const long long HWp = (long long)d.in_H * d.in_W;
     const long long vox = (long long)d.valid_D * d.valid_H * d.valid_W;
-#pragma omp parallel for schedule(static)
+    const bool f16 = d.operand_kind != SVX_OPERAND_TF32;   // the device converts operands to fp16 (saturating)
+    const float acc_scale = d.acc_scale != 0.f ? d.acc_scale : 1.f;
+    int saturated = 0;
+#pragma omp parallel for schedule(static) reduction(| : saturated)
     for (long long r = 0; r < d.M; ++r) {
       const long long n = r / vox;
       long long t = r % vox;
@@ -114,9 +117,13 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
               const float* px = d.A + row * d.in_Cs + d.in_c0;
               const float* wr = d.W + (long long)(kw * 16 + co) * d.Kpad + (kd * 3 + kh) * 32;
               for (int c = 0; c < live; ++c)
-                if (d.in_c0 + c < d.in_Cs) acc += tf32_trunc(px[c]) * tf32_trunc(wr[c]);
+                if (d.in_c0 + c < d.in_Cs) {
+                  float a = tf32_trunc(px[c]);
+                  if (f16 && !(std::fabs(a) <= 65504.f)) { saturated = 1; a = a > 0.f ? 65504.f : -65504.f; }
+                  acc += a * tf32_trunc(wr[c]);
+                }
             }
-        float v = acc + (d.bias ? d.bias[co] : 0.f);
+        float v = acc * acc_scale + (d.bias ? d.bias[co] : 0.f);
         const float res = d.residual ? d.residual[off + co] : 0.f;
         if (d.residual && !d.res_after_act) v += res;
         v = act_fn(v, d.act, d.act_param);
@@ -125,6 +132,7 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
         d.out[off + co] = rnd(v, d.round_tf32);
       }
     }
+    if (f16 && saturated && d.range_flag) *d.range_flag |= 1;
     return 0;
   }
   const long long rows_per_n = (long long)d.out_D * d.out_H * d.out_W;
@@ -544,6 +552,12 @@ int conv3to1_launch(const svx_conv3to1_desc& d, void*) {
 int mergefuse_launch(const svx_mergefuse_desc& d, void*) {
   for (long long b = 0; b < d.B; ++b)
     for (int p = 0; p < d.P; ++p) {
+      if (!d.weights) {
+        float s = 0.f;
+        for (int v = 0; v < d.V; ++v) s += d.coarse[(b * d.V + v) * (long long)d.P + p];
+        d.out[b * d.P + p] = s * (1.f / (float)d.V);
+        continue;
+      }
       float mx = -INFINITY;
       for (int v = 0; v < d.V; ++v) mx = std::max(mx, d.weights[(b * d.V + v) * (long long)d.P + p]);
       float den = 0.f, num = 0.f;

@@ -42,7 +42,6 @@ def _use_hostsim():
     import swinvox_b200.metrics as metrics
     _lib._lib = _lib.bind(os.path.join(ROOT, "tests", "hostsim", "libsvx_hostsim.so"))
     _base.require_device = lambda t: None
-    metrics.require_device = lambda t: None
 
 
 def _worker(rank, world, port, out_dir):
@@ -74,7 +73,7 @@ def test_gloo_world2_matches_single_process(hostsim, tmp_path):
     from swinvox_b200 import _lib
     from swinvox_b200.models import _base
     import swinvox_b200.metrics as metrics
-    saved = (_lib._lib, _base.require_device, metrics.require_device)
+    saved = (_lib._lib, _base.require_device)
     _use_hostsim()
     try:
         cfg = M.default_cfg(**CFG_OVER)
@@ -86,7 +85,7 @@ def test_gloo_world2_matches_single_process(hostsim, tmp_path):
         assert torch.allclose(r0[0], logits, rtol=0, atol=1e-6)
         assert torch.equal(r0[1], counts)
     finally:
-        _lib._lib, _base.require_device, metrics.require_device = saved
+        _lib._lib, _base.require_device = saved
 
 
 def _eval_worker(rank, world, port, out_dir):

@@ -24,6 +24,9 @@ class FakeRecon:
     def input_buffer(self, B, V):
         return torch.zeros(B, V, 3, 224, 224, device=self.device)
 
+    def _gate(self, key):
+        return True
+
 
 def make_data(n, V, seed):
     g = torch.Generator().manual_seed(seed)
@@ -36,10 +39,7 @@ def make_data(n, V, seed):
 
 
 def test_batched_driver_matches_reference_loop(dev, monkeypatch):
-    import swinvox_b200.metrics as metrics
     from swinvox_b200.evaluate import BatchedEvaluator
-    if dev == "cpu":
-        monkeypatch.setattr(metrics, "require_device", lambda t: None)
     cfg = M.default_cfg()
     th = cfg.TEST.VOXEL_THRESH
     n, V, B = 7, 2, 3

@@ -255,6 +255,49 @@ def test_conv3d_padded_channels(dev):
     assert got[:, 9:].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("case", ["huge_weights", "tiny_weights", "tiny_activations", "huge_activations_tf32",
+                                  "saturating_fp16"])
+def test_conv3d_slab_operand_range(dev, case):
+    """The slab kernel's MMA operands are fp16 (5 exponent bits).  BatchNorm-folded weights of any magnitude are handled
+    by the host's power-of-two weight scale; activations are exact in [6.1e-5, 65504], lose only absolute accuracy
+    (< 3e-8) below, and SATURATE above -- reported through range_flag, after which the caller re-runs with tf32 operands
+    (Merger.saturated does this)."""
+    DEV = dev
+    torch.manual_seed(5)
+    n, cin, D, H, W = 2, 9, 4, 6, 8
+    xs = {"tiny_activations": 1e-3, "huge_activations_tf32": 3e5, "saturating_fp16": 3e5}.get(case, 1.0)
+    x = E.tf32_round(torch.randn(n, cin, D, H, W) * xs)
+    conv = torch.nn.Conv3d(cin, 9, 3, padding=1)
+    bn = rand_bn(torch.nn.BatchNorm3d(9))
+    with torch.no_grad():
+        if case == "huge_weights":     # BN with a tiny running variance: folded weights ~1e6
+            bn.running_var.fill_(1e-12)
+            bn.eps = 1e-13
+        if case == "tiny_weights":
+            conv.weight.mul_(1e-9)
+    operands = "tf32" if case == "huge_activations_tf32" else "fp16"
+    p = E.Plan(DEV)
+    src = p.new_act(n, D, H, W, 32, pad=(1, 1, 1))
+    src.view()[..., :cin].copy_(x.permute(0, 2, 3, 4, 1))
+    dst = p.new_act(n, D, H, W, 16, pad=(1, 1, 1))
+    flag = p.zeros(1, dtype=torch.int32)
+    pk = E.pack_conv3_slab(conv.weight, conv.bias, bn, DEV, n_logical=16)
+    assert 2.0 ** 13 <= pk.W.abs().max().item() < 2.0 ** 14   # whatever the folded magnitude
+    p.conv3_slab(E.Act(src.buf, n, D + 2, H + 2, W + 2, 32, 0, (1, 1, 1)), pk, dst, cin, operands=operands, range_flag=flag)
+    p.run()
+    sync(DEV)
+    wf, bf = E.fold_bn(conv.weight, conv.bias, bn)
+    ws = pk.acc_scale
+    ref = F.conv3d(x.double(), (E.tf32_round(wf / ws) * ws).double(), bf.double(), padding=1)
+    got = dst.view().permute(0, 4, 1, 2, 3).cpu()[:, :9]
+    if case == "saturating_fp16":
+        assert flag.item() == 1                       # loud, not silent
+        assert torch.isfinite(got).all()              # saturated, never inf / nan
+    else:
+        assert flag.item() == 0
+        assert rel_err(got, ref) < (2e-4 if case == "tiny_activations" else 1e-4)
+
+
 @pytest.mark.parametrize("dims,c0,residual", [((6, 7, 9), 16, False), ((5, 32, 32), 0, False), ((4, 6, 8), 32, True),
                                                ((3, 32, 32), 48, True), ((32, 32, 32), 16, False)])
 def test_conv3d_slab_merger_style(dev, dims, c0, residual):

@@ -8,35 +8,50 @@ import torch
 from oracle import fixtures as FX
 from oracle import modules as M
 from swinvox_b200.models import CrossViewAttention, Decoder, Encoder, Merger, Refiner, SwinTransformer
-from util import RTOL_DEEP, RTOL_INTERNAL, dev, golden, stage_check, sync, voxel_check  # noqa: F401
+from util import RTOL_DEEP, RTOL_INTERNAL, dev, golden, parity_log, stage_check, sync, voxel_check  # noqa: F401
 
 PRODUCT = dict(encoder=Encoder, decoder=Decoder, merger=Merger, refiner=Refiner)
-CFGS = {
+CFGS = {   # the fixtures of oracle/make_golden.py: every NETWORK switch the hot path reads (config.py:83-94)
     "default": (dict(), 1, 2),
     "single_stage_nocva": (dict(USE_SWIN_T_MULTI_STAGE=False, SWIN_T_STAGES=[3], USE_CROSS_VIEW_ATTENTION=False), 1, 1),
+    "stages_3": (dict(SWIN_T_STAGES=[3]), 1, 2),
+    "stages_23": (dict(SWIN_T_STAGES=[2, 3]), 1, 2),
+    "stages_13": (dict(SWIN_T_STAGES=[1, 3]), 1, 2),
+    "tconv_bias_ratio1": (dict(TCONV_USE_BIAS=True, ATT_SPATIAL_DOWNSAMPLE_RATIO=1), 1, 2),
+    "nocva": (dict(USE_CROSS_VIEW_ATTENTION=False), 1, 2),
+    "nomerger": (dict(USE_MERGER=False), 1, 2),
+    "norefiner": (dict(USE_REFINER=False), 1, 2),
 }
+# the CPU tier (hostsim) lowers every configuration but runs the numeric comparison on a subset to stay within minutes
+HOSTSIM_TAGS = ("default", "single_stage_nocva", "stages_13", "tconv_bias_ratio1", "nomerger")
 
 
 def nchw(act):
     return act.view().squeeze(1).permute(0, 3, 1, 2)
 
 
-def oracle_forward(mods, images):
+def oracle_forward(mods, images, cfg=None):
+    """core/test.py:120-130 on the oracle modules, keeping every stage output"""
+    net = (cfg or M.default_cfg()).NETWORK
     taps = {}
     with torch.no_grad():
         f = mods["encoder"](images, taps)
         raw, gen = mods["decoder"](f)
-        m = mods["merger"](raw, gen, taps)
-        v = mods["refiner"](m, taps)
+        m = mods["merger"](raw, gen, taps) if net.USE_MERGER else gen.mean(1)
+        v = mods["refiner"](m, taps) if net.USE_REFINER else m
     taps.update(encoder=f, raw=raw, gen=gen, merged=m, final=v)
     return taps
 
 
 @pytest.mark.parametrize("tag", list(CFGS))
 def test_pipeline_parity_with_oracle_and_reference_golden(dev, tag):
+    if dev == "cpu" and tag not in HOSTSIM_TAGS:
+        pytest.skip("numeric comparison of this configuration runs in the gpu tier")
+    from swinvox_b200.pipeline import ViewMean
     over, B, V = CFGS[tag]
     cfg = M.default_cfg(**over)
-    ref = oracle_forward(FX.build(cfg, "calibrated", 0), FX.structured_inputs(B, V, seed=1234))
+    net = cfg.NETWORK
+    ref = oracle_forward(FX.build(cfg, "calibrated", 0), FX.structured_inputs(B, V, seed=1234), cfg)
     prod = FX.build(cfg, "calibrated", 0, PRODUCT)
     for m in prod.values():
         m.to(dev)
@@ -44,8 +59,8 @@ def test_pipeline_parity_with_oracle_and_reference_golden(dev, tag):
     with torch.no_grad():  # the reference's calling sequence, core/test.py:120-130
         f = prod["encoder"](images)
         raw, gen = prod["decoder"](f)
-        merged = prod["merger"](raw, gen)
-        final = prod["refiner"](merged)
+        merged = prod["merger"](raw, gen) if net.USE_MERGER else ViewMean()(gen)
+        final = prod["refiner"](merged) if net.USE_REFINER else merged
     sync(dev)
     plan = next(iter(prod["encoder"]._plans.values()))[0]
     reports = [stage_check("resnet branch", nchw(plan.taps["resnet"]), ref["resnet"], RTOL_DEEP)]
@@ -56,7 +71,8 @@ def test_pipeline_parity_with_oracle_and_reference_golden(dev, tag):
     reports.append(stage_check("encoder", f, ref["encoder"], RTOL_DEEP))
     reports.append(stage_check("decoder.raw", raw, ref["raw"]))
     reports.append(stage_check("decoder.gen", gen, ref["gen"]))
-    reports.append(stage_check("merger.weights", prod["merger"].last_volume_weights, ref["merger_weights"], RTOL_INTERNAL))
+    if net.USE_MERGER:
+        reports.append(stage_check("merger.weights", prod["merger"].last_volume_weights, ref["merger_weights"], RTOL_INTERNAL))
     reports.append(stage_check("merger", merged, ref["merged"]))
     reports.append(stage_check("refiner", final, ref["final"]))
     # ... and against what the unmodified reference produced in the build container
@@ -67,6 +83,7 @@ def test_pipeline_parity_with_oracle_and_reference_golden(dev, tag):
     vox = voxel_check(final, torch.from_numpy(g["final"]), FX.seeded_gt(B))
     print("\n".join(reports))
     print("voxels (th, mismatch, out-of-band mismatch, dIoU):", vox)
+    parity_log(f"{tag} [{dev}] B={B} V={V}", reports, vox)
 
 
 def test_modules_accept_foreign_tensors(dev):
@@ -95,6 +112,28 @@ def test_modules_accept_foreign_tensors(dev):
         cva.eval().to(dev)
         stage_check("cross_view_attention", cva(ref["pre_cva"].to(dev)), ref["post_cva"], RTOL_DEEP)
     sync(dev)
+
+
+def test_merger_fp16_range_fallback(dev):
+    """activations beyond fp16's range: the merger reports the saturation and switches itself to tf32 operands"""
+    cfg = M.default_cfg()
+    ora = FX.build(cfg, "calibrated", 0)["merger"]
+    g = torch.Generator().manual_seed(3)
+    raw = torch.randn(1, 2, 9, 32, 32, 32, generator=g) * 2e5
+    gen = torch.randn(1, 2, 32, 32, 32, generator=g)
+    with torch.no_grad():
+        taps = {}
+        ora(raw, gen, taps)   # compare the pre-softmax scores: at this magnitude the softmax is an arg-max
+        mer = Merger(cfg)
+        mer.load_state_dict(ora.state_dict())
+        mer.eval().to(dev)
+        mer(raw.to(dev), gen.to(dev))
+        sync(dev)
+        assert mer.saturated() and mer.slab_operands == "tf32"
+        mer(raw.to(dev), gen.to(dev))
+        sync(dev)
+        assert not mer.saturated()
+    stage_check("merger scores (tf32 operands, |x| ~ 2e5)", mer.last_volume_weights, taps["merger_weights"], RTOL_INTERNAL)
 
 
 def test_swin_wrapper_outputs(dev):

@@ -66,6 +66,19 @@ def voxel_check(got_logits, ref_logits, gt, thresholds=(0.2, 0.3, 0.4, 0.5)):
     return out
 
 
+def parity_log(title, reports, voxels=None):
+    """SVX_PARITY_LOG=<file>: append the per-stage numbers of a parity test (the table committed under profiles/)"""
+    path = os.environ.get("SVX_PARITY_LOG")
+    if not path:
+        return
+    with open(path, "a") as fh:
+        fh.write(f"## {title}\n")
+        for r in reports:
+            fh.write(f"  {r}\n")
+        for th, total, oob, d_iou in voxels or []:
+            fh.write(f"  voxels th={th}: mismatch={total:.2e} out_of_band={oob:.2e} dIoU={d_iou:.2e}\n")
+
+
 def golden(tag):
     return np.load(os.path.join(GOLDEN, f"golden_{tag}.npz"))
 
