@@ -10,8 +10,9 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
  *     (PyTorch).  The library allocates nothing persistent besides the plan object itself.
- *   - all activations are fp32, channels-last ([N,H,W,C] / [N,D,H,W,C]); contractions run on
- *     tcgen05 kind::tf32 with fp32 accumulation in TMEM.
+ *   - activations are channels-last ([N,H,W,C] / [N,D,H,W,C]), fp32 by default: contractions then run on tcgen05
+ *     kind::tf32 with fp32 accumulation in TMEM.  The encoder can alternatively be lowered with bf16 activation
+ *     storage (SVX_OPERAND_BF16 / SVX_DT_* flags): kind::f16 with bf16 operands, fp32 accumulation and statistics.
  *   - every function returns 0 on success, non-zero on failure; svx_last_error() returns a
  *     thread-local message.  No exceptions cross the ABI.
  *   - launches are stream ordered on the cudaStream_t passed as `void* stream`.
@@ -58,6 +59,9 @@ enum {
 };
 /* svx_gemm_desc.io_flags: storage type of the epilogue tensors (default fp32) */
 enum { SVX_IO_OUT_BF16 = 1, SVX_IO_RES_BF16 = 2 };
+/* `dtype` field of the non-contraction descriptors: storage type of the activation tensors (default: fp32 in, fp32 out).
+ * Arithmetic (statistics, softmax, accumulation) is fp32 either way; gamma / beta / bias / relative-position tables stay fp32. */
+enum { SVX_DT_IN_BF16 = 1, SVX_DT_OUT_BF16 = 2, SVX_DT_BF16 = 3 };
 /* pooling modes */
 enum { SVX_POOL_MAX = 0, SVX_POOL_AVG = 1 };
 
@@ -190,6 +194,7 @@ typedef struct svx_pool_desc {
   int32_t N, C, D, H, W, in_Cs, out_Cs;
   int32_t KD, KH, KW, SD, SH, SW, PD, PH, PW, OD, OH, OW;
   int32_t mode, round_tf32;
+  int32_t dtype;            /* SVX_DT_* bits */
 } svx_pool_desc;
 
 /* Row LayerNorm over C channels (timm norm1/norm2/patch_embed.norm/downsample.norm), eps 1e-5.
@@ -198,6 +203,7 @@ typedef struct svx_pool_desc {
 typedef struct svx_lnrows_desc {
   const float* in; float* out; const float* gamma; const float* beta;
   int32_t rows, C; int32_t merge, H, W; float eps; int32_t round_tf32;
+  int32_t dtype;            /* SVX_DT_* bits */
 } svx_lnrows_desc;
 
 /* nn.LayerNorm([C,H,W]) of the Swin wrapper (swin_transformer.py:64-67,84-86): statistics over
@@ -205,6 +211,7 @@ typedef struct svx_lnrows_desc {
 typedef struct svx_lnsample_desc {
   const float* in; float* out; const float* gamma; const float* beta;
   int32_t N, L; float eps; int32_t round_tf32;
+  int32_t dtype;            /* SVX_DT_* bits */
 } svx_lnsample_desc;
 
 /* W-MSA / SW-MSA (timm WindowAttention + roll/partition/reverse).  qkv is [N*H*W, 3C] in token
@@ -213,12 +220,14 @@ typedef struct svx_lnsample_desc {
 typedef struct svx_winattn_desc {
   const float* qkv; float* out; const float* bias;
   int32_t N, H, W, C, heads, shift; float scale; int32_t round_tf32;
+  int32_t dtype;            /* SVX_DT_* bits */
 } svx_winattn_desc;
 
 /* depthwise k=s conv without padding (cross_view_attention.py:26-34), channels-last */
 typedef struct svx_dwconv_desc {
   const float* in; float* out; const float* w /* [k*k, C] */; const float* bias;
   int32_t N, H, W, C, k, OH, OW; int32_t round_tf32;
+  int32_t dtype;            /* SVX_DT_* bits */
 } svx_dwconv_desc;
 
 /* attention over the view axis (cross_view_attention.py:81-103). qkv: [B*V, P, 3*R] channels-last
@@ -226,12 +235,14 @@ typedef struct svx_dwconv_desc {
 typedef struct svx_viewattn_desc {
   const float* qkv; float* out;
   int32_t B, V, P, R, heads; float scale; int32_t round_tf32;
+  int32_t dtype;            /* SVX_DT_* bits */
 } svx_viewattn_desc;
 
 /* out = bilinear_resize(in, align_corners=False) + skip  (cross_view_attention.py:110-120) */
 typedef struct svx_bilinear_desc {
   const float* in; const float* skip; float* out;
   int32_t N, IH, IW, OH, OW, C; int32_t round_tf32;
+  int32_t dtype;            /* SVX_DT_* bits */
 } svx_bilinear_desc;
 
 /* Conv3d(Cin <= 12 -> 1, k3, s1, p1) + folded BatchNorm + LeakyReLU on the CUDA cores in fp32 (merger.py:50-54, layer6:
@@ -272,7 +283,9 @@ typedef struct svx_metrics_desc {
 typedef struct svx_transpose_desc {
   const float* in; float* out;
   int32_t N, C, P, Cs; int32_t to_channels_last; int32_t round_tf32;
-  int32_t row_w, row_pitch, row_x0, reserved0;
+  int32_t row_w, row_pitch, row_x0;
+  int32_t dtype;            /* SVX_DT_* bits (the planar side is always fp32: only SVX_DT_OUT_BF16 with to_channels_last,
+                               SVX_DT_IN_BF16 without) */
 } svx_transpose_desc;
 
 /* binvox run-length decode (utils/binvox_rw.py:119-153 read_as_3d_array; utils/data_loaders.py:84-87): the payload

@@ -14,6 +14,7 @@ ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU = 0, 1, 2, 3
 A_PLAIN, A_GATHER, A_FLAT, A_SLAB3, A_IM2COL = 0, 1, 2, 3, 4
 OPERAND_DEFAULT, OPERAND_TF32, OPERAND_BF16 = 0, 1, 2
 IO_OUT_BF16, IO_RES_BF16 = 1, 2
+DT_IN_BF16, DT_OUT_BF16, DT_BF16 = 1, 2, 3
 EPI_STD, EPI_DEC_TAIL, EPI_POOL8, EPI_CONVT8 = 0, 1, 2, 3
 POOL_MAX, POOL_AVG = 0, 1
 
@@ -56,21 +57,21 @@ class PoolDesc(C.Structure):
         ("N", i32), ("C", i32), ("D", i32), ("H", i32), ("W", i32), ("in_Cs", i32), ("out_Cs", i32),
         ("KD", i32), ("KH", i32), ("KW", i32), ("SD", i32), ("SH", i32), ("SW", i32),
         ("PD", i32), ("PH", i32), ("PW", i32), ("OD", i32), ("OH", i32), ("OW", i32),
-        ("mode", i32), ("round_tf32", i32),
+        ("mode", i32), ("round_tf32", i32), ("dtype", i32),
     ]
 
 
 class LnRowsDesc(C.Structure):
     _fields_ = [
         ("inp", ptr), ("out", ptr), ("gamma", ptr), ("beta", ptr),
-        ("rows", i32), ("C", i32), ("merge", i32), ("H", i32), ("W", i32), ("eps", f32), ("round_tf32", i32),
+        ("rows", i32), ("C", i32), ("merge", i32), ("H", i32), ("W", i32), ("eps", f32), ("round_tf32", i32), ("dtype", i32),
     ]
 
 
 class LnSampleDesc(C.Structure):
     _fields_ = [
         ("inp", ptr), ("out", ptr), ("gamma", ptr), ("beta", ptr),
-        ("N", i32), ("L", i32), ("eps", f32), ("round_tf32", i32),
+        ("N", i32), ("L", i32), ("eps", f32), ("round_tf32", i32), ("dtype", i32),
     ]
 
 
@@ -78,28 +79,28 @@ class WinAttnDesc(C.Structure):
     _fields_ = [
         ("qkv", ptr), ("out", ptr), ("bias", ptr),
         ("N", i32), ("H", i32), ("W", i32), ("C", i32), ("heads", i32), ("shift", i32), ("scale", f32),
-        ("round_tf32", i32),
+        ("round_tf32", i32), ("dtype", i32),
     ]
 
 
 class DwConvDesc(C.Structure):
     _fields_ = [
         ("inp", ptr), ("out", ptr), ("w", ptr), ("bias", ptr),
-        ("N", i32), ("H", i32), ("W", i32), ("C", i32), ("k", i32), ("OH", i32), ("OW", i32), ("round_tf32", i32),
+        ("N", i32), ("H", i32), ("W", i32), ("C", i32), ("k", i32), ("OH", i32), ("OW", i32), ("round_tf32", i32), ("dtype", i32),
     ]
 
 
 class ViewAttnDesc(C.Structure):
     _fields_ = [
         ("qkv", ptr), ("out", ptr),
-        ("B", i32), ("V", i32), ("P", i32), ("R", i32), ("heads", i32), ("scale", f32), ("round_tf32", i32),
+        ("B", i32), ("V", i32), ("P", i32), ("R", i32), ("heads", i32), ("scale", f32), ("round_tf32", i32), ("dtype", i32),
     ]
 
 
 class BilinearDesc(C.Structure):
     _fields_ = [
         ("inp", ptr), ("skip", ptr), ("out", ptr),
-        ("N", i32), ("IH", i32), ("IW", i32), ("OH", i32), ("OW", i32), ("C", i32), ("round_tf32", i32),
+        ("N", i32), ("IH", i32), ("IW", i32), ("OH", i32), ("OW", i32), ("C", i32), ("round_tf32", i32), ("dtype", i32),
     ]
 
 
@@ -118,7 +119,7 @@ class TransposeDesc(C.Structure):
     _fields_ = [
         ("inp", ptr), ("out", ptr),
         ("N", i32), ("C", i32), ("P", i32), ("Cs", i32), ("to_channels_last", i32), ("round_tf32", i32),
-        ("row_w", i32), ("row_pitch", i32), ("row_x0", i32), ("reserved0", i32),
+        ("row_w", i32), ("row_pitch", i32), ("row_x0", i32), ("dtype", i32),
     ]
 
 

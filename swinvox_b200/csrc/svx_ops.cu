@@ -129,7 +129,10 @@ __global__ void __launch_bounds__(256) im2col_line_kernel(const svx_im2col_desc 
 }
 
 // ---- pooling ------------------------------------------------------------------------------------
+template <typename T>
 __global__ void pool_kernel(const svx_pool_desc d, long long total) {
+  const T* in = reinterpret_cast<const T*>(d.in);
+  T* out = reinterpret_cast<T*>(d.out);
   const int c4n = d.C >> 2;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -151,8 +154,7 @@ __global__ void pool_kernel(const svx_pool_desc d, long long total) {
         for (int kw = 0; kw < d.KW; ++kw) {
           const int iw = ow * d.SW - d.PW + kw;
           if ((unsigned)iw >= (unsigned)d.W) continue;
-          const float4 v = __ldg(reinterpret_cast<const float4*>(
-              d.in + (((n * d.D + id) * d.H + ih) * d.W + iw) * (long long)d.in_Cs + c4 * 4));
+          const float4 v = ld4g(in + (((n * d.D + id) * d.H + ih) * d.W + iw) * (long long)d.in_Cs + c4 * 4);
           if (d.mode == SVX_POOL_MAX) {
             acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y);
             acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
@@ -169,14 +171,17 @@ __global__ void pool_kernel(const svx_pool_desc d, long long total) {
     }
     acc.x = maybe_round(acc.x, d.round_tf32); acc.y = maybe_round(acc.y, d.round_tf32);
     acc.z = maybe_round(acc.z, d.round_tf32); acc.w = maybe_round(acc.w, d.round_tf32);
-    *reinterpret_cast<float4*>(d.out + (((n * d.OD + od) * d.OH + oh) * d.OW + ow) * (long long)d.out_Cs + c4 * 4) = acc;
+    st4(out + (((n * d.OD + od) * d.OH + oh) * d.OW + ow) * (long long)d.out_Cs + c4 * 4, acc);
   }
 }
 
 // ---- MaxPool2d(3, stride 2, pad 1), channels-last (the ResNet stem's pool): a thread marches down the output rows of one
 // (column, 4-channel group); per output row it reads two NEW input rows (3 float4 each, horizontal max first) and reuses
 // the horizontal max of the row shared with the previous output row: 6 loads per output instead of 9.
+template <typename T>
 __global__ void __launch_bounds__(256) maxpool3s2_kernel(const svx_pool_desc d, int cols_per_block) {
+  const T* in = reinterpret_cast<const T*>(d.in);
+  T* out = reinterpret_cast<T*>(d.out);
   const int c4n = d.C >> 2;
   const int c4 = threadIdx.x % c4n;
   const int ow = blockIdx.x * cols_per_block + threadIdx.x / c4n;
@@ -185,13 +190,13 @@ __global__ void __launch_bounds__(256) maxpool3s2_kernel(const svx_pool_desc d, 
   const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
   auto hmax = [&](int ih) -> float4 {
     if ((unsigned)ih >= (unsigned)d.H) return ninf;
-    const float* row = d.in + ((n * d.H + ih) * (long long)d.W) * d.in_Cs + c4 * 4;
+    const T* row = in + ((n * d.H + ih) * (long long)d.W) * d.in_Cs + c4 * 4;
     float4 m = ninf;
 #pragma unroll
     for (int k = -1; k <= 1; ++k) {
       const int iw = 2 * ow + k;
       if ((unsigned)iw < (unsigned)d.W) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(row + (long long)iw * d.in_Cs));
+        const float4 v = ld4g(row + (long long)iw * d.in_Cs);
         m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
       }
     }
@@ -203,13 +208,16 @@ __global__ void __launch_bounds__(256) maxpool3s2_kernel(const svx_pool_desc d, 
     float4 o;
     o.x = maybe_round(fmaxf(prev.x, fmaxf(a.x, b.x)), d.round_tf32); o.y = maybe_round(fmaxf(prev.y, fmaxf(a.y, b.y)), d.round_tf32);
     o.z = maybe_round(fmaxf(prev.z, fmaxf(a.z, b.z)), d.round_tf32); o.w = maybe_round(fmaxf(prev.w, fmaxf(a.w, b.w)), d.round_tf32);
-    *reinterpret_cast<float4*>(d.out + ((n * d.OH + oh) * (long long)d.OW + ow) * d.out_Cs + c4 * 4) = o;
+    st4(out + ((n * d.OH + oh) * (long long)d.OW + ow) * d.out_Cs + c4 * 4, o);
     prev = b;
   }
 }
 
 // ---- row LayerNorm: one warp per row ---------------------------------------------------------------
+template <typename T>
 __global__ void lnrows_kernel(const svx_lnrows_desc d) {
+  const T* in = reinterpret_cast<const T*>(d.in);
+  T* out = reinterpret_cast<T*>(d.out);
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int C = d.C;
@@ -217,7 +225,7 @@ __global__ void lnrows_kernel(const svx_lnrows_desc d) {
   const float invC = 1.f / (float)C;
   for (long long row = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); row < d.rows;
        row += (long long)gridDim.x * wpb) {
-    const float* src[4];
+    const T* src[4];
     if (d.merge) {
       const int W2 = d.W >> 1, H2 = d.H >> 1;
       const int x = (int)(row % W2);
@@ -227,18 +235,18 @@ __global__ void lnrows_kernel(const svx_lnrows_desc d) {
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
         const int dy = s & 1, dx = s >> 1;  // timm order: (h0,w0) (h1,w0) (h0,w1) (h1,w1)
-        src[s] = d.in + ((n * d.H + 2 * y + dy) * d.W + 2 * x + dx) * (long long)Cq;
+        src[s] = in + ((n * d.H + 2 * y + dy) * d.W + 2 * x + dx) * (long long)Cq;
       }
     } else {
-      src[0] = d.in + row * (long long)C;
+      src[0] = in + row * (long long)C;
       src[1] = src[2] = src[3] = src[0];
     }
     auto load4 = [&](int c) -> float4 {
       if (d.merge) {
         const int s = c / Cq;
-        return __ldg(reinterpret_cast<const float4*>(src[s] + (c - s * Cq)));
+        return ld4g(src[s] + (c - s * Cq));
       }
-      return __ldg(reinterpret_cast<const float4*>(src[0] + c));
+      return ld4g(src[0] + c);
     };
     float sum = 0.f;
     for (int c = lane * 4; c < C; c += 128) {
@@ -253,7 +261,7 @@ __global__ void lnrows_kernel(const svx_lnrows_desc d) {
       sq += (a * a + b * b) + (e * e + f * f);
     }
     const float rstd = rsqrtf(warp_sum(sq) * invC + d.eps);
-    float* dst = d.out + row * (long long)C;
+    T* dst = out + row * (long long)C;
     for (int c = lane * 4; c < C; c += 128) {
       const float4 v = load4(c);
       const float4 g = __ldg(reinterpret_cast<const float4*>(d.gamma + c));
@@ -263,7 +271,7 @@ __global__ void lnrows_kernel(const svx_lnrows_desc d) {
       o.y = maybe_round((v.y - mean) * rstd * g.y + b.y, d.round_tf32);
       o.z = maybe_round((v.z - mean) * rstd * g.z + b.z, d.round_tf32);
       o.w = maybe_round((v.w - mean) * rstd * g.w + b.w, d.round_tf32);
-      *reinterpret_cast<float4*>(dst + c) = o;
+      st4(dst + c, o);
     }
   }
 }
@@ -271,8 +279,10 @@ __global__ void lnrows_kernel(const svx_lnrows_desc d) {
 // ---- row LayerNorm, register-resident: one warp normalises R rows at a time, each row read from HBM exactly once
 // (NV float4 per lane) so R*NV independent 16-byte loads are in flight per lane; statistics are the exact two-pass
 // mean / variance computed from the registers.
-template <int NV, int R>
+template <int NV, int R, typename T>
 __global__ void __launch_bounds__(256) lnrows_reg_kernel(const svx_lnrows_desc d) {
+  const T* in = reinterpret_cast<const T*>(d.in);
+  T* out = reinterpret_cast<T*>(d.out);
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int C = d.C;
@@ -307,15 +317,15 @@ __global__ void __launch_bounds__(256) lnrows_reg_kernel(const svx_lnrows_desc d
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = lane * 4 + i * 128;
-        const float* src;
+        const T* src;
         if (d.merge) {
           const int sidx = c / Cq;
           const int dy = sidx & 1, dx = sidx >> 1;  // timm order: (h0,w0) (h1,w0) (h0,w1) (h1,w1)
-          src = d.in + ((n * d.H + 2 * y + dy) * d.W + 2 * x + dx) * (long long)Cq + (c - sidx * Cq);
+          src = in + ((n * d.H + 2 * y + dy) * d.W + 2 * x + dx) * (long long)Cq + (c - sidx * Cq);
         } else {
-          src = d.in + base + c;
+          src = in + base + c;
         }
-        v[r][i] = (rok && c < C) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[r][i] = (rok && c < C) ? ld4g(src) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 #pragma unroll
@@ -335,7 +345,7 @@ __global__ void __launch_bounds__(256) lnrows_reg_kernel(const svx_lnrows_desc d
       }
       const float rstd = rsqrtf(warp_sum(sq) * invC + d.eps);
       if (row < d.rows) {
-        float* dst = d.out + row * (long long)C;
+        T* dst = out + row * (long long)C;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           const int c = lane * 4 + i * 128;
@@ -351,7 +361,7 @@ __global__ void __launch_bounds__(256) lnrows_reg_kernel(const svx_lnrows_desc d
             o.y = maybe_round((v[r][i].y - mean) * rstd * g.y + b.y, d.round_tf32);
             o.z = maybe_round((v[r][i].z - mean) * rstd * g.z + b.z, d.round_tf32);
             o.w = maybe_round((v[r][i].w - mean) * rstd * g.w + b.w, d.round_tf32);
-            *reinterpret_cast<float4*>(dst + c) = o;
+            st4(dst + c, o);
           }
         }
       }
@@ -360,30 +370,31 @@ __global__ void __launch_bounds__(256) lnrows_reg_kernel(const svx_lnrows_desc d
 }
 
 // ---- whole-sample LayerNorm: one CTA per sample ----------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(1024) lnsample_kernel(const svx_lnsample_desc d) {
   __shared__ float red[32];
   const long long L = d.L;
   const int L4 = d.L >> 2;
   for (int n = blockIdx.x; n < d.N; n += gridDim.x) {
-    const float4* x = reinterpret_cast<const float4*>(d.in + n * L);
+    const T* x = reinterpret_cast<const T*>(d.in) + n * L;
     float sum = 0.f;
     for (int i = threadIdx.x; i < L4; i += blockDim.x) {
-      const float4 v = x[i];
+      const float4 v = ld4(x + 4 * i);
       sum += (v.x + v.y) + (v.z + v.w);
     }
     const float mean = block_sum(sum, red) / (float)L;
     float sq = 0.f;
     for (int i = threadIdx.x; i < L4; i += blockDim.x) {
-      const float4 v = x[i];
+      const float4 v = ld4(x + 4 * i);
       const float a = v.x - mean, b = v.y - mean, e = v.z - mean, f = v.w - mean;
       sq += (a * a + b * b) + (e * e + f * f);
     }
     const float rstd = rsqrtf(block_sum(sq, red) / (float)L + d.eps);
-    float4* y = reinterpret_cast<float4*>(d.out + n * L);
+    T* y = reinterpret_cast<T*>(d.out) + n * L;
     const float4* g4 = reinterpret_cast<const float4*>(d.gamma);
     const float4* b4 = reinterpret_cast<const float4*>(d.beta);
     for (int i = threadIdx.x; i < L4; i += blockDim.x) {
-      const float4 v = x[i];
+      const float4 v = ld4(x + 4 * i);
       const float4 g = __ldg(g4 + i);
       const float4 b = __ldg(b4 + i);
       float4 o;
@@ -391,7 +402,7 @@ __global__ void __launch_bounds__(1024) lnsample_kernel(const svx_lnsample_desc 
       o.y = maybe_round((v.y - mean) * rstd * g.y + b.y, d.round_tf32);
       o.z = maybe_round((v.z - mean) * rstd * g.z + b.z, d.round_tf32);
       o.w = maybe_round((v.w - mean) * rstd * g.w + b.w, d.round_tf32);
-      y[i] = o;
+      st4(y + 4 * i, o);
     }
   }
 }
@@ -410,7 +421,7 @@ __device__ __forceinline__ float dsmem_read(const float* local, unsigned rank) {
 __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-template <int NV>
+template <int NV, typename T>
 __global__ void __launch_bounds__(1024, 1) lnsample_cluster_kernel(const svx_lnsample_desc d) {
   __shared__ float red[32];
   __shared__ float part[2];
@@ -419,14 +430,14 @@ __global__ void __launch_bounds__(1024, 1) lnsample_cluster_kernel(const svx_lns
   const int n = blockIdx.x / kLnCluster;   // grid = N clusters (exactly one sample each)
   const long long L = d.L;
   const int L4 = d.L >> 2;
-  const float4* x = reinterpret_cast<const float4*>(d.in + n * L);
+  const T* x = reinterpret_cast<const T*>(d.in) + n * L;
   const int t0 = rank * 1024 + threadIdx.x, stride = kLnCluster * 1024;
   float4 v[NV];
   float sum = 0.f;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int i = t0 + k * stride;
-    v[k] = i < L4 ? __ldg(x + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[k] = i < L4 ? ld4g(x + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
     sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
   }
   sum = block_sum(sum, red);
@@ -451,7 +462,7 @@ __global__ void __launch_bounds__(1024, 1) lnsample_cluster_kernel(const svx_lns
 #pragma unroll
   for (unsigned r = 0; r < kLnCluster; ++r) tsq += dsmem_read(&part[1], r);
   const float rstd = rsqrtf(tsq / (float)L + d.eps);
-  float4* y = reinterpret_cast<float4*>(d.out + n * L);
+  T* y = reinterpret_cast<T*>(d.out) + n * L;
   const float4* g4 = reinterpret_cast<const float4*>(d.gamma);
   const float4* b4 = reinterpret_cast<const float4*>(d.beta);
 #pragma unroll
@@ -464,7 +475,7 @@ __global__ void __launch_bounds__(1024, 1) lnsample_cluster_kernel(const svx_lns
       o.y = maybe_round((v[k].y - mean) * rstd * g.y + b.y, d.round_tf32);
       o.z = maybe_round((v[k].z - mean) * rstd * g.z + b.z, d.round_tf32);
       o.w = maybe_round((v[k].w - mean) * rstd * g.w + b.w, d.round_tf32);
-      y[i] = o;
+      st4(y + 4 * i, o);
     }
   }
   cluster_barrier();   // nobody leaves while a peer may still read its partials
@@ -675,7 +686,10 @@ __global__ void __launch_bounds__(WA_ITEMS * 64, 2) winattn_kernel(const svx_win
 }
 
 // ---- depthwise k=s conv, channels-last ---------------------------------------------------------------
+template <typename T>
 __global__ void dwconv_kernel(const svx_dwconv_desc d, long long total) {
+  const T* in = reinterpret_cast<const T*>(d.in);
+  T* out = reinterpret_cast<T*>(d.out);
   const int c4n = d.C >> 2;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -687,20 +701,20 @@ __global__ void dwconv_kernel(const svx_dwconv_desc d, long long total) {
     float4 acc = d.bias ? __ldg(reinterpret_cast<const float4*>(d.bias + c4 * 4)) : make_float4(0, 0, 0, 0);
     for (int ky = 0; ky < d.k; ++ky)
       for (int kx = 0; kx < d.k; ++kx) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(
-            d.in + ((n * d.H + oy * d.k + ky) * d.W + ox * d.k + kx) * (long long)d.C + c4 * 4));
+        const float4 v = ld4g(in + ((n * d.H + oy * d.k + ky) * d.W + ox * d.k + kx) * (long long)d.C + c4 * 4);
         const float4 wv = __ldg(reinterpret_cast<const float4*>(d.w + (ky * d.k + kx) * d.C + c4 * 4));
         acc.x = fmaf(v.x, wv.x, acc.x); acc.y = fmaf(v.y, wv.y, acc.y);
         acc.z = fmaf(v.z, wv.z, acc.z); acc.w = fmaf(v.w, wv.w, acc.w);
       }
     acc.x = maybe_round(acc.x, d.round_tf32); acc.y = maybe_round(acc.y, d.round_tf32);
     acc.z = maybe_round(acc.z, d.round_tf32); acc.w = maybe_round(acc.w, d.round_tf32);
-    *reinterpret_cast<float4*>(d.out + ((n * d.OH + oy) * d.OW + ox) * (long long)d.C + c4 * 4) = acc;
+    st4(out + ((n * d.OH + oy) * d.OW + ox) * (long long)d.C + c4 * 4, acc);
   }
 }
 
 // ---- attention over the view axis: one CTA per (object, head) ----------------------------------------
 constexpr int kMaxViews = 32;
+template <typename T>
 __global__ void __launch_bounds__(256) viewattn_kernel(const svx_viewattn_desc d) {
   __shared__ float sc[kMaxViews * kMaxViews];
   const int head = blockIdx.x % d.heads;
@@ -708,15 +722,16 @@ __global__ void __launch_bounds__(256) viewattn_kernel(const svx_viewattn_desc d
   const int V = d.V, P = d.P, R = d.R, hd = R / d.heads;
   const int R3 = 3 * R;
   const int L = P * hd;  // dot-product length
-  const float* base = d.qkv + b * V * (long long)P * R3;
+  const T* base = reinterpret_cast<const T*>(d.qkv) + b * V * (long long)P * R3;
+  T* out = reinterpret_cast<T*>(d.out);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int pair = warp; pair < V * V; pair += nw) {
     const int v1 = pair / V, v2 = pair % V;
     float acc = 0.f;
     for (int e = lane; e < L; e += 32) {
       const int pos = e / hd, dd = e % hd;
-      const float qv = base[((long long)v1 * P + pos) * R3 + head * hd + dd];
-      const float kv = base[((long long)v2 * P + pos) * R3 + R + head * hd + dd];
+      const float qv = ld1(base + ((long long)v1 * P + pos) * R3 + head * hd + dd);
+      const float kv = ld1(base + ((long long)v2 * P + pos) * R3 + R + head * hd + dd);
       acc = fmaf(qv, kv, acc);
     }
     acc = warp_sum(acc);
@@ -736,13 +751,17 @@ __global__ void __launch_bounds__(256) viewattn_kernel(const svx_viewattn_desc d
     const int pos = e / hd, dd = e % hd;
     float acc = 0.f;
     for (int v2 = 0; v2 < V; ++v2)
-      acc = fmaf(sc[v1 * kMaxViews + v2], base[((long long)v2 * P + pos) * R3 + 2 * R + head * hd + dd], acc);
-    d.out[((b * V + v1) * P + pos) * (long long)R + head * hd + dd] = maybe_round(acc, d.round_tf32);
+      acc = fmaf(sc[v1 * kMaxViews + v2], ld1(base + ((long long)v2 * P + pos) * R3 + 2 * R + head * hd + dd), acc);
+    st1(out + ((b * V + v1) * P + pos) * (long long)R + head * hd + dd, maybe_round(acc, d.round_tf32));
   }
 }
 
 // ---- bilinear resize (align_corners=False) + skip ------------------------------------------------------
+template <typename T>
 __global__ void bilinear_kernel(const svx_bilinear_desc d, long long total) {
+  const T* in = reinterpret_cast<const T*>(d.in);
+  const T* skip = reinterpret_cast<const T*>(d.skip);
+  T* out = reinterpret_cast<T*>(d.out);
   const int c4n = d.C >> 2;
   const float sy = (float)d.IH / (float)d.OH, sx = (float)d.IW / (float)d.OW;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -757,18 +776,18 @@ __global__ void bilinear_kernel(const svx_bilinear_desc d, long long total) {
     const int y1 = min(y0 + 1, d.IH - 1), x1 = min(x0 + 1, d.IW - 1);
     const float ly = fy - (float)y0, lx = fx - (float)x0;
     auto at = [&](int y, int x) {
-      return __ldg(reinterpret_cast<const float4*>(d.in + ((n * d.IH + y) * d.IW + x) * (long long)d.C + c4 * 4));
+      return ld4g(in + ((n * d.IH + y) * d.IW + x) * (long long)d.C + c4 * 4);
     };
     const float4 a = at(y0, x0), b = at(y0, x1), c = at(y1, x0), e = at(y1, x1);
     const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
     const long long o = ((n * d.OH + oy) * d.OW + ox) * (long long)d.C + c4 * 4;
-    const float4 s = d.skip ? __ldg(reinterpret_cast<const float4*>(d.skip + o)) : make_float4(0, 0, 0, 0);
+    const float4 s = skip ? ld4g(skip + o) : make_float4(0, 0, 0, 0);
     float4 v;
     v.x = maybe_round(w00 * a.x + w01 * b.x + w10 * c.x + w11 * e.x + s.x, d.round_tf32);
     v.y = maybe_round(w00 * a.y + w01 * b.y + w10 * c.y + w11 * e.y + s.y, d.round_tf32);
     v.z = maybe_round(w00 * a.z + w01 * b.z + w10 * c.z + w11 * e.z + s.z, d.round_tf32);
     v.w = maybe_round(w00 * a.w + w01 * b.w + w10 * c.w + w11 * e.w + s.w, d.round_tf32);
-    *reinterpret_cast<float4*>(d.out + o) = v;
+    st4(out + o, v);
   }
 }
 
@@ -936,6 +955,7 @@ __global__ void __launch_bounds__(256) metrics_kernel(const svx_metrics_desc d, 
 }
 
 // ---- [N,C,P] <-> [N,P,Cs] ------------------------------------------------------------------------------
+template <typename TCL>   // storage type of the channels-last side; the planar side is fp32
 __global__ void transpose_kernel(const svx_transpose_desc d) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
@@ -948,16 +968,16 @@ __global__ void transpose_kernel(const svx_transpose_desc d) {
       tile[i][tx] = (c < d.C && p < d.P) ? src[(long long)c * d.P + p] : 0.f;
     }
     __syncthreads();
-    float* dst = d.out + (long long)n * d.P * d.Cs;
+    TCL* dst = reinterpret_cast<TCL*>(d.out) + (long long)n * d.P * d.Cs;
     for (int i = ty; i < 32; i += 8) {
       const int p = p0 + i, c = c0 + tx;
-      if (p < d.P && c < d.Cs) dst[(long long)p * d.Cs + c] = c < d.C ? maybe_round(tile[tx][i], d.round_tf32) : 0.f;
+      if (p < d.P && c < d.Cs) st1(dst + (long long)p * d.Cs + c, c < d.C ? maybe_round(tile[tx][i], d.round_tf32) : 0.f);
     }
   } else {
-    const float* src = d.in + (long long)n * d.P * d.Cs;
+    const TCL* src = reinterpret_cast<const TCL*>(d.in) + (long long)n * d.P * d.Cs;
     for (int i = ty; i < 32; i += 8) {
       const int p = p0 + i, c = c0 + tx;
-      tile[i][tx] = (p < d.P && c < d.C) ? src[(long long)p * d.Cs + c] : 0.f;
+      tile[i][tx] = (p < d.P && c < d.C) ? ld1(src + (long long)p * d.Cs + c) : 0.f;
     }
     __syncthreads();
     float* dst = d.out + (long long)n * d.C * d.P;
@@ -969,6 +989,7 @@ __global__ void transpose_kernel(const svx_transpose_desc d) {
 }
 
 // planar [N, C<=4, P] -> [N, P, 4] (image staging: NCHW fp32 -> NHWC with a zero fourth channel); one thread = one pixel
+template <typename TO>
 __global__ void interleave4_kernel(const svx_transpose_desc d, long long total) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -984,7 +1005,7 @@ __global__ void interleave4_kernel(const svx_transpose_desc d, long long total) 
       const int y = p / d.row_w, x = p - y * d.row_w;
       o = n * (long long)(d.P / d.row_w) * d.row_pitch + (long long)y * d.row_pitch + d.row_x0 + x;
     }
-    reinterpret_cast<float4*>(d.out)[o] = make_float4(v[0], v[1], v[2], v[3]);
+    st4(reinterpret_cast<TO*>(d.out) + 4 * o, make_float4(v[0], v[1], v[2], v[3]));
   }
 }
 
@@ -1009,17 +1030,20 @@ int im2col_launch(const svx_im2col_desc& d, void* stream) {
 int pool_launch(const svx_pool_desc& d, void* stream) {
   SVX_REQUIRE(d.in && d.out && d.C % 4 == 0 && d.in_Cs % 4 == 0 && d.out_Cs % 4 == 0 && al16(d.in) && al16(d.out),
               "pool: channels must be multiples of 4 and pointers 16-byte aligned");
+  SVX_REQUIRE(d.dtype == 0 || d.dtype == SVX_DT_BF16, "pool: input and output share one storage type");
   const long long total = (long long)d.N * d.OD * d.OH * d.OW * (d.C / 4);
   if (d.mode == SVX_POOL_MAX && d.D == 1 && d.OD == 1 && d.KD == 1 && d.KH == 3 && d.KW == 3 && d.SH == 2 && d.SW == 2 &&
       d.PD == 0 && d.PH == 1 && d.PW == 1 && d.C / 4 <= 256 && 256 % (d.C / 4) == 0 && d.N <= 65535 &&
       d.OH == (d.H - 1) / 2 + 1 && d.OW == (d.W - 1) / 2 + 1) {
     const int cols = 256 / (d.C / 4);
     dim3 grid((d.OW + cols - 1) / cols, d.N);
-    maxpool3s2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, cols);
+    if (d.dtype == SVX_DT_BF16) maxpool3s2_kernel<bf16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(d, cols);
+    else maxpool3s2_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(d, cols);
     SVX_LAUNCH_OK("maxpool3s2_kernel");
     return 0;
   }
-  pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
+  if (d.dtype == SVX_DT_BF16) pool_kernel<bf16_t><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
+  else pool_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
   SVX_LAUNCH_OK("pool_kernel");
   return 0;
 }
@@ -1029,22 +1053,33 @@ int lnrows_launch(const svx_lnrows_desc& d, void* stream) {
   SVX_REQUIRE(d.C % 4 == 0 && (!d.merge || (d.C % 16 == 0 && d.H % 2 == 0 && d.W % 2 == 0)),
               "layernorm_rows: C=%d unsupported", d.C);
   SVX_REQUIRE(al16(d.in) && al16(d.out) && al16(d.gamma) && al16(d.beta), "layernorm_rows: unaligned pointer");
+  SVX_REQUIRE(d.dtype != SVX_DT_BF16 || (d.C % 8 == 0 && (!d.merge || d.C % 32 == 0)), "layernorm_rows: bf16 rows need C %% 8 == 0");
   const int wpb = 8;
   const int nv = (d.C + 127) / 128;
   cudaStream_t st = (cudaStream_t)stream;
   auto grid = [&](int r) { return grid_for((d.rows + r - 1) / r, wpb, kSmCount * 8); };
-  if (nv == 1) lnrows_reg_kernel<1, 4><<<grid(4), wpb * 32, 0, st>>>(d);
-  else if (nv == 2) lnrows_reg_kernel<2, 4><<<grid(4), wpb * 32, 0, st>>>(d);
-  else if (nv == 3) lnrows_reg_kernel<3, 2><<<grid(2), wpb * 32, 0, st>>>(d);
-  else if (nv <= 6) lnrows_reg_kernel<6, 1><<<grid(1), wpb * 32, 0, st>>>(d);
-  else if (nv <= 12) lnrows_reg_kernel<12, 1><<<grid(1), wpb * 32, 0, st>>>(d);
-  else lnrows_kernel<<<grid_for(d.rows, wpb), wpb * 32, 0, st>>>(d);
+  SVX_REQUIRE(d.dtype == 0 || d.dtype == SVX_DT_BF16, "layernorm_rows: input and output share one storage type");
+  if (d.dtype == SVX_DT_BF16) {
+    if (nv == 1) lnrows_reg_kernel<1, 4, bf16_t><<<grid(4), wpb * 32, 0, st>>>(d);
+    else if (nv == 2) lnrows_reg_kernel<2, 4, bf16_t><<<grid(4), wpb * 32, 0, st>>>(d);
+    else if (nv == 3) lnrows_reg_kernel<3, 2, bf16_t><<<grid(2), wpb * 32, 0, st>>>(d);
+    else if (nv <= 6) lnrows_reg_kernel<6, 1, bf16_t><<<grid(1), wpb * 32, 0, st>>>(d);
+    else if (nv <= 12) lnrows_reg_kernel<12, 1, bf16_t><<<grid(1), wpb * 32, 0, st>>>(d);
+    else lnrows_kernel<bf16_t><<<grid_for(d.rows, wpb), wpb * 32, 0, st>>>(d);
+  } else if (nv == 1) lnrows_reg_kernel<1, 4, float><<<grid(4), wpb * 32, 0, st>>>(d);
+  else if (nv == 2) lnrows_reg_kernel<2, 4, float><<<grid(4), wpb * 32, 0, st>>>(d);
+  else if (nv == 3) lnrows_reg_kernel<3, 2, float><<<grid(2), wpb * 32, 0, st>>>(d);
+  else if (nv <= 6) lnrows_reg_kernel<6, 1, float><<<grid(1), wpb * 32, 0, st>>>(d);
+  else if (nv <= 12) lnrows_reg_kernel<12, 1, float><<<grid(1), wpb * 32, 0, st>>>(d);
+  else lnrows_kernel<float><<<grid_for(d.rows, wpb), wpb * 32, 0, st>>>(d);
   SVX_LAUNCH_OK("lnrows_kernel");
   return 0;
 }
 
 int lnsample_launch(const svx_lnsample_desc& d, void* stream) {
   SVX_REQUIRE(d.in && d.out && d.gamma && d.beta && d.N > 0 && d.L > 0 && d.L % 4 == 0, "layernorm_sample: bad description");
+  SVX_REQUIRE(d.dtype == 0 || d.dtype == SVX_DT_BF16, "layernorm_sample: input and output share one storage type");
+  const bool bf = d.dtype == SVX_DT_BF16;
   const int nv = ((d.L >> 2) + kLnCluster * 1024 - 1) / (kLnCluster * 1024);
   // measured (192 samples): 56x56x96: 0.162 ms vs 0.210 ms for the single-CTA kernel; 28x28x192: 0.114 vs 0.097;
   // 14x14x384: 0.093 vs 0.045 -> the cluster kernel only pays for the large samples (SVX_LN_CLUSTER=1 forces it)
@@ -1061,14 +1096,20 @@ int lnsample_launch(const svx_lnsample_desc& d, void* stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e;
-    if (nv <= 2) e = cudaLaunchKernelEx(&cfg, lnsample_cluster_kernel<2>, d);
-    else if (nv <= 3) e = cudaLaunchKernelEx(&cfg, lnsample_cluster_kernel<3>, d);
-    else if (nv <= 5) e = cudaLaunchKernelEx(&cfg, lnsample_cluster_kernel<5>, d);
-    else e = cudaLaunchKernelEx(&cfg, lnsample_cluster_kernel<10>, d);
+    if (bf) {
+      if (nv <= 2) e = cudaLaunchKernelEx(&cfg, lnsample_cluster_kernel<2, bf16_t>, d);
+      else if (nv <= 3) e = cudaLaunchKernelEx(&cfg, lnsample_cluster_kernel<3, bf16_t>, d);
+      else if (nv <= 5) e = cudaLaunchKernelEx(&cfg, lnsample_cluster_kernel<5, bf16_t>, d);
+      else e = cudaLaunchKernelEx(&cfg, lnsample_cluster_kernel<10, bf16_t>, d);
+    } else if (nv <= 2) e = cudaLaunchKernelEx(&cfg, lnsample_cluster_kernel<2, float>, d);
+    else if (nv <= 3) e = cudaLaunchKernelEx(&cfg, lnsample_cluster_kernel<3, float>, d);
+    else if (nv <= 5) e = cudaLaunchKernelEx(&cfg, lnsample_cluster_kernel<5, float>, d);
+    else e = cudaLaunchKernelEx(&cfg, lnsample_cluster_kernel<10, float>, d);
     if (e != cudaSuccess) return fail("cluster launch of lnsample_cluster_kernel failed: %s", cudaGetErrorString(e));
     return 0;
   }
-  lnsample_kernel<<<d.N, 1024, 0, (cudaStream_t)stream>>>(d);
+  if (bf) lnsample_kernel<bf16_t><<<d.N, 1024, 0, (cudaStream_t)stream>>>(d);
+  else lnsample_kernel<float><<<d.N, 1024, 0, (cudaStream_t)stream>>>(d);
   SVX_LAUNCH_OK("lnsample_kernel");
   return 0;
 }
@@ -1102,7 +1143,9 @@ int winattn_launch(const svx_winattn_desc& d, void* stream) {
 int dwconv_launch(const svx_dwconv_desc& d, void* stream) {
   SVX_REQUIRE(d.in && d.out && d.w && d.C % 4 == 0 && d.k >= 1, "dwconv: bad description");
   const long long total = (long long)d.N * d.OH * d.OW * (d.C / 4);
-  dwconv_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
+  SVX_REQUIRE(d.dtype == 0 || d.dtype == SVX_DT_BF16, "dwconv: input and output share one storage type");
+  if (d.dtype == SVX_DT_BF16) dwconv_kernel<bf16_t><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
+  else dwconv_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
   SVX_LAUNCH_OK("dwconv_kernel");
   return 0;
 }
@@ -1110,7 +1153,9 @@ int dwconv_launch(const svx_dwconv_desc& d, void* stream) {
 int viewattn_launch(const svx_viewattn_desc& d, void* stream) {
   SVX_REQUIRE(d.qkv && d.out && d.V >= 1 && d.V <= kMaxViews && d.R % d.heads == 0,
               "view_attention: supports 1..%d views (V=%d)", kMaxViews, d.V);
-  viewattn_kernel<<<d.B * d.heads, 256, 0, (cudaStream_t)stream>>>(d);
+  SVX_REQUIRE(d.dtype == 0 || d.dtype == SVX_DT_BF16, "view_attention: input and output share one storage type");
+  if (d.dtype == SVX_DT_BF16) viewattn_kernel<bf16_t><<<d.B * d.heads, 256, 0, (cudaStream_t)stream>>>(d);
+  else viewattn_kernel<float><<<d.B * d.heads, 256, 0, (cudaStream_t)stream>>>(d);
   SVX_LAUNCH_OK("viewattn_kernel");
   return 0;
 }
@@ -1118,7 +1163,9 @@ int viewattn_launch(const svx_viewattn_desc& d, void* stream) {
 int bilinear_launch(const svx_bilinear_desc& d, void* stream) {
   SVX_REQUIRE(d.in && d.out && d.C % 4 == 0, "bilinear_add: bad description");
   const long long total = (long long)d.N * d.OH * d.OW * (d.C / 4);
-  bilinear_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
+  SVX_REQUIRE(d.dtype == 0 || d.dtype == SVX_DT_BF16, "bilinear_add: tensors share one storage type");
+  if (d.dtype == SVX_DT_BF16) bilinear_kernel<bf16_t><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
+  else bilinear_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
   SVX_LAUNCH_OK("bilinear_kernel");
   return 0;
 }
@@ -1170,14 +1217,18 @@ int transpose_launch(const svx_transpose_desc& d, void* stream) {
               "transpose: padded rows need the 4-channel channels-last form");
   if (d.to_channels_last && d.Cs == 4 && d.C <= 4 && al16(d.out)) {
     const long long total = (long long)d.N * d.P;
-    interleave4_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
+    if (d.dtype == SVX_DT_OUT_BF16) interleave4_kernel<bf16_t><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
+    else interleave4_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
     SVX_LAUNCH_OK("interleave4_kernel");
     return 0;
   }
   SVX_REQUIRE(d.N <= 65535, "transpose: N too large");
   const int cext = d.to_channels_last ? d.Cs : d.C;
   dim3 grid((d.P + 31) / 32, (cext + 31) / 32, d.N);
-  transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(d);
+  const int want = d.to_channels_last ? SVX_DT_OUT_BF16 : SVX_DT_IN_BF16;
+  SVX_REQUIRE(d.dtype == 0 || d.dtype == want, "transpose: only the channels-last side may be bf16");
+  if (d.dtype) transpose_kernel<bf16_t><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(d);
+  else transpose_kernel<float><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(d);
   SVX_LAUNCH_OK("transpose_kernel");
   return 0;
 }

@@ -102,7 +102,8 @@ def test_full_size_oracle_parity_gpu():
     rec.set_graph(True)
     for _ in range(2):   # second call = CUDA-graph replay of the cached plans
         logits, counts = rec.evaluate(images.cuda(), gt.cuda())
-    f = rec.encoder(images.cuda()).clone()
+    with torch.no_grad():
+        f = rec.encoder(images.cuda()).clone()
     torch.cuda.synchronize()
     reports = [stage_check("encoder B64xV3", f, enc, RTOL_DEEP), stage_check("logits B64xV3", logits, ref, RTOL)]
     vox = voxel_check(logits, ref, gt)

@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round-2 evidence run on the GPU box:  gpurun --timeout 1500 -- 'bash tools/gpu_round2.sh r2_vNN [quick]'
+set -x
+tag=${1:-r2_vXX}
+mode=${2:-full}
+rm -f gpurun_out/parity_$tag.txt
+SVX_PARITY_LOG=gpurun_out/parity_$tag.txt timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -25 > gpurun_out/gpu_tests_$tag.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_$tag.log 2>&1
+timeout 600 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
+cp gpurun_out/op_breakdown.json gpurun_out/op_breakdown_$tag.json
+if [ "$mode" = "full" ]; then
+  timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_${tag}_reference.json 2> gpurun_out/bench_${tag}_reference.err
+  timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 4400 --csv \
+      --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 3 --no-eager > gpurun_out/ncu_launch_$tag.log 2>&1
+fi
+tail -3 gpurun_out/gpu_tests_$tag.log; tail -2 gpurun_out/smoke_$tag.log; cut -c1-400 gpurun_out/bench_$tag.json
