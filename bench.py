@@ -27,6 +27,7 @@ METRIC = "objects/sec, 3 views 224^2 -> 32^3"
 GF_PER_VIEW, GF_PER_OBJECT = 19.382, 2.485
 GF_ATTENTION_PER_VIEW = 0.280 + 0.0561   # window-attention bmm + CVA: run outside the contraction kernel
 GF_MERGER_PER_VIEW = 1.1625              # merger convolutions: conv3_slab_kernel, not the dominant kernel
+GF_ENCODER_PER_VIEW = 17.833             # encoder total per view (the part that runs in bf16 with --dtype bf16)
 TF32_CUBLAS_MEASURED = 712.5             # torch.matmul fp32/TF32 8192^3 on this pool (profiles/r1_gemm_bench_v6.log)
 
 
@@ -207,7 +208,9 @@ def run_ours(args):
     B, V = args.batch, args.views
     cfg = svx_config.make_cfg()
     torch.manual_seed(0)
-    rec = Reconstructor(cfg, device=dev, zero_copy=True)   # random-init weights of the reference architecture
+    bf16 = args.dtype == "bf16"
+    # random-init weights of the reference architecture; --dtype bf16: the encoder stores / multiplies in bf16
+    rec = Reconstructor(cfg, device=dev, zero_copy=True, dtype=args.dtype)
     rec.set_graph(not args.no_graph)
     dp = DataParallelReconstructor(rec)
     images_h, gt_h = synthetic_batch(B, V, 100 + rank)
@@ -280,10 +283,11 @@ def run_ours(args):
     d2h_bytes = B * 32768 * 4 + B * len(cfg.TEST.VOXEL_THRESH) * 5 * 4
 
     # ---- roofline of the dominant kernel (the tcgen05 contraction kernel), measured live with CUDA events -------
-    gemm_ms, slab_ms, mlp_ms, mlp_gf, total_ms, gemm_bytes, breakdown = 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, []
+    gemm_ms, slab_ms, mlp_ms, mlp_gf, total_ms, gemm_bytes, breakdown, n_gemm, other_gemm_ms = 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, [], 0, 0.0
     for mod in rec.modules():
         for entry in mod._plans.values():
             plan = entry[0]
+            plan_bf16 = plan.dtype == torch.bfloat16
             times = plan.time_ops(iters=3)
             for nm, t, fl, nb in zip(plan.op_names, times, plan.flops, plan.bytes):
                 total_ms += t
@@ -293,12 +297,19 @@ def run_ours(args):
                     mlp_ms += t
                     mlp_gf += fl / 1e9
                 elif fl > 0 and not nm.endswith(".attn"):
-                    gemm_ms += t
-                    gemm_bytes += nb
-                breakdown.append((nm, t, fl, nb))
+                    if plan_bf16 == bf16:       # the dominant kernel: gemm_bf16_kernel (encoder) with --dtype bf16, else gemm_tf32_kernel
+                        gemm_ms += t
+                        gemm_bytes += nb
+                        n_gemm += 1
+                    else:
+                        other_gemm_ms += t
+                breakdown.append((nm, t, fl, nb, plan_bf16))
     # dominant kernel = gemm_tf32_kernel (every Linear / Conv2d / Conv3d k4 / ConvTranspose3d).  Algorithmic FLOPs per
     # step = SURVEY 8(d) figure of the reference forward minus what other kernels execute (attention, merger convs).
-    algo_gf = B * ((GF_PER_VIEW - GF_ATTENTION_PER_VIEW - GF_MERGER_PER_VIEW) * V + GF_PER_OBJECT) - mlp_gf
+    if bf16:   # gemm_bf16_kernel executes the encoder's contractions (everything but window attention / CVA's view attention)
+        algo_gf = B * V * (GF_ENCODER_PER_VIEW - GF_ATTENTION_PER_VIEW)
+    else:
+        algo_gf = B * ((GF_PER_VIEW - GF_ATTENTION_PER_VIEW - GF_MERGER_PER_VIEW) * V + GF_PER_OBJECT) - mlp_gf
     achieved = algo_gf / gemm_ms if gemm_ms > 0 else 0.0   # GFLOP / ms = TFLOP/s
     peaks = {}
     try:
@@ -306,32 +317,34 @@ def run_ours(args):
     except Exception:  # noqa: BLE001
         pass
     bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak = bf16_peak / 2.0   # kind::tf32 runs at half the bf16 rate; MEASURED_PEAKS.json has no tf32 entry
-    n_gemm = sum(1 for nm, t, fl, nb in breakdown
-                 if fl > 0 and not nm.endswith((".attn", ".mlp")) and not nm.startswith("merger.layer"))
+    tf32_peak = bf16_peak / 2.0   # kind::tf32 runs at half the bf16 rate; MEASURED_PEAKS.json has no tf32 entry
+    peak = bf16_peak if bf16 else tf32_peak
     hbm = peaks.get("hbm_gbs", 6550.7)
     # per-op roofline floor: every op is bounded by max(algorithmic FLOP / tensor peak, algorithmic bytes / HBM peak)
-    floor_ms = sum(max(fl / (peak * 1e9), nb / (hbm * 1e6)) for nm, t, fl, nb in breakdown)
+    floor_ms = sum(max(fl / ((bf16_peak if pb else tf32_peak) * 1e9), nb / (hbm * 1e6)) for nm, t, fl, nb, pb in breakdown)
     traffic = None   # DRAM bytes per launch of the dominant kernel from the committed ncu launch list of this command
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["gemm_tf32_kernel"]["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[
+            "gemm_bf16_kernel" if bf16 else "gemm_tf32_kernel"]["dram_bytes_per_launch"]
     except Exception:  # noqa: BLE001
         pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "gemm_tf32_kernel", "launches_per_step": n_gemm,
+                "traffic": traffic, "kernel": "gemm_bf16_kernel" if bf16 else "gemm_tf32_kernel", "launches_per_step": n_gemm,
                 "algorithmic_bytes_per_launch": gemm_bytes / max(n_gemm, 1),
                 "step_floor_ms": floor_ms, "step_frac_of_floor": floor_ms / total_ms if total_ms > 0 else None,
                 "kernel_ms_per_step": gemm_ms, "all_kernels_ms_per_step": total_ms,
                 "algorithmic_gflop_per_step": algo_gf, "conv3_slab_ms_per_step": slab_ms,
                 "mlp_fused_ms_per_step": mlp_ms, "mlp_fused_tflops": (mlp_gf / mlp_ms if mlp_ms > 0 else None),
                 "tf32_cublas_tflops_measured": TF32_CUBLAS_MEASURED,
-                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32), of measured" if peaks
-                                else "fallback 1.4 PFLOP/s sustained bf16 / 2 (tf32), of fallback")}
+                "other_gemm_ms_per_step": other_gemm_ms,
+                "peak_source": (("MEASURED_PEAKS.json bf16_tflops_sustained" if bf16 else
+                                 "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32)") + ", of measured" if peaks
+                                else "fallback 1.4 PFLOP/s sustained bf16" + ("" if bf16 else " / 2 (tf32)") + ", of fallback")}
 
     if rank == 0:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "op_breakdown.json"), "w") as fh:
-            json.dump(sorted(breakdown, key=lambda r: -r[1]), fh)
+            json.dump(sorted([list(r[:4]) for r in breakdown], key=lambda r: -r[1]), fh)
         cpu_value, cores, sample = cpu_reference_rate(V, args.cpu_seconds) if world == 1 else (None, None, None)
         eager = None
         if world == 1 and not args.no_eager:
@@ -342,9 +355,10 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16" if bf16 else "tf32", "data": "synthetic",
             "config": {"workload": f"batch {B} x {V} views per GPU, merger + refiner, CVA on, 224x224 -> 32^3 "
-                                   "(BASELINE configs[1])",
+                                   + ("(BASELINE configs[2]; encoder in bf16, decoder / merger / refiner in TF32)" if bf16
+                                      else "(BASELINE configs[1])"),
                        "l2": "per-step working set (activations) is several GB, far larger than the 126 MB L2",
                        "cuda_graph": not args.no_graph, "weights": "random init (reference architecture)"},
             "e2e": {"value": e2e_value, "unit": "objects/s", "h2d_bytes_per_step": h2d_bytes,
@@ -371,6 +385,8 @@ def main():
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline leg")
     ap.add_argument("--batch", type=int, default=64, help="objects per GPU")
     ap.add_argument("--views", type=int, default=3)
+    ap.add_argument("--dtype", default="tf32", choices=["tf32", "bf16"],
+                    help="bf16: the encoder stores / multiplies in bf16 (BASELINE configs[2] with --views 5)")
     ap.add_argument("--ref-sample", type=int, default=4, help="objects per reference-arm step (bounded CPU sample)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget inside the default run")
     ap.add_argument("--no-graph", action="store_true")

@@ -113,7 +113,7 @@ typedef struct svx_gemm_desc {
   int32_t Kpad, Npad;       /* padded weight extents (Kpad % 32 == 0, Npad % block_n == 0) */
   int32_t block_n;          /* N tile: 16, 32, 64, 96, 128, 192 or 256 (48 in slab mode) */
   int32_t a_mode;
-  const float* A;
+  const void* A;            /* fp32, or bf16 with SVX_OPERAND_BF16 */
   int64_t lda;              /* plain: row stride (elements); flat: number of rows of the padded matrix */
   /* gather description */
   int32_t in_D, in_H, in_W, in_Cs, in_c0, Cin;
@@ -124,10 +124,10 @@ typedef struct svx_gemm_desc {
   const int32_t* taps_host; /* the same table in host memory (flat mode; read at plan-build time only) */
   int32_t valid_D, valid_H, valid_W; /* flat mode: extents of the rows that are real outputs (0 = all) */
   /* weights / epilogue */
-  const float* W;
-  const float* bias;        /* [Npad] or NULL */
-  const float* residual;    /* or NULL */
-  float* out;
+  const void* W;            /* fp32 (TF32-rounded), or bf16 with SVX_OPERAND_BF16 (then Kpad % 64 == 0) */
+  const float* bias;        /* [Npad] or NULL (always fp32) */
+  const void* residual;     /* or NULL; fp32, or bf16 with SVX_IO_RES_BF16 */
+  void* out;                /* fp32, or bf16 with SVX_IO_OUT_BF16 */
   int64_t o_base, o_sn, o_sd, o_sh, o_sw;
   int32_t act;
   float act_param;          /* LeakyReLU slope */

@@ -68,6 +68,7 @@ struct GemmParams {
   long long c_sd, c_sh, c_sw, c2_sd, c2_sh, c2_sw;   // class-bit offsets in out / residual and in out2
   int i2c_lo_d, i2c_lo_h, i2c_lo_w;   // im2col mode: base-pixel coordinate of output 0 on each axis (= smallest tap)
   int i2c_narrow, ntaps;              // 4-channel pixels (image stems): eight 16-byte taps per k-chunk, unswizzled A tile
+  int io16;                 // bf16 kernels: out and residual are bf16 in memory (otherwise fp32)
   const float* Wg;          // slab mode, fp16 operands: the fp32 weight matrix in global memory (converted once per CTA)
   int* range_flag;          // slab mode, fp16 operands: OR-ed with 1 when an activation saturated in the conversion
   float acc_scale;          // slab mode: accumulator scale applied before the bias (inverse of the host's weight scale)
@@ -141,7 +142,7 @@ __device__ __forceinline__ bool decode_row(const GemmParams& p, int r, long long
 
 // One epilogue pass of a warp over a staged 32 x SLAB accumulator block: every warp-wide access covers whole
 // 16*CP-byte row segments (coalesced), rows are processed G at a time so their loads overlap.
-template <int SLAB, int ACT>
+template <int SLAB, int ACT, bool IO16 = false>
 __device__ __forceinline__ void store_slab(const GemmParams& p, const float* staging, const long long* soff,
                                            int lane, int jb) {
   constexpr int CP = SLAB / 4;
@@ -167,9 +168,13 @@ __device__ __forceinline__ void store_slab(const GemmParams& p, const float* sta
       a4[i] = *reinterpret_cast<const float4*>(staging + row * SLAB + ((ch ^ (row & (CP - 1))) << 2));
     }
 #pragma unroll
-    for (int i = 0; i < G; ++i)   // plain loads: out may alias the residual
-      r4[i] = (has_res && ok[i]) ? *reinterpret_cast<const float4*>(p.residual + ro[i] + col)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < G; ++i) {  // plain loads: out may alias the residual
+      if constexpr (IO16)
+        r4[i] = (has_res && ok[i]) ? ld4(reinterpret_cast<const bf16_t*>(p.residual) + ro[i] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      else
+        r4[i] = (has_res && ok[i]) ? *reinterpret_cast<const float4*>(p.residual + ro[i] + col)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int i = 0; i < G; ++i) {
       float x[4] = {a4[i].x + b4.x, a4[i].y + b4.y, a4[i].z + b4.z, a4[i].w + b4.w};
@@ -182,18 +187,24 @@ __device__ __forceinline__ void store_slab(const GemmParams& p, const float* sta
         t *= scale;
         x[q] = rnd ? round_tf32(t) : t;
       }
-      if (ok[i]) *reinterpret_cast<float4*>(p.out + ro[i] + col) = make_float4(x[0], x[1], x[2], x[3]);
+      if (ok[i]) {
+        if constexpr (IO16) st4(reinterpret_cast<bf16_t*>(p.out) + ro[i] + col, make_float4(x[0], x[1], x[2], x[3]));
+        else *reinterpret_cast<float4*>(p.out + ro[i] + col) = make_float4(x[0], x[1], x[2], x[3]);
+      }
     }
   }
 }
 
-template <int BN, int PARTS>
-__global__ void __launch_bounds__(Cfg<BN, PARTS>::kThreadsT, Cfg<BN, PARTS>::kCtasPerSm)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
-                 const __grid_constant__ GemmParams p) {
+// BF = false: fp32 storage read as TF32 (kind::tf32, 32 elements per 128-byte k-chunk).  BF = true: bf16 A / W
+// (kind::f16 with bf16 operand formats, 64 elements per k-chunk, K = 16 per MMA); the byte geometry of the pipeline --
+// 128-byte swizzled rows, four 32-byte MMA steps per chunk -- is identical, so one body serves both.
+template <int BN, int PARTS, bool BF>
+__device__ __forceinline__ void gemm_body(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_c,
+                                          const CUtensorMap& map_r, const GemmParams& p) {
   using C = Cfg<BN, PARTS>;
   constexpr int S = C::kStages;
+  constexpr int BKE = BF ? 64 : 32;        // elements per k-chunk
+  constexpr int ESZ = BF ? 2 : 4;          // bytes per operand element
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -262,13 +273,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t b_dst = a_dst + A_STAGE_BYTES;
           if (a_mode == SVX_A_PLAIN) {
             mbar_arrive_expect_tx(full_bar(s), A_STAGE_BYTES + C::kBBytes);
-            if (kc < p.nk_a) tma_load_2d(a_dst, &map_a, full_bar(s), kc * BK, m0);
-            else tma_load_2d(a_dst, &map_r, full_bar(s), n0 + (kc - p.nk_a) * BK, m0);   // residual x identity
+            if (kc < p.nk_a) tma_load_2d(a_dst, &map_a, full_bar(s), kc * BKE, m0);
+            else tma_load_2d(a_dst, &map_r, full_bar(s), n0 + (kc - p.nk_a) * BKE, m0);   // residual x identity
           } else if (a_mode == SVX_A_FLAT) {
             mbar_arrive_expect_tx(full_bar(s), A_STAGE_BYTES + C::kBBytes);
             const int tap = kc / p.chunks_per_tap;
             const int cc = kc - tap * p.chunks_per_tap;
-            tma_load_2d(a_dst, &map_a, full_bar(s), p.in_c0 + cc * BK, m0 + p.flat_off[tap]);
+            tma_load_2d(a_dst, &map_a, full_bar(s), p.in_c0 + cc * BKE, m0 + p.flat_off[tap]);
           } else if (a_mode == SVX_A_IM2COL) {
             mbar_arrive_expect_tx(full_bar(s), A_STAGE_BYTES + C::kBBytes);
             if (kc == 0) {   // first output pixel of the tile -> base pixel of the hardware traversal
@@ -303,13 +314,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               const int tap = kc / p.chunks_per_tap;
               const int cc = kc - tap * p.chunks_per_tap;
               const int o = p.flat_off[tap];
-              tma_load_im2col_5d(a_dst, &map_a, full_bar(s), p.in_c0 + cc * BK, i2c_w, i2c_h, i2c_d, i2c_n,
+              tma_load_im2col_5d(a_dst, &map_a, full_bar(s), p.in_c0 + cc * BKE, i2c_w, i2c_h, i2c_d, i2c_n,
                                  (uint16_t)(o & 255), (uint16_t)((o >> 8) & 255), (uint16_t)((o >> 16) & 255));
             }
           } else {
             mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
           }
-          tma_load_2d(b_dst, &map_b, full_bar(s), kc * BK, n0);
+          tma_load_2d(b_dst, &map_b, full_bar(s), kc * BKE, n0);
         }
       }
     }
@@ -317,7 +328,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else if (warp == 5) {
     // ---- MMA issuer -----------------------------------------------------------------------
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+      constexpr uint32_t idesc = BF ? umma_idesc_bf16(BM, BN) : umma_idesc_tf32(BM, BN);
       uint32_t g = 0, it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t as = it & 1u;
@@ -338,7 +349,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 8 fp32 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-            umma_tf32(acc, da + a_step * k, db + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+            if constexpr (BF) umma_f16(acc, da + a_step * k, db + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+            else umma_tf32(acc, da + a_step * k, db + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(s));
         }
@@ -368,7 +380,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int od = t % p.out_D;
             const int n = t / p.out_D;
             const int zd = od * p.sd, zh = oh * p.sh, zw = ow * p.sw;
-            base[i] = ((((long long)n * p.in_D + zd) * p.in_H + zh) * p.in_W + zw) * p.in_Cs;
+            base[i] = ((((long long)n * p.in_D + zd) * p.in_H + zh) * p.in_W + zw) * p.in_Cs * ESZ;   // bytes
             crd[i] = zd | (zh << 10) | (zw << 20) | (1 << 30);
           } else {
             base[i] = 0;
@@ -379,7 +391,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const int s = g % S;
           const uint32_t ph = (g / S) & 1;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          const int k4 = kc * BK + j * 4;
+          const int k4 = kc * BKE + j * (16 / ESZ);   // first element of this lane's 16-byte chunk
           const bool kv = k4 < p.K;
           int dd = 0, dh = 0, dw = 0, delta = 0;
           if (kv) {
@@ -387,7 +399,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int c = k4 - tap * p.Cin;
             const int4 t = __ldg(p.taps + tap);
             dd = t.x; dh = t.y; dw = t.z;
-            delta = ((dd * p.in_H + dh) * p.in_W + dw) * p.in_Cs + p.in_c0 + c;
+            delta = (((dd * p.in_H + dh) * p.in_W + dw) * p.in_Cs + p.in_c0 + c) * ESZ;   // bytes
           }
           const uint32_t a_dst = smem_base + s * C::kStageBytes;
 #pragma unroll
@@ -398,7 +410,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int iw = ((crd[i] >> 20) & 1023) + dw;
             const bool ok = kv && (crd[i] >> 30) && (unsigned)id < (unsigned)p.in_D &&
                             (unsigned)ih < (unsigned)p.in_H && (unsigned)iw < (unsigned)p.in_W;
-            const float* src = ok ? (p.A + base[i] + delta) : p.A;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.A) + (ok ? base[i] + delta : 0);
             const uint32_t dst = a_dst + row * 128 + ((j ^ (row & 7)) << 4);
             cp_async16_zfill(dst, src, ok ? 16u : 0u);
           }
@@ -444,6 +456,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int row = m0 + quarter * 32 + lane;
         const bool row_ok = row < p.M;
         const float* res_row = p.residual + static_cast<long long>(row) * p.ldc;
+        const bf16_t* res_row16 = reinterpret_cast<const bf16_t*>(p.residual) + static_cast<long long>(row) * p.ldc;
+        const bool io16 = BF && p.io16;
         const bool has_res = p.residual != nullptr;
         const bool pre = has_res && !p.res_after_act, post = has_res && p.res_after_act;
         char* stg = reinterpret_cast<char*>(staging);                       // 2 x 2 KB, 1024-byte aligned
@@ -457,6 +471,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         constexpr int kAhead = 1;   // deeper prefetch measured slower: the row-per-lane loads congest the L1 pipeline
         float4 rq[kAhead][4];
         auto load_res = [&](int jbn, float4 (&dst)[4]) {
+          if (io16) {   // 16 columns = two 16-byte loads of eight bf16 each
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint4 u = make_uint4(0u, 0u, 0u, 0u);
+              if (row_ok && jbn + 8 * h < p.N) u = *reinterpret_cast<const uint4*>(res_row16 + jbn + 8 * h);
+              dst[2 * h] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+              dst[2 * h + 1] = make_float4(bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w));
+            }
+            return;
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             dst[c] = (row_ok && jbn + 4 * c < p.N) ? *reinterpret_cast<const float4*>(res_row + jbn + 4 * c)
@@ -547,10 +571,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           // this buffer's previous store (two blocks ago) must have been read out of smem by the TMA unit
           if (lane == 0) tma_store_wait_read<C::kEpiBufs - 1>();
           __syncwarp();
-          char* my_row = stg + buf * 2048 + lane * 64;
+          if (io16) {   // 32-byte rows (16 bf16), 32B swizzle: chunk ^= bit 7 of the byte address = bit 2 of the row
+            char* my_row = stg + buf * 2048 + lane * 32;
+            const int sw1 = (lane >> 2) & 1;
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<float4*>(my_row + ((c ^ sw) << 4)) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+            for (int h = 0; h < 2; ++h)
+              *reinterpret_cast<uint4*>(my_row + ((h ^ sw1) << 4)) =
+                  make_uint4(pack_bf16x2(x[8 * h], x[8 * h + 1]), pack_bf16x2(x[8 * h + 2], x[8 * h + 3]),
+                             pack_bf16x2(x[8 * h + 4], x[8 * h + 5]), pack_bf16x2(x[8 * h + 6], x[8 * h + 7]));
+          } else {
+            char* my_row = stg + buf * 2048 + lane * 64;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<float4*>(my_row + ((c ^ sw) << 4)) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -587,13 +621,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             *reinterpret_cast<uint4*>(staging + lane * SLAB + ((c ^ (lane & (CP - 1))) << 2)) =
                 make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           __syncwarp();
-          switch (p.act) {
-            case SVX_ACT_RELU: store_slab<SLAB, SVX_ACT_RELU>(p, staging, soff, lane, jb); break;
-            case SVX_ACT_LEAKY: store_slab<SLAB, SVX_ACT_LEAKY>(p, staging, soff, lane, jb); break;
-            case SVX_ACT_GELU: store_slab<SLAB, SVX_ACT_GELU>(p, staging, soff, lane, jb); break;
-            default: store_slab<SLAB, SVX_ACT_NONE>(p, staging, soff, lane, jb); break;
+          if (BF && p.io16) {
+            switch (p.act) {
+              case SVX_ACT_RELU: store_slab<SLAB, SVX_ACT_RELU, true>(p, staging, soff, lane, jb); break;
+              case SVX_ACT_LEAKY: store_slab<SLAB, SVX_ACT_LEAKY, true>(p, staging, soff, lane, jb); break;
+              case SVX_ACT_GELU: store_slab<SLAB, SVX_ACT_GELU, true>(p, staging, soff, lane, jb); break;
+              default: store_slab<SLAB, SVX_ACT_NONE, true>(p, staging, soff, lane, jb); break;
+            }
+          } else {
+            switch (p.act) {
+              case SVX_ACT_RELU: store_slab<SLAB, SVX_ACT_RELU>(p, staging, soff, lane, jb); break;
+              case SVX_ACT_LEAKY: store_slab<SLAB, SVX_ACT_LEAKY>(p, staging, soff, lane, jb); break;
+              case SVX_ACT_GELU: store_slab<SLAB, SVX_ACT_GELU>(p, staging, soff, lane, jb); break;
+              default: store_slab<SLAB, SVX_ACT_NONE>(p, staging, soff, lane, jb); break;
+            }
           }
-        } else if (valid) {
+        } else if (!BF && valid) {   // (row-wise epilogues exist for fp32 storage only: decoder / refiner tails)
           // one thread = one output row (decoder tail needs the whole row; N % 4 != 0 outputs are scalar)
           float x[SLAB];
 #pragma unroll
@@ -699,6 +742,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (warp == 5) tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+template <int BN, int PARTS>
+__global__ void __launch_bounds__(Cfg<BN, PARTS>::kThreadsT, Cfg<BN, PARTS>::kCtasPerSm)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
+                 const __grid_constant__ GemmParams p) {
+  gemm_body<BN, PARTS, false>(map_a, map_b, map_c, map_r, p);
+}
+
+template <int BN, int PARTS>
+__global__ void __launch_bounds__(Cfg<BN, PARTS>::kThreadsT, Cfg<BN, PARTS>::kCtasPerSm)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
+                 const __grid_constant__ GemmParams p) {
+  gemm_body<BN, PARTS, true>(map_a, map_b, map_c, map_r, p);
 }
 
 
@@ -1165,20 +1224,25 @@ EncodeTiledFn get_encode_fn() {
 
 // 2-D fp32 tensor [rows, cols] with row pitch `pitch_elems`; box = box_rows x box_cols columns (32: 128B swizzle,
 // 16: 64B swizzle)
-int encode_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
-               uint32_t box_rows, uint32_t box_cols = BK) {
+// esize = 4: fp32 elements; 2: bf16.  The swizzle mode follows the box width in BYTES (128 / 64 / 32).
+int encode_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+               uint32_t box_rows, uint32_t box_cols = BK, int esize = 4) {
   if (box_rows > 256) return fail("TMA box of %u rows exceeds 256", box_rows);
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {pitch_elems * 4};
+  cuuint64_t strides[1] = {pitch_elems * (uint64_t)esize};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+  const uint32_t box_bytes = box_cols * (uint32_t)esize;
+  if (box_bytes != 128 && box_bytes != 64 && box_bytes != 32) return fail("TMA box of %u bytes per row unsupported", box_bytes);
+  if ((pitch_elems * (uint64_t)esize) % 16 != 0) return fail("TMA row pitch of %llu bytes is not a multiple of 16", (unsigned long long)(pitch_elems * esize));
+  CUresult r = fn(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr),
+                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  box_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   // a 64-byte box out of a wider row must not be promoted to 128-byte L2 fills: that doubled the DRAM
                   // reads of the merger's 16-channel layers (profiles/r1_ncu_merger_v17.txt)
-                  box_cols == 16 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  box_bytes <= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
@@ -1191,8 +1255,8 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 
 // im2col-mode map over the channels-last tensor [N, D, H, W, Cs]: boxes of 128 pixels x 32 channels, 128B swizzle.
 // lo / up: bounding-box corners of the base pixel per axis (d, h, w); str: convolution strides (d, h, w).
-int encode_im2col_map(CUtensorMap* map, const float* ptr, uint64_t N, uint64_t D, uint64_t H, uint64_t W, uint64_t Cs,
-                      const int lo[3], const int up[3], const int str[3], int box_ch = BK) {
+int encode_im2col_map(CUtensorMap* map, const void* ptr, uint64_t N, uint64_t D, uint64_t H, uint64_t W, uint64_t Cs,
+                      const int lo[3], const int up[3], const int str[3], int box_ch = BK, int esize = 4) {
   static EncodeIm2colFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -1203,13 +1267,15 @@ int encode_im2col_map(CUtensorMap* map, const float* ptr, uint64_t N, uint64_t D
   }
   if (!fn) return fail("cuTensorMapEncodeIm2col entry point not available");
   cuuint64_t dims[5] = {Cs, W, H, D, N};
-  cuuint64_t strides[4] = {Cs * 4, W * Cs * 4, H * W * Cs * 4, D * H * W * Cs * 4};
+  const uint64_t es = (uint64_t)esize;
+  cuuint64_t strides[4] = {Cs * es, W * Cs * es, H * W * Cs * es, D * H * W * Cs * es};
+  const int box_bytes = box_ch * esize;
   int lower[3] = {lo[2], lo[1], lo[0]}, upper[3] = {up[2], up[1], up[0]};   // the driver takes (w, h, d)
   cuuint32_t estr[5] = {1, (cuuint32_t)str[2], (cuuint32_t)str[1], (cuuint32_t)str[0], 1};
   // narrow: one 4-channel (16-byte) pixel per row, stored densely (no swizzle) = a column of 8x16B core matrices
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(ptr), dims, strides, lower, upper,
-                  (cuuint32_t)box_ch, BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  box_ch == 4 ? CU_TENSOR_MAP_SWIZZLE_NONE : box_ch == 8 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = fn(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(ptr),
+                  dims, strides, lower, upper, (cuuint32_t)box_ch, BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  box_bytes == 16 ? CU_TENSOR_MAP_SWIZZLE_NONE : box_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -1231,12 +1297,16 @@ int sm_count() {
 
 template <int BN, int PARTS>
 int launch_bn_parts(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr,
-                    const GemmParams& p, int grid, cudaStream_t st) {
+                    const GemmParams& p, int grid, cudaStream_t st, bool bf) {
   using C = Cfg<BN, PARTS>;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in is per device and cheap: set it on every launch path rather than caching a per-process flag
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
     SVX_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    configured = true;
+    SVX_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    configured_dev = dev;
   }
   static const bool pdl = getenv("SVX_PDL") != nullptr;   // opt-in until validated on the GPU tier
   cudaLaunchConfig_t cfg = {};
@@ -1249,22 +1319,24 @@ int launch_bn_parts(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensor
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, PARTS>, ma, mb, mc, mr, p);
-  if (le != cudaSuccess) return fail("launch of gemm_tf32_kernel failed: %s", cudaGetErrorString(le));
+  cudaError_t le = bf ? cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, PARTS>, ma, mb, mc, mr, p)
+                      : cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, PARTS>, ma, mb, mc, mr, p);
+  if (le != cudaSuccess) return fail("launch of gemm_%s_kernel failed: %s", bf ? "bf16" : "tf32", cudaGetErrorString(le));
   SVX_LAUNCH_OK("gemm_tf32_kernel");
   return 0;
 }
 
 template <int BN>
 int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mr,
-              const GemmParams& p, int grid, cudaStream_t st) {
+              const GemmParams& p, int grid, cudaStream_t st, bool bf) {
   if constexpr (BN >= 128) {
     // erf-GELU epilogues through the TMA-store path: twice the epilogue warps (see Cfg)
-    // (only while the main loop is short: at K = 768 the tensor pipe is the bound again and the variant loses)
-    if (p.act == SVX_ACT_GELU && p.epi_tma && p.a_mode != SVX_A_GATHER && p.K <= 512 && !getenv("SVX_GEMM_NO_WIDE_EPILOGUE"))
-      return launch_bn_parts<BN, 4>(ma, mb, mc, mr, p, grid, st);
+    // (only while the main loop is short: at K = 768 the tensor pipe is the bound again and the variant loses;
+    //  bf16 main loops take half the time per K, so the epilogue bound holds up to twice the depth)
+    if (p.act == SVX_ACT_GELU && p.epi_tma && p.a_mode != SVX_A_GATHER && p.K <= (bf ? 1024 : 512))
+      return launch_bn_parts<BN, 4>(ma, mb, mc, mr, p, grid, st, bf);
   }
-  return launch_bn_parts<BN, 2>(ma, mb, mc, mr, p, grid, st);
+  return launch_bn_parts<BN, 2>(ma, mb, mc, mr, p, grid, st, bf);
 }
 
 }  // namespace
@@ -1277,6 +1349,7 @@ struct GemmPrepared {
   bool slab_narrow = false;   // 16-channel (64-byte) rows
   bool slab_pair = false;     // CTA pairs (cta_group::2): one M = 256 MMA per step for two units
   bool slab_f16 = false;      // fp16 MMA operands converted inside the kernel (kind::f16: half the MMA instructions)
+  bool bf16 = false;          // SVX_OPERAND_BF16: gemm_bf16_kernel
 };
 
 int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
@@ -1285,7 +1358,19 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   SVX_REQUIRE(d.block_n == 16 || d.block_n == 32 || d.block_n == 64 || d.block_n == 96 || d.block_n == 128 ||
                   d.block_n == 192 || d.block_n == 256 || (d.block_n == 48 && d.a_mode == SVX_A_SLAB3),
               "gemm: block_n=%d unsupported", d.block_n);
-  SVX_REQUIRE(d.Kpad % BK == 0 && d.Kpad >= d.K, "gemm: Kpad=%d must be a multiple of 32 and >= K=%d", d.Kpad, d.K);
+  const bool bf = d.operand_kind == SVX_OPERAND_BF16;
+  const int esz = bf ? 2 : 4;             // bytes per operand element
+  const int BKE = 128 / esz;              // elements per 128-byte k-chunk
+  const int e16 = 16 / esz;               // elements per 16 bytes
+  SVX_REQUIRE(d.operand_kind == SVX_OPERAND_DEFAULT || bf || (d.operand_kind == SVX_OPERAND_TF32 && d.a_mode == SVX_A_SLAB3),
+              "gemm: operand_kind %d unsupported for this operand mode", d.operand_kind);
+  SVX_REQUIRE(bf || d.io_flags == 0, "gemm: bf16 outputs / residuals need bf16 operands");
+  SVX_REQUIRE(!bf || (d.a_mode != SVX_A_SLAB3 && d.epi_mode == SVX_EPI_STD),
+              "gemm: bf16 operands support the standard epilogue of the plain / flat / im2col / gather modes only");
+  const bool io16 = (d.io_flags & SVX_IO_OUT_BF16) != 0;
+  SVX_REQUIRE(!d.residual || ((d.io_flags & SVX_IO_RES_BF16) != 0) == io16 || d.res_via_mma,
+              "gemm: the epilogue residual must have the output's storage type");
+  SVX_REQUIRE(d.Kpad % BKE == 0 && d.Kpad >= d.K, "gemm: Kpad=%d must be a multiple of %d and >= K=%d", d.Kpad, BKE, d.K);
   SVX_REQUIRE(d.Npad % d.block_n == 0 && d.Npad >= d.N, "gemm: Npad=%d vs N=%d block_n=%d", d.Npad, d.N, d.block_n);
   SVX_REQUIRE(d.A && d.W && d.out, "gemm: null operand");
   SVX_REQUIRE((reinterpret_cast<uintptr_t>(d.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.W) & 15) == 0,
@@ -1299,13 +1384,13 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   memset(&g->map_r, 0, sizeof(g->map_r));
   p.chunks_per_tap = 1;
   if (d.a_mode == SVX_A_PLAIN) {
-    if (d.lda % 4 != 0 || d.lda < d.K) {
+    if (d.lda % e16 != 0 || d.lda < d.K) {
       delete g;
-      return fail("gemm: plain A needs lda %% 4 == 0 and lda >= K (lda=%lld K=%d)", (long long)d.lda, d.K);
+      return fail("gemm: plain A needs a 16-byte row pitch and lda >= K (lda=%lld K=%d)", (long long)d.lda, d.K);
     }
-    if (encode_map(&g->map_a, d.A, (uint64_t)d.M, (uint64_t)d.K, (uint64_t)d.lda, BM)) { delete g; return 1; }
+    if (encode_map(&g->map_a, d.A, (uint64_t)d.M, (uint64_t)d.K, (uint64_t)d.lda, BM, BKE, esz)) { delete g; return 1; }
   } else if (d.a_mode == SVX_A_GATHER) {
-    bool ok = d.Cin > 0 && d.Cin % 4 == 0 && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.ntaps > 0 && d.taps &&
+    bool ok = d.Cin > 0 && d.Cin % e16 == 0 && d.in_c0 % e16 == 0 && d.in_Cs % e16 == 0 && d.ntaps > 0 && d.taps &&
               d.K == d.ntaps * d.Cin && d.in_D > 0 && d.in_H > 0 && d.in_W > 0 && d.in_D < 1024 &&
               d.in_H < 1024 && d.in_W < 1024;
     if (!ok) {
@@ -1314,7 +1399,7 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
                   d.ntaps, d.K);
     }
   } else if (d.a_mode == SVX_A_FLAT) {
-    bool ok = d.Cin > 0 && d.Cin % BK == 0 && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.ntaps > 0 &&
+    bool ok = d.Cin > 0 && d.Cin % BKE == 0 && d.in_c0 % e16 == 0 && d.in_Cs % e16 == 0 && d.ntaps > 0 &&
               d.ntaps <= kMaxTaps && d.taps_host && d.K == d.ntaps * d.Cin && d.Kpad == d.K &&
               d.out_D == d.in_D && d.out_H == d.in_H && d.out_W == d.in_W;
     if (!ok) {
@@ -1328,11 +1413,11 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
       if (dd < 0 || dh < 0 || dw < 0) { delete g; return fail("gemm: flat-conv taps must be non-negative"); }
       p.flat_off[t] = (dd * d.in_H + dh) * d.in_W + dw;
     }
-    p.chunks_per_tap = d.Cin / BK;
-    if (encode_map(&g->map_a, d.A, (uint64_t)rows_total, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs, BM)) { delete g; return 1; }
+    p.chunks_per_tap = d.Cin / BKE;
+    if (encode_map(&g->map_a, d.A, (uint64_t)rows_total, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs, BM, BKE, esz)) { delete g; return 1; }
   } else if (d.a_mode == SVX_A_IM2COL) {
-    const bool narrow = d.Cin == 4, pairs = d.Cin == 8;
-    bool ok = d.Cin > 0 && (narrow || ((pairs || d.Cin % BK == 0) && d.Kpad == d.K)) && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 &&
+    const bool narrow = d.Cin * esz == 16, pairs = d.Cin * esz == 32;   // 16-byte / 32-byte pixels
+    bool ok = d.Cin > 0 && (narrow || ((pairs || d.Cin % BKE == 0) && d.Kpad == d.K)) && d.in_c0 % e16 == 0 && d.in_Cs % e16 == 0 &&
               d.ntaps > 0 && d.ntaps <= kMaxTaps && d.taps_host && d.K == d.ntaps * d.Cin && d.in_D > 0 && d.in_H > 0 && d.in_W > 0 &&
               d.stride_d >= 1 && d.stride_h >= 1 && d.stride_w >= 1 && d.stride_d <= 8 && d.stride_h <= 8 && d.stride_w <= 8 &&
               d.M % (d.out_D * d.out_H * d.out_W) == 0;
@@ -1362,11 +1447,12 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
       p.flat_off[t] = (d.taps_host[4 * t + 2] - lo[2]) | ((d.taps_host[4 * t + 1] - lo[1]) << 8) |
                       ((d.taps_host[4 * t] - lo[0]) << 16);
     p.i2c_lo_d = lo[0]; p.i2c_lo_h = lo[1]; p.i2c_lo_w = lo[2];
-    p.chunks_per_tap = (narrow || pairs) ? 1 : d.Cin / BK;
+    p.chunks_per_tap = (narrow || pairs) ? 1 : d.Cin / BKE;
     p.i2c_narrow = narrow ? 1 : pairs ? 2 : 0;
     p.ntaps = d.ntaps;
     const uint64_t n_img = (uint64_t)(d.M / (d.out_D * d.out_H * d.out_W));
-    if (encode_im2col_map(&g->map_a, d.A, n_img, d.in_D, d.in_H, d.in_W, d.in_Cs, lo, up, str, narrow ? 4 : pairs ? 8 : BK)) { delete g; return 1; }
+    if (encode_im2col_map(&g->map_a, d.A, n_img, d.in_D, d.in_H, d.in_W, d.in_Cs, lo, up, str,
+                          narrow ? e16 : pairs ? 2 * e16 : BKE, esz)) { delete g; return 1; }
   } else if (d.a_mode == SVX_A_SLAB3) {
     const int live = d.cin_live > 0 ? d.cin_live : BK;
     bool ok = d.Cin == BK && live <= BK && d.in_Cs % 4 == 0 && d.in_c0 >= 0 && d.N <= 16 && d.block_n == S3_N &&
@@ -1394,11 +1480,13 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   // faster than single CTAs on this kernel (profiles/README.md, "merger slab kernel experiments"): opt-in only.
   g->slab_pair = g->slab && getenv("SVX_SLAB_PAIR") != nullptr;
   g->slab_f16 = g->slab && !g->slab_pair && d.operand_kind != SVX_OPERAND_TF32;
-  p.Wg = d.W;
+  g->bf16 = bf;
+  p.io16 = io16 ? 1 : 0;
+  p.Wg = reinterpret_cast<const float*>(d.W);
   p.range_flag = g->slab_f16 ? d.range_flag : nullptr;
   p.acc_scale = d.acc_scale != 0.f ? d.acc_scale : 1.f;
   if (encode_map(&g->map_b, d.W, (uint64_t)d.Npad, (uint64_t)w_cols, (uint64_t)w_cols,
-                 g->slab_pair ? (uint32_t)(S3_N / 2) : (uint32_t)d.block_n, g->slab_narrow ? 16 : BK)) {
+                 g->slab_pair ? (uint32_t)(S3_N / 2) : (uint32_t)d.block_n, g->slab_narrow ? 16 : BKE, esz)) {
     delete g;
     return 1;
   }
@@ -1416,15 +1504,15 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
                           : true);
     if (!ok) { delete g; return fail("gemm: bad transposed-convolution class epilogue (cls_cout=%d N=%d)", d.cls_cout, d.N); }
   }
-  p.M = d.M; p.N = d.N; p.K = d.K; p.Npad = d.Npad; p.nk = d.Kpad / BK; p.nk_a = p.nk; p.tiles_n = d.Npad / d.block_n; p.a_mode = d.a_mode;
-  p.A = d.A;
+  p.M = d.M; p.N = d.N; p.K = d.K; p.Npad = d.Npad; p.nk = d.Kpad / BKE; p.nk_a = p.nk; p.tiles_n = d.Npad / d.block_n; p.a_mode = d.a_mode;
+  p.A = reinterpret_cast<const float*>(d.A);
   p.in_D = d.in_D; p.in_H = d.in_H; p.in_W = d.in_W; p.in_Cs = d.in_Cs; p.in_c0 = d.in_c0; p.Cin = d.Cin;
   p.out_D = d.out_D; p.out_H = d.out_H; p.out_W = d.out_W;
   p.valid_D = d.valid_D; p.valid_H = d.valid_H; p.valid_W = d.valid_W;
   if (p.valid_W > 0 && (p.valid_D <= 0 || p.valid_H <= 0)) { delete g; return fail("gemm: valid extents must all be set"); }
   p.sd = d.stride_d; p.sh = d.stride_h; p.sw = d.stride_w;
   p.taps = reinterpret_cast<const int4*>(d.taps);
-  p.bias = d.bias; p.residual = d.residual; p.out = d.out;
+  p.bias = d.bias; p.residual = reinterpret_cast<const float*>(d.residual); p.out = reinterpret_cast<float*>(d.out);
   p.o_base = d.o_base; p.o_sn = d.o_sn; p.o_sd = d.o_sd; p.o_sh = d.o_sh; p.o_sw = d.o_sw;
   p.act = d.act; p.act_param = d.act_param; p.res_after_act = d.res_after_act;
   p.out_scale = d.out_scale; p.round_tf32 = d.round_tf32; p.epi_mode = d.epi_mode;
@@ -1435,6 +1523,7 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   p.vec_ok = (d.N % 4 == 0) && al4(d.o_base) && al4(d.o_sn) && al4(d.o_sd) && al4(d.o_sh) && al4(d.o_sw) &&
              (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
              (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0);
+  if (bf && !p.vec_ok) { delete g; return fail("gemm: bf16 operands need 4-element aligned outputs (N=%d)", d.N); }
   // Plain row-major output (row r lands at out + o_base + r*ldc, every row a real output): the epilogue stores
   // through TMA.  True for every linear layer and for convolutions writing an unpadded channels-last tensor.
   {
@@ -1442,26 +1531,29 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
                          d.o_sn == (long long)d.out_D * d.o_sd;
     const bool pool8 = d.epi_mode == SVX_EPI_POOL8;
     const int n_out = pool8 ? d.N / 8 : d.N;
+    const int oe16 = io16 ? 8 : 4;   // output elements per 16 bytes
     const bool plain = compact && d.valid_W == 0 && (d.epi_mode == SVX_EPI_STD || pool8) && d.a_mode != SVX_A_SLAB3 &&
-                       d.block_n >= 32 && n_out % 4 == 0 && d.o_sw % 4 == 0 && d.o_sw >= n_out && (d.o_base & 3) == 0 &&
+                       d.block_n >= 32 && n_out % oe16 == 0 && d.o_sw % oe16 == 0 && d.o_sw >= n_out && (d.o_base % oe16) == 0 &&
                        (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
                        (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0) && !getenv("SVX_NO_TMA_EPILOGUE");
     if (plain) {
       p.epi_tma = 1;
       p.ldc = d.o_sw;
-      p.out = d.out + d.o_base;
-      if (d.residual) p.residual = d.residual + d.o_base;
-      if (encode_map(&g->map_c, p.out, (uint64_t)d.M, (uint64_t)n_out, (uint64_t)d.o_sw, 32, 16)) { delete g; return 1; }
+      const size_t osz = io16 ? 2 : 4;
+      p.out = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d.out) + (size_t)d.o_base * osz);
+      if (d.residual)
+        p.residual = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(d.residual) + (size_t)d.o_base * osz);
+      if (encode_map(&g->map_c, p.out, (uint64_t)d.M, (uint64_t)n_out, (uint64_t)d.o_sw, 32, 16, (int)osz)) { delete g; return 1; }
     }
     if (d.res_via_mma) {
       // act(A W^T + b + R) with R added by the tensor cores: the k loop runs block_n / 32 extra chunks whose A
       // operand is the residual tile (TMA, coalesced) and whose B operand is an identity block.  Exact when R holds
       // TF32-representable values (the caller's contract).
       const bool ok = plain && d.a_mode == SVX_A_PLAIN && d.residual && !d.res_after_act && d.N % d.block_n == 0 &&
-                      d.block_n % BK == 0;
+                      d.block_n % BKE == 0 && (!bf || (d.io_flags & SVX_IO_RES_BF16));
       if (!ok) { delete g; return fail("gemm: res_via_mma needs a plain operand, a plain output, a pre-activation residual and N %% block_n == 0"); }
-      if (encode_map(&g->map_r, p.residual, (uint64_t)d.M, (uint64_t)d.N, (uint64_t)d.o_sw, BM)) { delete g; return 1; }
-      p.nk = p.nk_a + d.block_n / BK;
+      if (encode_map(&g->map_r, p.residual, (uint64_t)d.M, (uint64_t)d.N, (uint64_t)d.o_sw, BM, BKE, esz)) { delete g; return 1; }
+      p.nk = p.nk_a + d.block_n / BKE;
       p.residual = nullptr;   // nothing left for the epilogue to add
     }
     if (pool8 && !(plain && d.N == d.block_n && d.N % 128 == 0 && !d.residual)) {
@@ -1502,15 +1594,17 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = 0;
   if (g->slab) {
-    static bool configured = false;
-    if (!configured) {
+    static thread_local int configured_dev = -1;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (configured_dev != cur_dev) {
       SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<128>::kSmem));
       SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<64>::kSmem));
       SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<128, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<128>::kSmem));
       SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<64, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<64>::kSmem));
       SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<128, true>::kSmem));
       SVX_CUDA_OK(cudaFuncSetAttribute(conv3_slab_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S3Cfg<64, true>::kSmem));
-      configured = true;
+      configured_dev = cur_dev;
     }
     if (g->slab_pair) {
       cudaLaunchConfig_t cfg = {};
@@ -1544,13 +1638,13 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void* stream) {
     return 0;
   }
   switch (g->bn) {
-    case 16: rc = launch_bn<16>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st); break;
-    case 32: rc = launch_bn<32>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st); break;
-    case 64: rc = launch_bn<64>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st); break;
-    case 96: rc = launch_bn<96>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st); break;
-    case 128: rc = launch_bn<128>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st); break;
-    case 192: rc = launch_bn<192>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st); break;
-    default: rc = launch_bn<256>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st); break;
+    case 16: rc = launch_bn<16>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st, g->bf16); break;
+    case 32: rc = launch_bn<32>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st, g->bf16); break;
+    case 64: rc = launch_bn<64>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st, g->bf16); break;
+    case 96: rc = launch_bn<96>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st, g->bf16); break;
+    case 128: rc = launch_bn<128>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st, g->bf16); break;
+    case 192: rc = launch_bn<192>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st, g->bf16); break;
+    default: rc = launch_bn<256>(g->map_a, g->map_b, g->map_c, g->map_r, g->p, g->grid, st, g->bf16); break;
   }
   if (!prepared) delete g;
   return rc;

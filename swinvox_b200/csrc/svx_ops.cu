@@ -515,29 +515,64 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // Two warps per item (query strips {0,1} and {2,3}); they stage the item together and meet on a named barrier.
 // Scores are kept in the log2 domain: scale and bias carry a factor log2(e), so the softmax exponent is one ex2.
-template <bool SHIFTED>
+// T = storage type of qkv / out (fp32 or bf16): rows are staged as stored (bf16 rows are 64 bytes, 80-byte pitch) and
+// widened to fp32 when the MMA fragments are loaded, so the arithmetic is the same TF32 mma.sync either way.
+template <typename T> struct WaRow;
+template <> struct WaRow<float> {
+  static constexpr int kPitch = WA_STRIDE * 4, kChunks = 8;   // bytes per staged row, 16-byte chunks per 32-dim row
+  static __device__ __forceinline__ void ld8(const uint8_t* row, int d0, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(row + d0 * 4), b = *reinterpret_cast<const float4*>(row + d0 * 4 + 16);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ float4 ld4v(const uint8_t* row, int d0) { return *reinterpret_cast<const float4*>(row + d0 * 4); }
+  static __device__ __forceinline__ void st8(float* dst, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct WaRow<bf16_t> {
+  static constexpr int kPitch = 80, kChunks = 4;
+  static __device__ __forceinline__ void ld8(const uint8_t* row, int d0, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + d0 * 2);
+    v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+    v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+  }
+  static __device__ __forceinline__ float4 ld4v(const uint8_t* row, int d0) {
+    const uint2 u = *reinterpret_cast<const uint2*>(row + d0 * 2);
+    return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+  }
+  static __device__ __forceinline__ void st8(bf16_t* dst, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                                pack_bf16x2(v[6], v[7]));
+  }
+};
+
+template <bool SHIFTED, typename T>
 __global__ void __launch_bounds__(WA_ITEMS * 64, 2) winattn_kernel(const svx_winattn_desc d, int ctas_per_head) {
+  using R = WaRow<T>;
+  constexpr int PITCH = R::kPitch, MAT = WA_ROWS * PITCH;   // bytes per staged row / per staged Q, K or V
   extern __shared__ __align__(16) uint8_t wa_smem[];
   float* sbias = reinterpret_cast<float*>(wa_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = warp >> 1, half = warp & 1, ptid = threadIdx.x & 63;
   uint8_t* mine = wa_smem + WA_BIAS_BYTES + pair * WA_ITEM_BYTES;
-  float* Qs = reinterpret_cast<float*>(mine);
-  float* Ks = Qs + WA_ROWS * WA_STRIDE;
-  float* Vs = Ks + WA_ROWS * WA_STRIDE;
-  uint32_t* stok = reinterpret_cast<uint32_t*>(Vs + WA_ROWS * WA_STRIDE);   // token row offset in 16-byte units
+  uint8_t* Qs = mine;
+  uint8_t* Ks = Qs + MAT;
+  uint8_t* Vs = Ks + MAT;
+  uint32_t* stok = reinterpret_cast<uint32_t*>(mine + 3 * WA_ROWS * WA_STRIDE * 4);   // token row index
   int* sreg = reinterpret_cast<int*>(stok + 64);
   const int head = blockIdx.x % d.heads;
   const int cta_in_head = blockIdx.x / d.heads;
   for (int i = threadIdx.x; i < WT * WT; i += blockDim.x)
     sbias[(i / WT) * WA_BSTRIDE + (i % WT)] = __ldg(d.bias + (long long)head * WT * WT + i) * kLog2e;
-  for (int i = ptid; i < 3 * WA_ROWS * WA_STRIDE; i += 64) Qs[i] = 0.f;   // incl. the padding rows, never rewritten
+  for (int i = ptid; i < 3 * MAT / 4; i += 64) reinterpret_cast<uint32_t*>(Qs)[i] = 0u;   // incl. the padding rows, never rewritten
   __syncthreads();
   const int nwx = d.W / WS, nwy = d.H / WS;
-  const int num_windows = d.N * nwx * nwy;   // < 2^31 (checked by the launcher): 32-bit index arithmetic throughout
-  const uint32_t C3q = (3 * d.C) >> 2, Cq = d.C >> 2;
+  const int num_windows = d.N * nwx * nwy;   // < 2^31 (checked by the launcher)
+  const size_t tok_pitch = (size_t)3 * d.C * sizeof(T);
+  const size_t c_bytes = (size_t)d.C * sizeof(T);
   const int g = lane >> 2, t = lane & 3;
-  const float4* qkv4 = reinterpret_cast<const float4*>(d.qkv + head * HD);
+  const uint8_t* qkvb = reinterpret_cast<const uint8_t*>(d.qkv) + (size_t)head * HD * sizeof(T);
   const uint32_t qs_u32 = smem_u32(Qs);
   const float scale2 = d.scale * kLog2e;
   const float kMask = -100.f * kLog2e;
@@ -564,14 +599,14 @@ __global__ void __launch_bounds__(WA_ITEMS * 64, 2) winattn_kernel(const svx_win
       sreg[ptid] = reg;
     }
     named_bar(barid, 64);
-    // stage Q | K | V rows (49 x 128 B each) with 16-byte cp.async: 8 lanes per row
-    for (int i = ptid; i < WT * 8; i += 64) {
-      const int row = i >> 3, ch = i & 7;
-      const float4* base = qkv4 + stok[row] * C3q + ch;
-      const uint32_t dst = qs_u32 + (row * WA_STRIDE + ch * 4) * 4;
+    // stage Q | K | V rows (49 rows of 32 dims each) with 16-byte cp.async
+    for (int i = ptid; i < WT * R::kChunks; i += 64) {
+      const int row = i / R::kChunks, ch = i % R::kChunks;
+      const uint8_t* base = qkvb + (size_t)stok[row] * tok_pitch + ch * 16;
+      const uint32_t dst = qs_u32 + row * PITCH + ch * 16;
       cp_async16_zfill(dst, base, 16u);
-      cp_async16_zfill(dst + WA_ROWS * WA_STRIDE * 4, base + Cq, 16u);
-      cp_async16_zfill(dst + 2 * WA_ROWS * WA_STRIDE * 4, base + 2 * Cq, 16u);
+      cp_async16_zfill(dst + MAT, base + c_bytes, 16u);
+      cp_async16_zfill(dst + 2 * MAT, base + 2 * c_bytes, 16u);
     }
     cp_async_commit();
     int kreg[7][2];
@@ -589,19 +624,15 @@ __global__ void __launch_bounds__(WA_ITEMS * 64, 2) winattn_kernel(const svx_win
       const int r0 = 16 * (2 * half + mi) + g, r1 = r0 + 8;
       const int r1c = min(r1, WA_ROWS - 1);
       // Q fragments: lane t holds d = 8t .. 8t+7 of rows r0, r1 (contraction slot map above)
-      const float4 qa0 = *reinterpret_cast<const float4*>(Qs + r0 * WA_STRIDE + 8 * t);
-      const float4 qb0 = *reinterpret_cast<const float4*>(Qs + r0 * WA_STRIDE + 8 * t + 4);
-      const float4 qa1 = *reinterpret_cast<const float4*>(Qs + r1c * WA_STRIDE + 8 * t);
-      const float4 qb1 = *reinterpret_cast<const float4*>(Qs + r1c * WA_STRIDE + 8 * t + 4);
-      const float q0[8] = {qa0.x, qa0.y, qa0.z, qa0.w, qb0.x, qb0.y, qb0.z, qb0.w};
-      const float q1[8] = {qa1.x, qa1.y, qa1.z, qa1.w, qb1.x, qb1.y, qb1.z, qb1.w};
+      float q0[8], q1[8];
+      R::ld8(Qs + r0 * PITCH, 8 * t, q0);
+      R::ld8(Qs + r1c * PITCH, 8 * t, q1);
       float s[7][4];
 #pragma unroll
       for (int nb = 0; nb < 7; ++nb) {
         s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
-        const float4 ka = *reinterpret_cast<const float4*>(Ks + (8 * nb + g) * WA_STRIDE + 8 * t);
-        const float4 kb = *reinterpret_cast<const float4*>(Ks + (8 * nb + g) * WA_STRIDE + 8 * t + 4);
-        const float kk[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+        float kk[8];
+        R::ld8(Ks + (8 * nb + g) * PITCH, 8 * t, kk);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
           mma_tf32_16x8x8(s[nb], __float_as_uint(q0[2 * ks]), __float_as_uint(q1[2 * ks]), __float_as_uint(q0[2 * ks + 1]),
@@ -657,8 +688,8 @@ __global__ void __launch_bounds__(WA_ITEMS * 64, 2) winattn_kernel(const svx_win
         const uint32_t p0 = __float_as_uint(round_tf32(s[j][0])), p1 = __float_as_uint(round_tf32(s[j][2]));
         const uint32_t p2 = __float_as_uint(round_tf32(s[j][1])), p3 = __float_as_uint(round_tf32(s[j][3]));
         // keys 8j+2t and 8j+2t+1; output column c of tile dn is d = 4c + dn, so lane column g reads d = 4g .. 4g+3
-        const float4 va = *reinterpret_cast<const float4*>(Vs + (8 * j + 2 * t) * WA_STRIDE + 4 * g);
-        const float4 vb = *reinterpret_cast<const float4*>(Vs + (8 * j + 2 * t + 1) * WA_STRIDE + 4 * g);
+        const float4 va = R::ld4v(Vs + (8 * j + 2 * t) * PITCH, 4 * g);
+        const float4 vb = R::ld4v(Vs + (8 * j + 2 * t + 1) * PITCH, 4 * g);
         mma_tf32_16x8x8(o[0], p0, p1, p2, p3, __float_as_uint(va.x), __float_as_uint(vb.x));
         mma_tf32_16x8x8(o[1], p0, p1, p2, p3, __float_as_uint(va.y), __float_as_uint(vb.y));
         mma_tf32_16x8x8(o[2], p0, p1, p2, p3, __float_as_uint(va.z), __float_as_uint(vb.z));
@@ -666,20 +697,20 @@ __global__ void __launch_bounds__(WA_ITEMS * 64, 2) winattn_kernel(const svx_win
       }
       // accumulator column 2t / 2t+1 of tile dn is d = 8t + dn / 8t + 4 + dn: the lane owns d = 8t .. 8t+7 of its rows
       const float inv0 = __frcp_rn(sum0), inv1 = __frcp_rn(sum1);
-      float4* out4 = reinterpret_cast<float4*>(d.out + head * HD) + 2 * t;
+      T* outh = reinterpret_cast<T*>(d.out) + head * HD + 8 * t;
       if (r0 < WT) {
-        float4* dst = out4 + stok[r0] * Cq;
-        dst[0] = make_float4(maybe_round(o[0][0] * inv0, d.round_tf32), maybe_round(o[1][0] * inv0, d.round_tf32),
-                             maybe_round(o[2][0] * inv0, d.round_tf32), maybe_round(o[3][0] * inv0, d.round_tf32));
-        dst[1] = make_float4(maybe_round(o[0][1] * inv0, d.round_tf32), maybe_round(o[1][1] * inv0, d.round_tf32),
-                             maybe_round(o[2][1] * inv0, d.round_tf32), maybe_round(o[3][1] * inv0, d.round_tf32));
+        const float v[8] = {maybe_round(o[0][0] * inv0, d.round_tf32), maybe_round(o[1][0] * inv0, d.round_tf32),
+                            maybe_round(o[2][0] * inv0, d.round_tf32), maybe_round(o[3][0] * inv0, d.round_tf32),
+                            maybe_round(o[0][1] * inv0, d.round_tf32), maybe_round(o[1][1] * inv0, d.round_tf32),
+                            maybe_round(o[2][1] * inv0, d.round_tf32), maybe_round(o[3][1] * inv0, d.round_tf32)};
+        R::st8(outh + (size_t)stok[r0] * d.C, v);
       }
       if (r1 < WT) {
-        float4* dst = out4 + stok[r1] * Cq;
-        dst[0] = make_float4(maybe_round(o[0][2] * inv1, d.round_tf32), maybe_round(o[1][2] * inv1, d.round_tf32),
-                             maybe_round(o[2][2] * inv1, d.round_tf32), maybe_round(o[3][2] * inv1, d.round_tf32));
-        dst[1] = make_float4(maybe_round(o[0][3] * inv1, d.round_tf32), maybe_round(o[1][3] * inv1, d.round_tf32),
-                             maybe_round(o[2][3] * inv1, d.round_tf32), maybe_round(o[3][3] * inv1, d.round_tf32));
+        const float v[8] = {maybe_round(o[0][2] * inv1, d.round_tf32), maybe_round(o[1][2] * inv1, d.round_tf32),
+                            maybe_round(o[2][2] * inv1, d.round_tf32), maybe_round(o[3][2] * inv1, d.round_tf32),
+                            maybe_round(o[0][3] * inv1, d.round_tf32), maybe_round(o[1][3] * inv1, d.round_tf32),
+                            maybe_round(o[2][3] * inv1, d.round_tf32), maybe_round(o[3][3] * inv1, d.round_tf32)};
+        R::st8(outh + (size_t)stok[r1] * d.C, v);
       }
     }
   }
@@ -1125,17 +1156,21 @@ int winattn_launch(const svx_winattn_desc& d, void* stream) {
   const long long cap = (2LL * kSmCount + d.heads - 1) / d.heads;   // two resident CTAs per SM over all heads
   if (per_head > cap) per_head = cap;
   if (per_head < 1) per_head = 1;
-  static bool configured = false;
-  if (!configured) {
-    SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
-    SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
-    configured = true;
-  }
+  SVX_REQUIRE(d.dtype == 0 || (d.dtype == SVX_DT_BF16 && d.C % 8 == 0), "window_attention: qkv and out share one storage type");
+  // (per device: a process may drive several GPUs)
+  SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
+  SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
+  SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel<false, bf16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
+  SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel<true, bf16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
   const int grid = (int)(per_head * d.heads);
-  if (d.shift > 0)
-    winattn_kernel<true><<<grid, WA_ITEMS * 64, WA_SMEM, (cudaStream_t)stream>>>(d, (int)per_head);
-  else
-    winattn_kernel<false><<<grid, WA_ITEMS * 64, WA_SMEM, (cudaStream_t)stream>>>(d, (int)per_head);
+  const bool bf = d.dtype == SVX_DT_BF16;
+  if (d.shift > 0) {
+    if (bf) winattn_kernel<true, bf16_t><<<grid, WA_ITEMS * 64, WA_SMEM, (cudaStream_t)stream>>>(d, (int)per_head);
+    else winattn_kernel<true, float><<<grid, WA_ITEMS * 64, WA_SMEM, (cudaStream_t)stream>>>(d, (int)per_head);
+  } else {
+    if (bf) winattn_kernel<false, bf16_t><<<grid, WA_ITEMS * 64, WA_SMEM, (cudaStream_t)stream>>>(d, (int)per_head);
+    else winattn_kernel<false, float><<<grid, WA_ITEMS * 64, WA_SMEM, (cudaStream_t)stream>>>(d, (int)per_head);
+  }
   SVX_LAUNCH_OK("winattn_kernel");
   return 0;
 }

@@ -57,6 +57,15 @@ def choose_block_n(n, rows=None, gather=False, heavy_epilogue=False, k=None):
     return best
 
 
+def esize_of(dtype):
+    return 2 if dtype == torch.bfloat16 else 4
+
+
+def to_operand(t, dtype):
+    """values as the tensor cores will read them: TF32-rounded fp32, or bf16 (round to nearest even)"""
+    return t.to(torch.bfloat16).contiguous() if dtype == torch.bfloat16 else tf32_round(t)
+
+
 def mlp_fusable(c, hidden):
     """shapes the fused MLP kernel (svx_mlp.cu) is instantiated for: Swin stages 0 and 1"""
     return c in (96, 192) and hidden == 4 * c and not os.environ.get("SVX_NO_MLP_FUSION")
@@ -99,6 +108,18 @@ class Act:
         return self.buf.shape[-1]
 
     @property
+    def dtype(self):
+        return self.buf.dtype
+
+    @property
+    def esize(self):
+        return self.buf.element_size()
+
+    @property
+    def bf16(self):
+        return self.buf.dtype == torch.bfloat16
+
+    @property
     def pixels(self):
         return self.N * self.D * self.H * self.W
 
@@ -116,24 +137,30 @@ class WeightPack:
     """Prepared weights of one contraction.  The N tile (and with it the zero padding of W to [Npad, Kpad]) is fixed
     lazily by `finalize`, when the op that uses the pack knows its row count and operand mode."""
 
-    def __init__(self, W, bias, N, K, block_n=None):
-        self.raw_W, self.raw_bias = W, bias     # [n_rows, K] tf32-rounded / [n_rows]
+    def __init__(self, W, bias, N, K, block_n=None, prepared=False):
+        self.raw_W, self.raw_bias = W, bias     # [n_rows, K] fp32 (not yet rounded unless `prepared`) / [n_rows]
         self.N, self.K, self.block_n = N, K, block_n
         self.W = self.bias = None
-        if block_n is not None:
+        self.dtype = torch.float32
+        self.prepared = prepared
+        if prepared:   # already in the kernel's final layout and rounding (the slab packs)
             self.finalize()
 
-    def finalize(self, rows=None, gather=False, heavy_epilogue=False):
+    def finalize(self, rows=None, gather=False, heavy_epilogue=False, dtype=torch.float32):
+        """fixes the N tile, pads to [Npad, Kpad] (Kpad: whole 128-byte k-chunks) and rounds to the operand type"""
         if self.W is not None:
+            assert self.dtype == dtype, "a weight pack serves one operand type"
             return self
+        self.dtype = dtype
         bn = self.block_n or choose_block_n(self.N, rows, gather, heavy_epilogue, self.K)
         n, k = self.raw_W.shape
-        npad, kpad = round_up(max(n, self.N), bn), round_up(k, 32)
+        npad, kpad = round_up(max(n, self.N), bn), round_up(k, 128 // esize_of(dtype))
+        raw = self.raw_W if self.prepared else to_operand(self.raw_W, dtype)
         if (npad, kpad) == (n, k):
-            self.W = self.raw_W.contiguous()
+            self.W = raw.contiguous()
         else:
-            self.W = torch.zeros(npad, kpad, dtype=torch.float32, device=self.raw_W.device)
-            self.W[:n, :k] = self.raw_W
+            self.W = torch.zeros(npad, kpad, dtype=dtype, device=self.raw_W.device)
+            self.W[:n, :k] = raw
         self.bias = torch.zeros(npad, dtype=torch.float32, device=self.raw_W.device)
         if self.raw_bias is not None:
             self.bias[:self.raw_bias.numel()] = self.raw_bias
@@ -143,7 +170,7 @@ class WeightPack:
 
     @property
     def Kpad(self):
-        return round_up(self.K, 32)
+        return self.W.shape[1] if self.W is not None else round_up(self.K, 128 // esize_of(self.dtype))
 
     @property
     def Npad(self):
@@ -153,7 +180,7 @@ class WeightPack:
 def pack_matrix(w2d, bias, device, block_n=None, n_logical=None):
     """w2d: [N, K] fp32 (already folded / permuted)."""
     n, k = w2d.shape
-    W = tf32_round(w2d.detach().to(device=device, dtype=torch.float32))
+    W = w2d.detach().to(device=device, dtype=torch.float32).contiguous()   # rounded to the operand type by finalize()
     b = bias.detach().to(device=device, dtype=torch.float32) if bias is not None else None
     return WeightPack(W, b, n_logical or n, k, block_n)
 
@@ -204,7 +231,7 @@ def pack_conv3_slab(weight, bias, bn, device, n_logical=None):
     W = tf32_round((W * ws).reshape(48, 288)).to(device)
     bb = torch.zeros(48, dtype=torch.float32, device=device)
     bb[:cout] = b.to(device)
-    pack = WeightPack(W, bb, n_logical or cout, 288, 48)   # [48, 288] is already the padded layout
+    pack = WeightPack(W, bb, n_logical or cout, 288, 48, prepared=True)   # [48, 288] is already the padded layout
     pack.acc_scale = 1.0 / ws
     return pack
 
@@ -264,9 +291,13 @@ CONVT_FUSED_TAPS = [(a - 1, b - 1, c - 1) for a in range(3) for b in range(3) fo
 class Plan:
     """A recorded op list bound to fixed device buffers."""
 
-    def __init__(self, device, lib=None):
+    def __init__(self, device, lib=None, dtype=torch.float32):
+        """dtype: storage type of the activations this plan allocates and operand type of its contractions
+        (torch.float32: TF32 tensor cores; torch.bfloat16: bf16 operands, fp32 accumulation)"""
         self.lib = lib or _lib.get()
         self.device = torch.device(device)
+        self.dtype = dtype
+        assert dtype in (torch.float32, torch.bfloat16)
         self.handle = C.c_void_p(self.lib.svx_plan_create())
         if not self.handle:
             raise _lib.SvxError("svx_plan_create failed")
@@ -291,12 +322,19 @@ class Plan:
     def zeros(self, *shape, dtype=torch.float32):
         return self.hold(torch.zeros(*shape, dtype=dtype, device=self.device))
 
-    def new_act(self, N, D, H, W, C, Cs=None, zero=False, pad=(0, 0, 0)):
+    def new_act(self, N, D, H, W, C, Cs=None, zero=False, pad=(0, 0, 0), dtype=None):
         """D, H, W are the data extents; `pad` adds a zero border that producers never write (flat-conv inputs)"""
         Cs = Cs or C
         Dp, Hp, Wp = D + 2 * pad[0], H + 2 * pad[1], W + 2 * pad[2]
-        buf = (self.zeros if (zero or any(pad)) else self.empty)(N * Dp * Hp * Wp, Cs)
+        buf = (self.zeros if (zero or any(pad)) else self.empty)(N * Dp * Hp * Wp, Cs, dtype=dtype or self.dtype)
         return Act(buf, N, Dp, Hp, Wp, C, 0, tuple(pad))
+
+    @staticmethod
+    def _dt(x, out):
+        """SVX_DT_* bits of a non-contraction op (x / out: Act or tensor)"""
+        xb = (x.buf if isinstance(x, Act) else x).dtype == torch.bfloat16
+        ob = (out.buf if isinstance(out, Act) else out).dtype == torch.bfloat16
+        return (_lib.DT_IN_BF16 if xb else 0) | (_lib.DT_OUT_BF16 if ob else 0)
 
     def hold(self, t):
         """keep every tensor whose address is baked into an op alive as long as the plan"""
@@ -370,9 +408,10 @@ class Plan:
         d.ntaps = len(taps)
         lo = [min(t[a] for t in taps) for a in range(3)]
         up = [lo[a] + (rows_dhw[a] - 1) * stride[a] - ((x.D, x.H, x.W)[a] - 1) for a in range(3)]
-        # whole 32-channel boxes, or 4-channel pixels (the image stems: eight 16-byte taps per k-chunk)
-        narrow_ok = (cin == 4 or (cin == 8 and len(taps) % 4 == 0)) and not os.environ.get("SVX_NO_IM2COL_NARROW")
-        tma = ((cin % 32 == 0 or narrow_ok)
+        # whole 128-byte boxes, or 16-byte pixels (the image stems: eight taps per k-chunk) / 32-byte pixels (four taps)
+        es = x.esize
+        narrow_ok = cin * es == 16 or (cin * es == 32 and len(taps) % 4 == 0)
+        tma = (((cin * es) % 128 == 0 or narrow_ok)
                and len(taps) <= 64 and all(-16 <= v <= 15 for v in lo + up) and not os.environ.get("SVX_NO_IM2COL"))
         if tma:
             d.a_mode = A_IM2COL
@@ -385,14 +424,20 @@ class Plan:
         return tma
 
     def _fill_epilogue(self, d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out,
-                       res_via_mma=False):
-        pack.finalize(rows=d.M, gather=(d.a_mode == A_GATHER), heavy_epilogue=(act == ACT_GELU))
+                       res_via_mma=False, op_dtype=torch.float32):
+        pack.finalize(rows=d.M, gather=(d.a_mode == A_GATHER), heavy_epilogue=(act == ACT_GELU), dtype=op_dtype)
+        assert pack.dtype == op_dtype, "weights and the A operand must share the operand type"
+        bf = op_dtype == torch.bfloat16
+        d.operand_kind = _lib.OPERAND_BF16 if bf else d.operand_kind
+        if out.bf16:
+            assert bf, "bf16 outputs come from bf16-operand contractions"
+            d.io_flags |= _lib.IO_OUT_BF16
         d.W = pack.W.data_ptr()
         if res_via_mma:
             # the residual is added by the tensor cores: block_n identity columns appended to every weight row
             assert residual is not None and not res_after_act and pack.N % pack.block_n == 0
             if getattr(pack, "W_ext", None) is None:
-                eye = torch.zeros(pack.Npad, pack.block_n, dtype=torch.float32, device=pack.W.device)
+                eye = torch.zeros(pack.Npad, pack.block_n, dtype=pack.W.dtype, device=pack.W.device)
                 idx = torch.arange(pack.Npad, device=pack.W.device)
                 eye[idx, idx % pack.block_n] = 1.0
                 pack.W_ext = torch.cat([pack.W, eye], dim=1).contiguous()
@@ -410,8 +455,10 @@ class Plan:
         d.epi_mode = EPI_STD
         if residual is not None:
             assert (residual.Cs == out.Cs and residual.c0 == out.c0 and residual.pixels == out.pixels
-                    and residual.pad == out.pad), "residual must share the output layout"
+                    and residual.pad == out.pad and residual.dtype == out.dtype), "residual must share the output layout"
             d.residual = self.hold(residual).buf.data_ptr()
+            if residual.bf16:
+                d.io_flags |= _lib.IO_RES_BF16
             d.res_after_act = 1 if res_after_act else 0
         self.hold(pack.W)
         self.hold(pack.bias)
@@ -425,20 +472,21 @@ class Plan:
         oD, oH, oW = out.inner
         assert x.C == pack.K and x.pixels == out.N * oD * oH * oW, (x.C, pack.K, out.C, pack.N)
         assert (out.C * 8 == pack.N) if pool8 else (out.C >= pack.N), (out.C, pack.N)
-        assert x.c0 % 4 == 0 and x.Cs % 4 == 0 and not any(x.pad), "plain operands are dense matrices"
+        e16 = 16 // x.esize
+        assert x.c0 % e16 == 0 and x.Cs % e16 == 0 and not any(x.pad), "plain operands are dense matrices"
         d = _lib.GemmDesc()
         d.M = x.pixels
         d.a_mode = A_PLAIN
-        d.A = self.hold(x).buf.data_ptr() + 4 * x.c0
+        d.A = self.hold(x).buf.data_ptr() + x.esize * x.c0
         d.lda = x.Cs
         d.out_D, d.out_H, d.out_W = oD, oH, oW
         self._fill_epilogue(d, pack, out, None, act, act_param, residual, res_after_act, out_scale, round_out,
-                            res_via_mma=res_via_mma)
+                            res_via_mma=res_via_mma, op_dtype=x.dtype)
         if pool8:
             d.epi_mode = EPI_POOL8
         n_out = pack.N // 8 if pool8 else pack.N
         self._add("gemm", d, name or "linear", 2.0 * d.M * pack.N * pack.K,
-                  4.0 * (d.M * pack.K + d.M * n_out * (2 if residual is not None else 1) + pack.N * pack.K))
+                  x.esize * (d.M * pack.K + pack.N * pack.K) + out.esize * d.M * n_out * (2 if residual is not None else 1))
         return out
 
     def mlp(self, x, pack1, pack2, out, residual, round_out=False, name=None, ln=None):
@@ -471,12 +519,14 @@ class Plan:
              residual=None, res_after_act=True, out_scale=1.0, round_out=False, name=None, epi_tail=None):
         """Implicit-GEMM convolution.  rows_dhw: extents the GEMM rows run over (default: out D,H,W)."""
         cin_pad = pack.K // len(taps)
-        assert cin_pad * len(taps) == pack.K and cin_pad % 4 == 0 and cin_pad >= x.C
-        assert x.c0 % 4 == 0 and x.Cs % 4 == 0 and x.c0 + cin_pad <= x.Cs, (x.c0, cin_pad, x.Cs)
+        e16 = 16 // x.esize
+        assert cin_pad * len(taps) == pack.K and cin_pad % e16 == 0 and cin_pad >= x.C
+        assert x.c0 % e16 == 0 and x.Cs % e16 == 0 and x.c0 + cin_pad <= x.Cs, (x.c0, cin_pad, x.Cs)
         assert not any(x.pad), "gather mode reads unpadded tensors (use conv_flat for padded ones)"
         d = _lib.GemmDesc()
         self._gather_operand(d, x, cin_pad, taps, rows_dhw or out.inner, stride)
-        self._fill_epilogue(d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out)
+        self._fill_epilogue(d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out,
+                            op_dtype=x.dtype)
         if epi_tail is not None:
             aux, out2, map2 = epi_tail
             d.epi_mode = EPI_DEC_TAIL
@@ -484,7 +534,7 @@ class Plan:
             d.epi_out2 = self.hold(out2).data_ptr()
             d.o2_base, d.o2_sn, d.o2_sd, d.o2_sh, d.o2_sw = map2
         self._add("gemm", d, name or "conv", 2.0 * d.M * pack.N * pack.K,
-                  4.0 * (x.pixels * x.C + d.M * pack.N * (2 if residual is not None else 1) + pack.N * pack.K))
+                  x.esize * (x.pixels * x.C + pack.N * pack.K) + out.esize * d.M * pack.N * (2 if residual is not None else 1))
         return out
 
     def convT_fused(self, x, pack, out, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True, out_scale=1.0,
@@ -524,7 +574,7 @@ class Plan:
         `taps` are non-negative (dd, dh, dw) offsets from the window corner in padded coordinates; `valid` =
         number of window corners per axis that are real outputs (default: the extents of `out`)."""
         cin = pack.K // len(taps)
-        assert cin * len(taps) == pack.K and cin % 32 == 0 and cin == x.C and pack.Kpad == pack.K, (cin, x.C, pack.K)
+        assert cin * len(taps) == pack.K and (cin * x.esize) % 128 == 0 and cin == x.C, (cin, x.C, pack.K)
         assert all(min(t) >= 0 for t in taps)
         vD, vH, vW = valid or out.inner
         d = _lib.GemmDesc()
@@ -542,9 +592,12 @@ class Plan:
         host = (C.c_int32 * (4 * len(taps)))(*[v for t in taps for v in (t[0], t[1], t[2], 0)])
         self.keep[id(host)] = host
         d.taps_host = C.cast(host, C.c_void_p)
-        self._fill_epilogue(d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out)
+        self._fill_epilogue(d, pack, out, out_map, act, act_param, residual, res_after_act, out_scale, round_out,
+                            op_dtype=x.dtype)
+        assert pack.Kpad == pack.K
         self._add("gemm", d, name or "conv_flat", 2.0 * x.N * vD * vH * vW * pack.N * pack.K,
-                  4.0 * (x.N * vD * vH * vW * (cin + pack.N * (2 if residual is not None else 1)) + pack.N * pack.K))
+                  x.esize * (x.N * vD * vH * vW * cin + pack.N * pack.K)
+                  + out.esize * x.N * vD * vH * vW * pack.N * (2 if residual is not None else 1))
         return out
 
     def conv3_slab(self, x, pack, out, cin_live, act=ACT_NONE, act_param=0.0, residual=None, res_after_act=True,
@@ -606,7 +659,8 @@ class Plan:
         d.OD, d.OH, d.OW = out.D, out.H, out.W
         d.mode = mode
         d.round_tf32 = 1 if round_out else 0
-        self._add("pool", d, name, 0.0, 4.0 * x.C * (x.pixels + out.pixels))
+        d.dtype = self._dt(x, out)
+        self._add("pool", d, name, 0.0, x.esize * x.C * (x.pixels + out.pixels))
         return out
 
     def layernorm_rows(self, x, gamma, beta, out, merge_hw=None, eps=1e-5, round_out=True, name=None):
@@ -618,7 +672,8 @@ class Plan:
             d.merge, d.H, d.W = 1, merge_hw[0], merge_hw[1]
         d.eps = eps
         d.round_tf32 = 1 if round_out else 0
-        self._add("layernorm_rows", d, name, 0.0, 8.0 * out.pixels * out.C)
+        d.dtype = self._dt(x, out)
+        self._add("layernorm_rows", d, name, 0.0, 2.0 * x.esize * out.pixels * out.C)
         return out
 
     def layernorm_sample(self, x, gamma, beta, out, eps=1e-5, round_out=True, name=None):
@@ -628,7 +683,8 @@ class Plan:
         d.N, d.L = x.N, x.D * x.H * x.W * x.Cs
         d.eps = eps
         d.round_tf32 = 1 if round_out else 0
-        self._add("layernorm_sample", d, name, 0.0, 8.0 * d.N * d.L)
+        d.dtype = self._dt(x, out)
+        self._add("layernorm_sample", d, name, 0.0, 2.0 * x.esize * d.N * d.L)
         return out
 
     def window_attention(self, qkv, out, bias, H, W, heads, shift, scale, round_out=True, name=None):
@@ -636,7 +692,8 @@ class Plan:
         d.qkv, d.out, d.bias = self.hold(qkv).buf.data_ptr(), self.hold(out).buf.data_ptr(), self.hold(bias).data_ptr()
         d.N, d.H, d.W, d.C, d.heads, d.shift, d.scale = qkv.N, H, W, out.C, heads, shift, scale
         d.round_tf32 = 1 if round_out else 0
-        self._add("window_attention", d, name, 4.0 * qkv.N * H * W * 49 * out.C, 16.0 * qkv.N * H * W * out.C)
+        d.dtype = self._dt(qkv, out)
+        self._add("window_attention", d, name, 4.0 * qkv.N * H * W * 49 * out.C, 4.0 * qkv.esize * qkv.N * H * W * out.C)
         return out
 
     def dwconv(self, x, w, bias, out, k, round_out=True, name=None):
@@ -645,6 +702,7 @@ class Plan:
         d.bias = self.hold(bias).data_ptr() if bias is not None else None
         d.N, d.H, d.W, d.C, d.k, d.OH, d.OW = x.N, x.H, x.W, x.C, k, out.H, out.W
         d.round_tf32 = 1 if round_out else 0
+        d.dtype = self._dt(x, out)
         self._add("dwconv", d, name)
         return out
 
@@ -653,6 +711,7 @@ class Plan:
         d.qkv, d.out = self.hold(qkv).buf.data_ptr(), self.hold(out).buf.data_ptr()
         d.B, d.V, d.P, d.R, d.heads, d.scale = B, V, qkv.H * qkv.W, out.C, heads, scale
         d.round_tf32 = 1 if round_out else 0
+        d.dtype = self._dt(qkv, out)
         self._add("view_attention", d, name)
         return out
 
@@ -662,6 +721,8 @@ class Plan:
         d.skip = self.hold(skip).buf.data_ptr() if skip is not None else None
         d.N, d.IH, d.IW, d.OH, d.OW, d.C = x.N, x.H, x.W, out.H, out.W, x.C
         d.round_tf32 = 1 if round_out else 0
+        d.dtype = self._dt(x, out)
+        assert skip is None or skip.dtype == x.dtype
         self._add("bilinear_add", d, name)
         return out
 
@@ -711,7 +772,8 @@ class Plan:
         d.N, d.C, d.P, d.Cs = N, Cc, P, Cs
         d.to_channels_last = 1 if to_channels_last else 0
         d.round_tf32 = 1 if round_out else 0
-        self._add("transpose", d, name, 0.0, 4.0 * N * P * (Cc + Cs))
+        d.dtype = self._dt(src, dst)
+        self._add("transpose", d, name, 0.0, N * P * (src.element_size() * Cc + dst.element_size() * Cs))
         return dst
 
 

@@ -25,30 +25,36 @@ def _dev(plan):
 # --------------------------------------------------------------------------------------------------
 # ResNet-50 trunk: torchvision resnet50 children[:7]  (models/encoder.py:22-23,119)
 # --------------------------------------------------------------------------------------------------
-IMG_PITCH = 226   # staged image rows: one zero pixel, 224 pixels, one zero pixel
+def img_layout(plan):
+    """(row pitch, left zero pixels) of the staged image.  fp32: 226 / 1 -- Swin's patch embedding reads 16-byte pixels,
+    the ResNet stem the 8-channel pixel pairs (2j-1, 2j) of its stride-2 window.  bf16: a pixel is 8 bytes, below the TMA
+    unit's 16-byte minimum, so BOTH stems read pixel pairs and the image starts at an even staged column: 228 / 2."""
+    return (228, 2) if plan.dtype == torch.bfloat16 else (226, 1)
 
 
 def stage_image(plan, img, N):
-    """[N,3,224,224] NCHW fp32 tensor -> Act [N,224,226,4] (channels-last, zero fourth channel, TF32-rounded, one zero
-    pixel left and right of every row): Swin's patch embedding reads it as 16-byte pixels, the ResNet stem as the
-    8-channel pixel pairs (2j-1, 2j) of its stride-2 window.  Idempotent per plan."""
+    """[N,3,224,224] NCHW fp32 tensor -> Act [N,224,pitch,4] (channels-last, zero fourth channel, rounded to the plan's
+    operand type, zero pixels left and right of every row; see img_layout).  Idempotent per plan."""
     if isinstance(img, Act):
         return img
     key = ("nhwc4", img.data_ptr())
     if key not in plan.taps:
-        a = plan.new_act(N, 1, 224, IMG_PITCH, 4, zero=True)
-        plan.transpose(img, a.buf, N, 3, 224 * 224, 4, True, round_out=True, name="image.nhwc4", rows=(224, IMG_PITCH, 1))
+        pitch, x0 = img_layout(plan)
+        a = plan.new_act(N, 1, 224, pitch, 4, zero=True)
+        plan.transpose(img, a.buf, N, 3, 224 * 224, 4, True, round_out=True, name="image.nhwc4", rows=(224, pitch, x0))
         plan.taps[key] = a
     return plan.taps[key]
 
 
-def pack_stem_pairs(conv1, bn1, dev):
-    """ResNet conv1 (7x7, stride 2, pad 3) over pixel pairs: output ow reads padded pixels 2(ow-1) + kw, i.e. pairs
-    (ow-1) + kw//2, element kw%2 -> K = 7 kh x 4 pair taps x (2 pixels x 4 channels) = 224; kw = 7 and channel 3 are zero."""
+def pack_stem_pairs(conv1, bn1, dev, x0=1):
+    """ResNet conv1 (7x7, stride 2, pad 3) over pixel pairs.  Image column 2ow - 3 + kw sits at staged column
+    2ow - 3 + kw + x0 = 2(ow - 1) + s with s = kw + x0 - 1, i.e. pair (ow - 1) + s//2, element s%2 -> K = 7 kh x 4 pair
+    taps x (2 pixels x 4 channels) = 224; the unused eighth pixel slot and channel 3 carry zero weights."""
     w, b = E.fold_bn(conv1.weight, conv1.bias, bn1)            # [64, 3, 7, 7]
     W = torch.zeros(64, 7, 4, 2, 4, dtype=torch.float32, device=w.device)
     for kw in range(7):
-        W[:, :, kw // 2, kw % 2, :3] = w[:, :, :, kw].permute(0, 2, 1)
+        s_ = kw + x0 - 1
+        W[:, :, s_ // 2, s_ % 2, :3] = w[:, :, :, kw].permute(0, 2, 1)
     taps = [(0, kh - 3, pt - 1) for kh in range(7) for pt in range(4)]
     return E.pack_matrix(W.reshape(64, 224), b, dev), taps
 
@@ -59,9 +65,10 @@ def lower_resnet_trunk(plan, resnet, img, N):
     conv1, bn1 = resnet[0], resnet[1]
     x4 = stage_image(plan, img, N)
     # 7x7 s2 p3 stem as an implicit GEMM over 28 pixel-pair taps of 8 channels (32-byte TMA im2col boxes): K = 224
-    pairs = Act(x4.buf.view(-1, 8), N, 1, 224, IMG_PITCH // 2, 8)
+    pitch, x0 = img_layout(plan)
+    pairs = Act(x4.buf.view(-1, 8), N, 1, 224, pitch // 2, 8)
     stem = plan.new_act(N, 1, 112, 112, 64)
-    pk, taps = pack_stem_pairs(conv1, bn1, dev)
+    pk, taps = pack_stem_pairs(conv1, bn1, dev, x0)
     plan.conv(pairs, pk, taps, stem, stride=(1, 2, 1), act=ACT_RELU, name="resnet.stem")
     x = plan.new_act(N, 1, 56, 56, 64)
     plan.pool(stem, x, (1, 3, 3), (1, 2, 2), (0, 1, 1), POOL_MAX, round_out=True, name="resnet.maxpool")
@@ -76,7 +83,8 @@ def _bottleneck(plan, blk, x, name):
     s = blk.conv2.stride[0]
     width, cout = blk.conv1.out_channels, blk.conv3.out_channels
     H2 = (x.H + 2 - 3) // s + 1
-    flat = s == 1 and width % 32 == 0   # stride-1 3x3: TMA-fed "flat" conv over a zero-padded conv1 output
+    # stride-1 3x3: TMA-fed "flat" conv over a zero-padded conv1 output (whole 128-byte channel chunks)
+    flat = s == 1 and (width * E.esize_of(plan.dtype)) % 128 == 0
     t1 = plan.new_act(x.N, 1, x.H, x.W, width, pad=(0, 1, 1) if flat else (0, 0, 0))
     plan.linear(x, E.pack_conv(blk.conv1.weight, None, blk.bn1, dev), t1, act=ACT_RELU, round_out=True, name=name + ".conv1")
     t2 = plan.new_act(x.N, 1, H2, H2, width)
@@ -127,10 +135,23 @@ def lower_swin(plan, swin, img, N, stage_tail=None):
     pe = model.patch_embed
     x4 = stage_image(plan, img, N)
     emb = plan.new_act(N, 1, 56, 56, 96)
-    # patch embedding: 4x4 s4 conv = 16 one-pixel taps, K = 64 (image column x sits at staged column x + 1)
-    plan.conv(x4, E.pack_conv(pe.proj.weight, pe.proj.bias, None, dev, cin_pad=4),
-              [(0, kh, kw + 1) for kh in range(4) for kw in range(4)], emb, stride=(1, 4, 4), rows_dhw=(1, 56, 56),
-              name="swin.patch_embed.proj")
+    pitch, x0 = img_layout(plan)
+    if plan.dtype == torch.bfloat16:
+        # patch embedding over pixel pairs (16 bytes): image columns 4j .. 4j+3 are staged columns 4j+2 .. 4j+5 = pairs
+        # 2j+1, 2j+2 -> 4 kh x 2 pair taps of 8 channels, K = 64, stride 2 in pair units
+        w = pe.proj.weight.detach().float()                                  # [96, 3, 4, 4]
+        Wp = torch.zeros(96, 4, 2, 2, 4, dtype=torch.float32, device=w.device)   # [co, kh, pair, pixel, channel]
+        for kw in range(4):
+            Wp[:, :, kw // 2, kw % 2, :3] = w[:, :, :, kw].permute(0, 2, 1)
+        pairs = Act(x4.buf.view(-1, 8), N, 1, 224, pitch // 2, 8)
+        plan.conv(pairs, E.pack_matrix(Wp.reshape(96, 64), pe.proj.bias, dev),
+                  [(0, kh, x0 // 2 + pr) for kh in range(4) for pr in range(2)], emb, stride=(1, 4, 2), rows_dhw=(1, 56, 56),
+                  name="swin.patch_embed.proj")
+    else:
+        # patch embedding: 4x4 s4 conv = 16 one-pixel taps, K = 64 (image column x sits at staged column x + 1)
+        plan.conv(x4, E.pack_conv(pe.proj.weight, pe.proj.bias, None, dev, cin_pad=4),
+                  [(0, kh, kw + x0) for kh in range(4) for kw in range(4)], emb, stride=(1, 4, 4), rows_dhw=(1, 56, 56),
+                  name="swin.patch_embed.proj")
     x = plan.new_act(N, 1, 56, 56, 96)
     plan.layernorm_rows(emb, pe.norm.weight.detach().float().to(dev), pe.norm.bias.detach().float().to(dev), x,
                         eps=pe.norm.eps, round_out=False, name="swin.patch_embed.norm")
@@ -162,7 +183,8 @@ def lower_swin(plan, swin, img, N, stage_tail=None):
             plan.linear(att, E.pack_matrix(blk.attn.proj.weight, blk.attn.proj.bias, dev), x1, residual=x,
                         name=nm + ".proj")
             g2, b2 = blk.norm2.weight.detach().float().to(dev), blk.norm2.bias.detach().float().to(dev)
-            fused = E.mlp_fusable(Cc, blk.mlp.fc1.out_features)
+            # (the fused MLP kernel exists for fp32 / TF32 storage; bf16 plans run fc1 / fc2 as two contractions)
+            fused = E.mlp_fusable(Cc, blk.mlp.fc1.out_features) and plan.dtype == torch.float32
             x = plan.new_act(N, 1, H, H, Cc)
             if fused and E.mlp_ln_fusable(Cc):
                 # stage 0: norm2 -> fc1 -> GELU -> fc2 -> + x1 in one kernel (x1 is read once, normalised in shared memory)
@@ -318,7 +340,8 @@ def lower_encoder(plan, enc, img, B, V):
     seq = [("fusion_layer", enc.fusion_layer), ("layer1", enc.layer1), ("layer2", enc.layer2), ("layer3", enc.layer3)]
     for li, (nm, layer) in enumerate(seq):
         last = li == len(seq) - 1
-        o = plan.new_act(N, 1, 7, 7, 256, pad=(0, 0, 0) if last else (0, 1, 1))
+        # the module output is fp32 whatever the plan's storage type (the decoder reads it)
+        o = plan.new_act(N, 1, 7, 7, 256, pad=(0, 0, 0) if last else (0, 1, 1), dtype=torch.float32 if last else None)
         pk = E.pack_conv(layer[0].weight, layer[0].bias, layer[1], dev)
         if any(x.pad):   # zero-bordered input: one TMA box per filter tap
             plan.conv_flat(x, pk, E.conv_taps(1, 3, 3, 0, 0, 0), o, act=ACT_RELU, round_out=not last, name="encoder." + nm)

@@ -18,6 +18,11 @@ def _conv_bn_relu(cin, cout, stride):
 
 
 class Encoder(PlannedModule):
+    # "tf32" (default: fp32 activations, TF32 tensor cores, the reference's fp32 numerics within rtol 1e-3) or "bf16"
+    # (bf16 activation storage and tensor-core operands, fp32 accumulation / LayerNorm / softmax statistics; BASELINE
+    # configs[2]).  The module's input and output stay fp32 either way.  Set before the first forward.
+    compute_dtype = "tf32"
+
     def __init__(self, cfg):
         super().__init__()
         import torchvision
@@ -51,12 +56,16 @@ class Encoder(PlannedModule):
         return img.view(B, V, 3, 224, 224)
 
     def _get_plan(self, B, V, device):
+        if self.compute_dtype not in ("tf32", "bf16"):
+            raise ValueError(f"Encoder.compute_dtype must be 'tf32' or 'bf16', got {self.compute_dtype!r}")
+
         def build():
-            plan = E.Plan(device)
+            import torch
+            plan = E.Plan(device, dtype=torch.bfloat16 if self.compute_dtype == "bf16" else torch.float32)
             img = plan.empty(B * V, 3, 224, 224)
             return plan, img, graph.lower_encoder(plan, self, img, B, V)
 
-        return self._plan_for((B, V, str(device)), build)
+        return self._plan_for((B, V, str(device), self.compute_dtype), build)
 
     def forward(self, rendering_images):
         self._guard(rendering_images)

@@ -64,11 +64,15 @@ class Reconstructor:
     """Outputs: `forward` / `evaluate` return FRESH tensors (like the reference's modules) unless `zero_copy=True`, in
     which case they are views of plan-owned buffers that the next call with the same (B, V) overwrites."""
 
-    def __init__(self, cfg, encoder=None, decoder=None, merger=None, refiner=None, device="cuda", zero_copy=False):
+    def __init__(self, cfg, encoder=None, decoder=None, merger=None, refiner=None, device="cuda", zero_copy=False,
+                 dtype="tf32"):
+        """dtype: "tf32" (default) or "bf16" -- the encoder's storage / operand type (Encoder.compute_dtype); decoder,
+        merger and refiner compute in fp32 / TF32 either way"""
         self.cfg = cfg
         self.device = torch.device(device)
         self.zero_copy = zero_copy
         self.encoder = (encoder or Encoder(cfg)).eval().to(self.device)
+        self.encoder.compute_dtype = dtype
         self.decoder = (decoder or Decoder(cfg)).eval().to(self.device)
         self.merger = (merger or Merger(cfg)).eval().to(self.device) if cfg.NETWORK.USE_MERGER else None
         self.refiner = (refiner or Refiner(cfg)).eval().to(self.device) if cfg.NETWORK.USE_REFINER else None

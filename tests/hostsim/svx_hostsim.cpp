@@ -31,6 +31,23 @@ static inline float tf32_rna(float x) {  // cvt.rna.tf32.f32
   return x;
 }
 static inline float rnd(float x, int r) { return r ? tf32_rna(x) : x; }
+// bf16 storage (the encoder's reduced-precision mode): round-to-nearest-even on store, exact widening on load
+static inline float bf2f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float x; memcpy(&x, &u, 4); return x; }
+static inline uint16_t f2bf(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+// element i of a tensor stored as fp32 or bf16
+static inline float ldx(const void* p, long long i, bool bf) {
+  return bf ? bf2f(reinterpret_cast<const uint16_t*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+}
+static inline void stx(void* p, long long i, float v, bool bf) {
+  if (bf) reinterpret_cast<uint16_t*>(p)[i] = f2bf(v);
+  else reinterpret_cast<float*>(p)[i] = v;
+}
 
 static inline float act_fn(float x, int act, float slope) {
   switch (act) {
@@ -45,12 +62,18 @@ struct GemmPrepared { int unused; };
 int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
   *out = nullptr;
   SVX_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "gemm: empty problem");
-  SVX_REQUIRE(d.Kpad % 32 == 0 && d.Kpad >= d.K, "gemm: bad Kpad");
+  const bool bf = d.operand_kind == SVX_OPERAND_BF16;
+  const int BKE = bf ? 64 : 32, e16 = bf ? 8 : 4, esz = bf ? 2 : 4;
+  SVX_REQUIRE(d.Kpad % BKE == 0 && d.Kpad >= d.K, "gemm: bad Kpad");
+  SVX_REQUIRE(bf || d.io_flags == 0, "gemm: bf16 outputs need bf16 operands");
+  SVX_REQUIRE(!bf || (d.a_mode != SVX_A_SLAB3 && d.epi_mode == SVX_EPI_STD && d.N % 4 == 0), "gemm: bf16 operands: standard epilogue only");
+  SVX_REQUIRE(!d.residual || d.res_via_mma || (((d.io_flags & SVX_IO_RES_BF16) != 0) == ((d.io_flags & SVX_IO_OUT_BF16) != 0)),
+              "gemm: residual / output storage types differ");
   SVX_REQUIRE(d.Npad % d.block_n == 0 && d.Npad >= d.N, "gemm: bad Npad");
   if (d.a_mode == SVX_A_GATHER)
-    SVX_REQUIRE(d.Cin % 4 == 0 && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.K == d.ntaps * d.Cin, "gemm: bad gather");
+    SVX_REQUIRE(d.Cin % e16 == 0 && d.in_c0 % e16 == 0 && d.in_Cs % e16 == 0 && d.K == d.ntaps * d.Cin, "gemm: bad gather");
   else if (d.a_mode == SVX_A_IM2COL) {
-    SVX_REQUIRE((d.Cin == 4 || ((d.Cin == 8 || d.Cin % 32 == 0) && d.Kpad == d.K)) && d.in_c0 % 4 == 0 && d.in_Cs % 4 == 0 && d.K == d.ntaps * d.Cin &&
+    SVX_REQUIRE((d.Cin * esz == 16 || ((d.Cin * esz == 32 || d.Cin % BKE == 0) && d.Kpad == d.K)) && d.in_c0 % e16 == 0 && d.in_Cs % e16 == 0 && d.K == d.ntaps * d.Cin &&
                     d.taps_host && d.ntaps <= 64 && d.M % (d.out_D * d.out_H * d.out_W) == 0,
                 "gemm: bad im2col");
     const int in_ext[3] = {d.in_D, d.in_H, d.in_W}, out_ext[3] = {d.out_D, d.out_H, d.out_W};
@@ -64,7 +87,7 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     }
   }
   else if (d.a_mode == SVX_A_FLAT)
-    SVX_REQUIRE(d.Cin % 32 == 0 && d.K == d.ntaps * d.Cin && d.Kpad == d.K && d.taps_host && d.ntaps <= 64 &&
+    SVX_REQUIRE(d.Cin % BKE == 0 && d.in_Cs % e16 == 0 && d.K == d.ntaps * d.Cin && d.Kpad == d.K && d.taps_host && d.ntaps <= 64 &&
                     d.out_D == d.in_D && d.out_H == d.in_H && d.out_W == d.in_W && d.lda >= d.M,
                 "gemm: bad flat conv");
   else if (d.a_mode == SVX_A_SLAB3)
@@ -73,7 +96,8 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
                     d.lda > 0 && d.epi_mode == SVX_EPI_STD,
                 "gemm: bad slab conv");
   else
-    SVX_REQUIRE(d.lda % 4 == 0 && d.lda >= d.K, "gemm: bad lda");
+    SVX_REQUIRE(d.lda % e16 == 0 && d.lda >= d.K, "gemm: bad lda");
+  if (d.res_via_mma) SVX_REQUIRE(d.block_n % BKE == 0 && (!bf || (d.io_flags & SVX_IO_RES_BF16)), "gemm: bad res_via_mma");
   if (d.epi_mode == SVX_EPI_CONVT8)
     SVX_REQUIRE(d.a_mode != SVX_A_SLAB3 && d.cls_cout > 0 && d.N == 8 * d.cls_cout && (!d.epi_aux || (d.cls_cout == 8 && d.epi_out2)),
                 "gemm: bad transposed-convolution class epilogue");
@@ -114,8 +138,8 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
             for (int kw = 0; kw < 3; ++kw) {
               const long long row = (n * d.in_D + dd + kd) * HWp + (long long)(h + kh) * d.in_W + (w + kw);
               if (row >= d.lda) continue;
-              const float* px = d.A + row * d.in_Cs + d.in_c0;
-              const float* wr = d.W + (long long)(kw * 16 + co) * d.Kpad + (kd * 3 + kh) * 32;
+              const float* px = reinterpret_cast<const float*>(d.A) + row * d.in_Cs + d.in_c0;
+              const float* wr = reinterpret_cast<const float*>(d.W) + (long long)(kw * 16 + co) * d.Kpad + (kd * 3 + kh) * 32;
               for (int c = 0; c < live; ++c)
                 if (d.in_c0 + c < d.in_Cs) {
                   float a = tf32_trunc(px[c]);
@@ -124,12 +148,12 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
                 }
             }
         float v = acc * acc_scale + (d.bias ? d.bias[co] : 0.f);
-        const float res = d.residual ? d.residual[off + co] : 0.f;
+        const float res = d.residual ? reinterpret_cast<const float*>(d.residual)[off + co] : 0.f;
         if (d.residual && !d.res_after_act) v += res;
         v = act_fn(v, d.act, d.act_param);
         if (d.residual && d.res_after_act) v += res;
         v *= d.out_scale;
-        d.out[off + co] = rnd(v, d.round_tf32);
+        reinterpret_cast<float*>(d.out)[off + co] = rnd(v, d.round_tf32);
       }
     }
     if (f16 && saturated && d.range_flag) *d.range_flag |= 1;
@@ -137,6 +161,13 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
   }
   const long long rows_per_n = (long long)d.out_D * d.out_H * d.out_W;
   const long long w_pitch = d.Kpad + (d.res_via_mma ? d.block_n : 0);   // identity columns appended for the device
+  const bool bfA = d.operand_kind == SVX_OPERAND_BF16;
+  const bool bfO = (d.io_flags & SVX_IO_OUT_BF16) != 0, bfR = (d.io_flags & SVX_IO_RES_BF16) != 0;
+  // what the tensor cores see of an operand element: fp32 storage is truncated to TF32, bf16 storage is exact
+  auto opA = [&](long long i) { return bfA ? ldx(d.A, i, true) : tf32_trunc(reinterpret_cast<const float*>(d.A)[i]); };
+  auto opW = [&](long long i) { return bfA ? ldx(d.W, i, true) : tf32_trunc(reinterpret_cast<const float*>(d.W)[i]); };
+  auto RES = [&](long long i) { return ldx(d.residual, i, bfR); };
+  auto OUT = [&](long long i, float v) { stx(d.out, i, v, bfO); };
 #pragma omp parallel
   {
     std::vector<float> arow(d.K);
@@ -151,16 +182,16 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
       (void)rows_per_n;
       if (d.valid_W > 0 && (ow >= d.valid_W || oh >= d.valid_H || od >= d.valid_D)) continue;
       if (d.a_mode == SVX_A_PLAIN) {
-        for (int k = 0; k < d.K; ++k) arow[k] = tf32_trunc(d.A[(long long)r * d.lda + k]);
+        for (int k = 0; k < d.K; ++k) arow[k] = opA((long long)r * d.lda + k);
       } else if (d.a_mode == SVX_A_FLAT) {
         for (int tap = 0; tap < d.ntaps; ++tap) {
           const long long row = r + ((long long)d.taps_host[tap * 4] * d.in_H + d.taps_host[tap * 4 + 1]) * d.in_W +
                                 d.taps_host[tap * 4 + 2];
           const bool ok = row < d.lda;  // TMA zero-fills rows past the end of the matrix
-          const float* px = d.A + row * d.in_Cs + d.in_c0;
+          const long long px = row * d.in_Cs + d.in_c0;
           // TMA zero-fills columns past the end of a row as well (a 32-channel box may overhang the tensor)
           for (int c = 0; c < d.Cin; ++c)
-            arow[tap * d.Cin + c] = (ok && d.in_c0 + c < d.in_Cs) ? tf32_trunc(px[c]) : 0.f;
+            arow[tap * d.Cin + c] = (ok && d.in_c0 + c < d.in_Cs) ? opA(px + c) : 0.f;
         }
       } else {
         const int32_t* tp = d.a_mode == SVX_A_IM2COL ? d.taps_host : d.taps;
@@ -169,8 +200,8 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
           const int ih = oh * d.stride_h + tp[tap * 4 + 1];
           const int iw = ow * d.stride_w + tp[tap * 4 + 2];
           const bool ok = id >= 0 && id < d.in_D && ih >= 0 && ih < d.in_H && iw >= 0 && iw < d.in_W;
-          const float* px = d.A + (((n * d.in_D + id) * d.in_H + ih) * (long long)d.in_W + iw) * d.in_Cs + d.in_c0;
-          for (int c = 0; c < d.Cin; ++c) arow[tap * d.Cin + c] = ok ? tf32_trunc(px[c]) : 0.f;
+          const long long px = (((n * d.in_D + id) * d.in_H + ih) * (long long)d.in_W + iw) * d.in_Cs + d.in_c0;
+          for (int c = 0; c < d.Cin; ++c) arow[tap * d.Cin + c] = ok ? opA(px + c) : 0.f;
         }
       }
       const long long off = d.o_base + n * d.o_sn + od * d.o_sd + oh * d.o_sh + ow * d.o_sw;
@@ -179,8 +210,8 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
         float g = d.epi_aux[8];
         for (int j = 0; j < 8; ++j) {
           float acc = 0.f;
-          const float* w = d.W + (long long)j * w_pitch;
-          for (int k = 0; k < d.K; ++k) acc += arow[k] * tf32_trunc(w[k]);
+          const long long w = (long long)j * w_pitch;
+          for (int k = 0; k < d.K; ++k) acc += arow[k] * opW(w + k);
           acc += d.bias ? d.bias[j] : 0.f;
           x[j] = acc > 0.f ? acc : 0.f;
           g = fmaf(d.epi_aux[j], x[j], g);
@@ -188,7 +219,7 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
         x[8] = g;
         for (int j = 9; j < 16; ++j) x[j] = 0.f;
         d.epi_out2[d.o2_base + n * d.o2_sn + od * d.o2_sd + oh * d.o2_sh + ow * d.o2_sw] = g;
-        for (int j = 0; j < 16; ++j) d.out[off + j] = rnd(x[j], d.round_tf32);
+        for (int j = 0; j < 16; ++j) OUT(off + j, rnd(x[j], d.round_tf32));
         continue;
       }
       if (d.epi_mode == SVX_EPI_CONVT8) {
@@ -199,24 +230,24 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
           for (int c = 0; c < cc; ++c) {
             const int j = cls * cc + c;
             float acc = 0.f;
-            const float* w = d.W + (long long)j * w_pitch;
-            for (int k = 0; k < d.K; ++k) acc += arow[k] * tf32_trunc(w[k]);
+            const long long w = (long long)j * w_pitch;
+            for (int k = 0; k < d.K; ++k) acc += arow[k] * opW(w + k);
             float v = acc + (d.bias ? d.bias[j] : 0.f);
             if (d.epi_aux) {
               v = v > 0.f ? v : 0.f;
               g = fmaf(d.epi_aux[c], v, g);
             } else {
-              const float res = d.residual ? d.residual[o + c] : 0.f;
+              const float res = d.residual ? RES(o + c) : 0.f;
               if (d.residual && !d.res_after_act) v += res;
               v = act_fn(v, d.act, d.act_param);
               if (d.residual && d.res_after_act) v += res;
               v *= d.out_scale;
             }
-            d.out[o + c] = rnd(v, d.round_tf32);
+            OUT(o + c, rnd(v, d.round_tf32));
           }
           if (d.epi_aux) {
-            d.out[o + 8] = rnd(g, d.round_tf32);
-            d.out[o + 9] = d.out[o + 10] = d.out[o + 11] = 0.f;
+            OUT(o + 8, rnd(g, d.round_tf32));
+            OUT(o + 9, 0.f); OUT(o + 10, 0.f); OUT(o + 11, 0.f);
             d.epi_out2[d.o2_base + n * d.o2_sn + od * d.o2_sd + oh * d.o2_sh + ow * d.o2_sw + (cls >> 2) * d.c2_sd +
                        ((cls >> 1) & 1) * d.c2_sh + (cls & 1) * d.c2_sw] = g;
           }
@@ -229,26 +260,26 @@ int gemm_launch(const svx_gemm_desc& d, GemmPrepared* prepared, void*) {
           float best = -INFINITY;
           for (int gq = 0; gq < 8; ++gq) {
             float acc = 0.f;
-            const float* w = d.W + (long long)(gq * nc + c) * w_pitch;
-            for (int k = 0; k < d.K; ++k) acc += arow[k] * tf32_trunc(w[k]);
+            const long long w = (long long)(gq * nc + c) * w_pitch;
+            for (int k = 0; k < d.K; ++k) acc += arow[k] * opW(w + k);
             best = std::max(best, acc);
           }
           float v = act_fn(best + (d.bias ? d.bias[c] : 0.f), d.act, d.act_param) * d.out_scale;
-          d.out[off + c] = rnd(v, d.round_tf32);
+          OUT(off + c, rnd(v, d.round_tf32));
         }
         continue;
       }
       for (int j = 0; j < d.N; ++j) {
         float acc = 0.f;
-        const float* w = d.W + (long long)j * w_pitch;
-        for (int k = 0; k < d.K; ++k) acc += arow[k] * tf32_trunc(w[k]);
+        const long long w = (long long)j * w_pitch;
+        for (int k = 0; k < d.K; ++k) acc += arow[k] * opW(w + k);
         float v = acc + (d.bias ? d.bias[j] : 0.f);
-        const float res = d.residual ? d.residual[off + j] : 0.f;
+        const float res = d.residual ? RES(off + j) : 0.f;
         if (d.residual && !d.res_after_act) v += res;
         v = act_fn(v, d.act, d.act_param);
         if (d.residual && d.res_after_act) v += res;
         v *= d.out_scale;
-        d.out[off + j] = rnd(v, d.round_tf32);
+        OUT(off + j, rnd(v, d.round_tf32));
       }
     }
   }
@@ -300,12 +331,12 @@ int pool_launch(const svx_pool_desc& d, void*) {
           for (int kw = 0; kw < d.KW; ++kw) {
             const int id = od * d.SD - d.PD + kd, ih = oh * d.SH - d.PH + kh, iw = ow * d.SW - d.PW + kw;
             if (id < 0 || id >= d.D || ih < 0 || ih >= d.H || iw < 0 || iw >= d.W) continue;
-            const float v = d.in[(((n * d.D + id) * d.H + ih) * d.W + iw) * (long long)d.in_Cs + c];
+            const float v = ldx(d.in, (((n * d.D + id) * d.H + ih) * d.W + iw) * (long long)d.in_Cs + c, d.dtype & SVX_DT_IN_BF16);
             acc = d.mode == SVX_POOL_MAX ? std::max(acc, v) : acc + v;
             ++cnt;
           }
       if (d.mode == SVX_POOL_AVG) acc /= (float)std::max(cnt, 1);
-      d.out[r * d.out_Cs + c] = rnd(acc, d.round_tf32);
+      stx(d.out, r * d.out_Cs + c, rnd(acc, d.round_tf32), d.dtype & SVX_DT_OUT_BF16);
     }
   }
   return 0;
@@ -376,11 +407,11 @@ int lnrows_launch(const svx_lnrows_desc& d, void*) {
         const long long n = r / (W2 * H2);
         for (int s = 0; s < 4; ++s) {
           const int dy = s & 1, dx = s >> 1;
-          const float* src = d.in + ((n * d.H + 2 * y + dy) * d.W + 2 * x + dx) * (long long)Cq;
-          for (int c = 0; c < Cq; ++c) row[s * Cq + c] = src[c];
+          const long long src = ((n * d.H + 2 * y + dy) * d.W + 2 * x + dx) * (long long)Cq;
+          for (int c = 0; c < Cq; ++c) row[s * Cq + c] = ldx(d.in, src + c, d.dtype & SVX_DT_IN_BF16);
         }
       } else {
-        memcpy(row.data(), d.in + (long long)r * d.C, sizeof(float) * d.C);
+        for (int c = 0; c < d.C; ++c) row[c] = ldx(d.in, (long long)r * d.C + c, d.dtype & SVX_DT_IN_BF16);
       }
       double mean = 0, var = 0;
       for (int c = 0; c < d.C; ++c) mean += row[c];
@@ -389,7 +420,8 @@ int lnrows_launch(const svx_lnrows_desc& d, void*) {
       var /= d.C;
       const float rstd = 1.f / sqrtf((float)var + d.eps);
       for (int c = 0; c < d.C; ++c)
-        d.out[(long long)r * d.C + c] = rnd((row[c] - (float)mean) * rstd * d.gamma[c] + d.beta[c], d.round_tf32);
+        stx(d.out, (long long)r * d.C + c, rnd((row[c] - (float)mean) * rstd * d.gamma[c] + d.beta[c], d.round_tf32),
+            d.dtype & SVX_DT_OUT_BF16);
     }
   }
   return 0;
@@ -398,7 +430,8 @@ int lnrows_launch(const svx_lnrows_desc& d, void*) {
 int lnsample_launch(const svx_lnsample_desc& d, void*) {
 #pragma omp parallel for
   for (int n = 0; n < d.N; ++n) {
-    const float* x = d.in + (long long)n * d.L;
+    std::vector<float> x(d.L);
+    for (int i = 0; i < d.L; ++i) x[i] = ldx(d.in, (long long)n * d.L + i, d.dtype & SVX_DT_IN_BF16);
     double mean = 0, var = 0;
     for (int i = 0; i < d.L; ++i) mean += x[i];
     mean /= d.L;
@@ -406,7 +439,8 @@ int lnsample_launch(const svx_lnsample_desc& d, void*) {
     var /= d.L;
     const float rstd = 1.f / sqrtf((float)var + d.eps);
     for (int i = 0; i < d.L; ++i)
-      d.out[(long long)n * d.L + i] = rnd((x[i] - (float)mean) * rstd * d.gamma[i] + d.beta[i], d.round_tf32);
+      stx(d.out, (long long)n * d.L + i, rnd((x[i] - (float)mean) * rstd * d.gamma[i] + d.beta[i], d.round_tf32),
+          d.dtype & SVX_DT_OUT_BF16);
   }
   return 0;
 }
@@ -433,12 +467,13 @@ int winattn_launch(const svx_winattn_desc& d, void*) {
     }
     for (int h = 0; h < d.heads; ++h)
       for (int i = 0; i < 49; ++i) {
-        const float* q = d.qkv + tok[i] * 3 * d.C + h * 32;
+        const bool bfi = d.dtype & SVX_DT_IN_BF16;
+        const long long q = tok[i] * 3 * d.C + h * 32;
         float s[49], mx = -INFINITY;
         for (int j = 0; j < 49; ++j) {
-          const float* k = d.qkv + tok[j] * 3 * d.C + d.C + h * 32;
+          const long long k = tok[j] * 3 * d.C + d.C + h * 32;
           float acc = 0.f;
-          for (int e = 0; e < 32; ++e) acc += q[e] * d.scale * k[e];
+          for (int e = 0; e < 32; ++e) acc += ldx(d.qkv, q + e, bfi) * d.scale * ldx(d.qkv, k + e, bfi);
           acc += d.bias[((long long)h * 49 + i) * 49 + j];
           if (reg[i] != reg[j]) acc += -100.f;
           s[j] = acc;
@@ -448,8 +483,8 @@ int winattn_launch(const svx_winattn_desc& d, void*) {
         for (int j = 0; j < 49; ++j) { s[j] = expf(s[j] - mx); den += s[j]; }
         for (int e = 0; e < 32; ++e) {
           float acc = 0.f;
-          for (int j = 0; j < 49; ++j) acc += s[j] / den * d.qkv[tok[j] * 3 * d.C + 2 * d.C + h * 32 + e];
-          d.out[tok[i] * d.C + h * 32 + e] = rnd(acc, d.round_tf32);
+          for (int j = 0; j < 49; ++j) acc += s[j] / den * ldx(d.qkv, tok[j] * 3 * d.C + 2 * d.C + h * 32 + e, bfi);
+          stx(d.out, tok[i] * d.C + h * 32 + e, rnd(acc, d.round_tf32), d.dtype & SVX_DT_OUT_BF16);
         }
       }
   }
@@ -464,9 +499,9 @@ int dwconv_launch(const svx_dwconv_desc& d, void*) {
           float acc = d.bias ? d.bias[c] : 0.f;
           for (int ky = 0; ky < d.k; ++ky)
             for (int kx = 0; kx < d.k; ++kx)
-              acc += d.in[((n * d.H + oy * d.k + ky) * d.W + ox * d.k + kx) * (long long)d.C + c] *
+              acc += ldx(d.in, ((n * d.H + oy * d.k + ky) * d.W + ox * d.k + kx) * (long long)d.C + c, d.dtype & SVX_DT_IN_BF16) *
                      d.w[(ky * d.k + kx) * d.C + c];
-          d.out[((n * d.OH + oy) * d.OW + ox) * (long long)d.C + c] = rnd(acc, d.round_tf32);
+          stx(d.out, ((n * d.OH + oy) * d.OW + ox) * (long long)d.C + c, rnd(acc, d.round_tf32), d.dtype & SVX_DT_OUT_BF16);
         }
   return 0;
 }
@@ -475,7 +510,8 @@ int viewattn_launch(const svx_viewattn_desc& d, void*) {
   const int hd = d.R / d.heads, R3 = 3 * d.R;
   for (long long b = 0; b < d.B; ++b)
     for (int h = 0; h < d.heads; ++h) {
-      const float* base = d.qkv + b * d.V * (long long)d.P * R3;
+      const long long b0 = b * d.V * (long long)d.P * R3;
+      auto base = [&](long long i) { return ldx(d.qkv, b0 + i, d.dtype & SVX_DT_IN_BF16); };
       std::vector<float> sc(d.V * d.V);
       for (int v1 = 0; v1 < d.V; ++v1) {
         float mx = -INFINITY;
@@ -483,8 +519,8 @@ int viewattn_launch(const svx_viewattn_desc& d, void*) {
           float acc = 0.f;
           for (int pos = 0; pos < d.P; ++pos)
             for (int e = 0; e < hd; ++e)
-              acc += base[((long long)v1 * d.P + pos) * R3 + h * hd + e] *
-                     base[((long long)v2 * d.P + pos) * R3 + d.R + h * hd + e];
+              acc += base(((long long)v1 * d.P + pos) * R3 + h * hd + e) *
+                     base(((long long)v2 * d.P + pos) * R3 + d.R + h * hd + e);
           sc[v1 * d.V + v2] = acc * d.scale;
           mx = std::max(mx, acc * d.scale);
         }
@@ -497,8 +533,8 @@ int viewattn_launch(const svx_viewattn_desc& d, void*) {
           for (int e = 0; e < hd; ++e) {
             float acc = 0.f;
             for (int v2 = 0; v2 < d.V; ++v2)
-              acc += sc[v1 * d.V + v2] * base[((long long)v2 * d.P + pos) * R3 + 2 * d.R + h * hd + e];
-            d.out[((b * d.V + v1) * d.P + pos) * (long long)d.R + h * hd + e] = rnd(acc, d.round_tf32);
+              acc += sc[v1 * d.V + v2] * base(((long long)v2 * d.P + pos) * R3 + 2 * d.R + h * hd + e);
+            stx(d.out, ((b * d.V + v1) * d.P + pos) * (long long)d.R + h * hd + e, rnd(acc, d.round_tf32), d.dtype & SVX_DT_OUT_BF16);
           }
     }
   return 0;
@@ -514,12 +550,12 @@ int bilinear_launch(const svx_bilinear_desc& d, void*) {
         const int y1 = std::min(y0 + 1, d.IH - 1), x1 = std::min(x0 + 1, d.IW - 1);
         const float ly = fy - y0, lx = fx - x0;
         for (int c = 0; c < d.C; ++c) {
-          auto at = [&](int y, int x) { return d.in[((n * d.IH + y) * d.IW + x) * (long long)d.C + c]; };
+          auto at = [&](int y, int x) { return ldx(d.in, ((n * d.IH + y) * d.IW + x) * (long long)d.C + c, d.dtype & SVX_DT_IN_BF16); };
           const long long o = ((n * d.OH + oy) * d.OW + ox) * (long long)d.C + c;
           float v = (1 - ly) * (1 - lx) * at(y0, x0) + (1 - ly) * lx * at(y0, x1) + ly * (1 - lx) * at(y1, x0) +
                     ly * lx * at(y1, x1);
-          if (d.skip) v += d.skip[o];
-          d.out[o] = rnd(v, d.round_tf32);
+          if (d.skip) v += ldx(d.skip, o, d.dtype & SVX_DT_IN_BF16);
+          stx(d.out, o, rnd(v, d.round_tf32), d.dtype & SVX_DT_OUT_BF16);
         }
       }
   return 0;
@@ -604,10 +640,11 @@ int transpose_launch(const svx_transpose_desc& d, void*) {
         long long o = n * d.P + p;
         if (d.row_w > 0) o = n * (long long)(d.P / d.row_w) * d.row_pitch + (long long)(p / d.row_w) * d.row_pitch + d.row_x0 + p % d.row_w;
         for (int c = 0; c < d.Cs; ++c)
-          d.out[o * (long long)d.Cs + c] = c < d.C ? rnd(d.in[(n * d.C + c) * (long long)d.P + p], d.round_tf32) : 0.f;
+          stx(d.out, o * (long long)d.Cs + c, c < d.C ? rnd(d.in[(n * d.C + c) * (long long)d.P + p], d.round_tf32) : 0.f,
+              d.dtype & SVX_DT_OUT_BF16);
       } else {
         for (int c = 0; c < d.C; ++c)
-          d.out[(n * d.C + c) * (long long)d.P + p] = rnd(d.in[(n * d.P + p) * (long long)d.Cs + c], d.round_tf32);
+          d.out[(n * d.C + c) * (long long)d.P + p] = rnd(ldx(d.in, (n * d.P + p) * (long long)d.Cs + c, d.dtype & SVX_DT_IN_BF16), d.round_tf32);
       }
     }
   return 0;

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_python_mirror_matches_struct_layouts_and_names():
     lib = _lib.bind(_lib.LIB_PATH)     # raises on any size / symbol / ABI-version mismatch
-    assert lib.svx_abi_version() == 1
+    assert lib.svx_abi_version() == 2
     declared = set(declared_functions())
     bound = set(_lib.ALL_SYMBOLS) | set(_lib.IO_SYMBOLS)
     assert bound <= declared, f"bound in python but not declared in the header: {sorted(bound - declared)}"
