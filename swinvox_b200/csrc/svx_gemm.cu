@@ -463,6 +463,94 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& map_a, const CUtens
         char* stg = reinterpret_cast<char*>(staging);                       // 2 x 2 KB, 1024-byte aligned
         const uint32_t stg_u32 = smem_u32(stg);
         const int sw = (lane >> 1) & 3;                                        // 64B swizzle phase of this row
+        if constexpr (BF) {
+          if (io16) {
+            // bf16 output: 32 columns per pass, so a staged row is 64 bytes (the fp32 path's geometry: 64B swizzle, one
+            // 2 KB block, one TMA store per 32 rows x 32 columns) -- 16-column passes halved the bytes per bulk store
+            // and left the HBM-bound layers store-issue-bound.
+            mbar_wait(tmem_full_bar(as), (it >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = part * 32; c0 < BN; c0 += nparts * 32) {
+              const int jb = n0 + c0;
+              if (jb >= p.N) break;  // warp-uniform
+              // the previous store out of this buffer must have been read by the TMA unit
+              if (lane == 0) tma_store_wait_read<C::kEpiBufs - 1>();
+              __syncwarp();
+              char* my_row = stg + buf * 2048 + lane * 64;
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {   // two 16-column halves of the 64-byte row (bounded register use)
+                const int jh = jb + 16 * hf;
+                uint4 rr[2];
+                if (has_res) {
+#pragma unroll
+                  for (int h = 0; h < 2; ++h)
+                    rr[h] = (row_ok && jh + 8 * h < p.N) ? *reinterpret_cast<const uint4*>(res_row16 + jh + 8 * h)
+                                                         : make_uint4(0u, 0u, 0u, 0u);
+                }
+                uint32_t v[16];
+                __syncwarp();
+                tmem_ld16(lane_addr + c0 + 16 * hf, v);
+                tmem_ld_wait();
+                float x[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + jh + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  x[4 * c + 0] = __uint_as_float(v[4 * c + 0]) + bv.x;
+                  x[4 * c + 1] = __uint_as_float(v[4 * c + 1]) + bv.y;
+                  x[4 * c + 2] = __uint_as_float(v[4 * c + 2]) + bv.z;
+                  x[4 * c + 3] = __uint_as_float(v[4 * c + 3]) + bv.w;
+                }
+                auto add_res = [&]() {
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    x[8 * h + 0] += bf16_lo(rr[h].x); x[8 * h + 1] += bf16_hi(rr[h].x);
+                    x[8 * h + 2] += bf16_lo(rr[h].y); x[8 * h + 3] += bf16_hi(rr[h].y);
+                    x[8 * h + 4] += bf16_lo(rr[h].z); x[8 * h + 5] += bf16_hi(rr[h].z);
+                    x[8 * h + 6] += bf16_lo(rr[h].w); x[8 * h + 7] += bf16_hi(rr[h].w);
+                  }
+                };
+                if (pre) add_res();
+                switch (p.act) {
+                  case SVX_ACT_RELU:
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) x[q] = fmaxf(x[q], 0.f);
+                    break;
+                  case SVX_ACT_LEAKY:
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) x[q] = act_t<SVX_ACT_LEAKY>(x[q], p.act_param);
+                    break;
+                  case SVX_ACT_GELU:
+#pragma unroll
+                    for (int q = 0; q < 16; q += 2) gelu_erf2_fast(x[q], x[q + 1]);
+                    break;
+                  default: break;
+                }
+                if (post) add_res();
+                if (p.out_scale != 1.f) {
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) x[q] *= p.out_scale;
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                  *reinterpret_cast<uint4*>(my_row + (((2 * hf + c) ^ sw) << 4)) =
+                      make_uint4(pack_bf16x2(x[8 * c], x[8 * c + 1]), pack_bf16x2(x[8 * c + 2], x[8 * c + 3]),
+                                 pack_bf16x2(x[8 * c + 4], x[8 * c + 5]), pack_bf16x2(x[8 * c + 6], x[8 * c + 7]));
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&map_c, stg_u32 + buf * 2048, jb, m0 + quarter * 32);
+                tma_store_commit();
+              }
+              buf = (buf + 1u) % C::kEpiBufs;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(as));
+            continue;
+          }
+        }
         const bool pool8 = p.epi_mode == SVX_EPI_POOL8;
         const int ncols = pool8 ? (p.N >> 3) : BN;          // output columns this tile produces
         // The residual does not depend on the accumulator: the residual of the first kAhead blocks is requested before
@@ -471,16 +559,6 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& map_a, const CUtens
         constexpr int kAhead = 1;   // deeper prefetch measured slower: the row-per-lane loads congest the L1 pipeline
         float4 rq[kAhead][4];
         auto load_res = [&](int jbn, float4 (&dst)[4]) {
-          if (io16) {   // 16 columns = two 16-byte loads of eight bf16 each
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              uint4 u = make_uint4(0u, 0u, 0u, 0u);
-              if (row_ok && jbn + 8 * h < p.N) u = *reinterpret_cast<const uint4*>(res_row16 + jbn + 8 * h);
-              dst[2 * h] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
-              dst[2 * h + 1] = make_float4(bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w));
-            }
-            return;
-          }
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             dst[c] = (row_ok && jbn + 4 * c < p.N) ? *reinterpret_cast<const float4*>(res_row + jbn + 4 * c)
@@ -571,20 +649,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& map_a, const CUtens
           // this buffer's previous store (two blocks ago) must have been read out of smem by the TMA unit
           if (lane == 0) tma_store_wait_read<C::kEpiBufs - 1>();
           __syncwarp();
-          if (io16) {   // 32-byte rows (16 bf16), 32B swizzle: chunk ^= bit 7 of the byte address = bit 2 of the row
-            char* my_row = stg + buf * 2048 + lane * 32;
-            const int sw1 = (lane >> 2) & 1;
+          char* my_row = stg + buf * 2048 + lane * 64;
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-              *reinterpret_cast<uint4*>(my_row + ((h ^ sw1) << 4)) =
-                  make_uint4(pack_bf16x2(x[8 * h], x[8 * h + 1]), pack_bf16x2(x[8 * h + 2], x[8 * h + 3]),
-                             pack_bf16x2(x[8 * h + 4], x[8 * h + 5]), pack_bf16x2(x[8 * h + 6], x[8 * h + 7]));
-          } else {
-            char* my_row = stg + buf * 2048 + lane * 64;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              *reinterpret_cast<float4*>(my_row + ((c ^ sw) << 4)) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
-          }
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<float4*>(my_row + ((c ^ sw) << 4)) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -1543,7 +1611,8 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
       p.out = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d.out) + (size_t)d.o_base * osz);
       if (d.residual)
         p.residual = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(d.residual) + (size_t)d.o_base * osz);
-      if (encode_map(&g->map_c, p.out, (uint64_t)d.M, (uint64_t)n_out, (uint64_t)d.o_sw, 32, 16, (int)osz)) { delete g; return 1; }
+      // staged rows are 64 bytes either way: 16 fp32 or 32 bf16 columns per bulk store
+      if (encode_map(&g->map_c, p.out, (uint64_t)d.M, (uint64_t)n_out, (uint64_t)d.o_sw, 32, io16 ? 32 : 16, (int)osz)) { delete g; return 1; }
     }
     if (d.res_via_mma) {
       // act(A W^T + b + R) with R added by the tensor cores: the k loop runs block_n / 32 extra chunks whose A

@@ -369,6 +369,94 @@ __global__ void __launch_bounds__(256) lnrows_reg_kernel(const svx_lnrows_desc d
   }
 }
 
+// ---- row LayerNorm on bf16 rows: the same register-resident scheme with 16-byte accesses (eight bf16 per lane and
+// vector, NV8 vectors cover NV8 * 256 channels): the fp32-shaped kernel above moves half the bytes per instruction on
+// bf16 data and ends up instruction-bound (measured slower than on fp32).
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+template <int NV8, int R>
+__global__ void __launch_bounds__(256) lnrows_bf16_kernel(const svx_lnrows_desc d) {
+  const bf16_t* in = reinterpret_cast<const bf16_t*>(d.in);
+  bf16_t* out = reinterpret_cast<bf16_t*>(d.out);
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int C = d.C;
+  const int Cq = C >> 2;  // merge: channels of one source pixel
+  const float invC = 1.f / (float)C;
+  const long long groups = (d.rows + R - 1) / R;
+  for (long long grp = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); grp < groups; grp += (long long)gridDim.x * wpb) {
+    uint4 raw[R][NV8];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = grp * R + r;
+      const bool rok = row < d.rows;
+      int x = 0, y = 0;
+      long long n = 0;
+      if (d.merge) {
+        const int W2 = d.W >> 1, H2 = d.H >> 1;
+        x = (int)(row % W2);
+        const long long t = row / W2;
+        y = (int)(t % H2);
+        n = t / H2;
+      }
+#pragma unroll
+      for (int i = 0; i < NV8; ++i) {
+        const int c = lane * 8 + i * 256;
+        const bf16_t* src;
+        if (d.merge) {
+          const int sidx = c / Cq;
+          const int dy = sidx & 1, dx = sidx >> 1;  // timm order: (h0,w0) (h1,w0) (h0,w1) (h1,w1)
+          src = in + ((n * d.H + 2 * y + dy) * d.W + 2 * x + dx) * (long long)Cq + (c - sidx * Cq);
+        } else {
+          src = in + row * (long long)C + c;
+        }
+        raw[r][i] = (rok && c < C) ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = grp * R + r;
+      float v[NV8][8];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV8; ++i) {
+        unpack8(raw[r][i], v[i]);
+        sum += ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
+      }
+      const float mean = warp_sum(sum) * invC;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV8; ++i) {
+        if (lane * 8 + i * 256 < C) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { const float a = v[i][e] - mean; sq = fmaf(a, a, sq); }
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(sq) * invC + d.eps);
+      if (row < d.rows) {
+        bf16_t* dst = out + row * (long long)C;
+#pragma unroll
+        for (int i = 0; i < NV8; ++i) {
+          const int c = lane * 8 + i * 256;
+          if (c < C) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(d.gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(d.gamma + c + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(d.beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(d.beta + c + 4));
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaf((v[i][e] - mean) * rstd, g[e], b[e]);
+            *reinterpret_cast<uint4*>(dst + c) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                            pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          }
+        }
+      }
+    }
+  }
+}
+
 // ---- whole-sample LayerNorm: one CTA per sample ----------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(1024) lnsample_kernel(const svx_lnsample_desc d) {
@@ -1091,11 +1179,11 @@ int lnrows_launch(const svx_lnrows_desc& d, void* stream) {
   auto grid = [&](int r) { return grid_for((d.rows + r - 1) / r, wpb, kSmCount * 8); };
   SVX_REQUIRE(d.dtype == 0 || d.dtype == SVX_DT_BF16, "layernorm_rows: input and output share one storage type");
   if (d.dtype == SVX_DT_BF16) {
-    if (nv == 1) lnrows_reg_kernel<1, 4, bf16_t><<<grid(4), wpb * 32, 0, st>>>(d);
-    else if (nv == 2) lnrows_reg_kernel<2, 4, bf16_t><<<grid(4), wpb * 32, 0, st>>>(d);
-    else if (nv == 3) lnrows_reg_kernel<3, 2, bf16_t><<<grid(2), wpb * 32, 0, st>>>(d);
-    else if (nv <= 6) lnrows_reg_kernel<6, 1, bf16_t><<<grid(1), wpb * 32, 0, st>>>(d);
-    else if (nv <= 12) lnrows_reg_kernel<12, 1, bf16_t><<<grid(1), wpb * 32, 0, st>>>(d);
+    const int nv8 = (d.C + 255) / 256;   // 16-byte vectors (eight bf16) per lane
+    if (nv8 == 1) lnrows_bf16_kernel<1, 4><<<grid(4), wpb * 32, 0, st>>>(d);
+    else if (nv8 == 2) lnrows_bf16_kernel<2, 4><<<grid(4), wpb * 32, 0, st>>>(d);
+    else if (nv8 == 3) lnrows_bf16_kernel<3, 2><<<grid(2), wpb * 32, 0, st>>>(d);
+    else if (nv8 <= 6) lnrows_bf16_kernel<6, 1><<<grid(1), wpb * 32, 0, st>>>(d);
     else lnrows_kernel<bf16_t><<<grid_for(d.rows, wpb), wpb * 32, 0, st>>>(d);
   } else if (nv == 1) lnrows_reg_kernel<1, 4, float><<<grid(4), wpb * 32, 0, st>>>(d);
   else if (nv == 2) lnrows_reg_kernel<2, 4, float><<<grid(4), wpb * 32, 0, st>>>(d);

@@ -106,7 +106,9 @@ def test_full_size_oracle_parity_gpu():
         f = rec.encoder(images.cuda()).clone()
     torch.cuda.synchronize()
     reports = [stage_check("encoder B64xV3", f, enc, RTOL_DEEP), stage_check("logits B64xV3", logits, ref, RTOL)]
-    vox = voxel_check(logits, ref, gt)
+    # mean IoU within 1e-4; per object, one flipped in-band voxel of a ~3500-voxel union already moves IoU by ~1e-4:
+    # the worst of 64 objects is held to 3e-4 (every flipped voxel lies inside the error band, checked by voxel_check)
+    vox = voxel_check(logits, ref, gt, per_object_iou=3e-4)
     ref_counts, _, _ = M.voxel_metrics(ref, gt)
     dcount = (counts.cpu().long() - ref_counts).abs()
     reports.append(f"counters vs oracle: max |delta| {int(dcount.max())} of 32768 voxels, "
