@@ -51,6 +51,7 @@ int pool_launch(const svx_pool_desc& d, void* stream);
 int lnrows_launch(const svx_lnrows_desc& d, void* stream);
 int lnsample_launch(const svx_lnsample_desc& d, void* stream);
 int winattn_launch(const svx_winattn_desc& d, void* stream);
+int winattn_umma_launch(const svx_winattn_desc& d, void* stream);   // svx_winattn.cu: the tcgen05 kernel behind winattn_launch
 int dwconv_launch(const svx_dwconv_desc& d, void* stream);
 int viewattn_launch(const svx_viewattn_desc& d, void* stream);
 int bilinear_launch(const svx_bilinear_desc& d, void* stream);

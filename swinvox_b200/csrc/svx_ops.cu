@@ -1245,6 +1245,10 @@ int winattn_launch(const svx_winattn_desc& d, void* stream) {
   if (per_head > cap) per_head = cap;
   if (per_head < 1) per_head = 1;
   SVX_REQUIRE(d.dtype == 0 || (d.dtype == SVX_DT_BF16 && d.C % 8 == 0), "window_attention: qkv and out share one storage type");
+  // the tensor-core (tcgen05 / TMEM) kernel of svx_winattn.cu; SVX_WINATTN_MMASYNC=1 keeps the round-1 mma.sync kernel
+  // below reachable for A/B measurements
+  static const bool legacy = getenv("SVX_WINATTN_MMASYNC") != nullptr;
+  if (!legacy) return winattn_umma_launch(d, stream);
   // (per device: a process may drive several GPUs)
   SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
   SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));

@@ -1,0 +1,416 @@
+// svx_winattn.cu -- W-MSA / SW-MSA of the Swin blocks (timm WindowAttention + the roll / window_partition /
+// window_reverse around it; restated in oracle/swin_t.py) on the sm_100a tensor cores: tcgen05.mma with the score and
+// output accumulators in TMEM.
+//
+// One work item = TWO 7x7 windows of one head stacked into a 128-row tile (window w occupies rows 64w .. 64w+48, the
+// other 15 rows of each half are padding):
+//   S (TMEM, 128 x 128 fp32) = Q K^T      A = Q tile [128 rows x 32 dims], B = K tile [128 keys x 32 dims], both K-major
+//   P (smem, 128 x 128)      = exp2(S * scale*log2e + bias*log2e + mask*log2e - rowmax)  on the rows of TMEM: one thread
+//                              per query row reads its own window's 64 score columns, writes its 49 probabilities in
+//                              the MMA's A-operand layout; the off-diagonal 64 x 64 blocks of P are zero and never
+//                              written, which is what keeps the two windows of a tile apart
+//   O (TMEM, 128 x 32 fp32)  = P V        A = P, B = V tile [128 keys x 32 dims] read as an MN-major operand: the V rows
+//                              are used exactly as they lie in the qkv tensor, no transpose
+//   out[token] = O / rowsum
+// The cyclic shift and the inverse roll are folded into the token addresses of the row gather / the output rows; the
+// -100 attention mask of the shifted blocks is recomputed from the window position ("a key is masked iff it lies in a
+// different wrap-around piece than the query"), so neither a rolled copy nor a mask tensor exists.
+//
+// Storage type T: fp32 (values stored TF32-rounded; kind::tf32 operands, P rounded to TF32) or bf16 (kind::f16 with
+// bf16 operands).  Accumulation, softmax statistics and the bias are fp32 either way.
+//
+// Warp roles (12 warps):  0-3 / 4-7  two softmax + output groups (TMEM lane quarter = warp % 4), alternating items
+//                         8-9        row gather: cp.async 16-byte chunks of the token rows into 128B / 64B-swizzled
+//                                    operand tiles (a ring of stages)
+//                         10         MMA issuer (one elected thread), owns the TMEM allocation
+#include <cuda_runtime.h>
+
+#include "svx_internal.h"
+#include "svx_ptx.cuh"
+
+namespace svx {
+namespace {
+
+constexpr int WS = 7, WT = 49, HD = 32;
+constexpr int WU_THREADS = 11 * 32;
+constexpr int WU_PRODUCER_WARPS = 2;
+constexpr int WU_LAG = 1;                       // cp.async groups a producer warp keeps in flight beyond the current one
+constexpr float kLog2e = 1.4426950408889634f;
+
+template <typename T>
+struct WuCfg {
+  static constexpr bool kBf = sizeof(T) == 2;
+  static constexpr int kRowB = HD * (int)sizeof(T);          // bytes per Q / K / V row: 128 | 64
+  static constexpr int kMatB = 128 * kRowB;                  // one 128-row operand tile: 16 KB | 8 KB
+  static constexpr int kStageB = 3 * kMatB;                  // Q | K | V
+  static constexpr int kStages = kBf ? 4 : 3;
+  static constexpr int kPAtoms = 128 * (int)sizeof(T) / 128; // 128-byte-wide K atoms of the P tile: 4 | 2
+  static constexpr int kPBytes = kPAtoms * 128 * 128;        // 64 KB | 32 KB
+  static constexpr int kPBufs = kBf ? 2 : 1;
+  static constexpr int kBiasB = (WT * WT * 4 + 127) / 128 * 128;
+  static constexpr int kKS = kRowB / 32;                     // MMA K steps of S = Q K^T (32 bytes each): 4 | 2
+  static constexpr int kKP = 128 * (int)sizeof(T) / 32;      // MMA K steps of O = P V over the 128 keys: 16 | 8
+  static constexpr int kSmem = 1024 + kStages * kStageB + kPBufs * kPBytes + kBiasB + 256;
+  static_assert(kSmem <= 232448, "window attention shared memory");
+};
+
+// instruction descriptors: fp32 accumulate; A K-major; B K-major (S) or MN-major (O = P V: bit 16)
+__host__ __device__ constexpr uint32_t wu_idesc(bool bf, uint32_t n, bool b_mn) {
+  const uint32_t fmt = bf ? 1u : 2u;   // bf16 : tf32
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (b_mn ? (1u << 16) : 0u) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// MN-major operand tile as the row gather leaves it: rows = keys (the MMA's K), 32 dims contiguous per row (the MMA's N =
+// one swizzle atom wide); groups of 8 keys are `sbo` bytes apart.  Layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
+__device__ __forceinline__ uint64_t wu_desc(uint32_t smem_addr, uint32_t sbo, uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;                 // leading byte offset: unused (one atom along the contiguous dimension)
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout) << 61;
+  return d;
+}
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// keys (bit j = key j = (ky, kx) = (j / 7, j % 7)) whose ky (kx) is >= 4: the second wrap-around piece of a window in the
+// last window row (column) of a shifted map.  A query with qy < 4 masks exactly these keys, a query with qy >= 4 the others.
+__host__ __device__ constexpr uint64_t wu_keys_ge4(bool by_row) {
+  uint64_t m = 0;
+  for (int j = 0; j < WT; ++j)
+    if ((by_row ? j / WS : j % WS) >= 4) m |= 1ull << j;
+  return m;
+}
+constexpr uint64_t kKeysAll = (1ull << WT) - 1;
+
+template <typename T, bool SHIFTED>
+__global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_winattn_desc d, int ctas_per_head) {
+  using K = WuCfg<T>;
+  constexpr bool BF = K::kBf;
+  constexpr int NS = K::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t stage_smem = smem_base;
+  const uint32_t p_smem = stage_smem + NS * K::kStageB;
+  uint8_t* p_gen = smem_gen + NS * K::kStageB;
+  float* sbias = reinterpret_cast<float*>(smem_gen + NS * K::kStageB + K::kPBufs * K::kPBytes);
+  const uint32_t bar_base = p_smem + K::kPBufs * K::kPBytes + K::kBiasB;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                 // stage s holds Q, K, V of an item
+  auto empty_bar = [&](int s) { return bar_base + 8u * (NS + s); };         // every MMA that reads stage s has completed
+  auto s_full = [&](int b) { return bar_base + 8u * (2 * NS + b); };        // scores of an item are in TMEM buffer b
+  auto s_empty = [&](int b) { return bar_base + 8u * (2 * NS + 2 + b); };   // ... and have been read out
+  auto p_full = [&](int b) { return bar_base + 8u * (2 * NS + 4 + b); };    // probabilities are in P buffer b
+  auto p_empty = [&](int b) { return bar_base + 8u * (2 * NS + 6 + b); };   // the P V MMAs have read P buffer b
+  auto o_full = [&](int b) { return bar_base + 8u * (2 * NS + 8 + b); };
+  auto o_empty = [&](int b) { return bar_base + 8u * (2 * NS + 10 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NS + 12);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * NS + 12));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.x % d.heads;
+  const int cta_in_head = blockIdx.x / d.heads;
+  const int nwx = d.W / WS, nwy = d.H / WS;
+  const int num_windows = d.N * nwx * nwy;
+  const int num_items = (num_windows + 1) >> 1;
+  const int nt = cta_in_head < num_items ? (num_items - cta_in_head + ctas_per_head - 1) / ctas_per_head : 0;   // items of this CTA
+
+  // ---- one-time setup: zero the operand stages and P (padding rows / off-diagonal blocks are never written again),
+  // the head's bias (x log2 e), barriers, TMEM ----------------------------------------------------------------------
+  for (int i = threadIdx.x; i < (NS * K::kStageB + K::kPBufs * K::kPBytes) / 16; i += WU_THREADS)
+    reinterpret_cast<uint4*>(smem_gen)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < WT * WT; i += WU_THREADS) sbias[i] = __ldg(d.bias + (long long)head * WT * WT + i) * kLog2e;
+  if (warp == 10) {
+    if (lane == 0) {
+      for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), WU_PRODUCER_WARPS); mbar_init(empty_bar(s), 1u); }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(s_full(b), 1u); mbar_init(s_empty(b), 4u);
+        mbar_init(p_full(b), 4u); mbar_init(p_empty(b), 1u);
+        mbar_init(o_full(b), 1u); mbar_init(o_empty(b), 4u);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  fence_proxy_async_smem();   // the zero fill is read by the tensor cores (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  // TMEM columns: scores S[b] at b * 128 (128 columns each), outputs O[b] at 256 + b * 32
+  auto item_of = [&](int i) { return cta_in_head + i * ctas_per_head; };
+  // window `win` -> (image row base n * H, first rolled row wy * 7 + shift, first rolled column wx * 7 + shift, wy, wx)
+  struct WinPos { int nH, y0, x0, wy, wx; };
+  auto window_pos = [&](int win) {
+    const int wq = win / nwx, wx = win - wq * nwx;
+    const int n = wq / nwy, wy = wq - n * nwy;
+    return WinPos{n * d.H, wy * WS + d.shift, wx * WS + d.shift, wy, wx};
+  };
+  // token row (n * H + oy) * W + ox of window position (qy, qx): the cyclic shift is one conditional subtraction per axis
+  auto token_of = [&](const WinPos& wp, int qy, int qx) -> long long {
+    int oy = wp.y0 + qy, ox = wp.x0 + qx;
+    oy -= oy >= d.H ? d.H : 0;
+    ox -= ox >= d.W ? d.W : 0;
+    return ((long long)(wp.nH + oy)) * d.W + ox;
+  };
+
+  if (warp >= 8 && warp < 10) {
+    // ---- row gather: each producer warp owns one half of the tile = one window ------------------------------------
+    const int w = warp - 8;
+    constexpr int CH = K::kRowB / 16;            // 16-byte chunks per row: 8 | 4
+    constexpr int RPI = 32 / CH;                 // rows one warp-wide cp.async instruction covers: 4 | 8
+    const int ch = lane % CH, rsub = lane / CH;
+    const size_t tok_pitch = (size_t)3 * d.C * sizeof(T), c_bytes = (size_t)d.C * sizeof(T);
+    const uint8_t* qkvb = reinterpret_cast<const uint8_t*>(d.qkv) + (size_t)head * HD * sizeof(T) + ch * 16;
+    for (int i = 0; i < nt; ++i) {
+      const int s = i % NS;
+      mbar_wait(empty_bar(s), (((uint32_t)(i / NS)) & 1u) ^ 1u);
+      const int win = 2 * item_of(i) + w;
+      if (win < num_windows) {
+        const uint32_t dst0 = stage_smem + s * K::kStageB + (64 * w) * K::kRowB;
+        const WinPos wp = window_pos(win);
+#pragma unroll 1
+        for (int r0 = 0; r0 < WT; r0 += RPI) {
+          const int q = r0 + rsub;
+          if (q < WT) {
+            const uint8_t* src = qkvb + (size_t)token_of(wp, q / WS, q % WS) * tok_pitch;
+            const int row = 64 * w + q;
+            // 128B swizzle: chunk ^= row & 7;  64B swizzle: chunk ^= (row >> 1) & 3
+            const uint32_t dst = dst0 + q * K::kRowB + ((BF ? (ch ^ ((row >> 1) & 3)) : (ch ^ (row & 7))) << 4);
+            cp_async16_zfill(dst, src, 16u);
+            cp_async16_zfill(dst + K::kMatB, src + c_bytes, 16u);
+            cp_async16_zfill(dst + 2 * K::kMatB, src + 2 * c_bytes, 16u);
+          }
+        }
+      }
+      cp_async_commit();
+      if (i >= WU_LAG) {
+        cp_async_wait<WU_LAG>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar((i - WU_LAG) % NS));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0)
+      for (int i = (nt > WU_LAG ? nt - WU_LAG : 0); i < nt; ++i) mbar_arrive(full_bar(i % NS));
+  } else if (warp == 10) {
+    // ---- MMA issuer: S(0) S(1) | PV(0) S(2) | PV(1) S(3) ... -------------------------------------------------------
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = wu_idesc(BF, 128, false);
+      constexpr uint32_t idesc_o = wu_idesc(BF, 32, true);
+      constexpr uint32_t lay = BF ? 4u : 2u;
+      constexpr uint32_t sbo = 8 * K::kRowB;     // 8-row groups of the Q / K / V tiles: 1024 | 512 bytes
+      auto issue_s = [&](int i) {
+        const int s = i % NS, b = i & 1;
+        mbar_wait(full_bar(s), ((uint32_t)(i / NS)) & 1u);
+        mbar_wait(s_empty(b), (((uint32_t)i >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t q_addr = stage_smem + s * K::kStageB;
+        const uint64_t da = wu_desc(q_addr, sbo, lay), db = wu_desc(q_addr + K::kMatB, sbo, lay);
+#pragma unroll
+        for (int k = 0; k < K::kKS; ++k) {
+          if constexpr (BF) umma_f16(tmem_base + b * 128, da + 2u * k, db + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+          else umma_tf32(tmem_base + b * 128, da + 2u * k, db + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(s_full(b));
+      };
+      auto issue_pv = [&](int i) {
+        const int s = i % NS, b = i & 1, pb = K::kPBufs == 2 ? b : 0;
+        const uint32_t pi = K::kPBufs == 2 ? (uint32_t)i >> 1 : (uint32_t)i;
+        mbar_wait(p_full(pb), pi & 1u);
+        mbar_wait(o_empty(b), (((uint32_t)i >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t v_addr = stage_smem + s * K::kStageB + 2 * K::kMatB;
+        const uint32_t p_addr = p_smem + pb * K::kPBytes;
+#pragma unroll
+        for (int k = 0; k < K::kKP; ++k) {
+          // A: k-th 32-byte step of the P rows (four steps per 128-byte atom, atoms 16 KB apart);
+          // B: keys of this step = 1024 bytes of V rows (8 fp32 rows | 16 bf16 rows)
+          const uint64_t da = umma_desc_sw128(p_addr + (k >> 2) * (128 * 128)) + 2u * (k & 3);
+          const uint64_t db = wu_desc(v_addr + k * 1024, sbo, lay);
+          if constexpr (BF) umma_f16(tmem_base + 256 + b * 32, da, db, idesc_o, k != 0 ? 1u : 0u);
+          else umma_tf32(tmem_base + 256 + b * 32, da, db, idesc_o, k != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));     // Q, K, V of this item are no longer needed
+        umma_commit(p_empty(pb));
+        umma_commit(o_full(b));
+      };
+      if (nt > 0) issue_s(0);
+      if (nt > 1) issue_s(1);
+      for (int i = 0; i < nt; ++i) {
+        issue_pv(i);
+        if (i + 2 < nt) issue_s(i + 2);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- softmax + output: group g = warp / 4 takes the items with i % 2 == g; thread = one query row ----------------
+    const int grp = warp >> 2, quarter = warp & 3;
+    const int r = quarter * 32 + lane;           // tile row = TMEM lane
+    const int w = r >> 6, q = r & 63;            // window of the tile, row inside the window
+    const bool qreal = q < WT;
+    const int qy = q / WS, qx = q - qy * WS;
+    const float scale2 = d.scale * kLog2e;
+    const float kMask = -100.f * kLog2e;
+    const float* brow = sbias + (qreal ? q : 0) * WT;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    constexpr uint64_t kRowGe4 = wu_keys_ge4(true), kColGe4 = wu_keys_ge4(false);
+    for (int i = grp; i < nt; i += 2) {
+      const int b = i & 1, pb = K::kPBufs == 2 ? b : 0;
+      const int win = 2 * item_of(i) + w;
+      const bool live = qreal && win < num_windows;
+      long long tok = 0;
+      uint64_t masked = 0;   // keys this query must not see (shifted blocks only)
+      if (live) {
+        const WinPos wp = window_pos(win);
+        tok = token_of(wp, qy, qx);
+        if (SHIFTED) {
+          if (wp.wy == nwy - 1) masked |= qy < 4 ? kRowGe4 : (kKeysAll & ~kRowGe4);
+          if (wp.wx == nwx - 1) masked |= qx < 4 ? kColGe4 : (kKeysAll & ~kColGe4);
+        }
+      }
+      mbar_wait(s_full(b), ((uint32_t)i >> 1) & 1u);
+      tc_fence_after();
+      // this row's scores against the 64 key slots of its own window (slots 49..63 are padding)
+      uint32_t sv[4][16];
+      const uint32_t s_addr = tmem_base + lane_sel + b * 128 + w * 64;
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16(s_addr + 16 * c, sv[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty(b));
+      float e[WT];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < WT; ++j) {
+        float v = fmaf(__uint_as_float(sv[j >> 4][j & 15]), scale2, brow[j]);
+        if (SHIFTED) v += ((masked >> j) & 1ull) ? kMask : 0.f;
+        e[j] = v;
+        mx = fmaxf(mx, v);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < WT; ++j) {
+        e[j] = ex2f(e[j] - mx);
+        sum += e[j];
+      }
+      // P row in the A-operand layout (K-major, 128B swizzle): only the 49 (+3 zero) slots of the own window
+      const uint32_t pi = K::kPBufs == 2 ? (uint32_t)i >> 1 : (uint32_t)i;
+      mbar_wait(p_empty(pb), (pi & 1u) ^ 1u);
+      if (live) {
+        uint8_t* prow = p_gen + pb * K::kPBytes + r * 128;
+        if constexpr (BF) {
+          // 64 bf16 slots of window w = atom w; chunk c holds slots 8c .. 8c+7
+#pragma unroll
+          for (int c = 0; c < 7; ++c) {
+            uint32_t u[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int j0 = 8 * c + 2 * h;
+              u[h] = pack_bf16x2(j0 < WT ? e[j0 < WT ? j0 : 0] : 0.f, j0 + 1 < WT ? e[j0 + 1 < WT ? j0 + 1 : 0] : 0.f);
+            }
+            *reinterpret_cast<uint4*>(prow + w * (128 * 128) + ((c ^ (r & 7)) << 4)) = make_uint4(u[0], u[1], u[2], u[3]);
+          }
+        } else {
+          // 64 fp32 slots of window w = atoms 2w, 2w+1; chunk c of atom a holds slots 32a' + 4c .. + 3.  The MMA truncates
+          // fp32 to TF32: adding half a TF32 ulp first makes that a round-to-nearest
+#pragma unroll
+          for (int c = 0; c < 13; ++c) {
+            float f[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int j = 4 * c + h;
+              f[h] = j < WT ? __uint_as_float(__float_as_uint(e[j < WT ? j : 0]) + 0x1000u) : 0.f;
+            }
+            *reinterpret_cast<float4*>(prow + (2 * w + (c >> 3)) * (128 * 128) + (((c & 7) ^ (r & 7)) << 4)) =
+                make_float4(f[0], f[1], f[2], f[3]);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(pb));
+      // ---- output row: O / rowsum -> out[token, head*32 ..] ---------------------------------------------------------
+      const float inv = __frcp_rn(sum);
+      mbar_wait(o_full(b), ((uint32_t)i >> 1) & 1u);
+      tc_fence_after();
+      uint32_t ov[2][16];
+      const uint32_t o_addr = tmem_base + lane_sel + 256 + b * 32;
+      __syncwarp();
+      tmem_ld16(o_addr, ov[0]);
+      tmem_ld16(o_addr + 16, ov[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty(b));
+      if (live) {
+        T* dst = reinterpret_cast<T*>(d.out) + (size_t)tok * d.C + head * HD;
+        if constexpr (BF) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t* o8 = &ov[c >> 1][(c & 1) * 8];
+            *reinterpret_cast<uint4*>(dst + 8 * c) =
+                make_uint4(pack_bf16x2(__uint_as_float(o8[0]) * inv, __uint_as_float(o8[1]) * inv),
+                           pack_bf16x2(__uint_as_float(o8[2]) * inv, __uint_as_float(o8[3]) * inv),
+                           pack_bf16x2(__uint_as_float(o8[4]) * inv, __uint_as_float(o8[5]) * inv),
+                           pack_bf16x2(__uint_as_float(o8[6]) * inv, __uint_as_float(o8[7]) * inv));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t* o4 = &ov[c >> 2][(c & 3) * 4];
+            float4 o = make_float4(__uint_as_float(o4[0]) * inv, __uint_as_float(o4[1]) * inv, __uint_as_float(o4[2]) * inv,
+                                   __uint_as_float(o4[3]) * inv);
+            if (d.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+            *reinterpret_cast<float4*>(dst + 4 * c) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
+
+int winattn_umma_launch(const svx_winattn_desc& d, void* stream) {
+  const long long windows = (long long)d.N * (d.H / WS) * (d.W / WS);
+  const long long items = (windows + 1) / 2;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  long long per_head = sms / d.heads;      // one CTA per SM (it takes most of the shared memory), whole heads
+  if (per_head < 1) per_head = 1;
+  if (per_head > items) per_head = items;
+  const int grid = (int)(per_head * d.heads);
+  const bool bf = d.dtype == SVX_DT_BF16;
+  cudaStream_t st = (cudaStream_t)stream;
+  SVX_CUDA_OK(cudaFuncSetAttribute(winattn_umma_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WuCfg<float>::kSmem));
+  SVX_CUDA_OK(cudaFuncSetAttribute(winattn_umma_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WuCfg<float>::kSmem));
+  SVX_CUDA_OK(cudaFuncSetAttribute(winattn_umma_kernel<bf16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WuCfg<bf16_t>::kSmem));
+  SVX_CUDA_OK(cudaFuncSetAttribute(winattn_umma_kernel<bf16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WuCfg<bf16_t>::kSmem));
+  if (bf) {
+    if (d.shift > 0) winattn_umma_kernel<bf16_t, true><<<grid, WU_THREADS, WuCfg<bf16_t>::kSmem, st>>>(d, (int)per_head);
+    else winattn_umma_kernel<bf16_t, false><<<grid, WU_THREADS, WuCfg<bf16_t>::kSmem, st>>>(d, (int)per_head);
+  } else {
+    if (d.shift > 0) winattn_umma_kernel<float, true><<<grid, WU_THREADS, WuCfg<float>::kSmem, st>>>(d, (int)per_head);
+    else winattn_umma_kernel<float, false><<<grid, WU_THREADS, WuCfg<float>::kSmem, st>>>(d, (int)per_head);
+  }
+  SVX_LAUNCH_OK("winattn_umma_kernel");
+  return 0;
+}
+
+}  // namespace svx

@@ -612,11 +612,15 @@ def test_layernorm_rows_widths(dev, rows, C, merge):
     assert rel_err(o.view().reshape(-1, C), F.layer_norm(ref_in.double(), (C,), g.double(), b.double())) < 1e-5
 
 
-@pytest.mark.parametrize("H,heads,shift", [(14, 3, 0), (14, 3, 3), (7, 6, 0), (28, 2, 3)])
-def test_window_attention(dev, H, heads, shift):
+@pytest.mark.parametrize("H,heads,shift,N", [(14, 3, 0, 2), (14, 3, 3, 2), (7, 6, 0, 2), (28, 2, 3, 2), (7, 24, 0, 3),
+                                             (14, 12, 3, 5), (56, 3, 3, 3), (7, 2, 0, 1)])
+def test_window_attention(dev, H, heads, shift, N):
+    """W-MSA / SW-MSA: the tensor-core kernel packs two windows per 128-row tile, so odd window counts (N = 3 or 1 images
+    of one window, 5 x 4 windows), every wrap-around window type of the shifted maps and all four Swin stage shapes are
+    covered"""
     DEV = dev
     torch.manual_seed(7)
-    N, Cc = 2, heads * 32
+    Cc = heads * 32
     qkv = E.tf32_round(torch.randn(N, H, H, 3 * Cc))   # the qkv GEMM stores its output TF32-rounded
     bias = torch.randn(heads, 49, 49)
     scale = 32 ** -0.5
