@@ -216,11 +216,15 @@ typedef struct svx_lnsample_desc {
 
 /* W-MSA / SW-MSA (timm WindowAttention + roll/partition/reverse).  qkv is [N*H*W, 3C] in token
  * order, columns (which, head, d); out is [N*H*W, C].  bias is the expanded relative-position
- * bias [heads, 49, 49].  The cyclic shift and the -100 region mask are applied by indexing. */
+ * bias [heads, 49, 49].  The cyclic shift and the -100 region mask are applied by indexing.
+ * tcgen05 kernel (svx_winattn.cu): two windows per 128-row tile, score / output accumulators in TMEM. */
 typedef struct svx_winattn_desc {
   const float* qkv; float* out; const float* bias;
   int32_t N, H, W, C, heads, shift; float scale; int32_t round_tf32;
   int32_t dtype;            /* SVX_DT_* bits */
+  int32_t reserved0;
+  int32_t* range_flag;      /* fp32 storage: the P V product uses fp16 operands (exact for the TF32-rounded values this path
+                               stores while |v| <= 65504); device int32 OR-ed with 1 if a V value saturated, or NULL */
 } svx_winattn_desc;
 
 /* depthwise k=s conv without padding (cross_view_attention.py:26-34), channels-last */
@@ -288,6 +292,15 @@ typedef struct svx_transpose_desc {
                                SVX_DT_IN_BF16 without) */
 } svx_transpose_desc;
 
+/* torch.nn.functional.interpolate(x, size=(OH, OW), mode="bilinear", align_corners=False) on planar fp32 images
+ * (models/swin_transformer.py:74-75 resizes inputs that are not img_size x img_size): in [NC, IH, IW] -> out [NC, OH, OW],
+ * source coordinate max((o + 0.5) * IH / OH - 0.5, 0), the neighbour index clamped at the border. */
+typedef struct svx_resize_desc {
+  const float* in; float* out;
+  int32_t NC, IH, IW, OH, OW;
+  int32_t reserved0;
+} svx_resize_desc;
+
 /* binvox run-length decode (utils/binvox_rw.py:119-153 read_as_3d_array; utils/data_loaders.py:84-87): the payload
  * after the text header is (value, count) byte pairs; np.repeat(values, counts).astype(bool).reshape(dims) gives the
  * volume in file order x, z, y (y fastest); fix_coords transposes it to x, y, z.  B objects per launch: their
@@ -320,6 +333,15 @@ typedef struct svx_preprocess_desc {
   int32_t N, H, W, C, OH, OW;
   int32_t y0, y1, x0, x1;
   float mean[3], std[3], bg_norm[3];
+  int32_t reserved0;
+  /* optional per-image overrides (device arrays, or NULL):
+   * windows [N][4] = {y0, y1, x0, x1}: the bounding-box crops of utils/data_transforms.py:93-131 -- the window may leave
+   *   the image; rows / columns outside are the nearest edge pixel (the reference's np.pad(mode='edge')), i.e. source
+   *   coordinates clamp.  y1 > y0, x1 > x0 and the window must intersect the image (the reference raises otherwise).
+   * bg_norm_n [N][3]: per-image normalised background colour (RandomBackground with a proper colour range draws one
+   *   colour per sample, utils/data_transforms.py:433-435; the host draws, the kernel applies). */
+  const int32_t* windows;
+  const float* bg_norm_n;
 } svx_preprocess_desc;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -344,6 +366,7 @@ int svx_merger_fuse(const svx_mergefuse_desc*, void* stream);
 int svx_conv3to1(const svx_conv3to1_desc*, void* stream);
 int svx_voxel_metrics(const svx_metrics_desc*, void* stream);
 int svx_transpose(const svx_transpose_desc*, void* stream);
+int svx_resize_bilinear(const svx_resize_desc*, void* stream);
 int svx_binvox_decode(const svx_binvox_decode_desc*, void* stream);
 int svx_binvox_encode(const svx_binvox_encode_desc*, void* stream);
 int svx_preprocess(const svx_preprocess_desc*, void* stream);
@@ -367,6 +390,7 @@ int svx_plan_add_merger_fuse(svx_plan*, const svx_mergefuse_desc*);
 int svx_plan_add_conv3to1(svx_plan*, const svx_conv3to1_desc*);
 int svx_plan_add_voxel_metrics(svx_plan*, const svx_metrics_desc*);
 int svx_plan_add_transpose(svx_plan*, const svx_transpose_desc*);
+int svx_plan_add_resize_bilinear(svx_plan*, const svx_resize_desc*);
 /* Concurrency hints.  Ops are recorded into the current lane (default 0 = the caller's stream).  Ops of a side lane
  * k in [1, 8] run in order on the plan's side stream k, forked from the caller's stream where the lane's first op
  * since the last join sits in the op list; svx_plan_add_join makes the caller's stream wait for every side lane (the

@@ -49,15 +49,47 @@ def crop_window(h, w, crop_h, crop_w):
     return 0, h, 0, w
 
 
-def eval_transform(images_u8, img_size=(224, 224), crop_size=(128, 128), bg=(240, 240, 240), mean=(0.5, 0.5, 0.5),
-                   std=(0.5, 0.5, 0.5)):
-    """images_u8: uint8 [V, H, W, C] (C = 4: BGRA with alpha, or 3) -> float32 [V, 3, img_h, img_w]"""
+def bbox_windows(bounding_box, shapes):
+    """utils/data_transforms.py:93-128: square crop windows (y_top, y_bottom + 1, x_left, x_right + 1) around the
+    bounding box, possibly outside the image (the reference pads with np.pad(mode='edge'), i.e. coordinates clamp).
+    Faithful to the reference's loop, which re-assigns `bounding_box` to its pixel-scaled value inside the per-view
+    loop (:95-100): from the second view on the already scaled box is scaled again."""
     out = []
+    for (h, w) in shapes:
+        bounding_box = [bounding_box[0] * w, bounding_box[1] * h, bounding_box[2] * w, bounding_box[3] * h]
+        bw, bh = bounding_box[2] - bounding_box[0], bounding_box[3] - bounding_box[1]
+        xm, ym = (bounding_box[2] + bounding_box[0]) * .5, (bounding_box[3] + bounding_box[1]) * .5
+        sq = max(bw, bh)
+        x_left, x_right = int(xm - sq * .5), int(xm + sq * .5)
+        y_top, y_bottom = int(ym - sq * .5), int(ym + sq * .5)
+        out.append((y_top, y_bottom + 1, x_left, x_right + 1))
+    return out
+
+
+def eval_transform(images_u8, img_size=(224, 224), crop_size=(128, 128), bg=(240, 240, 240), mean=(0.5, 0.5, 0.5),
+                   std=(0.5, 0.5, 0.5), bounding_box=None, bg_range=None, rng=None):
+    """images_u8: uint8 [V, H, W, C] (C = 4: BGRA with alpha, or 3) -> float32 [V, 3, img_h, img_w].
+    bounding_box: normalised (x0, y0, x1, y1) as the Pascal3D / Pix3D loaders pass it (utils/data_loaders.py).
+    bg_range: ((lo, hi),) * 3 -- one colour per call drawn like utils/data_transforms.py:433-435 from `rng`
+    (default: numpy's global generator, as the reference uses)."""
+    out = []
+    if bg_range is not None:
+        rng = rng or np.random
+        bg = [rng.randint(bg_range[i][0], bg_range[i][1] + 1) for i in range(3)]
     bgc = np.array(bg, np.float64) / 255.
-    for u8 in images_u8:
+    wins = bbox_windows(list(bounding_box), [u8.shape[:2] for u8 in images_u8]) if bounding_box is not None else None
+    for vi, u8 in enumerate(images_u8):
         img = u8.astype(np.float32) / 255.
-        y0, y1, x0, x1 = crop_window(img.shape[0], img.shape[1], crop_size[0], crop_size[1])
-        img = resize_linear(img[y0:y1, x0:x1], img_size[0], img_size[1]).astype(np.float64)   # np.append upcasts
+        h, w = img.shape[:2]
+        if wins is not None:
+            y0, y1, x0, x1 = wins[vi]
+            ys = np.clip(np.arange(y0, y1), 0, h - 1)
+            xs = np.clip(np.arange(x0, x1), 0, w - 1)
+            crop = img[ys][:, xs]
+        else:
+            y0, y1, x0, x1 = crop_window(h, w, crop_size[0], crop_size[1])
+            crop = img[y0:y1, x0:x1]
+        img = resize_linear(crop, img_size[0], img_size[1]).astype(np.float64)   # np.append upcasts
         if img.shape[2] == 4:
             alpha = (img[:, :, 3:4] == 0).astype(np.float32)
             img = alpha * bgc[None, None, :] + (1 - alpha) * img[:, :, :3]

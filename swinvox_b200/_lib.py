@@ -79,7 +79,7 @@ class WinAttnDesc(C.Structure):
     _fields_ = [
         ("qkv", ptr), ("out", ptr), ("bias", ptr),
         ("N", i32), ("H", i32), ("W", i32), ("C", i32), ("heads", i32), ("shift", i32), ("scale", f32),
-        ("round_tf32", i32), ("dtype", i32),
+        ("round_tf32", i32), ("dtype", i32), ("reserved0", i32), ("range_flag", ptr),
     ]
 
 
@@ -147,12 +147,17 @@ class BinvoxEncodeDesc(C.Structure):
 
 class PreprocessDesc(C.Structure):
     _fields_ = [("inp", ptr), ("out", ptr), ("N", i32), ("H", i32), ("W", i32), ("C", i32), ("OH", i32), ("OW", i32),
-                ("y0", i32), ("y1", i32), ("x0", i32), ("x1", i32), ("mean", f32 * 3), ("std", f32 * 3), ("bg_norm", f32 * 3)]
+                ("y0", i32), ("y1", i32), ("x0", i32), ("x1", i32), ("mean", f32 * 3), ("std", f32 * 3), ("bg_norm", f32 * 3),
+                ("reserved0", i32), ("windows", ptr), ("bg_norm_n", ptr)]
+
+
+class ResizeDesc(C.Structure):
+    _fields_ = [("inp", ptr), ("out", ptr), ("NC", i32), ("IH", i32), ("IW", i32), ("OH", i32), ("OW", i32), ("reserved0", i32)]
 
 
 # order must match svx_desc_sizes()
 DESC_TYPES = [GemmDesc, Im2colDesc, PoolDesc, LnRowsDesc, LnSampleDesc, WinAttnDesc, DwConvDesc,
-              ViewAttnDesc, BilinearDesc, MergeFuseDesc, MetricsDesc, TransposeDesc, Conv3to1Desc, MlpDesc]
+              ViewAttnDesc, BilinearDesc, MergeFuseDesc, MetricsDesc, TransposeDesc, Conv3to1Desc, MlpDesc, ResizeDesc]
 
 # op name -> (immediate symbol, plan_add symbol, descriptor type)
 OPS = {
@@ -170,6 +175,7 @@ OPS = {
     "transpose": ("svx_transpose", "svx_plan_add_transpose", TransposeDesc),
     "conv3to1": ("svx_conv3to1", "svx_plan_add_conv3to1", Conv3to1Desc),
     "mlp": ("svx_mlp", "svx_plan_add_mlp", MlpDesc),
+    "resize_bilinear": ("svx_resize_bilinear", "svx_plan_add_resize_bilinear", ResizeDesc),
 }
 
 OTHER_SYMBOLS = ["svx_abi_version", "svx_last_error", "svx_desc_sizes", "svx_device_info", "svx_plan_create",

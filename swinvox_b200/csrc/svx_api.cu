@@ -25,7 +25,7 @@ int fail(const char* fmt, ...) {
 
 enum OpKind {
   OP_GEMM, OP_IM2COL, OP_POOL, OP_LNROWS, OP_LNSAMPLE, OP_WINATTN, OP_DWCONV, OP_VIEWATTN, OP_BILINEAR,
-  OP_MERGEFUSE, OP_METRICS, OP_TRANSPOSE, OP_CONV3TO1, OP_MLP, OP_JOIN
+  OP_MERGEFUSE, OP_METRICS, OP_TRANSPOSE, OP_CONV3TO1, OP_MLP, OP_RESIZE, OP_JOIN
 };
 
 struct Op {
@@ -45,6 +45,7 @@ struct Op {
     svx_conv3to1_desc conv3to1;
     svx_transpose_desc transpose;
     svx_mlp_desc mlp;
+    svx_resize_desc resize;
   } u;
   GemmPrepared* prepared = nullptr;
   MlpPrepared* mlp_prepared = nullptr;
@@ -67,6 +68,7 @@ int launch_op(Op& op, void* stream) {
     case OP_TRANSPOSE: return transpose_launch(op.u.transpose, stream);
     case OP_CONV3TO1: return conv3to1_launch(op.u.conv3to1, stream);
     case OP_MLP: return mlp_launch(op.u.mlp, op.mlp_prepared, stream);
+    case OP_RESIZE: return resize_launch(op.u.resize, stream);
     case OP_JOIN: return 0;
   }
   return fail("unknown op kind");
@@ -101,7 +103,8 @@ int svx_desc_sizes(int32_t* sizes, int n) {
                        (int32_t)sizeof(svx_dwconv_desc),   (int32_t)sizeof(svx_viewattn_desc),
                        (int32_t)sizeof(svx_bilinear_desc), (int32_t)sizeof(svx_mergefuse_desc),
                        (int32_t)sizeof(svx_metrics_desc),  (int32_t)sizeof(svx_transpose_desc),
-                       (int32_t)sizeof(svx_conv3to1_desc), (int32_t)sizeof(svx_mlp_desc)};
+                       (int32_t)sizeof(svx_conv3to1_desc), (int32_t)sizeof(svx_mlp_desc),
+                       (int32_t)sizeof(svx_resize_desc)};
   const int have = (int)(sizeof(s) / sizeof(s[0]));
   for (int i = 0; i < n && i < have; ++i) sizes[i] = s[i];
   return have;
@@ -152,6 +155,7 @@ SVX_IMMEDIATE(svx_merger_fuse, svx_mergefuse_desc, mergefuse_launch)
 SVX_IMMEDIATE(svx_voxel_metrics, svx_metrics_desc, metrics_launch)
 SVX_IMMEDIATE(svx_transpose, svx_transpose_desc, transpose_launch)
 SVX_IMMEDIATE(svx_conv3to1, svx_conv3to1_desc, conv3to1_launch)
+SVX_IMMEDIATE(svx_resize_bilinear, svx_resize_desc, resize_launch)
 
 svx_plan* svx_plan_create(void) { return new svx_plan(); }
 
@@ -218,6 +222,7 @@ SVX_PLAN_ADD(svx_plan_add_merger_fuse, svx_mergefuse_desc, OP_MERGEFUSE, mergefu
 SVX_PLAN_ADD(svx_plan_add_voxel_metrics, svx_metrics_desc, OP_METRICS, metrics)
 SVX_PLAN_ADD(svx_plan_add_transpose, svx_transpose_desc, OP_TRANSPOSE, transpose)
 SVX_PLAN_ADD(svx_plan_add_conv3to1, svx_conv3to1_desc, OP_CONV3TO1, conv3to1)
+SVX_PLAN_ADD(svx_plan_add_resize_bilinear, svx_resize_desc, OP_RESIZE, resize)
 
 int svx_plan_set_lane(svx_plan* p, int lane) {
   if (!p || lane < 0 || lane > kMaxLanes) return fail("svx_plan_set_lane: lane must be in [0, %d]", kMaxLanes);

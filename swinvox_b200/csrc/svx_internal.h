@@ -59,6 +59,7 @@ int mergefuse_launch(const svx_mergefuse_desc& d, void* stream);
 int conv3to1_launch(const svx_conv3to1_desc& d, void* stream);
 int metrics_launch(const svx_metrics_desc& d, void* stream);
 int transpose_launch(const svx_transpose_desc& d, void* stream);
+int resize_launch(const svx_resize_desc& d, void* stream);
 
 // kernel launches a single op issues (for svx_plan_num_launches)
 int gemm_num_launches(const svx_gemm_desc& d);

@@ -189,7 +189,6 @@ namespace {
 
 __global__ void __launch_bounds__(256) preprocess_kernel(const svx_preprocess_desc d) {
   const long long total = (long long)d.N * d.OH * d.OW;
-  const int ch = d.y1 - d.y0, cw = d.x1 - d.x0;   // crop window
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int ox = (int)(idx % d.OW);
     const long long t = idx / d.OW;
@@ -204,15 +203,24 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const svx_preprocess_de
       if (s >= src - 1) { s = src - 1; f = 0.f; }
       i0 = s; i1 = s + 1 < src ? s + 1 : src - 1; w1 = f;
     };
+    // crop window of this image; a per-image window may leave the image: outside coordinates clamp (edge padding)
+    int y0 = d.y0, y1 = d.y1, x0 = d.x0, x1 = d.x1;
+    if (d.windows) {
+      const int4 wv = __ldg(reinterpret_cast<const int4*>(d.windows) + n);
+      y0 = wv.x; y1 = wv.y; x0 = wv.z; x1 = wv.w;
+    }
+    const int ch = y1 - y0, cw = x1 - x0;
     int xa, xb, ya, yb;
     float wx, wy;
     coord(ox, cw, d.OW, xa, xb, wx);
     coord(oy, ch, d.OH, ya, yb, wy);
+    auto cl = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
+    const int sya = cl(y0 + ya, d.H - 1), syb = cl(y0 + yb, d.H - 1), sxa = cl(x0 + xa, d.W - 1), sxb = cl(x0 + xb, d.W - 1);
     const uint8_t* img = d.in + n * (long long)d.H * d.W * d.C;
-    const uint8_t* p00 = img + ((long long)(d.y0 + ya) * d.W + d.x0 + xa) * d.C;
-    const uint8_t* p01 = img + ((long long)(d.y0 + ya) * d.W + d.x0 + xb) * d.C;
-    const uint8_t* p10 = img + ((long long)(d.y0 + yb) * d.W + d.x0 + xa) * d.C;
-    const uint8_t* p11 = img + ((long long)(d.y0 + yb) * d.W + d.x0 + xb) * d.C;
+    const uint8_t* p00 = img + ((long long)sya * d.W + sxa) * d.C;
+    const uint8_t* p01 = img + ((long long)sya * d.W + sxb) * d.C;
+    const uint8_t* p10 = img + ((long long)syb * d.W + sxa) * d.C;
+    const uint8_t* p11 = img + ((long long)syb * d.W + sxb) * d.C;
     auto lerp2 = [&](int c) {
       const float v00 = __fdiv_rn((float)p00[c], 255.f), v01 = __fdiv_rn((float)p01[c], 255.f);
       const float v10 = __fdiv_rn((float)p10[c], 255.f), v11 = __fdiv_rn((float)p11[c], 255.f);
@@ -224,7 +232,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const svx_preprocess_de
     float* out = d.out + n * 3LL * d.OH * d.OW + (long long)oy * d.OW + ox;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float v = background ? d.bg_norm[c] : (lerp2(c) - d.mean[c]) / d.std[c];
+      const float bgv = d.bg_norm_n ? __ldg(d.bg_norm_n + n * 3 + c) : d.bg_norm[c];
+      const float v = background ? bgv : (lerp2(c) - d.mean[c]) / d.std[c];
       out[(long long)c * d.OH * d.OW] = v;
     }
   }
@@ -238,10 +247,12 @@ extern "C" int svx_preprocess(const svx_preprocess_desc* d, void* stream) {
   if (!d) return fail("svx_preprocess: null descriptor");
   SVX_REQUIRE(d->in && d->out && d->N > 0 && d->H > 0 && d->W > 0 && (d->C == 3 || d->C == 4) && d->OH > 0 && d->OW > 0,
               "preprocess: bad description");
-  SVX_REQUIRE(d->y0 >= 0 && d->x0 >= 0 && d->y1 > d->y0 && d->x1 > d->x0 && d->y1 <= d->H && d->x1 <= d->W,
+  SVX_REQUIRE(d->windows || (d->y0 >= 0 && d->x0 >= 0 && d->y1 > d->y0 && d->x1 > d->x0 && d->y1 <= d->H && d->x1 <= d->W),
               "preprocess: crop window outside the image");
-  SVX_REQUIRE((long long)(2 * d->OW + 1) * (d->x1 - d->x0) < 0x7fffffffLL && (long long)(2 * d->OH + 1) * (d->y1 - d->y0) < 0x7fffffffLL,
+  SVX_REQUIRE(d->windows || ((long long)(2 * d->OW + 1) * (d->x1 - d->x0) < 0x7fffffffLL &&
+                             (long long)(2 * d->OH + 1) * (d->y1 - d->y0) < 0x7fffffffLL),
               "preprocess: image too large");
+  SVX_REQUIRE(!d->windows || (reinterpret_cast<uintptr_t>(d->windows) & 15) == 0, "preprocess: windows must be 16-byte aligned");
   const long long total = (long long)d->N * d->OH * d->OW;
   long long grid = (total + 255) / 256;
   if (grid > 148 * 16) grid = 148 * 16;

@@ -1128,7 +1128,34 @@ __global__ void interleave4_kernel(const svx_transpose_desc d, long long total) 
   }
 }
 
+// ---- F.interpolate(mode="bilinear", align_corners=False) on planar fp32 images (the Swin wrapper's input resize) -----------
+__global__ void resize_planar_kernel(const svx_resize_desc d, long long total) {
+  const float sy = (float)d.IH / (float)d.OH, sx = (float)d.IW / (float)d.OW;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % d.OW);
+    const long long t = idx / d.OW;
+    const int oy = (int)(t % d.OH);
+    const long long nc = t / d.OH;
+    const float fy = fmaxf((oy + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * sx - 0.5f, 0.f);
+    const int y0 = min((int)fy, d.IH - 1), x0 = min((int)fx, d.IW - 1);
+    const int y1 = min(y0 + 1, d.IH - 1), x1 = min(x0 + 1, d.IW - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float* img = d.in + nc * (long long)d.IH * d.IW;
+    const float a = __ldg(img + (long long)y0 * d.IW + x0), b = __ldg(img + (long long)y0 * d.IW + x1);
+    const float c = __ldg(img + (long long)y1 * d.IW + x0), e = __ldg(img + (long long)y1 * d.IW + x1);
+    d.out[idx] = (1.f - ly) * ((1.f - lx) * a + lx * b) + ly * ((1.f - lx) * c + lx * e);
+  }
+}
+
 }  // namespace
+
+int resize_launch(const svx_resize_desc& d, void* stream) {
+  SVX_REQUIRE(d.in && d.out && d.NC > 0 && d.IH > 0 && d.IW > 0 && d.OH > 0 && d.OW > 0, "resize_bilinear: bad description");
+  const long long total = (long long)d.NC * d.OH * d.OW;
+  resize_planar_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d, total);
+  SVX_LAUNCH_OK("resize_planar_kernel");
+  return 0;
+}
 
 int im2col_launch(const svx_im2col_desc& d, void* stream) {
   const int K = d.KD * d.KH * d.KW * d.C;

@@ -16,13 +16,19 @@
 // -100 attention mask of the shifted blocks is recomputed from the window position ("a key is masked iff it lies in a
 // different wrap-around piece than the query"), so neither a rolled copy nor a mask tensor exists.
 //
-// Storage type T: fp32 (values stored TF32-rounded; kind::tf32 operands, P rounded to TF32) or bf16 (kind::f16 with
-// bf16 operands).  Accumulation, softmax statistics and the bias are fp32 either way.
+// Storage type T: bf16 (kind::f16 with bf16 operands throughout) or fp32.  fp32 tensors of this path hold TF32-rounded
+// values: S = Q K^T runs as kind::tf32 on the rows as stored; for O = P V the probabilities are written as fp16 (11
+// significant bits, what a TF32 rounding keeps) and two converter warps rewrite the V rows as fp16 (exact for TF32-rounded
+// |v| in [6.1e-5, 65504], saturating beyond -- reported through svx_winattn_desc.range_flag), because kind::tf32 accepts an
+// MN-major operand only in a 32-byte-interleaved layout the 16-byte row gather cannot produce, while 16-bit MN-major
+// operands take the rows as they are; it also halves the P V instructions.  Accumulation, softmax statistics and the bias
+// are fp32 either way.
 //
-// Warp roles (12 warps):  0-3 / 4-7  two softmax + output groups (TMEM lane quarter = warp % 4), alternating items
+// Warp roles (13 warps):  0-3 / 4-7  two softmax + output groups (TMEM lane quarter = warp % 4), alternating items
 //                         8-9        row gather: cp.async 16-byte chunks of the token rows into 128B / 64B-swizzled
 //                                    operand tiles (a ring of stages)
 //                         10         MMA issuer (one elected thread), owns the TMEM allocation
+//                         11-12      fp32 storage only: V rows fp32 -> fp16
 #include <cuda_runtime.h>
 
 #include "svx_internal.h"
@@ -32,9 +38,9 @@ namespace svx {
 namespace {
 
 constexpr int WS = 7, WT = 49, HD = 32;
-constexpr int WU_THREADS = 11 * 32;
+constexpr int WU_THREADS = 13 * 32;
 constexpr int WU_PRODUCER_WARPS = 2;
-constexpr int WU_LAG = 1;                       // cp.async groups a producer warp keeps in flight beyond the current one
+constexpr int WU_PREFETCH = 6;                  // items ahead whose token rows are pulled into L2 (prefetch.global.L2)
 constexpr float kLog2e = 1.4426950408889634f;
 
 template <typename T>
@@ -44,23 +50,24 @@ struct WuCfg {
   static constexpr int kMatB = 128 * kRowB;                  // one 128-row operand tile: 16 KB | 8 KB
   static constexpr int kStageB = 3 * kMatB;                  // Q | K | V
   static constexpr int kStages = kBf ? 4 : 3;
-  static constexpr int kPAtoms = 128 * (int)sizeof(T) / 128; // 128-byte-wide K atoms of the P tile: 4 | 2
-  static constexpr int kPBytes = kPAtoms * 128 * 128;        // 64 KB | 32 KB
+  static constexpr int kV16B = kBf ? 0 : 128 * 64;           // fp32 storage: the fp16 copy of V, one per stage (8 KB)
+  static constexpr int kPBytes = 2 * 128 * 128;              // P is 16-bit either way: two 64-key atoms of 128 rows x 128 B
   static constexpr int kPBufs = kBf ? 2 : 1;
   static constexpr int kBiasB = (WT * WT * 4 + 127) / 128 * 128;
   static constexpr int kKS = kRowB / 32;                     // MMA K steps of S = Q K^T (32 bytes each): 4 | 2
-  static constexpr int kKP = 128 * (int)sizeof(T) / 32;      // MMA K steps of O = P V over the 128 keys: 16 | 8
-  static constexpr int kSmem = 1024 + kStages * kStageB + kPBufs * kPBytes + kBiasB + 256;
+  static constexpr int kKP = 8;                              // MMA K steps of O = P V: 128 keys, 16 per step
+  static constexpr int kSmem = 1024 + kStages * (kStageB + kV16B) + kPBufs * kPBytes + kBiasB + 256;
   static_assert(kSmem <= 232448, "window attention shared memory");
 };
 
-// instruction descriptors: fp32 accumulate; A K-major; B K-major (S) or MN-major (O = P V: bit 16)
-__host__ __device__ constexpr uint32_t wu_idesc(bool bf, uint32_t n, bool b_mn) {
-  const uint32_t fmt = bf ? 1u : 2u;   // bf16 : tf32
+// instruction descriptors: fp32 accumulate; A K-major; B K-major (S) or MN-major (O = P V: bit 16).
+// fmt: operand format code 0 = fp16, 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32)
+__host__ __device__ constexpr uint32_t wu_idesc(uint32_t fmt, uint32_t n, bool b_mn) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (b_mn ? (1u << 16) : 0u) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
-// MN-major operand tile as the row gather leaves it: rows = keys (the MMA's K), 32 dims contiguous per row (the MMA's N =
-// one swizzle atom wide); groups of 8 keys are `sbo` bytes apart.  Layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
+// Operand tile descriptor.  K-major (Q, K): rows of 128 | 64 bytes, 8-row groups `sbo` bytes apart.  MN-major (the 16-bit
+// V tile): rows = keys (the MMA's K) of 64 bytes = 32 dims (the MMA's N = one swizzle atom wide), exactly as the rows lie
+// in the qkv tensor; groups of 8 keys `sbo` = 512 bytes apart.  Layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
 __device__ __forceinline__ uint64_t wu_desc(uint32_t smem_addr, uint32_t sbo, uint32_t layout) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
@@ -96,9 +103,11 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t stage_smem = smem_base;
-  const uint32_t p_smem = stage_smem + NS * K::kStageB;
-  uint8_t* p_gen = smem_gen + NS * K::kStageB;
-  float* sbias = reinterpret_cast<float*>(smem_gen + NS * K::kStageB + K::kPBufs * K::kPBytes);
+  const uint32_t v16_smem = stage_smem + NS * K::kStageB;                   // fp32 storage: fp16 V tiles, one per stage
+  constexpr int kPOff = NS * (K::kStageB + K::kV16B);
+  const uint32_t p_smem = smem_base + kPOff;
+  uint8_t* p_gen = smem_gen + kPOff;
+  float* sbias = reinterpret_cast<float*>(smem_gen + kPOff + K::kPBufs * K::kPBytes);
   const uint32_t bar_base = p_smem + K::kPBufs * K::kPBytes + K::kBiasB;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };                 // stage s holds Q, K, V of an item
   auto empty_bar = [&](int s) { return bar_base + 8u * (NS + s); };         // every MMA that reads stage s has completed
@@ -108,8 +117,9 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
   auto p_empty = [&](int b) { return bar_base + 8u * (2 * NS + 6 + b); };   // the P V MMAs have read P buffer b
   auto o_full = [&](int b) { return bar_base + 8u * (2 * NS + 8 + b); };
   auto o_empty = [&](int b) { return bar_base + 8u * (2 * NS + 10 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * NS + 12);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * NS + 12));
+  auto v16_full = [&](int s) { return bar_base + 8u * (2 * NS + 12 + s); };   // the fp16 copy of stage s's V rows is ready
+  const uint32_t tmem_slot = bar_base + 8u * (3 * NS + 12);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (3 * NS + 12));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.x % d.heads;
@@ -121,12 +131,16 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
 
   // ---- one-time setup: zero the operand stages and P (padding rows / off-diagonal blocks are never written again),
   // the head's bias (x log2 e), barriers, TMEM ----------------------------------------------------------------------
-  for (int i = threadIdx.x; i < (NS * K::kStageB + K::kPBufs * K::kPBytes) / 16; i += WU_THREADS)
+  for (int i = threadIdx.x; i < (kPOff + K::kPBufs * K::kPBytes) / 16; i += WU_THREADS)
     reinterpret_cast<uint4*>(smem_gen)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = threadIdx.x; i < WT * WT; i += WU_THREADS) sbias[i] = __ldg(d.bias + (long long)head * WT * WT + i) * kLog2e;
   if (warp == 10) {
     if (lane == 0) {
-      for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), WU_PRODUCER_WARPS); mbar_init(empty_bar(s), 1u); }
+      for (int s = 0; s < NS; ++s) {
+        mbar_init(full_bar(s), WU_PRODUCER_WARPS);
+        mbar_init(empty_bar(s), 1u);
+        mbar_init(v16_full(s), 2u);
+      }
       for (int b = 0; b < 2; ++b) {
         mbar_init(s_full(b), 1u); mbar_init(s_empty(b), 4u);
         mbar_init(p_full(b), 4u); mbar_init(p_empty(b), 1u);
@@ -167,8 +181,27 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
     const int ch = lane % CH, rsub = lane / CH;
     const size_t tok_pitch = (size_t)3 * d.C * sizeof(T), c_bytes = (size_t)d.C * sizeof(T);
     const uint8_t* qkvb = reinterpret_cast<const uint8_t*>(d.qkv) + (size_t)head * HD * sizeof(T) + ch * 16;
+    // The stage ring holds at most NS - 1 items in flight, about one item time of slack against ~1 us of HBM latency
+    // (measured: 2.5 TB/s, latency-bound).  The rows of the items WU_PREFETCH ahead are therefore pulled into L2 first
+    // (148 SMs x 6 items x 38 KB = 33 MB of the 126 MB L2), so the cp.async below hit L2.
+    auto prefetch_item = [&](int i) {
+      const int win = 2 * item_of(i) + w;
+      if (i < nt && win < num_windows) {
+        const WinPos wp = window_pos(win);
+        for (int q = lane; q < WT; q += 32) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(d.qkv) + (size_t)head * HD * sizeof(T) +
+                               (size_t)token_of(wp, q / WS, q % WS) * tok_pitch;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + c_bytes));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 2 * c_bytes));
+        }
+      }
+    };
+    for (int i = 0; i < WU_PREFETCH; ++i) prefetch_item(i);
+    constexpr int LAG = NS - 1;                  // cp.async groups a producer warp keeps in flight
     for (int i = 0; i < nt; ++i) {
       const int s = i % NS;
+      prefetch_item(i + WU_PREFETCH);
       mbar_wait(empty_bar(s), (((uint32_t)(i / NS)) & 1u) ^ 1u);
       const int win = 2 * item_of(i) + w;
       if (win < num_windows) {
@@ -189,25 +222,25 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
         }
       }
       cp_async_commit();
-      if (i >= WU_LAG) {
-        cp_async_wait<WU_LAG>();
+      if (i >= LAG) {
+        cp_async_wait<LAG>();
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar((i - WU_LAG) % NS));
+        if (lane == 0) mbar_arrive(full_bar((i - LAG) % NS));
       }
     }
     cp_async_wait<0>();
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0)
-      for (int i = (nt > WU_LAG ? nt - WU_LAG : 0); i < nt; ++i) mbar_arrive(full_bar(i % NS));
+      for (int i = (nt > LAG ? nt - LAG : 0); i < nt; ++i) mbar_arrive(full_bar(i % NS));
   } else if (warp == 10) {
     // ---- MMA issuer: S(0) S(1) | PV(0) S(2) | PV(1) S(3) ... -------------------------------------------------------
     if (elect_one()) {
-      constexpr uint32_t idesc_s = wu_idesc(BF, 128, false);
-      constexpr uint32_t idesc_o = wu_idesc(BF, 32, true);
+      constexpr uint32_t idesc_s = wu_idesc(BF ? 1u : 2u, 128, false);   // bf16 | tf32
+      constexpr uint32_t idesc_o = wu_idesc(BF ? 1u : 0u, 32, true);     // bf16 | fp16, V MN-major
       constexpr uint32_t lay = BF ? 4u : 2u;
-      constexpr uint32_t sbo = 8 * K::kRowB;     // 8-row groups of the Q / K / V tiles: 1024 | 512 bytes
+      constexpr uint32_t sbo = 8 * K::kRowB;     // 8-row groups of the Q / K tiles: 1024 | 512 bytes
       auto issue_s = [&](int i) {
         const int s = i % NS, b = i & 1;
         mbar_wait(full_bar(s), ((uint32_t)(i / NS)) & 1u);
@@ -225,19 +258,19 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       auto issue_pv = [&](int i) {
         const int s = i % NS, b = i & 1, pb = K::kPBufs == 2 ? b : 0;
         const uint32_t pi = K::kPBufs == 2 ? (uint32_t)i >> 1 : (uint32_t)i;
+        if constexpr (!BF) mbar_wait(v16_full(s), ((uint32_t)(i / NS)) & 1u);
         mbar_wait(p_full(pb), pi & 1u);
         mbar_wait(o_empty(b), (((uint32_t)i >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t v_addr = stage_smem + s * K::kStageB + 2 * K::kMatB;
+        const uint32_t v_addr = BF ? stage_smem + s * K::kStageB + 2 * K::kMatB : v16_smem + s * K::kV16B;
         const uint32_t p_addr = p_smem + pb * K::kPBytes;
 #pragma unroll
         for (int k = 0; k < K::kKP; ++k) {
-          // A: k-th 32-byte step of the P rows (four steps per 128-byte atom, atoms 16 KB apart);
-          // B: keys of this step = 1024 bytes of V rows (8 fp32 rows | 16 bf16 rows)
+          // A: k-th 32-byte step (16 keys) of the P rows: four steps per 128-byte atom, atoms 16 KB apart;
+          // B: the 16 V rows of this step = 1024 bytes (two 8-key groups 512 bytes apart)
           const uint64_t da = umma_desc_sw128(p_addr + (k >> 2) * (128 * 128)) + 2u * (k & 3);
-          const uint64_t db = wu_desc(v_addr + k * 1024, sbo, lay);
-          if constexpr (BF) umma_f16(tmem_base + 256 + b * 32, da, db, idesc_o, k != 0 ? 1u : 0u);
-          else umma_tf32(tmem_base + 256 + b * 32, da, db, idesc_o, k != 0 ? 1u : 0u);
+          const uint64_t db = wu_desc(v_addr + k * 1024, 512u, 4u);
+          umma_f16(tmem_base + 256 + b * 32, da, db, idesc_o, k != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar(s));     // Q, K, V of this item are no longer needed
         umma_commit(p_empty(pb));
@@ -251,6 +284,41 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       }
     }
     __syncwarp();
+  } else if (warp >= 11) {
+    // ---- fp32 storage: V rows (fp32, 128B-swizzled as gathered) -> fp16 rows of 64 bytes (64B swizzle) ---------------
+    if constexpr (!BF) {
+      const int ct = threadIdx.x - 11 * 32;      // 0..63
+      uint8_t* v16_gen = smem_gen + NS * K::kStageB;
+      uint32_t amax = 0u;
+      for (int i = 0; i < nt; ++i) {
+        const int s = i % NS;
+        mbar_wait(full_bar(s), ((uint32_t)(i / NS)) & 1u);
+        const uint8_t* src = smem_gen + s * K::kStageB + 2 * K::kMatB;
+        uint8_t* dst = v16_gen + s * K::kV16B;
+        // unit = (tile row, 16-byte output chunk = 8 dims); only the real rows of the two windows
+        for (int u = ct; u < 2 * WT * 4; u += 64) {
+          const int oc = u & 3, rr = u >> 2;
+          const int row = rr < WT ? rr : 64 + rr - WT;
+          const float4 a = *reinterpret_cast<const float4*>(src + row * 128 + (((2 * oc) ^ (row & 7)) << 4));
+          const float4 b = *reinterpret_cast<const float4*>(src + row * 128 + (((2 * oc + 1) ^ (row & 7)) << 4));
+          const uint32_t m0 = max(max(__float_as_uint(a.x) & 0x7fffffffu, __float_as_uint(a.y) & 0x7fffffffu),
+                                  max(__float_as_uint(a.z) & 0x7fffffffu, __float_as_uint(a.w) & 0x7fffffffu));
+          const uint32_t m1 = max(max(__float_as_uint(b.x) & 0x7fffffffu, __float_as_uint(b.y) & 0x7fffffffu),
+                                  max(__float_as_uint(b.z) & 0x7fffffffu, __float_as_uint(b.w) & 0x7fffffffu));
+          amax = max(amax, max(m0, m1));
+          uint4 o;
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(a.y), "f"(a.x));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(a.w), "f"(a.z));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(b.y), "f"(b.x));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(b.w), "f"(b.z));
+          *reinterpret_cast<uint4*>(dst + row * 64 + ((oc ^ ((row >> 1) & 3)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(v16_full(s));
+      }
+      if (d.range_flag && amax > 0x477fe000u) atomicOr(d.range_flag, 1);   // a V value beyond fp16's 65504 saturated
+    }
   } else {
     // ---- softmax + output: group g = warp / 4 takes the items with i % 2 == g; thread = one query row ----------------
     const int grp = warp >> 2, quarter = warp & 3;
@@ -309,32 +377,18 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       mbar_wait(p_empty(pb), (pi & 1u) ^ 1u);
       if (live) {
         uint8_t* prow = p_gen + pb * K::kPBytes + r * 128;
-        if constexpr (BF) {
-          // 64 bf16 slots of window w = atom w; chunk c holds slots 8c .. 8c+7
+        // 64 sixteen-bit slots of window w = atom w; chunk c holds slots 8c .. 8c+7 (bf16, or fp16 for fp32 storage)
 #pragma unroll
-          for (int c = 0; c < 7; ++c) {
-            uint32_t u[4];
+        for (int c = 0; c < 7; ++c) {
+          uint32_t u[4];
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              const int j0 = 8 * c + 2 * h;
-              u[h] = pack_bf16x2(j0 < WT ? e[j0 < WT ? j0 : 0] : 0.f, j0 + 1 < WT ? e[j0 + 1 < WT ? j0 + 1 : 0] : 0.f);
-            }
-            *reinterpret_cast<uint4*>(prow + w * (128 * 128) + ((c ^ (r & 7)) << 4)) = make_uint4(u[0], u[1], u[2], u[3]);
+          for (int h = 0; h < 4; ++h) {
+            const int j0 = 8 * c + 2 * h;
+            const float lo = j0 < WT ? e[j0 < WT ? j0 : 0] : 0.f, hi = j0 + 1 < WT ? e[j0 + 1 < WT ? j0 + 1 : 0] : 0.f;
+            if constexpr (BF) u[h] = pack_bf16x2(lo, hi);
+            else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u[h]) : "f"(hi), "f"(lo));
           }
-        } else {
-          // 64 fp32 slots of window w = atoms 2w, 2w+1; chunk c of atom a holds slots 32a' + 4c .. + 3.  The MMA truncates
-          // fp32 to TF32: adding half a TF32 ulp first makes that a round-to-nearest
-#pragma unroll
-          for (int c = 0; c < 13; ++c) {
-            float f[4];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              const int j = 4 * c + h;
-              f[h] = j < WT ? __uint_as_float(__float_as_uint(e[j < WT ? j : 0]) + 0x1000u) : 0.f;
-            }
-            *reinterpret_cast<float4*>(prow + (2 * w + (c >> 3)) * (128 * 128) + (((c & 7) ^ (r & 7)) << 4)) =
-                make_float4(f[0], f[1], f[2], f[3]);
-          }
+          *reinterpret_cast<uint4*>(prow + w * (128 * 128) + ((c ^ (r & 7)) << 4)) = make_uint4(u[0], u[1], u[2], u[3]);
         }
       }
       fence_proxy_async_smem();

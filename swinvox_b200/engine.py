@@ -687,8 +687,12 @@ class Plan:
         self._add("layernorm_sample", d, name, 0.0, 2.0 * x.esize * d.N * d.L)
         return out
 
-    def window_attention(self, qkv, out, bias, H, W, heads, shift, scale, round_out=True, name=None):
+    def window_attention(self, qkv, out, bias, H, W, heads, shift, scale, round_out=True, name=None, range_flag=None):
+        """range_flag: optional device int32[1] the fp32-storage kernel sets when a V value exceeded fp16's finite range
+        (its P V product runs on fp16 operands)"""
         d = _lib.WinAttnDesc()
+        if range_flag is not None and not qkv.bf16:
+            d.range_flag = self.hold(range_flag).data_ptr()
         d.qkv, d.out, d.bias = self.hold(qkv).buf.data_ptr(), self.hold(out).buf.data_ptr(), self.hold(bias).data_ptr()
         d.N, d.H, d.W, d.C, d.heads, d.shift, d.scale = qkv.N, H, W, out.C, heads, shift, scale
         d.round_tf32 = 1 if round_out else 0
@@ -762,6 +766,14 @@ class Plan:
         d.B, d.P, d.T = B, P, thresholds.numel()
         self._add("voxel_metrics", d, name, 0.0, 8.0 * B * P)
         return counts
+
+    def resize_bilinear(self, src, dst, name=None):
+        """planar fp32 [N, C, IH, IW] -> [N, C, OH, OW], F.interpolate(mode="bilinear", align_corners=False)"""
+        d = _lib.ResizeDesc()
+        d.inp, d.out = self.hold(src).data_ptr(), self.hold(dst).data_ptr()
+        d.NC, d.IH, d.IW, d.OH, d.OW = src.shape[0] * src.shape[1], src.shape[2], src.shape[3], dst.shape[2], dst.shape[3]
+        self._add("resize_bilinear", d, name or "resize", 0.0, 4.0 * (src.numel() + dst.numel()))
+        return dst
 
     def transpose(self, src, dst, N, Cc, P, Cs, to_channels_last, round_out=False, name=None, rows=None):
         """rows = (row_w, row_pitch, row_x0): write the 4-channel channels-last image with zero columns around each row"""

@@ -180,6 +180,11 @@ class BatchedEvaluator:
             import warnings
             warnings.warn("swinvox_b200: merger activations exceeded fp16's range (65504) during this evaluation; the fp16 "
                           "tensor-core operands saturated.  The merger now uses tf32 operands: re-run the evaluation.")
+        enc = getattr(self.recon, "encoder", None)
+        if enc is not None and hasattr(enc, "attention_saturated") and enc.attention_saturated():
+            import warnings
+            warnings.warn("swinvox_b200: a window-attention value exceeded fp16's range (65504) during this evaluation; the "
+                          "fp16 P.V operands saturated and the affected outputs are not within the parity tolerance.")
         self._reduce_over_ranks()
         nt = len(self._tax_index)
         packed = torch.cat([self._iou[:nt].flatten(), self._fsc[:nt].flatten(), self._cnt[:nt], self._loss]).cpu().numpy()

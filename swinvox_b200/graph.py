@@ -41,7 +41,8 @@ def stage_image(plan, img, N):
     if key not in plan.taps:
         pitch, x0 = img_layout(plan)
         a = plan.new_act(N, 1, 224, pitch, 4, zero=True)
-        plan.transpose(img, a.buf, N, 3, 224 * 224, 4, True, round_out=True, name="image.nhwc4", rows=(224, pitch, x0))
+        cin = img.shape[1]   # 3 (4 at most: one 16-byte fp32 pixel)
+        plan.transpose(img, a.buf, N, cin, 224 * 224, 4, True, round_out=True, name="image.nhwc4", rows=(224, pitch, x0))
         plan.taps[key] = a
     return plan.taps[key]
 
@@ -139,10 +140,10 @@ def lower_swin(plan, swin, img, N, stage_tail=None):
     if plan.dtype == torch.bfloat16:
         # patch embedding over pixel pairs (16 bytes): image columns 4j .. 4j+3 are staged columns 4j+2 .. 4j+5 = pairs
         # 2j+1, 2j+2 -> 4 kh x 2 pair taps of 8 channels, K = 64, stride 2 in pair units
-        w = pe.proj.weight.detach().float()                                  # [96, 3, 4, 4]
+        w = pe.proj.weight.detach().float()                                  # [96, Cin <= 4, 4, 4]
         Wp = torch.zeros(96, 4, 2, 2, 4, dtype=torch.float32, device=w.device)   # [co, kh, pair, pixel, channel]
         for kw in range(4):
-            Wp[:, :, kw // 2, kw % 2, :3] = w[:, :, :, kw].permute(0, 2, 1)
+            Wp[:, :, kw // 2, kw % 2, :w.shape[1]] = w[:, :, :, kw].permute(0, 2, 1)
         pairs = Act(x4.buf.view(-1, 8), N, 1, 224, pitch // 2, 8)
         plan.conv(pairs, E.pack_matrix(Wp.reshape(96, 64), pe.proj.bias, dev),
                   [(0, kh, x0 // 2 + pr) for kh in range(4) for pr in range(2)], emb, stride=(1, 4, 2), rows_dhw=(1, 56, 56),
@@ -178,7 +179,10 @@ def lower_swin(plan, swin, img, N, stage_tail=None):
             plan.linear(y, E.pack_matrix(blk.attn.qkv.weight, blk.attn.qkv.bias, dev), qkv, round_out=True, name=nm + ".qkv")
             att = plan.new_act(N, 1, H, H, Cc)
             bias = relative_position_bias(blk.attn.relative_position_bias_table, heads).to(dev)
-            plan.window_attention(qkv, att, bias, H, H, heads, shift, 32 ** -0.5, name=nm + ".attn")
+            if "attn_range_flag" not in plan.taps:
+                plan.taps["attn_range_flag"] = plan.zeros(1, dtype=torch.int32)
+            plan.window_attention(qkv, att, bias, H, H, heads, shift, 32 ** -0.5, name=nm + ".attn",
+                                  range_flag=plan.taps["attn_range_flag"])
             x1 = plan.new_act(N, 1, H, H, Cc)
             plan.linear(att, E.pack_matrix(blk.attn.proj.weight, blk.attn.proj.bias, dev), x1, residual=x,
                         name=nm + ".proj")

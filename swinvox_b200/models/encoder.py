@@ -67,6 +67,13 @@ class Encoder(PlannedModule):
 
         return self._plan_for((B, V, str(device), self.compute_dtype), build)
 
+    def attention_saturated(self):
+        """True if a window-attention V value exceeded fp16's finite range (65504) in any forward since the plans were
+        built: with fp32 / TF32 storage the P V product of the attention kernel runs on fp16 operands, which is exact for
+        this path's TF32-rounded values only inside that range.  Synchronises; meant for the end of an evaluation."""
+        return any(int(e[0].taps["attn_range_flag"].item()) != 0 for e in self._plans.values()
+                   if "attn_range_flag" in e[0].taps)
+
     def forward(self, rendering_images):
         self._guard(rendering_images)
         B, V, Cc, H, W = rendering_images.shape

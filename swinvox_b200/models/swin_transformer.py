@@ -113,21 +113,27 @@ class SwinTransformer(PlannedModule):
         self.in_channels = in_channels
 
     def forward(self, x):
+        """x: [N, in_channels, H, W] fp32.  Inputs that are not img_size x img_size are resized first (bilinear,
+        align_corners=False), like models/swin_transformer.py:74-75."""
         self._guard(x)
-        if tuple(x.shape[-2:]) != (self.img_size, self.img_size):
-            raise NotImplementedError("swinvox_b200 SwinTransformer expects 224x224 inputs (the reference would resize)")
-        if self.in_channels != 3:
-            raise NotImplementedError("swinvox_b200 lowers the 3-channel patch embedding only")
-        N = x.shape[0]
+        if x.dim() != 4 or x.shape[1] != self.in_channels:
+            raise ValueError(f"SwinTransformer expects [N, {self.in_channels}, H, W], got {tuple(x.shape)}")
+        if self.in_channels > 4:
+            raise NotImplementedError("swinvox_b200 lowers patch embeddings of up to 4 input channels (16-byte pixels)")
+        N, Cin, H, W = x.shape
+        resize = (H, W) != (self.img_size, self.img_size)
 
         def build():
             plan = E.Plan(x.device)
-            img = plan.empty(N, 3, 224, 224)
-            return plan, img, graph.lower_swin(plan, self, img, N)
+            img = plan.empty(N, Cin, 224, 224)
+            src = plan.empty(N, Cin, H, W) if resize else img
+            if resize:
+                plan.resize_bilinear(src, img, name="swin.input_resize")
+            return plan, src, graph.lower_swin(plan, self, img, N)
 
-        plan, img, feats = self._plan_for((N, str(x.device)), build)
-        if x.data_ptr() != img.data_ptr():
-            img.copy_(x)
+        plan, src, feats = self._plan_for((N, H, W, str(x.device)), build)
+        if x.data_ptr() != src.data_ptr():
+            src.copy_(x)
         plan.run(self.use_graph)
         outs = [mark_owned(f.buf.view(N, f.H, f.W, f.C).permute(0, 3, 1, 2), f.buf) for f in feats]
         return outs if self.cfg.NETWORK.USE_SWIN_T_MULTI_STAGE else outs[-1]

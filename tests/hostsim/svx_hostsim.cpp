@@ -633,6 +633,23 @@ int metrics_launch(const svx_metrics_desc& d, void*) {
   return 0;
 }
 
+int resize_launch(const svx_resize_desc& d, void*) {
+  const float sy = (float)d.IH / d.OH, sx = (float)d.IW / d.OW;
+  for (long long nc = 0; nc < d.NC; ++nc)
+    for (int oy = 0; oy < d.OH; ++oy)
+      for (int ox = 0; ox < d.OW; ++ox) {
+        const float fy = std::max((oy + 0.5f) * sy - 0.5f, 0.f), fx = std::max((ox + 0.5f) * sx - 0.5f, 0.f);
+        const int y0 = std::min((int)fy, d.IH - 1), x0 = std::min((int)fx, d.IW - 1);
+        const int y1 = std::min(y0 + 1, d.IH - 1), x1 = std::min(x0 + 1, d.IW - 1);
+        const float ly = fy - y0, lx = fx - x0;
+        const float* img = d.in + nc * (long long)d.IH * d.IW;
+        d.out[(nc * d.OH + oy) * (long long)d.OW + ox] =
+            (1.f - ly) * ((1.f - lx) * img[(long long)y0 * d.IW + x0] + lx * img[(long long)y0 * d.IW + x1]) +
+            ly * ((1.f - lx) * img[(long long)y1 * d.IW + x0] + lx * img[(long long)y1 * d.IW + x1]);
+      }
+  return 0;
+}
+
 int transpose_launch(const svx_transpose_desc& d, void*) {
   for (long long n = 0; n < d.N; ++n)
     for (int p = 0; p < d.P; ++p) {

@@ -154,6 +154,26 @@ def test_swin_wrapper_outputs(dev):
     assert sw1.out_channels == [768] and sw1.out_spatial == [7]
 
 
+def test_swin_wrapper_resize_and_input_channels(dev):
+    """models/swin_transformer.py:29-37 (patch embedding re-created for in_channels != 3) and :74-75 (inputs that are not
+    224 x 224 are resized, bilinear / align_corners=False)"""
+    cfg = M.default_cfg(SWIN_T_STAGES=[0, 1])
+    torch.manual_seed(0)
+    for cin, hw in ((3, (160, 200)), (4, (224, 224)), (1, (96, 96))):
+        ora = M.RefSwinTransformer(cfg, cin, 224, pretrained=False)
+        FX.analytic_(ora, 5)
+        ora.eval()
+        sw = SwinTransformer(cfg, cin, 224, pretrained=False)
+        sw.load_state_dict(ora.state_dict())
+        sw.eval().to(dev)
+        x = FX.structured_inputs(1, 1, seed=9)[0][:, :1].repeat(1, cin, 1, 1)[..., :hw[0], :hw[1]].contiguous()
+        with torch.no_grad():
+            ref, got = ora(x), sw(x.to(dev))
+        sync(dev)
+        for i, (a, b) in enumerate(zip(got, ref)):
+            stage_check(f"swin wrapper cin={cin} input {hw} stage {i}", a, b, RTOL_DEEP)
+
+
 @pytest.mark.gpu
 def test_batched_multi_view_parity_gpu():
     """B=2 objects x V=3 views (the metric's view count); views of one object interact only through CVA / merger"""

@@ -13,6 +13,7 @@ from oracle import preprocess as OP
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "preprocess_cases.npz")
 CASES = ["shapenet137", "small100", "rgb256", "exact224"]
+EXTRA = ["bbox_rgb", "bbox_edge_rgba", "bg_range"]    # bounding-box crops (edge padded) and a proper background range
 TOL = 1e-6
 
 
@@ -27,6 +28,24 @@ def test_oracle_matches_reference_transforms(name):
     out = OP.eval_transform(g[f"{name}.input"])
     assert out.shape == g[f"{name}.output"].shape
     assert np.abs(out - g[f"{name}.output"]).max() <= 5e-7
+
+
+@pytest.mark.parametrize("name", EXTRA)
+def test_oracle_matches_reference_bbox_and_background_range(name):
+    g = load()
+    bbox = g[f"{name}.bbox"].tolist() or None
+    bgr = g[f"{name}.bg_range"].tolist() or None
+    np.random.seed(int(g[f"{name}.seed"]))
+    out = OP.eval_transform(g[f"{name}.input"], bounding_box=bbox, bg_range=bgr)
+    assert np.abs(out - g[f"{name}.output"]).max() <= 5e-7
+
+
+def test_bbox_windows_host_rule():
+    from swinvox_b200.preprocess import bbox_windows
+    assert bbox_windows([0.2, 0.1, 0.7, 0.95], 1, 180, 240) == OP.bbox_windows([0.2, 0.1, 0.7, 0.95], [(180, 240)])
+    assert bbox_windows([0.55, 0.4, 1.0, 1.0], 1, 137, 137) == OP.bbox_windows([0.55, 0.4, 1.0, 1.0], [(137, 137)])
+    with pytest.raises(ValueError):      # the reference re-scales the box per view: a second view misses the image
+        bbox_windows([0.2, 0.1, 0.7, 0.95], 2, 180, 240)
 
 
 def test_crop_window_rule():
@@ -66,5 +85,19 @@ def test_kernel_batched_into_encoder_input():
     assert got.data_ptr() == buf.data_ptr()
     want = np.stack([OP.eval_transform(u8[b]) for b in range(2)])
     assert np.abs(got.cpu().numpy() - want).max() <= TOL
-    with pytest.raises(ValueError):
-        EvalTransform(bg_color_range=((225, 255),) * 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", EXTRA)
+def test_kernel_bbox_and_background_range(name):
+    """Pascal3D / Pix3D style bounding-box crops (windows that leave the image read the nearest edge pixel) and
+    RandomBackground with a proper colour range (one colour per sample from numpy's generator, like the reference)"""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from swinvox_b200.preprocess import EvalTransform
+    g = load()
+    bbox = g[f"{name}.bbox"].tolist() or None
+    bgr = g[f"{name}.bg_range"].tolist() or [[240, 240]] * 3
+    np.random.seed(int(g[f"{name}.seed"]))
+    out = EvalTransform(bg_color_range=bgr)(torch.from_numpy(g[f"{name}.input"]).cuda(), bounding_box=bbox).cpu().numpy()
+    assert np.abs(out - g[f"{name}.output"]).max() <= TOL

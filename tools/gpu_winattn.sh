@@ -9,6 +9,8 @@ timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -8 > gpurun_out/gpu_tes
 timeout 300 python bench.py --no-eager --cpu-seconds 2 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; cp gpurun_out/op_breakdown.json gpurun_out/op_breakdown_$tag.json
 SVX_WINATTN_MMASYNC=1 timeout 300 python bench.py --no-eager --cpu-seconds 2 > gpurun_out/bench_${tag}_legacy.json 2> gpurun_out/bench_${tag}_legacy.err; cp gpurun_out/op_breakdown.json gpurun_out/op_breakdown_${tag}_legacy.json
 timeout 300 python bench.py --dtype bf16 --views 5 --no-eager --cpu-seconds 2 > gpurun_out/bench_${tag}_bf16v5.json 2> gpurun_out/bench_${tag}_bf16v5.err; cp gpurun_out/op_breakdown.json gpurun_out/op_breakdown_${tag}_bf16v5.json
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"winattn_umma" -c 3 \
+    -o gpurun_out/prof_winattn_$tag python tools/run_module.py encoder 64 3 1 > gpurun_out/ncu_winattn_$tag.log 2>&1
 python - <<PY
 import json
 for t in ("$tag", "${tag}_legacy", "${tag}_bf16v5"):
