@@ -1534,7 +1534,7 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     }
     p.cin_live = live;
     g->slab = true;
-    g->slab_narrow = live <= 16 && !getenv("SVX_SLAB_WIDE");
+    g->slab_narrow = live <= 16;
     if (encode_map(&g->map_a, d.A, (uint64_t)d.lda, (uint64_t)d.in_Cs, (uint64_t)d.in_Cs, S3_PART_ROWS, g->slab_narrow ? 16 : BK)) {
       delete g;
       return 1;
@@ -1603,7 +1603,7 @@ int gemm_prepare(const svx_gemm_desc& d, GemmPrepared** out) {
     const bool plain = compact && d.valid_W == 0 && (d.epi_mode == SVX_EPI_STD || pool8) && d.a_mode != SVX_A_SLAB3 &&
                        d.block_n >= 32 && n_out % oe16 == 0 && d.o_sw % oe16 == 0 && d.o_sw >= n_out && (d.o_base % oe16) == 0 &&
                        (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
-                       (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0) && !getenv("SVX_NO_TMA_EPILOGUE");
+                       (!d.residual || (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0);
     if (plain) {
       p.epi_tma = 1;
       p.ldc = d.o_sw;

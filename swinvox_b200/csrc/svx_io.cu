@@ -148,11 +148,7 @@ int svx_binvox_decode(const svx_binvox_decode_desc* d, void* stream) {
   SVX_REQUIRE(d->B > 0 && d->d0 > 0 && d->d1 > 0 && d->d2 > 0, "binvox_decode: empty problem");
   const long long P = (long long)d->d0 * d->d1 * d->d2;
   SVX_REQUIRE(P <= 200 * 1024, "binvox_decode: volumes above 204800 voxels are not supported (got %lld)", P);
-  static bool configured = false;
-  if (!configured) {
-    SVX_CUDA_OK(cudaFuncSetAttribute(binvox_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  SVX_CUDA_OK(cudaFuncSetAttribute(binvox_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device
   const int grid = d->B < 148 * 4 ? d->B : 148 * 4;
   binvox_decode_kernel<<<grid, kIoThreads, (size_t)P, (cudaStream_t)stream>>>(*d);
   SVX_LAUNCH_OK("binvox_decode_kernel");
@@ -166,11 +162,7 @@ int svx_binvox_encode(const svx_binvox_encode_desc* d, void* stream) {
   const long long P = (long long)d->d0 * d->d1 * d->d2;
   SVX_REQUIRE(P <= 40000, "binvox_encode: volumes above 40000 voxels are not supported (got %lld)", P);
   const size_t smem = (size_t)((P + 15) / 16 * 16 + 4 * (P + 1));
-  static bool configured = false;
-  if (!configured) {
-    SVX_CUDA_OK(cudaFuncSetAttribute(binvox_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    configured = true;
-  }
+  SVX_CUDA_OK(cudaFuncSetAttribute(binvox_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));   // per device
   const int grid = d->B < 148 ? d->B : 148;
   binvox_encode_kernel<<<grid, kIoThreads, smem, (cudaStream_t)stream>>>(*d);
   SVX_LAUNCH_OK("binvox_encode_kernel");

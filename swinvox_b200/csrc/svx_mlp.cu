@@ -617,11 +617,13 @@ int encode_rows_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t 
 template <int C, int HC>
 int launch_mlp(const CUtensorMap& mx, const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& mr,
                const CUtensorMap& mo, const MlpParams& p, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static thread_local int configured_dev = -1;   // the opt-in is per device
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  if (configured_dev != cur_dev) {
     SVX_CUDA_OK(cudaFuncSetAttribute(mlp_fused_kernel<C, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      MlpCfg<C, HC>::kSmem));
-    configured = true;
+    configured_dev = cur_dev;
   }
   static const bool pdl = getenv("SVX_PDL") != nullptr;   // opt-in until validated on the GPU tier
   cudaLaunchConfig_t cfg = {};
@@ -660,9 +662,9 @@ int mlp_prepare(const svx_mlp_desc& d, MlpPrepared** out) {
   SVX_REQUIRE(!d.ln_gamma || (d.C == 96 && d.ln_beta && al16(d.ln_gamma) && al16(d.ln_beta)),
               "mlp: the fused LayerNorm exists for C = 96 only and needs gamma and beta");
   MlpPrepared* g = new MlpPrepared();
-  // C = 192: HC = 128 (half the fc1 MMAs of HC = 64, the two H slots used twice per chunk): 0.210 -> 0.177 ms per launch; the
-  // GPU tier passes with either instance (128/128).  SVX_MLP_NARROW192=1 selects the HC = 64 instance.
-  const int hc = d.C == 96 ? 128 : (getenv("SVX_MLP_NARROW192") ? 64 : 128);
+  // C = 192: HC = 128 (half the fc1 MMAs of an HC = 64 instance, the two H slots used twice per chunk: 0.210 -> 0.177 ms per
+  // launch, measured in round 1; the HC = 64 instance is no longer built)
+  const int hc = 128;
   int rc = encode_rows_map(&g->map_x, d.x, (uint64_t)d.M, (uint64_t)d.C, (uint64_t)d.ldx, ML_BM);
   if (!rc) rc = encode_rows_map(&g->map_w1, d.W1, (uint64_t)d.hidden, (uint64_t)d.C, (uint64_t)d.C, (uint32_t)hc);
   if (!rc) rc = encode_rows_map(&g->map_w2, d.W2, (uint64_t)d.C, (uint64_t)d.hidden, (uint64_t)d.hidden, (uint32_t)d.C);
@@ -701,8 +703,7 @@ int mlp_launch(const svx_mlp_desc& d, MlpPrepared* prepared, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
   if (g->C == 96) rc = launch_mlp<96, 128>(g->map_x, g->map_w1, g->map_w2, g->map_r, g->map_o, g->p, g->grid, st);
-  else if (g->hc == 128) rc = launch_mlp<192, 128>(g->map_x, g->map_w1, g->map_w2, g->map_r, g->map_o, g->p, g->grid, st);
-  else rc = launch_mlp<192, 64>(g->map_x, g->map_w1, g->map_w2, g->map_r, g->map_o, g->p, g->grid, st);
+  else rc = launch_mlp<192, 128>(g->map_x, g->map_w1, g->map_w2, g->map_r, g->map_o, g->p, g->grid, st);
   if (!prepared) delete g;
   return rc;
 }

@@ -1228,8 +1228,8 @@ int lnsample_launch(const svx_lnsample_desc& d, void* stream) {
   const bool bf = d.dtype == SVX_DT_BF16;
   const int nv = ((d.L >> 2) + kLnCluster * 1024 - 1) / (kLnCluster * 1024);
   // measured (192 samples): 56x56x96: 0.162 ms vs 0.210 ms for the single-CTA kernel; 28x28x192: 0.114 vs 0.097;
-  // 14x14x384: 0.093 vs 0.045 -> the cluster kernel only pays for the large samples (SVX_LN_CLUSTER=1 forces it)
-  if (nv <= 10 && d.L >= 4096 && (nv >= 6 || getenv("SVX_LN_CLUSTER"))) {
+  // 14x14x384: 0.093 vs 0.045 -> the cluster kernel only pays for the large samples
+  if (nv <= 10 && d.L >= 4096 && nv >= 6) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(d.N * kLnCluster);
     cfg.blockDim = dim3(1024);
@@ -1340,11 +1340,7 @@ int conv3to1_launch(const svx_conv3to1_desc& d, void* stream) {
               "conv3to1: needs W == 32, H %% 16 == 0, 16-byte aligned 12-channel reads (Cin=%d W=%d H=%d Cs=%d c0=%d)",
               d.Cin, d.W, d.H, d.Cs, d.c0);
   const int smem = (4 * C31_PLANE * 3 + 27 * 3) * (int)sizeof(float4);
-  static bool configured = false;
-  if (!configured) {
-    SVX_CUDA_OK(cudaFuncSetAttribute(conv3to1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  SVX_CUDA_OK(cudaFuncSetAttribute(conv3to1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   // per device
   conv3to1_kernel<<<d.N * (d.H / C31_TH), C31_THREADS, smem, (cudaStream_t)stream>>>(d);
   SVX_LAUNCH_OK("conv3to1_kernel");
   return 0;

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
   if (warp == 10) {
     if (lane == 0) {
       for (int s = 0; s < NS; ++s) {
-        mbar_init(full_bar(s), WU_PRODUCER_WARPS);
+        mbar_init(full_bar(s), WU_PRODUCER_WARPS * 32);
         mbar_init(empty_bar(s), 1u);
         mbar_init(v16_full(s), 2u);
       }
@@ -198,7 +198,6 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       }
     };
     for (int i = 0; i < WU_PREFETCH; ++i) prefetch_item(i);
-    constexpr int LAG = NS - 1;                  // cp.async groups a producer warp keeps in flight
     for (int i = 0; i < nt; ++i) {
       const int s = i % NS;
       prefetch_item(i + WU_PREFETCH);
@@ -221,19 +220,10 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
           }
         }
       }
-      cp_async_commit();
-      if (i >= LAG) {
-        cp_async_wait<LAG>();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar((i - LAG) % NS));
-      }
+      // every producer thread arrives on the stage's barrier when ITS copies have landed (the barrier counts all 64
+      // threads): the producers never wait for data, they run ahead as far as the stage ring lets them
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0)
-      for (int i = (nt > LAG ? nt - LAG : 0); i < nt; ++i) mbar_arrive(full_bar(i % NS));
   } else if (warp == 10) {
     // ---- MMA issuer: S(0) S(1) | PV(0) S(2) | PV(1) S(3) ... -------------------------------------------------------
     if (elect_one()) {

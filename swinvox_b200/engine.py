@@ -68,12 +68,12 @@ def to_operand(t, dtype):
 
 def mlp_fusable(c, hidden):
     """shapes the fused MLP kernel (svx_mlp.cu) is instantiated for: Swin stages 0 and 1"""
-    return c in (96, 192) and hidden == 4 * c and not os.environ.get("SVX_NO_MLP_FUSION")
+    return c in (96, 192) and hidden == 4 * c
 
 
 def mlp_ln_fusable(c):
     """widths for which the fused MLP kernel can also apply the preceding LayerNorm (two X buffers: stage 0)"""
-    return c == 96 and not os.environ.get("SVX_NO_MLP_LN_FUSION")
+    return c == 96
 
 
 def round_up(x, m):
@@ -412,7 +412,7 @@ class Plan:
         es = x.esize
         narrow_ok = cin * es == 16 or (cin * es == 32 and len(taps) % 4 == 0)
         tma = (((cin * es) % 128 == 0 or narrow_ok)
-               and len(taps) <= 64 and all(-16 <= v <= 15 for v in lo + up) and not os.environ.get("SVX_NO_IM2COL"))
+               and len(taps) <= 64 and all(-16 <= v <= 15 for v in lo + up))
         if tma:
             d.a_mode = A_IM2COL
             host = (C.c_int32 * (4 * len(taps)))(*[v for t in taps for v in (t[0], t[1], t[2], 0)])

@@ -276,7 +276,7 @@ def lower_encoder(plan, enc, img, B, V):
     img = stage_image(plan, img, N)   # shared by both branches: staged before they fork
     # The ResNet and the Swin branch are independent until the concat (encoder.py:119-143): they are recorded as two
     # concurrent graph branches (lane 1 / lane 0), so the tail of one branch's persistent kernels overlaps the other's.
-    two_lanes = not os.environ.get("SVX_ENCODER_ONE_LANE")
+    two_lanes = True
     if two_lanes:
         plan.lane(1)
     # ResNet branch.  avg_pool2d(conv1x1(x)) == conv1x1(avg_pool2d(x)): pool first, 4x fewer MACs.

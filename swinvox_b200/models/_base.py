@@ -1,4 +1,6 @@
 """Shared machinery of the drop-in modules: eval-only guard, plan cache, zero-copy chaining."""
+import collections
+
 import torch
 import torch.nn as nn
 
@@ -27,10 +29,13 @@ class PlannedModule(nn.Module):
     Parameters live in ordinary nn layers (the reference's state_dict layout); `forward` never calls them."""
 
     use_graph = False
+    # plans kept per module (least recently used are dropped): each holds the activations of one input signature
+    # (about 6 GB for the encoder at 64 x 3 views), so a long-lived process that varies B or V must not keep them all
+    max_plans = 4
 
     def __init__(self):
         super().__init__()
-        self._plans = {}
+        self._plans = collections.OrderedDict()
         self._param_version = None
 
     def _guard(self, *tensors):
@@ -56,13 +61,17 @@ class PlannedModule(nn.Module):
             self._param_version = ver
         if key not in self._plans:
             self._plans[key] = builder()
+            while len(self._plans) > self.max_plans:
+                self._plans.popitem(last=False)
+        else:
+            self._plans.move_to_end(key)
         return self._plans[key]
 
     def invalidate(self):
         self._plans.clear()
 
     def _apply(self, fn, *a, **k):
-        self._plans = {}
+        self._plans = collections.OrderedDict()
         return super()._apply(fn, *a, **k)
 
 
