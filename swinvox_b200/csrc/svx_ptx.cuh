@@ -72,6 +72,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// The same bounded wait WITHOUT a suspend-time hint.  With a hint ptxas emits TRYWAIT; NANOSLEEP.SYNCS <hint>; PHASECHK, and
+// a warp parked there resumes late: fine for deep pipelines that rarely block, but a latency chain of short hand-offs
+// (window attention: scores -> softmax -> P -> P.V -> output, per item) paid ~0.5 us per hand-off
+// (profiles/r2_ncu_winattn_wa5.txt).  Use this variant on such chains.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((it & 4095u) == 4095u) {   // ~2 s of SM clocks without progress: a protocol bug, not a long main loop
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+
 // ---- proxies / fences -------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -24,12 +24,14 @@
 // operands take the rows as they are; it also halves the P V instructions.  Accumulation, softmax statistics and the bias
 // are fp32 either way.
 //
-// Warp roles (13 warps):  0-3 / 4-7  two softmax + output groups (TMEM lane quarter = warp % 4), alternating items
+// Warp roles (15 warps):  0-3 / 4-7  two softmax + output groups (TMEM lane quarter = warp % 4), alternating items
 //                         8-9        row gather: cp.async 16-byte chunks of the token rows into 128B / 64B-swizzled
 //                                    operand tiles (a ring of stages)
 //                         10         MMA issuer (one elected thread), owns the TMEM allocation
-//                         11-12      fp32 storage only: V rows fp32 -> fp16
+//                         11-14      fp32 storage only: V rows fp32 -> fp16
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "svx_internal.h"
 #include "svx_ptx.cuh"
@@ -38,7 +40,8 @@ namespace svx {
 namespace {
 
 constexpr int WS = 7, WT = 49, HD = 32;
-constexpr int WU_THREADS = 13 * 32;
+constexpr int WU_THREADS = 15 * 32;
+constexpr int WU_CONV_WARPS = 4;
 constexpr int WU_PRODUCER_WARPS = 2;
 constexpr int WU_PREFETCH = 6;                  // items ahead whose token rows are pulled into L2 (prefetch.global.L2)
 constexpr float kLog2e = 1.4426950408889634f;
@@ -56,7 +59,8 @@ struct WuCfg {
   static constexpr int kBiasB = (WT * WT * 4 + 127) / 128 * 128;
   static constexpr int kKS = kRowB / 32;                     // MMA K steps of S = Q K^T (32 bytes each): 4 | 2
   static constexpr int kKP = 8;                              // MMA K steps of O = P V: 128 keys, 16 per step
-  static constexpr int kSmem = 1024 + kStages * (kStageB + kV16B) + kPBufs * kPBytes + kBiasB + 256;
+  static constexpr int kTokB = 8 * 32 * 4;                   // per softmax warp: the token row of each of its 32 tile rows
+  static constexpr int kSmem = 1024 + kStages * (kStageB + kV16B) + kPBufs * kPBytes + kBiasB + kTokB + 256;
   static_assert(kSmem <= 232448, "window attention shared memory");
 };
 
@@ -108,7 +112,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
   const uint32_t p_smem = smem_base + kPOff;
   uint8_t* p_gen = smem_gen + kPOff;
   float* sbias = reinterpret_cast<float*>(smem_gen + kPOff + K::kPBufs * K::kPBytes);
-  const uint32_t bar_base = p_smem + K::kPBufs * K::kPBytes + K::kBiasB;
+  int* stok_all = reinterpret_cast<int*>(smem_gen + kPOff + K::kPBufs * K::kPBytes + K::kBiasB);
+  const uint32_t bar_base = p_smem + K::kPBufs * K::kPBytes + K::kBiasB + K::kTokB;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };                 // stage s holds Q, K, V of an item
   auto empty_bar = [&](int s) { return bar_base + 8u * (NS + s); };         // every MMA that reads stage s has completed
   auto s_full = [&](int b) { return bar_base + 8u * (2 * NS + b); };        // scores of an item are in TMEM buffer b
@@ -138,8 +143,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
     if (lane == 0) {
       for (int s = 0; s < NS; ++s) {
         mbar_init(full_bar(s), WU_PRODUCER_WARPS * 32);
-        mbar_init(empty_bar(s), 1u);
-        mbar_init(v16_full(s), 2u);
+        mbar_init(empty_bar(s), 1u + 4u);            // the P.V MMAs + the four warps that stage the output rows in it
+        mbar_init(v16_full(s), (uint32_t)WU_CONV_WARPS);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(s_full(b), 1u); mbar_init(s_empty(b), 4u);
@@ -201,9 +206,9 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
     for (int i = 0; i < nt; ++i) {
       const int s = i % NS;
       prefetch_item(i + WU_PREFETCH);
-      mbar_wait(empty_bar(s), (((uint32_t)(i / NS)) & 1u) ^ 1u);
+      mbar_wait_spin(empty_bar(s), (((uint32_t)(i / NS)) & 1u) ^ 1u);
       const int win = 2 * item_of(i) + w;
-      if (win < num_windows) {
+      if (win < num_windows && !(d.reserved0 & 1)) {   // (probe bit 1: no loads -- timing experiments only)
         const uint32_t dst0 = stage_smem + s * K::kStageB + (64 * w) * K::kRowB;
         const WinPos wp = window_pos(win);
 #pragma unroll 1
@@ -233,8 +238,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       constexpr uint32_t sbo = 8 * K::kRowB;     // 8-row groups of the Q / K tiles: 1024 | 512 bytes
       auto issue_s = [&](int i) {
         const int s = i % NS, b = i & 1;
-        mbar_wait(full_bar(s), ((uint32_t)(i / NS)) & 1u);
-        mbar_wait(s_empty(b), (((uint32_t)i >> 1) & 1u) ^ 1u);
+        mbar_wait_spin(full_bar(s), ((uint32_t)(i / NS)) & 1u);
+        mbar_wait_spin(s_empty(b), (((uint32_t)i >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t q_addr = stage_smem + s * K::kStageB;
         const uint64_t da = wu_desc(q_addr, sbo, lay), db = wu_desc(q_addr + K::kMatB, sbo, lay);
@@ -248,9 +253,9 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       auto issue_pv = [&](int i) {
         const int s = i % NS, b = i & 1, pb = K::kPBufs == 2 ? b : 0;
         const uint32_t pi = K::kPBufs == 2 ? (uint32_t)i >> 1 : (uint32_t)i;
-        if constexpr (!BF) mbar_wait(v16_full(s), ((uint32_t)(i / NS)) & 1u);
-        mbar_wait(p_full(pb), pi & 1u);
-        mbar_wait(o_empty(b), (((uint32_t)i >> 1) & 1u) ^ 1u);
+        if constexpr (!BF) mbar_wait_spin(v16_full(s), ((uint32_t)(i / NS)) & 1u);
+        mbar_wait_spin(p_full(pb), pi & 1u);
+        mbar_wait_spin(o_empty(b), (((uint32_t)i >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t v_addr = BF ? stage_smem + s * K::kStageB + 2 * K::kMatB : v16_smem + s * K::kV16B;
         const uint32_t p_addr = p_smem + pb * K::kPBytes;
@@ -260,6 +265,10 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
           // B: the 16 V rows of this step = 1024 bytes (two 8-key groups 512 bytes apart)
           const uint64_t da = umma_desc_sw128(p_addr + (k >> 2) * (128 * 128)) + 2u * (k & 3);
           const uint64_t db = wu_desc(v_addr + k * 1024, 512u, 4u);
+          if (d.reserved0 & 8) continue;                                    // (probe bit 8: no P.V MMAs)
+          if (d.reserved0 & 4)                                              // (probe bit 4: V read as a K-major operand)
+            umma_f16(tmem_base + 256 + b * 32, da, wu_desc(v_addr + k * 32, 512u, 4u), idesc_o & ~(1u << 16), k != 0 ? 1u : 0u);
+          else
           umma_f16(tmem_base + 256 + b * 32, da, db, idesc_o, k != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar(s));     // Q, K, V of this item are no longer needed
@@ -277,30 +286,45 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
   } else if (warp >= 11) {
     // ---- fp32 storage: V rows (fp32, 128B-swizzled as gathered) -> fp16 rows of 64 bytes (64B swizzle) ---------------
     if constexpr (!BF) {
-      const int ct = threadIdx.x - 11 * 32;      // 0..63
+      const int ct = threadIdx.x - 11 * 32;      // 0 .. 127
       uint8_t* v16_gen = smem_gen + NS * K::kStageB;
       uint32_t amax = 0u;
+      // unit = (tile row, 16-byte output chunk = 8 dims) over the real rows of the two windows: 392 units, up to four per
+      // thread; all loads of a thread are issued before the first conversion (the conversion sits on the path to P.V)
+      constexpr int UPT = (2 * WT * 4 + 32 * WU_CONV_WARPS - 1) / (32 * WU_CONV_WARPS);
+      int urow[UPT], uoc[UPT];
+#pragma unroll
+      for (int k = 0; k < UPT; ++k) {
+        const int u = ct + k * 32 * WU_CONV_WARPS, rr = u >> 2;
+        uoc[k] = u & 3;
+        urow[k] = u < 2 * WT * 4 ? (rr < WT ? rr : 64 + rr - WT) : -1;
+      }
       for (int i = 0; i < nt; ++i) {
         const int s = i % NS;
-        mbar_wait(full_bar(s), ((uint32_t)(i / NS)) & 1u);
+        mbar_wait_spin(full_bar(s), ((uint32_t)(i / NS)) & 1u);
         const uint8_t* src = smem_gen + s * K::kStageB + 2 * K::kMatB;
         uint8_t* dst = v16_gen + s * K::kV16B;
-        // unit = (tile row, 16-byte output chunk = 8 dims); only the real rows of the two windows
-        for (int u = ct; u < 2 * WT * 4; u += 64) {
-          const int oc = u & 3, rr = u >> 2;
-          const int row = rr < WT ? rr : 64 + rr - WT;
-          const float4 a = *reinterpret_cast<const float4*>(src + row * 128 + (((2 * oc) ^ (row & 7)) << 4));
-          const float4 b = *reinterpret_cast<const float4*>(src + row * 128 + (((2 * oc + 1) ^ (row & 7)) << 4));
-          const uint32_t m0 = max(max(__float_as_uint(a.x) & 0x7fffffffu, __float_as_uint(a.y) & 0x7fffffffu),
-                                  max(__float_as_uint(a.z) & 0x7fffffffu, __float_as_uint(a.w) & 0x7fffffffu));
-          const uint32_t m1 = max(max(__float_as_uint(b.x) & 0x7fffffffu, __float_as_uint(b.y) & 0x7fffffffu),
-                                  max(__float_as_uint(b.z) & 0x7fffffffu, __float_as_uint(b.w) & 0x7fffffffu));
+        float4 a[UPT], b[UPT];
+#pragma unroll
+        for (int k = 0; k < UPT; ++k) {
+          const int row = urow[k] < 0 ? 0 : urow[k], oc = uoc[k];
+          a[k] = *reinterpret_cast<const float4*>(src + row * 128 + (((2 * oc) ^ (row & 7)) << 4));
+          b[k] = *reinterpret_cast<const float4*>(src + row * 128 + (((2 * oc + 1) ^ (row & 7)) << 4));
+        }
+#pragma unroll
+        for (int k = 0; k < UPT; ++k) {
+          if (urow[k] < 0 || (d.reserved0 & 32)) continue;   // (probe bit 32: no V conversion)
+          const int row = urow[k], oc = uoc[k];
+          const uint32_t m0 = max(max(__float_as_uint(a[k].x) & 0x7fffffffu, __float_as_uint(a[k].y) & 0x7fffffffu),
+                                  max(__float_as_uint(a[k].z) & 0x7fffffffu, __float_as_uint(a[k].w) & 0x7fffffffu));
+          const uint32_t m1 = max(max(__float_as_uint(b[k].x) & 0x7fffffffu, __float_as_uint(b[k].y) & 0x7fffffffu),
+                                  max(__float_as_uint(b[k].z) & 0x7fffffffu, __float_as_uint(b[k].w) & 0x7fffffffu));
           amax = max(amax, max(m0, m1));
           uint4 o;
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(a.y), "f"(a.x));
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(a.w), "f"(a.z));
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(b.y), "f"(b.x));
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(b.w), "f"(b.z));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(a[k].y), "f"(a[k].x));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(a[k].w), "f"(a[k].z));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(b[k].y), "f"(b[k].x));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(b[k].w), "f"(b[k].z));
           *reinterpret_cast<uint4*>(dst + row * 64 + ((oc ^ ((row >> 1) & 3)) << 4)) = o;
         }
         fence_proxy_async_smem();
@@ -335,7 +359,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
           if (wp.wx == nwx - 1) masked |= qx < 4 ? kColGe4 : (kKeysAll & ~kColGe4);
         }
       }
-      mbar_wait(s_full(b), ((uint32_t)i >> 1) & 1u);
+      mbar_wait_spin(s_full(b), ((uint32_t)i >> 1) & 1u);
       tc_fence_after();
       // this row's scores against the 64 key slots of its own window (slots 49..63 are padding)
       uint32_t sv[4][16];
@@ -349,6 +373,10 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       if (lane == 0) mbar_arrive(s_empty(b));
       float e[WT];
       float mx = -INFINITY;
+      if (d.reserved0 & 2) {   // (probe bit 2: no softmax arithmetic -- timing experiments only)
+#pragma unroll
+        for (int j = 0; j < WT; ++j) e[j] = __uint_as_float(sv[j >> 4][j & 15]);
+      } else
 #pragma unroll
       for (int j = 0; j < WT; ++j) {
         float v = fmaf(__uint_as_float(sv[j >> 4][j & 15]), scale2, brow[j]);
@@ -357,6 +385,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
         mx = fmaxf(mx, v);
       }
       float sum = 0.f;
+      if (d.reserved0 & 2) sum = 1.f;
+      else
 #pragma unroll
       for (int j = 0; j < WT; ++j) {
         e[j] = ex2f(e[j] - mx);
@@ -364,7 +394,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       }
       // P row in the A-operand layout (K-major, 128B swizzle): only the 49 (+3 zero) slots of the own window
       const uint32_t pi = K::kPBufs == 2 ? (uint32_t)i >> 1 : (uint32_t)i;
-      mbar_wait(p_empty(pb), (pi & 1u) ^ 1u);
+      mbar_wait_spin(p_empty(pb), (pi & 1u) ^ 1u);
       if (live) {
         uint8_t* prow = p_gen + pb * K::kPBytes + r * 128;
         // 64 sixteen-bit slots of window w = atom w; chunk c holds slots 8c .. 8c+7 (bf16, or fp16 for fp32 storage)
@@ -386,7 +416,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       if (lane == 0) mbar_arrive(p_full(pb));
       // ---- output row: O / rowsum -> out[token, head*32 ..] ---------------------------------------------------------
       const float inv = __frcp_rn(sum);
-      mbar_wait(o_full(b), ((uint32_t)i >> 1) & 1u);
+      mbar_wait_spin(o_full(b), ((uint32_t)i >> 1) & 1u);
       tc_fence_after();
       uint32_t ov[2][16];
       const uint32_t o_addr = tmem_base + lane_sel + 256 + b * 32;
@@ -397,28 +427,55 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty(b));
-      if (live) {
-        T* dst = reinterpret_cast<T*>(d.out) + (size_t)tok * d.C + head * HD;
-        if constexpr (BF) {
+      // Row per lane -> global would touch 32 different cache lines per store instruction (measured: the output phase was
+      // the longest part of an item).  Each warp therefore transposes its 32 rows through the Q tile of the item's stage
+      // (dead since the score MMAs completed; the stage is only released below) and stores whole rows: 8 (4) lanes cover
+      // the 128 (64) bytes of one token's head slice.
+      {
+        const int s = i % NS;
+        uint8_t* scratch = smem_gen + s * K::kStageB + (quarter * 32) * K::kRowB;   // this warp's 32 rows of the Q tile
+        int* stok = stok_all + (warp & 7) * 32;
+        stok[lane] = live ? (int)tok : -1;
+        if (live) {
+          uint8_t* srow = scratch + lane * K::kRowB;
+          if constexpr (BF) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t* o8 = &ov[c >> 1][(c & 1) * 8];
-            *reinterpret_cast<uint4*>(dst + 8 * c) =
-                make_uint4(pack_bf16x2(__uint_as_float(o8[0]) * inv, __uint_as_float(o8[1]) * inv),
-                           pack_bf16x2(__uint_as_float(o8[2]) * inv, __uint_as_float(o8[3]) * inv),
-                           pack_bf16x2(__uint_as_float(o8[4]) * inv, __uint_as_float(o8[5]) * inv),
-                           pack_bf16x2(__uint_as_float(o8[6]) * inv, __uint_as_float(o8[7]) * inv));
-          }
-        } else {
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t* o8 = &ov[c >> 1][(c & 1) * 8];
+              *reinterpret_cast<uint4*>(srow + ((c ^ ((r >> 1) & 3)) << 4)) =
+                  make_uint4(pack_bf16x2(__uint_as_float(o8[0]) * inv, __uint_as_float(o8[1]) * inv),
+                             pack_bf16x2(__uint_as_float(o8[2]) * inv, __uint_as_float(o8[3]) * inv),
+                             pack_bf16x2(__uint_as_float(o8[4]) * inv, __uint_as_float(o8[5]) * inv),
+                             pack_bf16x2(__uint_as_float(o8[6]) * inv, __uint_as_float(o8[7]) * inv));
+            }
+          } else {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint32_t* o4 = &ov[c >> 2][(c & 3) * 4];
-            float4 o = make_float4(__uint_as_float(o4[0]) * inv, __uint_as_float(o4[1]) * inv, __uint_as_float(o4[2]) * inv,
-                                   __uint_as_float(o4[3]) * inv);
-            if (d.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-            *reinterpret_cast<float4*>(dst + 4 * c) = o;
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t* o4 = &ov[c >> 2][(c & 3) * 4];
+              float4 o = make_float4(__uint_as_float(o4[0]) * inv, __uint_as_float(o4[1]) * inv, __uint_as_float(o4[2]) * inv,
+                                     __uint_as_float(o4[3]) * inv);
+              if (d.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+              *reinterpret_cast<float4*>(srow + ((c ^ (r & 7)) << 4)) = o;
+            }
           }
         }
+        __syncwarp();
+        constexpr int CH = K::kRowB / 16;        // 16-byte chunks per row: 8 | 4
+        constexpr int RPI = 32 / CH;             // rows per store instruction: 4 | 8
+        const int ch = lane % CH, rsub = lane / CH;
+        T* outh = reinterpret_cast<T*>(d.out) + head * HD + ch * (16 / (int)sizeof(T));
+        if (!(d.reserved0 & 16)) {               // (probe bit 16: no output stores)
+#pragma unroll
+          for (int p0 = 0; p0 < 32; p0 += RPI) {
+            const int lr = p0 + rsub, row = quarter * 32 + lr;
+            const int tk = stok[lr];
+            const uint4 v = *reinterpret_cast<const uint4*>(scratch + lr * K::kRowB +
+                                                            ((BF ? (ch ^ ((row >> 1) & 3)) : (ch ^ (row & 7))) << 4));
+            if (tk >= 0) *reinterpret_cast<uint4*>(outh + (size_t)tk * d.C) = v;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(s));   // the scratch rows are free: with the P.V commit this releases the stage
       }
     }
   }
@@ -429,7 +486,10 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
 
 }  // namespace
 
-int winattn_umma_launch(const svx_winattn_desc& d, void* stream) {
+int winattn_umma_launch(const svx_winattn_desc& d_in, void* stream) {
+  svx_winattn_desc d = d_in;
+  static const char* probe = getenv("SVX_WINATTN_PROBE");   // timing experiments (wrong results): 1 = no loads, 2 = no softmax
+  d.reserved0 = probe ? atoi(probe) : 0;
   const long long windows = (long long)d.N * (d.H / WS) * (d.W / WS);
   const long long items = (windows + 1) / 2;
   int dev = 0, sms = 0;
