@@ -739,6 +739,28 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& map_a, const CUtens
               }
             } else {
               const int cc = p.cls_cout;
+              if ((cc & 15) == 0 && p.vec_ok) {
+                // the 16 columns of this pass are 16 consecutive channels of ONE class: 64 contiguous bytes per voxel
+                const int cls = jb / cc;
+                const long long o = off + cls_off(cls) + (jb - cls * cc);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const float4 r4 = p.residual ? *reinterpret_cast<const float4*>(p.residual + o + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
+                  float t4[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    float t = x[4 * c + e];
+                    if (!p.res_after_act) t += rv[e];
+                    t = apply_act(t, p.act, p.act_param);
+                    if (p.res_after_act) t += rv[e];
+                    t *= p.out_scale;
+                    t4[e] = p.round_tf32 ? round_tf32(t) : t;
+                  }
+                  *reinterpret_cast<float4*>(p.out + o + 4 * c) = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                }
+                continue;
+              }
 #pragma unroll
               for (int q = 0; q < SLAB; ++q) {
                 const int j = jb + q;

@@ -76,17 +76,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // a warp parked there resumes late: fine for deep pipelines that rarely block, but a latency chain of short hand-offs
 // (window attention: scores -> softmax -> P -> P.V -> output, per item) paid ~0.5 us per hand-off
 // (profiles/r2_ncu_winattn_wa5.txt).  Use this variant on such chains.
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, uint32_t hint_ns = 0) {
   uint32_t done = 0;
   long long t0 = 0;
   for (uint32_t it = 0;; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
+    if (hint_ns) {   // a SHORT suspend hint: the waiting warp leaves the issue slots to the working ones without a late wake-up
+      asm volatile(
+          "{\n\t.reg .pred P;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, P;\n\t}\n"
+          : "=r"(done)
+          : "r"(bar), "r"(parity), "r"(hint_ns)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred P;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, P;\n\t}\n"
+          : "=r"(done)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    }
     if (done) break;
     if ((it & 4095u) == 4095u) {   // ~2 s of SM clocks without progress: a protocol bug, not a long main loop
       const long long now = clock64();
@@ -94,6 +104,19 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
       else if (now - t0 > 4000000000LL) __trap();
     }
   }
+}
+
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 
 // ---- proxies / fences -------------------------------------------------------------------

@@ -24,11 +24,14 @@
 // operands take the rows as they are; it also halves the P V instructions.  Accumulation, softmax statistics and the bias
 // are fp32 either way.
 //
-// Warp roles (15 warps):  0-3 / 4-7  two softmax + output groups (TMEM lane quarter = warp % 4), alternating items
-//                         8-9        row gather: cp.async 16-byte chunks of the token rows into 128B / 64B-swizzled
+// Warp roles (17 warps):  0-3 / 4-7  two softmax groups (TMEM lane quarter = warp % 4), alternating items: scores -> P
+//                         8-11       output group, every item: O / rowsum -> global (through the item's dead Q tile)
+//                         12-13      row gather: cp.async 16-byte chunks of the token rows into 128B / 64B-swizzled
 //                                    operand tiles (a ring of stages)
-//                         10         MMA issuer (one elected thread), owns the TMEM allocation
-//                         11-14      fp32 storage only: V rows fp32 -> fp16
+//                         14         MMA issuer (one elected thread), owns the TMEM allocation
+//                         15-16      fp32 storage only: V rows fp32 -> fp16
+// The per-item latency chain (scores -> softmax -> P -> P.V -> output; measured ~5000 cycles through one group,
+// profiles/r2_winattn_probes.txt) is what bounds this kernel, not any one unit: three groups work on three items at once.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -40,10 +43,10 @@ namespace svx {
 namespace {
 
 constexpr int WS = 7, WT = 49, HD = 32;
-constexpr int WU_THREADS = 15 * 32;
-constexpr int WU_CONV_WARPS = 4;
+constexpr int WU_THREADS = 17 * 32;
+constexpr int WU_CONV_WARPS = 2;
+constexpr int WU_W_OUT = 8, WU_W_LOAD = 12, WU_W_MMA = 14, WU_W_CONV = 15;
 constexpr int WU_PRODUCER_WARPS = 2;
-constexpr int WU_PREFETCH = 6;                  // items ahead whose token rows are pulled into L2 (prefetch.global.L2)
 constexpr float kLog2e = 1.4426950408889634f;
 
 template <typename T>
@@ -59,8 +62,9 @@ struct WuCfg {
   static constexpr int kBiasB = (WT * WT * 4 + 127) / 128 * 128;
   static constexpr int kKS = kRowB / 32;                     // MMA K steps of S = Q K^T (32 bytes each): 4 | 2
   static constexpr int kKP = 8;                              // MMA K steps of O = P V: 128 keys, 16 per step
-  static constexpr int kTokB = 8 * 32 * 4;                   // per softmax warp: the token row of each of its 32 tile rows
-  static constexpr int kSmem = 1024 + kStages * (kStageB + kV16B) + kPBufs * kPBytes + kBiasB + kTokB + 256;
+  static constexpr int kTokB = 4 * 32 * 4 + 4 * 128 * 4;     // output warps: token row per tile row; 1/rowsum of the last four items
+  static constexpr int kScrB = 2 * WT * kRowB;               // output transpose scratch: the 98 live rows of a tile
+  static constexpr int kSmem = 1024 + kStages * (kStageB + kV16B) + kPBufs * kPBytes + kBiasB + kTokB + kScrB + 256;
   static_assert(kSmem <= 232448, "window attention shared memory");
 };
 
@@ -113,7 +117,9 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
   uint8_t* p_gen = smem_gen + kPOff;
   float* sbias = reinterpret_cast<float*>(smem_gen + kPOff + K::kPBufs * K::kPBytes);
   int* stok_all = reinterpret_cast<int*>(smem_gen + kPOff + K::kPBufs * K::kPBytes + K::kBiasB);
-  const uint32_t bar_base = p_smem + K::kPBufs * K::kPBytes + K::kBiasB + K::kTokB;
+  float* sinv = reinterpret_cast<float*>(stok_all + 4 * 32);                // [4 items][128 rows]
+  uint8_t* oscr = smem_gen + kPOff + K::kPBufs * K::kPBytes + K::kBiasB + K::kTokB;
+  const uint32_t bar_base = p_smem + K::kPBufs * K::kPBytes + K::kBiasB + K::kTokB + K::kScrB;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };                 // stage s holds Q, K, V of an item
   auto empty_bar = [&](int s) { return bar_base + 8u * (NS + s); };         // every MMA that reads stage s has completed
   auto s_full = [&](int b) { return bar_base + 8u * (2 * NS + b); };        // scores of an item are in TMEM buffer b
@@ -127,6 +133,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (3 * NS + 12));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t wait_hint = (uint32_t)d.reserved0 >> 16;   // (probe bits 16..: suspend-time hint of the barrier waits, ns)
   const int head = blockIdx.x % d.heads;
   const int cta_in_head = blockIdx.x / d.heads;
   const int nwx = d.W / WS, nwy = d.H / WS;
@@ -139,11 +146,11 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
   for (int i = threadIdx.x; i < (kPOff + K::kPBufs * K::kPBytes) / 16; i += WU_THREADS)
     reinterpret_cast<uint4*>(smem_gen)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = threadIdx.x; i < WT * WT; i += WU_THREADS) sbias[i] = __ldg(d.bias + (long long)head * WT * WT + i) * kLog2e;
-  if (warp == 10) {
+  if (warp == WU_W_MMA) {
     if (lane == 0) {
       for (int s = 0; s < NS; ++s) {
         mbar_init(full_bar(s), WU_PRODUCER_WARPS * 32);
-        mbar_init(empty_bar(s), 1u + 4u);            // the P.V MMAs + the four warps that stage the output rows in it
+        mbar_init(empty_bar(s), 1u);
         mbar_init(v16_full(s), (uint32_t)WU_CONV_WARPS);
       }
       for (int b = 0; b < 2; ++b) {
@@ -178,35 +185,17 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
     return ((long long)(wp.nH + oy)) * d.W + ox;
   };
 
-  if (warp >= 8 && warp < 10) {
+  if (warp >= WU_W_LOAD && warp < WU_W_MMA) {
     // ---- row gather: each producer warp owns one half of the tile = one window ------------------------------------
-    const int w = warp - 8;
+    const int w = warp - WU_W_LOAD;
     constexpr int CH = K::kRowB / 16;            // 16-byte chunks per row: 8 | 4
     constexpr int RPI = 32 / CH;                 // rows one warp-wide cp.async instruction covers: 4 | 8
     const int ch = lane % CH, rsub = lane / CH;
     const size_t tok_pitch = (size_t)3 * d.C * sizeof(T), c_bytes = (size_t)d.C * sizeof(T);
     const uint8_t* qkvb = reinterpret_cast<const uint8_t*>(d.qkv) + (size_t)head * HD * sizeof(T) + ch * 16;
-    // The stage ring holds at most NS - 1 items in flight, about one item time of slack against ~1 us of HBM latency
-    // (measured: 2.5 TB/s, latency-bound).  The rows of the items WU_PREFETCH ahead are therefore pulled into L2 first
-    // (148 SMs x 6 items x 38 KB = 33 MB of the 126 MB L2), so the cp.async below hit L2.
-    auto prefetch_item = [&](int i) {
-      const int win = 2 * item_of(i) + w;
-      if (i < nt && win < num_windows) {
-        const WinPos wp = window_pos(win);
-        for (int q = lane; q < WT; q += 32) {
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(d.qkv) + (size_t)head * HD * sizeof(T) +
-                               (size_t)token_of(wp, q / WS, q % WS) * tok_pitch;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + c_bytes));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 2 * c_bytes));
-        }
-      }
-    };
-    for (int i = 0; i < WU_PREFETCH; ++i) prefetch_item(i);
     for (int i = 0; i < nt; ++i) {
       const int s = i % NS;
-      prefetch_item(i + WU_PREFETCH);
-      mbar_wait_spin(empty_bar(s), (((uint32_t)(i / NS)) & 1u) ^ 1u);
+      mbar_wait_spin(empty_bar(s), (((uint32_t)(i / NS)) & 1u) ^ 1u, wait_hint);
       const int win = 2 * item_of(i) + w;
       if (win < num_windows && !(d.reserved0 & 1)) {   // (probe bit 1: no loads -- timing experiments only)
         const uint32_t dst0 = stage_smem + s * K::kStageB + (64 * w) * K::kRowB;
@@ -229,17 +218,27 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       // threads): the producers never wait for data, they run ahead as far as the stage ring lets them
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
     }
-  } else if (warp == 10) {
+  } else if (warp == WU_W_MMA) {
     // ---- MMA issuer: S(0) S(1) | PV(0) S(2) | PV(1) S(3) ... -------------------------------------------------------
     if (elect_one()) {
       constexpr uint32_t idesc_s = wu_idesc(BF ? 1u : 2u, 128, false);   // bf16 | tf32
       constexpr uint32_t idesc_o = wu_idesc(BF ? 1u : 0u, 32, true);     // bf16 | fp16, V MN-major
       constexpr uint32_t lay = BF ? 4u : 2u;
       constexpr uint32_t sbo = 8 * K::kRowB;     // 8-row groups of the Q / K tiles: 1024 | 512 bytes
+      // S(i) needs the item's rows and a free score buffer; P.V(i) needs the fp16 V rows (fp32 storage), the probabilities
+      // and a free output buffer.  Issue order S(0) S(1) | PV(0) S(2) | PV(1) S(3) ... -- but never block one kind behind
+      // the other: a late row gather must not hold back the P.V of an earlier item (it did: +40 % per launch).
+      auto ready_s = [&](int i) {
+        return mbar_test(full_bar(i % NS), ((uint32_t)(i / NS)) & 1u) && mbar_test(s_empty(i & 1), (((uint32_t)i >> 1) & 1u) ^ 1u);
+      };
+      auto ready_pv = [&](int i) {
+        const int pb = K::kPBufs == 2 ? (i & 1) : 0;
+        const uint32_t pi = K::kPBufs == 2 ? (uint32_t)i >> 1 : (uint32_t)i;
+        return (BF || mbar_test(v16_full(i % NS), ((uint32_t)(i / NS)) & 1u)) && mbar_test(p_full(pb), pi & 1u) &&
+               mbar_test(o_empty(i & 1), (((uint32_t)i >> 1) & 1u) ^ 1u);
+      };
       auto issue_s = [&](int i) {
         const int s = i % NS, b = i & 1;
-        mbar_wait_spin(full_bar(s), ((uint32_t)(i / NS)) & 1u);
-        mbar_wait_spin(s_empty(b), (((uint32_t)i >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t q_addr = stage_smem + s * K::kStageB;
         const uint64_t da = wu_desc(q_addr, sbo, lay), db = wu_desc(q_addr + K::kMatB, sbo, lay);
@@ -252,10 +251,6 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       };
       auto issue_pv = [&](int i) {
         const int s = i % NS, b = i & 1, pb = K::kPBufs == 2 ? b : 0;
-        const uint32_t pi = K::kPBufs == 2 ? (uint32_t)i >> 1 : (uint32_t)i;
-        if constexpr (!BF) mbar_wait_spin(v16_full(s), ((uint32_t)(i / NS)) & 1u);
-        mbar_wait_spin(p_full(pb), pi & 1u);
-        mbar_wait_spin(o_empty(b), (((uint32_t)i >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t v_addr = BF ? stage_smem + s * K::kStageB + 2 * K::kMatB : v16_smem + s * K::kV16B;
         const uint32_t p_addr = p_smem + pb * K::kPBytes;
@@ -266,27 +261,37 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
           const uint64_t da = umma_desc_sw128(p_addr + (k >> 2) * (128 * 128)) + 2u * (k & 3);
           const uint64_t db = wu_desc(v_addr + k * 1024, 512u, 4u);
           if (d.reserved0 & 8) continue;                                    // (probe bit 8: no P.V MMAs)
-          if (d.reserved0 & 4)                                              // (probe bit 4: V read as a K-major operand)
-            umma_f16(tmem_base + 256 + b * 32, da, wu_desc(v_addr + k * 32, 512u, 4u), idesc_o & ~(1u << 16), k != 0 ? 1u : 0u);
-          else
           umma_f16(tmem_base + 256 + b * 32, da, db, idesc_o, k != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar(s));     // Q, K, V of this item are no longer needed
         umma_commit(p_empty(pb));
         umma_commit(o_full(b));
       };
-      if (nt > 0) issue_s(0);
-      if (nt > 1) issue_s(1);
-      for (int i = 0; i < nt; ++i) {
-        issue_pv(i);
-        if (i + 2 < nt) issue_s(i + 2);
+      int ns = 0, np = 0;              // next item whose scores / whose P.V product is to be issued
+      long long t0 = 0;
+      const bool in_order = (d.reserved0 & 128) != 0;   // (probe bit 128: strict S(0) S(1) | PV(i) S(i+2) order)
+      for (uint32_t it = 0; np < nt; ++it) {
+        bool did = false;
+        if (in_order) {
+          if (ns < nt && ns < np + 2) { if (ready_s(ns)) { issue_s(ns); ++ns; did = true; } }
+          else if (ready_pv(np)) { issue_pv(np); ++np; did = true; }
+        } else {
+          if (np < ns && ready_pv(np)) { issue_pv(np); ++np; did = true; }
+          if (ns < nt && ready_s(ns)) { issue_s(ns); ++ns; did = true; }
+        }
+        if (did) { it = 0; t0 = 0; }
+        else if ((it & 4095u) == 4095u) {   // ~2 s without progress: a protocol bug (see mbar_wait)
+          const long long now = clock64();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 4000000000LL) __trap();
+        }
       }
     }
     __syncwarp();
-  } else if (warp >= 11) {
+  } else if (warp >= WU_W_CONV) {
     // ---- fp32 storage: V rows (fp32, 128B-swizzled as gathered) -> fp16 rows of 64 bytes (64B swizzle) ---------------
     if constexpr (!BF) {
-      const int ct = threadIdx.x - 11 * 32;      // 0 .. 127
+      const int ct = threadIdx.x - WU_W_CONV * 32;      // 0 .. 63
       uint8_t* v16_gen = smem_gen + NS * K::kStageB;
       uint32_t amax = 0u;
       // unit = (tile row, 16-byte output chunk = 8 dims) over the real rows of the two windows: 392 units, up to four per
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       }
       for (int i = 0; i < nt; ++i) {
         const int s = i % NS;
-        mbar_wait_spin(full_bar(s), ((uint32_t)(i / NS)) & 1u);
+        mbar_wait_spin(full_bar(s), ((uint32_t)(i / NS)) & 1u, wait_hint);
         const uint8_t* src = smem_gen + s * K::kStageB + 2 * K::kMatB;
         uint8_t* dst = v16_gen + s * K::kV16B;
         float4 a[UPT], b[UPT];
@@ -333,8 +338,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       }
       if (d.range_flag && amax > 0x477fe000u) atomicOr(d.range_flag, 1);   // a V value beyond fp16's 65504 saturated
     }
-  } else {
-    // ---- softmax + output: group g = warp / 4 takes the items with i % 2 == g; thread = one query row ----------------
+  } else if (warp < WU_W_OUT) {
+    // ---- softmax: group g = warp / 4 takes the items with i % 2 == g; thread = one query row ---------------------------
     const int grp = warp >> 2, quarter = warp & 3;
     const int r = quarter * 32 + lane;           // tile row = TMEM lane
     const int w = r >> 6, q = r & 63;            // window of the tile, row inside the window
@@ -349,19 +354,16 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       const int b = i & 1, pb = K::kPBufs == 2 ? b : 0;
       const int win = 2 * item_of(i) + w;
       const bool live = qreal && win < num_windows;
-      long long tok = 0;
       uint64_t masked = 0;   // keys this query must not see (shifted blocks only)
-      if (live) {
+      if (SHIFTED && live) {
         const WinPos wp = window_pos(win);
-        tok = token_of(wp, qy, qx);
-        if (SHIFTED) {
-          if (wp.wy == nwy - 1) masked |= qy < 4 ? kRowGe4 : (kKeysAll & ~kRowGe4);
-          if (wp.wx == nwx - 1) masked |= qx < 4 ? kColGe4 : (kKeysAll & ~kColGe4);
-        }
+        if (wp.wy == nwy - 1) masked |= qy < 4 ? kRowGe4 : (kKeysAll & ~kRowGe4);
+        if (wp.wx == nwx - 1) masked |= qx < 4 ? kColGe4 : (kKeysAll & ~kColGe4);
       }
-      mbar_wait_spin(s_full(b), ((uint32_t)i >> 1) & 1u);
+      mbar_wait_spin(s_full(b), ((uint32_t)i >> 1) & 1u, wait_hint);
       tc_fence_after();
-      // this row's scores against the 64 key slots of its own window (slots 49..63 are padding)
+      // this row's scores against the 64 key slots of its own window (slots 49..63 are padding); the values are turned
+      // into logits and then probabilities in place
       uint32_t sv[4][16];
       const uint32_t s_addr = tmem_base + lane_sel + b * 128 + w * 64;
       __syncwarp();
@@ -371,30 +373,33 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty(b));
-      float e[WT];
-      float mx = -INFINITY;
-      if (d.reserved0 & 2) {   // (probe bit 2: no softmax arithmetic -- timing experiments only)
+      auto E = [&](int j) -> uint32_t& { return sv[j >> 4][j & 15]; };
+      float mxp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four partial maxima / sums: short dependency chains
+      if (!(d.reserved0 & 2)) {   // (probe bit 2: no softmax arithmetic -- timing experiments only)
 #pragma unroll
-        for (int j = 0; j < WT; ++j) e[j] = __uint_as_float(sv[j >> 4][j & 15]);
-      } else
-#pragma unroll
-      for (int j = 0; j < WT; ++j) {
-        float v = fmaf(__uint_as_float(sv[j >> 4][j & 15]), scale2, brow[j]);
-        if (SHIFTED) v += ((masked >> j) & 1ull) ? kMask : 0.f;
-        e[j] = v;
-        mx = fmaxf(mx, v);
+        for (int j = 0; j < WT; ++j) {
+          float v = fmaf(__uint_as_float(E(j)), scale2, brow[j]);
+          if (SHIFTED) v += ((masked >> j) & 1ull) ? kMask : 0.f;
+          E(j) = __float_as_uint(v);
+          mxp[j & 3] = fmaxf(mxp[j & 3], v);
+        }
       }
-      float sum = 0.f;
-      if (d.reserved0 & 2) sum = 1.f;
-      else
+      const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
+      float smp[4] = {0.f, 0.f, 0.f, 0.f};
+      if (d.reserved0 & 2) smp[0] = 1.f;
+      else {
 #pragma unroll
-      for (int j = 0; j < WT; ++j) {
-        e[j] = ex2f(e[j] - mx);
-        sum += e[j];
+        for (int j = 0; j < WT; ++j) {
+          const float e = ex2f(__uint_as_float(E(j)) - mx);
+          E(j) = __float_as_uint(e);
+          smp[j & 3] += e;
+        }
       }
-      // P row in the A-operand layout (K-major, 128B swizzle): only the 49 (+3 zero) slots of the own window
+      const float sum = (smp[0] + smp[1]) + (smp[2] + smp[3]);
+      // P row in the A-operand layout (K-major, 128B swizzle): only the 49 (+7 zero) slots of the own window
       const uint32_t pi = K::kPBufs == 2 ? (uint32_t)i >> 1 : (uint32_t)i;
-      mbar_wait_spin(p_empty(pb), (pi & 1u) ^ 1u);
+      mbar_wait_spin(p_empty(pb), (pi & 1u) ^ 1u, wait_hint);
+      sinv[(i & 3) * 128 + r] = __frcp_rn(sum);   // for the output group (ring of four items: see the barrier order there)
       if (live) {
         uint8_t* prow = p_gen + pb * K::kPBytes + r * 128;
         // 64 sixteen-bit slots of window w = atom w; chunk c holds slots 8c .. 8c+7 (bf16, or fp16 for fp32 storage)
@@ -404,7 +409,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             const int j0 = 8 * c + 2 * h;
-            const float lo = j0 < WT ? e[j0 < WT ? j0 : 0] : 0.f, hi = j0 + 1 < WT ? e[j0 + 1 < WT ? j0 + 1 : 0] : 0.f;
+            const float lo = j0 < WT ? __uint_as_float(E(j0 < WT ? j0 : 0)) : 0.f;
+            const float hi = j0 + 1 < WT ? __uint_as_float(E(j0 + 1 < WT ? j0 + 1 : 0)) : 0.f;
             if constexpr (BF) u[h] = pack_bf16x2(lo, hi);
             else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u[h]) : "f"(hi), "f"(lo));
           }
@@ -414,9 +420,23 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(pb));
-      // ---- output row: O / rowsum -> out[token, head*32 ..] ---------------------------------------------------------
-      const float inv = __frcp_rn(sum);
-      mbar_wait_spin(o_full(b), ((uint32_t)i >> 1) & 1u);
+    }
+  } else {
+    // ---- output group (warps 8-11), every item: O / rowsum -> out[token, head*32 ..] -------------------------------------
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int w = r >> 6, q = r & 63;
+    const bool qreal = q < WT;
+    const int qy = q / WS, qx = q - qy * WS;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    int* stok = stok_all + quarter * 32;
+    for (int i = 0; i < nt; ++i) {
+      const int b = i & 1;
+      const int win = 2 * item_of(i) + w;
+      const bool live = qreal && win < num_windows;
+      long long tok = 0;
+      if (live) tok = token_of(window_pos(win), qy, qx);
+      mbar_wait_spin(o_full(b), ((uint32_t)i >> 1) & 1u, wait_hint);
       tc_fence_after();
       uint32_t ov[2][16];
       const uint32_t o_addr = tmem_base + lane_sel + 256 + b * 32;
@@ -425,63 +445,65 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       tmem_ld16(o_addr + 16, ov[1]);
       tmem_ld_wait();
       tc_fence_before();
+      // 1/rowsum was written by the softmax thread of this row before it arrived on p_full, which the MMA thread acquired
+      // before issuing P.V(i), whose completion this thread has just observed.  Read BEFORE o_empty is released: the ring
+      // slot (i & 3) is rewritten by item i + 4, whose scores cannot even be issued before P.V(i + 2), which waits for
+      // that release.
+      const float inv = sinv[(i & 3) * 128 + r];
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty(b));
       // Row per lane -> global would touch 32 different cache lines per store instruction (measured: the output phase was
-      // the longest part of an item).  Each warp therefore transposes its 32 rows through the Q tile of the item's stage
-      // (dead since the score MMAs completed; the stage is only released below) and stores whole rows: 8 (4) lanes cover
-      // the 128 (64) bytes of one token's head slice.
-      {
-        const int s = i % NS;
-        uint8_t* scratch = smem_gen + s * K::kStageB + (quarter * 32) * K::kRowB;   // this warp's 32 rows of the Q tile
-        int* stok = stok_all + (warp & 7) * 32;
-        stok[lane] = live ? (int)tok : -1;
-        if (live) {
-          uint8_t* srow = scratch + lane * K::kRowB;
-          if constexpr (BF) {
+      // the longest part of an item).  Each warp therefore transposes its rows through a small scratch and stores whole
+      // rows: 8 (4) lanes cover the 128 (64) bytes of one token's head slice.
+      // this warp's live rows (32 of the first, 17 of the second quarter of each window half) in the transpose scratch
+      uint8_t* scratch = oscr + ((quarter >> 1) * WT + (quarter & 1) * 32) * K::kRowB;
+      stok[lane] = live ? (int)tok : -1;
+      if (live) {
+        uint8_t* srow = scratch + lane * K::kRowB;
+        if constexpr (BF) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t* o8 = &ov[c >> 1][(c & 1) * 8];
-              *reinterpret_cast<uint4*>(srow + ((c ^ ((r >> 1) & 3)) << 4)) =
-                  make_uint4(pack_bf16x2(__uint_as_float(o8[0]) * inv, __uint_as_float(o8[1]) * inv),
-                             pack_bf16x2(__uint_as_float(o8[2]) * inv, __uint_as_float(o8[3]) * inv),
-                             pack_bf16x2(__uint_as_float(o8[4]) * inv, __uint_as_float(o8[5]) * inv),
-                             pack_bf16x2(__uint_as_float(o8[6]) * inv, __uint_as_float(o8[7]) * inv));
-            }
-          } else {
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t* o8 = &ov[c >> 1][(c & 1) * 8];
+            *reinterpret_cast<uint4*>(srow + ((c ^ ((r >> 1) & 3)) << 4)) =
+                make_uint4(pack_bf16x2(__uint_as_float(o8[0]) * inv, __uint_as_float(o8[1]) * inv),
+                           pack_bf16x2(__uint_as_float(o8[2]) * inv, __uint_as_float(o8[3]) * inv),
+                           pack_bf16x2(__uint_as_float(o8[4]) * inv, __uint_as_float(o8[5]) * inv),
+                           pack_bf16x2(__uint_as_float(o8[6]) * inv, __uint_as_float(o8[7]) * inv));
+          }
+        } else {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint32_t* o4 = &ov[c >> 2][(c & 3) * 4];
-              float4 o = make_float4(__uint_as_float(o4[0]) * inv, __uint_as_float(o4[1]) * inv, __uint_as_float(o4[2]) * inv,
-                                     __uint_as_float(o4[3]) * inv);
-              if (d.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-              *reinterpret_cast<float4*>(srow + ((c ^ (r & 7)) << 4)) = o;
-            }
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t* o4 = &ov[c >> 2][(c & 3) * 4];
+            float4 o = make_float4(__uint_as_float(o4[0]) * inv, __uint_as_float(o4[1]) * inv, __uint_as_float(o4[2]) * inv,
+                                   __uint_as_float(o4[3]) * inv);
+            if (d.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+            *reinterpret_cast<float4*>(srow + ((c ^ (r & 7)) << 4)) = o;
           }
         }
-        __syncwarp();
-        constexpr int CH = K::kRowB / 16;        // 16-byte chunks per row: 8 | 4
-        constexpr int RPI = 32 / CH;             // rows per store instruction: 4 | 8
-        const int ch = lane % CH, rsub = lane / CH;
-        T* outh = reinterpret_cast<T*>(d.out) + head * HD + ch * (16 / (int)sizeof(T));
-        if (!(d.reserved0 & 16)) {               // (probe bit 16: no output stores)
+      }
+      __syncwarp();
+      constexpr int CH = K::kRowB / 16;        // 16-byte chunks per row: 8 | 4
+      constexpr int RPI = 32 / CH;             // rows per store instruction: 4 | 8
+      const int ch = lane % CH, rsub = lane / CH;
+      T* outh = reinterpret_cast<T*>(d.out) + head * HD + ch * (16 / (int)sizeof(T));
+      if (!(d.reserved0 & 16)) {               // (probe bit 16: no output stores)
 #pragma unroll
-          for (int p0 = 0; p0 < 32; p0 += RPI) {
-            const int lr = p0 + rsub, row = quarter * 32 + lr;
-            const int tk = stok[lr];
+        for (int p0 = 0; p0 < 32; p0 += RPI) {
+          const int lr = p0 + rsub, row = quarter * 32 + lr;
+          const int tk = stok[lr];
+          if (tk >= 0) {   // (rows without a token do not exist in the scratch)
             const uint4 v = *reinterpret_cast<const uint4*>(scratch + lr * K::kRowB +
                                                             ((BF ? (ch ^ ((row >> 1) & 3)) : (ch ^ (row & 7))) << 4));
-            if (tk >= 0) *reinterpret_cast<uint4*>(outh + (size_t)tk * d.C) = v;
+            *reinterpret_cast<uint4*>(outh + (size_t)tk * d.C) = v;
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar(s));   // the scratch rows are free: with the P.V commit this releases the stage
       }
+      __syncwarp();   // the scratch is reused by the next item
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 10) tmem_dealloc<512>(tmem_base);
+  if (warp == WU_W_MMA) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace

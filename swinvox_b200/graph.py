@@ -396,7 +396,14 @@ def lower_decoder(plan, dec, feat, N):
     for li, (layer, pads, cout) in enumerate(((dec.layer1, (2, 1, 1), 128), (dec.layer2, (1, 1, 1), 64),
                                               (dec.layer3, (1, 1, 1), 32))):
         o = plan.new_act(N, 2 * x.D, 2 * x.H, 2 * x.W, cout)
-        _convT_layer(plan, x, layer[0], layer[1], pads, o, f"decoder.layer{li + 1}")
+        if tuple(layer[0].kernel_size) == (4, 4, 4):
+            # k4 s2 p1: all eight output-parity classes in the N dimension of ONE contraction over the 3x3x3 input
+            # neighbourhood (one launch instead of eight; the structural zeros cost 3.4x MACs on a layer that is launch-
+            # and latency-bound: 24 micro-launches took 0.63 ms against a 0.08 ms floor)
+            plan.convT_fused(x, E.pack_convT_fused(layer[0].weight, layer[1], dev, bias=layer[0].bias), o, act=ACT_RELU,
+                             round_out=True, name=f"decoder.layer{li + 1}")
+        else:   # layer1: kernel (6, 4, 4) -- three depth taps per class
+            _convT_layer(plan, x, layer[0], layer[1], pads, o, f"decoder.layer{li + 1}")
         x = o
     raw = plan.new_act(N, 32, 32, 32, 16, Cs=32, pad=(1, 1, 1))
     coarse = plan.empty(N, 32768)

@@ -451,6 +451,25 @@ def test_convtranspose3d_fused_classes(dev, cout, ind):
     assert rel_err(to_nchw(out), (ref + skip.double()) * 0.5) < 1e-4
 
 
+@pytest.mark.parametrize("cin,cout,ind", [(128, 64, (4, 4, 4)), (64, 32, (8, 8, 8)), (32, 16, (3, 5, 6))])
+def test_convtranspose3d_classes_in_n(dev, cin, cout, ind):
+    """ConvTranspose3d(k4, s2, p1) + BN + ReLU with the eight parity classes in N (decoder layers 2 and 3): class blocks of
+    a multiple of 16 channels leave through 64-byte vector stores"""
+    DEV = dev
+    torch.manual_seed(cin)
+    x = E.tf32_round(torch.randn(2, cin, *ind))
+    ct = torch.nn.ConvTranspose3d(cin, cout, 4, 2, 1, bias=False)
+    bn = rand_bn(torch.nn.BatchNorm3d(cout))
+    p = E.Plan(DEV)
+    out = p.new_act(2, 2 * ind[0], 2 * ind[1], 2 * ind[2], cout)
+    p.convT_fused(act_from_nchw(x, DEV), E.pack_convT_fused(ct.weight, bn, DEV), out, act=E.ACT_RELU, round_out=True)
+    p.run()
+    sync(DEV)
+    wf, bf = E.fold_bn(ct.weight.transpose(0, 1), None, bn)
+    ref = F.relu(F.conv_transpose3d(x.double(), E.tf32_round(wf).transpose(0, 1).double(), bf.double(), 2, 1))
+    assert rel_err(to_nchw(out), ref) < 6e-4   # result stored TF32-rounded
+
+
 def test_decoder_tail_fused_classes(dev):
     """decoder layer4 + layer5 + cat with the eight classes in one GEMM, writing the merger's zero-bordered layout"""
     DEV = dev
