@@ -364,8 +364,6 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "objects/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "api": "swinvox_b200.evaluate.BatchedEvaluator.submit/finish"},
             "gpu_launches": rec.num_launches() * args.steps,
-            "attention_kernel": ("mma.sync (SVX_WINATTN_MMASYNC)" if os.environ.get("SVX_WINATTN_MMASYNC")
-                                 else "tcgen05 / TMEM (winattn_umma_kernel)"),
             "clocks": sampler.summary(),
             "roofline": roofline,
         }
@@ -397,31 +395,8 @@ def main():
         run_reference(args)
     elif args.impl == "reference-gpu":
         run_reference_gpu(args)
-    elif "WORLD_SIZE" in os.environ or os.environ.get("SVX_BENCH_CHILD"):
-        run_ours(args)
     else:
-        # Single-process launch: the measurement runs in a child so that a launch failure (which poisons the CUDA context of
-        # its process) cannot take the whole benchmark line down.  If the child fails, it is re-run ONCE with the round-1
-        # mma.sync window-attention kernel and the line says so (`attention_kernel`); normally the child's line is passed on.
-        import subprocess
-        env = dict(os.environ, SVX_BENCH_CHILD="1")
-        r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, stdout=subprocess.PIPE, text=True)
-        note = None
-        if r.returncode != 0 or not r.stdout.strip():
-            sys.stderr.write(f"bench.py: the measurement process exited with {r.returncode}; retrying with SVX_WINATTN_MMASYNC=1\n")
-            note = f"mma.sync fallback (the first attempt exited with code {r.returncode})"
-            r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=dict(env, SVX_WINATTN_MMASYNC="1"),
-                               stdout=subprocess.PIPE, text=True)
-        lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
-        if note and lines:
-            try:
-                d = json.loads(lines[-1])
-                d["attention_kernel"] = note
-                lines[-1] = json.dumps(d)
-            except ValueError:
-                pass
-        print("\n".join(lines), flush=True)
-        sys.exit(r.returncode)
+        run_ours(args)
 
 
 if __name__ == "__main__":

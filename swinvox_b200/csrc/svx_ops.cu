@@ -25,9 +25,6 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ void named_bar(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 // block-wide sum for blockDim.x <= 1024; `red` is 32 floats of shared memory
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
@@ -568,241 +565,8 @@ __global__ void __launch_bounds__(1024, 1) lnsample_cluster_kernel(const svx_lns
   }
   cluster_barrier();   // nobody leaves while a peer may still read its partials
 }
-
-// ---- shifted-window attention (timm WindowAttention + roll / partition / reverse) on the tensor cores ------
-// One warp per (window, head); a CTA's four warps share one head so its relative-position bias sits in shared
-// memory.  Per item Q, K and V (49 x 32 each) are staged in shared memory by cp.async; S = Q K^T and O = P V run as
-// mma.sync m16n8k8 TF32 (fp32 accumulate) on 16-query-row strips; softmax (scale, bias, -100 shift mask) works on
-// the accumulator fragments in registers.  The cyclic shift, window partition and their inverses are index
-// arithmetic on the token rows.  Index maps are chosen so every fragment is a 16-byte shared-memory read:
-//   QK^T contraction slot (step ks, slot t / t+4)  <->  d = 8t + 2ks / 8t + 2ks + 1   (same map for Q and K)
-//   PV   contraction slot (block j, slot t / t+4)  <->  key 8j + 2t / 8j + 2t + 1     (= the accumulator's columns)
-//   PV   output column (tile dn, column c)         <->  d = 4c + dn                    (a lane ends up with 8 adjacent d)
+// ---- shifted-window attention: the kernel lives in svx_winattn.cu (tcgen05 / TMEM); only the argument checks are here
 constexpr int WS = 7, WT = 49, HD = 32;
-constexpr int WA_ITEMS = 4;       // (window, head) items in flight per CTA, two warps each
-constexpr int WA_STRIDE = 36;     // floats per staged row: conflict-free 16-byte fragment loads
-constexpr int WA_ROWS = 56;       // 49 tokens padded to 7 blocks of 8 (rows 49..55 stay zero)
-constexpr int WA_BSTRIDE = 50;    // floats per bias row in shared memory
-constexpr int WA_BIAS_BYTES = (WT * WA_BSTRIDE * 4 + 15) / 16 * 16;
-constexpr int WA_ITEM_BYTES = 3 * WA_ROWS * WA_STRIDE * 4 + 2 * 64 * 4;
-constexpr int WA_SMEM = WA_BIAS_BYTES + WA_ITEMS * WA_ITEM_BYTES;
-constexpr float kLog2e = 1.4426950408889634f;
-
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                                uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// Two warps per item (query strips {0,1} and {2,3}); they stage the item together and meet on a named barrier.
-// Scores are kept in the log2 domain: scale and bias carry a factor log2(e), so the softmax exponent is one ex2.
-// T = storage type of qkv / out (fp32 or bf16): rows are staged as stored (bf16 rows are 64 bytes, 80-byte pitch) and
-// widened to fp32 when the MMA fragments are loaded, so the arithmetic is the same TF32 mma.sync either way.
-template <typename T> struct WaRow;
-template <> struct WaRow<float> {
-  static constexpr int kPitch = WA_STRIDE * 4, kChunks = 8;   // bytes per staged row, 16-byte chunks per 32-dim row
-  static __device__ __forceinline__ void ld8(const uint8_t* row, int d0, float (&v)[8]) {
-    const float4 a = *reinterpret_cast<const float4*>(row + d0 * 4), b = *reinterpret_cast<const float4*>(row + d0 * 4 + 16);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  }
-  static __device__ __forceinline__ float4 ld4v(const uint8_t* row, int d0) { return *reinterpret_cast<const float4*>(row + d0 * 4); }
-  static __device__ __forceinline__ void st8(float* dst, const float (&v)[8]) {
-    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-  }
-};
-template <> struct WaRow<bf16_t> {
-  static constexpr int kPitch = 80, kChunks = 4;
-  static __device__ __forceinline__ void ld8(const uint8_t* row, int d0, float (&v)[8]) {
-    const uint4 u = *reinterpret_cast<const uint4*>(row + d0 * 2);
-    v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
-    v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
-  }
-  static __device__ __forceinline__ float4 ld4v(const uint8_t* row, int d0) {
-    const uint2 u = *reinterpret_cast<const uint2*>(row + d0 * 2);
-    return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
-  }
-  static __device__ __forceinline__ void st8(bf16_t* dst, const float (&v)[8]) {
-    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                                pack_bf16x2(v[6], v[7]));
-  }
-};
-
-template <bool SHIFTED, typename T>
-__global__ void __launch_bounds__(WA_ITEMS * 64, 2) winattn_kernel(const svx_winattn_desc d, int ctas_per_head) {
-  using R = WaRow<T>;
-  constexpr int PITCH = R::kPitch, MAT = WA_ROWS * PITCH;   // bytes per staged row / per staged Q, K or V
-  extern __shared__ __align__(16) uint8_t wa_smem[];
-  float* sbias = reinterpret_cast<float*>(wa_smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = warp >> 1, half = warp & 1, ptid = threadIdx.x & 63;
-  uint8_t* mine = wa_smem + WA_BIAS_BYTES + pair * WA_ITEM_BYTES;
-  uint8_t* Qs = mine;
-  uint8_t* Ks = Qs + MAT;
-  uint8_t* Vs = Ks + MAT;
-  uint32_t* stok = reinterpret_cast<uint32_t*>(mine + 3 * WA_ROWS * WA_STRIDE * 4);   // token row index
-  int* sreg = reinterpret_cast<int*>(stok + 64);
-  const int head = blockIdx.x % d.heads;
-  const int cta_in_head = blockIdx.x / d.heads;
-  for (int i = threadIdx.x; i < WT * WT; i += blockDim.x)
-    sbias[(i / WT) * WA_BSTRIDE + (i % WT)] = __ldg(d.bias + (long long)head * WT * WT + i) * kLog2e;
-  for (int i = ptid; i < 3 * MAT / 4; i += 64) reinterpret_cast<uint32_t*>(Qs)[i] = 0u;   // incl. the padding rows, never rewritten
-  __syncthreads();
-  const int nwx = d.W / WS, nwy = d.H / WS;
-  const int num_windows = d.N * nwx * nwy;   // < 2^31 (checked by the launcher)
-  const size_t tok_pitch = (size_t)3 * d.C * sizeof(T);
-  const size_t c_bytes = (size_t)d.C * sizeof(T);
-  const int g = lane >> 2, t = lane & 3;
-  const uint8_t* qkvb = reinterpret_cast<const uint8_t*>(d.qkv) + (size_t)head * HD * sizeof(T);
-  const uint32_t qs_u32 = smem_u32(Qs);
-  const float scale2 = d.scale * kLog2e;
-  const float kMask = -100.f * kLog2e;
-  const int barid = 1 + pair;
-  for (int win = cta_in_head * WA_ITEMS + pair; win < num_windows; win += ctas_per_head * WA_ITEMS) {
-    const int wq = win / nwx;
-    const int wx = win - wq * nwx;
-    const int n = wq / nwy;
-    const int wy = wq - n * nwy;
-    named_bar(barid, 64);   // both warps are done with the previous item's staging buffers
-    {
-      const int tk = min(ptid, WT - 1);
-      const int py = wy * WS + tk / WS, px = wx * WS + tk % WS;   // position in the rolled map
-      int oy = py + d.shift, ox = px + d.shift;   // shift < H, W: one conditional subtraction instead of a modulo
-      oy -= oy >= d.H ? d.H : 0;
-      ox -= ox >= d.W ? d.W : 0;
-      stok[ptid] = (uint32_t)((n * d.H + oy) * d.W + ox);   // token row
-      int reg = 0;
-      if (SHIFTED) {
-        const int ry = py < d.H - WS ? 0 : (py < d.H - d.shift ? 1 : 2);
-        const int rx = px < d.W - WS ? 0 : (px < d.W - d.shift ? 1 : 2);
-        reg = ry * 3 + rx;
-      }
-      sreg[ptid] = reg;
-    }
-    named_bar(barid, 64);
-    // stage Q | K | V rows (49 rows of 32 dims each) with 16-byte cp.async
-    for (int i = ptid; i < WT * R::kChunks; i += 64) {
-      const int row = i / R::kChunks, ch = i % R::kChunks;
-      const uint8_t* base = qkvb + (size_t)stok[row] * tok_pitch + ch * 16;
-      const uint32_t dst = qs_u32 + row * PITCH + ch * 16;
-      cp_async16_zfill(dst, base, 16u);
-      cp_async16_zfill(dst + MAT, base + c_bytes, 16u);
-      cp_async16_zfill(dst + 2 * MAT, base + 2 * c_bytes, 16u);
-    }
-    cp_async_commit();
-    int kreg[7][2];
-    if (SHIFTED) {
-#pragma unroll
-      for (int nb = 0; nb < 7; ++nb) {
-        kreg[nb][0] = sreg[8 * nb + 2 * t];
-        kreg[nb][1] = sreg[8 * nb + 2 * t + 1];
-      }
-    }
-    cp_async_wait<0>();
-    named_bar(barid, 64);
-#pragma unroll 1
-    for (int mi = 0; mi < 2; ++mi) {
-      const int r0 = 16 * (2 * half + mi) + g, r1 = r0 + 8;
-      const int r1c = min(r1, WA_ROWS - 1);
-      // Q fragments: lane t holds d = 8t .. 8t+7 of rows r0, r1 (contraction slot map above)
-      float q0[8], q1[8];
-      R::ld8(Qs + r0 * PITCH, 8 * t, q0);
-      R::ld8(Qs + r1c * PITCH, 8 * t, q1);
-      float s[7][4];
-#pragma unroll
-      for (int nb = 0; nb < 7; ++nb) {
-        s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
-        float kk[8];
-        R::ld8(Ks + (8 * nb + g) * PITCH, 8 * t, kk);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          mma_tf32_16x8x8(s[nb], __float_as_uint(q0[2 * ks]), __float_as_uint(q1[2 * ks]), __float_as_uint(q0[2 * ks + 1]),
-                          __float_as_uint(q1[2 * ks + 1]), __float_as_uint(kk[2 * ks]), __float_as_uint(kk[2 * ks + 1]));
-      }
-      const int myreg0 = SHIFTED ? sreg[r0] : 0, myreg1 = SHIFTED ? sreg[r1] : 0;
-      const float* b0p = sbias + min(r0, WT - 1) * WA_BSTRIDE + 2 * t;
-      const float* b1p = sbias + min(r1, WT - 1) * WA_BSTRIDE + 2 * t;
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int nb = 0; nb < 7; ++nb) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          // columns 8nb + 2t + e; only block 6 has columns beyond the 49 keys (everything but t == 0, e == 0)
-          const bool ok = nb < 6 || (t == 0 && e == 0);
-          float v0 = fmaf(s[nb][e], scale2, ok ? b0p[8 * nb + e] : 0.f);
-          float v1 = fmaf(s[nb][2 + e], scale2, ok ? b1p[8 * nb + e] : 0.f);
-          if (SHIFTED) {
-            v0 += kreg[nb][e] != myreg0 ? kMask : 0.f;
-            v1 += kreg[nb][e] != myreg1 ? kMask : 0.f;
-          }
-          if (nb == 6) {
-            v0 = ok ? v0 : -INFINITY;
-            v1 = ok ? v1 : -INFINITY;
-          }
-          s[nb][e] = v0;
-          s[nb][2 + e] = v1;
-          mx0 = fmaxf(mx0, v0);
-          mx1 = fmaxf(mx1, v1);
-        }
-      }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-      for (int nb = 0; nb < 7; ++nb) {
-        s[nb][0] = ex2_approx(s[nb][0] - mx0); s[nb][1] = ex2_approx(s[nb][1] - mx0);
-        s[nb][2] = ex2_approx(s[nb][2] - mx1); s[nb][3] = ex2_approx(s[nb][3] - mx1);
-        sum0 += s[nb][0] + s[nb][1];
-        sum1 += s[nb][2] + s[nb][3];
-      }
-      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-      float o[4][4];
-#pragma unroll
-      for (int dn = 0; dn < 4; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        const uint32_t p0 = __float_as_uint(round_tf32(s[j][0])), p1 = __float_as_uint(round_tf32(s[j][2]));
-        const uint32_t p2 = __float_as_uint(round_tf32(s[j][1])), p3 = __float_as_uint(round_tf32(s[j][3]));
-        // keys 8j+2t and 8j+2t+1; output column c of tile dn is d = 4c + dn, so lane column g reads d = 4g .. 4g+3
-        const float4 va = R::ld4v(Vs + (8 * j + 2 * t) * PITCH, 4 * g);
-        const float4 vb = R::ld4v(Vs + (8 * j + 2 * t + 1) * PITCH, 4 * g);
-        mma_tf32_16x8x8(o[0], p0, p1, p2, p3, __float_as_uint(va.x), __float_as_uint(vb.x));
-        mma_tf32_16x8x8(o[1], p0, p1, p2, p3, __float_as_uint(va.y), __float_as_uint(vb.y));
-        mma_tf32_16x8x8(o[2], p0, p1, p2, p3, __float_as_uint(va.z), __float_as_uint(vb.z));
-        mma_tf32_16x8x8(o[3], p0, p1, p2, p3, __float_as_uint(va.w), __float_as_uint(vb.w));
-      }
-      // accumulator column 2t / 2t+1 of tile dn is d = 8t + dn / 8t + 4 + dn: the lane owns d = 8t .. 8t+7 of its rows
-      const float inv0 = __frcp_rn(sum0), inv1 = __frcp_rn(sum1);
-      T* outh = reinterpret_cast<T*>(d.out) + head * HD + 8 * t;
-      if (r0 < WT) {
-        const float v[8] = {maybe_round(o[0][0] * inv0, d.round_tf32), maybe_round(o[1][0] * inv0, d.round_tf32),
-                            maybe_round(o[2][0] * inv0, d.round_tf32), maybe_round(o[3][0] * inv0, d.round_tf32),
-                            maybe_round(o[0][1] * inv0, d.round_tf32), maybe_round(o[1][1] * inv0, d.round_tf32),
-                            maybe_round(o[2][1] * inv0, d.round_tf32), maybe_round(o[3][1] * inv0, d.round_tf32)};
-        R::st8(outh + (size_t)stok[r0] * d.C, v);
-      }
-      if (r1 < WT) {
-        const float v[8] = {maybe_round(o[0][2] * inv1, d.round_tf32), maybe_round(o[1][2] * inv1, d.round_tf32),
-                            maybe_round(o[2][2] * inv1, d.round_tf32), maybe_round(o[3][2] * inv1, d.round_tf32),
-                            maybe_round(o[0][3] * inv1, d.round_tf32), maybe_round(o[1][3] * inv1, d.round_tf32),
-                            maybe_round(o[2][3] * inv1, d.round_tf32), maybe_round(o[3][3] * inv1, d.round_tf32)};
-        R::st8(outh + (size_t)stok[r1] * d.C, v);
-      }
-    }
-  }
-}
 
 // ---- depthwise k=s conv, channels-last ---------------------------------------------------------------
 template <typename T>
@@ -1267,31 +1031,8 @@ int winattn_launch(const svx_winattn_desc& d, void* stream) {
   const long long windows = (long long)d.N * (d.H / WS) * (d.W / WS);
   SVX_REQUIRE(windows * WT * (3LL * d.C / 4) < 0xffffffffLL && d.C % 4 == 0 && al16(d.qkv) && al16(d.out),
               "window_attention: tensor too large for 32-bit row offsets, or unaligned");
-  long long per_head = (windows + WA_ITEMS - 1) / WA_ITEMS;
-  const long long cap = (2LL * kSmCount + d.heads - 1) / d.heads;   // two resident CTAs per SM over all heads
-  if (per_head > cap) per_head = cap;
-  if (per_head < 1) per_head = 1;
   SVX_REQUIRE(d.dtype == 0 || (d.dtype == SVX_DT_BF16 && d.C % 8 == 0), "window_attention: qkv and out share one storage type");
-  // the tensor-core (tcgen05 / TMEM) kernel of svx_winattn.cu; SVX_WINATTN_MMASYNC=1 keeps the round-1 mma.sync kernel
-  // below reachable for A/B measurements
-  static const bool legacy = getenv("SVX_WINATTN_MMASYNC") != nullptr;
-  if (!legacy) return winattn_umma_launch(d, stream);
-  // (per device: a process may drive several GPUs)
-  SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
-  SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
-  SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel<false, bf16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
-  SVX_CUDA_OK(cudaFuncSetAttribute(winattn_kernel<true, bf16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
-  const int grid = (int)(per_head * d.heads);
-  const bool bf = d.dtype == SVX_DT_BF16;
-  if (d.shift > 0) {
-    if (bf) winattn_kernel<true, bf16_t><<<grid, WA_ITEMS * 64, WA_SMEM, (cudaStream_t)stream>>>(d, (int)per_head);
-    else winattn_kernel<true, float><<<grid, WA_ITEMS * 64, WA_SMEM, (cudaStream_t)stream>>>(d, (int)per_head);
-  } else {
-    if (bf) winattn_kernel<false, bf16_t><<<grid, WA_ITEMS * 64, WA_SMEM, (cudaStream_t)stream>>>(d, (int)per_head);
-    else winattn_kernel<false, float><<<grid, WA_ITEMS * 64, WA_SMEM, (cudaStream_t)stream>>>(d, (int)per_head);
-  }
-  SVX_LAUNCH_OK("winattn_kernel");
-  return 0;
+  return winattn_umma_launch(d, stream);
 }
 
 int dwconv_launch(const svx_dwconv_desc& d, void* stream) {

@@ -102,8 +102,51 @@ __host__ __device__ constexpr uint64_t wu_keys_ge4(bool by_row) {
 }
 constexpr uint64_t kKeysAll = (1ull << WT) - 1;
 
+
+// Stall diagnostics (SVX_WINATTN_DEBUG=<address of a pinned, zeroed host buffer of >= 148*17*32 u64>): a barrier wait that
+// makes no progress for ~2 s writes who waited for what, and the state of every barrier of the CTA, into host memory
+// (readable after the trap has killed the context).
+__device__ __noinline__ void wu_report(unsigned long long* dbg, uint32_t bar_base, int nbars, uint32_t tag, uint32_t bar,
+                                       uint32_t parity, int i, int extra) {
+  if (dbg) {
+    unsigned long long* rec = dbg + ((size_t)blockIdx.x * 17 + (threadIdx.x >> 5)) * 32;
+    rec[0] = 0xD1A6000000000000ull | ((unsigned long long)tag << 32) | ((unsigned long long)((bar - bar_base) / 8) << 16) |
+             ((unsigned long long)parity << 8) | (threadIdx.x & 31);
+    rec[1] = ((unsigned long long)(uint32_t)i << 32) | (uint32_t)extra;
+    rec[2] = ((unsigned long long)gridDim.x << 32) | blockIdx.x;
+    for (int b = 0; b < nbars && b < 28; ++b) {
+      unsigned long long v;
+      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(bar_base + 8u * b));
+      rec[3 + b] = v;
+    }
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void wu_wait(uint32_t bar, uint32_t parity, unsigned long long* dbg, uint32_t bar_base, int nbars,
+                                        uint32_t tag, int i) {
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    if (mbar_test(bar, parity)) break;
+    if ((it & 4095u) == 4095u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) wu_report(dbg, bar_base, nbars, tag, bar, parity, i, 0);
+    }
+  }
+}
+
+// Timing probes (builds with -DSVX_WINATTN_PROBES only; they switch single stages of the pipeline off and give WRONG
+// results -- how profiles/r2_winattn_probes.txt was measured).  The product build has none.
+#ifdef SVX_WINATTN_PROBES
+#define WU_PROBE(bit) ((d.reserved0 & (bit)) != 0)
+#else
+#define WU_PROBE(bit) false
+#endif
+#define WU_WAIT(bar, parity, tag) wu_wait(bar, parity, dbg, bar_base, 3 * NS + 12, tag, i)
+
 template <typename T, bool SHIFTED>
-__global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_winattn_desc d, int ctas_per_head) {
+__global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_winattn_desc d, int ctas_per_head, unsigned long long* dbg) {
   using K = WuCfg<T>;
   constexpr bool BF = K::kBf;
   constexpr int NS = K::kStages;
@@ -133,7 +176,6 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (3 * NS + 12));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t wait_hint = (uint32_t)d.reserved0 >> 16;   // (probe bits 16..: suspend-time hint of the barrier waits, ns)
   const int head = blockIdx.x % d.heads;
   const int cta_in_head = blockIdx.x / d.heads;
   const int nwx = d.W / WS, nwy = d.H / WS;
@@ -195,9 +237,9 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
     const uint8_t* qkvb = reinterpret_cast<const uint8_t*>(d.qkv) + (size_t)head * HD * sizeof(T) + ch * 16;
     for (int i = 0; i < nt; ++i) {
       const int s = i % NS;
-      mbar_wait_spin(empty_bar(s), (((uint32_t)(i / NS)) & 1u) ^ 1u, wait_hint);
+      WU_WAIT(empty_bar(s), (((uint32_t)(i / NS)) & 1u) ^ 1u, 1u);
       const int win = 2 * item_of(i) + w;
-      if (win < num_windows && !(d.reserved0 & 1)) {   // (probe bit 1: no loads -- timing experiments only)
+      if (win < num_windows && !WU_PROBE(1)) {   // (probe bit 1: no loads -- timing experiments only)
         const uint32_t dst0 = stage_smem + s * K::kStageB + (64 * w) * K::kRowB;
         const WinPos wp = window_pos(win);
 #pragma unroll 1
@@ -240,6 +282,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       auto issue_s = [&](int i) {
         const int s = i % NS, b = i & 1;
         tc_fence_after();
+        fence_proxy_async_smem();   // the rows were written by cp.async (generic proxy), the MMAs read them through the async proxy
         const uint32_t q_addr = stage_smem + s * K::kStageB;
         const uint64_t da = wu_desc(q_addr, sbo, lay), db = wu_desc(q_addr + K::kMatB, sbo, lay);
 #pragma unroll
@@ -260,7 +303,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
           // B: the 16 V rows of this step = 1024 bytes (two 8-key groups 512 bytes apart)
           const uint64_t da = umma_desc_sw128(p_addr + (k >> 2) * (128 * 128)) + 2u * (k & 3);
           const uint64_t db = wu_desc(v_addr + k * 1024, 512u, 4u);
-          if (d.reserved0 & 8) continue;                                    // (probe bit 8: no P.V MMAs)
+          if (WU_PROBE(8)) continue;                                    // (probe bit 8: no P.V MMAs)
           umma_f16(tmem_base + 256 + b * 32, da, db, idesc_o, k != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar(s));     // Q, K, V of this item are no longer needed
@@ -269,7 +312,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       };
       int ns = 0, np = 0;              // next item whose scores / whose P.V product is to be issued
       long long t0 = 0;
-      const bool in_order = (d.reserved0 & 128) != 0;   // (probe bit 128: strict S(0) S(1) | PV(i) S(i+2) order)
+      const bool in_order = WU_PROBE(128);   // (probe bit 128: strict S(0) S(1) | PV(i) S(i+2) order)
       for (uint32_t it = 0; np < nt; ++it) {
         bool did = false;
         if (in_order) {
@@ -277,13 +320,19 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
           else if (ready_pv(np)) { issue_pv(np); ++np; did = true; }
         } else {
           if (np < ns && ready_pv(np)) { issue_pv(np); ++np; did = true; }
-          if (ns < nt && ready_s(ns)) { issue_s(ns); ++ns; did = true; }
+          // S(i) only after P.V(i - 2) [i - 4 with two P buffers] has been ISSUED: the softmax thread of item i tells "the
+          // P buffer is free" from the PARITY of p_empty, which cannot distinguish "P.V(i-1) done" from "P.V(i-3) done".
+          // The tensor pipe runs in issue order, so with this gate P.V(i-2) [and its commit] precede the scores the softmax
+          // of item i waits for.  (Without it, an output group held up by slow stores let S(i) overtake P.V(i-2): the
+          // P buffer was overwritten early, p_full ran one phase ahead, and the CTA deadlocked -- seen only with other
+          // streams loading the memory system.)
+          if (ns < nt && ns < np + 2 * K::kPBufs && ready_s(ns)) { issue_s(ns); ++ns; did = true; }
         }
         if (did) { it = 0; t0 = 0; }
         else if ((it & 4095u) == 4095u) {   // ~2 s without progress: a protocol bug (see mbar_wait)
           const long long now = clock64();
           if (t0 == 0) t0 = now;
-          else if (now - t0 > 4000000000LL) __trap();
+          else if (now - t0 > 4000000000LL) wu_report(dbg, bar_base, 3 * NS + 12, 6u, bar_base, 0u, np, ns | (nt << 16));
         }
       }
     }
@@ -306,7 +355,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       }
       for (int i = 0; i < nt; ++i) {
         const int s = i % NS;
-        mbar_wait_spin(full_bar(s), ((uint32_t)(i / NS)) & 1u, wait_hint);
+        WU_WAIT(full_bar(s), ((uint32_t)(i / NS)) & 1u, 2u);
         const uint8_t* src = smem_gen + s * K::kStageB + 2 * K::kMatB;
         uint8_t* dst = v16_gen + s * K::kV16B;
         float4 a[UPT], b[UPT];
@@ -318,7 +367,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
         }
 #pragma unroll
         for (int k = 0; k < UPT; ++k) {
-          if (urow[k] < 0 || (d.reserved0 & 32)) continue;   // (probe bit 32: no V conversion)
+          if (urow[k] < 0 || WU_PROBE(32)) continue;   // (probe bit 32: no V conversion)
           const int row = urow[k], oc = uoc[k];
           const uint32_t m0 = max(max(__float_as_uint(a[k].x) & 0x7fffffffu, __float_as_uint(a[k].y) & 0x7fffffffu),
                                   max(__float_as_uint(a[k].z) & 0x7fffffffu, __float_as_uint(a[k].w) & 0x7fffffffu));
@@ -360,7 +409,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
         if (wp.wy == nwy - 1) masked |= qy < 4 ? kRowGe4 : (kKeysAll & ~kRowGe4);
         if (wp.wx == nwx - 1) masked |= qx < 4 ? kColGe4 : (kKeysAll & ~kColGe4);
       }
-      mbar_wait_spin(s_full(b), ((uint32_t)i >> 1) & 1u, wait_hint);
+      WU_WAIT(s_full(b), ((uint32_t)i >> 1) & 1u, 3u);
       tc_fence_after();
       // this row's scores against the 64 key slots of its own window (slots 49..63 are padding); the values are turned
       // into logits and then probabilities in place
@@ -375,7 +424,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       if (lane == 0) mbar_arrive(s_empty(b));
       auto E = [&](int j) -> uint32_t& { return sv[j >> 4][j & 15]; };
       float mxp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four partial maxima / sums: short dependency chains
-      if (!(d.reserved0 & 2)) {   // (probe bit 2: no softmax arithmetic -- timing experiments only)
+      if (!WU_PROBE(2)) {   // (probe bit 2: no softmax arithmetic -- timing experiments only)
 #pragma unroll
         for (int j = 0; j < WT; ++j) {
           float v = fmaf(__uint_as_float(E(j)), scale2, brow[j]);
@@ -386,7 +435,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       }
       const float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
       float smp[4] = {0.f, 0.f, 0.f, 0.f};
-      if (d.reserved0 & 2) smp[0] = 1.f;
+      if (WU_PROBE(2)) smp[0] = 1.f;
       else {
 #pragma unroll
         for (int j = 0; j < WT; ++j) {
@@ -398,7 +447,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       const float sum = (smp[0] + smp[1]) + (smp[2] + smp[3]);
       // P row in the A-operand layout (K-major, 128B swizzle): only the 49 (+7 zero) slots of the own window
       const uint32_t pi = K::kPBufs == 2 ? (uint32_t)i >> 1 : (uint32_t)i;
-      mbar_wait_spin(p_empty(pb), (pi & 1u) ^ 1u, wait_hint);
+      WU_WAIT(p_empty(pb), (pi & 1u) ^ 1u, 4u);
       sinv[(i & 3) * 128 + r] = __frcp_rn(sum);   // for the output group (ring of four items: see the barrier order there)
       if (live) {
         uint8_t* prow = p_gen + pb * K::kPBytes + r * 128;
@@ -436,7 +485,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       const bool live = qreal && win < num_windows;
       long long tok = 0;
       if (live) tok = token_of(window_pos(win), qy, qx);
-      mbar_wait_spin(o_full(b), ((uint32_t)i >> 1) & 1u, wait_hint);
+      WU_WAIT(o_full(b), ((uint32_t)i >> 1) & 1u, 5u);
       tc_fence_after();
       uint32_t ov[2][16];
       const uint32_t o_addr = tmem_base + lane_sel + 256 + b * 32;
@@ -486,7 +535,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       constexpr int RPI = 32 / CH;             // rows per store instruction: 4 | 8
       const int ch = lane % CH, rsub = lane / CH;
       T* outh = reinterpret_cast<T*>(d.out) + head * HD + ch * (16 / (int)sizeof(T));
-      if (!(d.reserved0 & 16)) {               // (probe bit 16: no output stores)
+      if (!WU_PROBE(16)) {               // (probe bit 16: no output stores)
 #pragma unroll
         for (int p0 = 0; p0 < 32; p0 += RPI) {
           const int lr = p0 + rsub, row = quarter * 32 + lr;
@@ -510,8 +559,13 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
 
 int winattn_umma_launch(const svx_winattn_desc& d_in, void* stream) {
   svx_winattn_desc d = d_in;
-  static const char* probe = getenv("SVX_WINATTN_PROBE");   // timing experiments (wrong results): 1 = no loads, 2 = no softmax
-  d.reserved0 = probe ? atoi(probe) : 0;
+  d.reserved0 = 0;
+#ifdef SVX_WINATTN_PROBES
+  static const char* probe = getenv("SVX_WINATTN_PROBE");   // 1 no loads, 2 no softmax, 8 no P.V, 16 no stores, 32 no V conversion,
+  d.reserved0 = probe ? atoi(probe) : 0;                    // 128 strictly ordered MMA issue
+#endif
+  static const char* dbg_env = getenv("SVX_WINATTN_DEBUG");
+  unsigned long long* dbg = dbg_env ? reinterpret_cast<unsigned long long*>(strtoull(dbg_env, nullptr, 0)) : nullptr;
   const long long windows = (long long)d.N * (d.H / WS) * (d.W / WS);
   const long long items = (windows + 1) / 2;
   int dev = 0, sms = 0;
@@ -529,11 +583,11 @@ int winattn_umma_launch(const svx_winattn_desc& d_in, void* stream) {
   SVX_CUDA_OK(cudaFuncSetAttribute(winattn_umma_kernel<bf16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WuCfg<bf16_t>::kSmem));
   SVX_CUDA_OK(cudaFuncSetAttribute(winattn_umma_kernel<bf16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WuCfg<bf16_t>::kSmem));
   if (bf) {
-    if (d.shift > 0) winattn_umma_kernel<bf16_t, true><<<grid, WU_THREADS, WuCfg<bf16_t>::kSmem, st>>>(d, (int)per_head);
-    else winattn_umma_kernel<bf16_t, false><<<grid, WU_THREADS, WuCfg<bf16_t>::kSmem, st>>>(d, (int)per_head);
+    if (d.shift > 0) winattn_umma_kernel<bf16_t, true><<<grid, WU_THREADS, WuCfg<bf16_t>::kSmem, st>>>(d, (int)per_head, dbg);
+    else winattn_umma_kernel<bf16_t, false><<<grid, WU_THREADS, WuCfg<bf16_t>::kSmem, st>>>(d, (int)per_head, dbg);
   } else {
-    if (d.shift > 0) winattn_umma_kernel<float, true><<<grid, WU_THREADS, WuCfg<float>::kSmem, st>>>(d, (int)per_head);
-    else winattn_umma_kernel<float, false><<<grid, WU_THREADS, WuCfg<float>::kSmem, st>>>(d, (int)per_head);
+    if (d.shift > 0) winattn_umma_kernel<float, true><<<grid, WU_THREADS, WuCfg<float>::kSmem, st>>>(d, (int)per_head, dbg);
+    else winattn_umma_kernel<float, false><<<grid, WU_THREADS, WuCfg<float>::kSmem, st>>>(d, (int)per_head, dbg);
   }
   SVX_LAUNCH_OK("winattn_umma_kernel");
   return 0;
