@@ -713,11 +713,20 @@ __global__ void mergefuse_kernel(const svx_mergefuse_desc d, long long total4) {
 }
 
 // ---- Conv3d(Cin <= 12 -> 1, k3, p1) + LeakyReLU in fp32 on the CUDA cores (merger layer6) -------------------------------
-// One CTA marches along depth over a 16-row x 32-column tile of the (h, w) plane: three input planes (18 x 34 voxels x 12
-// channels) ring in shared memory, each plane is loaded from HBM once per tile; a thread owns four consecutive ROWS of
+// One CTA marches along depth over a C31_ROWS-row x 32-column tile of the (h, w) plane: three input planes ((ROWS + 2) x 34
+// voxels x 12 channels) ring in shared memory, each plane is loaded from HBM once per tile (measured on B200,
+// profiles/r2_conv3to1_variants.txt: 8-row tiles with four rows per thread, i.e. three 64-thread CTAs per SM, 0.243 ms per
+// merger layer6 at 64 x 3 views against 0.280 ms for 16-row tiles; two or one row per thread lose to shared-memory
+// bandwidth: 0.31 - 0.48 ms); a thread owns C31_RPT consecutive ROWS of
 // one column, so every staged voxel it reads (3 float4) feeds up to three kh taps of up to four outputs from registers,
 // and the 32 lanes of a warp read 32 adjacent voxels (48 bytes apart: bank-conflict free).
-constexpr int C31_TH = 16, C31_TW = 32, C31_THREADS = (C31_TH / 4) * C31_TW;
+#ifndef C31_RPT
+#define C31_RPT 4               // output rows per thread (threads per CTA = C31_ROWS / C31_RPT * 32)
+#endif
+#ifndef C31_ROWS
+#define C31_ROWS 8              // rows of the (h, w) tile of one CTA (16: 118 KB of planes, one CTA per SM; 8: 65 KB, three)
+#endif
+constexpr int C31_TH = C31_ROWS, C31_TW = 32, C31_THREADS = (C31_TH / C31_RPT) * C31_TW;
 constexpr int C31_PLANE = (C31_TH + 2) * (C31_TW + 2);          // staged voxels per plane
 __global__ void __launch_bounds__(C31_THREADS) conv3to1_kernel(const svx_conv3to1_desc d) {
   extern __shared__ float4 c31_smem[];                          // [4 planes][C31_PLANE][3 float4] + weights [27][3]
@@ -725,7 +734,7 @@ __global__ void __launch_bounds__(C31_THREADS) conv3to1_kernel(const svx_conv3to
   const int tiles_h = d.H / C31_TH;
   const int n = blockIdx.x / tiles_h, h0 = (blockIdx.x % tiles_h) * C31_TH;
   const int Hp = d.H + 2, Wp = d.W + 2;
-  const int ty = (threadIdx.x / C31_TW) * 4, tx = threadIdx.x % C31_TW;   // rows ty..ty+3 of column tx
+  const int ty = (threadIdx.x / C31_TW) * C31_RPT, tx = threadIdx.x % C31_TW;   // rows ty..ty+RPT-1 of column tx
   for (int i = threadIdx.x; i < 27 * 3; i += C31_THREADS) wsm[i] = __ldg(reinterpret_cast<const float4*>(d.w) + i);
   const float bias = d.bias ? __ldg(d.bias) : 0.f;
   auto load_plane = [&](int dp) {   // padded depth index dp -> ring slot dp % 4, asynchronously (one cp.async group)
@@ -746,7 +755,9 @@ __global__ void __launch_bounds__(C31_THREADS) conv3to1_kernel(const svx_conv3to
     load_plane(dd + 3);                                         // lands while depths dd .. dd+? compute
     asm volatile("cp.async.wait_group 1;" ::: "memory");        // planes dd, dd+1, dd+2 have landed
     __syncthreads();
-    float acc[4] = {bias, bias, bias, bias};
+    float acc[C31_RPT];
+#pragma unroll
+    for (int r = 0; r < C31_RPT; ++r) acc[r] = bias;
 #pragma unroll
     for (int kd = 0; kd < 3; ++kd) {
       const float4* pl = c31_smem + ((dd + kd) % 4) * C31_PLANE * 3;
@@ -754,13 +765,13 @@ __global__ void __launch_bounds__(C31_THREADS) conv3to1_kernel(const svx_conv3to
       for (int kw = 0; kw < 3; ++kw) {
         const float4* col = pl + (ty * (C31_TW + 2) + tx + kw) * 3;
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {                            // six staged rows feed four outputs x three kh taps
+        for (int j = 0; j < C31_RPT + 2; ++j) {                  // RPT + 2 staged rows feed RPT outputs x three kh taps
           const float4* vx = col + j * (C31_TW + 2) * 3;
           const float4 a = vx[0], b = vx[1], c = vx[2];
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
             const int o = j - kh;
-            if (o < 0 || o > 3) continue;
+            if (o < 0 || o >= C31_RPT) continue;
             const float4* wk = wsm + ((kd * 3 + kh) * 3 + kw) * 3;
             const float4 wa = wk[0], wb = wk[1], wc = wk[2];
             float s = acc[o];
@@ -774,7 +785,7 @@ __global__ void __launch_bounds__(C31_THREADS) conv3to1_kernel(const svx_conv3to
     }
     float* orow = d.out + (((long long)n * d.D + dd) * d.H + h0 + ty) * d.W + tx;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) orow[r * d.W] = acc[r] > 0.f ? acc[r] : acc[r] * d.slope;
+    for (int r = 0; r < C31_RPT; ++r) orow[r * d.W] = acc[r] > 0.f ? acc[r] : acc[r] * d.slope;
     __syncthreads();   // the slot of plane dd is overwritten by the load issued two iterations from now
   }
 }

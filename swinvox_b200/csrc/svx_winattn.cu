@@ -123,11 +123,22 @@ __device__ __noinline__ void wu_report(unsigned long long* dbg, uint32_t bar_bas
   }
   __trap();
 }
+#ifndef SVX_WU_BACKOFF_NS
+#define SVX_WU_BACKOFF_NS 0
+#endif
+#ifndef SVX_WU_BACKOFF_TAGS
+#define SVX_WU_BACKOFF_TAGS 0x3eu   // every wait site (tags 1 .. 5)
+#endif
 __device__ __forceinline__ void wu_wait(uint32_t bar, uint32_t parity, unsigned long long* dbg, uint32_t bar_base, int nbars,
                                         uint32_t tag, int i) {
   long long t0 = 0;
   for (uint32_t it = 0;; ++it) {
     if (mbar_test(bar, parity)) break;
+#if SVX_WU_BACKOFF_NS > 0
+    // back-off of the roles selected by SVX_WU_BACKOFF_TAGS (bit = wait-site tag): a polling warp is always eligible and
+    // takes issue slots from the softmax warps of its scheduler (profiles/r2_ncu_winattn_v40.txt: 50 % of the samples poll)
+    if ((SVX_WU_BACKOFF_TAGS >> tag) & 1u) __nanosleep(SVX_WU_BACKOFF_NS);
+#endif
     if ((it & 4095u) == 4095u) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;

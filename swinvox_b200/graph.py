@@ -445,7 +445,9 @@ def lower_merger(plan, mer, raw, coarse, B, V, operands="fp16", range_flag=None)
     # layer5 sees cat(w1..w4): reference channel 9*g + c lives at 16*g + c here.  Two slab passes over the two
     # 32-channel halves; the second adds the first's partial sums before bias / LeakyReLU.
     w5, b5 = E.fold_bn(mer.layer5[0].weight, mer.layer5[0].bias, mer.layer5[1])
-    t = plan.new_act(N, 32, 32, 32, 16, Cs=32, pad=(1, 1, 1))
+    # (64-byte rows: layer6 streams this buffer on the CUDA cores and a 128-byte row would double its DRAM traffic --
+    # ncu: 989 MB per launch for 483 MB of 16-channel rows, profiles/r2_launches_v40_summary.txt)
+    t = plan.new_act(N, 32, 32, 32, 16, pad=(1, 1, 1))
     for half in (0, 1):
         wh = torch.zeros(9, 32, 3, 3, 3, device=w5.device)
         for gi in (0, 1):
@@ -456,7 +458,7 @@ def lower_merger(plan, mer, raw, coarse, B, V, operands="fp16", range_flag=None)
                         name=f"merger.layer5.{'ab'[half]}", operands=operands, range_flag=range_flag)
     # layer6 (9 -> 1 channel): 243 MACs per voxel, fp32 on the CUDA cores (a tensor-core tile is issue-bound here)
     wts = plan.empty(N, 32768)
-    plan.conv3_to1(box(t, 0), mer.layer6[0].weight, mer.layer6[0].bias, mer.layer6[1], wts, slope, name="merger.layer6")
+    plan.conv3_to1(t, mer.layer6[0].weight, mer.layer6[0].bias, mer.layer6[1], wts, slope, name="merger.layer6")
     merged = plan.empty(B, 32768)
     plan.merger_fuse(wts, coarse, merged, B, V, 32768, name="merger.softmax_fuse")
     return merged, wts
