@@ -302,6 +302,16 @@ class Plan:
         if not self.handle:
             raise _lib.SvxError("svx_plan_create failed")
         self.keep = {}
+        # activation-buffer reuse: `release(act)` after the last op that reads `act` has been recorded returns its memory to
+        # the pool of the CURRENT lane; later `new_act` calls in the same lane draw from it (ops of one lane run in recording
+        # order, so the new writer is ordered after the old readers; lanes overlap, so they never share a pool; a join
+        # merges the side pools into lane 0's).
+        self._lane = 0
+        self._pools = {}          # lane -> list of free raw uint8 tensors
+        self._pad_pools = {}      # lane -> {geometry key: [zero-bordered buffers whose producers wrote interiors only]}
+        self._raw_of = {}         # id(view tensor) -> (raw uint8 tensor | None, geometry key | None)
+        self.bytes_allocated = 0  # fresh device memory obtained for activations (diagnostics / tests)
+        self.bytes_reused = 0
         self.op_names = []
         self.flops = []
         self.bytes = []   # algorithmic HBM bytes per op: every operand read once, every result written once
@@ -325,9 +335,55 @@ class Plan:
     def new_act(self, N, D, H, W, C, Cs=None, zero=False, pad=(0, 0, 0), dtype=None):
         """D, H, W are the data extents; `pad` adds a zero border that producers never write (flat-conv inputs)"""
         Cs = Cs or C
+        dtype = dtype or self.dtype
         Dp, Hp, Wp = D + 2 * pad[0], H + 2 * pad[1], W + 2 * pad[2]
-        buf = (self.zeros if (zero or any(pad)) else self.empty)(N * Dp * Hp * Wp, Cs, dtype=dtype or self.dtype)
+        rows = N * Dp * Hp * Wp
+        if zero:                       # relies on zeros nobody rewrites (channel / column padding): never pooled
+            buf = self.zeros(rows, Cs, dtype=dtype)
+        elif any(pad):                 # zero border, interior-only producers: reusable by an identical geometry only
+            key = (N, Dp, Hp, Wp, Cs, dtype, tuple(pad))
+            free = self._pad_pools.get(self._lane, {}).get(key)
+            if free:
+                buf = free.pop()
+                self.bytes_reused += buf.numel() * buf.element_size()
+            else:
+                buf = self.zeros(rows, Cs, dtype=dtype)
+                self.bytes_allocated += buf.numel() * buf.element_size()
+                self._raw_of[id(buf)] = (None, key)
+        else:
+            buf = self._pooled_empty(rows, Cs, dtype)
         return Act(buf, N, Dp, Hp, Wp, C, 0, tuple(pad))
+
+    def _pooled_empty(self, rows, Cs, dtype):
+        need = rows * Cs * esize_of(dtype)
+        pool = self._pools.setdefault(self._lane, [])
+        best = None
+        for i, raw in enumerate(pool):   # best fit: the smallest free block that is large enough
+            if raw.numel() >= need and (best is None or raw.numel() < pool[best].numel()):
+                best = i
+        if best is not None:
+            raw = pool.pop(best)
+            self.bytes_reused += need
+        else:
+            raw = torch.empty(max(need, 16), dtype=torch.uint8, device=self.device)
+            self.bytes_allocated += raw.numel()
+        buf = raw[:need].view(dtype).view(rows, Cs)
+        self._raw_of[id(buf)] = (raw, None)
+        return self.hold(buf)
+
+    def release(self, act):
+        """The last op reading `act` (a whole buffer from new_act) has been recorded in the CURRENT lane, and every other
+        reader was recorded in this lane too (or before this lane forked): its memory may back later activations of this
+        lane.  Tensors not created by new_act (module inputs, zero-initialised staging buffers) are ignored."""
+        buf = act.buf if isinstance(act, Act) else act
+        ent = self._raw_of.pop(id(buf), None)
+        if ent is None:
+            return
+        raw, key = ent
+        if raw is not None:
+            self._pools.setdefault(self._lane, []).append(raw)
+        else:
+            self._pad_pools.setdefault(self._lane, {}).setdefault(key, []).append(buf)
 
     @staticmethod
     def _dt(x, out):
@@ -381,11 +437,17 @@ class Plan:
     def lane(self, k):
         """ops recorded from now on go to lane k (0 = the caller's stream, 1..8 = side streams / graph branches)"""
         _lib.check(self.lib.svx_plan_set_lane(self.handle, k), self.lib)
+        self._lane = k
 
     def join(self):
         """the caller's stream waits for every side lane; also resets the current lane to 0"""
         self.lane(0)
         _lib.check(self.lib.svx_plan_add_join(self.handle), self.lib)
+        for k in [k for k in self._pools if k != 0]:          # everything recorded so far precedes everything after the join
+            self._pools.setdefault(0, []).extend(self._pools.pop(k))
+        for k in [k for k in self._pad_pools if k != 0]:
+            for key, bufs in self._pad_pools.pop(k).items():
+                self._pad_pools.setdefault(0, {}).setdefault(key, []).extend(bufs)
         self.op_names.append("join")
         self.flops.append(0.0)
         self.bytes.append(0.0)

@@ -16,6 +16,7 @@ from . import engine as E
 from .engine import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, POOL_AVG, POOL_MAX, Act
 
 WINDOW = 7
+RAW_CS = 16   # row width (channels) of the decoder -> merger hand-off buffer `raw`: 9 live channels in 64-byte rows
 
 
 def _dev(plan):
@@ -73,9 +74,10 @@ def lower_resnet_trunk(plan, resnet, img, N):
     plan.conv(pairs, pk, taps, stem, stride=(1, 2, 1), act=ACT_RELU, name="resnet.stem")
     x = plan.new_act(N, 1, 56, 56, 64)
     plan.pool(stem, x, (1, 3, 3), (1, 2, 2), (0, 1, 1), POOL_MAX, round_out=True, name="resnet.maxpool")
+    plan.release(stem)
     for li in (4, 5, 6):
         for bi, blk in enumerate(resnet[li]):
-            x = _bottleneck(plan, blk, x, f"resnet.{li}.{bi}")
+            x = _bottleneck(plan, blk, x, f"resnet.{li}.{bi}")   # (releases its input: nobody else reads it)
     return x
 
 
@@ -109,6 +111,10 @@ def _bottleneck(plan, blk, x, name):
     pk3 = E.pack_conv(blk.conv3.weight, None, blk.bn3, dev)
     plan.linear(t2, pk3, out, act=ACT_RELU, residual=idn, res_after_act=False, round_out=True,
                 res_via_mma=(cout % 256 == 0), name=name + ".conv3")
+    # every reader of the block's temporaries and of its input has been recorded (all in this lane): their memory backs
+    # the next blocks (the whole trunk lives in ~4 buffers per resolution instead of ~50)
+    for a in (t1, t2, idn, x):
+        plan.release(a)
     return out
 
 
@@ -156,6 +162,8 @@ def lower_swin(plan, swin, img, N, stage_tail=None):
     x = plan.new_act(N, 1, 56, 56, 96)
     plan.layernorm_rows(emb, pe.norm.weight.detach().float().to(dev), pe.norm.bias.detach().float().to(dev), x,
                         eps=pe.norm.eps, round_out=False, name="swin.patch_embed.norm")
+    plan.release(emb)
+    x_private = True   # `x` is read by this lane only (a stage output is also read by its wrapper LayerNorm in a side lane)
     feats = {}
     outs = [None] * len(stages)
     for s in range(max(stages) + 1):
@@ -169,6 +177,8 @@ def lower_swin(plan, swin, img, N, stage_tail=None):
                                 merged, merge_hw=(2 * H, 2 * H), eps=ds.norm.eps, name=f"swin.{s}.merge.norm")
             x = plan.new_act(N, 1, H, H, Cc)
             plan.linear(merged, E.pack_matrix(ds.reduction.weight, None, dev), x, name=f"swin.{s}.merge.reduction")
+            plan.release(merged)
+            x_private = True
         for j, blk in enumerate(layer.blocks):
             nm = f"swin.{s}.{j}"
             shift = WINDOW // 2 if (j % 2 == 1 and H > WINDOW) else 0
@@ -177,15 +187,21 @@ def lower_swin(plan, swin, img, N, stage_tail=None):
                                 eps=blk.norm1.eps, name=nm + ".norm1")
             qkv = plan.new_act(N, 1, H, H, 3 * Cc)
             plan.linear(y, E.pack_matrix(blk.attn.qkv.weight, blk.attn.qkv.bias, dev), qkv, round_out=True, name=nm + ".qkv")
+            plan.release(y)
             att = plan.new_act(N, 1, H, H, Cc)
             bias = relative_position_bias(blk.attn.relative_position_bias_table, heads).to(dev)
             if "attn_range_flag" not in plan.taps:
                 plan.taps["attn_range_flag"] = plan.zeros(1, dtype=torch.int32)
             plan.window_attention(qkv, att, bias, H, H, heads, shift, 32 ** -0.5, name=nm + ".attn",
                                   range_flag=plan.taps["attn_range_flag"])
+            plan.release(qkv)
             x1 = plan.new_act(N, 1, H, H, Cc)
             plan.linear(att, E.pack_matrix(blk.attn.proj.weight, blk.attn.proj.bias, dev), x1, residual=x,
                         name=nm + ".proj")
+            plan.release(att)
+            if x_private:
+                plan.release(x)
+            x_private = True   # the block output below has no reader outside this lane unless it ends the stage
             g2, b2 = blk.norm2.weight.detach().float().to(dev), blk.norm2.bias.detach().float().to(dev)
             # (the fused MLP kernel exists for fp32 / TF32 storage; bf16 plans run fc1 / fc2 as two contractions)
             fused = E.mlp_fusable(Cc, blk.mlp.fc1.out_features) and plan.dtype == torch.float32
@@ -195,6 +211,7 @@ def lower_swin(plan, swin, img, N, stage_tail=None):
                 plan.mlp(x1, E.pack_matrix(blk.mlp.fc1.weight, blk.mlp.fc1.bias, dev),
                          E.pack_matrix(blk.mlp.fc2.weight, blk.mlp.fc2.bias, dev), x, residual=x1, name=nm + ".mlp",
                          ln=(g2, b2, blk.norm2.eps))
+                plan.release(x1)
                 continue
             y2 = plan.new_act(N, 1, H, H, Cc)
             plan.layernorm_rows(x1, g2, b2, y2, eps=blk.norm2.eps, name=nm + ".norm2")
@@ -202,12 +219,18 @@ def lower_swin(plan, swin, img, N, stage_tail=None):
                 # stage 1: fc1 -> GELU -> fc2 -> + x1 in one kernel, the 4C-wide hidden activation stays on the SM
                 plan.mlp(y2, E.pack_matrix(blk.mlp.fc1.weight, blk.mlp.fc1.bias, dev),
                          E.pack_matrix(blk.mlp.fc2.weight, blk.mlp.fc2.bias, dev), x, residual=x1, name=nm + ".mlp")
+                plan.release(y2)
+                plan.release(x1)
                 continue
             hid = plan.new_act(N, 1, H, H, 4 * Cc)
             plan.linear(y2, E.pack_matrix(blk.mlp.fc1.weight, blk.mlp.fc1.bias, dev), hid, act=ACT_GELU, round_out=True,
                         name=nm + ".fc1")
+            plan.release(y2)
             plan.linear(hid, E.pack_matrix(blk.mlp.fc2.weight, blk.mlp.fc2.bias, dev), x, residual=x1, name=nm + ".fc2")
+            plan.release(hid)
+            plan.release(x1)
         feats[s] = x
+        x_private = False   # read by the wrapper LayerNorm (a side lane when stage tails overlap) and by the next stage
         for i, si in enumerate(stages):   # wrapper LayerNorm (+ the caller's per-stage tail) as soon as the stage is done
             if si != s:
                 continue
@@ -283,8 +306,10 @@ def lower_encoder(plan, enc, img, B, V):
     r = lower_resnet_trunk(plan, enc.resnet, img, N)
     rp = plan.new_act(N, 1, 7, 7, 1024)
     plan.pool(r, rp, (1, 2, 2), (1, 2, 2), (0, 0, 0), POOL_AVG, round_out=True, name="encoder.avg_pool")
+    plan.release(r)
     plan.linear(rp, E.pack_conv(enc.resnet_reduce.weight, enc.resnet_reduce.bias, None, dev), cat.channels(0, 256),
                 round_out=True, name="encoder.resnet_reduce")
+    plan.release(rp)
     if two_lanes:
         plan.lane(0)
     # Swin branch.  Per-stage tails (wrapper LayerNorm, 1x1 reduce, all but the last strided convolution of the
@@ -385,7 +410,7 @@ def _convT_layer(plan, x, conv, bn, pads, out, name, act=ACT_RELU, residual=None
 
 
 def lower_decoder(plan, dec, feat, N):
-    """feat: Act [N,7,7,256].  Returns (raw Act: 32^3 voxels inside a zero border, 32-channel rows with 9 live
+    """feat: Act [N,7,7,256].  Returns (raw Act: 32^3 voxels inside a zero border, RAW_CS-channel rows with 9 live
     channels -- the layout the merger's slab convolution streams by TMA -- and coarse [N, 32768])."""
     dev = _dev(plan)
     g = plan.new_act(N, 2, 2, 2, 256)
@@ -405,7 +430,7 @@ def lower_decoder(plan, dec, feat, N):
         else:   # layer1: kernel (6, 4, 4) -- three depth taps per class
             _convT_layer(plan, x, layer[0], layer[1], pads, o, f"decoder.layer{li + 1}")
         x = o
-    raw = plan.new_act(N, 32, 32, 32, 16, Cs=32, pad=(1, 1, 1))
+    raw = plan.new_act(N, 32, 32, 32, 16, Cs=RAW_CS, pad=(1, 1, 1))
     coarse = plan.empty(N, 32768)
     l5 = dec.layer5[0]
     w5 = torch.zeros(9)
@@ -422,7 +447,7 @@ def lower_decoder(plan, dec, feat, N):
 # Merger (models/merger.py:56-107)
 # --------------------------------------------------------------------------------------------------
 def lower_merger(plan, mer, raw, coarse, B, V, operands="fp16", range_flag=None):
-    """raw: Act of 32^3 voxels inside a (1,1,1) zero border, 32-channel rows (9 live, TF32-rounded, rest zero);
+    """raw: Act of 32^3 voxels inside a (1,1,1) zero border, RAW_CS-channel rows (9 live, TF32-rounded, rest zero);
     coarse: [N,32768] tensor.  Returns (merged [B, 32768], pre-softmax scores [N, 32768]).
     All six Conv3d(k3,p1) layers run on the depth-marching TMA slab kernel over zero-bordered 34^3 volumes.
     operands: MMA operand type of the slab kernel ("fp16": exact for this path's TF32-rounded activations up to 65504,

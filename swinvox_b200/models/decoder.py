@@ -41,6 +41,6 @@ class Decoder(PlannedModule):
         plan, inp, raw, coarse = self._plan_for((B, V, str(image_features.device), src_key(image_features)), build)
         inp.feed(image_features)
         plan.run(self.use_graph)
-        raw_features = mark_owned(raw.buf.view(B, V, 34, 34, 34, 32)[:, :, 1:33, 1:33, 1:33, :9].permute(0, 1, 5, 2, 3, 4), raw.buf)
+        raw_features = mark_owned(raw.buf.view(B, V, 34, 34, 34, graph.RAW_CS)[:, :, 1:33, 1:33, 1:33, :9].permute(0, 1, 5, 2, 3, 4), raw.buf)
         gen_volumes = mark_owned(coarse.view(B, V, 32, 32, 32), coarse)
         return raw_features, gen_volumes

@@ -37,9 +37,9 @@ class Merger(PlannedModule):
         def build():
             plan = E.Plan(raw_features.device)
             src = owned_src(raw_features)
-            bound = isinstance(src, torch.Tensor) and tuple(src.shape) == (N * 34 ** 3, 32)
-            # the decoder's own output buffer (zero-bordered 34^3 x 32-channel rows), or a private one
-            raw = E.Act(plan.hold(src) if bound else plan.zeros(N * 34 ** 3, 32), N, 34, 34, 34, 16, 0, (1, 1, 1))
+            bound = isinstance(src, torch.Tensor) and tuple(src.shape) == (N * 34 ** 3, graph.RAW_CS)
+            # the decoder's own output buffer (zero-bordered 34^3 x RAW_CS-channel rows), or a private one
+            raw = E.Act(plan.hold(src) if bound else plan.zeros(N * 34 ** 3, graph.RAW_CS), N, 34, 34, 34, 16, 0, (1, 1, 1))
             coarse = PlanarInput(plan, coarse_volumes, (N, 32768))
             flag = plan.zeros(1, dtype=torch.int32)
             merged, weights = graph.lower_merger(plan, self, raw, coarse.buf, B, V, operands=self.slab_operands,
