@@ -67,6 +67,20 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def workload_tag(B, V, world, bf16):
+    """which BASELINE.json configuration a (batch per GPU, views, ranks, dtype) combination is"""
+    if bf16:
+        tag = "BASELINE configs[2]" if (B, V) == (64, 5) else "bf16 variant"
+        return f"({tag}; encoder in bf16, decoder / merger / refiner in TF32)"
+    if (B, V) == (64, 3):
+        return "(BASELINE configs[1])"
+    if V == 20 and B * world == 256:
+        return "(BASELINE configs[3]: batch 256 x 20 views over the ranks)"
+    if B * world == 128:
+        return "(BASELINE configs[4]: a point of the 1-24 view sweep at batch 128)"
+    return "(a shape outside BASELINE.json's list)"
+
+
 def synthetic_batch(B, V, seed):
     g = torch.Generator().manual_seed(seed)
     images = torch.rand(B, V, 3, 224, 224, generator=g) * 2 - 1
@@ -357,8 +371,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if bf16 else "tf32", "data": "synthetic",
             "config": {"workload": f"batch {B} x {V} views per GPU, merger + refiner, CVA on, 224x224 -> 32^3 "
-                                   + ("(BASELINE configs[2]; encoder in bf16, decoder / merger / refiner in TF32)" if bf16
-                                      else "(BASELINE configs[1])"),
+                                   + workload_tag(B, V, world, bf16),
                        "l2": "per-step working set (activations) is several GB, far larger than the 126 MB L2",
                        "cuda_graph": not args.no_graph, "weights": "random init (reference architecture)"},
             "e2e": {"value": e2e_value, "unit": "objects/s", "h2d_bytes_per_step": h2d_bytes,
