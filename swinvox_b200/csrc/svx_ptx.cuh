@@ -74,8 +74,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 // The same bounded wait WITHOUT a suspend-time hint.  With a hint ptxas emits TRYWAIT; NANOSLEEP.SYNCS <hint>; PHASECHK, and
 // a warp parked there resumes late: fine for deep pipelines that rarely block, but a latency chain of short hand-offs
-// (window attention: scores -> softmax -> P -> P.V -> output, per item) paid ~0.5 us per hand-off
-// (profiles/r2_ncu_winattn_wa5.txt).  Use this variant on such chains.
+// (window attention: scores -> softmax -> P -> P.V -> output, per item) paid ~0.5 us per hand-off (measured in round 2
+// with the hinted wait in that kernel; the capture itself was not kept).  Use this variant on such chains.
 __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, uint32_t hint_ns = 0) {
   uint32_t done = 0;
   long long t0 = 0;
