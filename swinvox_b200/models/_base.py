@@ -30,7 +30,7 @@ class PlannedModule(nn.Module):
 
     use_graph = False
     # plans kept per module (least recently used are dropped): each holds the activations of one input signature
-    # (about 6 GB for the encoder at 64 x 3 views), so a long-lived process that varies B or V must not keep them all
+    # (about 6.5 GB for the encoder at 64 x 3 views: 34 MB per image), so a long-lived process that varies B or V must not keep them all
     max_plans = 4
 
     def __init__(self):
