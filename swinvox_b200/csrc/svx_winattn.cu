@@ -43,10 +43,19 @@ namespace svx {
 namespace {
 
 constexpr int WS = 7, WT = 49, HD = 32;
-constexpr int WU_THREADS = 17 * 32;
+// gather warps: 2 (one per window of the tile), 4 or 6 (two / three per window, alternating row groups).  Measured
+// (profiles/r2_winattn_gather_warps.txt): two warps could not issue the 16-byte cp.async chunks of an item (plus their
+// address arithmetic) faster than ~2.5 us per item -- 316 us per stage-0 launch where the rest of the pipeline needs 164;
+// with four 217 us (4.3 TB/s).
+#ifndef SVX_WU_LOAD_WARPS
+#define SVX_WU_LOAD_WARPS 4
+#endif
 constexpr int WU_CONV_WARPS = 2;
-constexpr int WU_W_OUT = 8, WU_W_LOAD = 12, WU_W_MMA = 14, WU_W_CONV = 15;
-constexpr int WU_PRODUCER_WARPS = 2;
+constexpr int WU_PRODUCER_WARPS = SVX_WU_LOAD_WARPS;
+static_assert(WU_PRODUCER_WARPS == 2 || WU_PRODUCER_WARPS == 4 || WU_PRODUCER_WARPS == 6, "gather warps");
+constexpr int WU_W_OUT = 8, WU_W_LOAD = 12, WU_W_MMA = WU_W_LOAD + WU_PRODUCER_WARPS, WU_W_CONV = WU_W_MMA + 1;
+constexpr int WU_WARPS = WU_W_CONV + WU_CONV_WARPS;      // 17 | 19 | 21
+constexpr int WU_THREADS = WU_WARPS * 32;
 constexpr float kLog2e = 1.4426950408889634f;
 
 template <typename T>
@@ -103,13 +112,13 @@ __host__ __device__ constexpr uint64_t wu_keys_ge4(bool by_row) {
 constexpr uint64_t kKeysAll = (1ull << WT) - 1;
 
 
-// Stall diagnostics (SVX_WINATTN_DEBUG=<address of a pinned, zeroed host buffer of >= 148*17*32 u64>): a barrier wait that
+// Stall diagnostics (SVX_WINATTN_DEBUG=<address of a pinned, zeroed host buffer of >= 148*21*32 u64>): a barrier wait that
 // makes no progress for ~2 s writes who waited for what, and the state of every barrier of the CTA, into host memory
 // (readable after the trap has killed the context).
 __device__ __noinline__ void wu_report(unsigned long long* dbg, uint32_t bar_base, int nbars, uint32_t tag, uint32_t bar,
                                        uint32_t parity, int i, int extra) {
   if (dbg) {
-    unsigned long long* rec = dbg + ((size_t)blockIdx.x * 17 + (threadIdx.x >> 5)) * 32;
+    unsigned long long* rec = dbg + ((size_t)blockIdx.x * 21 + (threadIdx.x >> 5)) * 32;   // (21 = the largest warp count)
     rec[0] = 0xD1A6000000000000ull | ((unsigned long long)tag << 32) | ((unsigned long long)((bar - bar_base) / 8) << 16) |
              ((unsigned long long)parity << 8) | (threadIdx.x & 31);
     rec[1] = ((unsigned long long)(uint32_t)i << 32) | (uint32_t)extra;
@@ -123,6 +132,13 @@ __device__ __noinline__ void wu_report(unsigned long long* dbg, uint32_t bar_bas
   }
   __trap();
 }
+// fp32 storage: release an operand stage as soon as S(i) has completed and the V rows have been converted (the P.V product
+// reads the fp16 copy), instead of after P.V(i): the stage ring then holds items that are LOADING, not items that wait for
+// their softmax (profiles/r2_winattn_probes.txt: the row gather bounds the kernel because little more than one stage was
+// in flight).  The fp16 V copies get their own empty barriers.
+#ifndef SVX_WU_EARLY_RELEASE
+#define SVX_WU_EARLY_RELEASE 1
+#endif
 #ifndef SVX_WU_BACKOFF_NS
 #define SVX_WU_BACKOFF_NS 0
 #endif
@@ -183,6 +199,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
   auto o_full = [&](int b) { return bar_base + 8u * (2 * NS + 8 + b); };
   auto o_empty = [&](int b) { return bar_base + 8u * (2 * NS + 10 + b); };
   auto v16_full = [&](int s) { return bar_base + 8u * (2 * NS + 12 + s); };   // the fp16 copy of stage s's V rows is ready
+  auto v16_empty = [&](int s) { return bar_base + 8u * (3 * NS + 13 + s); };  // P.V has read the fp16 V copy of stage s
+  constexpr bool kEarly = SVX_WU_EARLY_RELEASE != 0 && !BF;
   const uint32_t tmem_slot = bar_base + 8u * (3 * NS + 12);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (3 * NS + 12));
 
@@ -203,8 +221,9 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
     if (lane == 0) {
       for (int s = 0; s < NS; ++s) {
         mbar_init(full_bar(s), WU_PRODUCER_WARPS * 32);
-        mbar_init(empty_bar(s), 1u);
+        mbar_init(empty_bar(s), kEarly ? 1u + (uint32_t)WU_CONV_WARPS : 1u);   // early: S(i) committed + both converter warps
         mbar_init(v16_full(s), (uint32_t)WU_CONV_WARPS);
+        mbar_init(v16_empty(s), 1u);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(s_full(b), 1u); mbar_init(s_empty(b), 4u);
@@ -240,7 +259,9 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
 
   if (warp >= WU_W_LOAD && warp < WU_W_MMA) {
     // ---- row gather: each producer warp owns one half of the tile = one window ------------------------------------
-    const int w = warp - WU_W_LOAD;
+    const int w = (warp - WU_W_LOAD) & 1;                          // window of the tile
+    constexpr int kSplit = WU_PRODUCER_WARPS / 2;                  // warps per window
+    const int part = (warp - WU_W_LOAD) >> 1;                      // this warp takes row groups part, part + kSplit, ...
     constexpr int CH = K::kRowB / 16;            // 16-byte chunks per row: 8 | 4
     constexpr int RPI = 32 / CH;                 // rows one warp-wide cp.async instruction covers: 4 | 8
     const int ch = lane % CH, rsub = lane / CH;
@@ -254,7 +275,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
         const uint32_t dst0 = stage_smem + s * K::kStageB + (64 * w) * K::kRowB;
         const WinPos wp = window_pos(win);
 #pragma unroll 1
-        for (int r0 = 0; r0 < WT; r0 += RPI) {
+        for (int r0 = part * RPI; r0 < WT; r0 += kSplit * RPI) {
           const int q = r0 + rsub;
           if (q < WT) {
             const uint8_t* src = qkvb + (size_t)token_of(wp, q / WS, q % WS) * tok_pitch;
@@ -302,6 +323,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
           else umma_tf32(tmem_base + b * 128, da + 2u * k, db + 2u * k, idesc_s, k != 0 ? 1u : 0u);
         }
         umma_commit(s_full(b));
+        if constexpr (kEarly) umma_commit(empty_bar(s));   // Q and K of this item are dead once the scores exist
       };
       auto issue_pv = [&](int i) {
         const int s = i % NS, b = i & 1, pb = K::kPBufs == 2 ? b : 0;
@@ -317,7 +339,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
           if (WU_PROBE(8)) continue;                                    // (probe bit 8: no P.V MMAs)
           umma_f16(tmem_base + 256 + b * 32, da, db, idesc_o, k != 0 ? 1u : 0u);
         }
-        umma_commit(empty_bar(s));     // Q, K, V of this item are no longer needed
+        if constexpr (kEarly) umma_commit(v16_empty(s));   // the fp16 V copy of this stage may be rewritten
+        else umma_commit(empty_bar(s));                    // Q, K, V of this item are no longer needed
         umma_commit(p_empty(pb));
         umma_commit(o_full(b));
       };
@@ -367,6 +390,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
       for (int i = 0; i < nt; ++i) {
         const int s = i % NS;
         WU_WAIT(full_bar(s), ((uint32_t)(i / NS)) & 1u, 2u);
+        // early release: the fp16 copy of this stage is free once P.V(i - NS) has completed (long before, normally)
+        if constexpr (kEarly) WU_WAIT(v16_empty(s), (((uint32_t)(i / NS)) & 1u) ^ 1u, 2u);
         const uint8_t* src = smem_gen + s * K::kStageB + 2 * K::kMatB;
         uint8_t* dst = v16_gen + s * K::kV16B;
         float4 a[UPT], b[UPT];
@@ -394,7 +419,10 @@ __global__ void __launch_bounds__(WU_THREADS, 1) winattn_umma_kernel(const svx_w
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(v16_full(s));
+        if (lane == 0) {
+          mbar_arrive(v16_full(s));
+          if constexpr (kEarly) mbar_arrive(empty_bar(s));   // this warp has read its share of the fp32 V rows
+        }
       }
       if (d.range_flag && amax > 0x477fe000u) atomicOr(d.range_flag, 1);   // a V value beyond fp16's 65504 saturated
     }
