@@ -24,14 +24,18 @@
 // operands take the rows as they are; it also halves the P V instructions.  Accumulation, softmax statistics and the bias
 // are fp32 either way.
 //
-// Warp roles (17 warps):  0-3 / 4-7  two softmax groups (TMEM lane quarter = warp % 4), alternating items: scores -> P
-//                         8-11       output group, every item: O / rowsum -> global (through the item's dead Q tile)
-//                         12-13      row gather: cp.async 16-byte chunks of the token rows into 128B / 64B-swizzled
-//                                    operand tiles (a ring of stages)
-//                         14         MMA issuer (one elected thread), owns the TMEM allocation
-//                         15-16      fp32 storage only: V rows fp32 -> fp16
-// The per-item latency chain (scores -> softmax -> P -> P.V -> output; measured ~5000 cycles through one group,
-// profiles/r2_winattn_probes.txt) is what bounds this kernel, not any one unit: three groups work on three items at once.
+// Warp roles (19 warps):  0-3 / 4-7  two softmax groups (TMEM lane quarter = warp % 4), alternating items: scores -> P
+//                         8-11       output group, every item: O / rowsum -> global (rows transposed through a private
+//                                    scratch so that a store instruction covers whole token rows)
+//                         12-15      row gather, two warps per window: cp.async 16-byte chunks of the token rows into
+//                                    128B / 64B-swizzled operand tiles (a ring of stages)
+//                         16         MMA issuer (one elected thread), owns the TMEM allocation
+//                         17-18      fp32 storage only: V rows fp32 -> fp16
+// What bounds it (stage-knockout probes, profiles/r2_winattn_probes.txt and r2_winattn_gather_warps.txt): with two gather
+// warps the row gather -- ~110 cp.async instructions per thread and item plus their address arithmetic -- took as long as
+// the rest of the pipeline together (316 us per stage-0 launch against 164 us without loads); four gather warps and the
+// early stage release give 217 us (4.3 TB/s).  The remaining gap is the per-item chain scores -> softmax -> P -> P.V ->
+// output (~5000 cycles through one group; three groups work on three items at once).
 #include <cuda_runtime.h>
 
 #include <cstdlib>
