@@ -302,7 +302,9 @@ def run_ours(args):
         for entry in mod._plans.values():
             plan = entry[0]
             plan_bf16 = plan.dtype == torch.bfloat16
-            times = plan.time_ops(iters=3)
+            # per-op CUDA-event times: mean of 3 launches, measured twice, the smaller mean kept (one run in v44 had a single
+            # op of the list at 3x its usual time; the step time itself is not derived from these)
+            times = [min(a, b) for a, b in zip(plan.time_ops(iters=3), plan.time_ops(iters=3))]
             for nm, t, fl, nb in zip(plan.op_names, times, plan.flops, plan.bytes):
                 total_ms += t
                 if fl > 0 and nm.startswith("merger.layer"):
