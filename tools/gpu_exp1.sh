@@ -1,5 +1,7 @@
 #!/bin/bash
 # experiment run: wait back-off variants of the attention kernel, merger layer5 64-byte rows, refiner FC tiles
+# (variant libraries first, in the build container:  tools/build_variant.sh bo40all svx_winattn -DSVX_WU_BACKOFF_NS=40 ; bo40slack / bo100slack:
+#  -DSVX_WU_BACKOFF_NS=40|100 -DSVX_WU_BACKOFF_TAGS=0x22u.  Result: profiles/README.md, "What the round-2 captures showed")
 O=gpurun_out; mkdir -p $O
 run() {  # label, lib
   SVX_LIB_PATH=$2 timeout 200 python bench.py --steps 5 --no-eager --cpu-seconds 0 2> $O/exp1_$1.err | python -c "

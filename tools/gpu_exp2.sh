@@ -1,6 +1,8 @@
 #!/bin/bash
 # experiment run 2: conv3to1 (merger layer6) thread-shape variants, contraction kernel vs cuBLAS / cuDNN on HEAD,
 # the other BASELINE configuration shapes on one GPU (configs[3] per-GPU shard, the 1..24 view sweep at batch 128)
+# (variant libraries first:  tools/build_variant.sh rpt2 svx_ops -DC31_RPT=2 ; rpt1 ; th8rpt4 = -DC31_RPT=4 -DC31_ROWS=8 ; th8rpt2 ; th8rpt1
+#  -- the default was C31_ROWS=16 at the time.  Results: profiles/r2_conv3to1_variants.txt, r2_gemm_bench_v41.log, r2_config_sweep_v42.txt)
 O=gpurun_out; mkdir -p $O
 {
 for v in "" _rpt2 _rpt1 _th8rpt4 _th8rpt2 _th8rpt1; do

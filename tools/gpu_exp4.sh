@@ -1,5 +1,6 @@
 #!/bin/bash
 # early stage release of the attention kernel (-DSVX_WU_EARLY_RELEASE=1 variant): timing, kernel tests, stress, pipeline parity
+# (variant library first:  tools/build_variant.sh early svx_winattn -DSVX_WU_EARLY_RELEASE=1 -DSVX_WU_LOAD_WARPS=2.  Result: no change)
 O=gpurun_out; mkdir -p $O
 E=swinvox_b200/libswinvox_b200_early.so
 {

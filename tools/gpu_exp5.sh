@@ -1,6 +1,8 @@
 #!/bin/bash
 # four gather warps (and + early stage release) in the attention kernel: timing, then the GPU tier, stress and bench with the
 # faster variant library
+# (variant libraries first:  tools/build_variant.sh g4 svx_winattn -DSVX_WU_LOAD_WARPS=4 -DSVX_WU_EARLY_RELEASE=0 ; g4e = -DSVX_WU_LOAD_WARPS=4
+#  -DSVX_WU_EARLY_RELEASE=1 ; base was 2 warps / no early release then.  Result: profiles/r2_winattn_gather_warps.txt; g4e is the default now)
 O=gpurun_out; mkdir -p $O
 L=swinvox_b200/libswinvox_b200
 {
